@@ -1,0 +1,175 @@
+/*
+ * libpe_b200 -- C ABI of the B200-native PhysicEdit / Qwen-Image-Edit DiT hot path.
+ *
+ * The reference (liangbingzhao/PhysicEdit @ 5f239b9) is pure Python/PyTorch: its "FFI" for this path
+ * is the set of ATen/cuBLAS/SDPA library calls made from
+ *     DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py:1302-1403  (model_fn_qwen_image)
+ *     DiffSynth-Studio/diffsynth/models/qwen_image_dit.py:14-57,228-401      (attention, MLP, block)
+ *     DiffSynth-Studio/diffsynth/models/utils.py:189-309                     (timestep emb, RMSNorm, AdaLN)
+ *     DiffSynth-Studio/diffsynth/pipelines/helpers.py:123-164                (VisualThinkingDualAdapter)
+ *     DiffSynth-Studio/diffsynth/schedulers/flow_match.py:72-82              (Euler step)
+ * Every entry point below names the reference call site(s) it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  All tensor pointers are DEVICE pointers owned by the
+ *     caller; `stream` is a cudaStream_t passed as void*.  The library never allocates tensors and
+ *     never synchronises the stream: calls enqueue work and return.
+ *   - every function returns 0 (PE_OK) or a negative pe_status; pe_last_error(h) gives the text.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device of compute
+ *     capability 10.x pe_create fails with PE_ERR_UNSUPPORTED_DEVICE.
+ *   - activations / weights are bf16 (row-major, innermost stride 1) unless a parameter says otherwise;
+ *     accumulation is fp32.  Rounding points follow SURVEY.md Appendix B.
+ *   - one handle per device per host thread; functions are re-entrant across handles.
+ */
+#ifndef PE_B200_H_
+#define PE_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_B200_ABI_VERSION 1
+
+typedef enum pe_status {
+    PE_OK = 0,
+    PE_ERR_INVALID_ARGUMENT = -1,
+    PE_ERR_CUDA = -2,
+    PE_ERR_UNSUPPORTED_DEVICE = -3,
+    PE_ERR_KERNEL_TIMEOUT = -4,   /* a bounded in-kernel wait expired (see pe_check_async_error) */
+    PE_ERR_OUT_OF_MEMORY = -5,
+    PE_ERR_NOT_INITIALIZED = -6
+} pe_status;
+
+typedef struct pe_handle_s* pe_handle_t;
+
+/* ------------------------------------------------------------------------------------------- */
+/* life cycle                                                                                   */
+/* ------------------------------------------------------------------------------------------- */
+int pe_abi_version(void);
+/* device: CUDA ordinal.  Fails (PE_ERR_UNSUPPORTED_DEVICE) unless the device is sm_100. */
+int pe_create(pe_handle_t* out, int device);
+int pe_destroy(pe_handle_t h);
+const char* pe_last_error(pe_handle_t h);
+/* Synchronises `stream` and reports whether any kernel since the last check hit a bounded-wait
+ * timeout (PE_ERR_KERNEL_TIMEOUT; diagnostic word in *diag if non-NULL).  Test/debug helper. */
+int pe_check_async_error(pe_handle_t h, void* stream, unsigned int* diag);
+/* number of SMs of the handle's device (grid sizing information for callers / benchmarks). */
+int pe_sm_count(pe_handle_t h);
+
+/* ------------------------------------------------------------------------------------------- */
+/* grouped linear layer with fused epilogue  (tcgen05 / TMEM / TMA)                             */
+/*   replaces F.linear at qwen_image_dit.py:45,240,259-264,312-313 and the elementwise ops      */
+/*   around them (ApproximateGELU :47, gate*x+residual :386-399, RMSNorm utils.py:250-257,       */
+/*   apply_rotary_emb_qwen :51-57, torch.cat :304-306).                                          */
+/* ------------------------------------------------------------------------------------------- */
+typedef enum pe_epilogue {
+    PE_EPI_BIAS = 0,           /* out = bf16(acc + bias)                                         */
+    PE_EPI_BIAS_GELU_TANH = 1, /* reserved                                                       */
+    PE_EPI_BIAS_GELU_SIGMOID = 2, /* h=bf16(acc+bias); out = h * sigmoid(1.702 h)  (ApproximateGELU) */
+    PE_EPI_BIAS_GELU_ERF = 3,  /* h=bf16(acc+bias); out = gelu_erf(h)   (nn.GELU, helpers.py:127) */
+    PE_EPI_GATE_RESIDUAL = 4,  /* o=bf16(acc+bias); out = residual + gate[n]*o  (in place on out) */
+    PE_EPI_QKV_NORM_ROPE = 5,  /* N = 3*H*128: per-head RMSNorm(q,k)*w, RoPE(q,k), v passthrough;
+                                  writes q/k/v into three [M, H*128] buffers                      */
+    PE_EPI_BIAS_SILU = 6       /* out = silu(bf16(acc + bias))   (timestep MLP)                   */
+} pe_epilogue;
+
+/* One segment (= token stream with its own weights) of a grouped GEMM. */
+typedef struct pe_gemm_seg {
+    const void* a;        /* bf16 [M, K], row stride lda elements                                 */
+    int64_t lda;
+    const void* w;        /* bf16 [N, K] contiguous (nn.Linear.weight layout)                     */
+    const void* bias;     /* bf16 [N] or NULL                                                     */
+    void* out;            /* bf16 [M, N] row stride ldo; for QKV: q buffer                        */
+    int64_t ldo;
+    int32_t M;
+    int32_t _pad0;
+    const void* gate;     /* PE_EPI_GATE_RESIDUAL: bf16 [N]                                       */
+    void* out_k;          /* PE_EPI_QKV_NORM_ROPE: k buffer, same ldo                             */
+    void* out_v;          /* PE_EPI_QKV_NORM_ROPE: v buffer, same ldo                             */
+    const void* norm_q_w; /* PE_EPI_QKV_NORM_ROPE: bf16 [128]                                     */
+    const void* norm_k_w; /* PE_EPI_QKV_NORM_ROPE: bf16 [128]                                     */
+    const void* rope;     /* PE_EPI_QKV_NORM_ROPE: float2 (cos,sin) [M, 64]                       */
+} pe_gemm_seg;
+
+#define PE_GEMM_FLAG_CTA_PAIR 1   /* use cta_group::2 (256-row tiles on an SM pair) */
+
+int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* joint (text+image) non-causal attention, head dim 128                                        */
+/*   replaces qwen_image_flash_attention / F.scaled_dot_product_attention (qwen_image_dit.py:37) */
+/*   q,k,v,o: bf16 [S, H*128] token-major (row stride ld elements); scale = 1/sqrt(128).         */
+/* ------------------------------------------------------------------------------------------- */
+#define PE_ATTN_FLAG_SINGLE_Q_TILE 1  /* one 128-row query tile per CTA instead of two ping-ponged tiles  */
+#define PE_ATTN_FLAG_P_VIA_SMEM    2  /* stage P through shared memory (SS MMA) instead of TMEM (TS MMA)   */
+#define PE_ATTN_FLAG_SWAP_V_DESC   4  /* debug: swap LBO/SBO of the MN-major V descriptor                   */
+int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v, void* o,
+                     int S, int H, int64_t ld, float scale, int flags, void* stream);
+
+/* small generic attention for the training-path encoders (DINOv2 ViT-B: 261 tokens x 12 heads x 64,
+ * transformers modeling_dinov2_with_registers.py:174-254; perceiver resampler: 64 latent queries over
+ * <= 10304 keys, 8 heads x 64, helpers.py:21-65).  q: [B, Sq, *] row stride ldq, head hd at column
+ * hd*D; k, v: [B, Skv, *] row stride ldkv; o: [B, Sq, *] row stride ldo.  D in {64, 128}. */
+int pe_small_attention(pe_handle_t h, const void* q, const void* k, const void* v, void* o, int B, int H,
+                       int Sq, int Skv, int D, int64_t ldq, int64_t ldkv, int64_t ldo, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* row-wise / elementwise kernels (HBM-bound)                                                   */
+/* ------------------------------------------------------------------------------------------- */
+/* out[r,:] = bf16(bf16(LN(x[r,:])) * one_plus_scale) + shift ; LN non-affine, eps 1e-6
+ *   replaces F.layer_norm + _modulate (qwen_image_dit.py:355-357,378-383; utils.py:306-308).
+ *   shift / one_plus_scale: bf16 [C] (one_plus_scale already holds bf16(1+scale)). */
+int pe_layernorm_modulate(pe_handle_t h, const void* x, void* out, int rows, int C,
+                          const void* shift, const void* one_plus_scale, void* stream);
+/* nn.LayerNorm: out = bf16(LN(x) * w + b) (helpers.py:13,27-28,98; DINOv2 blocks); w = b = NULL gives the
+ * non-affine LN of Dinov2withNorm (dinov2.py:20-24). */
+int pe_layernorm(pe_handle_t h, const void* x, void* out, int rows, int C, const void* w, const void* b,
+                 float eps, void* stream);
+/* x[r,:] += alpha * add[r % period, :]  (positional / frame-index embedding adds, helpers.py:88,
+ * qwen_image_physical.py:1074-1116; alpha=-1 gives the "middle - source" delta). */
+int pe_add_rows(pe_handle_t h, void* x, const void* add, int rows, int C, int period, float alpha, void* stream);
+/* out = bf16(bf16(x*rsqrt(mean(x^2)+eps)) * w)     (RMSNorm, utils.py:250-257; txt_norm) */
+int pe_rmsnorm(pe_handle_t h, const void* x, void* out, int rows, int C, const void* w, float eps, void* stream);
+
+/* y[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ),  b < batch <= 8.  HBM-bound GEMV.
+ *   replaces the M=1 linears: img_mod/txt_mod (qwen_image_dit.py:335,349), norm_out.linear
+ *   (utils.py:305), timestep_embedder (utils.py:266-270).
+ *   act_in / act_out: 0 none, 1 SiLU.  If one_plus_mask != NULL it is a uint8 [N] mask: where 1 the
+ *   stored value is bf16(1 + y) (pre-computes the "1 + scale" of _modulate). */
+int pe_gemv(pe_handle_t h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K,
+            int act_in, int act_out, const uint8_t* one_plus_mask, void* stream);
+
+/* sinusoidal timestep embedding with the reference's bf16 quirks (utils.py:189-216):
+ *   t_in: bf16 [1] (already bf16(t)); computes ts = bf16(t_in/1000) on device, then
+ *   out[0:128]=cos(1000*ts*f_i), out[128:256]=sin(...), f_i = bf16(exp(-ln(1e4) i/128)); out bf16 [256]. */
+int pe_timestep_embedding(pe_handle_t h, const void* t_in, void* out, void* stream);
+
+/* patchify: latents bf16 [16, H8, W8] -> tokens [ (H8/2)*(W8/2), 64 ], channel order (c, p, q)
+ *   replaces rearrange "B C (H P) (W Q) -> B (H W) (C P Q)" (qwen_image_physical.py:1344,1354). */
+int pe_patchify(pe_handle_t h, const void* latents, void* tokens, int H8, int W8, void* stream);
+/* inverse (qwen_image_physical.py:1402); tokens row stride ld elements. */
+int pe_unpatchify(pe_handle_t h, const void* tokens, int64_t ld, void* latents, int H8, int W8, void* stream);
+
+/* CFG combine + Euler update, bf16 roundings as the reference (qwen_image_physical.py:656-661,
+ * flow_match.py:72-82):  np = nega + cfg*(posi-nega);  latents = latents + np * dsigma. */
+int pe_cfg_euler_step(pe_handle_t h, void* latents, const void* posi, const void* nega, int64_t n,
+                      float cfg_scale, float dsigma, void* stream);
+
+/* special-token adapter plumbing (qwen_image_physical.py:1333-1336, helpers.py:142-164):
+ *   gather: rows of prompt_emb [T, C] where mask[t]!=0 -> dst [max_rows, C] (zero padded),
+ *           row indices -> idx int32 [max_rows] (-1 unused), count -> idx[max_rows].
+ *   blend_scatter: prompt_emb[idx[i], :] = bf16(alpha*dino[i]) + bf16((1-alpha)*vae[i]) ... with the
+ *           reference's bf16 op order; alpha computed on device from t (bf16 [1]), t_min, t_max. */
+int pe_special_gather(pe_handle_t h, const void* prompt_emb, const uint8_t* mask, int T, int C,
+                      void* dst, int32_t* idx, int max_rows, void* stream);
+int pe_special_blend_scatter(pe_handle_t h, void* prompt_emb, const int32_t* idx, int max_rows, int C,
+                             const void* pred_dino, const void* pred_vae, const void* t_in,
+                             float t_min, float t_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PE_B200_H_ */

@@ -1,0 +1,527 @@
+// Joint (text+image) non-causal attention forward, head dim 128, on tcgen05 / TMEM / TMA.
+//
+// Replaces qwen_image_flash_attention -> F.scaled_dot_product_attention
+// (DiffSynth-Studio/diffsynth/models/qwen_image_dit.py:14-39) on q,k,v produced by
+// QwenDoubleStreamAttention.forward (:274-316).  S x S is never materialised.
+//
+// One persistent CTA per SM; a work item is (head, block of kQT*128 query rows).
+//   warp 0          TMA producer : Q tiles once per item, then K_0,V_0,K_1,V_1,... through a ring of
+//                                  32 KB buffers (each tile = two [128 x 64] 128B-swizzled halves)
+//   warp 1          MMA issuer   : S_q = Q_q K_j^T  (SS, 128x128x16 x8)   -> TMEM  (fp32, 128 columns)
+//                                  O_q += P_q V_j   (P from TMEM ("TS") or from smem, V MN-major)
+//   warp 2          TMEM allocator
+//   warps 4..4+4kQT softmax      : one warpgroup per query tile, one thread per query row:
+//                                  tcgen05.ld S -> running max / exp2 / row sum -> P (bf16) written
+//                                  over S in TMEM (or to swizzled smem) -> mbarrier -> PV MMA.
+//                                  The O accumulator is rescaled lazily (only when the running max
+//                                  grows by more than 2^8), so the common KV step never touches O.
+// With kQT = 2 the two query tiles ping-pong: the tensor core computes S_1 / PV_1 while the
+// softmax warpgroup of tile 0 works, and vice versa.
+#include "ptx.cuh"
+#include "common.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int kTile = 128;           // query rows per tile, kv rows per tile, head dim
+constexpr int kHalfBytes = 128 * 64 * 2;   // one [128 x 64] bf16 swizzled half = 16 KB
+constexpr int kTileBytes = 2 * kHalfBytes; // 32 KB
+
+struct AttnParams {
+    CUtensorMap tmQ, tmK, tmV;
+    bf16* o;
+    long long ldo;
+    int S;
+    int H;
+    int n_qblk;      // blocks of kQT*128 query rows
+    int n_items;     // H * n_qblk
+    int n_kv;        // ceil(S / 128)
+    float scale_log2;
+    int swap_lbo_sbo;   // debug: swap the LBO/SBO roles of the MN-major V descriptor
+    unsigned int* abort_flag;
+};
+
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+template <int kQT, bool kPTmem>
+struct AttnCfg {
+    static constexpr int kKV = kPTmem ? (kQT == 2 ? 5 : 6) : (kQT == 2 ? 3 : 5);     // K/V ring depth (32 KB each)
+    static constexpr int kPBytes = kPTmem ? 0 : kQT * kTileBytes;
+    static constexpr int kSmemData = kQT * kTileBytes + kKV * kTileBytes + kPBytes;
+    static constexpr int kSmem = 1024 + kSmemData + 256;
+    static constexpr int kThreads = 128 + 128 * kQT;
+    static constexpr int kTmemCols = kQT == 2 ? 512 : 256;
+};
+
+template <int kQT, bool kPTmem>
+__global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+    using Cfg = AttnCfg<kQT, kPTmem>;
+    constexpr int kKV = Cfg::kKV;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto q_smem = [&](int q) { return smem_base + q * kTileBytes; };
+    auto kv_smem = [&](int s) { return smem_base + (kQT + s) * kTileBytes; };
+    auto p_smem = [&](int q) { return smem_base + (kQT + kKV + q) * kTileBytes; };
+    const uint32_t bar_base = smem_base + Cfg::kSmemData;
+    // barrier map (8 bytes each)
+    const uint32_t q_full = bar_base, q_empty = bar_base + 8;
+    auto kv_full = [&](int s) { return bar_base + 16 + s * 8; };
+    auto kv_empty = [&](int s) { return bar_base + 16 + (kKV + s) * 8; };
+    auto s_full = [&](int q) { return bar_base + 16 + (2 * kKV + q) * 8; };
+    auto p_full = [&](int q) { return bar_base + 16 + (2 * kKV + 2 + q) * 8; };
+    auto pv_done = [&](int q) { return bar_base + 16 + (2 * kKV + 4 + q) * 8; };
+    auto o_empty = [&](int q) { return bar_base + 16 + (2 * kKV + 6 + q) * 8; };
+    const uint32_t tmem_slot = bar_base + 16 + (2 * kKV + 8) * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmQ);
+        prefetch_tmap(&p.tmK);
+        prefetch_tmap(&p.tmV);
+    }
+    if (warp == 1 && elect_one()) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < kKV; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        for (int q = 0; q < kQT; ++q) {
+            mbar_init(s_full(q), 1);
+            mbar_init(p_full(q), 4);
+            mbar_init(pv_done(q), 1);
+            mbar_init(o_empty(q), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    auto s_tmem = [&](int q) { return tmem_base + q * 128; };
+    auto o_tmem = [&](int q) { return tmem_base + kQT * 128 + q * 128; };
+
+    if (warp == 0) {
+        // ======================================= TMA producer =======================================
+        uint32_t n = 0;          // ring sequence number (K_0, V_0, K_1, V_1, ...), continues across items
+        uint32_t it = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            const int col0 = head * kTile;
+            if (!mbar_wait(q_empty, (it & 1u) ^ 1u, p.abort_flag, 10)) break;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, kQT * kTileBytes);
+#pragma unroll
+                for (int q = 0; q < kQT; ++q) {
+                    const int row0 = (qb * kQT + q) * kTile;
+                    tma_load_2d(q_smem(q), &p.tmQ, q_full, col0, row0);
+                    tma_load_2d(q_smem(q) + kHalfBytes, &p.tmQ, q_full, col0 + 64, row0);
+                }
+            }
+            __syncwarp();
+            for (int j = 0; j < p.n_kv && ok; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv, ++n) {
+                    const int slot = n % kKV;
+                    const uint32_t ph = (n / kKV) & 1u;
+                    if (!mbar_wait(kv_empty(slot), ph ^ 1u, p.abort_flag, 11)) { ok = false; break; }
+                    if (elect_one()) {
+                        const CUtensorMap* tm = kv == 0 ? &p.tmK : &p.tmV;
+                        mbar_arrive_expect_tx(kv_full(slot), kTileBytes);
+                        tma_load_2d(kv_smem(slot), tm, kv_full(slot), col0, j * kTile);
+                        tma_load_2d(kv_smem(slot) + kHalfBytes, tm, kv_full(slot), col0 + 64, j * kTile);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================= MMA issuer =======================================
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);     // P (K-major) x V (MN-major)
+        const uint32_t v_lbo = p.swap_lbo_sbo ? 1024u : (uint32_t)kHalfBytes;
+        const uint32_t v_sbo = p.swap_lbo_sbo ? (uint32_t)kHalfBytes : 1024u;
+        uint32_t n = 0, it = 0;
+        uint32_t p_phase[2] = {0, 0};
+        bool ok = true;
+
+        auto issue_s = [&](int q, uint32_t k_base) {
+            // S_q = Q_q K^T : 8 k-steps of 16 head-dim elements; +32 B inside a swizzle row, +16 KB per half
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+                    umma_bf16<1>(s_tmem(q), make_smem_desc_sw128(q_smem(q) + off, 16, 1024),
+                                 make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full(q));
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate) {
+            // O_q (+)= P_q V : 8 k-steps of 16 kv rows; V rows are 128 B apart, 16 rows = 2 KB
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, v_lbo, v_sbo);
+                    const uint32_t acc = (accumulate || kk != 0) ? 1u : 0u;
+                    if (kPTmem) {
+                        umma_bf16_ts(o_tmem(q), s_tmem(q) + kk * 8, bdesc, idesc_o, acc);
+                    } else {
+                        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+                        umma_bf16<1>(o_tmem(q), make_smem_desc_sw128(p_smem(q) + off, 16, 1024), bdesc, idesc_o, acc);
+                    }
+                }
+                umma_commit(pv_done(q));
+            }
+            __syncwarp();
+        };
+
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            if (!mbar_wait(q_full, it & 1u, p.abort_flag, 20)) break;
+            // K_0
+            uint32_t k_slot = n % kKV;
+            if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 21)) break;
+            ++n;
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < kQT; ++q) issue_s(q, kv_smem(k_slot));
+            if (elect_one()) {
+                umma_commit(kv_empty(k_slot));
+                if (p.n_kv == 1) umma_commit(q_empty);
+            }
+            __syncwarp();
+            for (int j = 0; j < p.n_kv && ok; ++j) {
+                const uint32_t v_slot = n % kKV;
+                if (!mbar_wait(kv_full(v_slot), (n / kKV) & 1u, p.abort_flag, 22)) { ok = false; break; }
+                ++n;
+                const bool more = j + 1 < p.n_kv;
+                if (more) {
+                    k_slot = n % kKV;
+                    if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 23)) { ok = false; break; }
+                    ++n;
+                }
+#pragma unroll
+                for (int q = 0; q < kQT; ++q) {
+                    if (j == 0) {
+                        // previous item's epilogue must have drained O_q
+                        if (!mbar_wait(o_empty(q), (it & 1u) ^ 1u, p.abort_flag, 24)) { ok = false; break; }
+                    }
+                    if (!mbar_wait(p_full(q), p_phase[q], p.abort_flag, 25)) { ok = false; break; }
+                    p_phase[q] ^= 1u;
+                    tc_fence_after();
+                    issue_pv(q, kv_smem(v_slot), j > 0);
+                    if (more) issue_s(q, kv_smem(k_slot));
+                }
+                if (!ok) break;
+                if (elect_one()) {
+                    umma_commit(kv_empty(v_slot));
+                    if (more) umma_commit(kv_empty(k_slot));
+                    if (j + 2 == p.n_kv) umma_commit(q_empty);   // last S MMAs of this item were just issued
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================================= softmax / correction / epilogue =======================================
+        const int q = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+        const uint32_t s_addr = s_tmem(q) + lane_off;
+        const uint32_t o_addr = o_tmem(q) + lane_off;
+        const int row_in_tile = wq * 32 + lane;
+        uint32_t s_phase = 0, pv_phase = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            float m_used = -INFINITY;
+            float l = 0.f;
+            for (int j = 0; j < p.n_kv; ++j) {
+                if (!mbar_wait(s_full(q), s_phase, p.abort_flag, 30)) { ok = false; break; }
+                s_phase ^= 1u;
+                tc_fence_after();
+                const int kv_valid = p.S - j * kTile;     // >= 128 except possibly on the last tile
+                // ---- pass 1: row max ----
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(s_addr + c * 32, r);
+                    tmem_ld_wait();
+                    if (kv_valid >= kTile) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    }
+                }
+                const float mx_scaled = mx * p.scale_log2;
+                float m_new = m_used;
+                bool need = false;
+                if (mx_scaled > m_used + 8.0f) { m_new = mx_scaled; need = true; }
+                if (j > 0) {
+                    // PV(j-1) must have finished: it reads P (which we are about to overwrite) and updates O
+                    if (!mbar_wait(pv_done(q), pv_phase, p.abort_flag, 31)) { ok = false; break; }
+                    pv_phase ^= 1u;
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float f = need ? ex2(m_used - m_new) : 1.0f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(o_addr + c * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                            tmem_st32(o_addr + c * 32, r);
+                        }
+                        tmem_st_wait();
+                        l *= f;
+                    }
+                }
+                m_used = m_new;
+                // ---- pass 2: P = exp2(S*scale - m), row sum, write P ----
+                float lsum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(s_addr + c * 32, r);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_used));
+                        float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_used));
+                        if (kv_valid < kTile) {
+                            if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
+                            if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
+                        }
+                        lsum += p0 + p1;
+                        pk[i] = pack_bf16(p0, p1);
+                    }
+                    if (kPTmem) {
+                        tmem_st16(s_addr + c * 16, pk);   // P chunk c overlays S columns [16c, 16c+16): already consumed
+                    } else {
+                        // K-major 128B-swizzled [128 x 64] halves: row r at r*128, 16-byte chunk index ^ (r & 7)
+                        const uint32_t rowb = p_smem(q) + (c >> 1) * kHalfBytes + row_in_tile * 128;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int chunk = (c & 1) * 4 + v;
+                            st_shared_v4(rowb + ((chunk ^ (row_in_tile & 7)) << 4), pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                        }
+                    }
+                }
+                l += lsum;
+                if (kPTmem) tmem_st_wait(); else fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(q));
+            }
+            if (!ok) break;
+            // ---- epilogue: O / l -> bf16 -> global ----
+            if (!mbar_wait(pv_done(q), pv_phase, p.abort_flag, 32)) break;
+            pv_phase ^= 1u;
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            const long long row = (long long)(qb * kQT + q) * kTile + row_in_tile;
+            bf16* orow = p.o + row * p.ldo + head * kTile;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(o_addr + c * 32, r);
+                tmem_ld_wait();
+                if (row < p.S) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv);
+                        o.y = pack_bf16(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv);
+                        o.z = pack_bf16(__uint_as_float(r[8 * v + 4]) * inv, __uint_as_float(r[8 * v + 5]) * inv);
+                        o.w = pack_bf16(__uint_as_float(r[8 * v + 6]) * inv, __uint_as_float(r[8 * v + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + v * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty(q));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+template <int kQT, bool kPTmem>
+int launch_attention(Handle* h, AttnParams& p, cudaStream_t stream) {
+    using Cfg = AttnCfg<kQT, kPTmem>;
+    auto kern = attention_kernel<kQT, kPTmem>;
+    static bool configured = false;
+    if (!configured) {
+        PE_CHECK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        configured = true;
+    }
+    p.n_qblk = ceil_div(p.S, kTile * kQT);
+    p.n_items = p.H * p.n_qblk;
+    int ctas = h->sm_count;
+    if (ctas > p.n_items) ctas = p.n_items;
+    kern<<<ctas, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// small generic attention (CUDA cores) for the training-path encoders whose sequences are tiny:
+// DINOv2 ViT-B (261 tokens, 12 heads x 64; transformers modeling_dinov2_with_registers.py:174-254)
+// and the perceiver resampler (64 latent queries over <= 10304 media+latent keys, 8 heads x 64;
+// helpers.py:21-65).  One warp per query row; lanes stride over keys with a private online softmax
+// and are merged at the end.
+// -------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) small_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                                                              bf16* __restrict__ o, int H, int Sq, int Skv, long long ldq, long long ldkv,
+                                                              long long ldo, float scale) {
+    __shared__ float qs[4][D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 4 + warp;
+    const int hd = blockIdx.y, b = blockIdx.z;
+    if (qi >= Sq) return;
+    const bf16* qrow = q + ((long long)b * Sq + qi) * ldq + hd * D;
+    for (int d = lane; d < D; d += 32) qs[warp][d] = __bfloat162float(qrow[d]) * scale;
+    __syncwarp();
+    float m = -INFINITY, l = 0.f;
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    for (int kj = lane; kj < Skv; kj += 32) {
+        const bf16* krow = k + ((long long)b * Skv + kj) * ldkv + hd * D;
+        float s = 0.f;
+#pragma unroll
+        for (int d8 = 0; d8 < D / 8; ++d8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(krow + d8 * 8);
+            const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+            const float* qq = &qs[warp][d8 * 8];
+            s += a.x * qq[0] + a.y * qq[1] + bq.x * qq[2] + bq.y * qq[3] + c.x * qq[4] + c.y * qq[5] + e.x * qq[6] + e.y * qq[7];
+        }
+        const float m_new = fmaxf(m, s);
+        const float f = __expf(m - m_new);
+        const float pw = __expf(s - m_new);
+        l = l * f + pw;
+        const bf16* vrow = v + ((long long)b * Skv + kj) * ldkv + hd * D;
+#pragma unroll
+        for (int d8 = 0; d8 < D / 8; ++d8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(vrow + d8 * 8);
+            const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+            float* ac = &acc[d8 * 8];
+            ac[0] = ac[0] * f + pw * a.x; ac[1] = ac[1] * f + pw * a.y; ac[2] = ac[2] * f + pw * bq.x; ac[3] = ac[3] * f + pw * bq.y;
+            ac[4] = ac[4] * f + pw * c.x; ac[5] = ac[5] * f + pw * c.y; ac[6] = ac[6] * f + pw * e.x; ac[7] = ac[7] * f + pw * e.y;
+        }
+        m = m_new;
+    }
+    // merge the 32 partial softmaxes
+    float mg = m;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+    const float f = (m == -INFINITY) ? 0.f : __expf(m - mg);
+    l *= f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = 1.0f / l;
+    bf16* orow = o + ((long long)b * Sq + qi) * ldo + hd * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float a = acc[d] * f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == (d & 31)) orow[d] = __float2bfloat16_rn(a * inv);
+    }
+}
+
+}  // namespace
+
+int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
+                  int flags, cudaStream_t stream) {
+    PE_REQUIRE(h, q && k && v && o, "pe_attention_fwd: null pointer");
+    PE_REQUIRE(h, S > 0 && H > 0, "pe_attention_fwd: S and H must be positive (S=%d H=%d)", S, H);
+    PE_REQUIRE(h, ld >= (int64_t)H * 128 && ld % 8 == 0, "pe_attention_fwd: ld must be >= H*128 and a multiple of 8");
+    PE_REQUIRE(h, ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                    reinterpret_cast<uintptr_t>(o)) & 15) == 0, "pe_attention_fwd: q/k/v/o must be 16-byte aligned");
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_tmap_2d(h, &p.tmQ, q, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &p.tmK, k, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &p.tmV, v, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    p.o = static_cast<bf16*>(o);
+    p.ldo = ld;
+    p.S = S;
+    p.H = H;
+    p.n_kv = ceil_div(S, kTile);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.swap_lbo_sbo = (flags & PE_ATTN_FLAG_SWAP_V_DESC) ? 1 : 0;
+    p.abort_flag = h->abort_flag;
+    const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;
+    const bool p_smem = (flags & PE_ATTN_FLAG_P_VIA_SMEM) != 0;
+    if (one_tile) return p_smem ? launch_attention<1, false>(h, p, stream) : launch_attention<1, true>(h, p, stream);
+    return p_smem ? launch_attention<2, false>(h, p, stream) : launch_attention<2, true>(h, p, stream);
+}
+
+int small_attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Skv, int D,
+                        int64_t ldq, int64_t ldkv, int64_t ldo, float scale, cudaStream_t s) {
+    PE_REQUIRE(h, q && k && v && o, "pe_small_attention: null pointer");
+    PE_REQUIRE(h, B > 0 && H > 0 && Sq > 0 && Skv > 0, "pe_small_attention: sizes must be positive");
+    PE_REQUIRE(h, D == 64 || D == 128, "pe_small_attention: head dim must be 64 or 128 (got %d)", D);
+    PE_REQUIRE(h, ldq % 8 == 0 && ldkv % 8 == 0, "pe_small_attention: ldq / ldkv must be multiples of 8");
+    const dim3 grid(ceil_div(Sq, 4), H, B);
+    if (D == 64)
+        small_attention_kernel<64><<<grid, 128, 0, s>>>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
+                                                        static_cast<bf16*>(o), H, Sq, Skv, ldq, ldkv, ldo, scale);
+    else
+        small_attention_kernel<128><<<grid, 128, 0, s>>>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
+                                                         static_cast<bf16*>(o), H, Sq, Skv, ldq, ldkv, ldo, scale);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+}  // namespace pe

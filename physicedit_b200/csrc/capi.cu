@@ -1,0 +1,212 @@
+// C ABI of libpe_b200 (see include/pe_b200.h): handle life cycle, error reporting, tensor-map
+// encoding, and the extern "C" entry points that forward to the kernels' launchers.
+#include <stdarg.h>
+#include <new>
+#include "common.cuh"
+
+namespace pe {
+
+int set_error(Handle* h, int code, const char* fmt, ...) {
+    if (h != nullptr) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->last_error, sizeof(h->last_error), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_2d(Handle* h, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
+    if (h->encode_tiled == nullptr) return set_error(h, PE_ERR_NOT_INITIALIZED, "cuTensorMapEncodeTiled not resolved");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(bf16)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+        out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(h, PE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u",
+                         (int)r, base, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return PE_OK;
+}
+
+// launchers implemented in the kernel translation units
+int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream);
+int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
+                  int flags, cudaStream_t stream);
+int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C, const void* shift, const void* ops, cudaStream_t s);
+int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, float eps, cudaStream_t s);
+int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
+             int act_out, const uint8_t* one_plus_mask, cudaStream_t s);
+int timestep_embedding_run(Handle* h, const void* t_in, void* out, cudaStream_t s);
+int patchify_run(Handle* h, const void* latents, void* tokens, int H8, int W8, cudaStream_t s);
+int unpatchify_run(Handle* h, const void* tokens, int64_t ld, void* latents, int H8, int W8, cudaStream_t s);
+int cfg_euler_run(Handle* h, void* latents, const void* posi, const void* nega, int64_t n, float cfg, float dsigma, cudaStream_t s);
+int special_gather_run(Handle* h, const void* prompt_emb, const uint8_t* mask, int T, int C, void* dst, int32_t* idx,
+                       int max_rows, cudaStream_t s);
+int special_blend_scatter_run(Handle* h, void* prompt_emb, const int32_t* idx, int max_rows, int C, const void* pd,
+                              const void* pv, const void* t_in, float t_min, float t_max, cudaStream_t s);
+int small_attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Skv, int D,
+                        int64_t ldq, int64_t ldkv, int64_t ldo, float scale, cudaStream_t s);
+int layernorm_affine_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, cudaStream_t s);
+int add_bias_rows_run(Handle* h, void* x, const void* add, int rows, int C, int period, float alpha, cudaStream_t s);
+
+}  // namespace pe
+
+using pe::Handle;
+
+extern "C" {
+
+int pe_abi_version(void) { return PE_B200_ABI_VERSION; }
+
+int pe_create(pe_handle_t* out, int device) {
+    if (out == nullptr) return PE_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PE_ERR_UNSUPPORTED_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PE_ERR_CUDA;
+    if (prop.major != 10) return PE_ERR_UNSUPPORTED_DEVICE;   // sm_100a SASS only; no fallback path exists
+    if (cudaSetDevice(device) != cudaSuccess) return PE_ERR_CUDA;
+    Handle* h = new (std::nothrow) Handle();
+    if (h == nullptr) return PE_ERR_OUT_OF_MEMORY;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || h->encode_tiled == nullptr) {
+        delete h;
+        return PE_ERR_CUDA;
+    }
+    if (cudaMalloc(&h->abort_flag, 256) != cudaSuccess || cudaMemset(h->abort_flag, 0, 256) != cudaSuccess) {
+        delete h;
+        return PE_ERR_OUT_OF_MEMORY;
+    }
+    *out = reinterpret_cast<pe_handle_t>(h);
+    return PE_OK;
+}
+
+int pe_destroy(pe_handle_t hh) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (h == nullptr) return PE_ERR_INVALID_ARGUMENT;
+    if (h->abort_flag) cudaFree(h->abort_flag);
+    if (h->workspace) cudaFree(h->workspace);
+    delete h;
+    return PE_OK;
+}
+
+const char* pe_last_error(pe_handle_t hh) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    return h ? h->last_error : "null handle";
+}
+
+int pe_sm_count(pe_handle_t hh) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    return h ? h->sm_count : PE_ERR_INVALID_ARGUMENT;
+}
+
+int pe_check_async_error(pe_handle_t hh, void* stream, unsigned int* diag) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (h == nullptr) return PE_ERR_INVALID_ARGUMENT;
+    PE_CHECK_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    unsigned int v = 0;
+    PE_CHECK_CUDA(h, cudaMemcpy(&v, h->abort_flag, sizeof(v), cudaMemcpyDeviceToHost));
+    if (diag) *diag = v;
+    if (v != 0) {
+        cudaMemset(h->abort_flag, 0, sizeof(v));
+        return pe::set_error(h, PE_ERR_KERNEL_TIMEOUT, "kernel pipeline wait timed out: site=%u block=%u", (v >> 16) & 0x7fffu, v & 0xffffu);
+    }
+    return PE_OK;
+}
+
+#define PE_H(hh)                                        \
+    Handle* h = reinterpret_cast<Handle*>(hh);          \
+    if (h == nullptr) return PE_ERR_INVALID_ARGUMENT;
+
+int pe_gemm(pe_handle_t hh, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, segs != nullptr, "pe_gemm: segs is null");
+    return pe::gemm_run(h, segs, nseg, N, K, epilogue, flags, static_cast<cudaStream_t>(stream));
+}
+
+int pe_attention_fwd(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld,
+                     float scale, int flags, void* stream) {
+    PE_H(hh);
+    return pe::attention_run(h, q, k, v, o, S, H, ld, scale, flags, static_cast<cudaStream_t>(stream));
+}
+
+int pe_small_attention(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Skv,
+                       int D, int64_t ldq, int64_t ldkv, int64_t ldo, float scale, void* stream) {
+    PE_H(hh);
+    return pe::small_attention_run(h, q, k, v, o, B, H, Sq, Skv, D, ldq, ldkv, ldo, scale, static_cast<cudaStream_t>(stream));
+}
+
+int pe_layernorm_modulate(pe_handle_t hh, const void* x, void* out, int rows, int C, const void* shift,
+                          const void* one_plus_scale, void* stream) {
+    PE_H(hh);
+    return pe::layernorm_modulate_run(h, x, out, rows, C, shift, one_plus_scale, static_cast<cudaStream_t>(stream));
+}
+
+int pe_layernorm(pe_handle_t hh, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, void* stream) {
+    PE_H(hh);
+    return pe::layernorm_affine_run(h, x, out, rows, C, w, b, eps, static_cast<cudaStream_t>(stream));
+}
+
+int pe_rmsnorm(pe_handle_t hh, const void* x, void* out, int rows, int C, const void* w, float eps, void* stream) {
+    PE_H(hh);
+    return pe::rmsnorm_run(h, x, out, rows, C, w, eps, static_cast<cudaStream_t>(stream));
+}
+
+int pe_add_rows(pe_handle_t hh, void* x, const void* add, int rows, int C, int period, float alpha, void* stream) {
+    PE_H(hh);
+    return pe::add_bias_rows_run(h, x, add, rows, C, period, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int pe_gemv(pe_handle_t hh, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
+            int act_out, const uint8_t* one_plus_mask, void* stream) {
+    PE_H(hh);
+    return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, act_out, one_plus_mask, static_cast<cudaStream_t>(stream));
+}
+
+int pe_timestep_embedding(pe_handle_t hh, const void* t_in, void* out, void* stream) {
+    PE_H(hh);
+    return pe::timestep_embedding_run(h, t_in, out, static_cast<cudaStream_t>(stream));
+}
+
+int pe_patchify(pe_handle_t hh, const void* latents, void* tokens, int H8, int W8, void* stream) {
+    PE_H(hh);
+    return pe::patchify_run(h, latents, tokens, H8, W8, static_cast<cudaStream_t>(stream));
+}
+
+int pe_unpatchify(pe_handle_t hh, const void* tokens, int64_t ld, void* latents, int H8, int W8, void* stream) {
+    PE_H(hh);
+    return pe::unpatchify_run(h, tokens, ld, latents, H8, W8, static_cast<cudaStream_t>(stream));
+}
+
+int pe_cfg_euler_step(pe_handle_t hh, void* latents, const void* posi, const void* nega, int64_t n, float cfg_scale,
+                      float dsigma, void* stream) {
+    PE_H(hh);
+    return pe::cfg_euler_run(h, latents, posi, nega, n, cfg_scale, dsigma, static_cast<cudaStream_t>(stream));
+}
+
+int pe_special_gather(pe_handle_t hh, const void* prompt_emb, const uint8_t* mask, int T, int C, void* dst, int32_t* idx,
+                      int max_rows, void* stream) {
+    PE_H(hh);
+    return pe::special_gather_run(h, prompt_emb, mask, T, C, dst, idx, max_rows, static_cast<cudaStream_t>(stream));
+}
+
+int pe_special_blend_scatter(pe_handle_t hh, void* prompt_emb, const int32_t* idx, int max_rows, int C, const void* pred_dino,
+                             const void* pred_vae, const void* t_in, float t_min, float t_max, void* stream) {
+    PE_H(hh);
+    return pe::special_blend_scatter_run(h, prompt_emb, idx, max_rows, C, pred_dino, pred_vae, t_in, t_min, t_max,
+                                         static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,487 @@
+// Grouped linear layer  out = epilogue(A · Wᵀ + bias)  on the 5th-gen tensor cores.
+//
+// One persistent, warp-specialised kernel (bf16 operands, fp32 accumulation in TMEM):
+//   warp 0      TMA producer   : A[128 x 64] / W[256 x 64] tiles, 128-byte swizzle, mbarrier ring
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (UMMA 128x256x16, or
+//                                256x256x16 on a CTA pair with cta_group::2)
+//   warp 2      TMEM allocator : 512 columns = 2 accumulator stages x 256 fp32 columns
+//   warps 4..7  epilogue       : tcgen05.ld -> registers -> fused epilogue -> global
+// The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of
+// tile i+1.  A "segment" is a token stream with its own weights (image / text stream of the
+// double-stream DiT block): both streams run in ONE launch, each with its own tensor maps, which
+// also gives free M-tail handling (TMA zero-fills out-of-bounds rows, stores are row-guarded).
+//
+// Reference call sites replaced: F.linear in QwenDoubleStreamAttention.forward / QwenFeedForward /
+// ApproximateGELU (DiffSynth-Studio/diffsynth/models/qwen_image_dit.py:42-49,228-316), the
+// gate/residual adds of QwenImageTransformerBlock.forward (:386-399), RMSNorm (models/utils.py:241-257),
+// apply_rotary_emb_qwen (qwen_image_dit.py:51-57) and the three torch.cat's (:304-306).
+#include "ptx.cuh"
+#include "common.cuh"
+
+namespace pe {
+
+namespace {
+
+constexpr int kBlockK = 64;        // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTileN = 256;
+constexpr int kThreads = 256;
+constexpr int kGroupM = 8;         // rasterisation: 8 m-tiles share a sweep over n
+
+struct SegDev {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    const bf16* bias;
+    bf16* out;
+    const bf16* gate;
+    bf16* out_k;
+    bf16* out_v;
+    const bf16* norm_q_w;
+    const bf16* norm_k_w;
+    const float2* rope;
+    long long ldo;
+    int M;
+    int m_tiles;
+};
+
+struct GemmParams {
+    SegDev seg[2];
+    int nseg;
+    int N;
+    int K;
+    int num_n;
+    int total_m_tiles;
+    int num_tiles;
+    int num_kb;
+    int heads;             // QKV epilogue: N = 3 * heads * 128
+    unsigned int* abort_flag;
+};
+
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+struct Tile {
+    int seg;
+    int m0;   // first row of the tile inside its segment
+    int n0;
+};
+
+template <int kTileM>
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
+    const int group_size = kGroupM * p.num_n;
+    const int g = t / group_size;
+    const int first_m = g * kGroupM;
+    const int gm = min(kGroupM, p.total_m_tiles - first_m);
+    const int in_group = t - g * group_size;
+    int mt = first_m + in_group % gm;
+    const int nt = in_group / gm;
+    Tile r;
+    r.seg = 0;
+    if (p.nseg > 1 && mt >= p.seg[0].m_tiles) { r.seg = 1; mt -= p.seg[0].m_tiles; }
+    r.m0 = mt * kTileM;
+    r.n0 = nt * kTileN;
+    return r;
+}
+
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// ---- generic per-chunk epilogues: 32 consecutive columns of one row --------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const SegDev& sg, long long row, int n, int N) {
+    bf16* out_row = sg.out + row * sg.ldo;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int nn = n + v * 8;
+        if (nn >= N) break;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[v * 8 + j]);
+        if (sg.bias != nullptr) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(sg.bias + nn));
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16(bw[j]);
+                x[2 * j] += f.x;
+                x[2 * j + 1] += f.y;
+            }
+        }
+        // the reference materialises the linear output in bf16 here
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
+
+        if (EPI == PE_EPI_BIAS_GELU_SIGMOID) {
+            // ApproximateGELU: x * sigmoid(1.702 * x), each op rounded to bf16 (qwen_image_dit.py:47)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a = bf16_round(1.702f * x[j]);
+                const float s = bf16_round(sigmoidf_fast(a));
+                x[j] = x[j] * s;
+            }
+        } else if (EPI == PE_EPI_BIAS_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = 0.5f * x[j] * (1.0f + erff(x[j] * 0.70710678118654752f));
+        } else if (EPI == PE_EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = x[j] * sigmoidf_fast(x[j]);
+        } else if (EPI == PE_EPI_GATE_RESIDUAL) {
+            const uint4 g = __ldg(reinterpret_cast<const uint4*>(sg.gate + nn));
+            const uint4 r = *reinterpret_cast<const uint4*>(out_row + nn);
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 gf = unpack_bf16(gw[j]);
+                const float2 rf = unpack_bf16(rw[j]);
+                x[2 * j]     = rf.x + bf16_round(gf.x * x[2 * j]);
+                x[2 * j + 1] = rf.y + bf16_round(gf.y * x[2 * j + 1]);
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16(x[0], x[1]);
+        o.y = pack_bf16(x[2], x[3]);
+        o.z = pack_bf16(x[4], x[5]);
+        o.w = pack_bf16(x[6], x[7]);
+        *reinterpret_cast<uint4*>(out_row + nn) = o;
+    }
+}
+
+// ---- QKV epilogue: one 128-column head of one row ---------------------------------------------------
+// y0 = bf16(acc+bias); q,k: y1 = bf16(y0*rsqrt(mean(y0^2)+eps)); y2 = bf16(y1*w); RoPE in fp32 -> bf16.
+__device__ __forceinline__ void epilogue_qkv_head(uint32_t taddr_head, const SegDev& sg, long long row, bool row_valid,
+                                                  int n_head0, int heads) {
+    const int head = n_head0 >> 7;
+    const int which = head / heads;             // 0 q, 1 k, 2 v
+    const int col0 = (head - which * heads) << 7;
+    uint32_t y0[64];                            // 128 bf16 values, packed
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(taddr_head + c * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(sg.bias + n_head0 + c * 32 + v * 8));
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16(bw[j]);
+                const float a = bf16_round(__uint_as_float(acc[v * 8 + 2 * j]) + f.x);
+                const float d = bf16_round(__uint_as_float(acc[v * 8 + 2 * j + 1]) + f.y);
+                ss += a * a + d * d;
+                y0[c * 16 + v * 4 + j] = pack_bf16(a, d);
+            }
+        }
+    }
+    if (!row_valid) return;
+    bf16* dst = (which == 0 ? sg.out : (which == 1 ? sg.out_k : sg.out_v)) + row * sg.ldo + col0;
+    if (which == 2) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+            uint4 o;
+            o.x = y0[v * 4]; o.y = y0[v * 4 + 1]; o.z = y0[v * 4 + 2]; o.w = y0[v * 4 + 3];
+            *reinterpret_cast<uint4*>(dst + v * 8) = o;
+        }
+        return;
+    }
+    const float rs = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+    const bf16* w = which == 0 ? sg.norm_q_w : sg.norm_k_w;
+    const float4* rope = reinterpret_cast<const float4*>(sg.rope + row * 64);   // 2 (cos,sin) pairs per float4
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {   // 8 columns = 4 rotary pairs per iteration
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + v * 8));
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 y = unpack_bf16(y0[v * 4 + j]);
+            const float2 wf = unpack_bf16(ww[j]);
+            const float a = bf16_round(bf16_round(y.x * rs) * wf.x);
+            const float b = bf16_round(bf16_round(y.y * rs) * wf.y);
+            const float4 cs2 = __ldg(rope + v * 2 + (j >> 1));
+            const float c = (j & 1) ? cs2.z : cs2.x;
+            const float s = (j & 1) ? cs2.w : cs2.y;
+            ov[j] = pack_bf16(a * c - b * s, a * s + b * c);
+        }
+        uint4 o;
+        o.x = ov[0]; o.y = ov[1]; o.z = ov[2]; o.w = ov[3];
+        *reinterpret_cast<uint4*>(dst + v * 8) = o;
+    }
+}
+
+template <int kCG, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int kStages = kCG == 1 ? 4 : 6;
+    constexpr int kABytes = 128 * kBlockK * 2;
+    constexpr int kBRows = kCG == 1 ? 256 : 128;
+    constexpr int kBBytes = kBRows * kBlockK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kTileM = 128 * kCG;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    auto a_smem = [&](int s) { return smem_base + s * kStageBytes; };
+    auto b_smem = [&](int s) { return smem_base + s * kStageBytes + kABytes; };
+    auto full_bar = [&](int s) { return bar_base + s * 8; };
+    auto empty_bar = [&](int s) { return bar_base + (kStages + s) * 8; };
+    auto tfull_bar = [&](int s) { return bar_base + (2 * kStages + s) * 8; };
+    auto tempty_bar = [&](int s) { return bar_base + (2 * kStages + 2 + s) * 8; };
+    const uint32_t tmem_slot = bar_base + (2 * kStages + 4) * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t cta_rank = kCG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / kCG;
+    const int num_clusters = gridDim.x / kCG;
+
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.nseg; ++s) {
+            prefetch_tmap(&p.seg[s].tmA);
+            prefetch_tmap(&p.seg[s].tmB);
+        }
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4 * kCG);   // one elected arrival per epilogue warp (of both CTAs)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<kCG>(tmem_slot, 512);
+        tmem_relinquish<kCG>();
+    }
+    tc_fence_before();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int t = cluster_id; t < p.num_tiles && ok; t += num_clusters) {
+            const Tile tile = decode_tile<kTileM>(p, t);
+            const SegDev& sg = p.seg[tile.seg];
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (!mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_flag, 1)) { ok = false; break; }
+                if (elect_one()) {
+                    if (kCG == 1) {
+                        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                        tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, tile.m0);
+                        tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, tile.n0);
+                    } else {
+                        // both CTAs' bytes are accounted on the leader's barrier
+                        const uint32_t fb = mapa(full_bar(stage), 0);
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
+                        tma_load_2d_cg2(a_smem(stage), &sg.tmA, fb, kb * kBlockK, tile.m0 + (int)cta_rank * 128);
+                        tma_load_2d_cg2(b_smem(stage), &sg.tmB, fb, kb * kBlockK, tile.n0 + (int)cta_rank * 128);
+                    }
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(kTileM, kTileN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            bool ok = true;
+            for (int t = cluster_id; t < p.num_tiles && ok; t += num_clusters) {
+                if (!mbar_wait<kCG == 2>(tempty_bar(acc), acc_phase ^ 1u, p.abort_flag, 2)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kTileN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (!mbar_wait(full_bar(stage), phase, p.abort_flag, 3)) { ok = false; break; }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc = make_smem_desc_sw128(a_smem(stage), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(b_smem(stage), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // +32 bytes per UMMA_K step inside the 128-byte swizzle row (addr field is >>4)
+                            umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if (kCG == 1) umma_commit(empty_bar(stage)); else umma_commit_cg2(empty_bar(stage), 3);
+                        if (kb == p.num_kb - 1) {
+                            if (kCG == 1) umma_commit(tfull_bar(acc)); else umma_commit_cg2(tfull_bar(acc), 3);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int ew = warp - 4;                 // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        const int lane = lane_id();
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+            const Tile tile = decode_tile<kTileM>(p, t);
+            const SegDev& sg = p.seg[tile.seg];
+            if (!mbar_wait(tfull_bar(acc), acc_phase, p.abort_flag, 4)) break;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kTileN;
+            const long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
+            const bool row_valid = row < sg.M;
+            if (EPI == PE_EPI_QKV_NORM_ROPE) {
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int n_head0 = tile.n0 + hh * 128;
+                    if (n_head0 >= p.N) break;
+                    epilogue_qkv_head(taddr + hh * 128, sg, row, row_valid, n_head0, p.heads);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; ++c) {
+                    const int n = tile.n0 + c * 32;
+                    if (n >= p.N) break;
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    if (row_valid) epilogue_chunk<EPI>(r, sg, row, n, p.N);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) {
+                if (kCG == 1) mbar_arrive(tempty_bar(acc));
+                else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    // ================================ teardown ================================
+    tc_fence_before();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<kCG>(tmem_base, 512);
+    }
+}
+
+template <int kCG>
+constexpr int gemm_smem_bytes() {
+    return 1024 /*alignment slack*/ + (kCG == 1 ? 4 * (16384 + 32768) : 6 * (16384 + 16384)) + 256;
+}
+
+template <int kCG, int EPI>
+int launch_gemm(Handle* h, const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm_kernel<kCG, EPI>;
+    constexpr int smem = gemm_smem_bytes<kCG>();
+    static bool configured = false;   // per template instance; attribute is sticky per function
+    if (!configured) {
+        PE_CHECK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int ctas = h->sm_count;
+    if (kCG == 2) ctas &= ~1;
+    const int max_useful = p.num_tiles * kCG;
+    if (ctas > max_useful) ctas = max_useful;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PE_CHECK_CUDA(h, cudaLaunchKernelEx(&cfg, kern, p));
+    return PE_OK;
+}
+
+template <int kCG>
+int dispatch_epilogue(Handle* h, const GemmParams& p, int epilogue, cudaStream_t stream) {
+    switch (epilogue) {
+        case PE_EPI_BIAS: return launch_gemm<kCG, PE_EPI_BIAS>(h, p, stream);
+        case PE_EPI_BIAS_GELU_SIGMOID: return launch_gemm<kCG, PE_EPI_BIAS_GELU_SIGMOID>(h, p, stream);
+        case PE_EPI_BIAS_GELU_ERF: return launch_gemm<kCG, PE_EPI_BIAS_GELU_ERF>(h, p, stream);
+        case PE_EPI_GATE_RESIDUAL: return launch_gemm<kCG, PE_EPI_GATE_RESIDUAL>(h, p, stream);
+        case PE_EPI_QKV_NORM_ROPE: return launch_gemm<kCG, PE_EPI_QKV_NORM_ROPE>(h, p, stream);
+        case PE_EPI_BIAS_SILU: return launch_gemm<kCG, PE_EPI_BIAS_SILU>(h, p, stream);
+        default: return set_error(h, PE_ERR_INVALID_ARGUMENT, "pe_gemm: unknown epilogue %d", epilogue);
+    }
+}
+
+}  // namespace
+
+int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream) {
+    PE_REQUIRE(h, nseg >= 1 && nseg <= 2, "pe_gemm: nseg must be 1 or 2 (got %d)", nseg);
+    PE_REQUIRE(h, N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "pe_gemm: N and K must be positive multiples of 8 (N=%d K=%d)", N, K);
+    const int cg = (flags & PE_GEMM_FLAG_CTA_PAIR) ? 2 : 1;
+    const int tile_m = 128 * cg;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.nseg = nseg;
+    p.N = N;
+    p.K = K;
+    p.num_n = ceil_div(N, kTileN);
+    p.num_kb = ceil_div(K, kBlockK);
+    p.abort_flag = h->abort_flag;
+    if (epilogue == PE_EPI_QKV_NORM_ROPE) {
+        PE_REQUIRE(h, N % 384 == 0, "pe_gemm: QKV epilogue needs N = 3*heads*128 (N=%d)", N);
+        p.heads = N / 384;
+    }
+    int total_m_tiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        const pe_gemm_seg& in = segs[s];
+        PE_REQUIRE(h, in.M > 0, "pe_gemm: segment %d has M=%d", s, in.M);
+        PE_REQUIRE(h, in.a && in.w && in.out, "pe_gemm: segment %d has a null a/w/out pointer", s);
+        PE_REQUIRE(h, in.lda >= K && in.lda % 8 == 0, "pe_gemm: lda must be >= K and a multiple of 8");
+        PE_REQUIRE(h, in.ldo % 8 == 0, "pe_gemm: ldo must be a multiple of 8");
+        PE_REQUIRE(h, (reinterpret_cast<uintptr_t>(in.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(in.w) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(in.out) & 15) == 0,
+                   "pe_gemm: a / w / out must be 16-byte aligned");
+        SegDev& d = p.seg[s];
+        int rc = make_tmap_2d(h, &d.tmA, in.a, (uint64_t)in.M, (uint64_t)K, (uint64_t)in.lda, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? 256 : 128);
+        if (rc) return rc;
+        d.bias = static_cast<const bf16*>(in.bias);
+        d.out = static_cast<bf16*>(in.out);
+        d.gate = static_cast<const bf16*>(in.gate);
+        d.out_k = static_cast<bf16*>(in.out_k);
+        d.out_v = static_cast<bf16*>(in.out_v);
+        d.norm_q_w = static_cast<const bf16*>(in.norm_q_w);
+        d.norm_k_w = static_cast<const bf16*>(in.norm_k_w);
+        d.rope = static_cast<const float2*>(in.rope);
+        d.ldo = in.ldo;
+        d.M = in.M;
+        d.m_tiles = ceil_div(in.M, tile_m);
+        total_m_tiles += d.m_tiles;
+        if (epilogue == PE_EPI_GATE_RESIDUAL) PE_REQUIRE(h, in.gate != nullptr, "pe_gemm: gate-residual epilogue needs gate");
+        if (epilogue == PE_EPI_QKV_NORM_ROPE)
+            PE_REQUIRE(h, in.bias && in.out_k && in.out_v && in.norm_q_w && in.norm_k_w && in.rope,
+                       "pe_gemm: QKV epilogue needs bias, out_k, out_v, norm weights and rope table");
+    }
+    p.total_m_tiles = total_m_tiles;
+    p.num_tiles = total_m_tiles * p.num_n;
+    if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
+    return dispatch_epilogue<2>(h, p, epilogue, stream);
+}
+
+}  // namespace pe

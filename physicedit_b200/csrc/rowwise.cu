@@ -1,0 +1,477 @@
+// HBM-bound row-wise and element-wise kernels of the DiT forward: LayerNorm+modulate, RMSNorm, the
+// M=1 linears (GEMV), the timestep sinusoid, patchify / unpatchify, CFG + Euler update and the
+// special-token gather / blend-scatter.  All of them are plain coalesced 16-byte-vector kernels:
+// one warp owns one row (or one output feature for the GEMV) and keeps it in registers, so every
+// input byte is read exactly once.  bf16 rounding points follow the reference op by op
+//  so results are comparable with the reference's bf16 tensors.
+#include "ptx.cuh"
+#include "common.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    return u;
+}
+// streaming 16-byte load that does not pollute L1
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LayerNorm (no affine, eps) followed by one of three tails.
+//   MODE 0: out = bf16( bf16( bf16(n) * ops ) + shift )      (_modulate, qwen_image_dit.py:355-357)
+//   MODE 1: out = bf16( n * w + b )                           (nn.LayerNorm with affine, helpers.py / DINOv2)
+//   MODE 2: out = bf16( n )                                   (non-affine final LN, dinov2.py:20-24)
+// kVec = number of 8-element vectors each lane owns (C <= 256 * kVec).
+// -------------------------------------------------------------------------------------------------
+template <int kVec, int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int rows, int C,
+                                                                       const bf16* __restrict__ p0, const bf16* __restrict__ p1, float eps) {
+    const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 3;
+    const bf16* xr = x + (size_t)row * C;
+    float v[kVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            unpack8(ld_stream(xr + vi * 8), v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        if (lane + 32 * i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    bf16* orow = out + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi >= nvec) continue;
+        float o[8];
+        if (MODE == 0) {
+            float a[8], b[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p1 + vi * 8)), a);   // bf16(1 + scale)
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p0 + vi * 8)), b);   // shift
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float n = bf16_round((v[i][j] - mean) * rstd);
+                o[j] = bf16_round(n * a[j]) + b[j];
+            }
+        } else if (MODE == 1) {
+            float a[8], b[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p0 + vi * 8)), a);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p1 + vi * 8)), b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * a[j] + b[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+        }
+        *reinterpret_cast<uint4*>(orow + vi * 8) = pack8(o);
+    }
+}
+
+template <int MODE>
+int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const void* p0, const void* p1, float eps, cudaStream_t s) {
+    PE_REQUIRE(h, rows > 0 && C > 0 && C % 8 == 0 && C <= 4096, "layernorm: need rows>0, C%%8==0, C<=4096 (rows=%d C=%d)", rows, C);
+    PE_REQUIRE(h, x && out, "layernorm: null pointer");
+    const dim3 grid(ceil_div(rows, kWarpsPerCta)), block(kWarpsPerCta * 32);
+    const bf16* xb = static_cast<const bf16*>(x);
+    bf16* ob = static_cast<bf16*>(out);
+    const bf16* a = static_cast<const bf16*>(p0);
+    const bf16* b = static_cast<const bf16*>(p1);
+    if (C <= 256) layernorm_kernel<1, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
+    else if (C <= 1024) layernorm_kernel<4, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
+    else if (C <= 3072) layernorm_kernel<12, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
+    else layernorm_kernel<16, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// RMSNorm (models/utils.py:250-257): y = bf16( bf16( x * rsqrt(mean(x^2)+eps) ) * w )
+// -------------------------------------------------------------------------------------------------
+template <int kVec>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) rmsnorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int rows, int C,
+                                                                     const bf16* __restrict__ w, float eps) {
+    const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 3;
+    const bf16* xr = x + (size_t)row * C;
+    float v[kVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            unpack8(ld_stream(xr + vi * 8), v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+        }
+    }
+    const float rs = rsqrtf(warp_sum(ss) / (float)C + eps);
+    bf16* orow = out + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi >= nvec) continue;
+        float o[8];
+        if (w != nullptr) {
+            float a[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(w + vi * 8)), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = bf16_round(v[i][j] * rs) * a[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rs;
+        }
+        *reinterpret_cast<uint4*>(orow + vi * 8) = pack8(o);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// GEMV for the M=1 linears: one warp per output feature, x staged (after act_in) in shared memory.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_bf16(float x) { return bf16_round(x / (1.0f + expf(-x))); }
+
+template <int kBatch>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const bf16* __restrict__ bias, bf16* __restrict__ y, int N, int K,
+                                                                  int act_in, int act_out, const uint8_t* __restrict__ one_plus_mask) {
+    extern __shared__ float xs[];   // [kBatch][K]
+    for (int i = threadIdx.x; i < kBatch * K; i += blockDim.x) {
+        float f = __bfloat162float(x[i]);
+        if (act_in == 1) f = silu_bf16(f);
+        xs[i] = f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nvec = K >> 3;
+    for (int n = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); n < N; n += gridDim.x * kWarpsPerCta) {
+        const bf16* wr = w + (size_t)n * K;
+        float acc[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) acc[b] = 0.f;
+        for (int v0 = 0; v0 < nvec; v0 += 32 * 4) {
+            uint4 u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int vi = v0 + lane + 32 * i;
+                u[i] = vi < nvec ? ld_stream(wr + vi * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int vi = v0 + lane + 32 * i;
+                if (vi >= nvec) continue;
+                float f[8];
+                unpack8(u[i], f);
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8);
+                    const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8 + 4);
+                    acc[b] += f[0] * x0.x + f[1] * x0.y + f[2] * x0.z + f[3] * x0.w + f[4] * x1.x + f[5] * x1.y + f[6] * x1.z + f[7] * x1.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) acc[b] = warp_sum(acc[b]);
+        if (lane == 0) {
+            const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                float r = bf16_round(acc[b] + bv);
+                if (act_out == 1) r = silu_bf16(r);
+                if (one_plus_mask != nullptr && one_plus_mask[n]) r = bf16_round(1.0f + r);
+                y[(size_t)b * N + n] = __float2bfloat16_rn(r);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// timestep sinusoid with the reference's bf16 quirks (models/utils.py:189-216)
+// -------------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const bf16* __restrict__ t_in, bf16* __restrict__ out) {
+    const int i = threadIdx.x;   // 0..127
+    // timestep / 1000 on a bf16 CUDA tensor = bf16( float(t) * float(1/1000.) )  (ATen div-by-scalar)
+    const float ts = bf16_round(__bfloat162float(t_in[0]) * (float)(1.0 / 1000.0));
+    const float exponent = __fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), 128.0f);
+    const float freq = bf16_round(expf(exponent));        // align_dtype_to_timestep: freqs rounded to bf16
+    const float arg = __fmul_rn(1000.0f, __fmul_rn(ts, freq));
+    out[i] = __float2bfloat16_rn(cosf(arg));               // flip_sin_to_cos: cos half first
+    out[128 + i] = __float2bfloat16_rn(sinf(arg));
+}
+
+// -------------------------------------------------------------------------------------------------
+// patchify / unpatchify:  "C (H P) (W Q) -> (H W) (C P Q)", P = Q = 2, C = 16
+// -------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const bf16* __restrict__ lat, bf16* __restrict__ tok, int H8, int W8) {
+    const int W2 = W8 >> 1;
+    const int ntok = (H8 >> 1) * W2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // (token, c)
+    if (gid >= ntok * 16) return;
+    const int c = gid & 15;
+    const int t = gid >> 4;
+    const int hh = t / W2, ww = t - hh * W2;
+    const bf16* src = lat + ((size_t)c * H8 + 2 * hh) * W8 + 2 * ww;
+    const uint32_t r0 = *reinterpret_cast<const uint32_t*>(src);
+    const uint32_t r1 = *reinterpret_cast<const uint32_t*>(src + W8);
+    *reinterpret_cast<uint2*>(tok + (size_t)t * 64 + c * 4) = make_uint2(r0, r1);
+}
+__global__ void unpatchify_kernel(const bf16* __restrict__ tok, long long ld, bf16* __restrict__ lat, int H8, int W8) {
+    const int W2 = W8 >> 1;
+    const int ntok = (H8 >> 1) * W2;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;   // (c, token): consecutive threads -> consecutive w
+    if (gid >= ntok * 16) return;
+    const int c = gid / ntok;
+    const int t = gid - c * ntok;
+    const int hh = t / W2, ww = t - hh * W2;
+    const uint2 v = *reinterpret_cast<const uint2*>(tok + (size_t)t * ld + c * 4);
+    bf16* dst = lat + ((size_t)c * H8 + 2 * hh) * W8 + 2 * ww;
+    *reinterpret_cast<uint32_t*>(dst) = v.x;
+    *reinterpret_cast<uint32_t*>(dst + W8) = v.y;
+}
+
+// -------------------------------------------------------------------------------------------------
+// CFG combine + Euler update (qwen_image_physical.py:656, flow_match.py:81), every op rounded to bf16
+// -------------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(bf16* __restrict__ lat, const bf16* __restrict__ posi, const bf16* __restrict__ nega, long long n,
+                                 float cfg, float dsigma) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p = __bfloat162float(posi[i]);
+    float np = p;
+    if (nega != nullptr) {
+        const float q = __bfloat162float(nega[i]);
+        np = bf16_round(q + bf16_round(cfg * bf16_round(p - q)));
+    }
+    lat[i] = __float2bfloat16_rn(__bfloat162float(lat[i]) + bf16_round(np * dsigma));
+}
+
+// -------------------------------------------------------------------------------------------------
+// special tokens: ordered gather of the masked rows, and blend + scatter back
+// -------------------------------------------------------------------------------------------------
+__global__ void special_index_kernel(const uint8_t* __restrict__ mask, int T, int32_t* __restrict__ idx, int max_rows) {
+    // single CTA of 1024 threads; ordered compaction via per-chunk ballot + running offset
+    __shared__ int warp_cnt[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    for (int i = threadIdx.x; i <= max_rows; i += blockDim.x) idx[i] = -1;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+        const int t = t0 + threadIdx.x;
+        const bool m = t < T && mask[t] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        if (m && pos < max_rows) idx[pos] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_cnt[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) idx[max_rows] = base;
+}
+__global__ void special_gather_rows_kernel(const bf16* __restrict__ pe, const int32_t* __restrict__ idx, int C, bf16* __restrict__ dst) {
+    const int r = blockIdx.x;
+    const int t = idx[r];
+    const int nvec = C >> 3;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (t >= 0) u = *reinterpret_cast<const uint4*>(pe + (size_t)t * C + v * 8);
+        *reinterpret_cast<uint4*>(dst + (size_t)r * C + v * 8) = u;
+    }
+}
+__global__ void special_blend_scatter_kernel(bf16* __restrict__ pe, const int32_t* __restrict__ idx, int C, const bf16* __restrict__ pd,
+                                             const bf16* __restrict__ pv, const bf16* __restrict__ t_in, float t_min, float inv_range) {
+    const int r = blockIdx.x;
+    const int t = idx[r];
+    if (t < 0) return;
+    // helpers.py:142-150 on a bf16 CUDA timestep: (t - t_min) -> bf16, / range (ATen: * float(1/range)) -> bf16, clamp
+    float alpha = bf16_round(__bfloat162float(t_in[0]) - t_min);
+    alpha = bf16_round(alpha * inv_range);
+    alpha = fminf(fmaxf(alpha, 0.f), 1.f);
+    const float oma = bf16_round(1.0f - alpha);
+    const int nvec = C >> 3;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float a[8], b[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(pd + (size_t)r * C + v * 8), a);
+        unpack8(*reinterpret_cast<const uint4*>(pv + (size_t)r * C + v * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = bf16_round(alpha * a[j]) + bf16_round(oma * b[j]);
+        *reinterpret_cast<uint4*>(pe + (size_t)t * C + v * 8) = pack8(o);
+    }
+}
+
+// x[r, :] += alpha * add[(r % period), :]     (pos-emb / frame-embedding adds of the resampler path)
+__global__ void add_rows_kernel(bf16* __restrict__ x, const bf16* __restrict__ add, int rows, int C, int period, float alpha) {
+    const int nvec = C >> 3;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)rows * nvec) return;
+    const int r = (int)(gid / nvec), v = (int)(gid - (long long)r * nvec);
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + (size_t)r * C + v * 8), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(add + (size_t)(r % period) * C + v * 8)), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += alpha * b[j];
+    *reinterpret_cast<uint4*>(x + (size_t)r * C + v * 8) = pack8(a);
+}
+
+}  // namespace
+
+int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C, const void* shift, const void* ops, cudaStream_t s) {
+    PE_REQUIRE(h, shift && ops, "pe_layernorm_modulate: shift / one_plus_scale must not be null");
+    return launch_layernorm<0>(h, x, out, rows, C, shift, ops, 1e-6f, s);
+}
+
+int layernorm_affine_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, cudaStream_t s) {
+    if (w == nullptr && b == nullptr) return launch_layernorm<2>(h, x, out, rows, C, nullptr, nullptr, eps, s);
+    PE_REQUIRE(h, w && b, "pe_layernorm: weight and bias must both be given or both be null");
+    return launch_layernorm<1>(h, x, out, rows, C, w, b, eps, s);
+}
+
+int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, float eps, cudaStream_t s) {
+    PE_REQUIRE(h, rows > 0 && C > 0 && C % 8 == 0 && C <= 4096, "pe_rmsnorm: need rows>0, C%%8==0, C<=4096 (rows=%d C=%d)", rows, C);
+    PE_REQUIRE(h, x && out, "pe_rmsnorm: null pointer");
+    const dim3 grid(ceil_div(rows, kWarpsPerCta)), block(kWarpsPerCta * 32);
+    const bf16* xb = static_cast<const bf16*>(x);
+    bf16* ob = static_cast<bf16*>(out);
+    const bf16* wb = static_cast<const bf16*>(w);
+    if (C <= 256) rmsnorm_kernel<1><<<grid, block, 0, s>>>(xb, ob, rows, C, wb, eps);
+    else if (C <= 1024) rmsnorm_kernel<4><<<grid, block, 0, s>>>(xb, ob, rows, C, wb, eps);
+    else if (C <= 3072) rmsnorm_kernel<12><<<grid, block, 0, s>>>(xb, ob, rows, C, wb, eps);
+    else rmsnorm_kernel<16><<<grid, block, 0, s>>>(xb, ob, rows, C, wb, eps);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in, int act_out,
+             const uint8_t* one_plus_mask, cudaStream_t s) {
+    PE_REQUIRE(h, batch >= 1 && batch <= 8, "pe_gemv: batch must be 1..8 (got %d)", batch);
+    PE_REQUIRE(h, N > 0 && K > 0 && K % 8 == 0, "pe_gemv: N>0, K%%8==0 required (N=%d K=%d)", N, K);
+    PE_REQUIRE(h, x && w && y, "pe_gemv: null pointer");
+    PE_REQUIRE(h, (size_t)batch * K * 4 <= 200 * 1024, "pe_gemv: batch*K too large for shared memory");
+    const size_t smem = (size_t)batch * K * sizeof(float);
+    int grid = ceil_div(N, kWarpsPerCta);
+    const int cap = h->sm_count * 8;
+    if (grid > cap) grid = cap;
+    const bf16* xb = static_cast<const bf16*>(x);
+    const bf16* wb = static_cast<const bf16*>(w);
+    const bf16* bb = static_cast<const bf16*>(bias);
+    bf16* yb = static_cast<bf16*>(y);
+#define PE_GEMV_CASE(B)                                                                                                      \
+    case B: {                                                                                                                \
+        if (smem > 48 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gemv_kernel<B><<<grid, kWarpsPerCta * 32, smem, s>>>(xb, wb, bb, yb, N, K, act_in, act_out, one_plus_mask);           \
+        break;                                                                                                               \
+    }
+    switch (batch) {
+        PE_GEMV_CASE(1) PE_GEMV_CASE(2) PE_GEMV_CASE(3) PE_GEMV_CASE(4) PE_GEMV_CASE(5) PE_GEMV_CASE(6) PE_GEMV_CASE(7) PE_GEMV_CASE(8)
+    }
+#undef PE_GEMV_CASE
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int timestep_embedding_run(Handle* h, const void* t_in, void* out, cudaStream_t s) {
+    PE_REQUIRE(h, t_in && out, "pe_timestep_embedding: null pointer");
+    timestep_embedding_kernel<<<1, 128, 0, s>>>(static_cast<const bf16*>(t_in), static_cast<bf16*>(out));
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int patchify_run(Handle* h, const void* latents, void* tokens, int H8, int W8, cudaStream_t s) {
+    PE_REQUIRE(h, latents && tokens && H8 > 0 && W8 > 0 && H8 % 2 == 0 && W8 % 2 == 0, "pe_patchify: H8, W8 must be positive and even");
+    const int n = (H8 / 2) * (W8 / 2) * 16;
+    patchify_kernel<<<ceil_div(n, 256), 256, 0, s>>>(static_cast<const bf16*>(latents), static_cast<bf16*>(tokens), H8, W8);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int unpatchify_run(Handle* h, const void* tokens, int64_t ld, void* latents, int H8, int W8, cudaStream_t s) {
+    PE_REQUIRE(h, latents && tokens && H8 > 0 && W8 > 0 && H8 % 2 == 0 && W8 % 2 == 0, "pe_unpatchify: H8, W8 must be positive and even");
+    PE_REQUIRE(h, ld >= 64 && ld % 4 == 0, "pe_unpatchify: ld must be >= 64 and a multiple of 4");
+    const int n = (H8 / 2) * (W8 / 2) * 16;
+    unpatchify_kernel<<<ceil_div(n, 256), 256, 0, s>>>(static_cast<const bf16*>(tokens), (long long)ld, static_cast<bf16*>(latents), H8, W8);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int cfg_euler_run(Handle* h, void* latents, const void* posi, const void* nega, int64_t n, float cfg, float dsigma, cudaStream_t s) {
+    PE_REQUIRE(h, latents && posi && n > 0, "pe_cfg_euler_step: null pointer or n<=0");
+    cfg_euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<bf16*>(latents), static_cast<const bf16*>(posi),
+                                                                static_cast<const bf16*>(nega), (long long)n, cfg, dsigma);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int special_gather_run(Handle* h, const void* prompt_emb, const uint8_t* mask, int T, int C, void* dst, int32_t* idx, int max_rows,
+                       cudaStream_t s) {
+    PE_REQUIRE(h, prompt_emb && mask && dst && idx, "pe_special_gather: null pointer");
+    PE_REQUIRE(h, T > 0 && C > 0 && C % 8 == 0 && max_rows > 0, "pe_special_gather: bad sizes");
+    special_index_kernel<<<1, 1024, 0, s>>>(mask, T, idx, max_rows);
+    special_gather_rows_kernel<<<max_rows, 128, 0, s>>>(static_cast<const bf16*>(prompt_emb), idx, C, static_cast<bf16*>(dst));
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int special_blend_scatter_run(Handle* h, void* prompt_emb, const int32_t* idx, int max_rows, int C, const void* pd, const void* pv,
+                              const void* t_in, float t_min, float t_max, cudaStream_t s) {
+    PE_REQUIRE(h, prompt_emb && idx && pd && pv && t_in, "pe_special_blend_scatter: null pointer");
+    PE_REQUIRE(h, C > 0 && C % 8 == 0 && max_rows > 0, "pe_special_blend_scatter: bad sizes");
+    // Python evaluates (t_max - t_min + 1e-6) in double; ATen then multiplies by float(1/that)
+    const float inv_range = (float)(1.0 / ((double)t_max - (double)t_min + 1e-6));
+    special_blend_scatter_kernel<<<max_rows, 128, 0, s>>>(static_cast<bf16*>(prompt_emb), idx, C, static_cast<const bf16*>(pd),
+                                                          static_cast<const bf16*>(pv), static_cast<const bf16*>(t_in), t_min, inv_range);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int add_bias_rows_run(Handle* h, void* x, const void* add, int rows, int C, int period, float alpha, cudaStream_t s) {
+    PE_REQUIRE(h, x && add && rows > 0 && C > 0 && C % 8 == 0 && period > 0, "pe_add_rows: bad arguments");
+    const long long n = (long long)rows * (C / 8);
+    add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<bf16*>(x), static_cast<const bf16*>(add), rows, C, period, alpha);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+}  // namespace pe

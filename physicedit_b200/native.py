@@ -1,0 +1,248 @@
+"""ctypes binding of libpe_b200.so (the C ABI declared in include/pe_b200.h).
+
+PyTorch is used only for device memory and streams: every function here takes torch CUDA tensors,
+checks dtype / contiguity, and passes raw device pointers + sizes + the current stream to the
+library.  There is no fallback: if the shared library is missing or the device is not sm_100 the
+import of the native path fails loudly (`NativeUnavailable`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint, c_uint8, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpe_b200.so")
+
+PE_OK = 0
+EPI_BIAS = 0
+EPI_BIAS_GELU_SIGMOID = 2
+EPI_BIAS_GELU_ERF = 3
+EPI_GATE_RESIDUAL = 4
+EPI_QKV_NORM_ROPE = 5
+EPI_BIAS_SILU = 6
+GEMM_FLAG_CTA_PAIR = 1
+ATTN_FLAG_SINGLE_Q_TILE = 1
+ATTN_FLAG_P_VIA_SMEM = 2
+ATTN_FLAG_SWAP_V_DESC = 4
+
+EXPORTED_SYMBOLS = [
+    "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count",
+    "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm", "pe_add_rows",
+    "pe_rmsnorm", "pe_gemv", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
+    "pe_special_gather", "pe_special_blend_scatter",
+]
+
+
+class NativeUnavailable(RuntimeError):
+    pass
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class GemmSeg(Structure):
+    """Mirror of `pe_gemm_seg` (include/pe_b200.h)."""
+    _fields_ = [
+        ("a", c_void_p), ("lda", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
+        ("M", c_int32), ("_pad0", c_int32), ("gate", c_void_p), ("out_k", c_void_p), ("out_v", c_void_p),
+        ("norm_q_w", c_void_p), ("norm_k_w", c_void_p), ("rope", c_void_p),
+    ]
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    path = path or _LIB_PATH
+    if not os.path.exists(path):
+        raise NativeUnavailable(
+            f"{path} not found: build it with physicedit_b200/csrc/build.sh (or __graft_entry__.build()); "
+            "there is no CPU / PyTorch fallback for the hot path")
+    lib = ctypes.CDLL(path)
+    lib.pe_last_error.restype = c_char_p
+    lib.pe_last_error.argtypes = [c_void_p]
+    lib.pe_create.argtypes = [POINTER(c_void_p), c_int]
+    lib.pe_destroy.argtypes = [c_void_p]
+    lib.pe_sm_count.argtypes = [c_void_p]
+    lib.pe_check_async_error.argtypes = [c_void_p, c_void_p, POINTER(c_uint)]
+    lib.pe_gemm.argtypes = [c_void_p, POINTER(GemmSeg), c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.pe_attention_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p]
+    lib.pe_small_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_int64, c_int64, c_int64, c_float, c_void_p]
+    lib.pe_layernorm_modulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pe_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]
+    lib.pe_add_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_rmsnorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p]
+    lib.pe_gemv.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.pe_timestep_embedding.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pe_patchify.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.pe_unpatchify.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]
+    lib.pe_cfg_euler_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]
+    lib.pe_special_gather.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    lib.pe_special_blend_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _bf16(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise NativeError(f"{name}: expected a CUDA bfloat16 tensor, got {t.dtype} on {t.device}")
+    if t.stride(-1) != 1:
+        raise NativeError(f"{name}: innermost stride must be 1")
+    return t
+
+
+class Native:
+    """One handle per device.  All methods enqueue on torch's current stream and return."""
+
+    _instances: dict = {}
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise NativeUnavailable("no CUDA device: the physicedit_b200 hot path has no CPU fallback")
+        self.lib = load_library()
+        self.device = int(device)
+        h = c_void_p()
+        rc = self.lib.pe_create(byref(h), self.device)
+        if rc != PE_OK:
+            raise NativeUnavailable(f"pe_create(device={device}) failed with {rc} (needs an sm_100 GPU)")
+        self.h = h
+        self.sm_count = self.lib.pe_sm_count(self.h)
+        self.launches = 0      # number of kernels of this library enqueued (bench.py reports it)
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Native":
+        dev = int(device)
+        if dev not in cls._instances:
+            cls._instances[dev] = Native(dev)
+        return cls._instances[dev]
+
+    # -------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != PE_OK:
+            raise NativeError(f"{what} failed ({rc}): {self.lib.pe_last_error(self.h).decode()}")
+
+    def check_async(self) -> None:
+        diag = c_uint(0)
+        self._check(self.lib.pe_check_async_error(self.h, self._stream(), byref(diag)), "pe_check_async_error")
+
+    # -------------------------------------------------------------------------------------------
+    def gemm(self, segs: Sequence[dict], N: int, K: int, epilogue: int = EPI_BIAS, flags: int = 0) -> None:
+        """segs: dicts with a [M,K], w [N,K], bias [N]|None, out [M,*] and the epilogue extras."""
+        arr = (GemmSeg * len(segs))()
+        for i, s in enumerate(segs):
+            a = _bf16(s["a"], "a")
+            out = _bf16(s["out"], "out")
+            w = _bf16(s["w"], "w")
+            if not w.is_contiguous():
+                raise NativeError("w must be contiguous [N, K]")
+            g = arr[i]
+            g.a, g.lda, g.w, g.bias = a.data_ptr(), a.stride(0), w.data_ptr(), _ptr(s.get("bias"))
+            g.out, g.ldo, g.M = out.data_ptr(), out.stride(0), a.shape[0]
+            g.gate, g.out_k, g.out_v = _ptr(s.get("gate")), _ptr(s.get("out_k")), _ptr(s.get("out_v"))
+            g.norm_q_w, g.norm_k_w, g.rope = _ptr(s.get("norm_q_w")), _ptr(s.get("norm_k_w")), _ptr(s.get("rope"))
+        self._check(self.lib.pe_gemm(self.h, arr, len(segs), N, K, epilogue, flags, self._stream()), "pe_gemm")
+        self.launches += 1
+
+    def linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = EPI_BIAS, flags: int = 0) -> torch.Tensor:
+        out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        self.gemm([dict(a=x, w=w, bias=bias, out=out)], w.shape[0], w.shape[1], epilogue, flags)
+        return out
+
+    def attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, H: int, scale: float, flags: int = 0) -> None:
+        """q, k, v, o: [S, >= H*128] token-major with a common row stride."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+            _bf16(t, n)
+            if t.stride(0) != q.stride(0):
+                raise NativeError("q, k, v, o must share one row stride")
+        self._check(self.lib.pe_attention_fwd(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), q.shape[0], H,
+                                              q.stride(0), scale, flags, self._stream()), "pe_attention_fwd")
+        self.launches += 1
+
+    def small_attention(self, q, k, v, o, B: int, H: int, Sq: int, Skv: int, D: int, scale: float) -> None:
+        """q: [B*Sq, ldq], k/v: [B*Skv, ldkv] (same stride), o: [B*Sq, ldo]; head h lives at columns [h*D, (h+1)*D)."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+            _bf16(t, n)
+        if k.stride(0) != v.stride(0):
+            raise NativeError("k and v must share one row stride")
+        self._check(self.lib.pe_small_attention(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, Sq, Skv, D,
+                                                q.stride(0), k.stride(0), o.stride(0), scale, self._stream()), "pe_small_attention")
+        self.launches += 1
+
+    def layernorm_modulate(self, x, out, shift, one_plus_scale) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        if not (x.is_contiguous() and out.is_contiguous()):
+            raise NativeError("layernorm_modulate: x / out must be contiguous")
+        self._check(self.lib.pe_layernorm_modulate(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], shift.data_ptr(),
+                                                   one_plus_scale.data_ptr(), self._stream()), "pe_layernorm_modulate")
+        self.launches += 1
+
+    def layernorm(self, x, out, w=None, b=None, eps: float = 1e-5) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        self._check(self.lib.pe_layernorm(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ptr(w), _ptr(b), eps,
+                                          self._stream()), "pe_layernorm")
+        self.launches += 1
+
+    def add_rows(self, x, add, period: int, alpha: float = 1.0) -> None:
+        _bf16(x, "x"); _bf16(add, "add")
+        self._check(self.lib.pe_add_rows(self.h, x.data_ptr(), add.data_ptr(), x.shape[0], x.shape[1], period, alpha, self._stream()),
+                    "pe_add_rows")
+        self.launches += 1
+
+    def rmsnorm(self, x, out, w, eps: float = 1e-6) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        self._check(self.lib.pe_rmsnorm(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ptr(w), eps, self._stream()),
+                    "pe_rmsnorm")
+        self.launches += 1
+
+    def gemv(self, x, w, bias, y, act_in: int = 0, act_out: int = 0, one_plus_mask=None) -> None:
+        """x [batch, K], w [N, K], y [batch, N]."""
+        _bf16(x, "x"); _bf16(w, "w"); _bf16(y, "y")
+        batch = 1 if x.dim() == 1 else x.shape[0]
+        self._check(self.lib.pe_gemv(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1],
+                                     act_in, act_out, _ptr(one_plus_mask), self._stream()), "pe_gemv")
+        self.launches += 1
+
+    def timestep_embedding(self, t_in, out) -> None:
+        _bf16(t_in, "t_in"); _bf16(out, "out")
+        self._check(self.lib.pe_timestep_embedding(self.h, t_in.data_ptr(), out.data_ptr(), self._stream()), "pe_timestep_embedding")
+        self.launches += 1
+
+    def patchify(self, latents, tokens) -> None:
+        """latents [16, H8, W8] contiguous -> tokens [(H8/2)*(W8/2), 64] contiguous."""
+        _bf16(latents, "latents"); _bf16(tokens, "tokens")
+        self._check(self.lib.pe_patchify(self.h, latents.data_ptr(), tokens.data_ptr(), latents.shape[-2], latents.shape[-1],
+                                         self._stream()), "pe_patchify")
+        self.launches += 1
+
+    def unpatchify(self, tokens, latents) -> None:
+        _bf16(latents, "latents"); _bf16(tokens, "tokens")
+        self._check(self.lib.pe_unpatchify(self.h, tokens.data_ptr(), tokens.stride(0), latents.data_ptr(), latents.shape[-2],
+                                           latents.shape[-1], self._stream()), "pe_unpatchify")
+        self.launches += 1
+
+    def cfg_euler_step(self, latents, posi, nega, cfg_scale: float, dsigma: float) -> None:
+        _bf16(latents, "latents"); _bf16(posi, "posi")
+        self._check(self.lib.pe_cfg_euler_step(self.h, latents.data_ptr(), posi.data_ptr(), _ptr(nega), latents.numel(), cfg_scale,
+                                               dsigma, self._stream()), "pe_cfg_euler_step")
+        self.launches += 1
+
+    def special_gather(self, prompt_emb, mask_u8, dst, idx) -> None:
+        _bf16(prompt_emb, "prompt_emb"); _bf16(dst, "dst")
+        self._check(self.lib.pe_special_gather(self.h, prompt_emb.data_ptr(), mask_u8.data_ptr(), prompt_emb.shape[0], prompt_emb.shape[1],
+                                               dst.data_ptr(), idx.data_ptr(), dst.shape[0], self._stream()), "pe_special_gather")
+        self.launches += 2
+
+    def special_blend_scatter(self, prompt_emb, idx, pred_dino, pred_vae, t_in, t_min: float, t_max: float) -> None:
+        _bf16(prompt_emb, "prompt_emb")
+        self._check(self.lib.pe_special_blend_scatter(self.h, prompt_emb.data_ptr(), idx.data_ptr(), pred_dino.shape[0], prompt_emb.shape[1],
+                                                      pred_dino.data_ptr(), pred_vae.data_ptr(), t_in.data_ptr(), t_min, t_max,
+                                                      self._stream()), "pe_special_blend_scatter")
+        self.launches += 1
