@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoise steps/s of a 1024x1024 Qwen-Image-Edit / PhysicEdit edit (BASELINE.json).
+
+One "step" = one denoise step of the reference loop (qwen_image_physical.py:648-661): TWO DiT forwards
+(CFG 4.0: posi T=512, nega T=288; 4096 noise + 4096 edit-image tokens, 60 blocks, adapter on the 64 special
+tokens) + CFG combine + Euler update.  Weights are random-init bf16 of the real architecture, inputs synthetic.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework (CUDA path through libpe_b200.so)
+    python bench.py --impl reference ...                      # the reference algorithm on the host CPU (oracle port)
+
+Under torchrun (--gpus N) every rank denoises its own image (one image per GPU, no per-step collective); value is
+the whole-job steps/s, timed on the device with CUDA events between barriers, max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, LAYERS = 3072, 60
+T_POSI, T_NEGA = 512, 288
+
+
+def flops_forward(S_img, T, layers=LAYERS):
+    S = S_img + T
+    return layers * (24 * DIM * DIM * S + 4 * S * S * DIM + 24 * DIM * DIM) + 2 * S_img * 64 * DIM * 2 + 2 * T * 3584 * DIM
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def build_model(device, layers, seed=0):
+    """Random-init bf16 weights of the real architecture, generated on the device (uniform, PyTorch-default bound)."""
+    from physicedit_b200.dit import QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=layers)
+    sd = {}
+    for k, v in dit.state_dict().items():
+        if v.dim() == 2:
+            b = 1.0 / math.sqrt(v.shape[1])
+            t = (torch.rand(v.shape, generator=g, device=device, dtype=torch.float32) * 2 - 1) * b
+        elif k.endswith(".bias"):
+            t = (torch.rand(v.shape, generator=g, device=device, dtype=torch.float32) * 2 - 1) * 0.02
+        else:
+            t = torch.ones(v.shape, device=device)
+        sd[k] = t.to(torch.bfloat16)
+    dit.load_state_dict(sd, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    for i, b in enumerate(dit.transformer_blocks):
+        object.__setattr__(b, "_owner", (dit, i))
+    dit.eval()
+    pipe = QwenImagePhysicPipeline(device=device, torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    for p in pipe.visual_thinking_adapter.parameters():
+        b = 1.0 / math.sqrt(p.shape[-1]) if p.dim() == 2 else 0.02
+        p.data = ((torch.rand(p.shape, generator=g, device=device, dtype=torch.float32) * 2 - 1) * b).to(torch.bfloat16)
+    return pipe
+
+
+def host_inputs(height, width, seed):
+    """Pinned host buffers of one edit request (what a serving front-end would hand over)."""
+    from oracle.dit_oracle import synth_inputs        # input recipe only (shapes / seeds); no oracle arithmetic
+    posi = synth_inputs(height, width, T_POSI, seed=seed, dtype=torch.bfloat16, edit_hw=(1024, 1024))
+    nega = synth_inputs(height, width, T_NEGA, seed=seed + 1, dtype=torch.bfloat16, edit_hw=(1024, 1024))
+    host = dict(latents=posi["latents"], edit_latents=posi["edit_latents"], pe_posi=posi["prompt_emb"], pe_nega=nega["prompt_emb"],
+                mask_posi=posi["prompt_emb_mask"], mask_nega=nega["prompt_emb_mask"], sp_posi=posi["special_token_mask"], sp_nega=nega["special_token_mask"])
+    return {k: v.pin_memory() for k, v in host.items()}
+
+
+def run_native(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from physicedit_b200 import native as nv
+    from physicedit_b200 import parallel
+    nat = nv.Native.get(local)            # raises NativeUnavailable when libpe_b200.so / an sm_100 GPU is missing
+    H = W = args.resolution
+    pipe = build_model(device, args.layers, seed=0)
+    if world > 1:
+        parallel.broadcast_weights(pipe, src=0)          # the one start-up collective: rank 0's weights to every GPU over NVLink
+    eng = pipe.dit.engine()
+    eng.use_cta_pair = not args.no_cta_pair
+    host = host_inputs(H, W, seed=100 + rank)             # a different image per rank
+    dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+    ip = dict(prompt_emb=dev["pe_posi"], prompt_emb_mask=dev["mask_posi"], special_token_mask=dev["sp_posi"])
+    in_ = dict(prompt_emb=dev["pe_nega"], prompt_emb_mask=dev["mask_nega"], special_token_mask=dev["sp_nega"])
+    sched = pipe.scheduler
+    sched.set_timesteps(50, dynamic_shift_len=(H // 16) * (W // 16))
+    ts_dev = sched.timesteps.to(torch.bfloat16).to(device)
+    vp, vn = torch.empty_like(dev["latents"]), torch.empty_like(dev["latents"])
+    lat = dev["latents"].clone()
+
+    def one_step(i, latents):
+        pid = i % 50
+        t_host = float(sched.timesteps[pid].to(torch.bfloat16))
+        kw = dict(dit=pipe.dit, visual_thinking_adapter=pipe.visual_thinking_adapter, latents=latents, timestep=ts_dev[pid:pid + 1], height=H, width=W,
+                  edit_latents=dev["edit_latents"], is_train=False, timestep_host=t_host)
+        pipe.model_fn(**kw, **ip, out=vp)
+        pipe.model_fn(**kw, **in_, out=vn)
+        nat.cfg_euler_step(latents, vp, vn, 4.0, float(sched.dsigma(sched.timesteps[pid])))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i, lat)
+    nat.check_async()
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = nat.launches
+    nat.prof = {} if not args.no_kernel_events else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(args.warmup + i, lat)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = nat.launches - l0
+    prof = nat.profile_summary()
+    nat.prof = None
+    nat.check_async()
+    finite = bool(torch.isfinite(lat.float()).all().item())
+
+    # ---- end to end through the public API with host buffers (e2e) ----
+    h_lat = host["latents"].clone().pin_memory()
+    d_in = {k: torch.empty_like(v, device=device) for k, v in host.items()}
+    e2e_steps = max(2, min(args.steps, 4))
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(e2e_steps):
+        for k in ("latents", "edit_latents", "pe_posi", "pe_nega", "mask_posi", "mask_nega", "sp_posi", "sp_nega"):
+            d_in[k].copy_(h_lat if k == "latents" else host[k], non_blocking=True)
+        ipe = dict(prompt_emb=d_in["pe_posi"], prompt_emb_mask=d_in["mask_posi"], special_token_mask=d_in["sp_posi"])
+        ine = dict(prompt_emb=d_in["pe_nega"], prompt_emb_mask=d_in["mask_nega"], special_token_mask=d_in["sp_nega"])
+        out = pipe.denoise_step(d_in["latents"], ipe, ine, d_in["edit_latents"], progress_id=i % 50, height=H, width=W, cfg_scale=4.0)
+        h_lat.copy_(out, non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+    d2h = h_lat.numel() * h_lat.element_size()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    S_img = (H // 16) * (W // 16) + 4096
+    fl_step = flops_forward(S_img, T_POSI, args.layers) + flops_forward(S_img, T_NEGA, args.layers)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    # dominant kernel: the MLP up-projection GEMM (tcgen05): algorithmic FLOPs per launch / mean launch duration
+    roof = None
+    if prof.get("gemm_up"):
+        n, tot = prof["gemm_up"]
+        S_avg = S_img + (T_POSI + T_NEGA) / 2
+        fl = 2 * S_avg * DIM * 4 * DIM
+        ach = fl / (tot / n * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_kernel<cta_pair, bias+gelu> (MLP up-projection, M=S N=12288 K=3072)", "achieved": round(ach, 1),
+                "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
+                "frac": round(ach / peak_tf, 4), "traffic": None, "launches": n, "avg_ms": round(tot / n, 4),
+                "whole_step_frac": round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)}
+    shares = {k: round(v[1] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    res = {
+        "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(world * args.steps / (ms * 1e-3), 4), "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights of the real architecture, seeded inputs)",
+        "config": {"workload": f"{H}x{W} single-image edit, 50-step schedule, bf16, {args.layers} blocks, 4096 edit tokens, T=512/288, one image per GPU",
+                   "l2": "inputs larger than L2: 40.8 GB of weights stream per forward", "images_per_sec_50_steps": round(world * args.steps / (ms * 1e-3) / 50, 5),
+                   "tflops_per_step": round(fl_step / 1e12, 2), "achieved_tflops_per_gpu": round(fl_step * args.steps / (ms * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(world * e2e_steps / (ms_e2e * 1e-3), 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches, "finite": finite, "clocks": clocks, "roofline": roof, "kernel_time_share": shares,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, blocks=1):
+    """The reference algorithm (oracle port, torch CPU bf16 like the reference's own CPU path) on the host cores:
+    `blocks` of the 60 blocks of ONE posi forward at the benchmark's sequence length, extrapolated to a full CFG step."""
+    from oracle import dit_oracle as O
+    torch.manual_seed(0)
+    H = W = args.resolution
+    S_img = (H // 16) * (W // 16) + 4096
+    shapes = {k: v for k, v in O.dit_param_shapes(1).items() if k.startswith("transformer_blocks.0.")}
+    Wt = O.synth_weights(shapes, seed=0, dtype=torch.bfloat16)
+    image = torch.randn(1, S_img, DIM).bfloat16()
+    text = torch.randn(1, T_POSI, DIM).bfloat16()
+    temb = torch.randn(1, DIM).bfloat16()
+    rope = O.rope_tables([(1, H // 16, W // 16), (1, 64, 64)], T_POSI)
+    t0 = time.time()
+    with torch.no_grad():
+        for _ in range(blocks):
+            O.block_forward(Wt, 0, image, text, temb, rope)
+    dt = (time.time() - t0) / blocks
+    frac_nega = flops_forward(S_img, T_NEGA) / flops_forward(S_img, T_POSI)
+    step_s = dt * LAYERS * (1 + frac_nega)
+    return {"value": round(1.0 / step_s, 6), "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{blocks} of 60 blocks of one posi forward (S={S_img + T_POSI}) in bf16 on CPU: {dt:.2f} s/block, extrapolated x60 x(1+{frac_nega:.3f})"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    vals = []
+    for i in range(args.warmup_ref + args.steps_ref):
+        cb = cpu_baseline(args, blocks=1)
+        if i >= args.warmup_ref:
+            vals.append(cb)
+    v = sum(c["value"] for c in vals) / len(vals)
+    cb = dict(vals[-1]); cb["value"] = round(v, 6)
+    H = W = args.resolution
+    res = {"impl": "reference", "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(v, 6), "unit": "steps/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 / v, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"{H}x{W} single-image edit, 50-step schedule, bf16, 60 blocks, 4096 edit tokens, T=512/288; CPU sample: one block per step, extrapolated"},
+           "cpu_baseline": cb, "e2e": {"value": round(v, 6), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(res), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--resolution", type=int, default=1024)
+    ap.add_argument("--layers", type=int, default=LAYERS)
+    ap.add_argument("--no-cta-pair", action="store_true")
+    ap.add_argument("--no-kernel-events", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=2)
+    ap.add_argument("--warmup-ref", dest="warmup_ref", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,12 @@ int pe_small_attention(pe_handle_t h, const void* q, const void* k, const void* 
  *   shift / one_plus_scale: bf16 [C] (one_plus_scale already holds bf16(1+scale)). */
 int pe_layernorm_modulate(pe_handle_t h, const void* x, void* out, int rows, int C,
                           const void* shift, const void* one_plus_scale, void* stream);
+/* same over a joint [text; image] token buffer: rows [0, split_row) use (shift0, one_plus_scale0) (txt_mod),
+ * rows [split_row, rows) use (shift1, one_plus_scale1) (img_mod) -- one launch for both streams of
+ * QwenImageTransformerBlock.forward (qwen_image_dit.py:378-383, 389-393). */
+int pe_layernorm_modulate2(pe_handle_t h, const void* x, void* out, int rows, int C, int split_row,
+                           const void* shift0, const void* one_plus_scale0,
+                           const void* shift1, const void* one_plus_scale1, void* stream);
 /* nn.LayerNorm: out = bf16(LN(x) * w + b) (helpers.py:13,27-28,98; DINOv2 blocks); w = b = NULL gives the
  * non-affine LN of Dinov2withNorm (dinov2.py:20-24). */
 int pe_layernorm(pe_handle_t h, const void* x, void* out, int rows, int C, const void* w, const void* b,
@@ -143,9 +149,10 @@ int pe_gemv(pe_handle_t h, const void* x, const void* w, const void* bias, void*
             int act_in, int act_out, const uint8_t* one_plus_mask, void* stream);
 
 /* sinusoidal timestep embedding with the reference's bf16 quirks (utils.py:189-216):
- *   t_in: bf16 [1] (already bf16(t)); computes ts = bf16(t_in/1000) on device, then
+ *   t_in: bf16 [1].  raw != 0: t_in is the loop's bf16(t) and ts = bf16(t_in/1000) is formed on device with
+ *   ATen's CUDA rounding (qwen_image_physical.py:1342); raw == 0: t_in already holds ts (TimestepEmbeddings.forward). Then
  *   out[0:128]=cos(1000*ts*f_i), out[128:256]=sin(...), f_i = bf16(exp(-ln(1e4) i/128)); out bf16 [256]. */
-int pe_timestep_embedding(pe_handle_t h, const void* t_in, void* out, void* stream);
+int pe_timestep_embedding(pe_handle_t h, const void* t_in, void* out, int raw, void* stream);
 
 /* patchify: latents bf16 [16, H8, W8] -> tokens [ (H8/2)*(W8/2), 64 ], channel order (c, p, q)
  *   replaces rearrange "B C (H P) (W Q) -> B (H W) (C P Q)" (qwen_image_physical.py:1344,1354). */

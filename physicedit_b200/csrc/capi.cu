@@ -42,10 +42,12 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
                   int flags, cudaStream_t stream);
 int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C, const void* shift, const void* ops, cudaStream_t s);
+int layernorm_modulate2_run(Handle* h, const void* x, void* out, int rows, int C, int split_row, const void* shift0, const void* ops0,
+                            const void* shift1, const void* ops1, cudaStream_t s);
 int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, float eps, cudaStream_t s);
 int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
              int act_out, const uint8_t* one_plus_mask, cudaStream_t s);
-int timestep_embedding_run(Handle* h, const void* t_in, void* out, cudaStream_t s);
+int timestep_embedding_run(Handle* h, const void* t_in, void* out, int raw, cudaStream_t s);
 int patchify_run(Handle* h, const void* latents, void* tokens, int H8, int W8, cudaStream_t s);
 int unpatchify_run(Handle* h, const void* tokens, int64_t ld, void* latents, int H8, int W8, cudaStream_t s);
 int cfg_euler_run(Handle* h, void* latents, const void* posi, const void* nega, int64_t n, float cfg, float dsigma, cudaStream_t s);
@@ -154,6 +156,13 @@ int pe_layernorm_modulate(pe_handle_t hh, const void* x, void* out, int rows, in
     return pe::layernorm_modulate_run(h, x, out, rows, C, shift, one_plus_scale, static_cast<cudaStream_t>(stream));
 }
 
+int pe_layernorm_modulate2(pe_handle_t hh, const void* x, void* out, int rows, int C, int split_row, const void* shift0,
+                           const void* one_plus_scale0, const void* shift1, const void* one_plus_scale1, void* stream) {
+    PE_H(hh);
+    return pe::layernorm_modulate2_run(h, x, out, rows, C, split_row, shift0, one_plus_scale0, shift1, one_plus_scale1,
+                                       static_cast<cudaStream_t>(stream));
+}
+
 int pe_layernorm(pe_handle_t hh, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, void* stream) {
     PE_H(hh);
     return pe::layernorm_affine_run(h, x, out, rows, C, w, b, eps, static_cast<cudaStream_t>(stream));
@@ -175,9 +184,9 @@ int pe_gemv(pe_handle_t hh, const void* x, const void* w, const void* bias, void
     return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, act_out, one_plus_mask, static_cast<cudaStream_t>(stream));
 }
 
-int pe_timestep_embedding(pe_handle_t hh, const void* t_in, void* out, void* stream) {
+int pe_timestep_embedding(pe_handle_t hh, const void* t_in, void* out, int raw, void* stream) {
     PE_H(hh);
-    return pe::timestep_embedding_run(h, t_in, out, static_cast<cudaStream_t>(stream));
+    return pe::timestep_embedding_run(h, t_in, out, raw, static_cast<cudaStream_t>(stream));
 }
 
 int pe_patchify(pe_handle_t hh, const void* latents, void* tokens, int H8, int W8, void* stream) {

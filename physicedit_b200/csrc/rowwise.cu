@@ -43,9 +43,11 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
 // -------------------------------------------------------------------------------------------------
 template <int kVec, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int rows, int C,
-                                                                       const bf16* __restrict__ p0, const bf16* __restrict__ p1, float eps) {
+                                                                       const bf16* __restrict__ p0, const bf16* __restrict__ p1, float eps,
+                                                                       int split_row, const bf16* __restrict__ q0, const bf16* __restrict__ q1) {
     const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (MODE == 0 && row >= split_row) { p0 = q0; p1 = q1; }   // second token stream has its own modulation vectors
     const int lane = threadIdx.x & 31;
     const int nvec = C >> 3;
     const bf16* xr = x + (size_t)row * C;
@@ -103,7 +105,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16
 }
 
 template <int MODE>
-int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const void* p0, const void* p1, float eps, cudaStream_t s) {
+int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const void* p0, const void* p1, float eps, cudaStream_t s,
+                     int split_row = 0x7fffffff, const void* r0 = nullptr, const void* r1 = nullptr) {
     PE_REQUIRE(h, rows > 0 && C > 0 && C % 8 == 0 && C <= 4096, "layernorm: need rows>0, C%%8==0, C<=4096 (rows=%d C=%d)", rows, C);
     PE_REQUIRE(h, x && out, "layernorm: null pointer");
     const dim3 grid(ceil_div(rows, kWarpsPerCta)), block(kWarpsPerCta * 32);
@@ -111,10 +114,12 @@ int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const
     bf16* ob = static_cast<bf16*>(out);
     const bf16* a = static_cast<const bf16*>(p0);
     const bf16* b = static_cast<const bf16*>(p1);
-    if (C <= 256) layernorm_kernel<1, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
-    else if (C <= 1024) layernorm_kernel<4, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
-    else if (C <= 3072) layernorm_kernel<12, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
-    else layernorm_kernel<16, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps);
+    const bf16* q0 = static_cast<const bf16*>(r0);
+    const bf16* q1 = static_cast<const bf16*>(r1);
+    if (C <= 256) layernorm_kernel<1, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
+    else if (C <= 1024) layernorm_kernel<4, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
+    else if (C <= 3072) layernorm_kernel<12, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
+    else layernorm_kernel<16, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }
@@ -223,10 +228,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
 // -------------------------------------------------------------------------------------------------
 // timestep sinusoid with the reference's bf16 quirks (models/utils.py:189-216)
 // -------------------------------------------------------------------------------------------------
-__global__ void timestep_embedding_kernel(const bf16* __restrict__ t_in, bf16* __restrict__ out) {
+__global__ void timestep_embedding_kernel(const bf16* __restrict__ t_in, bf16* __restrict__ out, int raw) {
     const int i = threadIdx.x;   // 0..127
     // timestep / 1000 on a bf16 CUDA tensor = bf16( float(t) * float(1/1000.) )  (ATen div-by-scalar)
-    const float ts = bf16_round(__bfloat162float(t_in[0]) * (float)(1.0 / 1000.0));
+    const float t0 = __bfloat162float(t_in[0]);
+    const float ts = raw ? bf16_round(t0 * (float)(1.0 / 1000.0)) : t0;
     const float exponent = __fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), 128.0f);
     const float freq = bf16_round(expf(exponent));        // align_dtype_to_timestep: freqs rounded to bf16
     const float arg = __fmul_rn(1000.0f, __fmul_rn(ts, freq));
@@ -363,6 +369,13 @@ int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C,
     return launch_layernorm<0>(h, x, out, rows, C, shift, ops, 1e-6f, s);
 }
 
+int layernorm_modulate2_run(Handle* h, const void* x, void* out, int rows, int C, int split_row, const void* shift0, const void* ops0,
+                            const void* shift1, const void* ops1, cudaStream_t s) {
+    PE_REQUIRE(h, shift0 && ops0 && shift1 && ops1, "pe_layernorm_modulate2: modulation vectors must not be null");
+    PE_REQUIRE(h, split_row >= 0 && split_row <= rows, "pe_layernorm_modulate2: split_row out of range");
+    return launch_layernorm<0>(h, x, out, rows, C, shift0, ops0, 1e-6f, s, split_row, shift1, ops1);
+}
+
 int layernorm_affine_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, cudaStream_t s) {
     if (w == nullptr && b == nullptr) return launch_layernorm<2>(h, x, out, rows, C, nullptr, nullptr, eps, s);
     PE_REQUIRE(h, w && b, "pe_layernorm: weight and bias must both be given or both be null");
@@ -412,9 +425,9 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
     return PE_OK;
 }
 
-int timestep_embedding_run(Handle* h, const void* t_in, void* out, cudaStream_t s) {
+int timestep_embedding_run(Handle* h, const void* t_in, void* out, int raw, cudaStream_t s) {
     PE_REQUIRE(h, t_in && out, "pe_timestep_embedding: null pointer");
-    timestep_embedding_kernel<<<1, 128, 0, s>>>(static_cast<const bf16*>(t_in), static_cast<bf16*>(out));
+    timestep_embedding_kernel<<<1, 128, 0, s>>>(static_cast<const bf16*>(t_in), static_cast<bf16*>(out), raw);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

@@ -1,0 +1,442 @@
+"""Qwen-Image-Edit DiT with the reference's exact module / parameter layout, executed by libpe_b200.
+
+Mirrors DiffSynth-Studio/diffsynth/models/qwen_image_dit.py (QwenImageDiT, QwenImageTransformerBlock,
+QwenDoubleStreamAttention, QwenFeedForward, ApproximateGELU, QwenEmbedRope) and models/utils.py
+(RMSNorm, AdaLayerNorm, TimestepEmbeddings): identical attribute names and parameter shapes, so
+`state_dict()` hashes to the registry value 0319a1cb19835fb510907dd3367c95ff
+(configs/model_config.py:21) and the reference's loader, LoRA loader, PEFT injection and checkpoints
+work unchanged.  The arithmetic never runs through torch ops: `DiTEngine` drives the C-ABI kernels
+(9 launches per block instead of ~70 ATen launches).  bf16 on an sm_100 GPU only -- no fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import native as nv
+
+DIM = 3072
+NUM_HEADS = 24
+HEAD_DIM = 128
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names / shapes as the reference)
+# ------------------------------------------------------------------------------------------------
+class RMSNorm(nn.Module):
+    """models/utils.py:241-257."""
+
+    def __init__(self, dim, eps, elementwise_affine=True):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones((dim,))) if elementwise_affine else None
+
+    def forward(self, hidden_states):
+        nat = nv.Native.get(hidden_states.device.index or 0)
+        x = hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous()
+        out = torch.empty_like(x)
+        nat.rmsnorm(x, out, self.weight, self.eps)
+        return out.view(hidden_states.shape)
+
+
+class _TimestepProj(nn.Module):
+    """_DiffusersCompatibleTimestepProj (models/utils.py:259-271)."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.linear_1 = nn.Linear(dim_in, dim_out)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(dim_out, dim_out)
+
+
+class TimestepEmbeddings(nn.Module):
+    """models/utils.py:274-293 with flip_sin_to_cos, scale=1000, align_dtype_to_timestep (qwen_image_dit.py:413)."""
+
+    def __init__(self, dim_in=256, dim_out=DIM):
+        super().__init__()
+        self.timestep_embedder = _TimestepProj(dim_in, dim_out)
+
+    def forward(self, timestep: torch.Tensor, dtype=torch.bfloat16, raw: bool = False) -> torch.Tensor:
+        """timestep: bf16 [1] holding t/1000 as in the reference (raw=False), or the loop's bf16(t) with the
+        division fused into the kernel (raw=True).  Returns temb [1, 3072]."""
+        nat = nv.Native.get(timestep.device.index or 0)
+        dev = timestep.device
+        sinus = torch.empty(256, dtype=torch.bfloat16, device=dev)
+        nat.timestep_embedding(timestep, sinus, raw)
+        h = torch.empty(1, DIM, dtype=torch.bfloat16, device=dev)
+        te = self.timestep_embedder
+        nat.gemv(sinus.view(1, 256), te.linear_1.weight, te.linear_1.bias, h, 0, 1)
+        out = torch.empty(1, DIM, dtype=torch.bfloat16, device=dev)
+        nat.gemv(h, te.linear_2.weight, te.linear_2.bias, out, 0, 0)
+        return out
+
+
+class AdaLayerNorm(nn.Module):
+    """models/utils.py:296-309, single=True: linear(silu(emb)) -> (scale, shift)."""
+
+    def __init__(self, dim, single=True):
+        super().__init__()
+        assert single
+        self.single = True
+        self.linear = nn.Linear(dim, dim * 2)
+        self.norm = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+
+
+class ApproximateGELU(nn.Module):
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out, bias=bias)
+
+
+class QwenFeedForward(nn.Module):
+    def __init__(self, dim, dim_out=None, dropout=0.0):
+        super().__init__()
+        inner = int(dim * 4)
+        self.net = nn.ModuleList([ApproximateGELU(dim, inner), nn.Dropout(dropout), nn.Linear(inner, dim_out)])
+
+
+class QwenDoubleStreamAttention(nn.Module):
+    def __init__(self, dim_a, dim_b, num_heads, head_dim):
+        super().__init__()
+        self.num_heads, self.head_dim = num_heads, head_dim
+        self.to_q = nn.Linear(dim_a, dim_a)
+        self.to_k = nn.Linear(dim_a, dim_a)
+        self.to_v = nn.Linear(dim_a, dim_a)
+        self.norm_q = RMSNorm(head_dim, eps=1e-6)
+        self.norm_k = RMSNorm(head_dim, eps=1e-6)
+        self.add_q_proj = nn.Linear(dim_b, dim_b)
+        self.add_k_proj = nn.Linear(dim_b, dim_b)
+        self.add_v_proj = nn.Linear(dim_b, dim_b)
+        self.norm_added_q = RMSNorm(head_dim, eps=1e-6)
+        self.norm_added_k = RMSNorm(head_dim, eps=1e-6)
+        self.to_out = nn.Sequential(nn.Linear(dim_a, dim_a))
+        self.to_add_out = nn.Linear(dim_b, dim_b)
+
+
+class QwenImageTransformerBlock(nn.Module):
+    def __init__(self, dim, num_attention_heads, attention_head_dim, eps=1e-6):
+        super().__init__()
+        self.dim, self.num_attention_heads, self.attention_head_dim = dim, num_attention_heads, attention_head_dim
+        self.img_mod = nn.Sequential(nn.SiLU(), nn.Linear(dim, 6 * dim))
+        self.img_norm1 = nn.LayerNorm(dim, elementwise_affine=False, eps=eps)
+        self.attn = QwenDoubleStreamAttention(dim, dim, num_attention_heads, attention_head_dim)
+        self.img_norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=eps)
+        self.img_mlp = QwenFeedForward(dim=dim, dim_out=dim)
+        self.txt_mod = nn.Sequential(nn.SiLU(), nn.Linear(dim, 6 * dim, bias=True))
+        self.txt_norm1 = nn.LayerNorm(dim, elementwise_affine=False, eps=eps)
+        self.txt_norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=eps)
+        self.txt_mlp = QwenFeedForward(dim=dim, dim_out=dim)
+        self._owner = None      # set by QwenImageDiT: (dit, index) for the engine
+
+    def forward(self, image, text, temb, image_rotary_emb=None, attention_mask=None, enable_fp8_attention=False):
+        """Same signature / return order as the reference (qwen_image_dit.py:359-401): returns (text, image).
+        image [1,S_img,3072], text [1,T,3072], temb [1,3072]; image_rotary_emb = (vid complex [S_img,64], txt complex [T,64])."""
+        if attention_mask is not None or enable_fp8_attention:
+            raise NotImplementedError("entity attention masks / fp8 attention are outside the PhysicEdit hot path (SURVEY 8f5)")
+        dit, idx = self._owner
+        eng = dit.engine()
+        T, S_img = text.shape[1], image.shape[1]
+        x = torch.cat([text[0], image[0]], dim=0).contiguous()
+        vid, txt = image_rotary_emb
+        rope = torch.view_as_real(torch.cat([txt, vid], dim=0).to(torch.complex64)).contiguous().to(x.device)
+        ws = eng.workspace(S_img, T)
+        mods = eng.block_mods(temb.reshape(1, DIM), [idx])
+        eng.run_block(idx, x, T, mods[0], rope, ws)
+        return x[:T].unsqueeze(0), x[T:].unsqueeze(0)
+
+
+class QwenEmbedRope(nn.Module):
+    """qwen_image_dit.py:60-165: 3-axis RoPE tables (complex64 on the host), scale_rope=True."""
+
+    def __init__(self, theta: int, axes_dim: Sequence[int], scale_rope=False):
+        super().__init__()
+        self.theta, self.axes_dim, self.scale_rope = theta, list(axes_dim), scale_rope
+        self._build(4096)
+        self.rope_cache: Dict[str, torch.Tensor] = {}
+
+    def rope_params(self, index, dim, theta=10000):
+        assert dim % 2 == 0
+        freqs = torch.outer(index, 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float32).div(dim)))
+        return torch.polar(torch.ones_like(freqs), freqs)
+
+    def _build(self, n):
+        pos_index = torch.arange(n)
+        neg_index = torch.arange(n).flip(0) * -1 - 1
+        self.pos_freqs = torch.cat([self.rope_params(pos_index, d, self.theta) for d in self.axes_dim], dim=1)
+        self.neg_freqs = torch.cat([self.rope_params(neg_index, d, self.theta) for d in self.axes_dim], dim=1)
+
+    def _expand_pos_freqs_if_needed(self, video_fhw, txt_seq_lens):
+        if isinstance(video_fhw, list):
+            video_fhw = tuple(max([i[j] for i in video_fhw]) for j in range(3))
+        _, height, width = video_fhw
+        max_vid_index = max(height // 2, width // 2) if self.scale_rope else max(height, width)
+        required = max_vid_index + max(txt_seq_lens)
+        if required > self.pos_freqs.shape[0]:
+            self._build(math.ceil(required / 512) * 512)
+
+    def forward(self, video_fhw, txt_seq_lens, device=None):
+        self._expand_pos_freqs_if_needed(video_fhw, txt_seq_lens)
+        split = [x // 2 for x in self.axes_dim]
+        vid_freqs = []
+        max_vid_index = 0
+        for idx, (frame, height, width) in enumerate(video_fhw):
+            key = f"{idx}_{height}_{width}"
+            if key not in self.rope_cache:
+                fpos, fneg = self.pos_freqs.split(split, dim=1), self.neg_freqs.split(split, dim=1)
+                f_frame = fpos[0][idx: idx + frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+                if self.scale_rope:
+                    f_h = torch.cat([fneg[1][-(height - height // 2):], fpos[1][: height // 2]], dim=0)
+                    f_w = torch.cat([fneg[2][-(width - width // 2):], fpos[2][: width // 2]], dim=0)
+                else:
+                    f_h, f_w = fpos[1][:height], fpos[2][:width]
+                f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
+                f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
+                self.rope_cache[key] = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1).clone().contiguous()
+            vid_freqs.append(self.rope_cache[key])
+            max_vid_index = max(height // 2, width // 2, max_vid_index) if self.scale_rope else max(height, width, max_vid_index)
+        max_len = max(txt_seq_lens)
+        txt_freqs = self.pos_freqs[max_vid_index: max_vid_index + max_len, ...]
+        vid_freqs = torch.cat(vid_freqs, dim=0)
+        if device is not None:
+            vid_freqs, txt_freqs = vid_freqs.to(device), txt_freqs.to(device)
+        return vid_freqs, txt_freqs
+
+
+class QwenImageDiTStateDictConverter:
+    def from_civitai(self, state_dict):
+        return state_dict
+
+    def from_diffusers(self, state_dict):
+        return state_dict
+
+
+class QwenImageDiT(nn.Module):
+    """qwen_image_dit.py:404-546.  `forward` is the stock (non-edit) entry; PhysicEdit calls
+    physicedit_b200.model_fn.model_fn_qwen_image, which uses `engine()` directly."""
+
+    def __init__(self, num_layers: int = 60):
+        super().__init__()
+        self.pos_embed = QwenEmbedRope(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+        self.time_text_embed = TimestepEmbeddings(256, DIM)
+        self.txt_norm = RMSNorm(3584, eps=1e-6)
+        self.img_in = nn.Linear(64, DIM)
+        self.txt_in = nn.Linear(3584, DIM)
+        self.transformer_blocks = nn.ModuleList(
+            [QwenImageTransformerBlock(dim=DIM, num_attention_heads=NUM_HEADS, attention_head_dim=HEAD_DIM) for _ in range(num_layers)])
+        self.norm_out = AdaLayerNorm(DIM, single=True)
+        self.proj_out = nn.Linear(DIM, 64)
+        self._engine: Optional["DiTEngine"] = None
+        for i, b in enumerate(self.transformer_blocks):
+            object.__setattr__(b, "_owner", (self, i))
+
+    def engine(self) -> "DiTEngine":
+        if self._engine is None:
+            object.__setattr__(self, "_engine", DiTEngine(self))
+        self._engine.refresh_if_stale()
+        return self._engine
+
+    def forward(self, latents=None, timestep=None, prompt_emb=None, prompt_emb_mask=None, height=None, width=None):
+        from .model_fn import model_fn_qwen_image
+        out, _ = model_fn_qwen_image(dit=self, latents=latents, timestep=timestep * 1000 if timestep is not None else None,
+                                     prompt_emb=prompt_emb, prompt_emb_mask=prompt_emb_mask, special_token_mask=None,
+                                     height=height, width=width, is_train=False)
+        return out
+
+    @staticmethod
+    def state_dict_converter():
+        return QwenImageDiTStateDictConverter()
+
+
+# ------------------------------------------------------------------------------------------------
+# the engine: packed weights, workspaces, kernel sequencing
+# ------------------------------------------------------------------------------------------------
+class Workspace:
+    def __init__(self, S_img: int, T: int, device):
+        S = S_img + T
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.S_img, self.T, self.S = S_img, T, S
+        self.x = torch.empty(S, DIM, **bf)          # residual stream, [text; image]
+        self.xhat = torch.empty(S, DIM, **bf)       # LN + modulate output
+        self.q = torch.empty(S, DIM, **bf)
+        self.k = torch.empty(S, DIM, **bf)
+        self.v = torch.empty(S, DIM, **bf)
+        self.att = torch.empty(S, DIM, **bf)
+        self.h = torch.empty(S, 4 * DIM, **bf)      # MLP hidden
+        self.tok = torch.empty(S_img, 64, **bf)     # patchified latents
+        self.txt_n = torch.empty(T, 3584, **bf)     # txt_norm output
+        self.out_tok = torch.empty(S_img, 64, **bf)
+
+
+class DiTEngine:
+    """Holds fused QKV weights (the module's to_q/to_k/to_v parameters are re-pointed at views of the
+    fused buffer, so in-place LoRA folds and load_state_dict keep working) and runs the kernel sequence."""
+
+    def __init__(self, dit: QwenImageDiT):
+        self.dit = dit
+        p = next(dit.parameters())
+        if not p.is_cuda or p.dtype != torch.bfloat16:
+            raise nv.NativeUnavailable(f"the native DiT runs in bfloat16 on an sm_100 GPU only (got {p.dtype} on {p.device}); "
+                                       "there is no CPU / fp32 fallback")
+        self.device = p.device
+        self.nat = nv.Native.get(self.device.index or 0)
+        self.use_cta_pair = True
+        self.attn_flags = 0
+        self._ws: Dict[Tuple[int, int], Workspace] = {}
+        self._rope: Dict[tuple, torch.Tensor] = {}
+        self._mods_cache: Optional[Tuple[float, torch.Tensor, torch.Tensor, torch.Tensor]] = None
+        self._pack()
+
+    # -- weights ---------------------------------------------------------------------------------
+    def _pack(self):
+        self.qkv_w: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self.qkv_b: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        with torch.no_grad():
+            for blk in self.dit.transformer_blocks:
+                a = blk.attn
+                packs = []
+                for mods in ((a.to_q, a.to_k, a.to_v), (a.add_q_proj, a.add_k_proj, a.add_v_proj)):
+                    w = torch.cat([m.weight.data for m in mods], dim=0).contiguous()
+                    b = torch.cat([m.bias.data for m in mods], dim=0).contiguous()
+                    for j, m in enumerate(mods):                      # re-point: parameters become views of the fused buffers
+                        m.weight.data = w[j * DIM:(j + 1) * DIM]
+                        m.bias.data = b[j * DIM:(j + 1) * DIM]
+                    packs.append((w, b))
+                self.qkv_w.append((packs[0][0], packs[1][0]))
+                self.qkv_b.append((packs[0][1], packs[1][1]))
+        # which output features of the modulation linears are "scale" (stored as 1 + scale)
+        m6 = torch.zeros(6 * DIM, dtype=torch.uint8, device=self.device)
+        m6[DIM:2 * DIM] = 1
+        m6[4 * DIM:5 * DIM] = 1
+        self.mask6 = m6
+        m2 = torch.zeros(2 * DIM, dtype=torch.uint8, device=self.device)
+        m2[:DIM] = 1                                                   # AdaLayerNorm(single): (scale, shift)
+        self.mask2 = m2
+        self._mods_cache = None
+
+    def refresh_if_stale(self):
+        blocks = self.dit.transformer_blocks
+        for i in (0, len(blocks) - 1):
+            a = blocks[i].attn
+            if a.to_q.weight.data_ptr() != self.qkv_w[i][0].data_ptr() or a.add_v_proj.weight.data_ptr() != self.qkv_w[i][1][2 * DIM:].data_ptr():
+                self._pack()      # parameters were replaced (e.g. load_state_dict(assign=True))
+                return
+
+    def invalidate(self):
+        """Call after modifying weights in place (LoRA fold): drops cached modulation vectors."""
+        self._mods_cache = None
+
+    # -- cached per-shape state ---------------------------------------------------------------------
+    def workspace(self, S_img: int, T: int) -> Workspace:
+        key = (S_img, T)
+        if key not in self._ws:
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = Workspace(S_img, T, self.device)
+        return self._ws[key]
+
+    def rope(self, img_shapes: Sequence[Tuple[int, int, int]], T: int) -> torch.Tensor:
+        """float2 (cos, sin) table [T + S_img, 64] in joint [text; image] order."""
+        key = (tuple(tuple(s) for s in img_shapes), T)
+        if key not in self._rope:
+            vid, txt = self.dit.pos_embed(list(img_shapes), [T], device=None)
+            joint = torch.cat([txt, vid], dim=0).to(torch.complex64)
+            self._rope[key] = torch.view_as_real(joint).contiguous().to(self.device)
+        return self._rope[key]
+
+    # -- pieces ---------------------------------------------------------------------------------------
+    def block_mods(self, temb: torch.Tensor, indices: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """img_mod / txt_mod of the given blocks: [n, 2 (img, txt), 18432] with bf16(1+scale) in the scale slots."""
+        blocks = self.dit.transformer_blocks
+        indices = list(range(len(blocks))) if indices is None else list(indices)
+        out = torch.empty(len(indices), 2, 6 * DIM, dtype=torch.bfloat16, device=self.device)
+        for n, i in enumerate(indices):
+            b = blocks[i]
+            self.nat.tag = "gemv_mod"
+            self.nat.gemv(temb, b.img_mod[1].weight, b.img_mod[1].bias, out[n, 0:1], 1, 0, self.mask6)
+            self.nat.tag = "gemv_mod"
+            self.nat.gemv(temb, b.txt_mod[1].weight, b.txt_mod[1].bias, out[n, 1:2], 1, 0, self.mask6)
+        return out
+
+    def conditioning(self, timestep_bf16: torch.Tensor, t_key: Optional[float]):
+        """temb, all block modulation vectors and the norm_out (scale, shift) for this timestep.  They depend on
+        the timestep only, so the two CFG branches of a denoise step share them (cache keyed by the host value)."""
+        if t_key is not None and self._mods_cache is not None and self._mods_cache[0] == t_key:
+            return self._mods_cache[1:]
+        temb = self.dit.time_text_embed(timestep_bf16, raw=True)
+        mods = self.block_mods(temb)
+        no = self.dit.norm_out.linear
+        out_mod = torch.empty(1, 2 * DIM, dtype=torch.bfloat16, device=self.device)
+        self.nat.gemv(temb, no.weight, no.bias, out_mod, 1, 0, self.mask2)
+        if t_key is not None:
+            self._mods_cache = (t_key, temb, mods, out_mod)
+        return temb, mods, out_mod
+
+    def run_block(self, i: int, x: torch.Tensor, T: int, mods: torch.Tensor, rope: torch.Tensor, ws: Workspace):
+        """One double-stream block in place on the joint residual stream x [T + S_img, 3072].
+        mods: [2, 18432] = (img, txt) x (shift_a, 1+scale_a, gate_a, shift_m, 1+scale_m, gate_m)."""
+        nat, blk = self.nat, self.dit.transformer_blocks[i]
+        a = blk.attn
+        flags = nv.GEMM_FLAG_CTA_PAIR if self.use_cta_pair else 0
+        mi, mt = mods[0], mods[1]
+        D = DIM
+        xi, xt = x[T:], x[:T]
+        hi, ht = ws.xhat[T:], ws.xhat[:T]
+        # LN + modulate (attention branch), both streams in one launch
+        nat.tag = "ln_mod"
+        nat.layernorm_modulate2(x, ws.xhat, T, mt[0:D], mt[D:2 * D], mi[0:D], mi[D:2 * D])
+        # fused QKV projection + per-head RMSNorm + RoPE, written straight into the joint q/k/v buffers
+        (wq_i, wq_t), (bq_i, bq_t) = self.qkv_w[i], self.qkv_b[i]
+        nat.tag = "gemm_qkv"
+        nat.gemm([dict(a=hi, w=wq_i, bias=bq_i, out=ws.q[T:], out_k=ws.k[T:], out_v=ws.v[T:], norm_q_w=a.norm_q.weight,
+                       norm_k_w=a.norm_k.weight, rope=rope[T:]),
+                  dict(a=ht, w=wq_t, bias=bq_t, out=ws.q[:T], out_k=ws.k[:T], out_v=ws.v[:T], norm_q_w=a.norm_added_q.weight,
+                       norm_k_w=a.norm_added_k.weight, rope=rope[:T])], 3 * D, D, nv.EPI_QKV_NORM_ROPE, flags)
+        nat.tag = "attention"
+        nat.attention(ws.q, ws.k, ws.v, ws.att, NUM_HEADS, 1.0 / math.sqrt(HEAD_DIM), self.attn_flags)
+        # output projections + gate * o + residual (in place on x)
+        nat.tag = "gemm_out"
+        nat.gemm([dict(a=ws.att[T:], w=a.to_out[0].weight, bias=a.to_out[0].bias, out=xi, gate=mi[2 * D:3 * D]),
+                  dict(a=ws.att[:T], w=a.to_add_out.weight, bias=a.to_add_out.bias, out=xt, gate=mt[2 * D:3 * D])],
+                 D, D, nv.EPI_GATE_RESIDUAL, flags)
+        # MLP branch
+        nat.tag = "ln_mod"
+        nat.layernorm_modulate2(x, ws.xhat, T, mt[3 * D:4 * D], mt[4 * D:5 * D], mi[3 * D:4 * D], mi[4 * D:5 * D])
+        im, tm = blk.img_mlp.net, blk.txt_mlp.net
+        nat.tag = "gemm_up"
+        nat.gemm([dict(a=hi, w=im[0].proj.weight, bias=im[0].proj.bias, out=ws.h[T:]),
+                  dict(a=ht, w=tm[0].proj.weight, bias=tm[0].proj.bias, out=ws.h[:T])], 4 * D, D, nv.EPI_BIAS_GELU_SIGMOID, flags)
+        nat.tag = "gemm_down"
+        nat.gemm([dict(a=ws.h[T:], w=im[2].weight, bias=im[2].bias, out=xi, gate=mi[5 * D:6 * D]),
+                  dict(a=ws.h[:T], w=tm[2].weight, bias=tm[2].bias, out=xt, gate=mt[5 * D:6 * D])], D, 4 * D, nv.EPI_GATE_RESIDUAL, flags)
+
+    def forward(self, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
+                out_latents: torch.Tensor, t_key: Optional[float] = None) -> torch.Tensor:
+        """latents_list: [noise latents, edit/context latents ...] each [1,16,h8,w8] bf16; prompt_emb [T,3584] bf16
+        (already updated by the adapter).  Writes the velocity for the first entry into out_latents [1,16,h8,w8]."""
+        nat, dit = self.nat, self.dit
+        T = prompt_emb.shape[0]
+        shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]
+        S_img = sum(h * w for _, h, w in shapes)
+        ws = self.workspace(S_img, T)
+        rope = self.rope(shapes, T)
+        temb, mods, out_mod = self.conditioning(timestep_bf16, t_key)
+        # patchify + img_in
+        off = 0
+        for l, (_, h, w) in zip(latents_list, shapes):
+            nat.patchify(l.reshape(16, l.shape[-2], l.shape[-1]), ws.tok[off:off + h * w])
+            off += h * w
+        nat.gemm([dict(a=ws.tok, w=dit.img_in.weight, bias=dit.img_in.bias, out=ws.x[T:])], DIM, 64, nv.EPI_BIAS)
+        # txt_norm + txt_in
+        nat.rmsnorm(prompt_emb, ws.txt_n, dit.txt_norm.weight, dit.txt_norm.eps)
+        nat.gemm([dict(a=ws.txt_n, w=dit.txt_in.weight, bias=dit.txt_in.bias, out=ws.x[:T])], DIM, 3584, nv.EPI_BIAS)
+        for i in range(len(dit.transformer_blocks)):
+            self.run_block(i, ws.x, T, mods[i], rope, ws)
+        # norm_out + proj_out on the noise tokens only (the reference slices after computing all image rows)
+        n0 = shapes[0][1] * shapes[0][2]
+        nat.layernorm_modulate(ws.x[T:T + n0], ws.xhat[:n0], out_mod[0, DIM:], out_mod[0, :DIM])
+        nat.gemm([dict(a=ws.xhat[:n0], w=dit.proj_out.weight, bias=dit.proj_out.bias, out=ws.out_tok[:n0])], 64, DIM, nv.EPI_BIAS)
+        nat.unpatchify(ws.out_tok[:n0], out_latents.reshape(16, out_latents.shape[-2], out_latents.shape[-1]))
+        return out_latents

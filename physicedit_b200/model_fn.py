@@ -1,0 +1,103 @@
+"""The per-forward step function of PhysicEdit, native.
+
+Drop-in for `model_fn_qwen_image` (DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py:1302-1403):
+same keyword signature, same return `(latents, special_token_loss)`, same in-place mutation of
+`prompt_emb` (the adapter output is written back into the caller's tensor, :1336, so step k sees the
+output of step k-1), same bf16 timestep bookkeeping (`t -> bf16 -> /1000 -> bf16`, bf16 frequencies).
+The pipeline installs it as `pipe.model_fn`.  Everything numeric runs in libpe_b200 kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native as nv
+
+_MASK_SUM_CACHE: dict = {}
+
+
+def _txt_len(mask: Optional[torch.Tensor], T: int) -> int:
+    """`prompt_emb_mask.sum(dim=1).tolist()` (:1341) is a device->host sync in the reference; the result only
+    depends on the mask tensor, so it is read once per mask tensor version."""
+    if mask is None:
+        return T
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape))
+    if key not in _MASK_SUM_CACHE:
+        if len(_MASK_SUM_CACHE) > 64:
+            _MASK_SUM_CACHE.clear()
+        _MASK_SUM_CACHE[key] = int(mask.sum(dim=1).max().item())
+    return _MASK_SUM_CACHE[key]
+
+
+def model_fn_qwen_image(
+    dit=None,
+    blockwise_controlnet=None,
+    visual_thinking_adapter=None,
+    latents=None,
+    timestep=None,
+    prompt_emb=None,
+    prompt_emb_mask=None,
+    special_token_mask=None,
+    height=None,
+    width=None,
+    blockwise_controlnet_conditioning=None,
+    blockwise_controlnet_inputs=None,
+    progress_id=0,
+    num_inference_steps=1,
+    entity_prompt_emb=None,
+    entity_prompt_emb_mask=None,
+    entity_masks=None,
+    edit_latents=None,
+    context_latents=None,
+    enable_fp8_attention=False,
+    use_gradient_checkpointing=False,
+    use_gradient_checkpointing_offload=False,
+    edit_rope_interpolation=False,
+    is_train=True,
+    pseudo_special_emb_dino=None,
+    pseudo_special_emb_vae=None,
+    timestep_host: Optional[float] = None,
+    out: Optional[torch.Tensor] = None,
+    **kwargs,
+):
+    if entity_prompt_emb is not None or blockwise_controlnet_conditioning is not None or edit_rope_interpolation or enable_fp8_attention:
+        raise NotImplementedError("EliGen entity control, blockwise controlnet, edit_rope_interpolation and fp8 attention are outside "
+                                  "the PhysicEdit hot path (SURVEY.md 8f5): no PhysicEdit script enables them")
+    if latents.shape[0] != 1 or prompt_emb.shape[0] != 1:
+        raise ValueError("the pipeline is strictly batch 1 (qwen_image_physical.py:688,821); batch edits shard one image per GPU")
+    if not (latents.is_cuda and latents.dtype == torch.bfloat16 and prompt_emb.dtype == torch.bfloat16):
+        raise nv.NativeUnavailable(f"native model_fn needs CUDA bfloat16 tensors (latents {latents.dtype} on {latents.device}); no fallback")
+    eng = dit.engine()
+    nat = eng.nat
+    t_bf16 = timestep.to(device=latents.device, dtype=torch.bfloat16).reshape(-1)[:1].contiguous()
+    if timestep_host is None and not timestep.is_cuda:
+        timestep_host = float(timestep.reshape(-1)[0])
+    T = prompt_emb.shape[1]
+    assert _txt_len(prompt_emb_mask, T) == T, "padded prompts are not produced by the B=1 pipeline (RoPE table would not match either)"
+    pe2d = prompt_emb[0]
+    if not pe2d.is_contiguous():
+        raise ValueError("prompt_emb must be contiguous: it is updated in place")
+
+    special_token_loss = 0
+    if special_token_mask is not None:
+        ad = visual_thinking_adapter
+        n_sp = getattr(model_fn_qwen_image, "special_token_num", 64)
+        gathered = torch.empty(n_sp, pe2d.shape[1], dtype=torch.bfloat16, device=pe2d.device)
+        idx = torch.empty(n_sp + 1, dtype=torch.int32, device=pe2d.device)
+        nat.special_gather(pe2d, special_token_mask[0].view(torch.uint8), gathered, idx)
+        pred_dino, pred_vae = ad.heads(gathered)
+        nat.special_blend_scatter(pe2d, idx, pred_dino, pred_vae, t_bf16, ad.t_min, ad.t_max)       # in place (:1336)
+        if is_train:
+            special_token_loss = ad.get_loss(pred_dino.unsqueeze(0), pred_vae.unsqueeze(0), pseudo_special_emb_dino, pseudo_special_emb_vae, timestep)
+
+    lat_list = [latents]
+    if context_latents is not None:
+        lat_list.append(context_latents)
+    if edit_latents is not None:
+        lat_list += list(edit_latents) if isinstance(edit_latents, list) else [edit_latents]
+    lat_list = [l.contiguous() for l in lat_list]
+    if out is None:
+        out = torch.empty_like(latents)
+    eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host)
+    return out, special_token_loss

@@ -30,7 +30,7 @@ ATTN_FLAG_SWAP_V_DESC = 4
 
 EXPORTED_SYMBOLS = [
     "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count",
-    "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm", "pe_add_rows",
+    "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
     "pe_rmsnorm", "pe_gemv", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
 ]
@@ -71,11 +71,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_small_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int64, c_int64, c_int64, c_float, c_void_p]
     lib.pe_layernorm_modulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pe_layernorm_modulate2.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pe_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]
     lib.pe_add_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
     lib.pe_rmsnorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p]
     lib.pe_gemv.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
-    lib.pe_timestep_embedding.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pe_timestep_embedding.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     lib.pe_patchify.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.pe_unpatchify.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]
     lib.pe_cfg_euler_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]
@@ -113,6 +114,8 @@ class Native:
         self.h = h
         self.sm_count = self.lib.pe_sm_count(self.h)
         self.launches = 0      # number of kernels of this library enqueued (bench.py reports it)
+        self.prof = None       # {tag: [(start_event, end_event), ...]} when per-launch CUDA-event timing is on
+        self.tag = None        # set by the engine before a launch to name it in `prof`
 
     @classmethod
     def get(cls, device: int = 0) -> "Native":
@@ -128,6 +131,29 @@ class Native:
     def _check(self, rc: int, what: str) -> None:
         if rc != PE_OK:
             raise NativeError(f"{what} failed ({rc}): {self.lib.pe_last_error(self.h).decode()}")
+        if self.prof is not None and self._ev0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.device))
+            self.prof.setdefault(self.tag or what, []).append((self._ev0, e1))
+            self._ev0 = None
+        self.tag = None
+
+    _ev0 = None
+
+    def _stream_prof(self) -> int:
+        """Stream handle for a launch; when profiling, first records the start event on that stream."""
+        st = torch.cuda.current_stream(self.device)
+        if self.prof is not None:
+            self._ev0 = torch.cuda.Event(enable_timing=True)
+            self._ev0.record(st)
+        return st.cuda_stream
+
+    def profile_summary(self) -> dict:
+        """{tag: (launches, total_ms)} from the recorded event pairs (call after a synchronize)."""
+        out = {}
+        for tag, evs in (self.prof or {}).items():
+            out[tag] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+        return out
 
     def check_async(self) -> None:
         diag = c_uint(0)
@@ -148,7 +174,7 @@ class Native:
             g.out, g.ldo, g.M = out.data_ptr(), out.stride(0), a.shape[0]
             g.gate, g.out_k, g.out_v = _ptr(s.get("gate")), _ptr(s.get("out_k")), _ptr(s.get("out_v"))
             g.norm_q_w, g.norm_k_w, g.rope = _ptr(s.get("norm_q_w")), _ptr(s.get("norm_k_w")), _ptr(s.get("rope"))
-        self._check(self.lib.pe_gemm(self.h, arr, len(segs), N, K, epilogue, flags, self._stream()), "pe_gemm")
+        self._check(self.lib.pe_gemm(self.h, arr, len(segs), N, K, epilogue, flags, self._stream_prof()), "pe_gemm")
         self.launches += 1
 
     def linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int = EPI_BIAS, flags: int = 0) -> torch.Tensor:
@@ -163,7 +189,7 @@ class Native:
             if t.stride(0) != q.stride(0):
                 raise NativeError("q, k, v, o must share one row stride")
         self._check(self.lib.pe_attention_fwd(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), q.shape[0], H,
-                                              q.stride(0), scale, flags, self._stream()), "pe_attention_fwd")
+                                              q.stride(0), scale, flags, self._stream_prof()), "pe_attention_fwd")
         self.launches += 1
 
     def small_attention(self, q, k, v, o, B: int, H: int, Sq: int, Skv: int, D: int, scale: float) -> None:
@@ -173,7 +199,7 @@ class Native:
         if k.stride(0) != v.stride(0):
             raise NativeError("k and v must share one row stride")
         self._check(self.lib.pe_small_attention(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, Sq, Skv, D,
-                                                q.stride(0), k.stride(0), o.stride(0), scale, self._stream()), "pe_small_attention")
+                                                q.stride(0), k.stride(0), o.stride(0), scale, self._stream_prof()), "pe_small_attention")
         self.launches += 1
 
     def layernorm_modulate(self, x, out, shift, one_plus_scale) -> None:
@@ -181,24 +207,32 @@ class Native:
         if not (x.is_contiguous() and out.is_contiguous()):
             raise NativeError("layernorm_modulate: x / out must be contiguous")
         self._check(self.lib.pe_layernorm_modulate(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], shift.data_ptr(),
-                                                   one_plus_scale.data_ptr(), self._stream()), "pe_layernorm_modulate")
+                                                   one_plus_scale.data_ptr(), self._stream_prof()), "pe_layernorm_modulate")
+        self.launches += 1
+
+    def layernorm_modulate2(self, x, out, split_row: int, shift0, ops0, shift1, ops1) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        if not (x.is_contiguous() and out.is_contiguous()):
+            raise NativeError("layernorm_modulate2: x / out must be contiguous")
+        self._check(self.lib.pe_layernorm_modulate2(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], split_row, shift0.data_ptr(),
+                                                    ops0.data_ptr(), shift1.data_ptr(), ops1.data_ptr(), self._stream_prof()), "pe_layernorm_modulate2")
         self.launches += 1
 
     def layernorm(self, x, out, w=None, b=None, eps: float = 1e-5) -> None:
         _bf16(x, "x"); _bf16(out, "out")
         self._check(self.lib.pe_layernorm(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ptr(w), _ptr(b), eps,
-                                          self._stream()), "pe_layernorm")
+                                          self._stream_prof()), "pe_layernorm")
         self.launches += 1
 
     def add_rows(self, x, add, period: int, alpha: float = 1.0) -> None:
         _bf16(x, "x"); _bf16(add, "add")
-        self._check(self.lib.pe_add_rows(self.h, x.data_ptr(), add.data_ptr(), x.shape[0], x.shape[1], period, alpha, self._stream()),
+        self._check(self.lib.pe_add_rows(self.h, x.data_ptr(), add.data_ptr(), x.shape[0], x.shape[1], period, alpha, self._stream_prof()),
                     "pe_add_rows")
         self.launches += 1
 
     def rmsnorm(self, x, out, w, eps: float = 1e-6) -> None:
         _bf16(x, "x"); _bf16(out, "out")
-        self._check(self.lib.pe_rmsnorm(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ptr(w), eps, self._stream()),
+        self._check(self.lib.pe_rmsnorm(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _ptr(w), eps, self._stream_prof()),
                     "pe_rmsnorm")
         self.launches += 1
 
@@ -207,42 +241,42 @@ class Native:
         _bf16(x, "x"); _bf16(w, "w"); _bf16(y, "y")
         batch = 1 if x.dim() == 1 else x.shape[0]
         self._check(self.lib.pe_gemv(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1],
-                                     act_in, act_out, _ptr(one_plus_mask), self._stream()), "pe_gemv")
+                                     act_in, act_out, _ptr(one_plus_mask), self._stream_prof()), "pe_gemv")
         self.launches += 1
 
-    def timestep_embedding(self, t_in, out) -> None:
+    def timestep_embedding(self, t_in, out, raw: bool = True) -> None:
         _bf16(t_in, "t_in"); _bf16(out, "out")
-        self._check(self.lib.pe_timestep_embedding(self.h, t_in.data_ptr(), out.data_ptr(), self._stream()), "pe_timestep_embedding")
+        self._check(self.lib.pe_timestep_embedding(self.h, t_in.data_ptr(), out.data_ptr(), int(raw), self._stream_prof()), "pe_timestep_embedding")
         self.launches += 1
 
     def patchify(self, latents, tokens) -> None:
         """latents [16, H8, W8] contiguous -> tokens [(H8/2)*(W8/2), 64] contiguous."""
         _bf16(latents, "latents"); _bf16(tokens, "tokens")
         self._check(self.lib.pe_patchify(self.h, latents.data_ptr(), tokens.data_ptr(), latents.shape[-2], latents.shape[-1],
-                                         self._stream()), "pe_patchify")
+                                         self._stream_prof()), "pe_patchify")
         self.launches += 1
 
     def unpatchify(self, tokens, latents) -> None:
         _bf16(latents, "latents"); _bf16(tokens, "tokens")
         self._check(self.lib.pe_unpatchify(self.h, tokens.data_ptr(), tokens.stride(0), latents.data_ptr(), latents.shape[-2],
-                                           latents.shape[-1], self._stream()), "pe_unpatchify")
+                                           latents.shape[-1], self._stream_prof()), "pe_unpatchify")
         self.launches += 1
 
     def cfg_euler_step(self, latents, posi, nega, cfg_scale: float, dsigma: float) -> None:
         _bf16(latents, "latents"); _bf16(posi, "posi")
         self._check(self.lib.pe_cfg_euler_step(self.h, latents.data_ptr(), posi.data_ptr(), _ptr(nega), latents.numel(), cfg_scale,
-                                               dsigma, self._stream()), "pe_cfg_euler_step")
+                                               dsigma, self._stream_prof()), "pe_cfg_euler_step")
         self.launches += 1
 
     def special_gather(self, prompt_emb, mask_u8, dst, idx) -> None:
         _bf16(prompt_emb, "prompt_emb"); _bf16(dst, "dst")
         self._check(self.lib.pe_special_gather(self.h, prompt_emb.data_ptr(), mask_u8.data_ptr(), prompt_emb.shape[0], prompt_emb.shape[1],
-                                               dst.data_ptr(), idx.data_ptr(), dst.shape[0], self._stream()), "pe_special_gather")
+                                               dst.data_ptr(), idx.data_ptr(), dst.shape[0], self._stream_prof()), "pe_special_gather")
         self.launches += 2
 
     def special_blend_scatter(self, prompt_emb, idx, pred_dino, pred_vae, t_in, t_min: float, t_max: float) -> None:
         _bf16(prompt_emb, "prompt_emb")
         self._check(self.lib.pe_special_blend_scatter(self.h, prompt_emb.data_ptr(), idx.data_ptr(), pred_dino.shape[0], prompt_emb.shape[1],
                                                       pred_dino.data_ptr(), pred_vae.data_ptr(), t_in.data_ptr(), t_min, t_max,
-                                                      self._stream()), "pe_special_blend_scatter")
+                                                      self._stream_prof()), "pe_special_blend_scatter")
         self.launches += 1

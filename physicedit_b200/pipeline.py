@@ -1,0 +1,327 @@
+"""QwenImagePhysicPipeline with the reference's API surface, the denoise loop on the native path.
+
+Mirrors DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py (class QwenImagePhysicPipeline:
+__init__ :185-247, load_lora :250-276, training_loss :313-329, enable_vram_management :375-494,
+from_pretrained :497-541, __call__ :544-669) and diffsynth/utils/__init__.py (BasePipeline, ModelConfig).
+
+In scope here: the in-iteration models (`dit`, `visual_thinking_adapter`), the scheduler,
+the CFG denoise loop, LoRA fold, checkpoint key layout, and the training-path feature extractors
+(DINOv2, resamplers).  Out of scope (8f "next"): the Qwen2.5-VL text encoder and the VAE -- the pipeline
+accepts them as user-supplied modules (`pipe.text_encoder`, `pipe.vae`, any object with the reference's
+`encode`/`decode`/`edit_forward` contract) or takes pre-computed embeddings / latents through
+`denoise(...)`, which is what bench.py and the parity tests drive.
+"""
+from __future__ import annotations
+
+import glob
+import os
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import native as nv
+from .adapters import Dinov2withNorm, PerceiverResampler, VisualThinkingAdapter, VisualThinkingDualAdapter
+from .dit import QwenImageDiT
+from .lora import GeneralLoRALoader
+from .model_fn import model_fn_qwen_image
+from .scheduler import FlowMatchScheduler
+
+SPECIAL_TOKEN_NUM = 64        # qwen_image_physical.py:28
+DIT_KEY_HASH = "0319a1cb19835fb510907dd3367c95ff"      # configs/model_config.py:21
+
+
+@dataclass
+class ModelConfig:
+    """diffsynth/utils/__init__.py:160-220 minus the downloaders (no network): resolves local files only."""
+    path: Union[str, list] = None
+    model_id: str = None
+    origin_file_pattern: Union[str, list] = None
+    download_resource: str = "ModelScope"
+    offload_device: Optional[Union[str, torch.device]] = None
+    offload_dtype: Optional[torch.dtype] = None
+    local_model_path: str = None
+    skip_download: bool = True
+
+    def download_if_necessary(self, use_usp=False):
+        if self.path is not None:
+            return
+        if self.model_id is None:
+            raise ValueError("No valid model files. Please use `ModelConfig(path=...)` or `ModelConfig(model_id=..., origin_file_pattern=...)`.")
+        base = self.local_model_path or "./models"
+        pattern = self.origin_file_pattern or ""
+        target = os.path.join(base, self.model_id, pattern)
+        if isinstance(pattern, str) and (pattern == "" or pattern.endswith("/")):
+            self.path = target
+            return
+        found = sorted(glob.glob(target))
+        self.path = found[0] if len(found) == 1 else found
+
+
+def load_state_dict(file_path, torch_dtype=None, device="cpu"):
+    """diffsynth.load_state_dict (models/utils.py:65-88)."""
+    if isinstance(file_path, (list, tuple)):
+        sd = {}
+        for p in file_path:
+            sd.update(load_state_dict(p, torch_dtype, device))
+        return sd
+    if file_path.endswith(".safetensors"):
+        from safetensors import safe_open
+        sd = {}
+        with safe_open(file_path, framework="pt", device=str(device)) as f:
+            for k in f.keys():
+                t = f.get_tensor(k)
+                sd[k] = t.to(torch_dtype) if torch_dtype is not None else t
+        return sd
+    sd = torch.load(file_path, map_location=device, weights_only=True)
+    if torch_dtype is not None:
+        sd = {k: (v.to(torch_dtype) if isinstance(v, torch.Tensor) else v) for k, v in sd.items()}
+    return sd
+
+
+def hash_state_dict_keys(state_dict, with_shape=True):
+    """models/utils.py:148-182."""
+    import hashlib
+    keys = []
+    for key, value in state_dict.items():
+        if isinstance(key, str) and isinstance(value, torch.Tensor):
+            if with_shape:
+                keys.append(key + ":" + "_".join(map(str, list(value.shape))))
+            keys.append(key)
+    keys.sort()
+    return hashlib.md5(",".join(keys).encode("UTF-8")).hexdigest()
+
+
+def load_dit(path, torch_dtype=torch.bfloat16, device="cuda") -> Optional[QwenImageDiT]:
+    """ModelManager.load_model for the one registry row on this path (model_manager.py:350-376): detect by key hash,
+    init on the meta device, `load_state_dict(assign=True)`, move.  Unknown files print and return None like the reference."""
+    sd = load_state_dict(path, torch_dtype=torch_dtype, device="cpu")
+    if hash_state_dict_keys(sd) != DIT_KEY_HASH:
+        print(f"    We cannot detect the model type. No models are loaded ({path}).")
+        return None
+    with torch.device("meta"):
+        dit = QwenImageDiT()
+    dit.load_state_dict(sd, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    for i, b in enumerate(dit.transformer_blocks):
+        object.__setattr__(b, "_owner", (dit, i))
+    return dit.to(dtype=torch_dtype, device=device).eval()
+
+
+class QwenImagePhysicPipeline(nn.Module):
+    def __init__(self, device="cuda", torch_dtype=torch.bfloat16, dinov2_path=None, dinov2_config: dict = None, build_training_path: bool = True):
+        super().__init__()
+        self.device, self.torch_dtype = device, torch_dtype
+        self.height_division_factor = self.width_division_factor = 16
+        self.scheduler = FlowMatchScheduler(sigma_min=0, sigma_max=1, extra_one_step=True, exponential_shift=True,
+                                            exponential_shift_mu=0.8, shift_terminal=0.02)
+        self.text_encoder = None
+        self.dit: QwenImageDiT = None
+        self.vae = None
+        if build_training_path:
+            assert dinov2_path is not None or dinov2_config is not None, "dinov2_path must be provided (path to DINOv2-with-registers-base)"
+            self.dinov2 = Dinov2withNorm(dinov2_path=dinov2_path, config=dinov2_config).to(device=device, dtype=torch_dtype)
+            self.dinov2_mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+            self.dinov2_std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+            self.dino_resampler = PerceiverResampler(dim=768, num_latents=SPECIAL_TOKEN_NUM, depth=2).to(device=device, dtype=torch_dtype)
+            self.dino_time_embed = nn.Embedding(6, 768).to(device=device, dtype=torch_dtype)
+            self.dino_resampler_adapter = VisualThinkingAdapter(in_dim=768, out_dim=3584).to(device=device, dtype=torch_dtype)
+            self.dino_input_size = 224
+            self.vae_resampler = PerceiverResampler(dim=64, num_latents=SPECIAL_TOKEN_NUM, depth=2, max_num_media_tokens=10240).to(device=device, dtype=torch_dtype)
+            self.vae_time_embed = nn.Embedding(6, 64).to(device=device, dtype=torch_dtype)
+            self.vae_resampler_adapter = VisualThinkingAdapter(in_dim=64, out_dim=3584).to(device=device, dtype=torch_dtype)
+        self.visual_thinking_adapter = VisualThinkingDualAdapter(in_dim=3584, out_dim=3584, t_min=self.scheduler.timesteps.min().item(),
+                                                                 t_max=self.scheduler.timesteps.max().item()).to(device=device, dtype=torch_dtype)
+        self.blockwise_controlnet = None
+        self.tokenizer = None
+        self.processor = None
+        self.in_iteration_models = ("dit", "blockwise_controlnet", "visual_thinking_adapter")
+        self.model_fn = model_fn_qwen_image
+        self.special_token_loss = 0.0
+        self.vram_management_enabled = False
+
+    # ---- reference API ------------------------------------------------------------------------------
+    @staticmethod
+    def from_pretrained(torch_dtype=torch.bfloat16, device="cuda", model_configs=(), tokenizer_config=None, processor_config=None,
+                        dinov2_path=None):
+        pipe = QwenImagePhysicPipeline(device=device, torch_dtype=torch_dtype, dinov2_path=dinov2_path)
+        for cfg in model_configs:
+            cfg.download_if_necessary()
+            paths = cfg.path if isinstance(cfg.path, list) else [cfg.path]
+            try:
+                model = load_dit(paths if len(paths) > 1 else paths[0], torch_dtype=cfg.offload_dtype or torch_dtype, device=device)
+            except Exception as e:  # noqa: BLE001  (the reference's loader prints and moves on, model_manager.py:375-376)
+                print(f"    Loading {paths} failed: {e}")
+                model = None
+            if model is not None:
+                pipe.dit = model
+        return pipe
+
+    def load_lora(self, module: nn.Module, lora_config=None, alpha=1, hotload=False, state_dict=None):
+        if hotload:
+            raise NotImplementedError("hotload (un-merged LoRA through AutoWrappedLinear) is unused by PhysicEdit (SURVEY 0.5)")
+        if state_dict is None:
+            path = lora_config if isinstance(lora_config, str) else lora_config.path
+            state_dict = load_state_dict(path, torch_dtype=self.torch_dtype, device=self.device)
+        GeneralLoRALoader(torch_dtype=self.torch_dtype, device=self.device).load(module, state_dict, alpha=alpha)
+
+    def enable_vram_management(self, *args, **kwargs):
+        """Accepted for API compatibility (inference_pica.py:246): weights stay resident -- a B200 has 180 GB."""
+        self.vram_management_enabled = False
+
+    def load_models_to_device(self, model_names=()):
+        return None
+
+    def freeze_except(self, model_names):
+        for name, model in self.named_children():
+            if name in model_names:
+                model.train(); model.requires_grad_(True)
+            else:
+                model.eval(); model.requires_grad_(False)
+
+    def check_resize_height_width(self, height, width):
+        """diffsynth/utils/__init__.py:43-52: silently rounds UP to multiples of 16."""
+        if height % 16 != 0:
+            height = (height + 15) // 16 * 16
+            print(f"height % 16 != 0. We round it up to {height}.")
+        if width % 16 != 0:
+            width = (width + 15) // 16 * 16
+            print(f"width % 16 != 0. We round it up to {width}.")
+        return height, width
+
+    def generate_noise(self, shape, seed=None, rand_device="cpu", rand_torch_dtype=torch.float32, device=None, torch_dtype=None):
+        generator = None if seed is None else torch.Generator(rand_device).manual_seed(seed)
+        noise = torch.randn(shape, generator=generator, device=rand_device, dtype=rand_torch_dtype)
+        return noise.to(dtype=torch_dtype or self.torch_dtype, device=device or self.device)
+
+    def step(self, scheduler, latents, progress_id, noise_pred, **kwargs):
+        return scheduler.step(noise_pred, scheduler.timesteps[progress_id], latents)
+
+    # ---- the hot loop -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise(self, latents, inputs_posi: dict, inputs_nega: Optional[dict], edit_latents=None, context_latents=None, *, height: int,
+                width: int, num_inference_steps: int = 30, cfg_scale: float = 4.0, denoising_strength: float = 1.0,
+                exponential_shift_mu=None, progress_bar_cmd=None, timesteps_device: Optional[torch.Tensor] = None):
+        """Lines 600 and 646-661 of the reference __call__: set_timesteps, then per step two model_fn forwards
+        (posi / nega, each with its own persistently-mutated prompt_emb), CFG combine and the Euler update
+        (one fused kernel).  inputs_*: dicts with prompt_emb [1,T,3584], prompt_emb_mask, special_token_mask."""
+        self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength,
+                                     dynamic_shift_len=(height // 16) * (width // 16), exponential_shift_mu=exponential_shift_mu)
+        nat = nv.Native.get(latents.device.index or 0)
+        ts = self.scheduler.timesteps
+        ts_dev = ts.to(dtype=self.torch_dtype).to(latents.device) if timesteps_device is None else timesteps_device   # one H2D for the whole table
+        latents = latents.clone()
+        vp = torch.empty_like(latents)
+        vn = torch.empty_like(latents)
+        it = enumerate(ts)
+        if progress_bar_cmd is not None:
+            it = progress_bar_cmd(list(it))
+        for progress_id, t in it:
+            t_host = float(t.to(self.torch_dtype))
+            kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=ts_dev[progress_id:progress_id + 1],
+                      height=height, width=width, edit_latents=edit_latents, context_latents=context_latents, is_train=False,
+                      progress_id=progress_id, timestep_host=t_host)
+            self.model_fn(**kw, **inputs_posi, out=vp)
+            if cfg_scale != 1.0:
+                self.model_fn(**kw, **inputs_nega, out=vn)
+            ds = float(self.scheduler.dsigma(t))
+            nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), ds)
+        return latents
+
+    @torch.no_grad()
+    def denoise_step(self, latents, inputs_posi: dict, inputs_nega: Optional[dict], edit_latents=None, context_latents=None, *, progress_id: int,
+                     height: int, width: int, cfg_scale: float = 4.0):
+        """One iteration of the loop above against the CURRENT scheduler table (call scheduler.set_timesteps first):
+        updates `latents` in place and returns it.  This is the unit bench.py times end to end."""
+        nat = nv.Native.get(latents.device.index or 0)
+        t = self.scheduler.timesteps[progress_id]
+        t_host = float(t.to(self.torch_dtype))
+        t_dev = t.to(self.torch_dtype).reshape(1).to(latents.device, non_blocking=True)
+        if not hasattr(self, "_vbuf") or self._vbuf[0].shape != latents.shape or self._vbuf[0].device != latents.device:
+            self._vbuf = (torch.empty_like(latents), torch.empty_like(latents))
+        vp, vn = self._vbuf
+        kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=t_dev, height=height, width=width,
+                  edit_latents=edit_latents, context_latents=context_latents, is_train=False, progress_id=progress_id, timestep_host=t_host)
+        self.model_fn(**kw, **inputs_posi, out=vp)
+        if cfg_scale != 1.0:
+            self.model_fn(**kw, **inputs_nega, out=vn)
+        nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), float(self.scheduler.dsigma(t)))
+        return latents
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, negative_prompt="", cfg_scale=4.0, height=1328, width=1328, seed=None, rand_device="cpu",
+                 num_inference_steps=30, edit_image=None, is_train=True, progress_bar_cmd=None, tiled=False, tile_size=128, tile_stride=64,
+                 prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, output_type="pil", **kwargs):
+        """Reference signature subset.  The pre-loop units that need the Qwen2.5-VL encoder / VAE run only if those
+        modules were attached (`pipe.text_encoder`, `pipe.vae`); otherwise pass `prompt_inputs_posi/nega` and
+        `edit_latents` and get latents back (`output_type="latent"`)."""
+        height, width = self.check_resize_height_width(height, width)
+        latents = self.generate_noise((1, 16, height // 8, width // 8), seed=seed, rand_device=rand_device)
+        if prompt_inputs_posi is None:
+            if self.text_encoder is None:
+                raise RuntimeError("no text encoder attached: pass prompt_inputs_posi / prompt_inputs_nega (prompt_emb, prompt_emb_mask, "
+                                   "special_token_mask) -- the Qwen2.5-VL encoder is outside this framework's scope (SURVEY 8f2)")
+            prompt_inputs_posi = self.text_encoder.encode_for_pipeline(self, prompt, edit_image, positive=True)
+            prompt_inputs_nega = self.text_encoder.encode_for_pipeline(self, negative_prompt, edit_image, positive=False)
+        if edit_latents is None and edit_image is not None:
+            if self.vae is None:
+                raise RuntimeError("no VAE attached: pass edit_latents (SURVEY 8f1)")
+            edit_latents = self.vae.encode(edit_image, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
+        latents = self.denoise(latents, prompt_inputs_posi, prompt_inputs_nega, edit_latents, height=height, width=width,
+                               num_inference_steps=num_inference_steps, cfg_scale=cfg_scale, progress_bar_cmd=progress_bar_cmd)
+        if output_type == "latent" or self.vae is None:
+            return latents
+        image = self.vae.decode(latents, device=self.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
+        return image
+
+    # ---- training path (forward only) -----------------------------------------
+    @torch.no_grad()
+    def physical_visual_embeddings(self, dino_middle: torch.Tensor, dino_source: torch.Tensor, vae_middle_latents: torch.Tensor,
+                                   vae_source_latents: torch.Tensor):
+        """QwenImageUnit_PhysicalVisualEmbedder.process (:1057-1118) from pre-processed tensors:
+        dino_* [F,3,224,224] normalised pixels, vae_* [F,16,h8,w8] latents.  Returns the regression targets
+        pseudo_special_emb_dino / pseudo_special_emb_vae [1,64,3584]."""
+        nat = nv.Native.get(dino_middle.device.index or 0)
+
+        def dino_branch(px, with_time):
+            hs = self.dinov2(px)                                         # [F,256,768]
+            Fn, L, Hd = hs.shape
+            hs = hs.reshape(Fn * L, Hd).contiguous()
+            if with_time:                                                  # + time_emb[f] on every token of frame f
+                te = self.dino_time_embed.weight[:Fn].repeat_interleave(L, dim=0).contiguous()
+                nat.add_rows(hs, te, Fn * L, 1.0)
+            return self.dino_resampler_adapter(self.dino_resampler(hs.unsqueeze(0)))
+
+        def vae_branch(lat, with_time):
+            Fn = lat.shape[0]
+            L = (lat.shape[2] // 2) * (lat.shape[3] // 2)
+            tok = torch.empty(Fn * L, 64, dtype=torch.bfloat16, device=lat.device)
+            for f in range(Fn):
+                nat.patchify(lat[f].contiguous(), tok[f * L:(f + 1) * L])
+            if with_time:
+                te = self.vae_time_embed.weight[:Fn].repeat_interleave(L, dim=0).contiguous()
+                nat.add_rows(tok, te, Fn * L, 1.0)
+            return self.vae_resampler_adapter(self.vae_resampler(tok.unsqueeze(0)))
+
+        def delta(a, b):
+            out = a.reshape(-1, a.shape[-1]).contiguous().clone()
+            nat.add_rows(out, b.reshape(-1, b.shape[-1]).contiguous(), out.shape[0], -1.0)
+            return out.view(a.shape)
+
+        return {"pseudo_special_emb_dino": delta(dino_branch(dino_middle, True), dino_branch(dino_source, False)),
+                "pseudo_special_emb_vae": delta(vae_branch(vae_middle_latents, True), vae_branch(vae_source_latents, False))}
+
+    def training_loss(self, global_step=None, **inputs):
+        """:313-329, forward value only (no autograd through the native kernels yet -- SURVEY 8f3)."""
+        timestep_id = torch.randint(0, self.scheduler.num_train_timesteps, (1,))
+        timestep = self.scheduler.timesteps[timestep_id].to(dtype=self.torch_dtype, device=self.device)
+        noise = torch.randn_like(inputs["input_latents"])
+        inputs["latents"] = self.scheduler.add_noise(inputs["input_latents"], noise, timestep)
+        target = self.scheduler.training_target(inputs["input_latents"], noise, timestep)
+        models = {name: getattr(self, name) for name in self.in_iteration_models}
+        noise_pred, special_token_loss = self.model_fn(**models, **inputs, timestep=timestep)
+        loss = torch.nn.functional.mse_loss(noise_pred.float(), target.float())
+        self.special_token_loss = float(special_token_loss.detach().mean().item()) if torch.is_tensor(special_token_loss) else 0.0
+        loss = loss * self.scheduler.training_weight(timestep)
+        return loss + special_token_loss
