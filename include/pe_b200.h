@@ -56,6 +56,8 @@ const char* pe_last_error(pe_handle_t h);
 /* Synchronises `stream` and reports whether any kernel since the last check hit a bounded-wait
  * timeout (PE_ERR_KERNEL_TIMEOUT; diagnostic word in *diag if non-NULL).  Test/debug helper. */
 int pe_check_async_error(pe_handle_t h, void* stream, unsigned int* diag);
+/* handle-owned device scratch (1 MiB): diagnostics of trace builds (-DPE_ATTN_TRACE) land here. */
+int pe_workspace(pe_handle_t h, void** ptr, size_t* bytes);
 /* number of SMs of the handle's device (grid sizing information for callers / benchmarks). */
 int pe_sm_count(pe_handle_t h);
 

@@ -27,6 +27,26 @@ constexpr int kTile = 128;           // query rows per tile, kv rows per tile, h
 constexpr int kHalfBytes = 128 * 64 * 2;   // one [128 x 64] bf16 swizzled half = 16 KB
 constexpr int kTileBytes = 2 * kHalfBytes; // 32 KB
 
+// Optional in-kernel timeline (build with -DPE_ATTN_TRACE): CTA 0 logs (event id, step, clock) triples of its first work
+// item into the handle's workspace; tools/attn_trace.py turns them into a per-step latency breakdown.
+#ifdef PE_ATTN_TRACE
+// fire-and-forget stores into a per-role region (role 0 = MMA issuer, 1 / 2 = softmax warp 0 of tile 0 / 1); the slot
+// counter lives in a register, so a trace point costs a clock read and one store (no round trip).
+#define PE_TRACE_DECL(role) unsigned int trace_n = 0; const int trace_role = (role);
+#define PE_TRACE(ev, step)                                                                                   \
+    do {                                                                                                     \
+        if (blockIdx.x == 0 && lane_id() == 0 && p.trace != nullptr && trace_n < 2000u) {                    \
+            long long* tp = p.trace + 2 + trace_role * 4000 + 2 * trace_n;                                   \
+            tp[0] = (static_cast<long long>(ev) << 32) | static_cast<unsigned int>(step);                    \
+            tp[1] = clock64();                                                                               \
+            ++trace_n;                                                                                       \
+        }                                                                                                    \
+    } while (0)
+#else
+#define PE_TRACE_DECL(role)
+#define PE_TRACE(ev, step) do {} while (0)
+#endif
+
 struct AttnParams {
     CUtensorMap tmQ, tmK, tmV;
     bf16* o;
@@ -39,6 +59,7 @@ struct AttnParams {
     float scale_log2;
     int swap_lbo_sbo;   // debug: swap the LBO/SBO roles of the MN-major V descriptor
     unsigned int* abort_flag;
+    long long* trace;
 };
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
@@ -68,6 +89,93 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+
+// ---- softmax helpers (one thread = one query row; a chunk = 32 consecutive kv columns) ------------------------------
+#ifndef PE_ATTN_POLY_EVERY
+#define PE_ATTN_POLY_EVERY 0      // >0: 1 of every N packed pairs takes the FMA-pipe exp2 instead of MUFU (measured: no gain on B200 with one softmax warp per SMSP)
+#endif
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], rel. error ~1e-4, far below
+// bf16's 2^-9): takes load off the MUFU unit, which is the co-bottleneck of the softmax on B200 (16 ex2/clk/SM).
+__device__ __forceinline__ float exp2_fma(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
+    float pz = fmaf(f, 0.05550410866f, 0.24022650696f);
+    pz = fmaf(pz, f, 0.69314718056f);
+    pz = fmaf(pz, f, 1.0f);
+    return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ void row_max_chunk(const uint32_t (&r)[32], int col0, int kv_valid, bool full, float& mx) {
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (col0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+}
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], int col0, int kv_valid, bool full, float scale_log2, float m,
+                                              float& lsum, float& mx, uint32_t (&pk)[16]) {
+    if (full) {
+        float s0 = 0.f, s1 = 0.f, m0 = mx, m1 = mx;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3])));
+        }
+        mx = fmaxf(m0, m1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaf(__uint_as_float(r[2 * i]), scale_log2, -m);
+            const float x1 = fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m);
+            float p0, p1;
+            if (PE_ATTN_POLY_EVERY > 0 && (i % (PE_ATTN_POLY_EVERY > 0 ? PE_ATTN_POLY_EVERY : 1)) == 1) { p0 = exp2_fma(x0); p1 = exp2_fma(x1); }
+            else { p0 = ex2(x0); p1 = ex2(x1); }
+            s0 += p0;
+            s1 += p1;
+            pk[i] = pack_bf16(p0, p1);
+        }
+        lsum += s0 + s1;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m));
+            float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m));
+            if (col0 + 2 * i >= kv_valid) p0 = 0.f; else mx = fmaxf(mx, __uint_as_float(r[2 * i]));
+            if (col0 + 2 * i + 1 >= kv_valid) p1 = 0.f; else mx = fmaxf(mx, __uint_as_float(r[2 * i + 1]));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+        }
+    }
+}
+// O[row, :] *= f for this thread's row (128 fp32 columns in TMEM); warp-collective
+__device__ __forceinline__ void scale_o_rows(uint32_t o_addr, float f, uint32_t (&tmp)[32]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        tmem_ld32(o_addr + c * 32, tmp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tmp[i] = __float_as_uint(__uint_as_float(tmp[i]) * f);
+        tmem_st32(o_addr + c * 32, tmp);
+    }
+    tmem_st_wait();
+}
+// P chunk c (32 kv columns, 16 packed words) -> TMEM (overlaying the consumed S columns [16c, 16c+16)) or swizzled smem
+template <bool kPTmem>
+__device__ __forceinline__ void store_p_chunk(const uint32_t (&pk)[16], int c, uint32_t p_row, int row_in_tile) {
+    if (kPTmem) {
+        tmem_st16(p_row + c * 16, pk);
+    } else {
+        // K-major 128B-swizzled [128 x 64] halves: row r at r*128, 16-byte chunk index ^ (r & 7)
+        const uint32_t rowb = p_row + (c >> 1) * kHalfBytes;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int chunk = (c & 1) * 4 + v;
+            st_shared_v4(rowb + ((chunk ^ (row_in_tile & 7)) << 4), pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+        }
+    }
 }
 
 template <int kQT, bool kPTmem>
@@ -176,6 +284,7 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
         uint32_t n = 0, it = 0;
         uint32_t p_phase[2] = {0, 0};
         bool ok = true;
+        PE_TRACE_DECL(0)
 
         auto issue_s = [&](int q, uint32_t k_base) {
             // S_q = Q_q K^T : 8 k-steps of 16 head-dim elements; +32 B inside a swizzle row, +16 KB per half
@@ -239,11 +348,14 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
                         // previous item's epilogue must have drained O_q
                         if (!mbar_wait(o_empty(q), (it & 1u) ^ 1u, p.abort_flag, 24)) { ok = false; break; }
                     }
+                    PE_TRACE(10 + q, j);
                     if (!mbar_wait(p_full(q), p_phase[q], p.abort_flag, 25)) { ok = false; break; }
                     p_phase[q] ^= 1u;
                     tc_fence_after();
+                    PE_TRACE(12 + q, j);
                     issue_pv(q, kv_smem(v_slot), j > 0);
                     if (more) issue_s(q, kv_smem(k_slot));
+                    PE_TRACE(14 + q, j);
                 }
                 if (!ok) break;
                 if (elect_one()) {
@@ -262,102 +374,113 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
         const uint32_t s_addr = s_tmem(q) + lane_off;
         const uint32_t o_addr = o_tmem(q) + lane_off;
         const int row_in_tile = wq * 32 + lane;
-        uint32_t s_phase = 0, pv_phase = 0;
+        uint32_t s_phase = 0, pv_commits = 0;
         bool ok = true;
+        PE_TRACE_DECL(1 + q)
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
             const int head = item / p.n_qblk;
             const int qb = item - head * p.n_qblk;
-            float m_used = -INFINITY;
+            // Softmax state.  m_ref is the exponent reference (log2 domain) of everything accumulated in O and l so far.
+            // It trails the true running max: a KV step exponentiates against the max of the PREVIOUS steps (one pass over
+            // S instead of two), and the reference is only moved -- with a deferred O rescale -- when the max grew by more
+            // than 2^8.  A stale (lower) reference scales P, O and l by the same factor, which the final O/l cancels; a guard
+            // re-does the step exactly in the (practically unreachable) case where the jump could overflow.
+            float m_ref = -INFINITY;
             float l = 0.f;
+            float f_pending = 1.0f;        // O must still be multiplied by this (applied after the previous PV finished)
             for (int j = 0; j < p.n_kv; ++j) {
+                if (wq == 0) PE_TRACE(20 + q, j);
                 if (!mbar_wait(s_full(q), s_phase, p.abort_flag, 30)) { ok = false; break; }
                 s_phase ^= 1u;
                 tc_fence_after();
+                if (wq == 0) PE_TRACE(22 + q, j);
                 const int kv_valid = p.S - j * kTile;     // >= 128 except possibly on the last tile
-                // ---- pass 1: row max ----
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(s_addr + c * 32, r);
+                const bool full = kv_valid >= kTile;
+                uint32_t ra[32], rb[32];
+                if (j == 0) {
+                    // first tile: exact row max (two passes), TMEM loads software-pipelined
+                    float mx = -INFINITY;
+                    tmem_ld32(s_addr, ra);
                     tmem_ld_wait();
-                    if (kv_valid >= kTile) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    }
+                    tmem_ld32(s_addr + 32, rb);
+                    row_max_chunk(ra, 0, kv_valid, full, mx);
+                    tmem_ld_wait();
+                    tmem_ld32(s_addr + 64, ra);
+                    row_max_chunk(rb, 32, kv_valid, full, mx);
+                    tmem_ld_wait();
+                    tmem_ld32(s_addr + 96, rb);
+                    row_max_chunk(ra, 64, kv_valid, full, mx);
+                    tmem_ld_wait();
+                    row_max_chunk(rb, 96, kv_valid, full, mx);
+                    m_ref = mx * p.scale_log2;
                 }
-                const float mx_scaled = mx * p.scale_log2;
-                float m_new = m_used;
-                bool need = false;
-                if (mx_scaled > m_used + 8.0f) { m_new = mx_scaled; need = true; }
+                tmem_ld32(s_addr, ra);       // first chunk is fetched while we wait for PV(j-1)
                 if (j > 0) {
-                    // PV(j-1) must have finished: it reads P (which we are about to overwrite) and updates O
-                    if (!mbar_wait(pv_done(q), pv_phase, p.abort_flag, 31)) { ok = false; break; }
-                    pv_phase ^= 1u;
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float f = need ? ex2(m_used - m_new) : 1.0f;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t r[32];
-                            tmem_ld32(o_addr + c * 32, r);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                            tmem_st32(o_addr + c * 32, r);
-                        }
-                        tmem_st_wait();
-                        l *= f;
+                    // PV(j-1) reads P (which we are about to overwrite) and updates O.  It was issued before S(j) and the
+                    // tensor pipe executes in order, so the s_full(j) arrival above already implies PV(j-1) has completed:
+                    // no separate wait on pv_done is needed inside the loop.
+                    if (__any_sync(0xffffffffu, f_pending != 1.0f)) {
+                        tmem_ld_wait();
+                        scale_o_rows(o_addr, f_pending, rb);
                     }
                 }
-                m_used = m_new;
-                // ---- pass 2: P = exp2(S*scale - m), row sum, write P ----
-                float lsum = 0.f;
+                f_pending = 1.0f;
+                if (wq == 0) PE_TRACE(24 + q, j);
+                // ---- single pass: P = exp2(S*scale - m_ref), row sum, row max of this tile ----
+                float lsum = 0.f, mx = -INFINITY;
+                uint32_t pk[64];
+                tmem_ld_wait();
+                tmem_ld32(s_addr + 32, rb);
+                softmax_chunk(ra, 0, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                tmem_ld_wait();
+                tmem_ld32(s_addr + 64, ra);
+                softmax_chunk(rb, 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                tmem_ld_wait();
+                tmem_ld32(s_addr + 96, rb);
+                softmax_chunk(ra, 64, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[32]));
+                tmem_ld_wait();
+                softmax_chunk(rb, 96, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[48]));
+                const float mx_scaled = mx * p.scale_log2;
+                if (__any_sync(0xffffffffu, mx_scaled - m_ref > 100.0f)) {
+                    // overflow guard (never taken for sane logits): move the reference to the true max and redo the tile.
+                    // S is still intact in TMEM because P has not been stored yet.
+                    const float m_new = fmaxf(m_ref, mx_scaled);
+                    const float f = ex2(m_ref - m_new);
+                    if (j > 0) scale_o_rows(o_addr, f, rb);
+                    l *= f;
+                    m_ref = m_new;
+                    lsum = 0.f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(s_addr + c * 32, r);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_used));
-                        float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_used));
-                        if (kv_valid < kTile) {
-                            if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
-                            if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
-                        }
-                        lsum += p0 + p1;
-                        pk[i] = pack_bf16(p0, p1);
-                    }
-                    if (kPTmem) {
-                        tmem_st16(s_addr + c * 16, pk);   // P chunk c overlays S columns [16c, 16c+16): already consumed
-                    } else {
-                        // K-major 128B-swizzled [128 x 64] halves: row r at r*128, 16-byte chunk index ^ (r & 7)
-                        const uint32_t rowb = p_smem(q) + (c >> 1) * kHalfBytes + row_in_tile * 128;
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const int chunk = (c & 1) * 4 + v;
-                            st_shared_v4(rowb + ((chunk ^ (row_in_tile & 7)) << 4), pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld32(s_addr + c * 32, ra);
+                        tmem_ld_wait();
+                        softmax_chunk(ra, c * 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
                     }
                 }
-                l += lsum;
+                if (wq == 0) PE_TRACE(26 + q, j);
+                const uint32_t p_row = kPTmem ? s_addr : p_smem(q) + row_in_tile * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_p_chunk<kPTmem>(*reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]), c, p_row, row_in_tile);
                 if (kPTmem) tmem_st_wait(); else fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full(q));
+                if (wq == 0) PE_TRACE(28 + q, j);
+                l += lsum;
+                // lazy reference update for the following steps (O is rescaled after PV(j) has finished)
+                if (mx_scaled > m_ref + 8.0f) {
+                    f_pending = ex2(m_ref - mx_scaled);
+                    l *= f_pending;
+                    m_ref = mx_scaled;
+                }
             }
             if (!ok) break;
+
             // ---- epilogue: O / l -> bf16 -> global ----
-            if (!mbar_wait(pv_done(q), pv_phase, p.abort_flag, 32)) break;
-            pv_phase ^= 1u;
+            pv_commits += (uint32_t)p.n_kv;                     // the MMA issuer commits pv_done once per KV step
+            if (!mbar_wait(pv_done(q), (pv_commits - 1u) & 1u, p.abort_flag, 32)) break;
             tc_fence_after();
-            const float inv = 1.0f / l;
+            const float inv = f_pending / l;     // includes the O rescale still pending from the last step
             const long long row = (long long)(qb * kQT + q) * kTile + row_in_tile;
             bf16* orow = p.o + row * p.ldo + head * kTile;
 #pragma unroll
@@ -501,6 +624,10 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     p.scale_log2 = scale * 1.4426950408889634f;
     p.swap_lbo_sbo = (flags & PE_ATTN_FLAG_SWAP_V_DESC) ? 1 : 0;
     p.abort_flag = h->abort_flag;
+#ifdef PE_ATTN_TRACE
+    p.trace = static_cast<long long*>(h->workspace);
+    if (p.trace) cudaMemsetAsync(p.trace, 0, 200000, stream);
+#endif
     const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;
     const bool p_smem = (flags & PE_ATTN_FLAG_P_VIA_SMEM) != 0;
     if (one_tile) return p_smem ? launch_attention<1, false>(h, p, stream) : launch_attention<1, true>(h, p, stream);

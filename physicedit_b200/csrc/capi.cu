@@ -91,6 +91,12 @@ int pe_create(pe_handle_t* out, int device) {
         delete h;
         return PE_ERR_OUT_OF_MEMORY;
     }
+    h->workspace_bytes = 1 << 20;
+    if (cudaMalloc(&h->workspace, h->workspace_bytes) != cudaSuccess || cudaMemset(h->workspace, 0, h->workspace_bytes) != cudaSuccess) {
+        cudaFree(h->abort_flag);
+        delete h;
+        return PE_ERR_OUT_OF_MEMORY;
+    }
     *out = reinterpret_cast<pe_handle_t>(h);
     return PE_OK;
 }
@@ -112,6 +118,14 @@ const char* pe_last_error(pe_handle_t hh) {
 int pe_sm_count(pe_handle_t hh) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     return h ? h->sm_count : PE_ERR_INVALID_ARGUMENT;
+}
+
+int pe_workspace(pe_handle_t hh, void** ptr, size_t* bytes) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (h == nullptr || ptr == nullptr || bytes == nullptr) return PE_ERR_INVALID_ARGUMENT;
+    *ptr = h->workspace;
+    *bytes = h->workspace_bytes;
+    return PE_OK;
 }
 
 int pe_check_async_error(pe_handle_t hh, void* stream, unsigned int* diag) {

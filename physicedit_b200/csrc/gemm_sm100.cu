@@ -5,7 +5,10 @@
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (UMMA 128x256x16, or
 //                                256x256x16 on a CTA pair with cta_group::2)
 //   warp 2      TMEM allocator : 512 columns = 2 accumulator stages x 256 fp32 columns
-//   warps 4..7  epilogue       : tcgen05.ld -> registers -> fused epilogue -> global
+//   warps 4..11 epilogue       : tcgen05.ld -> registers -> fused epilogue -> global.  Two warps per TMEM lane
+//                                quarter, each owning one 128-column half of the 256-column accumulator
+//                                (for the QKV epilogue: one attention head), so the epilogue of a tile costs
+//                                half as many cycles per warp and stays hidden behind the next tile's MMAs.
 // The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of
 // tile i+1.  A "segment" is a token stream with its own weights (image / text stream of the
 // double-stream DiT block): both streams run in ONE launch, each with its own tensor maps, which
@@ -25,7 +28,8 @@ namespace {
 constexpr int kBlockK = 64;        // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kTileN = 256;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kGroupM = 8;         // rasterisation: 8 m-tiles share a sweep over n
 
 struct SegDev {
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4 * kCG);   // one elected arrival per epilogue warp (of both CTAs)
+            mbar_init(tempty_bar(a), kEpiWarps * kCG);   // one elected arrival per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
@@ -330,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int ew = warp - 4;                 // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        const int ew = (warp - 4) & 3;           // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        const int half = (warp - 4) >> 2;        // which 128-column half of the accumulator this warp drains
         const int lane = lane_id();
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -343,15 +348,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
             const bool row_valid = row < sg.M;
             if (EPI == PE_EPI_QKV_NORM_ROPE) {
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int n_head0 = tile.n0 + hh * 128;
-                    if (n_head0 >= p.N) break;
-                    epilogue_qkv_head(taddr + hh * 128, sg, row, row_valid, n_head0, p.heads);
-                }
+                const int n_head0 = tile.n0 + half * 128;
+                if (n_head0 < p.N) epilogue_qkv_head(taddr + half * 128, sg, row, row_valid, n_head0, p.heads);
             } else {
 #pragma unroll 1
-                for (int c = 0; c < kTileN / 32; ++c) {
+                for (int c = half * 4; c < half * 4 + 4; ++c) {
                     const int n = tile.n0 + c * 32;
                     if (n >= p.N) break;
                     uint32_t r[32];

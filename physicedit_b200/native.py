@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpe_b200.so")
+_LIB_PATH = os.environ.get("PE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpe_b200.so")
 
 PE_OK = 0
 EPI_BIAS = 0
@@ -29,7 +29,7 @@ ATTN_FLAG_P_VIA_SMEM = 2
 ATTN_FLAG_SWAP_V_DESC = 4
 
 EXPORTED_SYMBOLS = [
-    "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count",
+    "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count", "pe_workspace",
     "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
     "pe_rmsnorm", "pe_gemv", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
@@ -65,6 +65,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_create.argtypes = [POINTER(c_void_p), c_int]
     lib.pe_destroy.argtypes = [c_void_p]
     lib.pe_sm_count.argtypes = [c_void_p]
+    lib.pe_workspace.argtypes = [c_void_p, POINTER(c_void_p), POINTER(ctypes.c_size_t)]
     lib.pe_check_async_error.argtypes = [c_void_p, c_void_p, POINTER(c_uint)]
     lib.pe_gemm.argtypes = [c_void_p, POINTER(GemmSeg), c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.pe_attention_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p]
@@ -153,6 +154,15 @@ class Native:
         out = {}
         for tag, evs in (self.prof or {}).items():
             out[tag] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+        return out
+
+    def workspace_read(self, n_int64: int) -> torch.Tensor:
+        """Copy of the first n_int64 words of the handle's diagnostic scratch (trace builds write there)."""
+        ptr, nbytes = c_void_p(), ctypes.c_size_t()
+        self._check(self.lib.pe_workspace(self.h, byref(ptr), byref(nbytes)), "pe_workspace")
+        out = torch.empty(n_int64, dtype=torch.int64)
+        torch.cuda.synchronize(self.device)
+        ctypes.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(c_void_p(out.data_ptr()), ptr, ctypes.c_size_t(n_int64 * 8), c_int(2))
         return out
 
     def check_async(self) -> None:

@@ -113,6 +113,15 @@ def test_attention_peaked_rows_trigger_lazy_rescale(nat):
     nat.check_async()
     ref = torch.softmax(q.float() @ k.float().t() / math.sqrt(128), dim=-1) @ v.float()
     assert rel_l2(o, ref) < 5e-3
+    # a jump of more than 2^100 between consecutive KV tiles takes the overflow-guard (redo) path
+    k2 = torch.randn(S, 128, device="cuda").bfloat16()
+    k2[384:] *= 60.0
+    for flags in (0, 3):
+        nat.attention(q, k2, v, o, H, 1 / math.sqrt(128), flags)
+        nat.check_async()
+        ref = torch.softmax(q.float() @ k2.float().t() / math.sqrt(128), dim=-1) @ v.float()
+        assert torch.isfinite(o.float()).all()
+        assert rel_l2(o, ref) < 1e-2
 
 
 @gpu
