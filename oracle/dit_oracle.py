@@ -71,7 +71,7 @@ def timestep_sinusoid(ts: torch.Tensor) -> torch.Tensor:
     """get_timestep_embedding(ts, 256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000,
     align_dtype_to_timestep=True) -> fp32 [B, 256] (cos half first).  ts already holds timestep/1000."""
     half = 128
-    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=ts.device)
     exponent = exponent / (half - 0)
     emb = torch.exp(exponent)
     emb = emb.to(ts.dtype)                                     # align_dtype_to_timestep: bf16 freqs on the bf16 path
@@ -450,7 +450,8 @@ def synth_weights(shapes: Dict[str, Tuple[int, ...]], seed: int, dtype=torch.flo
             b = weight_gain / math.sqrt(shp[1])
             t = (torch.rand(shp, generator=g, dtype=torch.float32) * 2 - 1) * b
         elif key.endswith(".bias"):
-            fan_in = shapes[key[:-5] + ".weight"][1]
+            wshape = shapes.get(key[:-5] + ".weight", ())
+            fan_in = wshape[1] if len(wshape) == 2 else 2500          # LayerNorm biases: small values
             t = (torch.rand(shp, generator=g, dtype=torch.float32) * 2 - 1) / math.sqrt(fan_in)
         else:
             t = 1 + 0.1 * torch.randn(shp, generator=g, dtype=torch.float32)

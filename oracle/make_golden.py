@@ -196,6 +196,38 @@ def main():
     out["loop"] = dict(meta=dict(num_layers=NL2, height=H2, T_posi=T2, T_nega=T2 - 3, steps=4, w_seed=4, a_seed=2, posi_seed=6, nega_seed=7),
                        latents=lat.clone(), prompt_emb_posi_after=pe_p[posi["special_token_mask"]][:, ::8].clone())
 
+    # ---- training-path feature extractors: reference PerceiverResampler / VisualThinkingAdapter and HF DINOv2 ----
+    from oracle import aux_oracle as AO
+    import tempfile
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+    dino_mod = importlib.import_module("diffsynth.pipelines.dinov2")
+    P = AO.aux_synth(seed=11)
+    ain = AO.aux_inputs(seed=12)
+    cfgd = Dinov2WithRegistersConfig(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, mlp_ratio=4, patch_size=14, image_size=518,
+                                     num_register_tokens=4)
+    with tempfile.TemporaryDirectory() as td:
+        hf = Dinov2WithRegistersModel(cfgd)
+        missing = hf.load_state_dict(P["dinov2"], strict=True)
+        hf.save_pretrained(td)
+        dn = dino_mod.Dinov2withNorm(dinov2_path=td).eval()          # the reference wrapper around the HF model
+    dino_src = dn(ain["dino_source"])
+    dino_mid = dn(ain["dino_middle"])
+    def ref_resampler(dim, max_tok, W):
+        m = helpers.PerceiverResampler(dim=dim, num_latents=64, depth=2, max_num_media_tokens=max_tok)
+        m.load_state_dict(W)
+        return m.eval()
+    dr, vr = ref_resampler(768, 4096, P["dino_resampler"]), ref_resampler(64, 10240, P["vae_resampler"])
+    da = helpers.VisualThinkingAdapter(768, 3584); da.load_state_dict(P["dino_resampler_adapter"])
+    va = helpers.VisualThinkingAdapter(64, 3584); va.load_state_dict(P["vae_resampler_adapter"])
+    hs_mid = dino_mid + P["dino_time_embed"]["weight"][:3].unsqueeze(1)
+    r_mid = dr(hs_mid.reshape(1, -1, 768))
+    emb_dino = da(r_mid) - da(dr(dino_src.reshape(1, -1, 768)))
+    tok_mid = O.patchify(ain["vae_middle_latents"]) + P["vae_time_embed"]["weight"][:3].unsqueeze(1)
+    emb_vae = va(vr(tok_mid.reshape(1, -1, 64))) - va(vr(O.patchify(ain["vae_source_latents"]).reshape(1, -1, 64)))
+    out["aux"] = dict(seed=11, in_seed=12, dino_source=dino_src[:, ::4, ::8].clone(), dino_middle=dino_mid[:, ::4, ::8].clone(),
+                      resampler_dino_mid=r_mid[..., ::4].clone(), pseudo_special_emb_dino=emb_dino[..., ::8].clone(),
+                      pseudo_special_emb_vae=emb_vae[..., ::8].clone(), transformers=__import__("transformers").__version__)
+
     for k, v in out.items():
         torch.save(v, os.path.join(GOLD, f"{k}.pt"))
         print(k, os.path.getsize(os.path.join(GOLD, f"{k}.pt")) // 1024, "KiB")

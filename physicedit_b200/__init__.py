@@ -1,0 +1,32 @@
+"""physicedit_b200 -- B200-native (sm_100a) hot path of PhysicEdit / Qwen-Image-Edit behind DiffSynth-Studio's API surface.
+
+Public entry points:
+    model_fn_qwen_image      drop-in for pipelines/qwen_image_physical.py:1302-1403 (install as `pipe.model_fn`)
+    QwenImagePhysicPipeline  the pipeline with the reference's constructor / loader / LoRA / denoise surface
+    QwenImageDiT, adopt_dit  the DiT with the reference's parameter layout; adopt a loaded reference module
+    FlowMatchScheduler, GeneralLoRALoader, ModelConfig, load_state_dict
+Everything numeric runs in physicedit_b200/lib/libpe_b200.so (include/pe_b200.h); there is no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+_LAZY = {
+    "model_fn_qwen_image": ("model_fn", "model_fn_qwen_image"),
+    "QwenImagePhysicPipeline": ("pipeline", "QwenImagePhysicPipeline"),
+    "ModelConfig": ("pipeline", "ModelConfig"),
+    "load_state_dict": ("pipeline", "load_state_dict"),
+    "load_dit": ("pipeline", "load_dit"),
+    "QwenImageDiT": ("dit", "QwenImageDiT"),
+    "FlowMatchScheduler": ("scheduler", "FlowMatchScheduler"),
+    "GeneralLoRALoader": ("lora", "GeneralLoRALoader"),
+    "VisualThinkingDualAdapter": ("adapters", "VisualThinkingDualAdapter"),
+    "adopt_dit": ("compat", "adopt_dit"),
+    "adopt_adapter": ("compat", "adopt_adapter"),
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    raise AttributeError(name)

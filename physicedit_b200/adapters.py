@@ -280,13 +280,11 @@ class Dinov2Encoder(nn.Module):
         n_tok = 1 + self.n_reg + gh * gw
         x = torch.empty(Fn, n_tok, hid, dtype=torch.bfloat16, device=pixel_values.device)
         pos = self._pos(gh, gw)
+        nat.add_rows(patches, pos[1:], gh * gw, 1.0)                          # patch tokens + interpolated position embedding
         x[:, 0] = self.embeddings.cls_token[0, 0] + pos[0]
-        x[:, 1:1 + self.n_reg] = self.embeddings.register_tokens[0]
+        x[:, 1:1 + self.n_reg] = self.embeddings.register_tokens[0]           # registers carry no position embedding
         x[:, 1 + self.n_reg:] = patches.view(Fn, gh * gw, hid)
         x = x.view(Fn * n_tok, hid)
-        body = x.view(Fn, n_tok, hid)[:, 1 + self.n_reg:].reshape(Fn * gh * gw, hid)   # copy: add positions to the patch tokens
-        nat.add_rows(body, pos[1:], gh * gw, 1.0)
-        x.view(Fn, n_tok, hid)[:, 1 + self.n_reg:] = body.view(Fn, gh * gw, hid)
         h = torch.empty_like(x)
         o = torch.empty_like(x)
         d = hid // self.heads

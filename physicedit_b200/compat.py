@@ -1,0 +1,76 @@
+"""Glue for running the reference's own scripts / pipeline objects on the native path.
+
+* `adopt_dit(ref_dit)` / `adopt_adapter(ref_adapter)`: wrap modules that the REFERENCE loaded (its ModelManager, LoRA loader,
+  `load_state_dict(strict=False)`) into the native classes without copying weights (`load_state_dict(assign=True)`).
+* `install()`: registers a `diffsynth` alias package so that the imports used by scripts/inference/*.py and
+  scripts/train/train_physicedit.py (`from diffsynth import load_state_dict`, `from diffsynth.pipelines.qwen_image_physical import
+  QwenImagePhysicPipeline, ModelConfig`, `from diffsynth.pipelines.flux_image_new import ControlNetInput`) resolve here.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+
+def adopt_dit(ref_dit: torch.nn.Module):
+    from .dit import QwenImageDiT
+    n = len(ref_dit.transformer_blocks)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=n)
+    dit.load_state_dict(ref_dit.state_dict(), assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    for i, b in enumerate(dit.transformer_blocks):
+        object.__setattr__(b, "_owner", (dit, i))
+    return dit.eval()
+
+
+def adopt_adapter(ref_adapter: torch.nn.Module):
+    from .adapters import VisualThinkingDualAdapter
+    with torch.device("meta"):
+        ad = VisualThinkingDualAdapter(3584, 3584, ref_adapter.t_min, ref_adapter.t_max)
+    ad.load_state_dict(ref_adapter.state_dict(), assign=True)
+    return ad.eval()
+
+
+@dataclass
+class ControlNetInput:
+    """pipelines/flux_image_new.py:5-13 (only imported by the scripts; blockwise controlnet is out of scope)."""
+    controlnet_id: int = 0
+    scale: float = 1.0
+    start: float = 1.0
+    end: float = 0.0
+    image: Optional[object] = None
+    inpaint_mask: Optional[object] = None
+    processor_id: Optional[str] = None
+
+
+def install() -> None:
+    from . import pipeline, scheduler, lora, dit, adapters, model_fn
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    root = mod("diffsynth", load_state_dict=pipeline.load_state_dict, ModelConfig=pipeline.ModelConfig)
+    root.__path__ = []
+    mod("diffsynth.pipelines").__path__ = []
+    mod("diffsynth.pipelines.qwen_image_physical", QwenImagePhysicPipeline=pipeline.QwenImagePhysicPipeline, ModelConfig=pipeline.ModelConfig,
+        model_fn_qwen_image=model_fn.model_fn_qwen_image, SPECIAL_TOKEN_NUM=pipeline.SPECIAL_TOKEN_NUM)
+    mod("diffsynth.pipelines.flux_image_new", ControlNetInput=ControlNetInput)
+    mod("diffsynth.pipelines.helpers", **{k: getattr(adapters, k) for k in ("FeedForward", "PerceiverAttention", "PerceiverResampler",
+                                                                              "VisualThinkingAdapter", "VisualThinkingDualAdapter")})
+    mod("diffsynth.pipelines.dinov2", Dinov2withNorm=adapters.Dinov2withNorm)
+    mod("diffsynth.models").__path__ = []
+    mod("diffsynth.models.qwen_image_dit", QwenImageDiT=dit.QwenImageDiT, QwenImageTransformerBlock=dit.QwenImageTransformerBlock,
+        QwenEmbedRope=dit.QwenEmbedRope, RMSNorm=dit.RMSNorm)
+    mod("diffsynth.models.utils", load_state_dict=pipeline.load_state_dict, hash_state_dict_keys=pipeline.hash_state_dict_keys,
+        RMSNorm=dit.RMSNorm, AdaLayerNorm=dit.AdaLayerNorm, TimestepEmbeddings=dit.TimestepEmbeddings)
+    mod("diffsynth.schedulers").__path__ = []
+    mod("diffsynth.schedulers.flow_match", FlowMatchScheduler=scheduler.FlowMatchScheduler)
+    mod("diffsynth.lora", GeneralLoRALoader=lora.GeneralLoRALoader)

@@ -279,3 +279,76 @@ def test_lora_fold_and_denoise_loop(golden):
     err = rel_l2(lat, lat32)
     assert err <= floor + TOL_EXTRA, (err, floor)
     assert torch.isfinite(lat).all()
+
+
+@gpu
+def test_training_path_feature_extractors(golden):
+    """DINOv2-with-registers, perceiver resamplers, VisualThinkingAdapters and the
+    pseudo_special_emb targets on the CUDA path vs the fp32 oracle (same seeded, bf16-representable weights)."""
+    from oracle import aux_oracle as AO
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    g = golden("aux")
+    P = AO.aux_synth(seed=g["seed"], dtype=torch.bfloat16)
+    ain = AO.aux_inputs(seed=g["in_seed"], dtype=torch.bfloat16)
+    pipe = QwenImagePhysicPipeline(device="cuda", torch_dtype=torch.bfloat16, dinov2_config=dict(hidden=768, layers=12, heads=12))
+    pipe.dinov2.encoder.load_state_dict({k: v for k, v in P["dinov2"].items() if not k.startswith("layernorm.")}, strict=True)
+    pipe.dino_resampler.load_state_dict(P["dino_resampler"])
+    pipe.vae_resampler.load_state_dict(P["vae_resampler"])
+    pipe.dino_resampler_adapter.load_state_dict(P["dino_resampler_adapter"])
+    pipe.vae_resampler_adapter.load_state_dict(P["vae_resampler_adapter"])
+    pipe.dino_time_embed.load_state_dict(P["dino_time_embed"])
+    pipe.vae_time_embed.load_state_dict(P["vae_time_embed"])
+    pipe.to("cuda")
+    Pf = {k: {n: t.float() for n, t in v.items()} for k, v in P.items()}
+    af = {k: v.float() for k, v in ain.items()}
+    with torch.no_grad():
+        d_nat = pipe.dinov2(ain["dino_middle"].cuda())
+        d_ref = AO.dinov2_with_norm(Pf["dinov2"], af["dino_middle"])
+        d_b16 = AO.dinov2_with_norm(P["dinov2"], ain["dino_middle"])
+        floor = rel_l2(d_b16, d_ref)
+        assert d_nat.shape == (3, 256, 768)
+        assert rel_l2(d_nat, d_ref) <= floor + 2e-3, (rel_l2(d_nat, d_ref), floor)
+        hs = torch.randn(1, 700, 768, generator=torch.Generator().manual_seed(3)).bfloat16()
+        r_nat = pipe.dino_resampler(hs.cuda())
+        r_ref = AO.perceiver_resampler(Pf["dino_resampler"], hs.float())
+        assert rel_l2(r_nat, r_ref) <= rel_l2(AO.perceiver_resampler(P["dino_resampler"], hs), r_ref) + 2e-3
+        out = pipe.physical_visual_embeddings(**{k: v.cuda() for k, v in ain.items()})
+        ed, ev = AO.physical_visual_embeddings(Pf, **af)
+        ed16, ev16 = AO.physical_visual_embeddings(P, **ain)
+        assert out["pseudo_special_emb_dino"].shape == (1, 64, 3584)
+        assert rel_l2(out["pseudo_special_emb_dino"], ed) <= rel_l2(ed16, ed) + 5e-3
+        assert rel_l2(out["pseudo_special_emb_vae"], ev) <= rel_l2(ev16, ev) + 5e-3
+    from physicedit_b200 import native as nv
+    nv.Native.get(0).check_async()
+
+
+@gpu
+def test_training_loss_forward_value(golden):
+    """training_loss (qwen_image_physical.py:313-329): flow-matching MSE x weight + adapter loss, forward value."""
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    fwd = golden("forward")
+    meta = fwd["meta"]
+    dit, W = _build_dit(1, meta["w_seed"])
+    pipe = QwenImagePhysicPipeline(device="cuda", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    A = {k: v.to(torch.bfloat16) for k, v in O.synth_weights(O.adapter_param_shapes(), seed=meta["a_seed"]).items()}
+    pipe.visual_thinking_adapter.load_state_dict(A)
+    pipe.visual_thinking_adapter.to(device="cuda", dtype=torch.bfloat16)
+    pipe.scheduler.set_timesteps(1000, training=True)
+    inp = O.synth_inputs(64, 64, 72, seed=8, dtype=torch.bfloat16)
+    torch.manual_seed(0)
+    gt_d = torch.randn(1, 64, 3584).bfloat16().cuda()
+    gt_v = torch.randn(1, 64, 3584).bfloat16().cuda()
+    pe = inp["prompt_emb"].cuda().clone()
+    loss = pipe.training_loss(input_latents=inp["latents"].cuda(), prompt_emb=pe, prompt_emb_mask=inp["prompt_emb_mask"].cuda(),
+                              special_token_mask=inp["special_token_mask"].cuda(), height=64, width=64, edit_latents=inp["edit_latents"].cuda(),
+                              pseudo_special_emb_dino=gt_d, pseudo_special_emb_vae=gt_v, is_train=True)
+    assert torch.isfinite(loss).all() and loss.item() > 0
+    assert pipe.special_token_loss > 0
+    # the adapter loss matches the oracle's formula on the predictions the native heads produced
+    x = inp["prompt_emb"][inp["special_token_mask"]].view(1, 64, 3584).cuda()
+    _, pd, pv = pipe.visual_thinking_adapter(x, torch.tensor([500.0]).bfloat16().cuda())
+    l_nat = pipe.visual_thinking_adapter.get_loss(pd, pv, gt_d, gt_v, torch.tensor([500.0]).bfloat16().cuda()).item()
+    l_ora = O.adapter_loss(pd.cpu().float(), pv.cpu().float(), gt_d.cpu().float(), gt_v.cpu().float(), torch.tensor([500.0]).bfloat16(),
+                           meta["t_min"], meta["t_max"]).item()
+    assert abs(l_nat - l_ora) < 2e-2 * abs(l_ora)

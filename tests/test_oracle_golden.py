@@ -190,3 +190,26 @@ def test_denoise_loop_matches_reference(golden):
     lat = O.denoise_loop(W, A, posi["latents"].clone(), posi, nega, posi["edit_latents"], meta["height"], meta["height"], meta["steps"])
     assert rel_l2(lat, g["latents"]) < 5e-6
     assert rel_l2(posi["prompt_emb"][posi["special_token_mask"]][:, ::8], g["prompt_emb_posi_after"]) < 5e-6
+
+
+def test_aux_training_path_oracle_matches_reference(golden):
+    """DINOv2-with-registers (transformers 5.5.0 through the reference's Dinov2withNorm), perceiver resamplers and
+    VisualThinkingAdapters: oracle/aux_oracle.py vs outputs of the reference modules (fp32, seeded weights)."""
+    from oracle import aux_oracle as AO
+    g = golden("aux")
+    P = AO.aux_synth(seed=g["seed"])
+    ain = AO.aux_inputs(seed=g["in_seed"])
+    with torch.no_grad():
+        src = AO.dinov2_with_norm(P["dinov2"], ain["dino_source"])
+        mid = AO.dinov2_with_norm(P["dinov2"], ain["dino_middle"])
+        assert src.shape == (1, 256, 768) and mid.shape == (3, 256, 768)
+        assert rel_l2(src[:, ::4, ::8], g["dino_source"]) < 2e-5
+        assert rel_l2(mid[:, ::4, ::8], g["dino_middle"]) < 2e-5
+        # non-affine final LayerNorm: unit variance per token
+        assert abs(src.var(dim=-1, unbiased=False).mean().item() - 1.0) < 1e-3
+        hs = (mid + P["dino_time_embed"]["weight"][:3].unsqueeze(1)).reshape(1, -1, 768)
+        assert rel_l2(AO.perceiver_resampler(P["dino_resampler"], hs)[..., ::4], g["resampler_dino_mid"]) < 2e-5
+        ed, ev = AO.physical_visual_embeddings(P, **ain)
+        assert ed.shape == ev.shape == (1, 64, 3584)
+        assert rel_l2(ed[..., ::8], g["pseudo_special_emb_dino"]) < 5e-5
+        assert rel_l2(ev[..., ::8], g["pseudo_special_emb_vae"]) < 5e-5

@@ -1,0 +1,143 @@
+"""Host-side logic of the data-parallel layer on CPU: world_size 2, gloo backend (one image per rank,
+one weight broadcast at start-up, one final gather, no per-step collective)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from physicedit_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                      # ranks start with DIFFERENT weights
+        fused = torch.randn(6, 4)
+        m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(4, 3))
+        m[0].weight.data = fused[0:3]                      # views into one storage, like the engine's fused QKV buffer
+        m[1].weight.data = fused[3:6]
+        nbytes = parallel.broadcast_weights(m, src=0)
+        ref = [torch.zeros_like(fused)]
+        if rank == 0:
+            ref = [fused.clone()]
+        dist.broadcast(ref[0], src=0)
+        same = torch.equal(fused, ref[0])
+        mine = parallel.shard_indices(5)
+        lat = torch.full((len(mine[:2]), 16, 2, 2), float(rank))
+        gathered = parallel.gather_latents(lat[:2], dst=0)
+        q.put((rank, same, nbytes, mine, None if gathered is None else [float(g.mean()) for g in gathered]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_shard_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, same0, n0, mine0, g0), (r1, same1, n1, mine1, g1) = res
+    assert same0 and same1                                  # rank 1 now holds rank 0's weights (through the views)
+    assert n0 == n1 == (6 * 4 + 3 + 3) * 4                  # shared storage de-duplicated per view, biases separate
+    assert mine0 == [0, 2, 4] and mine1 == [1, 3]           # disjoint, exhaustive
+    assert g0 == [0.0, 1.0] and g1 is None
+
+
+def test_shard_indices_cover_everything():
+    for n in (0, 1, 7, 8, 9, 64):
+        for world in (1, 2, 4, 8):
+            parts = [parallel.shard_indices(n, r, world) for r in range(world)]
+            flat = sorted(i for p in parts for i in p)
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The C-ABI library loads on a CPU-only host and exports every symbol include/pe_b200.h declares."""
+    import re
+    from physicedit_b200 import native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = native.load_library()
+    hdr = open(os.path.join(root, "include", "pe_b200.h")).read()
+    declared = set(re.findall(r"\b(pe_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in pe_b200.h but not exported"
+    assert set(native.EXPORTED_SYMBOLS) <= declared
+    assert lib.pe_abi_version() == 1
+    if not torch.cuda.is_available():
+        with pytest.raises(native.NativeUnavailable):      # the product path fails loudly without a GPU: no fallback
+            native.Native.get(0)
+
+
+def test_compat_alias_package_resolves_reference_imports():
+    """The import lines of scripts/inference/validate.py:10-12 and scripts/train/train_physicedit.py:1-6 resolve to this package."""
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
+    try:
+        from physicedit_b200 import compat
+        compat.install()
+        from diffsynth import load_state_dict, ModelConfig                                            # noqa: F401
+        from diffsynth.pipelines.qwen_image_physical import QwenImagePhysicPipeline, ModelConfig as MC  # noqa: F401
+        from diffsynth.pipelines.flux_image_new import ControlNetInput
+        from diffsynth.schedulers.flow_match import FlowMatchScheduler
+        assert ControlNetInput().scale == 1.0
+        s = FlowMatchScheduler(sigma_min=0, sigma_max=1, extra_one_step=True, exponential_shift=True, exponential_shift_mu=0.8, shift_terminal=0.02)
+        assert s.timesteps.max().item() == 1000.0
+        cfg = MC(path="/nonexistent/file.safetensors")
+        cfg.download_if_necessary()
+        assert cfg.path == "/nonexistent/file.safetensors"
+    finally:
+        for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_pipeline_host_contract_on_cpu():
+    """Host-side behaviours mirrored from the reference that need no GPU."""
+    import torch
+    from physicedit_b200.lora import GeneralLoRALoader
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline, hash_state_dict_keys, DIT_KEY_HASH
+    from physicedit_b200.dit import QwenImageDiT
+    with torch.device("meta"):
+        dit = QwenImageDiT()
+    assert hash_state_dict_keys(dit.state_dict()) == DIT_KEY_HASH
+    names = dict(dit.named_modules())
+    for tgt in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
+        assert isinstance(names[f"transformer_blocks.59.attn.{tgt}"], torch.nn.Linear)        # PEFT / LoRA targets are real nn.Linear
+    for tgt in ("img_mlp.net.2", "txt_mlp.net.2", "img_mod.1", "txt_mod.1"):
+        assert isinstance(names[f"transformer_blocks.0.{tgt}"], torch.nn.Linear)
+    loader = GeneralLoRALoader()
+    nd = loader.get_name_dict({"diffusion_model.transformer_blocks.3.attn.to_k.lora_B.weight": 0, "transformer_blocks.3.attn.to_q.lora_B.default.weight": 0,
+                               "transformer_blocks.3.attn.to_q.lora_A.default.weight": 0})
+    assert nd == {"transformer_blocks.3.attn.to_k": ("diffusion_model.transformer_blocks.3.attn.to_k.lora_B.weight", "diffusion_model.transformer_blocks.3.attn.to_k.lora_A.weight"),
+                  "transformer_blocks.3.attn.to_q": ("transformer_blocks.3.attn.to_q.lora_B.default.weight", "transformer_blocks.3.attn.to_q.lora_A.default.weight")}
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    assert pipe.check_resize_height_width(1000, 1030) == (1008, 1040)                          # rounds UP to multiples of 16
+    assert pipe.visual_thinking_adapter.t_min == 19.999980926513672 and pipe.visual_thinking_adapter.t_max == 1000.0
+    assert pipe.in_iteration_models == ("dit", "blockwise_controlnet", "visual_thinking_adapter")
+    n = pipe.generate_noise((1, 16, 4, 4), seed=0)
+    assert torch.equal(n, torch.randn((1, 16, 4, 4), generator=torch.Generator("cpu").manual_seed(0)).to(torch.bfloat16))
+    with pytest.raises(AssertionError):
+        QwenImagePhysicPipeline(device="cpu", dinov2_path=None)                                  # assert dinov2_path is not None (:198)
+    # checkpoint key layout of the reference (pipe.-stripped): strict=False load touches exactly the adapter keys
+    sd = {"visual_thinking_adapter.head_dino.0.weight": torch.zeros(10752, 3584, dtype=torch.bfloat16)}
+    res = pipe.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys
