@@ -124,6 +124,7 @@ def run_native(args):
         parallel.broadcast_weights(pipe, src=0)          # the one start-up collective: rank 0's weights to every GPU over NVLink
     eng = pipe.dit.engine()
     eng.use_cta_pair = not args.no_cta_pair
+    eng.attn_flags = args.attn_flags
     host = host_inputs(H, W, seed=100 + rank)             # a different image per rank
     dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
     ip = dict(prompt_emb=dev["pe_posi"], prompt_emb_mask=dev["mask_posi"], special_token_mask=dev["sp_posi"])
@@ -292,6 +293,7 @@ def main():
     ap.add_argument("--resolution", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cta-pair", action="store_true")
+    ap.add_argument("--attn-flags", dest="attn_flags", type=int, default=0, help="PE_ATTN_FLAG_* bits (8 = split-row softmax kernel)")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=2)

@@ -106,6 +106,47 @@ __device__ __forceinline__ float exp2_fma(float x) {
     pz = fmaf(pz, f, 1.0f);
     return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
 }
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): two elements per FMA-pipe issue slot ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#ifndef PE_ATTN_DBG
+#define PE_ATTN_DBG 0             // timing experiments only (wrong results): 1 = no exp, 2 = no P store, 4 = no max exchange, 8 = no S load
+#endif
+#ifndef PE_ATTN_POLY_PAIRS
+#define PE_ATTN_POLY_PAIRS 0      // of every 8 (element-pairs), how many take the FMA-pipe exp2 instead of MUFU (r1: 0..4 measured, no gain)
+#endif
+// (p0, p1) = 2^(x0, x1) for a packed pair on the FMA pipe: Cody-Waite split + degree-3 polynomial, all in f32x2
+__device__ __forceinline__ void exp2_fma_pair(uint64_t x2, float& p0, float& p1) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    x2 = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f), neg1 = pk2(-1.0f, -1.0f);
+    const uint64_t t2 = fadd2(x2, magic);                  // integer part lands in the low mantissa bits
+    const uint64_t n2 = fadd2(t2, nmagic);
+    const uint64_t f2 = ffma2(n2, neg1, x2);               // f = x - n in [-0.5, 0.5]
+    uint64_t pz = ffma2(f2, pk2(0.05550410866f, 0.05550410866f), pk2(0.24022650696f, 0.24022650696f));
+    pz = ffma2(pz, f2, pk2(0.69314718056f, 0.69314718056f));
+    pz = ffma2(pz, f2, pk2(1.0f, 1.0f));
+    float z0, z1, t0, t1;
+    upk2(pz, z0, z1);
+    upk2(t2, t0, t1);
+    p0 = __int_as_float(__float_as_int(z0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(z1) + (__float_as_int(t1) << 23));
+}
 __device__ __forceinline__ void row_max_chunk(const uint32_t (&r)[32], int col0, int kv_valid, bool full, float& mx) {
     if (full) {
 #pragma unroll
@@ -533,6 +574,409 @@ int launch_attention(Handle* h, AttnParams& p, cudaStream_t stream) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// attention_kernel2: same tensor-side pipeline (two ping-ponged 128-row query tiles, P in TMEM, 32 KB K/V ring), but the
+// softmax of each tile is spread over TWO warpgroups: a thread owns one query row x 64 kv columns and keeps that half row of
+// S in registers (one TMEM read pass).  Two softmax warps per SMSP per tile give the thread-level parallelism a single warp
+// lacks (r1 timeline: one warp per SMSP needed ~2150 cycles per 128x128 tile, twice the MUFU floor).  The exact row max is
+// formed every step: the two half-row owners exchange their maxima through shared memory around a 64-thread named barrier.
+//   warps 4..11  tile 0 (4..7: kv columns 0-63, 8..11: columns 64-127), warps 12..19 tile 1
+// P half h overlays S columns [64h, 64h+32) of its own half, so a thread only overwrites S values it has already consumed.
+// -------------------------------------------------------------------------------------------------
+constexpr int kA2KV = 4;                                    // K/V ring depth
+constexpr int kA2Threads = 128 + 512;
+constexpr int kA2SmemData = 2 * kTileBytes + kA2KV * kTileBytes;
+constexpr int kA2Exch = 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4;   // row-max exchange (2 slots) + row-sum exchange
+constexpr int kA2Smem = 1024 + kA2SmemData + kA2Exch + 256;
+
+__device__ __forceinline__ void tmem_ld16_(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_constant__ AttnParams p) {
+    constexpr int kKV = kA2KV;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto q_smem = [&](int q) { return smem_base + q * kTileBytes; };
+    auto kv_smem = [&](int s) { return smem_base + (2 + s) * kTileBytes; };
+    const uint32_t exch_base = smem_base + kA2SmemData;                 // [slot][q][half][128] f32 row max, then [q][half][128] f32 row sum
+    const uint32_t lsum_base = exch_base + 2 * 2 * 2 * 128 * 4;
+    const uint32_t bar_base = exch_base + kA2Exch;
+    const uint32_t q_full = bar_base, q_empty = bar_base + 8;
+    auto kv_full = [&](int s) { return bar_base + 16 + s * 8; };
+    auto kv_empty = [&](int s) { return bar_base + 16 + (kKV + s) * 8; };
+    auto s_full = [&](int q) { return bar_base + 16 + (2 * kKV + q) * 8; };
+    auto p_full = [&](int q) { return bar_base + 16 + (2 * kKV + 2 + q) * 8; };
+    auto pv_done = [&](int q) { return bar_base + 16 + (2 * kKV + 4 + q) * 8; };
+    auto o_empty = [&](int q) { return bar_base + 16 + (2 * kKV + 6 + q) * 8; };
+    const uint32_t tmem_slot = bar_base + 16 + (2 * kKV + 8) * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmQ);
+        prefetch_tmap(&p.tmK);
+        prefetch_tmap(&p.tmV);
+    }
+    if (warp == 1 && elect_one()) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < kKV; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(s_full(q), 1);
+            mbar_init(p_full(q), 8);       // 8 softmax warps per tile
+            mbar_init(pv_done(q), 1);
+            mbar_init(o_empty(q), 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    auto s_tmem = [&](int q) { return tmem_base + q * 128; };
+    auto o_tmem = [&](int q) { return tmem_base + 256 + q * 128; };
+
+    if (warp == 0) {
+        // ======================================= TMA producer =======================================
+        uint32_t n = 0, it = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            const int col0 = head * kTile;
+            if (!mbar_wait(q_empty, (it & 1u) ^ 1u, p.abort_flag, 40)) break;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int row0 = (qb * 2 + q) * kTile;
+                    tma_load_2d(q_smem(q), &p.tmQ, q_full, col0, row0);
+                    tma_load_2d(q_smem(q) + kHalfBytes, &p.tmQ, q_full, col0 + 64, row0);
+                }
+            }
+            __syncwarp();
+            for (int j = 0; j < p.n_kv && ok; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv, ++n) {
+                    const int slot = n % kKV;
+                    const uint32_t ph = (n / kKV) & 1u;
+                    if (!mbar_wait(kv_empty(slot), ph ^ 1u, p.abort_flag, 41)) { ok = false; break; }
+                    if (elect_one()) {
+                        const CUtensorMap* tm = kv == 0 ? &p.tmK : &p.tmV;
+                        mbar_arrive_expect_tx(kv_full(slot), kTileBytes);
+                        tma_load_2d(kv_smem(slot), tm, kv_full(slot), col0, j * kTile);
+                        tma_load_2d(kv_smem(slot) + kHalfBytes, tm, kv_full(slot), col0 + 64, j * kTile);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================= MMA issuer =======================================
+        // (A variant that ran this whole loop on one lane of a diverged warp was measured 35 % slower per batch:
+        //  the uniform datapath that feeds UTCHMMA needs the converged warp.)
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);
+        uint32_t n = 0, it = 0;
+        uint32_t p_phase[2] = {0, 0};
+        bool ok = true;
+        PE_TRACE_DECL(0)
+        auto issue_s = [&](int q, uint32_t k_base) {
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+                    umma_bf16<1>(s_tmem(q), make_smem_desc_sw128(q_smem(q) + off, 16, 1024),
+                                 make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full(q));
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate) {
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, kHalfBytes, 1024);
+                    // P: kv columns 0-63 are packed in TMEM columns [0,32), kv columns 64-127 in TMEM columns [64,96)
+                    const uint32_t a_tmem = s_tmem(q) + (kk >> 2) * 64 + (kk & 3) * 8;
+                    umma_bf16_ts(o_tmem(q), a_tmem, bdesc, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
+                }
+                umma_commit(pv_done(q));
+            }
+            __syncwarp();
+        };
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            if (!mbar_wait(q_full, it & 1u, p.abort_flag, 50)) break;
+            uint32_t k_slot = n % kKV;
+            if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 51)) break;
+            ++n;
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) issue_s(q, kv_smem(k_slot));
+            if (elect_one()) {
+                umma_commit(kv_empty(k_slot));
+                if (p.n_kv == 1) umma_commit(q_empty);
+            }
+            __syncwarp();
+            for (int j = 0; j < p.n_kv && ok; ++j) {
+                const uint32_t v_slot = n % kKV;
+                if (!mbar_wait(kv_full(v_slot), (n / kKV) & 1u, p.abort_flag, 52)) { ok = false; break; }
+                ++n;
+                const bool more = j + 1 < p.n_kv;
+                if (more) {
+                    k_slot = n % kKV;
+                    if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 53)) { ok = false; break; }
+                    ++n;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (j == 0) {
+                        if (!mbar_wait(o_empty(q), (it & 1u) ^ 1u, p.abort_flag, 54)) { ok = false; break; }
+                    }
+                    PE_TRACE(10 + q, j);
+                    if (!mbar_wait(p_full(q), p_phase[q], p.abort_flag, 55)) { ok = false; break; }
+                    p_phase[q] ^= 1u;
+                    tc_fence_after();
+                    PE_TRACE(12 + q, j);
+                    issue_pv(q, kv_smem(v_slot), j > 0);
+                    if (more) issue_s(q, kv_smem(k_slot));
+                    PE_TRACE(14 + q, j);
+                }
+                if (!ok) break;
+                if (elect_one()) {
+                    umma_commit(kv_empty(v_slot));
+                    if (more) umma_commit(kv_empty(k_slot));
+                    if (j + 2 == p.n_kv) umma_commit(q_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================================= softmax / correction / epilogue =======================================
+        const int sw = warp - 4;
+        const int q = sw >> 3;                 // query tile
+        const int half = (sw >> 2) & 1;        // which 64 kv columns of every S tile (and which 64 columns of O)
+        const int wq = sw & 3;                 // == warp % 4: TMEM lane quarter
+        const int row_in_tile = wq * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+        const uint32_t s_addr = s_tmem(q) + lane_off + half * 64;    // own S columns; P overlays the first 32 of them
+        const uint32_t o_addr = o_tmem(q) + lane_off + half * 64;
+        const int pair_bar = 1 + q * 4 + wq;                           // named barrier shared with the warp owning the other half
+        auto mx_slot = [&](int slot, int hf) { return exch_base + (((slot * 2 + q) * 2 + hf) * 128 + row_in_tile) * 4; };
+        const uint32_t l_own = lsum_base + ((q * 2 + half) * 128 + row_in_tile) * 4;
+        const uint32_t l_other = lsum_base + ((q * 2 + (half ^ 1)) * 128 + row_in_tile) * 4;
+        uint32_t s_phase = 0, pv_commits = 0;
+        bool ok = true;
+        const bool tr = (wq == 0 && half == 0);
+        PE_TRACE_DECL(1 + q)
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            float m_ref = -INFINITY;          // exponent reference (log2 domain) of O and l; trails the running max by < 2^8
+            float l = 0.f;                    // row sum over this thread's kv columns only
+            for (int j = 0; j < p.n_kv; ++j) {
+                if (tr) PE_TRACE(20 + q, j);
+                if (!mbar_wait(s_full(q), s_phase, p.abort_flag, 60)) { ok = false; break; }
+                s_phase ^= 1u;
+                tc_fence_after();
+                if (tr) PE_TRACE(22 + q, j);
+                const int kv_valid = p.S - j * kTile - half * 64;      // valid columns among this thread's 64
+                uint32_t r[64];
+                if (PE_ATTN_DBG & 8) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = __float_as_uint((float)((i * 7 + lane + j) & 15));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld16_(s_addr + c * 16, &r[c * 16]);
+                    tmem_ld_wait();
+                }
+                if (tr) PE_TRACE(30 + q, j);
+                // ---- exact row max: own 64 columns, then exchange with the owner of the other half ----
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                if (kv_valid >= 64) {
+#pragma unroll
+                    for (int i = 0; i < 64; i += 8) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i)
+                        if (i < kv_valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+                }
+                const float mx_own = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                st_shared_f32(mx_slot(j & 1, half), mx_own);
+                if (!(PE_ATTN_DBG & 4)) named_bar_sync(pair_bar, 64);
+                const float mx_scaled = fmaxf(mx_own, ld_shared_f32(mx_slot(j & 1, half ^ 1))) * p.scale_log2;
+                if (tr) PE_TRACE(24 + q, j);
+                // ---- lazy reference update: both owners of a row take the same decision from the same numbers ----
+                float f = 1.0f;
+                if (mx_scaled > m_ref + 8.0f) {
+                    f = ex2(m_ref - mx_scaled);       // 0 on the first tile (m_ref = -inf)
+                    m_ref = mx_scaled;
+                    l *= f;
+                }
+                // O rescale (own 64 columns).  PV(j-1) was issued before S(j) on the in-order tensor pipe, so the s_full(j)
+                // arrival implies it has completed.  On the first step O is uninitialised and PV(0) overwrites it.
+                if (j > 0 && __any_sync(0xffffffffu, f != 1.0f)) {
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t t[8];
+                        tmem_ld8_(o_addr + c * 8, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+                        tmem_st8_(o_addr + c * 8, t);
+                    }
+                    tmem_st_wait();
+                }
+                // ---- P = exp2(S*scale - m_ref) from registers, row sum, P (bf16) over the consumed S columns ----
+                float s0 = 0.f, s1 = 0.f;
+                if (kv_valid >= 64) {
+                    const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), negm2 = pk2(-m_ref, -m_ref);
+                    uint64_t sum2 = pk2(0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = c * 16 + 2 * i;
+                            const uint64_t x2 = ffma2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), scale2, negm2);
+                            float p0, p1;
+                            // pairs 1, 3, 6 (then 4, 0, ...) of every 8 go to the FMA pipe: spread so MUFU and FMA work interleave
+                            constexpr int kOrder[8] = {1, 3, 6, 4, 0, 7, 2, 5};
+                            bool poly = false;
+#pragma unroll
+                            for (int t = 0; t < PE_ATTN_POLY_PAIRS; ++t) poly = poly || (kOrder[t] == i);
+                            if (poly) {
+                                exp2_fma_pair(x2, p0, p1);
+                            } else {
+                                float x0, x1;
+                                upk2(x2, x0, x1);
+                                if (PE_ATTN_DBG & 1) { p0 = x0; p1 = x1; } else {
+                                p0 = ex2(x0);
+                                p1 = ex2(x1); }
+                            }
+                            sum2 = fadd2(sum2, pk2(p0, p1));
+                            pk[i] = pack_bf16(p0, p1);
+                        }
+                        if (!(PE_ATTN_DBG & 2)) tmem_st8_(s_addr + c * 8, pk); else if (pk[0] == 0x12345u) st_shared_f32(l_own, 1.f);
+                    }
+                    upk2(sum2, s0, s1);
+                } else {
+                    // ragged last KV tile: columns beyond the sequence contribute nothing
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = c * 16 + 2 * i;
+                            float p0 = ex2(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_ref));
+                            float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -m_ref));
+                            if (e >= kv_valid) p0 = 0.f;
+                            if (e + 1 >= kv_valid) p1 = 0.f;
+                            s0 += p0;
+                            s1 += p1;
+                            pk[i] = pack_bf16(p0, p1);
+                        }
+                        tmem_st8_(s_addr + c * 8, pk);
+                    }
+                }
+                l += s0 + s1;
+                if (tr) PE_TRACE(26 + q, j);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(q));
+                if (tr) PE_TRACE(28 + q, j);
+            }
+            if (!ok) break;
+            // ---- epilogue: O / l -> bf16 -> global (own 64 columns of the head) ----
+            pv_commits += (uint32_t)p.n_kv;
+            if (!mbar_wait(pv_done(q), (pv_commits - 1u) & 1u, p.abort_flag, 62)) break;
+            tc_fence_after();
+            st_shared_f32(l_own, l);
+            named_bar_sync(pair_bar, 64);
+            const float inv = 1.0f / (l + ld_shared_f32(l_other));
+            const long long row = (long long)(qb * 2 + q) * kTile + row_in_tile;
+            bf16* orow = p.o + row * p.ldo + head * kTile + half * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t t[16];
+                tmem_ld16_(o_addr + c * 16, t);
+                tmem_ld_wait();
+                if (row < p.S) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(t[8 * v]) * inv, __uint_as_float(t[8 * v + 1]) * inv);
+                        o.y = pack_bf16(__uint_as_float(t[8 * v + 2]) * inv, __uint_as_float(t[8 * v + 3]) * inv);
+                        o.z = pack_bf16(__uint_as_float(t[8 * v + 4]) * inv, __uint_as_float(t[8 * v + 5]) * inv);
+                        o.w = pack_bf16(__uint_as_float(t[8 * v + 6]) * inv, __uint_as_float(t[8 * v + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 16 + v * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty(q));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+int launch_attention2(Handle* h, AttnParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        PE_CHECK_CUDA(h, cudaFuncSetAttribute(attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+        configured = true;
+    }
+    p.n_qblk = ceil_div(p.S, kTile * 2);
+    p.n_items = p.H * p.n_qblk;
+    int ctas = h->sm_count;
+    if (ctas > p.n_items) ctas = p.n_items;
+    attention_kernel2<<<ctas, kA2Threads, kA2Smem, stream>>>(p);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // small generic attention (CUDA cores) for the training-path encoders whose sequences are tiny:
 // DINOv2 ViT-B (261 tokens, 12 heads x 64; transformers modeling_dinov2_with_registers.py:174-254)
 // and the perceiver resampler (64 latent queries over <= 10304 media+latent keys, 8 heads x 64;
@@ -628,6 +1072,8 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     p.trace = static_cast<long long*>(h->workspace);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 200000, stream);
 #endif
+    if (flags & PE_ATTN_FLAG_SPLIT_ROW_SOFTMAX)
+        return launch_attention2(h, p, stream);          // split-row softmax: exact max every step, two warps per SMSP per tile
     const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;
     const bool p_smem = (flags & PE_ATTN_FLAG_P_VIA_SMEM) != 0;
     if (one_tile) return p_smem ? launch_attention<1, false>(h, p, stream) : launch_attention<1, true>(h, p, stream);

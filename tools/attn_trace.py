@@ -22,8 +22,8 @@ for role in range(3):
             break
         ev.append((a >> 32, a & 0xffffffff, b))
 names = {10: "mma:wait_p0", 11: "mma:wait_p1", 12: "mma:got_p0", 13: "mma:got_p1", 14: "mma:issued0", 15: "mma:issued1",
-         20: "sm0:wait_s", 21: "sm1:wait_s", 22: "sm0:got_s", 23: "sm1:got_s", 24: "sm0:pv_ok", 25: "sm1:pv_ok", 26: "sm0:pass_done", 27: "sm1:pass_done",
-         28: "sm0:arrived", 29: "sm1:arrived"}
+         20: "sm0:wait_s", 21: "sm1:wait_s", 22: "sm0:got_s", 23: "sm1:got_s", 24: "sm0:max_ok", 25: "sm1:max_ok", 26: "sm0:pass_done", 27: "sm1:pass_done",
+         28: "sm0:arrived", 29: "sm1:arrived", 30: "sm0:loaded", 31: "sm1:loaded"}
 t0 = min(e[2] for e in ev)
 first = [e for e in ev if e[1] < 68]
 # keep only the first item's events: the first occurrence of each (event, step)

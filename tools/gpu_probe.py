@@ -299,6 +299,15 @@ for _q, _qn in ((1, "q1"), (0, "q2")):
             CASES[f"attn_{_qn}_{_pn}{_sn}_big"] = (lambda f=_f, n=f"attn_{_qn}_{_pn}{_sn}_big": case_attn(n, 8704, 24, f, timing=True))
 
 
+CASES["attn_v2_small"] = lambda: case_attn("attn_v2_small", 256, 2, 8)
+CASES["attn_v2_ragged"] = lambda: case_attn("attn_v2_ragged", 1000, 3, 8)
+CASES["attn_v2_big"] = lambda: case_attn("attn_v2_big", 8704, 24, 8, timing=True)
+CASES["attn_v2_big_t288"] = lambda: case_attn("attn_v2_big_t288", 8480, 24, 8, timing=True)
+CASES["attn_v1_big"] = lambda: case_attn("attn_v1_big", 8704, 24, 0, timing=True)
+CASES["attn_v2_2048"] = lambda: case_attn("attn_v2_2048", 20992, 24, 8, timing=True)
+CASES["attn_v1_2048"] = lambda: case_attn("attn_v1_2048", 20992, 24, 0, timing=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1] == "case":
