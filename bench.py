@@ -245,6 +245,10 @@ def cpu_baseline(args, blocks=1):
     `blocks` of the 60 blocks of ONE posi forward at the benchmark's sequence length, extrapolated to a full CFG step."""
     from oracle import dit_oracle as O
     torch.manual_seed(0)
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is allowed every host thread it can use
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     H = W = args.resolution
     S_img = (H // 16) * (W // 16) + 4096
     shapes = {k: v for k, v in O.dit_param_shapes(1).items() if k.startswith("transformer_blocks.0.")}
@@ -269,9 +273,11 @@ def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
     vals = []
-    for i in range(args.warmup_ref + args.steps_ref):
+    warm = min(args.warmup, args.warmup_ref) if args.warmup_ref >= 0 else args.warmup
+    steps = max(1, min(args.steps, args.steps_ref))          # each "step" = one bounded sample (one DiT block at full sequence length)
+    for i in range(warm + steps):
         cb = cpu_baseline(args, blocks=1)
-        if i >= args.warmup_ref:
+        if i >= warm:
             vals.append(cb)
     v = sum(c["value"] for c in vals) / len(vals)
     cb = dict(vals[-1]); cb["value"] = round(v, 6)
@@ -296,8 +302,8 @@ def main():
     ap.add_argument("--attn-flags", dest="attn_flags", type=int, default=0, help="PE_ATTN_FLAG_* bits (8 = split-row softmax kernel)")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=2)
-    ap.add_argument("--warmup-ref", dest="warmup_ref", type=int, default=1)
+    ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=8, help="cap on timed CPU samples of --impl reference")
+    ap.add_argument("--warmup-ref", dest="warmup_ref", type=int, default=2, help="cap on warm-up CPU samples of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
