@@ -66,6 +66,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
+def ncu_traffic_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    try:
+        for row in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_metrics.json"))):
+            if kernel_substr in row["kernel"]:
+                rd = float(row["dram__bytes_read.sum"].split()[0]) * 1e6
+                wr = float(row["dram__bytes_write.sum"].split()[0]) * 1e6
+                return int(rd + wr)
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def build_model(device, layers, seed=0):
     """Random-init bf16 weights of the real architecture, generated on the device (uniform, PyTorch-default bound)."""
     from physicedit_b200.dit import QwenImageDiT
@@ -219,7 +232,8 @@ def run_native(args):
         ach = fl / (tot / n * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_kernel<cta_pair, bias+gelu> (MLP up-projection, M=S N=12288 K=3072)", "achieved": round(ach, 1),
                 "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4), "traffic": None, "launches": n, "avg_ms": round(tot / n, 4),
+                "frac": round(ach / peak_tf, 4), "traffic": ncu_traffic_bytes("gemm_kernel<2, 2>"), "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_full_metrics.json)",
+                "algorithmic_bytes": int(2 * (S_avg * DIM + 4 * DIM * DIM + S_avg * 4 * DIM)), "launches": n, "avg_ms": round(tot / n, 4),
                 "whole_step_frac": round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)}
     shares = {k: round(v[1] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     res = {

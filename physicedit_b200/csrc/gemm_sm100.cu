@@ -30,7 +30,7 @@ constexpr int kUmmaK = 16;
 constexpr int kTileN = 256;
 constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
-constexpr int kGroupM = 8;         // rasterisation: 8 m-tiles share a sweep over n
+constexpr int kGroupM = 16;        // rasterisation: 16 m-tiles share a sweep over n (A panel <= 25 MB stays in the 126 MB L2)
 
 struct SegDev {
     CUtensorMap tmA;
