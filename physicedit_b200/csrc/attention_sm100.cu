@@ -91,6 +91,36 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 
+// ---- lean MMA issue: descriptors as (lo, hi) 32-bit words so that stepping through a tile is one uniform add per operand ----
+// smem matrix descriptor, 128B swizzle: lo = start address >> 4 | (LBO >> 4) << 16 ; hi = SBO >> 4 | version(1) << 14 | swizzle(2) << 29
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescLboK = (16u >> 4) << 16;                          // K-major operands (Q, K, P-in-smem): LBO unused
+constexpr uint32_t kDescLboV = (static_cast<uint32_t>(kHalfBytes) >> 4) << 16;   // MN-major V: 16 KB between the two 64-column halves
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t addr) { return ((addr & 0x3ffffu) >> 4) | kDescLboK; }
+__device__ __forceinline__ uint32_t desc_lo_v(uint32_t addr) { return ((addr & 0x3ffffu) >> 4) | kDescLboV; }
+template <bool kAcc>
+__device__ __forceinline__ void umma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(kAcc ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ss_lohi_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc) : "memory");
+}
+
 // ---- softmax helpers (one thread = one query row; a chunk = 32 consecutive kv columns) ------------------------------
 #ifndef PE_ATTN_POLY_EVERY
 #define PE_ATTN_POLY_EVERY 0      // >0: 1 of every N packed pairs takes the FMA-pipe exp2 instead of MUFU (measured: no gain on B200 with one softmax warp per SMSP)
@@ -318,10 +348,13 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
         }
     } else if (warp == 1) {
         // ======================================= MMA issuer =======================================
+        // One elected lane issues everything; the warp stays converged (the uniform datapath that feeds UTCHMMA needs it).
+        // r1 elimination runs showed this warp's own serial time line (blocking UTCHMMA issue + the instructions between
+        // batches) is what caps the kernel, so the per-batch overhead is kept minimal: the leader is elected once, PV_q(j) and
+        // S_q(j+1) go out as ONE batch, and every descriptor is "base word + small constant".
         constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
         constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);     // P (K-major) x V (MN-major)
-        const uint32_t v_lbo = p.swap_lbo_sbo ? 1024u : (uint32_t)kHalfBytes;
-        const uint32_t v_sbo = p.swap_lbo_sbo ? (uint32_t)kHalfBytes : 1024u;
+        const bool leader = elect_one();
         uint32_t n = 0, it = 0;
         uint32_t p_phase[2] = {0, 0};
         bool ok = true;
@@ -329,34 +362,29 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
 
         auto issue_s = [&](int q, uint32_t k_base) {
             // S_q = Q_q K^T : 8 k-steps of 16 head-dim elements; +32 B inside a swizzle row, +16 KB per half
-            if (elect_one()) {
+            const uint32_t qlo = desc_lo_k(q_smem(q)), klo = desc_lo_k(k_base);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-                    umma_bf16<1>(s_tmem(q), make_smem_desc_sw128(q_smem(q) + off, 16, 1024),
-                                 make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-                }
-                umma_commit(s_full(q));
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t off16 = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+                if (kk == 0) umma_ss_lohi<false>(s_tmem(q), qlo + off16, klo + off16, idesc_s);
+                else umma_ss_lohi<true>(s_tmem(q), qlo + off16, klo + off16, idesc_s);
             }
-            __syncwarp();
+            umma_commit(s_full(q));
         };
         auto issue_pv = [&](int q, uint32_t v_base, bool accumulate) {
             // O_q (+)= P_q V : 8 k-steps of 16 kv rows; V rows are 128 B apart, 16 rows = 2 KB
-            if (elect_one()) {
+            const uint32_t vlo = desc_lo_v(v_base);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, v_lbo, v_sbo);
-                    const uint32_t acc = (accumulate || kk != 0) ? 1u : 0u;
-                    if (kPTmem) {
-                        umma_bf16_ts(o_tmem(q), s_tmem(q) + kk * 8, bdesc, idesc_o, acc);
-                    } else {
-                        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-                        umma_bf16<1>(o_tmem(q), make_smem_desc_sw128(p_smem(q) + off, 16, 1024), bdesc, idesc_o, acc);
-                    }
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t acc = (accumulate || kk != 0) ? 1u : 0u;
+                if (kPTmem) {
+                    umma_ts_lohi(o_tmem(q), s_tmem(q) + kk * 8, vlo + kk * (2048 >> 4), idesc_o, acc);
+                } else {
+                    const uint32_t off16 = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+                    umma_ss_lohi_acc(o_tmem(q), desc_lo_k(p_smem(q)) + off16, vlo + kk * (2048 >> 4), idesc_o, acc);
                 }
-                umma_commit(pv_done(q));
             }
-            __syncwarp();
+            umma_commit(pv_done(q));
         };
 
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
@@ -366,9 +394,9 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
             if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 21)) break;
             ++n;
             tc_fence_after();
+            if (leader) {
 #pragma unroll
-            for (int q = 0; q < kQT; ++q) issue_s(q, kv_smem(k_slot));
-            if (elect_one()) {
+                for (int q = 0; q < kQT; ++q) issue_s(q, kv_smem(k_slot));
                 umma_commit(kv_empty(k_slot));
                 if (p.n_kv == 1) umma_commit(q_empty);
             }
@@ -394,17 +422,19 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
                     p_phase[q] ^= 1u;
                     tc_fence_after();
                     PE_TRACE(12 + q, j);
-                    issue_pv(q, kv_smem(v_slot), j > 0);
-                    if (more) issue_s(q, kv_smem(k_slot));
+                    if (leader) {
+                        issue_pv(q, kv_smem(v_slot), j > 0);
+                        if (more) issue_s(q, kv_smem(k_slot));
+                        if (q == kQT - 1) {
+                            umma_commit(kv_empty(v_slot));
+                            if (more) umma_commit(kv_empty(k_slot));
+                            if (j + 2 == p.n_kv) umma_commit(q_empty);   // last S MMAs of this item were just issued
+                        }
+                    }
+                    __syncwarp();
                     PE_TRACE(14 + q, j);
                 }
                 if (!ok) break;
-                if (elect_one()) {
-                    umma_commit(kv_empty(v_slot));
-                    if (more) umma_commit(kv_empty(k_slot));
-                    if (j + 2 == p.n_kv) umma_commit(q_empty);   // last S MMAs of this item were just issued
-                }
-                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -353,3 +353,111 @@ def test_training_loss_forward_value(golden):
     l_ora = O.adapter_loss(pd.cpu().float(), pv.cpu().float(), gt_d.cpu().float(), gt_v.cpu().float(), torch.tensor([500.0]).bfloat16(),
                            meta["t_min"], meta["t_max"]).item()
     assert abs(l_nat - l_ora) < 2e-2 * abs(l_ora)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size (BASELINE.json config #2 shapes) checks through size-independent properties: the oracle cannot run these
+# sizes in seconds, the properties can.
+# ---------------------------------------------------------------------------------------------------------------------
+@gpu
+@pytest.mark.parametrize("flags", [0, 8])
+def test_full_size_attention_properties(nat, flags):
+    S, H = 8192 + 512, 24
+    d = H * 128
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q, k, v1, v2 = (torch.randn(S, d, device="cuda", generator=g).bfloat16() for _ in range(4))
+    scale = 1 / math.sqrt(128)
+    o = torch.empty_like(q)
+    # (1) softmax rows sum to one: with V == 1 the output is exactly 1 up to the bf16 rounding of P
+    ones = torch.ones_like(q)
+    nat.attention(q, k, ones, o, H, scale, flags)
+    assert (o.float() - 1).abs().max().item() <= 2 ** -7
+    # (2) linear in V
+    o1, o2, o12 = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    nat.attention(q, k, v1, o1, H, scale, flags)
+    nat.attention(q, k, v2, o2, H, scale, flags)
+    nat.attention(q, k, (v1.float() + v2.float()).bfloat16(), o12, H, scale, flags)
+    assert rel_l2(o12, o1.float() + o2.float()) < 8e-3
+    # (3) invariant under a joint permutation of the keys / values (order of the KV tiles and of the online softmax)
+    perm = torch.randperm(S, device="cuda", generator=g)
+    op = torch.empty_like(q)
+    nat.attention(q, k[perm].contiguous(), v1[perm].contiguous(), op, H, scale, flags)
+    assert rel_l2(op, o1) < 4e-3
+    # (4) deterministic: no atomics, fixed schedule
+    o1b = torch.empty_like(q)
+    nat.attention(q, k, v1, o1b, H, scale, flags)
+    assert torch.equal(o1, o1b)
+    # (5) a spot check of 64 rows of one head against exact fp32 softmax
+    rows = torch.arange(0, S, S // 64, device="cuda")[:64]
+    ref = torch.softmax(q[rows, :128].float() @ k[:, :128].float().t() * scale, dim=-1) @ v1[:, :128].float()
+    assert rel_l2(o1[rows, :128], ref) < 5e-3
+    nat.check_async()
+
+
+@gpu
+def test_full_size_gemm_properties(nat):
+    from physicedit_b200 import native as nv
+    M, T, N, K = 8192, 512, 12288, 3072
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a1 = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    a2 = torch.randn(T, K, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    w2 = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    o1 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty(T, N, device="cuda", dtype=torch.bfloat16)
+    for flags in (0, nv.GEMM_FLAG_CTA_PAIR):
+        # zero activations -> exactly the bias in every row (both segments, every tile, every epilogue warp)
+        nat.gemm([dict(a=torch.zeros_like(a1), w=w1, bias=b, out=o1), dict(a=torch.zeros_like(a2), w=w2, bias=b, out=o2)], N, K, nv.EPI_BIAS, flags)
+        assert torch.equal(o1, b.expand(M, N)) and torch.equal(o2, b.expand(T, N))
+        # two segments with different weights in one launch == two separate launches, bit for bit
+        nat.gemm([dict(a=a1, w=w1, bias=b, out=o1), dict(a=a2, w=w2, bias=b, out=o2)], N, K, nv.EPI_BIAS, flags)
+        s1 = torch.empty_like(o1)
+        s2 = torch.empty_like(o2)
+        nat.gemm([dict(a=a1, w=w1, bias=b, out=s1)], N, K, nv.EPI_BIAS, flags)
+        nat.gemm([dict(a=a2, w=w2, bias=b, out=s2)], N, K, nv.EPI_BIAS, flags)
+        assert torch.equal(o1, s1) and torch.equal(o2, s2)
+        # sampled rows against fp32 matmul
+        rows = torch.arange(0, M, 257, device="cuda")
+        ref = a1[rows].float() @ w1.float().t() + b.float()
+        assert rel_l2(o1[rows], ref) < 3e-3
+    # CTA-pair and single-CTA kernels accumulate in the same k order -> identical results
+    p1 = torch.empty_like(o1)
+    nat.gemm([dict(a=a1, w=w1, bias=b, out=p1)], N, K, nv.EPI_BIAS, 0)
+    nat.gemm([dict(a=a1, w=w1, bias=b, out=s1)], N, K, nv.EPI_BIAS, nv.GEMM_FLAG_CTA_PAIR)
+    assert torch.equal(p1, s1)
+    nat.check_async()
+
+
+@gpu
+def test_full_sequence_block_is_deterministic_and_finite():
+    """One block at the full 1024^2 sequence (8192 image + 512 text tokens): two runs are bit-identical, outputs finite,
+    the text rows depend on the image rows (joint attention) and the result matches the oracle block on sampled rows."""
+    dit, W = _build_dit(1, 21)
+    eng = dit.engine()
+    T, S_img = 512, 8192
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(T + S_img, 3072, generator=g).bfloat16()
+    temb = torch.randn(1, 3072, generator=g).bfloat16()
+    rope = eng.rope([(1, 64, 64), (1, 64, 64)], T)
+    ws = eng.workspace(S_img, T)
+    mods = eng.block_mods(temb.cuda(), [0])
+    outs = []
+    for _ in range(2):
+        x = x0.cuda().clone()
+        eng.run_block(0, x, T, mods[0], rope, ws)
+        outs.append(x)
+    eng.nat.check_async()
+    assert torch.equal(outs[0], outs[1])
+    assert torch.isfinite(outs[0].float()).all()
+    x2 = x0.clone()
+    x2[T + 100:T + 200] += 1.0                                   # perturb image rows only
+    xp = x2.cuda()
+    eng.run_block(0, xp, T, mods[0], rope, ws)
+    assert not torch.equal(xp[:T], outs[0][:T])                  # text stream sees the image through the joint attention
+    # oracle on the same block (bf16 on CPU, ~10 s): sampled rows
+    vid, txt = O.rope_tables([(1, 64, 64), (1, 64, 64)], T)
+    t_o, i_o = O.block_forward(W, 0, x0[T:].unsqueeze(0), x0[:T].unsqueeze(0), temb, (vid, txt))
+    ref = torch.cat([t_o[0], i_o[0]], dim=0)
+    rows = torch.arange(0, T + S_img, 97)
+    assert rel_l2(outs[0].cpu()[rows], ref[rows]) < 1.5e-2
