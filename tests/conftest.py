@@ -12,6 +12,14 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    # the C-ABI library is a build artefact (git-ignored): build it once if a fresh checkout has none and nvcc is around
+    lib = os.path.join(ROOT, "physicedit_b200", "lib", "libpe_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            subprocess.run(["bash", os.path.join(ROOT, "physicedit_b200", "csrc", "build.sh")], check=False,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")

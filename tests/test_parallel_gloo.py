@@ -141,3 +141,27 @@ def test_pipeline_host_contract_on_cpu():
     sd = {"visual_thinking_adapter.head_dino.0.weight": torch.zeros(10752, 3584, dtype=torch.bfloat16)}
     res = pipe.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys
+
+
+def test_c_abi_rejects_null_handle_without_a_gpu():
+    """Error convention of include/pe_b200.h: every entry point returns a negative pe_status (never crashes, never throws)
+    when called with a NULL handle -- checked here without any CUDA device."""
+    import ctypes
+    from physicedit_b200 import native
+    lib = native.load_library()
+    null = ctypes.c_void_p(None)
+    assert lib.pe_destroy(null) == -1
+    assert lib.pe_sm_count(null) == -1
+    assert lib.pe_last_error(null) == b"null handle"
+    assert lib.pe_gemm(null, None, 1, 8, 8, 0, 0, None) == -1
+    assert lib.pe_attention_fwd(null, None, None, None, None, 1, 1, 128, ctypes.c_float(1.0), 0, None) == -1
+    assert lib.pe_layernorm_modulate(null, None, None, 1, 8, None, None, None) == -1
+    assert lib.pe_gemv(null, None, None, None, None, 1, 8, 8, 0, 0, None, None) == -1
+    assert lib.pe_timestep_embedding(null, None, None, 1, None) == -1
+    assert lib.pe_cfg_euler_step(null, None, None, None, 1, ctypes.c_float(1.0), ctypes.c_float(0.0), None) == -1
+    assert lib.pe_check_async_error(null, None, None) == -1
+    out = ctypes.c_void_p()
+    assert lib.pe_create(None, 0) == -1                              # null out pointer
+    if not torch.cuda.is_available():
+        assert lib.pe_create(ctypes.byref(out), 0) == -3             # PE_ERR_UNSUPPORTED_DEVICE: no sm_100 device, no fallback
+        assert out.value is None
