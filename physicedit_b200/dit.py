@@ -144,7 +144,7 @@ class QwenImageTransformerBlock(nn.Module):
         rope = torch.view_as_real(torch.cat([txt, vid], dim=0).to(torch.complex64)).contiguous().to(x.device)
         ws = eng.workspace(S_img, T)
         mods = eng.block_mods(temb.reshape(1, DIM), [idx])
-        eng.run_block(idx, x, T, mods[0], rope, ws)
+        eng.run_block(idx, x, T, mods[0, 0], rope, ws)
         return x[:T].unsqueeze(0), x[T:].unsqueeze(0)
 
 
@@ -315,6 +315,7 @@ class DiTEngine:
         m2[:DIM] = 1                                                   # AdaLayerNorm(single): (scale, shift)
         self.mask2 = m2
         self._mods_cache = None
+        self._cond_table = None
 
     def refresh_if_stale(self):
         blocks = self.dit.transformer_blocks
@@ -327,6 +328,7 @@ class DiTEngine:
     def invalidate(self):
         """Call after modifying weights in place (LoRA fold): drops cached modulation vectors."""
         self._mods_cache = None
+        self._cond_table = None
 
     # -- cached per-shape state ---------------------------------------------------------------------
     def workspace(self, S_img: int, T: int) -> Workspace:
@@ -348,31 +350,58 @@ class DiTEngine:
 
     # -- pieces ---------------------------------------------------------------------------------------
     def block_mods(self, temb: torch.Tensor, indices: Optional[Sequence[int]] = None) -> torch.Tensor:
-        """img_mod / txt_mod of the given blocks: [n, 2 (img, txt), 18432] with bf16(1+scale) in the scale slots."""
+        """img_mod / txt_mod of the given blocks for a batch of B <= 8 conditioning vectors temb [B, 3072]:
+        returns [B, n, 2 (img, txt), 18432] with bf16(1+scale) in the scale slots.  The GEMV streams each weight matrix once
+        for the whole batch."""
         blocks = self.dit.transformer_blocks
         indices = list(range(len(blocks))) if indices is None else list(indices)
-        out = torch.empty(len(indices), 2, 6 * DIM, dtype=torch.bfloat16, device=self.device)
+        B = temb.shape[0]
+        out = torch.empty(len(indices), 2, B, 6 * DIM, dtype=torch.bfloat16, device=self.device)
         for n, i in enumerate(indices):
             b = blocks[i]
             self.nat.tag = "gemv_mod"
-            self.nat.gemv(temb, b.img_mod[1].weight, b.img_mod[1].bias, out[n, 0:1], 1, 0, self.mask6)
+            self.nat.gemv(temb, b.img_mod[1].weight, b.img_mod[1].bias, out[n, 0], 1, 0, self.mask6)
             self.nat.tag = "gemv_mod"
-            self.nat.gemv(temb, b.txt_mod[1].weight, b.txt_mod[1].bias, out[n, 1:2], 1, 0, self.mask6)
-        return out
+            self.nat.gemv(temb, b.txt_mod[1].weight, b.txt_mod[1].bias, out[n, 1], 1, 0, self.mask6)
+        return out.permute(2, 0, 1, 3)          # [B, n, 2, 18432] view; [b] is contiguous per (n, stream) row
+
+    def _conditioning_batch(self, timesteps_bf16: torch.Tensor):
+        """temb, block modulation table and norm_out (scale, shift) for B <= 8 timesteps at once."""
+        B = timesteps_bf16.shape[0]
+        temb = torch.cat([self.dit.time_text_embed(timesteps_bf16[b:b + 1], raw=True) for b in range(B)], dim=0)
+        mods = self.block_mods(temb)
+        no = self.dit.norm_out.linear
+        out_mod = torch.empty(B, 2 * DIM, dtype=torch.bfloat16, device=self.device)
+        self.nat.tag = "gemv_mod"
+        self.nat.gemv(temb, no.weight, no.bias, out_mod, 1, 0, self.mask2)
+        return temb, mods, out_mod
+
+    def precompute_conditioning(self, timesteps_bf16: torch.Tensor, keys: Sequence[float]) -> None:
+        """Everything that depends on the timestep only (temb, the 120 modulation vectors per forward, norm_out's scale/shift)
+        for a whole schedule: the M=1 linears are run as batch-8 GEMVs, so the 13.6 GB of modulation weights stream once per 8
+        denoise steps instead of once per forward.  Values are identical to the per-forward computation of the reference
+        (qwen_image_dit.py:373-374 recomputes them in every block of every forward from the same temb)."""
+        table = {}
+        for c0 in range(0, len(keys), 8):
+            ts = timesteps_bf16[c0:c0 + 8].contiguous()
+            temb, mods, out_mod = self._conditioning_batch(ts)
+            for b in range(ts.shape[0]):
+                table[float(keys[c0 + b])] = (temb[b:b + 1], mods[b], out_mod[b:b + 1])
+        self._cond_table = table
 
     def conditioning(self, timestep_bf16: torch.Tensor, t_key: Optional[float]):
         """temb, all block modulation vectors and the norm_out (scale, shift) for this timestep.  They depend on
         the timestep only, so the two CFG branches of a denoise step share them (cache keyed by the host value)."""
+        tab = getattr(self, "_cond_table", None)
+        if t_key is not None and tab is not None and t_key in tab:
+            return tab[t_key]
         if t_key is not None and self._mods_cache is not None and self._mods_cache[0] == t_key:
             return self._mods_cache[1:]
-        temb = self.dit.time_text_embed(timestep_bf16, raw=True)
-        mods = self.block_mods(temb)
-        no = self.dit.norm_out.linear
-        out_mod = torch.empty(1, 2 * DIM, dtype=torch.bfloat16, device=self.device)
-        self.nat.gemv(temb, no.weight, no.bias, out_mod, 1, 0, self.mask2)
+        temb, mods, out_mod = self._conditioning_batch(timestep_bf16.reshape(-1)[:1])
+        res = (temb, mods[0], out_mod)
         if t_key is not None:
-            self._mods_cache = (t_key, temb, mods, out_mod)
-        return temb, mods, out_mod
+            self._mods_cache = (t_key,) + res
+        return res
 
     def run_block(self, i: int, x: torch.Tensor, T: int, mods: torch.Tensor, rope: torch.Tensor, ws: Workspace):
         """One double-stream block in place on the joint residual stream x [T + S_img, 3072].

@@ -214,6 +214,8 @@ class QwenImagePhysicPipeline(nn.Module):
         latents = latents.clone()
         vp = torch.empty_like(latents)
         vn = torch.empty_like(latents)
+        # timestep-only quantities for the whole schedule, batch-8 GEMVs (see DiTEngine.precompute_conditioning)
+        self.dit.engine().precompute_conditioning(ts_dev, [float(t.to(self.torch_dtype)) for t in ts])
         it = enumerate(ts)
         if progress_bar_cmd is not None:
             it = progress_bar_cmd(list(it))

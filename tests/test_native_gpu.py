@@ -441,7 +441,7 @@ def test_full_sequence_block_is_deterministic_and_finite():
     temb = torch.randn(1, 3072, generator=g).bfloat16()
     rope = eng.rope([(1, 64, 64), (1, 64, 64)], T)
     ws = eng.workspace(S_img, T)
-    mods = eng.block_mods(temb.cuda(), [0])
+    mods = eng.block_mods(temb.cuda(), [0])[0]
     outs = []
     for _ in range(2):
         x = x0.cuda().clone()
