@@ -461,3 +461,47 @@ def test_full_sequence_block_is_deterministic_and_finite():
     ref = torch.cat([t_o[0], i_o[0]], dim=0)
     rows = torch.arange(0, T + S_img, 97)
     assert rel_l2(outs[0].cpu()[rows], ref[rows]) < 1.5e-2
+
+
+@gpu
+def test_model_fn_ragged_shapes_context_and_edit_list():
+    """Non-square latents, an edit-image LIST plus context latents (qwen_image_physical.py:1347-1355), an odd text length and
+    no special tokens: every M / S tail path of the kernels in one forward, against the fp32 oracle."""
+    from physicedit_b200.model_fn import model_fn_qwen_image
+    dit, W = _build_dit(1, 33)
+    g = torch.Generator().manual_seed(9)
+    H, Wd, T = 96, 160, 77
+    lat = torch.randn(1, 16, H // 8, Wd // 8, generator=g).bfloat16()
+    ctx = torch.randn(1, 16, 8, 12, generator=g).bfloat16()
+    e1 = torch.randn(1, 16, 8, 16, generator=g).bfloat16()
+    e2 = torch.randn(1, 16, 6, 10, generator=g).bfloat16()
+    pe = (3 * torch.randn(1, T, 3584, generator=g)).bfloat16()
+    mask = torch.ones(1, T, dtype=torch.int64)
+    t = torch.tensor([426.6734719276428]).to(torch.bfloat16)
+    y, loss = model_fn_qwen_image(dit=dit, latents=lat.cuda(), timestep=t.cuda(), prompt_emb=pe.cuda(), prompt_emb_mask=mask.cuda(),
+                                  special_token_mask=None, height=H, width=Wd, edit_latents=[e1.cuda(), e2.cuda()], context_latents=ctx.cuda(),
+                                  is_train=False)
+    dit.engine().nat.check_async()
+    assert loss == 0 and y.shape == lat.shape
+    Wf = {k: v.float() for k, v in W.items()}
+
+    def oracle(dtype):
+        Wd_ = Wf if dtype == torch.float32 else W
+        c = lambda x: x.to(dtype)
+        # the oracle takes the image list in the reference's order: latents, context, edits
+        img = [c(lat), c(ctx), c(e1), c(e2)]
+        shapes = [(1, x.shape[2] // 2, x.shape[3] // 2) for x in img]
+        image = O.linear(torch.cat([O.patchify(x) for x in img], dim=1), Wd_, "img_in")
+        ts = c(t) / 1000
+        temb = O.time_text_embed(Wd_, ts, dtype)
+        text = O.linear(O.rmsnorm(c(pe), Wd_["txt_norm.weight"]), Wd_, "txt_in")
+        rope = O.rope_tables(shapes, T)
+        text, image = O.block_forward(Wd_, 0, image, text, temb, rope)
+        emb = O.linear(torch.nn.functional.silu(temb), Wd_, "norm_out.linear")
+        scale, shift = emb.unsqueeze(1).chunk(2, dim=2)
+        image = O.layernorm(image) * (1 + scale) + shift
+        n0 = shapes[0][1] * shapes[0][2]
+        return O.unpatchify(O.linear(image, Wd_, "proj_out")[:, :n0], H // 16, Wd // 16)
+    y32, y16 = oracle(torch.float32), oracle(torch.bfloat16)
+    floor = rel_l2(y16, y32)
+    assert rel_l2(y, y32) <= floor + TOL_EXTRA, (rel_l2(y, y32), floor)
