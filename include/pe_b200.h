@@ -109,7 +109,6 @@ int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int 
 #define PE_ATTN_FLAG_P_VIA_SMEM    2  /* stage P through shared memory (SS MMA) instead of TMEM (TS MMA)   */
 #define PE_ATTN_FLAG_SPLIT_ROW_SOFTMAX 8 /* attention_kernel2: a query row is shared by two threads (64 kv columns each), exact row
                                             max every step; r1: same speed isolated, 2 % slower inside the denoise loop -> not the default */
-#define PE_ATTN_FLAG_SWAP_V_DESC   4  /* debug: swap LBO/SBO of the MN-major V descriptor                   */
 int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v, void* o,
                      int S, int H, int64_t ld, float scale, int flags, void* stream);
 

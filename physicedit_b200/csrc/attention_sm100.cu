@@ -57,7 +57,6 @@ struct AttnParams {
     int n_items;     // H * n_qblk
     int n_kv;        // ceil(S / 128)
     float scale_log2;
-    int swap_lbo_sbo;   // debug: swap the LBO/SBO roles of the MN-major V descriptor
     unsigned int* abort_flag;
     long long* trace;
 };
@@ -1096,7 +1095,6 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     p.H = H;
     p.n_kv = ceil_div(S, kTile);
     p.scale_log2 = scale * 1.4426950408889634f;
-    p.swap_lbo_sbo = (flags & PE_ATTN_FLAG_SWAP_V_DESC) ? 1 : 0;
     p.abort_flag = h->abort_flag;
 #ifdef PE_ATTN_TRACE
     p.trace = static_cast<long long*>(h->workspace);

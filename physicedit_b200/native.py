@@ -26,7 +26,6 @@ EPI_BIAS_SILU = 6
 GEMM_FLAG_CTA_PAIR = 1
 ATTN_FLAG_SINGLE_Q_TILE = 1
 ATTN_FLAG_P_VIA_SMEM = 2
-ATTN_FLAG_SWAP_V_DESC = 4
 ATTN_FLAG_SPLIT_ROW_SOFTMAX = 8
 
 EXPORTED_SYMBOLS = [

@@ -292,7 +292,7 @@ CASES = {
 }
 for _q, _qn in ((1, "q1"), (0, "q2")):
     for _p, _pn in ((2, "psmem"), (0, "ptmem")):
-        for _s, _sn in ((0, ""), (4, "_swap")):
+        for _s, _sn in ((0, ""),):
             _f = _q | _p | _s
             CASES[f"attn_{_qn}_{_pn}{_sn}_small"] = (lambda f=_f, n=f"attn_{_qn}_{_pn}{_sn}_small": case_attn(n, 256, 2, f))
             CASES[f"attn_{_qn}_{_pn}{_sn}_ragged"] = (lambda f=_f, n=f"attn_{_qn}_{_pn}{_sn}_ragged": case_attn(n, 1000, 3, f))
