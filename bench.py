@@ -109,11 +109,24 @@ def build_model(device, layers, seed=0):
     return pipe
 
 
+def synth_inputs(height, width, T, seed, edit_hw=(1024, 1024), n_special=64):
+    """Synthetic request in the shapes of SURVEY 8d (self-contained: the native arm must not touch oracle/): latents via the
+    reference's generate_noise recipe (CPU generator, fp32 randn, cast to bf16), prompt_emb ~ 3 N(0,1), all-ones mask, special-token
+    mask = 64 consecutive rows ending 5 before the end."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    latents = torch.randn((1, 16, height // 8, width // 8), generator=g, dtype=torch.float32).to(torch.bfloat16)
+    edit = torch.randn((1, 16, edit_hw[0] // 8, edit_hw[1] // 8), generator=g, dtype=torch.float32).to(torch.bfloat16)
+    prompt = (3 * torch.randn((1, T, 3584), generator=g, dtype=torch.float32)).to(torch.bfloat16)
+    mask = torch.ones((1, T), dtype=torch.int64)
+    special = torch.zeros((1, T), dtype=torch.bool)
+    special[0, T - 5 - n_special: T - 5] = True
+    return dict(latents=latents, edit_latents=edit, prompt_emb=prompt, prompt_emb_mask=mask, special_token_mask=special)
+
+
 def host_inputs(height, width, seed):
     """Pinned host buffers of one edit request (what a serving front-end would hand over)."""
-    from oracle.dit_oracle import synth_inputs        # input recipe only (shapes / seeds); no oracle arithmetic
-    posi = synth_inputs(height, width, T_POSI, seed=seed, dtype=torch.bfloat16, edit_hw=(1024, 1024))
-    nega = synth_inputs(height, width, T_NEGA, seed=seed + 1, dtype=torch.bfloat16, edit_hw=(1024, 1024))
+    posi = synth_inputs(height, width, T_POSI, seed=seed)
+    nega = synth_inputs(height, width, T_NEGA, seed=seed + 1)
     host = dict(latents=posi["latents"], edit_latents=posi["edit_latents"], pe_posi=posi["prompt_emb"], pe_nega=nega["prompt_emb"],
                 mask_posi=posi["prompt_emb_mask"], mask_nega=nega["prompt_emb_mask"], sp_posi=posi["special_token_mask"], sp_nega=nega["special_token_mask"])
     return {k: v.pin_memory() for k, v in host.items()}
