@@ -109,6 +109,8 @@ int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int 
 #define PE_ATTN_FLAG_P_VIA_SMEM    2  /* stage P through shared memory (SS MMA) instead of TMEM (TS MMA)   */
 #define PE_ATTN_FLAG_SPLIT_ROW_SOFTMAX 8 /* attention_kernel2: a query row is shared by two threads (64 kv columns each), exact row
                                             max every step; r1: same speed isolated, 2 % slower inside the denoise loop -> not the default */
+#define PE_ATTN_FLAG_KV64 16           /* attention_kernel3: 64-row KV steps with two S buffers per query tile in TMEM, so S(j+2) is issued
+                                            one step ahead and the softmax never waits on the PV -> S latency chain */
 int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v, void* o,
                      int S, int H, int64_t ld, float scale, int flags, void* stream);
 

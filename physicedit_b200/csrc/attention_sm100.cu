@@ -1006,6 +1006,353 @@ int launch_attention2(Handle* h, AttnParams& p, cudaStream_t stream) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// attention_kernel3 (PE_ATTN_FLAG_KV64): the softmax is taken OFF the tensor pipe's latency chain.
+// In attention_kernel the chain of one query tile is  softmax(j) -> P hand-off -> PV(j) -> S(j+1) -> hand-off -> softmax(j+1):
+// S(j+1) cannot be issued before PV(j) has consumed P(j), because P overlays S and TMEM (512 columns = S0,S1,O0,O1) has no
+// room for a second S buffer.  Here a KV step is 64 rows, so an S tile is 128 x 64 fp32 = 64 columns and every query tile owns
+// TWO S buffers (TMEM: S00,S01,S10,S11 = 4 x 64 columns, O0,O1 = 2 x 128).  S(j+2) is issued together with PV(j), i.e. one whole
+// step ahead of the softmax, so the softmax warpgroups run back to back (they only wait when the tensor pipe is the slower side)
+// and both tiles' softmax run concurrently (two busy warps per SMSP).  Tensor work per 64-row step and tile: PV = 4 MMAs
+// 128x128x16 (P from TMEM), S = 8 MMAs 128x64x16.
+//   warp 0      TMA producer: Q once per item; a ring of 32 KB stages, stage(j) = [V_j | K_{j+2}], prologue stage = [K_0 | K_1]
+//   warp 1 / 3  MMA issuer of query tile 0 / 1 (r1 trace: one issuer warp's own instruction stream -- waits, commits, 24 MMAs per
+//               step -- took 2400 cycles per step against 1280 cycles of tensor work; with one issuer per tile each has the whole
+//               step for half of it.  TMEM hazards are per tile, so each tile's program order on its own warp is all that matters)
+//   warp 2      TMEM allocator
+//   warps 4-7 / 8-11  softmax + epilogue of query tile 0 / 1 (one thread per query row).
+// Softmax arithmetic (trailing reference, lazy O rescale, overflow guard) is the one of attention_kernel; the O rescale now
+// waits explicitly for PV(j-1), because the s_full(j) arrival no longer implies it: S(j+1) was issued right after PV(j-1), so its
+// s_full arrival does (non-consuming early wait); on the last step a pv_done commit (made for the last two steps only) does.
+// -------------------------------------------------------------------------------------------------
+#ifndef PE_A3_DBG
+#define PE_A3_DBG 0      // timing experiments only (wrong results): 1 = no S MMAs, 2 = no PV MMAs
+#endif
+#ifndef PE_A3_SKEW
+#define PE_A3_SKEW 0     // cycles by which tile 1's softmax warps are held back at the start of every work item
+#endif
+constexpr int kA3Rows = 64;                                  // kv rows per step
+constexpr int kA3Half = kA3Rows * 64 * 2;                    // one [64 x 64] bf16 swizzled half = 8 KB
+constexpr int kA3Tile = 2 * kA3Half;                         // one K_j or V_j tile: 16 KB
+constexpr int kA3Stage = 2 * kA3Tile;                        // [V_j | K_{j+2}] = 32 KB
+constexpr int kA3Ring = 4;
+constexpr int kA3Threads = 128 + 256;
+constexpr int kA3SmemData = 2 * kTileBytes + kA3Ring * kA3Stage;
+constexpr int kA3Smem = 1024 + kA3SmemData + 512;
+constexpr uint32_t kDescLboV64 = (static_cast<uint32_t>(kA3Half) >> 4) << 16;
+
+__global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_constant__ AttnParams p) {
+    constexpr int kR = kA3Ring;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto q_smem = [&](int q) { return smem_base + q * kTileBytes; };
+    auto st_smem = [&](int s) { return smem_base + 2 * kTileBytes + s * kA3Stage; };
+    const uint32_t bar_base = smem_base + kA3SmemData;
+    const uint32_t q_full = bar_base, q_empty = bar_base + 8;
+    auto st_full = [&](int s) { return bar_base + 16 + s * 8; };
+    auto st_empty = [&](int s) { return bar_base + 16 + (kR + s) * 8; };
+    auto s_full = [&](int q, int b) { return bar_base + 16 + (2 * kR + q * 2 + b) * 8; };
+    auto p_full = [&](int q, int b) { return bar_base + 16 + (2 * kR + 4 + q * 2 + b) * 8; };
+    auto pv_done = [&](int q) { return bar_base + 16 + (2 * kR + 8 + q) * 8; };
+    auto o_empty = [&](int q) { return bar_base + 16 + (2 * kR + 10 + q) * 8; };
+    const uint32_t tmem_slot = bar_base + 16 + (2 * kR + 12) * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&p.tmQ);
+        prefetch_tmap(&p.tmK);
+        prefetch_tmap(&p.tmV);
+    }
+    if (warp == 1 && elect_one()) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 2);                 // both issuers
+        for (int s = 0; s < kR; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 2); }
+        for (int q = 0; q < 2; ++q) {
+            for (int b = 0; b < 2; ++b) { mbar_init(s_full(q, b), 1); mbar_init(p_full(q, b), 4); }
+            mbar_init(pv_done(q), 1);
+            mbar_init(o_empty(q), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ld_shared_u32(tmem_slot);
+    auto s_tmem = [&](int q, int b) { return tmem_base + q * 128 + b * 64; };
+    auto o_tmem = [&](int q) { return tmem_base + 256 + q * 128; };
+    const int n_kv = p.n_kv;                 // 64-row steps
+
+    if (warp == 0) {
+        // ======================================= TMA producer =======================================
+        uint32_t n = 0, it = 0;              // n: stage sequence number, continues across items
+        bool ok = true;
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            const int col0 = head * kTile;
+            if (!mbar_wait(q_empty, (it & 1u) ^ 1u, p.abort_flag, 70)) break;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int row0 = (qb * 2 + q) * kTile;
+                    tma_load_2d(q_smem(q), &p.tmQ, q_full, col0, row0);
+                    tma_load_2d(q_smem(q) + kHalfBytes, &p.tmQ, q_full, col0 + 64, row0);
+                }
+            }
+            __syncwarp();
+            // stage = [first | second]; a negative step means "nothing in this half"
+            auto load = [&](const CUtensorMap* tm_a, int ja, int jb) -> bool {
+                const int slot = n % kR;
+                const uint32_t ph = (n / kR) & 1u;
+                if (!mbar_wait(st_empty(slot), ph ^ 1u, p.abort_flag, 71)) return false;
+                if (elect_one()) {
+                    const uint32_t dst = st_smem(slot);
+                    mbar_arrive_expect_tx(st_full(slot), jb >= 0 ? kA3Stage : kA3Tile);
+                    tma_load_2d(dst, tm_a, st_full(slot), col0, ja * kA3Rows);
+                    tma_load_2d(dst + kA3Half, tm_a, st_full(slot), col0 + 64, ja * kA3Rows);
+                    if (jb >= 0) {
+                        tma_load_2d(dst + kA3Tile, &p.tmK, st_full(slot), col0, jb * kA3Rows);
+                        tma_load_2d(dst + kA3Tile + kA3Half, &p.tmK, st_full(slot), col0 + 64, jb * kA3Rows);
+                    }
+                }
+                __syncwarp();
+                ++n;
+                return true;
+            };
+            ok = load(&p.tmK, 0, n_kv > 1 ? 1 : -1);
+            for (int j = 0; j < n_kv && ok; ++j) ok = load(&p.tmV, j, j + 2 < n_kv ? j + 2 : -1);
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ======================================= MMA issuer of query tile q =======================================
+        const int q = warp >> 1;
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);      // Q (K-major) x K_j (K-major, 64 rows)
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);     // P (TMEM) x V_j (MN-major, 64 rows)
+        const bool leader = elect_one();
+        const uint32_t qlo = desc_lo_k(q_smem(q));
+        const uint32_t o_acc = o_tmem(q);
+        uint32_t n = 0, it = 0;
+        uint32_t p_phase = 0;                 // bit b = parity of p_full(q, b)
+        bool ok = true;
+        PE_TRACE_DECL(0)
+
+        auto issue_s = [&](int b, uint32_t k_base) {
+            const uint32_t klo = desc_lo_k(k_base);
+            const uint32_t d = s_tmem(q, b);
+#pragma unroll
+            for (int kk = 0; kk < ((PE_A3_DBG & 1) ? 0 : 8); ++kk) {
+                const uint32_t qoff = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+                const uint32_t koff = ((kk >> 2) * kA3Half + (kk & 3) * 32) >> 4;
+                if (kk == 0) umma_ss_lohi<false>(d, qlo + qoff, klo + koff, idesc_s);
+                else umma_ss_lohi<true>(d, qlo + qoff, klo + koff, idesc_s);
+            }
+            umma_commit(s_full(q, b));
+        };
+        auto issue_pv = [&](int b, uint32_t v_base, bool accumulate) {
+            const uint32_t vlo = ((v_base & 0x3ffffu) >> 4) | kDescLboV64;
+            const uint32_t a = s_tmem(q, b);
+#pragma unroll
+            for (int kk = 0; kk < ((PE_A3_DBG & 2) ? 0 : 4); ++kk)
+                umma_ts_lohi(o_acc, a + kk * 8, vlo + kk * (2048 >> 4), idesc_o, (accumulate || kk != 0) ? 1u : 0u);
+        };
+
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+            if (!mbar_wait(q_full, it & 1u, p.abort_flag, 80)) break;
+            {
+                // prologue stage [K_0 | K_1]: S(q, 0) and S(q, 1) fill both S buffers
+                const uint32_t slot = n % kR;
+                if (!mbar_wait(st_full(slot), (n / kR) & 1u, p.abort_flag, 81)) break;
+                ++n;
+                tc_fence_after();
+                if (leader) {
+                    issue_s(0, st_smem(slot));
+                    if (n_kv > 1) issue_s(1, st_smem(slot) + kA3Tile);
+                    umma_commit(st_empty(slot));
+                    if (n_kv <= 2) umma_commit(q_empty);              // these were the item's last S MMAs
+                }
+                __syncwarp();
+            }
+            // previous item's epilogue must have drained O_q before PV(0) overwrites it
+            if (!mbar_wait(o_empty(q), (it & 1u) ^ 1u, p.abort_flag, 84)) break;
+            for (int j = 0; j < n_kv; ++j) {
+                const int b = j & 1;
+                const uint32_t slot = n % kR;
+                if (!mbar_wait(st_full(slot), (n / kR) & 1u, p.abort_flag, 82)) { ok = false; break; }
+                ++n;
+                if (q == 0) PE_TRACE(10, j);
+                if (!mbar_wait(p_full(q, b), (p_phase >> b) & 1u, p.abort_flag, 85)) { ok = false; break; }
+                p_phase ^= 1u << b;
+                tc_fence_after();
+                if (q == 0) PE_TRACE(12, j);
+                if (leader) {
+                    issue_pv(b, st_smem(slot), j > 0);
+                    if (j + 2 >= n_kv) umma_commit(pv_done(q));         // only the last two PVs are ever waited for
+                    if (q == 0) PE_TRACE(40, j);
+                    if (j + 2 < n_kv) issue_s(b, st_smem(slot) + kA3Tile);
+                    umma_commit(st_empty(slot));
+                    if (j + 3 == n_kv) umma_commit(q_empty);            // the item's last S MMAs were just issued
+                }
+                __syncwarp();
+                if (q == 0) PE_TRACE(14, j);
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================================= softmax / correction / epilogue =======================================
+        const int q = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+        const uint32_t o_addr = o_tmem(q) + lane_off;
+        const int row_in_tile = wq * 32 + lane;
+        uint32_t s_phase = 0;                 // bit b = parity of s_full(q, b)
+        uint32_t pv_base = 0;                 // pv_done(q) commits before this item (min(n_kv, 2) per item)
+        const uint32_t pv_per_item = n_kv >= 2 ? 2u : 1u;
+        bool ok = true;
+        PE_TRACE_DECL(1 + q)
+        for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+            const int head = item / p.n_qblk;
+            const int qb = item - head * p.n_qblk;
+            float m_ref = -INFINITY;          // exponent reference (log2 domain) of O and l; trails the running max
+            float l = 0.f;
+            float f_pending = 1.0f;           // O must still be multiplied by this before the next PV
+            for (int j = 0; j < n_kv; ++j) {
+                const int b = j & 1;
+                if (wq == 0) PE_TRACE(20 + q, j);
+                if (!mbar_wait(s_full(q, b), (s_phase >> b) & 1u, p.abort_flag, 90)) { ok = false; break; }
+                s_phase ^= 1u << b;
+                tc_fence_after();
+#if PE_A3_SKEW > 0
+                // The two tiles' softmax warps share the SMSPs pairwise.  Every item starts them together, and in lock step they
+                // reach their stall phases (barrier and TMEM waits) at the same time with the MUFU idle; a phase offset lets one
+                // tile's pass fill the other tile's stalls.
+                if (q == 1 && j == 0) {
+                    const long long t_skew = clock64() + PE_A3_SKEW;
+                    while (clock64() < t_skew) {}
+                }
+#endif
+                if (wq == 0) PE_TRACE(22 + q, j);
+                const uint32_t s_addr = s_tmem(q, b) + lane_off;
+                const int kv_valid = p.S - j * kA3Rows;
+                const bool full = kv_valid >= kA3Rows;
+                uint32_t ra[32], rb[32], pk[32];
+                tmem_ld32(s_addr, ra);
+                tmem_ld32(s_addr + 32, rb);
+                tmem_ld_wait();
+                if (wq == 0) PE_TRACE(30 + q, j);
+                if (j == 0) {
+                    // first step: exact row max
+                    float mx0 = -INFINITY;
+                    row_max_chunk(ra, 0, kv_valid, full, mx0);
+                    row_max_chunk(rb, 32, kv_valid, full, mx0);
+                    m_ref = mx0 * p.scale_log2;
+                }
+                float f_apply = f_pending;
+                f_pending = 1.0f;
+                float lsum = 0.f, mx = -INFINITY;
+                softmax_chunk(ra, 0, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                softmax_chunk(rb, 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                const float mx_scaled = mx * p.scale_log2;
+                const bool jump = mx_scaled - m_ref > 100.0f;
+                if (__any_sync(0xffffffffu, jump || f_apply != 1.0f)) {
+                    // rare path: overflow guard (redo the step against the true max; S is still in registers) and / or the
+                    // deferred O rescale.  Both touch O, which PV(j-1) may still be updating: wait for it first.
+                    if (__any_sync(0xffffffffu, jump)) {
+                        const float m_new = fmaxf(m_ref, mx_scaled);
+                        const float f = ex2(m_ref - m_new);
+                        f_apply *= f;
+                        l *= f;
+                        m_ref = m_new;
+                        lsum = 0.f;
+                        softmax_chunk(ra, 0, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                        softmax_chunk(rb, 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                    }
+                    if (j > 0) {
+                        bool done;
+                        if (j + 1 < n_kv) done = mbar_wait(s_full(q, b ^ 1), (s_phase >> (b ^ 1)) & 1u, p.abort_flag, 91);   // S(j+1) follows PV(j-1)
+                        else done = mbar_wait(pv_done(q), pv_base & 1u, p.abort_flag, 94);                                    // j = n-1: PV(n-2)
+                        if (!done) { ok = false; break; }
+                        tc_fence_after();
+                        scale_o_rows(o_addr, f_apply, ra);
+                    }
+                }
+                if (wq == 0) PE_TRACE(26 + q, j);
+                tmem_st16(s_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                tmem_st16(s_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(q, b));
+                if (wq == 0) PE_TRACE(28 + q, j);
+                l += lsum;
+                if (mx_scaled > m_ref + 8.0f) {
+                    f_pending = ex2(m_ref - mx_scaled);
+                    l *= f_pending;
+                    m_ref = mx_scaled;
+                }
+            }
+            if (!ok) break;
+
+            // ---- epilogue: O / l -> bf16 -> global ----
+            // A parity wait can only tell one phase from the next, so the item's pv_done commits (PV(n-2), PV(n-1)) are waited for in turn.
+            if (pv_per_item == 2u && !mbar_wait(pv_done(q), pv_base & 1u, p.abort_flag, 93)) break;
+            pv_base += pv_per_item;
+            if (!mbar_wait(pv_done(q), (pv_base - 1u) & 1u, p.abort_flag, 92)) break;
+            tc_fence_after();
+            const float inv = f_pending / l;
+            const long long row = (long long)(qb * 2 + q) * kTile + row_in_tile;
+            bf16* orow = p.o + row * p.ldo + head * kTile;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(o_addr + c * 32, r);
+                tmem_ld_wait();
+                if (row < p.S) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv);
+                        o.y = pack_bf16(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv);
+                        o.z = pack_bf16(__uint_as_float(r[8 * v + 4]) * inv, __uint_as_float(r[8 * v + 5]) * inv);
+                        o.w = pack_bf16(__uint_as_float(r[8 * v + 6]) * inv, __uint_as_float(r[8 * v + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + v * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty(q));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+int launch_attention3(Handle* h, AttnParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        PE_CHECK_CUDA(h, cudaFuncSetAttribute(attention_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3Smem));
+        configured = true;
+    }
+    p.n_qblk = ceil_div(p.S, kTile * 2);
+    p.n_items = p.H * p.n_qblk;
+    p.n_kv = ceil_div(p.S, kA3Rows);
+    int ctas = h->sm_count;
+    if (ctas > p.n_items) ctas = p.n_items;
+    attention_kernel3<<<ctas, kA3Threads, kA3Smem, stream>>>(p);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // small generic attention (CUDA cores) for the training-path encoders whose sequences are tiny:
 // DINOv2 ViT-B (261 tokens, 12 heads x 64; transformers modeling_dinov2_with_registers.py:174-254)
 // and the perceiver resampler (64 latent queries over <= 10304 media+latent keys, 8 heads x 64;
@@ -1085,9 +1432,10 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     memset(&p, 0, sizeof(p));
     int rc = make_tmap_2d(h, &p.tmQ, q, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(h, &p.tmK, k, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    const uint32_t kv_box_rows = (flags & PE_ATTN_FLAG_KV64) ? 64 : 128;
+    rc = make_tmap_2d(h, &p.tmK, k, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, kv_box_rows);
     if (rc) return rc;
-    rc = make_tmap_2d(h, &p.tmV, v, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    rc = make_tmap_2d(h, &p.tmV, v, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, kv_box_rows);
     if (rc) return rc;
     p.o = static_cast<bf16*>(o);
     p.ldo = ld;
@@ -1100,6 +1448,8 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     p.trace = static_cast<long long*>(h->workspace);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 200000, stream);
 #endif
+    if (flags & PE_ATTN_FLAG_KV64)
+        return launch_attention3(h, p, stream);          // 64-row KV steps, double-buffered S: softmax off the MMA latency chain
     if (flags & PE_ATTN_FLAG_SPLIT_ROW_SOFTMAX)
         return launch_attention2(h, p, stream);          // split-row softmax: exact max every step, two warps per SMSP per tile
     const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;

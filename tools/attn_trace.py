@@ -37,7 +37,7 @@ for step in (3, 4, 5, 20, 21):
     print(f"--- step {step}")
     for e in rows:
         if e[1] == step:
-            print(f"   {names.get(e[0], e[0]):16s} {e[2] - t0:9d}")
+            print(f"   {str(names.get(e[0], e[0])):16s} {e[2] - t0:9d}")
 # summary: mean per-step period and component durations over steps 8..60
 def T(evn, st):
     for e in rows:
@@ -58,3 +58,6 @@ for st in range(8, 60):
         issue.append(T(14, st) - T(12, st))
 mean = lambda x: sum(x) / max(len(x), 1)
 print(f"period/step {mean(per):.0f} cyc | softmax0 busy {mean(sm):.0f} | softmax0 waits for S {mean(wait_s):.0f} | mma waits for P0 {mean(mma_wait):.0f} | mma issue PV0+S0 {mean(issue):.0f}")
+# finer MMA-issuer events (attention_kernel3): 40/41 = PV issued, 42/43 = S issued
+for st in (20, 21):
+    print(f"--- issuer step {st}:", [(names.get(e[0], e[0]), e[2] - t0) for e in rows if e[1] == st and (e[0] < 20 or e[0] >= 40)])
