@@ -17,6 +17,7 @@
 //                                  grows by more than 2^8), so the common KV step never touches O.
 // With kQT = 2 the two query tiles ping-pong: the tensor core computes S_1 / PV_1 while the
 // softmax warpgroup of tile 0 works, and vice versa.
+#include <type_traits>
 #include "ptx.cuh"
 #include "common.cuh"
 
@@ -1052,9 +1053,12 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
     auto st_empty = [&](int s) { return bar_base + 16 + (kR + s) * 8; };
     auto s_full = [&](int q, int b) { return bar_base + 16 + (2 * kR + q * 2 + b) * 8; };
     auto p_full = [&](int q, int b) { return bar_base + 16 + (2 * kR + 4 + q * 2 + b) * 8; };
-    auto pv_done = [&](int q) { return bar_base + 16 + (2 * kR + 8 + q) * 8; };
-    auto o_empty = [&](int q) { return bar_base + 16 + (2 * kR + 10 + q) * 8; };
-    const uint32_t tmem_slot = bar_base + 16 + (2 * kR + 12) * 8;
+    // pv_done(q, 0): PV(n-2) of the item has completed; pv_done(q, 1): PV(n-1) has.  One commit per item each, so the phase
+    // parity is the item parity and a waiter can never be more than one phase behind (a single barrier taking both commits
+    // aliased when both PVs had completed before the epilogue's first wait -- found as a timeout with a slower softmax).
+    auto pv_done = [&](int q, int w) { return bar_base + 16 + (2 * kR + 8 + q * 2 + w) * 8; };
+    auto o_empty = [&](int q) { return bar_base + 16 + (2 * kR + 12 + q) * 8; };
+    const uint32_t tmem_slot = bar_base + 16 + (2 * kR + 14) * 8;
 
     const int warp = threadIdx.x >> 5;
     const int lane = lane_id();
@@ -1070,7 +1074,8 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
         for (int s = 0; s < kR; ++s) { mbar_init(st_full(s), 1); mbar_init(st_empty(s), 2); }
         for (int q = 0; q < 2; ++q) {
             for (int b = 0; b < 2; ++b) { mbar_init(s_full(q, b), 1); mbar_init(p_full(q, b), 4); }
-            mbar_init(pv_done(q), 1);
+            mbar_init(pv_done(q, 0), 1);
+            mbar_init(pv_done(q, 1), 1);
             mbar_init(o_empty(q), 4);
         }
         fence_mbar_init();
@@ -1191,7 +1196,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
                 if (q == 0) PE_TRACE(12, j);
                 if (leader) {
                     issue_pv(b, st_smem(slot), j > 0);
-                    if (j + 2 >= n_kv) umma_commit(pv_done(q));         // only the last two PVs are ever waited for
+                    if (j + 2 >= n_kv) umma_commit(pv_done(q, j + 2 - n_kv));   // only the last two PVs are ever waited for
                     if (q == 0) PE_TRACE(40, j);
                     if (j + 2 < n_kv) issue_s(b, st_smem(slot) + kA3Tile);
                     umma_commit(st_empty(slot));
@@ -1209,8 +1214,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
         const uint32_t o_addr = o_tmem(q) + lane_off;
         const int row_in_tile = wq * 32 + lane;
         uint32_t s_phase = 0;                 // bit b = parity of s_full(q, b)
-        uint32_t pv_base = 0;                 // pv_done(q) commits before this item (min(n_kv, 2) per item)
-        const uint32_t pv_per_item = n_kv >= 2 ? 2u : 1u;
+        uint32_t item_par = 0;                // parity of this CTA's item count = phase parity of pv_done(q, *)
         bool ok = true;
         PE_TRACE_DECL(1 + q)
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
@@ -1219,42 +1223,49 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
             float m_ref = -INFINITY;          // exponent reference (log2 domain) of O and l; trails the running max
             float l = 0.f;
             float f_pending = 1.0f;           // O must still be multiplied by this before the next PV
-            for (int j = 0; j < n_kv; ++j) {
+            bool s_ready = false;             // answer of the non-blocking probe of s_full for the coming step
+            // One KV step.  kFirst / kFull are compile-time so that the steady-state loop (full 64-row steps after the first) is one
+            // compact straight-line body: with the first-step, ragged-tail and redo code inlined into a single loop the executed path
+            // was spread over 28 KB of code and ~9 % of the softmax warps' samples were instruction-fetch stalls (r1 ncu source view).
+            auto kv_step = [&](auto first_tag, auto full_tag, const int j) -> bool {
+                constexpr bool kFirst = decltype(first_tag)::value;
+                constexpr bool kFull = decltype(full_tag)::value;
                 const int b = j & 1;
                 if (wq == 0) PE_TRACE(20 + q, j);
-                if (!mbar_wait(s_full(q, b), (s_phase >> b) & 1u, p.abort_flag, 90)) { ok = false; break; }
+                if (kFirst || !__all_sync(0xffffffffu, s_ready)) {
+                    if (!mbar_wait(s_full(q, b), (s_phase >> b) & 1u, p.abort_flag, 90)) return false;
+                }
                 s_phase ^= 1u << b;
                 tc_fence_after();
 #if PE_A3_SKEW > 0
-                // The two tiles' softmax warps share the SMSPs pairwise.  Every item starts them together, and in lock step they
-                // reach their stall phases (barrier and TMEM waits) at the same time with the MUFU idle; a phase offset lets one
-                // tile's pass fill the other tile's stalls.
-                if (q == 1 && j == 0) {
+                if (kFirst && q == 1) {
                     const long long t_skew = clock64() + PE_A3_SKEW;
                     while (clock64() < t_skew) {}
                 }
 #endif
                 if (wq == 0) PE_TRACE(22 + q, j);
                 const uint32_t s_addr = s_tmem(q, b) + lane_off;
-                const int kv_valid = p.S - j * kA3Rows;
-                const bool full = kv_valid >= kA3Rows;
+                const int kv_valid = kFull ? kA3Rows : p.S - j * kA3Rows;
                 uint32_t ra[32], rb[32], pk[32];
                 tmem_ld32(s_addr, ra);
                 tmem_ld32(s_addr + 32, rb);
                 tmem_ld_wait();
                 if (wq == 0) PE_TRACE(30 + q, j);
-                if (j == 0) {
+                if (kFirst) {
                     // first step: exact row max
                     float mx0 = -INFINITY;
-                    row_max_chunk(ra, 0, kv_valid, full, mx0);
-                    row_max_chunk(rb, 32, kv_valid, full, mx0);
+                    row_max_chunk(ra, 0, kv_valid, kFull, mx0);
+                    row_max_chunk(rb, 32, kv_valid, kFull, mx0);
                     m_ref = mx0 * p.scale_log2;
                 }
                 float f_apply = f_pending;
                 f_pending = 1.0f;
                 float lsum = 0.f, mx = -INFINITY;
-                softmax_chunk(ra, 0, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-                softmax_chunk(rb, 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                softmax_chunk(ra, 0, kv_valid, kFull, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                softmax_chunk(rb, 32, kv_valid, kFull, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                // Is S(j+1) there?  (It was issued a whole step ago.)  Asked here, answered at the top of the next step, so the
+                // ~130-cycle latency of a barrier poll is off the critical path (r1 ncu: 13 % of the softmax warps' samples).
+                s_ready = (j + 1 < n_kv) && mbar_test_wait(s_full(q, b ^ 1), (s_phase >> (b ^ 1)) & 1u);
                 const float mx_scaled = mx * p.scale_log2;
                 const bool jump = mx_scaled - m_ref > 100.0f;
                 if (__any_sync(0xffffffffu, jump || f_apply != 1.0f)) {
@@ -1267,14 +1278,14 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
                         l *= f;
                         m_ref = m_new;
                         lsum = 0.f;
-                        softmax_chunk(ra, 0, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-                        softmax_chunk(rb, 32, kv_valid, full, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+                        softmax_chunk(ra, 0, kv_valid, kFull, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+                        softmax_chunk(rb, 32, kv_valid, kFull, p.scale_log2, m_ref, lsum, mx, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
                     }
-                    if (j > 0) {
+                    if (!kFirst) {
                         bool done;
                         if (j + 1 < n_kv) done = mbar_wait(s_full(q, b ^ 1), (s_phase >> (b ^ 1)) & 1u, p.abort_flag, 91);   // S(j+1) follows PV(j-1)
-                        else done = mbar_wait(pv_done(q), pv_base & 1u, p.abort_flag, 94);                                    // j = n-1: PV(n-2)
-                        if (!done) { ok = false; break; }
+                        else done = mbar_wait(pv_done(q, 0), item_par, p.abort_flag, 94);                                     // j = n-1: PV(n-2)
+                        if (!done) return false;
                         tc_fence_after();
                         scale_o_rows(o_addr, f_apply, ra);
                     }
@@ -1293,14 +1304,20 @@ __global__ void __launch_bounds__(kA3Threads, 1) attention_kernel3(const __grid_
                     l *= f_pending;
                     m_ref = mx_scaled;
                 }
-            }
+                return true;
+            };
+            using T = std::true_type;
+            using F = std::false_type;
+            const int n_full = p.S / kA3Rows;         // steps with all 64 kv rows valid (n_kv - 1 or n_kv)
+            ok = n_full >= 1 ? kv_step(T{}, T{}, 0) : kv_step(T{}, F{}, 0);
+#pragma unroll 1
+            for (int j = 1; j < n_full && ok; ++j) ok = kv_step(F{}, T{}, j);
+            if (ok && n_full >= 1 && n_full < n_kv) ok = kv_step(F{}, F{}, n_full);
             if (!ok) break;
 
             // ---- epilogue: O / l -> bf16 -> global ----
-            // A parity wait can only tell one phase from the next, so the item's pv_done commits (PV(n-2), PV(n-1)) are waited for in turn.
-            if (pv_per_item == 2u && !mbar_wait(pv_done(q), pv_base & 1u, p.abort_flag, 93)) break;
-            pv_base += pv_per_item;
-            if (!mbar_wait(pv_done(q), (pv_base - 1u) & 1u, p.abort_flag, 92)) break;
+            if (!mbar_wait(pv_done(q, 1), item_par, p.abort_flag, 92)) break;      // PV(n-1), hence every PV of the item, has completed
+            item_par ^= 1u;
             tc_fence_after();
             const float inv = f_pending / l;
             const long long row = (long long)(qb * 2 + q) * kTile + row_in_tile;
