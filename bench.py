@@ -240,18 +240,42 @@ def run_native(args):
     except OSError:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    # dominant kernel: the MLP up-projection GEMM (tcgen05): algorithmic FLOPs per launch / mean launch duration
+    # Roofline per hot kernel: ALGORITHMIC flops (or bytes) per launch / mean launch duration (CUDA events on the launch stream).
+    # `roofline` is the kernel with the largest share of the step; `roofline_by_kernel` lists all of them.
+    peak_gbs = peaks.get("hbm_gbs", 6500.0)
+    S_avg = S_img + (T_POSI + T_NEGA) / 2
+    S2_avg = ((S_img + T_POSI) ** 2 + (S_img + T_NEGA) ** 2) / 2
+    hot = {  # tag: (description, bound, algorithmic flops per launch, algorithmic bytes per launch, ncu kernel name for the traffic figure)
+        "attention": ("attention_kernel<2 query tiles, P in TMEM> (joint attention, S x S x 128 x 24 heads)", "tensor", 4 * S2_avg * 128 * 24,
+                      4 * S_avg * DIM * 2, "attention_kernel<2, 1>"),
+        "gemm_up": ("gemm_kernel<cta_pair, bias+gelu> (MLP up-projection, M=S N=12288 K=3072)", "tensor", 2 * S_avg * DIM * 4 * DIM,
+                    2 * (S_avg * DIM + 4 * DIM * DIM + S_avg * 4 * DIM), "gemm_kernel<2, 2>"),
+        "gemm_down": ("gemm_kernel<cta_pair, gate-residual> (MLP down-projection, M=S N=3072 K=12288)", "tensor", 2 * S_avg * DIM * 4 * DIM,
+                      2 * (S_avg * 4 * DIM + 4 * DIM * DIM + 2 * S_avg * DIM), None),
+        "gemm_qkv": ("gemm_kernel<cta_pair, qkv norm+rope> (fused QKV projection, M=S N=9216 K=3072)", "tensor", 2 * S_avg * DIM * 3 * DIM,
+                     2 * (S_avg * DIM + 3 * DIM * DIM + 3 * S_avg * DIM), None),
+        "gemm_out": ("gemm_kernel<cta_pair, gate-residual> (attention out-projection, M=S N=3072 K=3072)", "tensor", 2 * S_avg * DIM * DIM,
+                     2 * (S_avg * DIM + DIM * DIM + 2 * S_avg * DIM), None),
+        "ln_mod": ("layernorm_modulate2 (LN + AdaLN scale/shift, both streams)", "hbm", None, 2 * S_avg * DIM * 2, None),
+    }
+    roofs = {}
+    for tag, (desc, bound, fl, by, ncu_name) in hot.items():
+        if not prof.get(tag):
+            continue
+        n, tot = prof[tag]
+        avg_s = tot / n * 1e-3
+        if bound == "tensor":
+            ach, pk, unit, src = fl / avg_s / 1e12, peak_tf, "TFLOP/s", "MEASURED_PEAKS.json bf16_tflops_sustained"
+        else:
+            ach, pk, unit, src = by / avg_s / 1e9, peak_gbs, "GB/s", "MEASURED_PEAKS.json hbm_gbs"
+        roofs[tag] = {"bound": bound, "kernel": desc, "achieved": round(ach, 1), "peak": pk, "peak_source": src if peaks else "fallback", "unit": unit,
+                      "frac": round(ach / pk, 4), "traffic": ncu_traffic_bytes(ncu_name) if ncu_name else None,
+                      "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_full_metrics.json)", "algorithmic_bytes": int(by),
+                      "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms, 4)}
     roof = None
-    if prof.get("gemm_up"):
-        n, tot = prof["gemm_up"]
-        S_avg = S_img + (T_POSI + T_NEGA) / 2
-        fl = 2 * S_avg * DIM * 4 * DIM
-        ach = fl / (tot / n * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_kernel<cta_pair, bias+gelu> (MLP up-projection, M=S N=12288 K=3072)", "achieved": round(ach, 1),
-                "peak": peak_tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4), "traffic": ncu_traffic_bytes("gemm_kernel<2, 2>"), "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_full_metrics.json)",
-                "algorithmic_bytes": int(2 * (S_avg * DIM + 4 * DIM * DIM + S_avg * 4 * DIM)), "launches": n, "avg_ms": round(tot / n, 4),
-                "whole_step_frac": round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)}
+    if roofs:
+        roof = dict(roofs[max(roofs, key=lambda k: roofs[k]["share_of_step"])])
+        roof["whole_step_frac"] = round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)
     shares = {k: round(v[1] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     res = {
         "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(world * args.steps / (ms * 1e-3), 4), "unit": "steps/s",
@@ -262,7 +286,7 @@ def run_native(args):
                    "tflops_per_step": round(fl_step / 1e12, 2), "achieved_tflops_per_gpu": round(fl_step * args.steps / (ms * 1e-3) / 1e12, 1)},
         "e2e": {"value": round(world * e2e_steps / (ms_e2e * 1e-3), 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
-        "gpu_launches": launches, "finite": finite, "clocks": clocks, "roofline": roof, "kernel_time_share": shares,
+        "gpu_launches": launches, "finite": finite, "clocks": clocks, "roofline": roof, "roofline_by_kernel": roofs, "kernel_time_share": shares,
     }
     if world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args)
