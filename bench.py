@@ -151,6 +151,7 @@ def run_native(args):
     eng = pipe.dit.engine()
     eng.use_cta_pair = not args.no_cta_pair
     eng.attn_flags = args.attn_flags
+    pipe.cfg_streams = args.cfg_streams
     host = host_inputs(H, W, seed=100 + rank)             # a different image per rank
     dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
     ip = dict(prompt_emb=dev["pe_posi"], prompt_emb_mask=dev["mask_posi"], special_token_mask=dev["sp_posi"])
@@ -166,8 +167,7 @@ def run_native(args):
         t_host = float(sched.timesteps[pid].to(torch.bfloat16))
         kw = dict(dit=pipe.dit, visual_thinking_adapter=pipe.visual_thinking_adapter, latents=latents, timestep=ts_dev[pid:pid + 1], height=H, width=W,
                   edit_latents=dev["edit_latents"], is_train=False, timestep_host=t_host)
-        pipe.model_fn(**kw, **ip, out=vp)
-        pipe.model_fn(**kw, **in_, out=vn)
+        pipe.run_cfg_branches(kw, ip, in_, vp, vn, ts_dev[pid:pid + 1], t_host)
         nat.cfg_euler_step(latents, vp, vn, 4.0, float(sched.dsigma(sched.timesteps[pid])))
 
     def barrier():
@@ -184,7 +184,11 @@ def run_native(args):
     if rank == 0:
         sampler.start()
     l0 = nat.launches
-    nat.prof = {} if not args.no_kernel_events else None
+    # Per-launch CUDA events are taken in the timed region itself when the branches run on one stream.  With two streams the launches
+    # of the two branches overlap on the GPU and a per-launch duration is ambiguous, so the attribution (roofline, kernel shares) then
+    # comes from `attr_steps` extra single-stream steps run right after the timed region (same process, same clocks, same inputs).
+    events_in_region = not args.no_kernel_events and args.cfg_streams == 1
+    nat.prof = {} if events_in_region else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -200,6 +204,22 @@ def run_native(args):
     launches = nat.launches - l0
     prof = nat.profile_summary()
     nat.prof = None
+    ms_attr, attr_steps = ms, args.steps
+    if not args.no_kernel_events and not events_in_region:
+        attr_steps = 2
+        pipe.cfg_streams = 1
+        nat.prof = {}
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(attr_steps):
+            one_step(args.warmup + args.steps + i, lat)
+        a1.record()
+        barrier()
+        ms_attr = a0.elapsed_time(a1)
+        prof = nat.profile_summary()
+        nat.prof = None
+        pipe.cfg_streams = args.cfg_streams
     nat.check_async()
     finite = bool(torch.isfinite(lat.float()).all().item())
 
@@ -271,18 +291,22 @@ def run_native(args):
         roofs[tag] = {"bound": bound, "kernel": desc, "achieved": round(ach, 1), "peak": pk, "peak_source": src if peaks else "fallback", "unit": unit,
                       "frac": round(ach / pk, 4), "traffic": ncu_traffic_bytes(ncu_name) if ncu_name else None,
                       "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_full_metrics.json)", "algorithmic_bytes": int(by),
-                      "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms, 4)}
+                      "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms_attr, 4)}
     roof = None
     if roofs:
         roof = dict(roofs[max(roofs, key=lambda k: roofs[k]["share_of_step"])])
         roof["whole_step_frac"] = round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)
-    shares = {k: round(v[1] / ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    shares = {k: round(v[1] / ms_attr, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     res = {
         "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(world * args.steps / (ms * 1e-3), 4), "unit": "steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights of the real architecture, seeded inputs)",
         "config": {"workload": f"{H}x{W} single-image edit, 50-step schedule, bf16, {args.layers} blocks, 4096 edit tokens, T=512/288, one image per GPU",
                    "l2": "inputs larger than L2: 40.8 GB of weights stream per forward", "images_per_sec_50_steps": round(world * args.steps / (ms * 1e-3) / 50, 5),
+                   "cfg_streams": args.cfg_streams,
+                   "attribution": ("per-launch CUDA events over the timed region" if events_in_region else
+                                   f"per-launch CUDA events over {attr_steps} extra single-stream steps right after the timed region "
+                                   f"({round(ms_attr / attr_steps, 2)} ms/step; with two streams the branches' launches overlap)"),
                    "tflops_per_step": round(fl_step / 1e12, 2), "achieved_tflops_per_gpu": round(fl_step * args.steps / (ms * 1e-3) / 1e12, 1)},
         "e2e": {"value": round(world * e2e_steps / (ms_e2e * 1e-3), 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
@@ -355,6 +379,8 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--no-cta-pair", action="store_true")
     ap.add_argument("--attn-flags", dest="attn_flags", type=int, default=0, help="PE_ATTN_FLAG_* bits (8 = split-row softmax kernel)")
+    ap.add_argument("--cfg-streams", dest="cfg_streams", type=int, default=2, choices=[1, 2],
+                    help="2 = the two CFG branches of a step run concurrently on two CUDA streams (fills partial last waves)")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=8, help="cap on timed CPU samples of --impl reference")

@@ -284,7 +284,7 @@ class DiTEngine:
         self.nat = nv.Native.get(self.device.index or 0)
         self.use_cta_pair = True
         self.attn_flags = 0
-        self._ws: Dict[Tuple[int, int], Workspace] = {}
+        self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._rope: Dict[tuple, torch.Tensor] = {}
         self._mods_cache: Optional[Tuple[float, torch.Tensor, torch.Tensor, torch.Tensor]] = None
         self._pack()
@@ -331,10 +331,12 @@ class DiTEngine:
         self._cond_table = None
 
     # -- cached per-shape state ---------------------------------------------------------------------
-    def workspace(self, S_img: int, T: int) -> Workspace:
-        key = (S_img, T)
+    def workspace(self, S_img: int, T: int, branch: int = 0) -> Workspace:
+        """Activation buffers for one forward.  `branch` separates the two CFG branches when they run concurrently on two
+        streams (pipeline.denoise_step, cfg_streams=2): equal shapes must not share buffers then."""
+        key = (S_img, T, branch)
         if key not in self._ws:
-            if len(self._ws) >= 4:
+            if len(self._ws) >= 6:
                 self._ws.pop(next(iter(self._ws)))
             self._ws[key] = Workspace(S_img, T, self.device)
         return self._ws[key]
@@ -442,14 +444,14 @@ class DiTEngine:
                   dict(a=ws.h[:T], w=tm[2].weight, bias=tm[2].bias, out=xt, gate=mt[5 * D:6 * D])], D, 4 * D, nv.EPI_GATE_RESIDUAL, flags)
 
     def forward(self, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
-                out_latents: torch.Tensor, t_key: Optional[float] = None) -> torch.Tensor:
+                out_latents: torch.Tensor, t_key: Optional[float] = None, branch: int = 0) -> torch.Tensor:
         """latents_list: [noise latents, edit/context latents ...] each [1,16,h8,w8] bf16; prompt_emb [T,3584] bf16
         (already updated by the adapter).  Writes the velocity for the first entry into out_latents [1,16,h8,w8]."""
         nat, dit = self.nat, self.dit
         T = prompt_emb.shape[0]
         shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]
         S_img = sum(h * w for _, h, w in shapes)
-        ws = self.workspace(S_img, T)
+        ws = self.workspace(S_img, T, branch)
         rope = self.rope(shapes, T)
         temb, mods, out_mod = self.conditioning(timestep_bf16, t_key)
         # patchify + img_in

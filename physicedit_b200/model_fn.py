@@ -59,6 +59,7 @@ def model_fn_qwen_image(
     pseudo_special_emb_vae=None,
     timestep_host: Optional[float] = None,
     out: Optional[torch.Tensor] = None,
+    cfg_branch: int = 0,
     **kwargs,
 ):
     if entity_prompt_emb is not None or blockwise_controlnet_conditioning is not None or edit_rope_interpolation or enable_fp8_attention:
@@ -99,5 +100,5 @@ def model_fn_qwen_image(
     lat_list = [l.contiguous() for l in lat_list]
     if out is None:
         out = torch.empty_like(latents)
-    eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host)
+    eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host, branch=cfg_branch)
     return out, special_token_loss

@@ -110,6 +110,10 @@ def load_dit(path, torch_dtype=torch.bfloat16, device="cuda") -> Optional[QwenIm
 
 
 class QwenImagePhysicPipeline(nn.Module):
+    # 2: the two CFG branches of a denoise step run concurrently on two CUDA streams (see run_cfg_branches); 1: back to back.
+    # Bit-identical results either way; two streams measured +3 % steps/s at 1024^2 (r1, power-capped B200).
+    cfg_streams = 2
+
     def __init__(self, device="cuda", torch_dtype=torch.bfloat16, dinov2_path=None, dinov2_config: dict = None, build_training_path: bool = True):
         super().__init__()
         self.device, self.torch_dtype = device, torch_dtype
@@ -224,12 +228,34 @@ class QwenImagePhysicPipeline(nn.Module):
             kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=ts_dev[progress_id:progress_id + 1],
                       height=height, width=width, edit_latents=edit_latents, context_latents=context_latents, is_train=False,
                       progress_id=progress_id, timestep_host=t_host)
-            self.model_fn(**kw, **inputs_posi, out=vp)
-            if cfg_scale != 1.0:
-                self.model_fn(**kw, **inputs_nega, out=vn)
+            self.run_cfg_branches(kw, inputs_posi, inputs_nega if cfg_scale != 1.0 else None, vp, vn, ts_dev[progress_id:progress_id + 1], t_host)
             ds = float(self.scheduler.dsigma(t))
             nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), ds)
         return latents
+
+    @torch.no_grad()
+    def run_cfg_branches(self, kw: dict, inputs_posi: dict, inputs_nega: Optional[dict], vp, vn, t_dev, t_host) -> None:
+        """The positive (and, with CFG, the negative) DiT forward of one denoise step (:653-655) into vp / vn.
+        With `self.cfg_streams == 2` the two branches -- independent until the combine -- run on two streams: every hot kernel is a
+        persistent grid of one CTA (pair) per SM whose last wave is partial (816 attention items or 408 out-projection tiles on
+        148 SMs = 5.51 waves), and with a second stream the other branch's CTAs take the SMs a finishing kernel releases.
+        Results are unchanged: same kernels, same inputs, separate workspaces (cfg_branch)."""
+        if inputs_nega is not None and getattr(self, "cfg_streams", 1) == 2:
+            dev = vp.device
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(dev)
+            side = self._side_stream
+            self.dit.engine().conditioning(t_dev, t_host)       # timestep-only tensors: computed (or found cached) before the fork
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.model_fn(**kw, **inputs_nega, out=vn, cfg_branch=1)
+            self.model_fn(**kw, **inputs_posi, out=vp, cfg_branch=0)
+            main.wait_stream(side)
+        else:
+            self.model_fn(**kw, **inputs_posi, out=vp)
+            if inputs_nega is not None:
+                self.model_fn(**kw, **inputs_nega, out=vn)
 
     @torch.no_grad()
     def denoise_step(self, latents, inputs_posi: dict, inputs_nega: Optional[dict], edit_latents=None, context_latents=None, *, progress_id: int,
@@ -245,9 +271,7 @@ class QwenImagePhysicPipeline(nn.Module):
         vp, vn = self._vbuf
         kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=t_dev, height=height, width=width,
                   edit_latents=edit_latents, context_latents=context_latents, is_train=False, progress_id=progress_id, timestep_host=t_host)
-        self.model_fn(**kw, **inputs_posi, out=vp)
-        if cfg_scale != 1.0:
-            self.model_fn(**kw, **inputs_nega, out=vn)
+        self.run_cfg_branches(kw, inputs_posi, inputs_nega if cfg_scale != 1.0 else None, vp, vn, t_dev, t_host)
         nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), float(self.scheduler.dsigma(t)))
         return latents
 

@@ -280,6 +280,20 @@ def test_lora_fold_and_denoise_loop(golden):
     err = rel_l2(lat, lat32)
     assert err <= floor + TOL_EXTRA, (err, floor)
     assert torch.isfinite(lat).all()
+    # the two CFG branches on two streams (pipe.cfg_streams = 2): same kernels, same inputs -> bit-identical latents; run it with
+    # equal text lengths too, where the branches would share a workspace without the per-branch key
+    for t_nega in (meta["T_nega"], meta["T_posi"]):
+        nega2 = O.synth_inputs(meta["height"], meta["height"], t_nega, seed=meta["nega_seed"], dtype=torch.bfloat16)
+        res = []
+        for streams in (1, 2):
+            pipe.cfg_streams = streams
+            ip = {k: posi[k].cuda() for k in keys}            # prompt_emb is mutated in place by the adapter: fresh copies per run
+            in_ = {k: nega2[k].cuda() for k in keys}
+            res.append(pipe.denoise(posi["latents"].cuda(), ip, in_, posi["edit_latents"].cuda(), height=meta["height"], width=meta["height"],
+                                    num_inference_steps=meta["steps"], cfg_scale=4.0))
+            dit.engine().nat.check_async()
+        assert torch.equal(res[0], res[1])
+    pipe.cfg_streams = 1
 
 
 @gpu
