@@ -153,6 +153,10 @@ int pe_rmsnorm(pe_handle_t h, const void* x, void* out, int rows, int C, const v
 int pe_gemv(pe_handle_t h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K,
             int act_in, int act_out, const uint8_t* one_plus_mask, void* stream);
 
+/* y = bf16(act(x)) element-wise on n bf16 values; act: 0 copy, 1 SiLU (the nn.SiLU in front of img_mod / txt_mod / norm_out.linear,
+ * qwen_image_dit.py:333,347, utils.py:305, materialised once per timestep instead of inside every GEMV). */
+int pe_act(pe_handle_t h, const void* x, void* y, int64_t n, int act, void* stream);
+
 /* sinusoidal timestep embedding with the reference's bf16 quirks (utils.py:189-216):
  *   t_in: bf16 [1].  raw != 0: t_in is the loop's bf16(t) and ts = bf16(t_in/1000) is formed on device with
  *   ATen's CUDA rounding (qwen_image_physical.py:1342); raw == 0: t_in already holds ts (TimestepEmbeddings.forward). Then

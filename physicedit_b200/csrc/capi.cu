@@ -47,6 +47,7 @@ int layernorm_modulate2_run(Handle* h, const void* x, void* out, int rows, int C
 int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, float eps, cudaStream_t s);
 int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
              int act_out, const uint8_t* one_plus_mask, cudaStream_t s);
+int act_run(Handle* h, const void* x, void* y, long long n, int act, cudaStream_t s);
 int timestep_embedding_run(Handle* h, const void* t_in, void* out, int raw, cudaStream_t s);
 int patchify_run(Handle* h, const void* latents, void* tokens, int H8, int W8, cudaStream_t s);
 int unpatchify_run(Handle* h, const void* tokens, int64_t ld, void* latents, int H8, int W8, cudaStream_t s);
@@ -196,6 +197,11 @@ int pe_gemv(pe_handle_t hh, const void* x, const void* w, const void* bias, void
             int act_out, const uint8_t* one_plus_mask, void* stream) {
     PE_H(hh);
     return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, act_out, one_plus_mask, static_cast<cudaStream_t>(stream));
+}
+
+int pe_act(pe_handle_t hh, const void* x, void* y, int64_t n, int act, void* stream) {
+    PE_H(hh);
+    return pe::act_run(h, x, y, (long long)n, act, static_cast<cudaStream_t>(stream));
 }
 
 int pe_timestep_embedding(pe_handle_t hh, const void* t_in, void* out, int raw, void* stream) {

@@ -82,14 +82,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16
         if (vi >= nvec) continue;
         float o[8];
         if (MODE == 0) {
-            float a[8], b[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p1 + vi * 8)), a);   // bf16(1 + scale)
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p0 + vi * 8)), b);   // shift
+            // bf16(bf16(n * (1+scale)) + shift) in packed bf16x2 arithmetic: a bf16 x bf16 product is exact in fp32 and a bf16 + bf16 sum
+            // is either exact in fp32 or dominated by one operand, so HMUL2 / HADD2 (one rounding each; the _rn intrinsics keep nvcc from contracting them into one HFMA2) give the bits of the
+            // reference's fp32-compute-then-round ops -- without the F2F.BF16 conversions of a scalar formulation, which run on the
+            // 16-lane XU pipe and made this HBM-bound kernel XU-bound (r1: 192 F2F per row-warp, 0.41 of the HBM roofline).
+            const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(p1 + vi * 8));   // bf16(1 + scale)
+            const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(p0 + vi * 8));   // shift
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+            uint32_t ow[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float n = bf16_round((v[i][j] - mean) * rstd);
-                o[j] = bf16_round(n * a[j]) + b[j];
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 n2 = __floats2bfloat162_rn((v[i][2 * j] - mean) * rstd, (v[i][2 * j + 1] - mean) * rstd);
+                const __nv_bfloat162 t2 = __hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+                const __nv_bfloat162 o2 = __hadd2_rn(t2, *reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+                ow[j] = *reinterpret_cast<const uint32_t*>(&o2);
             }
+            *reinterpret_cast<uint4*>(orow + vi * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            continue;
         } else if (MODE == 1) {
             float a[8], b[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(p0 + vi * 8)), a);
@@ -171,6 +180,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) rmsnorm_kernel(const bf16* 
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_bf16(float x) { return bf16_round(x / (1.0f + expf(-x))); }
 
+// Each warp owns kGemvRows consecutive output features at a time, so one shared-memory read of x feeds kGemvRows dot products
+// (r1: with one row per warp a batch-8 launch moved 98 KB of x from shared memory per 6 KB weight row and ran at 0.1 of the HBM
+// roofline), and the weight vectors of the next 32-vector slice are in flight while the current slice is multiplied.
+// The per-lane partial sums and the butterfly reduction are those of the one-row formulation, so results are bit-identical to it.
+constexpr int kGemvRows = 4;
+
 template <int kBatch>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                   const bf16* __restrict__ bias, bf16* __restrict__ y, int N, int K,
@@ -184,45 +199,73 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nvec = K >> 3;
-    for (int n = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); n < N; n += gridDim.x * kWarpsPerCta) {
-        const bf16* wr = w + (size_t)n * K;
-        float acc[kBatch];
+    const int ngroups = (N + kGemvRows - 1) / kGemvRows;
+    for (int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * kWarpsPerCta) {
+        const int n0 = g * kGemvRows;
+        const bf16* wr[kGemvRows];
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) acc[b] = 0.f;
-        for (int v0 = 0; v0 < nvec; v0 += 32 * 4) {
-            uint4 u[4];
+        for (int r = 0; r < kGemvRows; ++r) wr[r] = w + (size_t)min(n0 + r, N - 1) * K;     // rows past N repeat the last row (not stored)
+        float acc[kGemvRows][kBatch];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int vi = v0 + lane + 32 * i;
-                u[i] = vi < nvec ? ld_stream(wr + vi * 8) : make_uint4(0, 0, 0, 0);
-            }
+        for (int r = 0; r < kGemvRows; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int vi = v0 + lane + 32 * i;
-                if (vi >= nvec) continue;
-                float f[8];
-                unpack8(u[i], f);
+            for (int b = 0; b < kBatch; ++b) acc[r][b] = 0.f;
+        uint4 u[kGemvRows], un[kGemvRows];
+#pragma unroll
+        for (int r = 0; r < kGemvRows; ++r) u[r] = lane < nvec ? ld_stream(wr[r] + lane * 8) : make_uint4(0, 0, 0, 0);
+        for (int v0 = 0; v0 < nvec; v0 += 32) {
+            const int vi = v0 + lane;
+            const int vn = vi + 32;
+#pragma unroll
+            for (int r = 0; r < kGemvRows; ++r) un[r] = vn < nvec ? ld_stream(wr[r] + vn * 8) : make_uint4(0, 0, 0, 0);
+            if (vi < nvec) {
+                float f[kGemvRows][8];
+#pragma unroll
+                for (int r = 0; r < kGemvRows; ++r) unpack8(u[r], f[r]);
 #pragma unroll
                 for (int b = 0; b < kBatch; ++b) {
                     const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8);
                     const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8 + 4);
-                    acc[b] += f[0] * x0.x + f[1] * x0.y + f[2] * x0.z + f[3] * x0.w + f[4] * x1.x + f[5] * x1.y + f[6] * x1.z + f[7] * x1.w;
+#pragma unroll
+                    for (int r = 0; r < kGemvRows; ++r)
+                        acc[r][b] += f[r][0] * x0.x + f[r][1] * x0.y + f[r][2] * x0.z + f[r][3] * x0.w + f[r][4] * x1.x + f[r][5] * x1.y +
+                                     f[r][6] * x1.z + f[r][7] * x1.w;
                 }
             }
-        }
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) acc[b] = warp_sum(acc[b]);
-        if (lane == 0) {
-            const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+            for (int r = 0; r < kGemvRows; ++r) u[r] = un[r];
+        }
+        // reduce; afterwards lane r * kBatch + b holds output (row n0 + r, batch b) and stores it
+        float mine = 0.f;
+#pragma unroll
+        for (int r = 0; r < kGemvRows; ++r)
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
-                float r = bf16_round(acc[b] + bv);
-                if (act_out == 1) r = silu_bf16(r);
-                if (one_plus_mask != nullptr && one_plus_mask[n]) r = bf16_round(1.0f + r);
-                y[(size_t)b * N + n] = __float2bfloat16_rn(r);
+                const float t = warp_sum(acc[r][b]);
+                if (lane == r * kBatch + b) mine = t;
+            }
+        if (lane < kGemvRows * kBatch) {
+            const int r = lane / kBatch, b = lane - r * kBatch;
+            const int n = n0 + r;
+            if (n < N) {
+                const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+                float o = bf16_round(mine + bv);
+                if (act_out == 1) o = silu_bf16(o);
+                if (one_plus_mask != nullptr && one_plus_mask[n]) o = bf16_round(1.0f + o);
+                y[(size_t)b * N + n] = __float2bfloat16_rn(o);
             }
         }
     }
+}
+
+// y = bf16(act(x)) element-wise (act 1 = SiLU as the reference's nn.SiLU on a bf16 tensor).  The conditioning path applies
+// SiLU(temb) once and feeds it to all 121 modulation GEMVs of a timestep batch instead of re-evaluating it in every CTA.
+__global__ void act_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, int act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float f = __bfloat162float(x[i]);
+    if (act == 1) f = silu_bf16(f);
+    y[i] = __float2bfloat16_rn(f);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -404,8 +447,8 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
     PE_REQUIRE(h, x && w && y, "pe_gemv: null pointer");
     PE_REQUIRE(h, (size_t)batch * K * 4 <= 200 * 1024, "pe_gemv: batch*K too large for shared memory");
     const size_t smem = (size_t)batch * K * sizeof(float);
-    int grid = ceil_div(N, kWarpsPerCta);
-    const int cap = h->sm_count * 8;
+    int grid = ceil_div(ceil_div(N, kGemvRows), kWarpsPerCta);
+    const int cap = h->sm_count * 4;
     if (grid > cap) grid = cap;
     const bf16* xb = static_cast<const bf16*>(x);
     const bf16* wb = static_cast<const bf16*>(w);
@@ -421,6 +464,14 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
         PE_GEMV_CASE(1) PE_GEMV_CASE(2) PE_GEMV_CASE(3) PE_GEMV_CASE(4) PE_GEMV_CASE(5) PE_GEMV_CASE(6) PE_GEMV_CASE(7) PE_GEMV_CASE(8)
     }
 #undef PE_GEMV_CASE
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int act_run(Handle* h, const void* x, void* y, long long n, int act, cudaStream_t s) {
+    PE_REQUIRE(h, x && y && n > 0, "pe_act: null pointer or empty tensor");
+    PE_REQUIRE(h, act == 0 || act == 1, "pe_act: act must be 0 (copy) or 1 (SiLU), got %d", act);
+    act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n, act);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

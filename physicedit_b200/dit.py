@@ -351,31 +351,38 @@ class DiTEngine:
         return self._rope[key]
 
     # -- pieces ---------------------------------------------------------------------------------------
-    def block_mods(self, temb: torch.Tensor, indices: Optional[Sequence[int]] = None) -> torch.Tensor:
+    def block_mods(self, temb: torch.Tensor, indices: Optional[Sequence[int]] = None, temb_act: Optional[torch.Tensor] = None) -> torch.Tensor:
         """img_mod / txt_mod of the given blocks for a batch of B <= 8 conditioning vectors temb [B, 3072]:
         returns [B, n, 2 (img, txt), 18432] with bf16(1+scale) in the scale slots.  The GEMV streams each weight matrix once
-        for the whole batch."""
+        for the whole batch; SiLU(temb) (the nn.SiLU in front of every modulation linear) is materialised once."""
         blocks = self.dit.transformer_blocks
         indices = list(range(len(blocks))) if indices is None else list(indices)
         B = temb.shape[0]
+        if temb_act is None:
+            temb_act = torch.empty_like(temb)
+            self.nat.tag = "gemv_mod"
+            self.nat.act(temb.contiguous(), temb_act, 1)
         out = torch.empty(len(indices), 2, B, 6 * DIM, dtype=torch.bfloat16, device=self.device)
         for n, i in enumerate(indices):
             b = blocks[i]
             self.nat.tag = "gemv_mod"
-            self.nat.gemv(temb, b.img_mod[1].weight, b.img_mod[1].bias, out[n, 0], 1, 0, self.mask6)
+            self.nat.gemv(temb_act, b.img_mod[1].weight, b.img_mod[1].bias, out[n, 0], 0, 0, self.mask6)
             self.nat.tag = "gemv_mod"
-            self.nat.gemv(temb, b.txt_mod[1].weight, b.txt_mod[1].bias, out[n, 1], 1, 0, self.mask6)
+            self.nat.gemv(temb_act, b.txt_mod[1].weight, b.txt_mod[1].bias, out[n, 1], 0, 0, self.mask6)
         return out.permute(2, 0, 1, 3)          # [B, n, 2, 18432] view; [b] is contiguous per (n, stream) row
 
     def _conditioning_batch(self, timesteps_bf16: torch.Tensor):
         """temb, block modulation table and norm_out (scale, shift) for B <= 8 timesteps at once."""
         B = timesteps_bf16.shape[0]
         temb = torch.cat([self.dit.time_text_embed(timesteps_bf16[b:b + 1], raw=True) for b in range(B)], dim=0)
-        mods = self.block_mods(temb)
+        temb_act = torch.empty_like(temb)
+        self.nat.tag = "gemv_mod"
+        self.nat.act(temb, temb_act, 1)
+        mods = self.block_mods(temb, temb_act=temb_act)
         no = self.dit.norm_out.linear
         out_mod = torch.empty(B, 2 * DIM, dtype=torch.bfloat16, device=self.device)
         self.nat.tag = "gemv_mod"
-        self.nat.gemv(temb, no.weight, no.bias, out_mod, 1, 0, self.mask2)
+        self.nat.gemv(temb_act, no.weight, no.bias, out_mod, 0, 0, self.mask2)
         return temb, mods, out_mod
 
     def precompute_conditioning(self, timesteps_bf16: torch.Tensor, keys: Sequence[float]) -> None:

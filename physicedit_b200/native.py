@@ -32,7 +32,7 @@ ATTN_FLAG_KV64 = 16
 EXPORTED_SYMBOLS = [
     "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count", "pe_workspace",
     "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
-    "pe_rmsnorm", "pe_gemv", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
+    "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
 ]
 
@@ -77,6 +77,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]
     lib.pe_add_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
     lib.pe_rmsnorm.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p]
+    lib.pe_act.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]
     lib.pe_gemv.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.pe_timestep_embedding.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     lib.pe_patchify.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
@@ -253,6 +254,14 @@ class Native:
         batch = 1 if x.dim() == 1 else x.shape[0]
         self._check(self.lib.pe_gemv(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1],
                                      act_in, act_out, _ptr(one_plus_mask), self._stream_prof()), "pe_gemv")
+        self.launches += 1
+
+    def act(self, x, y, act: int = 1) -> None:
+        """y = bf16(act(x)) element-wise (1 = SiLU)."""
+        _bf16(x, "x"); _bf16(y, "y")
+        if not (x.is_contiguous() and y.is_contiguous()) or x.numel() != y.numel():
+            raise NativeError("act: x / y must be contiguous and of equal size")
+        self._check(self.lib.pe_act(self.h, x.data_ptr(), y.data_ptr(), x.numel(), act, self._stream_prof()), "pe_act")
         self.launches += 1
 
     def timestep_embedding(self, t_in, out, raw: bool = True) -> None:

@@ -160,6 +160,36 @@ def test_rowwise_kernels_bit_exact_bookkeeping(nat, golden):
 
 
 @gpu
+def test_layernorm_modulate_tail_is_bit_exact(nat):
+    """LN + AdaLN modulate (qwen_image_dit.py:319-401 `_modulate`): the bf16 rounding points of `norm(x) * (1 + scale) + shift` are
+    replayed bit for bit.  The normalised tensor n is obtained from the kernel itself (1+scale = 1, shift = 0 is exact), then
+    bf16(bf16(n * ops) + shift) computed by ATen's bf16 ops must equal the kernel's fused output -- including huge / tiny / mixed-sign
+    modulation values that stress the packed bf16x2 multiply and add."""
+    torch.manual_seed(3)
+    rows, C, split = 333, 3072, 100
+    x = (torch.randn(rows, C, device="cuda") * 3 + 0.5).bfloat16()
+    one = torch.ones(C, device="cuda", dtype=torch.bfloat16)
+    zero = torch.zeros(C, device="cuda", dtype=torch.bfloat16)
+    n = torch.empty_like(x)
+    nat.layernorm_modulate2(x, n, split, zero, one, zero, one)
+    ref_n = torch.nn.functional.layer_norm(x.float(), (C,), eps=1e-6)
+    assert (n.float() - ref_n).abs().max().item() <= 2 ** -6          # bf16 rounding of values up to ~4
+    mags = torch.tensor([1e-3, 1.0, 37.0, 3e4], device="cuda")
+    for seed in range(3):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        ops = [(torch.randn(C, device="cuda", generator=g) * mags[torch.randint(0, 4, (C,), device="cuda", generator=g)]).bfloat16() for _ in range(2)]
+        sh = [(torch.randn(C, device="cuda", generator=g) * mags[torch.randint(0, 4, (C,), device="cuda", generator=g)]).bfloat16() for _ in range(2)]
+        out = torch.empty_like(x)
+        nat.layernorm_modulate2(x, out, split, sh[0], ops[0], sh[1], ops[1])
+        ref = torch.cat([n[:split] * ops[0] + sh[0], n[split:] * ops[1] + sh[1]], dim=0)      # ATen bf16 mul, then bf16 add
+        assert torch.equal(out, ref)
+        out1 = torch.empty_like(x[:split])
+        nat.layernorm_modulate(x[:split].contiguous(), out1, sh[0], ops[0])
+        assert torch.equal(out1, ref[:split])
+    nat.check_async()
+
+
+@gpu
 def test_scheduler_matches_golden(golden):
     from physicedit_b200.scheduler import FlowMatchScheduler
     g = golden("scheduler")

@@ -26,11 +26,12 @@ ms = timeit(ln)
 print(f"layernorm_modulate2 [8704x3072]: {ms*1e3:.1f} us  {2*S*D*2/ms/1e6:.0f} GB/s")
 w = [(torch.randn(18432, D, device=dev) / 55).bfloat16() for _ in range(3)]
 b = torch.zeros(18432, device=dev).bfloat16(); mask = torch.zeros(18432, dtype=torch.uint8, device=dev)
+ACT_IN = int(os.environ.get("GEMV_ACT_IN", "0"))     # the engine pre-applies SiLU once (pe_act) and passes 0
 for B in (1, 4, 8):
     t = torch.randn(B, D, device=dev).bfloat16(); y = torch.empty(B, 18432, device=dev, dtype=torch.bfloat16)
     def gv():
         i[0] = (i[0] + 1) % 3
-        nat.gemv(t, w[i[0]], b, y, 1, 0, mask)
+        nat.gemv(t, w[i[0]], b, y, ACT_IN, 0, mask)
     ms = timeit(gv)
     print(f"gemv batch {B} [18432x3072]: {ms*1e3:.1f} us  {18432*D*2/ms/1e6:.0f} GB/s")
 nat.check_async()
