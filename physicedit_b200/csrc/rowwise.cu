@@ -4,6 +4,7 @@
 // one warp owns one row (or one output feature for the GEMV) and keeps it in registers, so every
 // input byte is read exactly once.  bf16 rounding points follow the reference op by op
 //  so results are comparable with the reference's bf16 tensors.
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "common.cuh"
 
@@ -113,6 +114,99 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// LN + modulate at the DiT width (C = 3072), bulk-copy staged: a persistent CTA per SM, every warp streams its rows through a
+// private ring of shared-memory row buffers filled by cp.async.bulk (lane 0 issues the copy of row k+kLnSlots-1 before row k is
+// normalised), so ~100 KB of loads per SM are in flight all the time regardless of what the warps compute.  The register-only
+// version above issues its loads, then computes, then stores, and reached 0.48 of the HBM roofline inside the power-capped loop
+// (its speed followed the SM clock).  Arithmetic and rounding points are those of layernorm_kernel<12, 0>.
+// -------------------------------------------------------------------------------------------------
+constexpr int kLnC = 3072;
+constexpr int kLnWarps = 8;
+constexpr int kLnSlots = 3;
+constexpr int kLnRowBytes = kLnC * 2;
+constexpr int kLnSmem = kLnWarps * kLnSlots * kLnRowBytes + 4 * kLnRowBytes + kLnWarps * kLnSlots * 8 + 128;
+
+__global__ void __launch_bounds__(kLnWarps * 32, 1) layernorm_modulate_bulk_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int rows,
+                                                                                     const bf16* __restrict__ p0, const bf16* __restrict__ p1, float eps,
+                                                                                     int split_row, const bf16* __restrict__ q0, const bf16* __restrict__ q1,
+                                                                                     unsigned int* abort_flag) {
+    extern __shared__ uint8_t ln_smem_raw[];
+    const uint32_t base = (smem_u32(ln_smem_raw) + 127u) & ~127u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = base + warp * (kLnSlots * kLnRowBytes);
+    const uint32_t mods = base + kLnWarps * kLnSlots * kLnRowBytes;        // [shift0 | ops0 | shift1 | ops1], 6 KB each
+    const uint32_t bars = mods + 4 * kLnRowBytes + (warp * kLnSlots) * 8;
+    const uint8_t* gen = ln_smem_raw + (base - smem_u32(ln_smem_raw));      // generic pointer to `base`
+    // modulation vectors -> shared memory once per CTA (stream 1 falls back to stream 0 when there is no second stream)
+    {
+        const bf16* srcs[4] = {p0, p1, q0 ? q0 : p0, q1 ? q1 : p1};
+        uint4* dst = reinterpret_cast<uint4*>(const_cast<uint8_t*>(gen) + kLnWarps * kLnSlots * kLnRowBytes);
+        for (int i = threadIdx.x; i < 4 * (kLnRowBytes / 16); i += blockDim.x)
+            dst[i] = __ldg(reinterpret_cast<const uint4*>(srcs[i / (kLnRowBytes / 16)]) + i % (kLnRowBytes / 16));
+    }
+    if (lane == 0)
+        for (int s = 0; s < kLnSlots; ++s) mbar_init(bars + s * 8, 1);
+    fence_mbar_init();
+    __syncthreads();
+    const int stride = gridDim.x * kLnWarps;
+    const int first = blockIdx.x * kLnWarps + warp;
+    auto issue = [&](int k) {                       // k-th row of this warp -> slot k % kLnSlots
+        const long long row = first + (long long)k * stride;
+        if (row < rows && lane == 0) {
+            const uint32_t bar = bars + (k % kLnSlots) * 8;
+            fence_proxy_async_smem();               // the slot's previous contents were read through the generic proxy
+            mbar_arrive_expect_tx(bar, kLnRowBytes);
+            bulk_load_1d(ring + (k % kLnSlots) * kLnRowBytes, x + row * kLnC, kLnRowBytes, bar);
+        }
+    };
+    for (int k = 0; k < kLnSlots - 1; ++k) issue(k);
+    for (int k = 0;; ++k) {
+        const long long row = first + (long long)k * stride;
+        if (row >= rows) break;
+        issue(k + kLnSlots - 1);                    // its slot was released (read into registers) in iteration k - 1
+        const int slot = k % kLnSlots;
+        if (!mbar_wait(bars + slot * 8, (k / kLnSlots) & 1, abort_flag, 100)) break;       // bounded like every wait in this library
+        const uint4* xr = reinterpret_cast<const uint4*>(gen + (size_t)warp * (kLnSlots * kLnRowBytes) + slot * kLnRowBytes);
+        float v[12][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            unpack8(xr[lane + 32 * i], v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[i][j];
+        }
+        // every lane has its part of the row in registers: the slot may be overwritten by the bulk copy issued in the next iteration
+        __syncwarp();
+        const float mean = warp_sum(sum) / (float)kLnC;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+        const float rstd = rsqrtf(warp_sum(ss) / (float)kLnC + eps);
+        const int st = row >= split_row ? 2 : 0;
+        const uint4* shift = reinterpret_cast<const uint4*>(gen + kLnWarps * kLnSlots * kLnRowBytes + st * kLnRowBytes);
+        const uint4* ops = shift + kLnRowBytes / 16;
+        uint4* orow = reinterpret_cast<uint4*>(out + row * kLnC);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int vi = lane + 32 * i;
+            const uint4 a4 = ops[vi], b4 = shift[vi];
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 n2 = __floats2bfloat162_rn((v[i][2 * j] - mean) * rstd, (v[i][2 * j + 1] - mean) * rstd);
+                const __nv_bfloat162 t2 = __hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+                const __nv_bfloat162 o2 = __hadd2_rn(t2, *reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+                ow[j] = *reinterpret_cast<const uint32_t*>(&o2);
+            }
+            orow[vi] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+    }
+}
+
 template <int MODE>
 int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const void* p0, const void* p1, float eps, cudaStream_t s,
                      int split_row = 0x7fffffff, const void* r0 = nullptr, const void* r1 = nullptr) {
@@ -125,6 +219,19 @@ int launch_layernorm(Handle* h, const void* x, void* out, int rows, int C, const
     const bf16* b = static_cast<const bf16*>(p1);
     const bf16* q0 = static_cast<const bf16*>(r0);
     const bf16* q1 = static_cast<const bf16*>(r1);
+    static const bool register_only = getenv("PE_LN_REGISTER_ONLY") != nullptr;      // A/B switch for the two LN + modulate kernels
+    if (MODE == 0 && C == kLnC && rows >= 4 * kLnWarps && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !register_only) {
+        static bool configured = false;
+        if (!configured) {
+            PE_CHECK_CUDA(h, cudaFuncSetAttribute(layernorm_modulate_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
+            configured = true;
+        }
+        int ctas = ceil_div(rows, kLnWarps);
+        if (ctas > h->sm_count) ctas = h->sm_count;
+        layernorm_modulate_bulk_kernel<<<ctas, kLnWarps * 32, kLnSmem, s>>>(xb, ob, rows, a, b, eps, split_row, q0, q1, h->abort_flag);
+        PE_CHECK_CUDA(h, cudaGetLastError());
+        return PE_OK;
+    }
     if (C <= 256) layernorm_kernel<1, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
     else if (C <= 1024) layernorm_kernel<4, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
     else if (C <= 3072) layernorm_kernel<12, MODE><<<grid, block, 0, s>>>(xb, ob, rows, C, a, b, eps, split_row, q0, q1);
