@@ -67,7 +67,14 @@ class ClockSampler:
 
 
 def ncu_traffic_bytes(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures (profiles/r01_ncu_full_metrics.json for
+    the attention and the MLP up-projection with a flushed L2, profiles/r01_gemm_traffic.json for the other GEMM shapes)."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get(kernel_substr)
+        if g:
+            return int((g["dram_read_MB"] + g["dram_write_MB"]) * 1e6)
+    except (OSError, KeyError, ValueError):
+        pass
     try:
         for row in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_metrics.json"))):
             if kernel_substr in row["kernel"]:
@@ -273,11 +280,11 @@ def run_native(args):
         "gemm_up": ("gemm_kernel<cta_pair, bias+gelu> (MLP up-projection, M=S N=12288 K=3072)", "tensor", 2 * S_avg * DIM * 4 * DIM,
                     2 * (S_avg * DIM + 4 * DIM * DIM + S_avg * 4 * DIM), "gemm_kernel<2, 2>"),
         "gemm_down": ("gemm_kernel<cta_pair, gate-residual> (MLP down-projection, M=S N=3072 K=12288)", "tensor", 2 * S_avg * DIM * 4 * DIM,
-                      2 * (S_avg * 4 * DIM + 4 * DIM * DIM + 2 * S_avg * DIM), None),
+                      2 * (S_avg * 4 * DIM + 4 * DIM * DIM + 2 * S_avg * DIM), "gemm_down"),
         "gemm_qkv": ("gemm_kernel<cta_pair, qkv norm+rope> (fused QKV projection, M=S N=9216 K=3072)", "tensor", 2 * S_avg * DIM * 3 * DIM,
                      2 * (S_avg * DIM + 3 * DIM * DIM + 3 * S_avg * DIM), None),
         "gemm_out": ("gemm_kernel<cta_pair, gate-residual> (attention out-projection, M=S N=3072 K=3072)", "tensor", 2 * S_avg * DIM * DIM,
-                     2 * (S_avg * DIM + DIM * DIM + 2 * S_avg * DIM), None),
+                     2 * (S_avg * DIM + DIM * DIM + 2 * S_avg * DIM), "gemm_out"),
         "ln_mod": ("layernorm_modulate2 (LN + AdaLN scale/shift, both streams)", "hbm", None, 2 * S_avg * DIM * 2, None),
     }
     roofs = {}
@@ -292,7 +299,7 @@ def run_native(args):
             ach, pk, unit, src = by / avg_s / 1e9, peak_gbs, "GB/s", "MEASURED_PEAKS.json hbm_gbs"
         roofs[tag] = {"bound": bound, "kernel": desc, "achieved": round(ach, 1), "peak": pk, "peak_source": src if peaks else "fallback", "unit": unit,
                       "frac": round(ach / pk, 4), "traffic": ncu_traffic_bytes(ncu_name) if ncu_name else None,
-                      "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_full_metrics.json)", "algorithmic_bytes": int(by),
+                      "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_full_metrics.json / r01_gemm_traffic.json)", "algorithmic_bytes": int(by),
                       "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms_attr, 4)}
     roof = None
     if roofs:

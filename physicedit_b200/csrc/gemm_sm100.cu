@@ -30,7 +30,7 @@ constexpr int kUmmaK = 16;
 constexpr int kTileN = 256;
 constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
-constexpr int kGroupM = 16;        // rasterisation: 16 m-tiles share a sweep over n (A panel <= 25 MB stays in the 126 MB L2)
+constexpr int kPanelBytes = 32 << 20;   // rasterisation: the m-tiles of a group share a sweep over n; their A panel (<= 32 MB) stays in the 126 MB L2
 
 struct SegDev {
     CUtensorMap tmA;
@@ -55,6 +55,7 @@ struct GemmParams {
     int K;
     int num_n;
     int total_m_tiles;
+    int group_m;           // m-tiles per rasterisation group (balanced: ceil(total / number of groups))
     int num_tiles;
     int num_kb;
     int heads;             // QKV epilogue: N = 3 * heads * 128
@@ -75,10 +76,10 @@ struct Tile {
 
 template <int kTileM>
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
-    const int group_size = kGroupM * p.num_n;
+    const int group_size = p.group_m * p.num_n;
     const int g = t / group_size;
-    const int first_m = g * kGroupM;
-    const int gm = min(kGroupM, p.total_m_tiles - first_m);
+    const int first_m = g * p.group_m;
+    const int gm = min(p.group_m, p.total_m_tiles - first_m);
     const int in_group = t - g * group_size;
     int mt = first_m + in_group % gm;
     const int nt = in_group / gm;
@@ -480,6 +481,18 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
                        "pe_gemm: QKV epilogue needs bias, out_k, out_v, norm weights and rope table");
     }
     p.total_m_tiles = total_m_tiles;
+    {
+        // as many m-tiles per group as keep the group's A panel within kPanelBytes, spread evenly (r1: a fixed 16 left a last group of
+        // 2 m-tiles that re-streamed the whole weight matrix, and at K = 12288 a 100 MB panel that did not fit the L2 next to W)
+        const long long tile_row_bytes = (long long)tile_m * K * 2;
+        int gm_max = (int)(kPanelBytes / tile_row_bytes);
+        if (gm_max < 1) gm_max = 1;
+        const int groups = ceil_div(total_m_tiles, gm_max);
+        p.group_m = ceil_div(total_m_tiles, groups);
+#ifdef PE_GEMM_GROUP_M
+        p.group_m = PE_GEMM_GROUP_M;      // experiments: fixed group size
+#endif
+    }
     p.num_tiles = total_m_tiles * p.num_n;
     if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
     return dispatch_epilogue<2>(h, p, epilogue, stream);
