@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
             }
             umma_commit(s_full(q));
         };
-        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate) {
+        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate, bool last) {
             // O_q (+)= P_q V : 8 k-steps of 16 kv rows; V rows are 128 B apart, 16 rows = 2 KB
             const uint32_t vlo = desc_lo_v(v_base);
 #pragma unroll
@@ -384,7 +384,9 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
                     umma_ss_lohi_acc(o_tmem(q), desc_lo_k(p_smem(q)) + off16, vlo + kk * (2048 >> 4), idesc_o, acc);
                 }
             }
-            umma_commit(pv_done(q));
+            // only the item's last PV is ever waited for (by the epilogue): one commit per item keeps every phase of the barrier
+            // observed by its waiter (compute-sanitizer synccheck flags arrivals on phases nobody waits for)
+            if (last) umma_commit(pv_done(q));
         };
 
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
                     tc_fence_after();
                     PE_TRACE(12 + q, j);
                     if (leader) {
-                        issue_pv(q, kv_smem(v_slot), j > 0);
+                        issue_pv(q, kv_smem(v_slot), j > 0, !more);
                         if (more) issue_s(q, kv_smem(k_slot));
                         if (q == kQT - 1) {
                             umma_commit(kv_empty(v_slot));
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
         const uint32_t s_addr = s_tmem(q) + lane_off;
         const uint32_t o_addr = o_tmem(q) + lane_off;
         const int row_in_tile = wq * 32 + lane;
-        uint32_t s_phase = 0, pv_commits = 0;
+        uint32_t s_phase = 0, item_par = 0;
         bool ok = true;
         PE_TRACE_DECL(1 + q)
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
@@ -548,8 +550,8 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
             if (!ok) break;
 
             // ---- epilogue: O / l -> bf16 -> global ----
-            pv_commits += (uint32_t)p.n_kv;                     // the MMA issuer commits pv_done once per KV step
-            if (!mbar_wait(pv_done(q), (pv_commits - 1u) & 1u, p.abort_flag, 32)) break;
+            if (!mbar_wait(pv_done(q), item_par, p.abort_flag, 32)) break;     // committed once per item, after its last PV
+            item_par ^= 1u;
             tc_fence_after();
             const float inv = f_pending / l;     // includes the O rescale still pending from the last step
             const long long row = (long long)(qb * kQT + q) * kTile + row_in_tile;
@@ -751,7 +753,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_
             }
             __syncwarp();
         };
-        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate) {
+        auto issue_pv = [&](int q, uint32_t v_base, bool accumulate, bool last) {
             if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_
                     const uint32_t a_tmem = s_tmem(q) + (kk >> 2) * 64 + (kk & 3) * 8;
                     umma_bf16_ts(o_tmem(q), a_tmem, bdesc, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
                 }
-                umma_commit(pv_done(q));
+                if (last) umma_commit(pv_done(q));       // once per item (see attention_kernel)
             }
             __syncwarp();
         };
@@ -797,7 +799,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_
                     p_phase[q] ^= 1u;
                     tc_fence_after();
                     PE_TRACE(12 + q, j);
-                    issue_pv(q, kv_smem(v_slot), j > 0);
+                    issue_pv(q, kv_smem(v_slot), j > 0, !more);
                     if (more) issue_s(q, kv_smem(k_slot));
                     PE_TRACE(14 + q, j);
                 }
@@ -824,7 +826,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_
         auto mx_slot = [&](int slot, int hf) { return exch_base + (((slot * 2 + q) * 2 + hf) * 128 + row_in_tile) * 4; };
         const uint32_t l_own = lsum_base + ((q * 2 + half) * 128 + row_in_tile) * 4;
         const uint32_t l_other = lsum_base + ((q * 2 + (half ^ 1)) * 128 + row_in_tile) * 4;
-        uint32_t s_phase = 0, pv_commits = 0;
+        uint32_t s_phase = 0, item_par = 0;
         bool ok = true;
         const bool tr = (wq == 0 && half == 0);
         PE_TRACE_DECL(1 + q)
@@ -953,8 +955,8 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel2(const __grid_
             }
             if (!ok) break;
             // ---- epilogue: O / l -> bf16 -> global (own 64 columns of the head) ----
-            pv_commits += (uint32_t)p.n_kv;
-            if (!mbar_wait(pv_done(q), (pv_commits - 1u) & 1u, p.abort_flag, 62)) break;
+            if (!mbar_wait(pv_done(q), item_par, p.abort_flag, 62)) break;
+            item_par ^= 1u;
             tc_fence_after();
             st_shared_f32(l_own, l);
             named_bar_sync(pair_bar, 64);
