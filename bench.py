@@ -159,14 +159,20 @@ def run_native(args):
     eng.use_cta_pair = not args.no_cta_pair
     eng.attn_flags = args.attn_flags
     pipe.cfg_streams = args.cfg_streams
-    host = host_inputs(H, W, seed=100 + rank)             # a different image per rank
+    n_images = world
+    if args.cfg_parallel:
+        # latency mode: one image per PAIR of GPUs, the two CFG branches of a step on the two ranks of the pair
+        grp, pair, n_images = parallel.make_cfg_pairs()
+        pipe.cfg_parallel_group = grp
+    host = host_inputs(H, W, seed=100 + (rank // 2 if args.cfg_parallel else rank))             # a different image per rank (or per pair)
     dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
     ip = dict(prompt_emb=dev["pe_posi"], prompt_emb_mask=dev["mask_posi"], special_token_mask=dev["sp_posi"])
     in_ = dict(prompt_emb=dev["pe_nega"], prompt_emb_mask=dev["mask_nega"], special_token_mask=dev["sp_nega"])
     sched = pipe.scheduler
     sched.set_timesteps(50, dynamic_shift_len=(H // 16) * (W // 16))
     ts_dev = sched.timesteps.to(torch.bfloat16).to(device)
-    vp, vn = torch.empty_like(dev["latents"]), torch.empty_like(dev["latents"])
+    vbuf = torch.empty((2,) + tuple(dev["latents"].shape), dtype=dev["latents"].dtype, device=device)
+    vp, vn = vbuf[0], vbuf[1]
     lat = dev["latents"].clone()
 
     def one_step(i, latents):
@@ -194,7 +200,7 @@ def run_native(args):
     # Per-launch CUDA events are taken in the timed region itself when the branches run on one stream.  With two streams the launches
     # of the two branches overlap on the GPU and a per-launch duration is ambiguous, so the attribution (roofline, kernel shares) then
     # comes from `attr_steps` extra single-stream steps run right after the timed region (same process, same clocks, same inputs).
-    events_in_region = not args.no_kernel_events and args.cfg_streams == 1
+    events_in_region = not args.no_kernel_events and (args.cfg_streams == 1 or args.cfg_parallel)
     nat.prof = {} if events_in_region else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,17 +313,18 @@ def run_native(args):
         roof["whole_step_frac"] = round(fl_step * args.steps / (ms * 1e-3) / 1e12 / peak_tf, 4)
     shares = {k: round(v[1] / ms_attr, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     res = {
-        "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(world * args.steps / (ms * 1e-3), 4), "unit": "steps/s",
+        "metric": "denoise steps/sec (1024x1024 edit, CFG: 2 DiT forwards/step)", "value": round(n_images * args.steps / (ms * 1e-3), 4), "unit": "steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights of the real architecture, seeded inputs)",
         "config": {"workload": f"{H}x{W} single-image edit, 50-step schedule, bf16, {args.layers} blocks, 4096 edit tokens, T=512/288, one image per GPU",
-                   "l2": "inputs larger than L2: 40.8 GB of weights stream per forward", "images_per_sec_50_steps": round(world * args.steps / (ms * 1e-3) / 50, 5),
+                   "l2": "inputs larger than L2: 40.8 GB of weights stream per forward", "images_per_sec_50_steps": round(n_images * args.steps / (ms * 1e-3) / 50, 5),
+                   "cfg_parallel": bool(args.cfg_parallel),
                    "cfg_streams": args.cfg_streams,
                    "attribution": ("per-launch CUDA events over the timed region" if events_in_region else
                                    f"per-launch CUDA events over {attr_steps} extra single-stream steps right after the timed region "
                                    f"({round(ms_attr / attr_steps, 2)} ms/step; with two streams the branches' launches overlap)"),
                    "tflops_per_step": round(fl_step / 1e12, 2), "achieved_tflops_per_gpu": round(fl_step * args.steps / (ms * 1e-3) / 1e12, 1)},
-        "e2e": {"value": round(world * e2e_steps / (ms_e2e * 1e-3), 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": round(n_images * e2e_steps / (ms_e2e * 1e-3), 4), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": launches, "finite": finite, "clocks": clocks, "roofline": roof, "roofline_by_kernel": roofs, "kernel_time_share": shares,
     }
@@ -390,6 +397,8 @@ def main():
     ap.add_argument("--attn-flags", dest="attn_flags", type=int, default=0, help="PE_ATTN_FLAG_* bits (8 = split-row softmax kernel)")
     ap.add_argument("--cfg-streams", dest="cfg_streams", type=int, default=2, choices=[1, 2],
                     help="2 = the two CFG branches of a step run concurrently on two CUDA streams (fills partial last waves)")
+    ap.add_argument("--cfg-parallel", dest="cfg_parallel", action="store_true",
+                    help="latency mode: one image per pair of GPUs (positive branch on the even rank, negative on the odd one); needs an even --gpus")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=8, help="cap on timed CPU samples of --impl reference")

@@ -110,6 +110,8 @@ def load_dit(path, torch_dtype=torch.bfloat16, device="cuda") -> Optional[QwenIm
 
 
 class QwenImagePhysicPipeline(nn.Module):
+    # Set to a 2-rank torch.distributed group (parallel.make_cfg_pairs) to split the two CFG branches of ONE image over two GPUs.
+    cfg_parallel_group = None
     # 2: the two CFG branches of a denoise step run concurrently on two CUDA streams (see run_cfg_branches); 1: back to back.
     # Bit-identical results either way; two streams measured +3 % steps/s at 1024^2 (r1, power-capped B200).
     cfg_streams = 2
@@ -216,8 +218,8 @@ class QwenImagePhysicPipeline(nn.Module):
         ts = self.scheduler.timesteps
         ts_dev = ts.to(dtype=self.torch_dtype).to(latents.device) if timesteps_device is None else timesteps_device   # one H2D for the whole table
         latents = latents.clone()
-        vp = torch.empty_like(latents)
-        vn = torch.empty_like(latents)
+        vbuf = torch.empty((2,) + tuple(latents.shape), dtype=latents.dtype, device=latents.device)     # [posi | nega], one buffer: the
+        vp, vn = vbuf[0], vbuf[1]                                                                         # CFG-parallel all-gather runs in place
         # timestep-only quantities for the whole schedule, batch-8 GEMVs (see DiTEngine.precompute_conditioning)
         self.dit.engine().precompute_conditioning(ts_dev, [float(t.to(self.torch_dtype)) for t in ts])
         it = enumerate(ts)
@@ -240,6 +242,17 @@ class QwenImagePhysicPipeline(nn.Module):
         persistent grid of one CTA (pair) per SM whose last wave is partial (816 attention items or 408 out-projection tiles on
         148 SMs = 5.51 waves), and with a second stream the other branch's CTAs take the SMs a finishing kernel releases.
         Results are unchanged: same kernels, same inputs, separate workspaces (cfg_branch)."""
+        grp = getattr(self, "cfg_parallel_group", None)
+        if inputs_nega is not None and grp is not None:
+            # Latency mode (SURVEY 8f4): ONE image on a pair of GPUs.  Rank 0 of the pair runs the positive branch, rank 1 the
+            # negative one (each keeps mutating only its own prompt_emb, as the reference does per branch), then the two
+            # [1,16,h8,w8] predictions (512 KiB at 1024^2) are exchanged with one all-gather over NVLink and both ranks apply the
+            # same CFG + Euler update, so their latents stay bit-identical without any further traffic.
+            from . import parallel
+            r = parallel.dist.get_rank(grp)
+            self.model_fn(**kw, **(inputs_posi if r == 0 else inputs_nega), out=vp if r == 0 else vn)
+            parallel.exchange_cfg_predictions(vp, vn, r, grp)
+            return
         if inputs_nega is not None and getattr(self, "cfg_streams", 1) == 2:
             dev = vp.device
             main = torch.cuda.current_stream(dev)
@@ -266,9 +279,9 @@ class QwenImagePhysicPipeline(nn.Module):
         t = self.scheduler.timesteps[progress_id]
         t_host = float(t.to(self.torch_dtype))
         t_dev = t.to(self.torch_dtype).reshape(1).to(latents.device, non_blocking=True)
-        if not hasattr(self, "_vbuf") or self._vbuf[0].shape != latents.shape or self._vbuf[0].device != latents.device:
-            self._vbuf = (torch.empty_like(latents), torch.empty_like(latents))
-        vp, vn = self._vbuf
+        if not hasattr(self, "_vbuf") or self._vbuf.shape[1:] != latents.shape or self._vbuf.device != latents.device:
+            self._vbuf = torch.empty((2,) + tuple(latents.shape), dtype=latents.dtype, device=latents.device)
+        vp, vn = self._vbuf[0], self._vbuf[1]
         kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=t_dev, height=height, width=width,
                   edit_latents=edit_latents, context_latents=context_latents, is_train=False, progress_id=progress_id, timestep_host=t_host)
         self.run_cfg_branches(kw, inputs_posi, inputs_nega if cfg_scale != 1.0 else None, vp, vn, t_dev, t_host)

@@ -165,3 +165,43 @@ def test_c_abi_rejects_null_handle_without_a_gpu():
     if not torch.cuda.is_available():
         assert lib.pe_create(ctypes.byref(out), 0) == -3             # PE_ERR_UNSUPPORTED_DEVICE: no sm_100 device, no fallback
         assert out.value is None
+
+
+def _cfg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from physicedit_b200.pipeline import QwenImagePhysicPipeline
+        grp, pair, npairs = parallel.make_cfg_pairs()
+        calls = []
+
+        class Fake:                                      # stands in for the pipeline: only run_cfg_branches' host logic is under test
+            cfg_parallel_group = grp
+            cfg_streams = 2
+
+            def model_fn(self, out=None, tag=None, **kw):
+                calls.append(tag)
+                out.fill_(1.0 if tag == "posi" else -2.0)
+
+        vbuf = torch.zeros(2, 1, 16, 4, 4)
+        QwenImagePhysicPipeline.run_cfg_branches(Fake(), {}, {"tag": "posi"}, {"tag": "nega"}, vbuf[0], vbuf[1], None, 0.0)
+        q.put((rank, pair, npairs, calls, float(vbuf[0].mean()), float(vbuf[1].mean())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_parallel_pair_runs_one_branch_per_rank_and_exchanges():
+    """SURVEY 8f4 host logic on CPU (gloo, world 2): rank 0 runs only the positive branch, rank 1 only the negative one, and after the
+    exchange both ranks hold both predictions."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == (0, 0, 1, ["posi"], 1.0, -2.0)
+    assert res[1] == (1, 0, 1, ["nega"], 1.0, -2.0)
