@@ -75,7 +75,8 @@ typedef enum pe_epilogue {
     PE_EPI_GATE_RESIDUAL = 4,  /* o=bf16(acc+bias); out = residual + gate[n]*o  (in place on out) */
     PE_EPI_QKV_NORM_ROPE = 5,  /* N = 3*H*128: per-head RMSNorm(q,k)*w, RoPE(q,k), v passthrough;
                                   writes q/k/v into three [M, H*128] buffers                      */
-    PE_EPI_BIAS_SILU = 6       /* out = silu(bf16(acc + bias))   (timestep MLP)                   */
+    PE_EPI_BIAS_SILU = 6,      /* out = silu(bf16(acc + bias))   (timestep MLP)                   */
+    PE_EPI_F32 = 7             /* out = acc as float [M, ldo] (ldo in floats; no bias): attention scores of the VAE mid block */
 } pe_epilogue;
 
 /* One segment (= token stream with its own weights) of a grouped GEMM. */
@@ -97,6 +98,7 @@ typedef struct pe_gemm_seg {
 } pe_gemm_seg;
 
 #define PE_GEMM_FLAG_CTA_PAIR 1   /* use cta_group::2 (256-row tiles on an SM pair) */
+#define PE_GEMM_FLAG_TRIM_N   2   /* narrow outputs (N % 256 != 0): issue the last n-tile's MMAs with N = round_up(N - n0, 16) */
 
 int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, void* stream);
 
@@ -184,6 +186,58 @@ int pe_special_gather(pe_handle_t h, const void* prompt_emb, const uint8_t* mask
 int pe_special_blend_scatter(pe_handle_t h, void* prompt_emb, const int32_t* idx, int max_rows, int C,
                              const void* pred_dino, const void* pred_vae, const void* t_in,
                              float t_min, float t_max, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* QwenImageVAE encode / decode (DiffSynth-Studio/diffsynth/models/qwen_image_vae.py; called at  */
+/* pipelines/qwen_image_physical.py:665,1273,1298,1092,1106).  Activation maps are channels-last */
+/* bf16 [H*W, C] (pixel stride ld elements).  At T = 1 without a feature cache every             */
+/* QwenImageCausalConv3d (:8-51) is a 2-D convolution with the last temporal slice of its kernel.*/
+/* ------------------------------------------------------------------------------------------- */
+/* Implicit-GEMM convolution on the tensor cores (same kernel as pe_gemm; the A operand is read tap by tap
+ * from the activation map through a 3-D TMA tensor map, zero padding = TMA out-of-bounds fill, no im2col):
+ *   out[y,x,n] = epi( sum_{dy<kh, dx<kw, c<C} x[y+dy-pad, x+dx-pad, c] * w[n, (dy*kw+dx)*cpad + c] + bias[n] ),
+ *   cpad = round_up(C, 64), stride 1, output H x W = input H x W.
+ * Replaces F.conv3d / F.conv2d at qwen_image_vae.py:51 (conv1/conv2/conv_in/conv_out), :243 (upsample conv) and, after
+ * pe_space_to_depth with a 2x2 kernel and pad 0, the stride-2 downsample conv :247-249.
+ * epilogue: PE_EPI_BIAS | PE_EPI_BIAS_SILU | PE_EPI_GATE_RESIDUAL (out += gate[n] * bf16(acc+bias), in place; gate = ones
+ * gives the residual add of QwenImageResidualBlock.forward :152). */
+typedef struct pe_conv2d_desc {
+    const void* x;      /* bf16 [H, W, >=C], pixel stride ldx elements                      */
+    int64_t ldx;
+    const void* w;      /* bf16 [N, kh*kw*cpad] contiguous, tap-major then channel          */
+    const void* bias;   /* bf16 [N] or NULL                                                  */
+    void* out;          /* bf16 [H*W, >=N], pixel stride ldo elements                        */
+    int64_t ldo;
+    const void* gate;   /* PE_EPI_GATE_RESIDUAL: bf16 [N]                                    */
+    int32_t H, W, C, N;
+    int32_t kh, kw, pad;
+    int32_t _pad0;
+} pe_conv2d_desc;
+int pe_conv2d(pe_handle_t h, const pe_conv2d_desc* desc, int epilogue, void* stream);
+
+/* QwenImageRMS_norm (:76-78) over the channels of every pixel, optionally followed by nn.SiLU:
+ *   n = max(bf16(||x||_2), 1e-12); y = bf16(bf16(bf16(x / n) * sqrt(C)) * gamma[c]); act != 0: y = bf16(silu(y)). */
+int pe_channel_rmsnorm(pe_handle_t h, const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int C,
+                       const void* gamma, int act, void* stream);
+/* QwenImageUpsample (:202-215, nearest-exact, scale 2): in [H, W, C] -> out [2H, 2W, C], both contiguous. */
+int pe_upsample2x(pe_handle_t h, const void* in, void* out, int H, int W, int C, void* stream);
+/* in [H, W, C] -> out [H/2, W/2, 4C], out[y,x,(py*2+px)*C+c] = in[2y+py, 2x+px, c]: with it the ZeroPad2d((0,1,0,1)) + 3x3 stride-2
+ * convolution of the downsample layers (:246-249) becomes a 2x2 stride-1 pe_conv2d with pad 0. */
+int pe_space_to_depth(pe_handle_t h, const void* in, void* out, int H, int W, int C, void* stream);
+/* layout changes at the ends of the VAE with the latent (de)normalisation folded in:
+ *   op 0 copy; op 1 y = bf16(bf16(x / p1[c]) + p0[c]) (decode :724-725, p0 = mean, p1 = 1/std);
+ *   op 2 y = bf16(bf16(x - p0[c]) * p1[c]) (encode :712-714).  p0, p1: bf16 [C]. */
+int pe_nchw_to_nhwc(pe_handle_t h, const void* src, void* dst, int64_t ldd, int C, int64_t HW, int op,
+                    const void* p0, const void* p1, void* stream);
+int pe_nhwc_to_nchw(pe_handle_t h, const void* src, int64_t lds, void* dst, int C, int64_t HW, int op,
+                    const void* p0, const void* p1, void* stream);
+/* bf16 [R, C] (row stride lds) -> [C, R] (row stride ldd): V^T for the P.V product of the mid-block attention. */
+int pe_transpose(pe_handle_t h, const void* src, int64_t lds, void* dst, int64_t ldd, int R, int C, void* stream);
+/* probs[r, 0:n] = bf16(softmax(scale * scores[r, 0:n])), probs[r, n:n_pad] = 0; scores float [rows, lds]
+ * (F.scaled_dot_product_attention of QwenImageAttentionBlock :189, single head of dim 384; the zero columns let the
+ * P.V product run with its K dimension padded to a multiple of 8). */
+int pe_softmax_rows(pe_handle_t h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad,
+                    float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,24 @@ int make_tmap_2d(Handle* h, CUtensorMap* out, const void* base, uint64_t rows, u
     return PE_OK;
 }
 
+int make_tmap_3d(Handle* h, CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t ld_w, uint64_t ld_h,
+                 uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+    if (h->encode_tiled == nullptr) return set_error(h, PE_ERR_NOT_INITIALIZED, "cuTensorMapEncodeTiled not resolved");
+    cuuint64_t dims[3] = {C, W, H};
+    cuuint64_t strides[2] = {ld_w * sizeof(bf16), ld_h * sizeof(bf16)};
+    cuuint32_t box[3] = {box_c, box_w, box_h};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+        out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(h, PE_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): base=%p C=%llu W=%llu H=%llu ld_w=%llu box=%ux%ux%u",
+                         (int)r, base, (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)ld_w,
+                         box_c, box_w, box_h);
+    return PE_OK;
+}
+
 // launchers implemented in the kernel translation units
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream);
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
@@ -60,6 +78,15 @@ int small_attention_run(Handle* h, const void* q, const void* k, const void* v, 
                         int64_t ldq, int64_t ldkv, int64_t ldo, float scale, cudaStream_t s);
 int layernorm_affine_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, const void* b, float eps, cudaStream_t s);
 int add_bias_rows_run(Handle* h, void* x, const void* add, int rows, int C, int period, float alpha, cudaStream_t s);
+int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t stream);
+int channel_rmsnorm_run(Handle* h, const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int C, const void* gamma, int act,
+                        cudaStream_t s);
+int upsample2x_run(Handle* h, const void* in, void* out, int H, int W, int C, cudaStream_t s);
+int space_to_depth_run(Handle* h, const void* in, void* out, int H, int W, int C, cudaStream_t s);
+int nchw_to_nhwc_run(Handle* h, const void* src, void* dst, int64_t ldd, int C, int64_t HW, int op, const void* p0, const void* p1, cudaStream_t s);
+int nhwc_to_nchw_run(Handle* h, const void* src, int64_t lds, void* dst, int C, int64_t HW, int op, const void* p0, const void* p1, cudaStream_t s);
+int transpose_run(Handle* h, const void* src, int64_t lds, void* dst, int64_t ldd, int R, int C, cudaStream_t s);
+int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s);
 
 }  // namespace pe
 
@@ -236,6 +263,51 @@ int pe_special_blend_scatter(pe_handle_t hh, void* prompt_emb, const int32_t* id
     PE_H(hh);
     return pe::special_blend_scatter_run(h, prompt_emb, idx, max_rows, C, pred_dino, pred_vae, t_in, t_min, t_max,
                                          static_cast<cudaStream_t>(stream));
+}
+
+int pe_conv2d(pe_handle_t hh, const pe_conv2d_desc* desc, int epilogue, void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, desc != nullptr, "pe_conv2d: desc is null");
+    return pe::conv2d_run(h, desc, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int pe_channel_rmsnorm(pe_handle_t hh, const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int C, const void* gamma, int act,
+                       void* stream) {
+    PE_H(hh);
+    return pe::channel_rmsnorm_run(h, x, ldx, out, ldo, rows, C, gamma, act, static_cast<cudaStream_t>(stream));
+}
+
+int pe_upsample2x(pe_handle_t hh, const void* in, void* out, int H, int W, int C, void* stream) {
+    PE_H(hh);
+    return pe::upsample2x_run(h, in, out, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+int pe_space_to_depth(pe_handle_t hh, const void* in, void* out, int H, int W, int C, void* stream) {
+    PE_H(hh);
+    return pe::space_to_depth_run(h, in, out, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+int pe_nchw_to_nhwc(pe_handle_t hh, const void* src, void* dst, int64_t ldd, int C, int64_t HW, int op, const void* p0, const void* p1,
+                    void* stream) {
+    PE_H(hh);
+    return pe::nchw_to_nhwc_run(h, src, dst, ldd, C, HW, op, p0, p1, static_cast<cudaStream_t>(stream));
+}
+
+int pe_nhwc_to_nchw(pe_handle_t hh, const void* src, int64_t lds, void* dst, int C, int64_t HW, int op, const void* p0, const void* p1,
+                    void* stream) {
+    PE_H(hh);
+    return pe::nhwc_to_nchw_run(h, src, lds, dst, C, HW, op, p0, p1, static_cast<cudaStream_t>(stream));
+}
+
+int pe_transpose(pe_handle_t hh, const void* src, int64_t lds, void* dst, int64_t ldd, int R, int C, void* stream) {
+    PE_H(hh);
+    return pe::transpose_run(h, src, lds, dst, ldd, R, C, static_cast<cudaStream_t>(stream));
+}
+
+int pe_softmax_rows(pe_handle_t hh, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale,
+                    void* stream) {
+    PE_H(hh);
+    return pe::softmax_rows_run(h, scores, lds, probs, ldp, rows, n, n_pad, scale, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -44,6 +44,11 @@ int set_error(Handle* h, int code, const char* fmt, ...);
 int make_tmap_2d(Handle* h, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols = 64);
 
+// 3-D bf16 tensor map over an NHWC activation map: dims (C, W, H), `ld_w` / `ld_h` elements between pixels / rows,
+// box = box_c x box_w x box_h, 128-byte swizzle (box_c = 64), out-of-bounds elements read as zero.
+int make_tmap_3d(Handle* h, CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t ld_w, uint64_t ld_h,
+                 uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace pe

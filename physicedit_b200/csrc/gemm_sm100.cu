@@ -59,8 +59,27 @@ struct GemmParams {
     int num_tiles;
     int num_kb;
     int heads;             // QKV epilogue: N = 3 * heads * 128
+    // implicit-GEMM convolution (pe_conv2d): segment 0's A operand is an activation map [H, W, C] read through a 3-D tensor map;
+    // an m-tile is a (128 >> tile_w_log2) x (1 << tile_w_log2) patch of output pixels, the K loop runs over (tap, 64-channel block)
+    int conv;              // 0: plain GEMM
+    int conv_kw;           // taps per kernel row
+    int conv_pad;          // zero padding on the top / left edge (bottom / right come from the TMA out-of-bounds fill)
+    int kb_per_tap;        // ceil(C / 64)
+    int conv_H;
+    int conv_W;
+    int tiles_x;
+    int tile_w_log2;
+    int trim_n;            // issue the MMAs of a ragged last n-tile with N = round_up(N - n0, 16) instead of 256
     unsigned int* abort_flag;
 };
+
+// (y0, x0) of the output-pixel patch that m-tile `m0 / 128` covers
+__device__ __forceinline__ void conv_tile_origin(const GemmParams& p, int m0, int& y0, int& x0) {
+    const int mt = m0 >> 7;
+    const int ty = mt / p.tiles_x;
+    y0 = ty << (7 - p.tile_w_log2);
+    x0 = (mt - ty * p.tiles_x) << p.tile_w_log2;
+}
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t v;
@@ -96,6 +115,19 @@ __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f
 // ---- generic per-chunk epilogues: 32 consecutive columns of one row --------------------------------
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const SegDev& sg, long long row, int n, int N) {
+    if (EPI == PE_EPI_F32) {
+        // raw fp32 accumulators (attention scores of the VAE mid block, qwen_image_vae.py:189): out is float [M, ldo]
+        float* o = reinterpret_cast<float*>(sg.out) + row * sg.ldo + n;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            if (n + v * 4 >= N) break;
+            float4 f;
+            f.x = __uint_as_float(acc[v * 4]); f.y = __uint_as_float(acc[v * 4 + 1]);
+            f.z = __uint_as_float(acc[v * 4 + 2]); f.w = __uint_as_float(acc[v * 4 + 3]);
+            *reinterpret_cast<float4*>(o + v * 4) = f;
+        }
+        return;
+    }
     bf16* out_row = sg.out + row * sg.ldo;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -278,12 +310,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         for (int t = cluster_id; t < p.num_tiles && ok; t += num_clusters) {
             const Tile tile = decode_tile<kTileM>(p, t);
             const SegDev& sg = p.seg[tile.seg];
+            int cy0 = 0, cx0 = 0;
+            if (kCG == 1 && p.conv) conv_tile_origin(p, tile.m0, cy0, cx0);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 if (!mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_flag, 1)) { ok = false; break; }
                 if (elect_one()) {
                     if (kCG == 1) {
                         mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-                        tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, tile.m0);
+                        if (p.conv) {
+                            // tap (dy, dx), channel block cb: the [tile_h x tile_w] pixel patch shifted by the tap; pixels outside the
+                            // map (negative or >= H / W coordinates) and channels >= C are zero-filled by the TMA unit
+                            const int tap = kb / p.kb_per_tap;
+                            const int cb = kb - tap * p.kb_per_tap;
+                            const int dy = tap / p.conv_kw;
+                            const int dx = tap - dy * p.conv_kw;
+                            tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cb * kBlockK, cx0 + dx - p.conv_pad, cy0 + dy - p.conv_pad);
+                        } else {
+                            tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, tile.m0);
+                        }
                         tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, tile.n0);
                     } else {
                         // both CTAs' bytes are accounted on the leader's barrier
@@ -300,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(kTileM, kTileN, 0, 0);
+            constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, kTileN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -310,6 +354,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (!mbar_wait<kCG == 2>(tempty_bar(acc), acc_phase ^ 1u, p.abort_flag, 2)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTileN;
+                uint32_t idesc = idesc_full;
+                if (kCG == 1 && p.trim_n) {
+                    // narrow layers (96 / 192 / 384 conv channels): do not multiply the zero-filled weight rows of a ragged n-tile
+                    const int n_left = p.N - decode_tile<kTileM>(p, t).n0;
+                    if (n_left < kTileN) idesc = make_idesc_bf16(kTileM, (uint32_t)((n_left + 15) & ~15), 0, 0);
+                }
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     if (!mbar_wait(full_bar(stage), phase, p.abort_flag, 3)) { ok = false; break; }
                     tc_fence_after();
@@ -346,8 +396,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if (!mbar_wait(tfull_bar(acc), acc_phase, p.abort_flag, 4)) break;
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kTileN;
-            const long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
-            const bool row_valid = row < sg.M;
+            long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
+            bool row_valid = row < sg.M;
+            if (kCG == 1 && p.conv) {
+                int cy0, cx0;
+                conv_tile_origin(p, tile.m0, cy0, cx0);
+                const int r = ew * 32 + lane;
+                const int yy = cy0 + (r >> p.tile_w_log2);
+                const int xx = cx0 + (r & ((1 << p.tile_w_log2) - 1));
+                row_valid = yy < p.conv_H && xx < p.conv_W;
+                row = (long long)yy * p.conv_W + xx;
+            }
             if (EPI == PE_EPI_QKV_NORM_ROPE) {
                 const int n_head0 = tile.n0 + half * 128;
                 if (n_head0 < p.N) epilogue_qkv_head(taddr + half * 128, sg, row, row_valid, n_head0, p.heads);
@@ -425,6 +484,7 @@ int dispatch_epilogue(Handle* h, const GemmParams& p, int epilogue, cudaStream_t
         case PE_EPI_GATE_RESIDUAL: return launch_gemm<kCG, PE_EPI_GATE_RESIDUAL>(h, p, stream);
         case PE_EPI_QKV_NORM_ROPE: return launch_gemm<kCG, PE_EPI_QKV_NORM_ROPE>(h, p, stream);
         case PE_EPI_BIAS_SILU: return launch_gemm<kCG, PE_EPI_BIAS_SILU>(h, p, stream);
+        case PE_EPI_F32: return launch_gemm<kCG, PE_EPI_F32>(h, p, stream);
         default: return set_error(h, PE_ERR_INVALID_ARGUMENT, "pe_gemm: unknown epilogue %d", epilogue);
     }
 }
@@ -494,8 +554,67 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
 #endif
     }
     p.num_tiles = total_m_tiles * p.num_n;
+    p.trim_n = (flags & PE_GEMM_FLAG_TRIM_N) ? 1 : 0;
     if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
     return dispatch_epilogue<2>(h, p, epilogue, stream);
+}
+
+// Implicit-GEMM 2-D convolution, stride 1, output size = input size:
+//   out[y, x, n] = epilogue( sum_{dy, dx, c} x[y + dy - pad, x + dx - pad, c] * w[n, (dy*kw + dx)*cpad + c] + bias[n] )
+// with zeros outside the map.  No im2col buffer: the producer warp of gemm_kernel reads one shifted pixel patch per tap straight
+// from the NHWC activation map through a 3-D tensor map.
+int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t stream) {
+    PE_REQUIRE(h, d->x && d->w && d->out, "pe_conv2d: null x / w / out");
+    PE_REQUIRE(h, d->H > 0 && d->W > 0 && d->C > 0 && d->N > 0, "pe_conv2d: H, W, C, N must be positive");
+    PE_REQUIRE(h, d->C % 8 == 0 && d->ldx % 8 == 0 && d->ldx >= d->C, "pe_conv2d: C and ldx must be multiples of 8, ldx >= C (C=%d ldx=%lld)", d->C, (long long)d->ldx);
+    PE_REQUIRE(h, d->N % 8 == 0 && d->ldo % 8 == 0, "pe_conv2d: N and ldo must be multiples of 8");
+    PE_REQUIRE(h, d->kh >= 1 && d->kh <= 3 && d->kw >= 1 && d->kw <= 3 && d->pad >= 0 && d->pad <= 1, "pe_conv2d: kernel up to 3x3, pad 0 or 1");
+    PE_REQUIRE(h, epilogue == PE_EPI_BIAS || epilogue == PE_EPI_GATE_RESIDUAL || epilogue == PE_EPI_BIAS_SILU,
+               "pe_conv2d: epilogue must be PE_EPI_BIAS, PE_EPI_BIAS_SILU or PE_EPI_GATE_RESIDUAL");
+    PE_REQUIRE(h, epilogue != PE_EPI_GATE_RESIDUAL || d->gate != nullptr, "pe_conv2d: gate-residual epilogue needs gate");
+    PE_REQUIRE(h, (reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pe_conv2d: x / w / out must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.nseg = 1;
+    p.N = d->N;
+    p.kb_per_tap = ceil_div(d->C, kBlockK);
+    const int cpad = p.kb_per_tap * kBlockK;
+    p.K = d->kh * d->kw * cpad;
+    p.num_n = ceil_div(d->N, kTileN);
+    p.num_kb = p.K / kBlockK;
+    p.abort_flag = h->abort_flag;
+    p.conv = 1;
+    p.conv_kw = d->kw;
+    p.conv_pad = d->pad;
+    p.conv_H = d->H;
+    p.conv_W = d->W;
+    p.tile_w_log2 = d->W > 8 ? 4 : 3;             // 8 x 16 pixel patches (16 x 8 for maps narrower than 9 pixels)
+    const int tile_w = 1 << p.tile_w_log2, tile_h = 128 >> p.tile_w_log2;
+    p.tiles_x = ceil_div(d->W, tile_w);
+    p.trim_n = 1;
+    SegDev& sd = p.seg[0];
+    int rc = make_tmap_3d(h, &sd.tmA, d->x, (uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->ldx, (uint64_t)d->ldx * d->W,
+                          64, (uint32_t)tile_w, (uint32_t)tile_h);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &sd.tmB, d->w, (uint64_t)d->N, (uint64_t)p.K, (uint64_t)p.K, 256);
+    if (rc) return rc;
+    sd.bias = static_cast<const bf16*>(d->bias);
+    sd.out = static_cast<bf16*>(d->out);
+    sd.gate = static_cast<const bf16*>(d->gate);
+    sd.ldo = d->ldo;
+    sd.M = d->H * d->W;
+    sd.m_tiles = p.tiles_x * ceil_div(d->H, tile_h);
+    p.total_m_tiles = sd.m_tiles;
+    {
+        const long long tile_row_bytes = (long long)128 * p.K * 2;
+        int gm_max = (int)(kPanelBytes / tile_row_bytes);
+        if (gm_max < 1) gm_max = 1;
+        const int groups = ceil_div(p.total_m_tiles, gm_max);
+        p.group_m = ceil_div(p.total_m_tiles, groups);
+    }
+    p.num_tiles = p.total_m_tiles * p.num_n;
+    return dispatch_epilogue<1>(h, p, epilogue, stream);
 }
 
 }  // namespace pe

@@ -23,7 +23,9 @@ EPI_BIAS_GELU_ERF = 3
 EPI_GATE_RESIDUAL = 4
 EPI_QKV_NORM_ROPE = 5
 EPI_BIAS_SILU = 6
+EPI_F32 = 7
 GEMM_FLAG_CTA_PAIR = 1
+GEMM_FLAG_TRIM_N = 2
 ATTN_FLAG_SINGLE_Q_TILE = 1
 ATTN_FLAG_P_VIA_SMEM = 2
 ATTN_FLAG_SPLIT_ROW_SOFTMAX = 8
@@ -34,6 +36,8 @@ EXPORTED_SYMBOLS = [
     "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
+    "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
+    "pe_softmax_rows",
 ]
 
 
@@ -51,6 +55,14 @@ class GemmSeg(Structure):
         ("a", c_void_p), ("lda", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
         ("M", c_int32), ("_pad0", c_int32), ("gate", c_void_p), ("out_k", c_void_p), ("out_v", c_void_p),
         ("norm_q_w", c_void_p), ("norm_k_w", c_void_p), ("rope", c_void_p),
+    ]
+
+
+class Conv2dDesc(Structure):
+    """Mirror of `pe_conv2d_desc` (include/pe_b200.h)."""
+    _fields_ = [
+        ("x", c_void_p), ("ldx", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("gate", c_void_p),
+        ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("kh", c_int32), ("kw", c_int32), ("pad", c_int32), ("_pad0", c_int32),
     ]
 
 
@@ -85,6 +97,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_cfg_euler_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]
     lib.pe_special_gather.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
     lib.pe_special_blend_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]
+    lib.pe_conv2d.argtypes = [c_void_p, POINTER(Conv2dDesc), c_int, c_void_p]
+    lib.pe_channel_rmsnorm.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p]
+    lib.pe_upsample2x.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.pe_space_to_depth.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.pe_nchw_to_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
+    lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
     return lib
 
 
@@ -177,7 +197,12 @@ class Native:
         arr = (GemmSeg * len(segs))()
         for i, s in enumerate(segs):
             a = _bf16(s["a"], "a")
-            out = _bf16(s["out"], "out")
+            out = s["out"]
+            if epilogue == EPI_F32:
+                if out.dtype != torch.float32 or not out.is_cuda or out.stride(-1) != 1:
+                    raise NativeError("out: EPI_F32 needs a CUDA float32 tensor with innermost stride 1")
+            else:
+                _bf16(out, "out")
             w = _bf16(s["w"], "w")
             if not w.is_contiguous():
                 raise NativeError("w must be contiguous [N, K]")
@@ -299,4 +324,73 @@ class Native:
         self._check(self.lib.pe_special_blend_scatter(self.h, prompt_emb.data_ptr(), idx.data_ptr(), pred_dino.shape[0], prompt_emb.shape[1],
                                                       pred_dino.data_ptr(), pred_vae.data_ptr(), t_in.data_ptr(), t_min, t_max,
                                                       self._stream_prof()), "pe_special_blend_scatter")
+        self.launches += 1
+
+    # ---- QwenImageVAE path (include/pe_b200.h, last section) -----------------------------------------------------------------
+    def conv2d(self, x, H: int, W: int, C: int, w, bias, out, N: int, kh: int, kw: int, pad: int, epilogue: int = EPI_BIAS, gate=None) -> None:
+        """x: [H*W, >=C] channels-last map, w: [N, kh*kw*round_up(C,64)], out: [H*W, >=N]; stride 1, same output size."""
+        _bf16(x, "x"); _bf16(w, "w"); _bf16(out, "out")
+        if x.shape[0] != H * W or out.shape[0] != H * W or not w.is_contiguous():
+            raise NativeError("conv2d: x / out must have H*W rows and w must be contiguous")
+        cpad = (C + 63) // 64 * 64
+        if w.shape[0] != N or w.shape[1] != kh * kw * cpad:
+            raise NativeError(f"conv2d: w must be [{N}, {kh * kw * cpad}], got {tuple(w.shape)}")
+        d = Conv2dDesc(x=x.data_ptr(), ldx=x.stride(0), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), ldo=out.stride(0), gate=_ptr(gate),
+                       H=H, W=W, C=C, N=N, kh=kh, kw=kw, pad=pad)
+        self._check(self.lib.pe_conv2d(self.h, byref(d), epilogue, self._stream_prof()), "pe_conv2d")
+        self.launches += 1
+
+    def channel_rmsnorm(self, x, out, C: int, gamma, act: bool) -> None:
+        _bf16(x, "x"); _bf16(out, "out"); _bf16(gamma, "gamma")
+        self._check(self.lib.pe_channel_rmsnorm(self.h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], C, gamma.data_ptr(),
+                                                int(act), self._stream_prof()), "pe_channel_rmsnorm")
+        self.launches += 1
+
+    def upsample2x(self, x, out, H: int, W: int, C: int) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        if not (x.is_contiguous() and out.is_contiguous()) or x.numel() != H * W * C or out.numel() != 4 * H * W * C:
+            raise NativeError("upsample2x: x [H*W, C] and out [4*H*W, C] must be contiguous")
+        self._check(self.lib.pe_upsample2x(self.h, x.data_ptr(), out.data_ptr(), H, W, C, self._stream_prof()), "pe_upsample2x")
+        self.launches += 1
+
+    def space_to_depth(self, x, out, H: int, W: int, C: int) -> None:
+        _bf16(x, "x"); _bf16(out, "out")
+        if not (x.is_contiguous() and out.is_contiguous()) or x.numel() != H * W * C or out.numel() != H * W * C:
+            raise NativeError("space_to_depth: x [H*W, C] and out [H*W/4, 4C] must be contiguous")
+        self._check(self.lib.pe_space_to_depth(self.h, x.data_ptr(), out.data_ptr(), H, W, C, self._stream_prof()), "pe_space_to_depth")
+        self.launches += 1
+
+    def nchw_to_nhwc(self, src, dst, C: int, op: int = 0, p0=None, p1=None) -> None:
+        """src [C, H, W] contiguous -> dst [H*W, >=C] (columns >= C untouched)."""
+        _bf16(src, "src"); _bf16(dst, "dst")
+        if not src.is_contiguous() or src.numel() != C * dst.shape[0]:
+            raise NativeError("nchw_to_nhwc: src must be contiguous [C, H*W]")
+        self._check(self.lib.pe_nchw_to_nhwc(self.h, src.data_ptr(), dst.data_ptr(), dst.stride(0), C, dst.shape[0], op, _ptr(p0), _ptr(p1),
+                                             self._stream_prof()), "pe_nchw_to_nhwc")
+        self.launches += 1
+
+    def nhwc_to_nchw(self, src, dst, C: int, op: int = 0, p0=None, p1=None) -> None:
+        """src [H*W, >=C] -> dst [C, H, W] contiguous (first C channels)."""
+        _bf16(src, "src"); _bf16(dst, "dst")
+        if not dst.is_contiguous() or dst.numel() != C * src.shape[0]:
+            raise NativeError("nhwc_to_nchw: dst must be contiguous [C, H*W]")
+        self._check(self.lib.pe_nhwc_to_nchw(self.h, src.data_ptr(), src.stride(0), dst.data_ptr(), C, src.shape[0], op, _ptr(p0), _ptr(p1),
+                                             self._stream_prof()), "pe_nhwc_to_nchw")
+        self.launches += 1
+
+    def transpose(self, src, dst) -> None:
+        _bf16(src, "src"); _bf16(dst, "dst")
+        if dst.shape[0] != src.shape[1] or dst.shape[1] != src.shape[0]:
+            raise NativeError("transpose: dst must be [C, R]")
+        self._check(self.lib.pe_transpose(self.h, src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0], src.shape[1],
+                                          self._stream_prof()), "pe_transpose")
+        self.launches += 1
+
+    def softmax_rows(self, scores, probs, n: int, scale: float) -> None:
+        """probs[:, :n] = softmax(scale * scores[:, :n]); probs[:, n:] = 0.  scores fp32 [rows, >=n], probs bf16 [rows, n_pad]."""
+        _bf16(probs, "probs")
+        if scores.dtype != torch.float32 or not scores.is_cuda or scores.stride(-1) != 1 or scores.shape[0] != probs.shape[0]:
+            raise NativeError("softmax_rows: scores must be CUDA float32 [rows, >=n] with as many rows as probs")
+        self._check(self.lib.pe_softmax_rows(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
+                                             n, probs.shape[1], scale, self._stream_prof()), "pe_softmax_rows")
         self.launches += 1

@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE: a torch-CPU emulation of the C-ABI entry points the VAE host code calls (include/pe_b200.h, last section).
+
+It restates each entry point's documented contract (argument layout, padding rules, epilogues) with plain tensor ops so that the
+HOST logic of physicedit_b200/vae.py -- weight repacking, tap order, space-to-depth mapping, buffer strides, the attention
+chunking -- can be checked against the oracle without a GPU.  It is never imported by the product; the GPU tests run the same host
+code on the real library.  Arithmetic is fp32 with bf16 rounding at the points the header documents."""
+import torch
+import torch.nn.functional as F
+
+EPI_BIAS, EPI_GATE_RESIDUAL, EPI_F32 = 0, 4, 7
+
+
+def _r(x):
+    return x.to(torch.bfloat16).float()
+
+
+class EmulatedNative:
+    def __init__(self):
+        self.tag = None
+        self.launches = 0
+        self.calls = []
+
+    def _note(self, what):
+        self.calls.append((what, self.tag))
+        self.tag = None
+        self.launches += 1
+
+    # out = epi(A . W^T + bias), A [M, K] (row stride = a.stride(0)), W [N, K]
+    def gemm(self, segs, N, K, epilogue=EPI_BIAS, flags=0):
+        for s in segs:
+            a, w, out = s["a"], s["w"], s["out"]
+            assert a.shape[1] >= K and w.shape == (N, K) and w.is_contiguous() and N % 8 == 0 and K % 8 == 0
+            assert a.stride(0) >= K and out.shape[0] == a.shape[0]
+            acc = a[:, :K].float() @ w.float().t()
+            if epilogue == EPI_F32:
+                assert out.dtype == torch.float32
+                out[:, :N] = acc
+                continue
+            if s.get("bias") is not None:
+                acc = acc + s["bias"].float()[:N]
+            y = _r(acc)
+            if epilogue == EPI_GATE_RESIDUAL:
+                y = out[:, :N].float() + _r(s["gate"].float()[:N] * y)
+            out[:, :N] = y.to(torch.bfloat16)
+        self._note("pe_gemm")
+
+    def conv2d(self, x, H, W, C, w, bias, out, N, kh, kw, pad, epilogue=EPI_BIAS, gate=None):
+        cpad = (C + 63) // 64 * 64
+        assert x.shape[0] == H * W and x.stride(0) >= C and w.shape == (N, kh * kw * cpad) and N % 8 == 0 and C % 8 == 0
+        xm = x[:, :C].float().reshape(H, W, C).permute(2, 0, 1).unsqueeze(0)
+        wk = w.float().reshape(N, kh, kw, cpad)[..., :C].permute(0, 3, 1, 2)
+        xm = F.pad(xm, (pad, kw - 1 - pad, pad, kh - 1 - pad))          # zeros outside the map on every side
+        acc = F.conv2d(xm, wk)[0].permute(1, 2, 0).reshape(H * W, N)
+        if bias is not None:
+            acc = acc + bias.float()[:N]
+        y = _r(acc)
+        if epilogue == EPI_GATE_RESIDUAL:
+            y = out[:, :N].float() + _r(gate.float()[:N] * y)
+        out[:, :N] = y.to(torch.bfloat16)
+        self._note("pe_conv2d")
+
+    def channel_rmsnorm(self, x, out, C, gamma, act):
+        v = x[:, :C].float()
+        n = _r(v.pow(2).sum(-1, keepdim=True).sqrt()).clamp_min(1e-12)
+        y = _r(_r(_r(v / n) * float(torch.tensor(C ** 0.5, dtype=torch.float32))) * gamma.float())
+        if act:
+            y = y / (1 + torch.exp(-y))
+        out[:, :C] = y.to(torch.bfloat16)
+        self._note("pe_channel_rmsnorm")
+
+    def upsample2x(self, x, out, H, W, C):
+        m = x.reshape(H, W, C)
+        out.copy_(m.repeat_interleave(2, 0).repeat_interleave(2, 1).reshape(4 * H * W, C))
+        self._note("pe_upsample2x")
+
+    def space_to_depth(self, x, out, H, W, C):
+        m = x.reshape(H // 2, 2, W // 2, 2, C).permute(0, 2, 1, 3, 4)          # [y, x, py, px, c]
+        out.copy_(m.reshape(H * W // 4, 4 * C))
+        self._note("pe_space_to_depth")
+
+    @staticmethod
+    def _affine(v, op, p0, p1):
+        if op == 1:
+            return _r(_r(v / p1.float()) + p0.float())
+        if op == 2:
+            return _r(_r(v - p0.float()) * p1.float())
+        return v
+
+    def nchw_to_nhwc(self, src, dst, C, op=0, p0=None, p1=None):
+        v = src.reshape(C, -1).t().float()
+        dst[:, :C] = self._affine(v, op, p0, p1).to(torch.bfloat16)
+        self._note("pe_nchw_to_nhwc")
+
+    def nhwc_to_nchw(self, src, dst, C, op=0, p0=None, p1=None):
+        v = self._affine(src[:, :C].float(), op, p0, p1)
+        dst.copy_(v.t().reshape(dst.shape).to(torch.bfloat16))
+        self._note("pe_nhwc_to_nchw")
+
+    def transpose(self, src, dst):
+        dst.copy_(src.t())
+        self._note("pe_transpose")
+
+    def softmax_rows(self, scores, probs, n, scale):
+        p = torch.softmax(scores[:, :n].float() * scale, dim=-1)
+        probs.zero_()
+        probs[:, :n] = p.to(torch.bfloat16)
+        self._note("pe_softmax_rows")
