@@ -4,6 +4,7 @@ Public entry points:
     model_fn_qwen_image      drop-in for pipelines/qwen_image_physical.py:1302-1403 (install as `pipe.model_fn`)
     QwenImagePhysicPipeline  the pipeline with the reference's constructor / loader / LoRA / denoise surface
     QwenImageDiT, adopt_dit  the DiT with the reference's parameter layout; adopt a loaded reference module
+    QwenImageVAE, load_vae   the VAE either side of the loop (encode / decode of single images), same parameter layout
     FlowMatchScheduler, GeneralLoRALoader, ModelConfig, load_state_dict
 Everything numeric runs in physicedit_b200/lib/libpe_b200.so (include/pe_b200.h); there is no CPU fallback.
 """
@@ -15,6 +16,8 @@ _LAZY = {
     "ModelConfig": ("pipeline", "ModelConfig"),
     "load_state_dict": ("pipeline", "load_state_dict"),
     "load_dit": ("pipeline", "load_dit"),
+    "load_vae": ("pipeline", "load_vae"),
+    "QwenImageVAE": ("vae", "QwenImageVAE"),
     "QwenImageDiT": ("dit", "QwenImageDiT"),
     "FlowMatchScheduler": ("scheduler", "FlowMatchScheduler"),
     "GeneralLoRALoader": ("lora", "GeneralLoRALoader"),

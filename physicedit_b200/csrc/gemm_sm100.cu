@@ -70,6 +70,7 @@ struct GemmParams {
     int tiles_x;
     int tile_w_log2;
     int trim_n;            // issue the MMAs of a ragged last n-tile with N = round_up(N - n0, 16) instead of 256
+    int stage_tx_bytes;    // bytes one pipeline stage receives (A box + W box): the W box has only round_up(N, 16) rows for narrow layers
     unsigned int* abort_flag;
 };
 
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (!mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_flag, 1)) { ok = false; break; }
                 if (elect_one()) {
                     if (kCG == 1) {
-                        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx_bytes);
                         if (p.conv) {
                             // tap (dy, dx), channel block cb: the [tile_h x tile_w] pixel patch shifted by the tap; pixels outside the
                             // map (negative or >= H / W coordinates) and channels >= C are zero-filled by the TMA unit
@@ -508,6 +509,9 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         PE_REQUIRE(h, N % 384 == 0, "pe_gemm: QKV epilogue needs N = 3*heads*128 (N=%d)", N);
         p.heads = N / 384;
     }
+    // narrow layers (PE_GEMM_FLAG_TRIM_N, N < 256): the W box has only round_up(N, 16) rows, so no zero-filled rows are written to shared memory
+    const int b_box_rows = ((flags & PE_GEMM_FLAG_TRIM_N) && N < kTileN) ? ((N + 15) & ~15) : kTileN;
+    p.stage_tx_bytes = 128 * kBlockK * 2 + b_box_rows * kBlockK * 2;
     int total_m_tiles = 0;
     for (int s = 0; s < nseg; ++s) {
         const pe_gemm_seg& in = segs[s];
@@ -521,7 +525,7 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         SegDev& d = p.seg[s];
         int rc = make_tmap_2d(h, &d.tmA, in.a, (uint64_t)in.M, (uint64_t)K, (uint64_t)in.lda, 128);
         if (rc) return rc;
-        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? 256 : 128);
+        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? (uint32_t)b_box_rows : 128u);
         if (rc) return rc;
         d.bias = static_cast<const bf16*>(in.bias);
         d.out = static_cast<bf16*>(in.out);
@@ -597,7 +601,9 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     int rc = make_tmap_3d(h, &sd.tmA, d->x, (uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->ldx, (uint64_t)d->ldx * d->W,
                           64, (uint32_t)tile_w, (uint32_t)tile_h);
     if (rc) return rc;
-    rc = make_tmap_2d(h, &sd.tmB, d->w, (uint64_t)d->N, (uint64_t)p.K, (uint64_t)p.K, 256);
+    const int b_box_rows = d->N < kTileN ? ((d->N + 15) & ~15) : kTileN;
+    p.stage_tx_bytes = 128 * kBlockK * 2 + b_box_rows * kBlockK * 2;
+    rc = make_tmap_2d(h, &sd.tmB, d->w, (uint64_t)d->N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)b_box_rows);
     if (rc) return rc;
     sd.bias = static_cast<const bf16*>(d->bias);
     sd.out = static_cast<bf16*>(d->out);

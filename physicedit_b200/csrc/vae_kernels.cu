@@ -35,46 +35,74 @@ __device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
     return u;
 }
 
-// ---- F.normalize(x, dim=C) * sqrt(C) * gamma (+ SiLU): one warp per pixel, the pixel's channels in registers -------------------
+// ---- F.normalize(x, dim=C) * sqrt(C) * gamma (+ SiLU) -------------------------------------------------------------------------
 //   n = bf16(||x||_2) clamped at 1e-12; y = bf16(x / n); y = bf16(y * sqrt(C)); y = bf16(y * gamma); act: y = bf16(silu(y))
-template <int kVec>
+// A pixel (row) is owned by a group of kGroup lanes (16 for C <= 128, else 32), each lane holding kVec 16-byte vectors in
+// registers, so the narrow 96-channel maps still keep 24 of 32 lanes busy; every byte is read once.  Rounding to bf16 goes
+// through the packed converter (two values per instruction) and integer unpacking: scalar F2F conversions, IEEE divisions and
+// expf would make this pass XU-bound instead of HBM-bound.
+__device__ __forceinline__ void round_pair(float& a, float& b) {
+    const uint32_t p = pack_bf16(a, b);
+    a = __uint_as_float(p << 16);
+    b = __uint_as_float(p & 0xffff0000u);
+}
+template <int kGroup, int kVec>
 __global__ void __launch_bounds__(kWarps * 32) channel_rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
                                                                        long long rows, int C, const bf16* __restrict__ gamma, float scale, int act) {
+    constexpr int kRowsPerWarp = 32 / kGroup;
     const int lane = threadIdx.x & 31;
+    const int gl = lane & (kGroup - 1);                 // lane inside its row group
+    const int sub = lane / kGroup;                      // which of the warp's rows
     const int nvec = C >> 3;
     float g[kVec][8];
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
-        const int vi = lane + 32 * i;
+        const int vi = gl + kGroup * i;
         if (vi < nvec) unpack8v(__ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)), g[i]);
     }
-    for (long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * kWarps) {
+    const long long warp_id = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long warp_stride = (long long)gridDim.x * kWarps;
+    for (long long r0 = warp_id * kRowsPerWarp; r0 < rows; r0 += warp_stride * kRowsPerWarp) {
+        const long long row = r0 + sub;
+        const bool live = row < rows;
         const bf16* xr = x + row * ldx;
         float v[kVec][8];
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < kVec; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nvec) {
+            const int vi = gl + kGroup * i;
+            if (live && vi < nvec) {
                 unpack8v(*reinterpret_cast<const uint4*>(xr + vi * 8), v[i]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
             }
         }
-        const float n = fmaxf(bf16_round(sqrtf(warp_sum_f(ss))), 1e-12f);
+#pragma unroll
+        for (int o = kGroup / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        // x / n as x * (1 / n): one reciprocal per pixel instead of an IEEE division per element (the two differ by <= 1 fp32 ulp, i.e. the
+        // bf16 result differs for ~2^-15 of the elements, by one bf16 ulp)
+        const float rn = __frcp_rn(fmaxf(bf16_round(sqrtf(ss)), 1e-12f));
         bf16* orow = out + row * ldo;
 #pragma unroll
         for (int i = 0; i < kVec; ++i) {
-            const int vi = lane + 32 * i;
-            if (vi < nvec) {
+            const int vi = gl + kGroup * i;
+            if (live && vi < nvec) {
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float y = bf16_round(__fdiv_rn(v[i][j], n));
-                    y = bf16_round(y * scale);
-                    y = bf16_round(y * g[i][j]);
-                    if (act) y = __fdiv_rn(y, 1.0f + expf(-y));
-                    o[j] = y;
+                for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rn;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] *= scale;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] *= g[i][j];
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-o[j]));
                 }
                 *reinterpret_cast<uint4*>(orow + vi * 8) = pack8v(o);
             }
@@ -200,15 +228,16 @@ int channel_rmsnorm_run(Handle* h, const void* x, int64_t ldx, void* out, int64_
     PE_REQUIRE(h, rows > 0 && C > 0 && C % 8 == 0 && C <= 512, "pe_channel_rmsnorm: C must be a multiple of 8, <= 512 (C=%d)", C);
     PE_REQUIRE(h, ldx % 8 == 0 && ldo % 8 == 0 && ldx >= C && ldo >= C, "pe_channel_rmsnorm: row strides must be multiples of 8 and >= C");
     const float scale = (float)sqrt((double)C);                 // self.scale = dim ** 0.5, applied as an fp32 scalar
-    long long blocks = (rows + kWarps - 1) / kWarps;
+    const int group = C <= 128 ? 16 : 32;
+    long long blocks = (rows + kWarps * (32 / group) - 1) / (kWarps * (32 / group));
     const long long cap = (long long)h->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    if (C <= 256)
-        channel_rmsnorm_kernel<1><<<(int)blocks, kWarps * 32, 0, s>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(out), ldo, rows, C,
-                                                                      static_cast<const bf16*>(gamma), scale, act);
-    else
-        channel_rmsnorm_kernel<2><<<(int)blocks, kWarps * 32, 0, s>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(out), ldo, rows, C,
-                                                                      static_cast<const bf16*>(gamma), scale, act);
+    const bf16* xp = static_cast<const bf16*>(x);
+    bf16* op = static_cast<bf16*>(out);
+    const bf16* gp = static_cast<const bf16*>(gamma);
+    if (C <= 128) channel_rmsnorm_kernel<16, 1><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
+    else if (C <= 256) channel_rmsnorm_kernel<32, 1><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
+    else channel_rmsnorm_kernel<32, 2><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

@@ -6,9 +6,9 @@ from_pretrained :497-541, __call__ :544-669) and diffsynth/utils/__init__.py (Ba
 
 In scope here: the in-iteration models (`dit`, `visual_thinking_adapter`), the scheduler,
 the CFG denoise loop, LoRA fold, checkpoint key layout, and the training-path feature extractors
-(DINOv2, resamplers).  Out of scope (8f "next"): the Qwen2.5-VL text encoder and the VAE -- the pipeline
-accepts them as user-supplied modules (`pipe.text_encoder`, `pipe.vae`, any object with the reference's
-`encode`/`decode`/`edit_forward` contract) or takes pre-computed embeddings / latents through
+(DINOv2, resamplers), and -- SURVEY 8f1 -- the VAE either side of the loop (`physicedit_b200/vae.py`, loaded by registry hash
+like the DiT).  Out of scope (8f2): the Qwen2.5-VL text encoder -- the pipeline accepts it as a user-supplied module
+(`pipe.text_encoder`, any object with the reference's `edit_forward` contract) or takes pre-computed embeddings through
 `denoise(...)`, which is what bench.py and the parity tests drive.
 """
 from __future__ import annotations
@@ -27,9 +27,11 @@ from .dit import QwenImageDiT
 from .lora import GeneralLoRALoader
 from .model_fn import model_fn_qwen_image
 from .scheduler import FlowMatchScheduler
+from .vae import QwenImageVAE
 
 SPECIAL_TOKEN_NUM = 64        # qwen_image_physical.py:28
 DIT_KEY_HASH = "0319a1cb19835fb510907dd3367c95ff"      # configs/model_config.py:21
+VAE_KEY_HASH = "ed4ea5824d55ec3107b09815e318123a"      # configs/model_config.py:24
 
 
 @dataclass
@@ -93,10 +95,10 @@ def hash_state_dict_keys(state_dict, with_shape=True):
     return hashlib.md5(",".join(keys).encode("UTF-8")).hexdigest()
 
 
-def load_dit(path, torch_dtype=torch.bfloat16, device="cuda") -> Optional[QwenImageDiT]:
+def load_dit(path, torch_dtype=torch.bfloat16, device="cuda", state_dict=None) -> Optional[QwenImageDiT]:
     """ModelManager.load_model for the one registry row on this path (model_manager.py:350-376): detect by key hash,
     init on the meta device, `load_state_dict(assign=True)`, move.  Unknown files print and return None like the reference."""
-    sd = load_state_dict(path, torch_dtype=torch_dtype, device="cpu")
+    sd = state_dict if state_dict is not None else load_state_dict(path, torch_dtype=torch_dtype, device="cpu")
     if hash_state_dict_keys(sd) != DIT_KEY_HASH:
         print(f"    We cannot detect the model type. No models are loaded ({path}).")
         return None
@@ -107,6 +109,19 @@ def load_dit(path, torch_dtype=torch.bfloat16, device="cuda") -> Optional[QwenIm
     for i, b in enumerate(dit.transformer_blocks):
         object.__setattr__(b, "_owner", (dit, i))
     return dit.to(dtype=torch_dtype, device=device).eval()
+
+
+def load_vae(path, torch_dtype=torch.bfloat16, device="cuda", state_dict=None) -> Optional[QwenImageVAE]:
+    """The `qwen_image_vae` registry row (configs/model_config.py:24; converter `from_diffusers` is the identity,
+    models/qwen_image_vae.py:737-742): detect by key hash, meta-init, assign.  Unknown files print and return None."""
+    sd = state_dict if state_dict is not None else load_state_dict(path, torch_dtype=torch_dtype, device="cpu")
+    if hash_state_dict_keys(sd) != VAE_KEY_HASH:
+        print(f"    We cannot detect the model type. No models are loaded ({path}).")
+        return None
+    with torch.device("meta"):
+        vae = QwenImageVAE()
+    vae.load_state_dict(sd, assign=True)
+    return vae.to(dtype=torch_dtype, device=device).eval()
 
 
 class QwenImagePhysicPipeline(nn.Module):
@@ -156,7 +171,12 @@ class QwenImagePhysicPipeline(nn.Module):
             cfg.download_if_necessary()
             paths = cfg.path if isinstance(cfg.path, list) else [cfg.path]
             try:
-                model = load_dit(paths if len(paths) > 1 else paths[0], torch_dtype=cfg.offload_dtype or torch_dtype, device=device)
+                dtype = cfg.offload_dtype or torch_dtype
+                sd = load_state_dict(paths if len(paths) > 1 else paths[0], torch_dtype=dtype, device="cpu")
+                if hash_state_dict_keys(sd) == VAE_KEY_HASH:          # model detection by key hash (model_manager.py:350-376)
+                    pipe.vae = load_vae(paths, torch_dtype=dtype, device=device, state_dict=sd)
+                    continue
+                model = load_dit(paths, torch_dtype=dtype, device=device, state_dict=sd)
             except Exception as e:  # noqa: BLE001  (the reference's loader prints and moves on, model_manager.py:375-376)
                 print(f"    Loading {paths} failed: {e}")
                 model = None
@@ -195,6 +215,23 @@ class QwenImagePhysicPipeline(nn.Module):
             width = (width + 15) // 16 * 16
             print(f"width % 16 != 0. We round it up to {width}.")
         return height, width
+
+    def preprocess_image(self, image, torch_dtype=None, device=None, pattern="B C H W", min_value=-1, max_value=1):
+        """PIL.Image -> tensor in [min_value, max_value] (diffsynth/utils/__init__.py:60-66)."""
+        import numpy as np
+        t = torch.Tensor(np.array(image, dtype=np.float32)).to(dtype=torch_dtype or self.torch_dtype, device=device or self.device)
+        t = t * ((max_value - min_value) / 255) + min_value
+        t = t.permute(2, 0, 1)
+        return t.unsqueeze(0) if "B" in pattern else t
+
+    def vae_output_to_image(self, vae_output, pattern="B C H W", min_value=-1, max_value=1):
+        """tensor -> PIL.Image (diffsynth/utils/__init__.py:76-83; the batch axis is averaged away as there)."""
+        import numpy as np  # noqa: F401
+        from PIL import Image
+        if pattern == "B C H W":
+            vae_output = vae_output.mean(dim=0).permute(1, 2, 0)
+        image = ((vae_output - min_value) * (255 / (max_value - min_value))).clip(0, 255)
+        return Image.fromarray(image.to(device="cpu", dtype=torch.uint8).numpy())
 
     def generate_noise(self, shape, seed=None, rand_device="cpu", rand_torch_dtype=torch.float32, device=None, torch_dtype=None):
         generator = None if seed is None else torch.Generator(rand_device).manual_seed(seed)
@@ -305,14 +342,18 @@ class QwenImagePhysicPipeline(nn.Module):
             prompt_inputs_nega = self.text_encoder.encode_for_pipeline(self, negative_prompt, edit_image, positive=False)
         if edit_latents is None and edit_image is not None:
             if self.vae is None:
-                raise RuntimeError("no VAE attached: pass edit_latents (SURVEY 8f1)")
-            edit_latents = self.vae.encode(edit_image, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
+                raise RuntimeError("no VAE loaded: pass edit_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
+            # QwenImageUnit_EditImageEmbedder.process (qwen_image_physical.py:1265-1285): one image or a list of images
+            imgs = edit_image if isinstance(edit_image, (list, tuple)) else [edit_image]
+            enc = [self.vae.encode(im if isinstance(im, torch.Tensor) else self.preprocess_image(im), tiled=tiled, tile_size=tile_size,
+                                   tile_stride=tile_stride) for im in imgs]
+            edit_latents = enc if isinstance(edit_image, (list, tuple)) else enc[0]
         latents = self.denoise(latents, prompt_inputs_posi, prompt_inputs_nega, edit_latents, height=height, width=width,
                                num_inference_steps=num_inference_steps, cfg_scale=cfg_scale, progress_bar_cmd=progress_bar_cmd)
         if output_type == "latent" or self.vae is None:
             return latents
         image = self.vae.decode(latents, device=self.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
-        return image
+        return self.vae_output_to_image(image) if output_type == "pil" else image
 
     # ---- training path (forward only) -----------------------------------------
     @torch.no_grad()

@@ -275,7 +275,7 @@ class QwenImageVAE(nn.Module):
             out = torch.empty((H * W, n8), dtype=torch.bfloat16, device=x.device)
         elif out is None:                       # narrow output inside a zero-padded `ldo`-wide map (feeds a K = ldo layer)
             out = torch.zeros((H * W, ldo), dtype=torch.bfloat16, device=x.device)
-        nat.tag = f"vae_conv{kh}x{kw}"
+        nat.tag = f"vae_conv{kh}x{kw}_{H}x{W}_{cin}to{n8}"
         if kh == 1 and kw == 1:
             nat.gemm([dict(a=x, w=w2d, bias=b, out=out, gate=P["ones"] if residual else None)], n8, w2d.shape[1],
                      nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N)
@@ -287,7 +287,7 @@ class QwenImageVAE(nn.Module):
     @staticmethod
     def _norm(nat, gamma, x, act=True):
         out = torch.empty_like(x)
-        nat.tag = "vae_rmsnorm"
+        nat.tag = f"vae_rmsnorm_{x.shape[0]}x{gamma.numel()}"
         nat.channel_rmsnorm(x, out, gamma.numel(), gamma, act)
         return out
 

@@ -27,6 +27,8 @@ def assert_within_one_ulp(got, want, what, frac_exact=0.90, floor=1e-30):
     """bf16 tensors equal up to one unit in the last place (summation-order noise), most entries identical.  `floor`: magnitude of the
     operands of a final add (residual epilogue), whose one-ulp flips survive cancellation."""
     g, w = got.float().cpu(), want.float().cpu()
+    # entries that cancel to ~0 carry the fp32 summation-order noise of their O(rms) partial sums: measure them against 2 % of the rms
+    floor = max(floor, 0.02 * w.pow(2).mean().sqrt().item())
     ulp = torch.maximum(w.abs(), g.abs()).clamp_min(floor) * 2.0 ** -7      # >= 1 bf16 ulp of the larger magnitude
     bad = (g - w).abs() > ulp
     assert not bad.any(), f"{what}: {int(bad.sum())} of {g.numel()} entries differ by more than 1 bf16 ulp; max abs diff {(g - w).abs().max().item()}"
@@ -231,3 +233,42 @@ def test_vae_full_size_properties(nat, vae):
     assert enc.shape == (1, 16, 128, 128) and dec.shape == (1, 3, 1024, 1024)
     assert torch.isfinite(enc.float()).all() and torch.isfinite(dec.float()).all()
     assert torch.equal(m.encode(img), enc) and torch.equal(m.decode(inp["latents"].cuda()), dec), "not deterministic"
+
+
+@gpu
+def test_pipeline_call_pil_in_pil_out(nat, vae):
+    """QwenImagePhysicPipeline.__call__ (qwen_image_physical.py:544-669) end to end at toy size with the native VAE either side of the
+    native denoise loop: PIL edit image -> preprocess -> vae.encode -> 2 CFG steps of a 1-block DiT -> vae.decode -> PIL image."""
+    import numpy as np
+    from PIL import Image
+    from oracle import dit_oracle as O
+    from physicedit_b200.dit import QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    m, _ = vae
+    W = {k: v.to(torch.bfloat16) for k, v in O.synth_weights(O.dit_param_shapes(1), seed=4).items()}
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict(W, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe = QwenImagePhysicPipeline(device="cuda", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit.to("cuda").eval()
+    pipe.vae = m
+    A = {k: v.to(torch.bfloat16) for k, v in O.synth_weights(O.adapter_param_shapes(), seed=2).items()}
+    pipe.visual_thinking_adapter.load_state_dict(A)
+    pipe.visual_thinking_adapter.to(device="cuda", dtype=torch.bfloat16)
+    posi = O.synth_inputs(64, 96, 72, seed=6, dtype=torch.bfloat16)
+    nega = O.synth_inputs(64, 96, 69, seed=7, dtype=torch.bfloat16)
+    keys = ("prompt_emb", "prompt_emb_mask", "special_token_mask")
+    rng = np.random.default_rng(0)
+    edit = Image.fromarray(rng.integers(0, 256, size=(64, 96, 3), dtype=np.uint8))
+    kw = dict(prompt_inputs_posi={k: posi[k].cuda() for k in keys}, prompt_inputs_nega={k: nega[k].cuda() for k in keys}, edit_image=edit,
+              height=64, width=96, seed=3, num_inference_steps=2, is_train=False)
+    img = pipe(**kw)
+    nat.check_async()
+    assert isinstance(img, Image.Image) and img.size == (96, 64)
+    lat = pipe(output_type="latent", **{k: (v if not isinstance(v, dict) else {a: b.clone() for a, b in v.items()}) for k, v in kw.items()})
+    assert lat.shape == (1, 16, 8, 12) and torch.isfinite(lat.float()).all()
+    # the edit latents the call used are the VAE encoding of the pre-processed image (qwen_image_physical.py:1271-1273)
+    enc = m.encode(pipe.preprocess_image(edit))
+    want = VO.encode({k: v.float() for k, v in vae[1].items()}, pipe.preprocess_image(edit).float().cpu())
+    assert rel_l2(enc, want) <= 2.0e-2

@@ -63,3 +63,20 @@ def test_host_logic_decode_and_encode_match_reference(golden, model):
         assert err_e <= floor_e * 1.5 + 1e-3, (key, err_e, floor_e)
         kinds = {k for k, _ in emu.calls}
         assert {"pe_conv2d", "pe_gemm", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_softmax_rows", "pe_transpose"} <= kinds
+
+
+def test_load_vae_by_registry_hash(tmp_path, capsys):
+    """configs/model_config.py:24: the VAE checkpoint is recognised by its key/shape hash; anything else prints and returns None
+    (model_manager.py:375-376)."""
+    from physicedit_b200.pipeline import VAE_KEY_HASH, hash_state_dict_keys, load_vae
+    W = {k: v.to(torch.bfloat16) for k, v in VO.vae_synth_weights(seed=21).items()}
+    assert hash_state_dict_keys(W) == VAE_KEY_HASH == "ed4ea5824d55ec3107b09815e318123a"
+    good = tmp_path / "vae.pt"
+    torch.save(W, good)
+    m = load_vae(str(good), torch_dtype=torch.bfloat16, device="cpu")
+    assert isinstance(m, V.QwenImageVAE) and m.decoder.conv_out.weight.shape == (3, 96, 3, 3, 3)
+    assert torch.equal(m.decoder.conv_out.weight, W["decoder.conv_out.weight"])
+    bad = tmp_path / "other.pt"
+    torch.save({"x.weight": torch.zeros(2, 2)}, bad)
+    assert load_vae(str(bad), device="cpu") is None
+    assert "cannot detect the model type" in capsys.readouterr().out
