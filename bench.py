@@ -328,11 +328,63 @@ def run_native(args):
                 "steps": e2e_steps},
         "gpu_launches": launches, "finite": finite, "clocks": clocks, "roofline": roof, "roofline_by_kernel": roofs, "kernel_time_share": shares,
     }
+    if not args.no_vae:
+        res["vae"] = vae_leg(device, H, W, ms / args.steps)
     if world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def vae_leg(device, H, W, ms_per_step):
+    """The step either side of the loop, outside the headline metric: native QwenImageVAE.encode of one HxW edit image from
+    pinned host memory and .decode of the final latents back to host, random-init weights of the real architecture.  With it the
+    per-image time of a 50-step edit (text encoder excluded) is encode + 50 steps + decode."""
+    from physicedit_b200 import native as nv
+    from physicedit_b200.vae import QwenImageVAE
+    nat = nv.Native.get(device.index or 0)
+    with torch.device("meta"):
+        vae = QwenImageVAE()
+    g = torch.Generator(device=device).manual_seed(0)
+    sd = {}
+    for k, v in vae.state_dict().items():
+        if k.endswith("gamma"):
+            t = 1 + 0.1 * torch.randn(v.shape, generator=g, device=device)
+        elif k.endswith("weight"):
+            t = (torch.rand(v.shape, generator=g, device=device) * 2 - 1) * 1.7 / (v.shape[1] * v.shape[-1] * v.shape[-2]) ** 0.5
+        else:
+            t = (torch.rand(v.shape, generator=g, device=device) * 2 - 1) * 0.05
+        sd[k] = t.to(torch.bfloat16)
+    vae.load_state_dict(sd, assign=True)
+    vae.eval()
+    img_h = (torch.rand(1, 3, H, W) * 2 - 1).to(torch.bfloat16).pin_memory()
+    lat = torch.randn(1, 16, H // 8, W // 8, device=device).to(torch.bfloat16)
+    out_h = torch.empty(1, 3, H, W, dtype=torch.bfloat16).pin_memory()
+    times = {}
+    for name in ("encode", "decode"):
+        def run():
+            if name == "encode":
+                return vae.encode(img_h.to(device, non_blocking=True))
+            out_h.copy_(vae.decode(lat), non_blocking=True)
+            return out_h
+        for _ in range(2):
+            run()
+        nat.check_async()
+        n0 = nat.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            r = run()
+        e1.record()
+        torch.cuda.synchronize(device)
+        times[name] = {"ms": round(e0.elapsed_time(e1) / 5, 3), "launches": (nat.launches - n0) // 5, "finite": bool(torch.isfinite(r.float()).all())}
+    per_image_ms = times["encode"]["ms"] + 50 * ms_per_step + times["decode"]["ms"]
+    return {"what": f"QwenImageVAE encode (host image -> latents) / decode (latents -> host image) at {H}x{W}, native path, outside the headline metric",
+            "encode": times["encode"], "decode": times["decode"],
+            "image_50_steps": {"ms": round(per_image_ms, 1), "images_per_sec_per_gpu": round(1e3 / per_image_ms, 5),
+                               "vae_share": round((times["encode"]["ms"] + times["decode"]["ms"]) / per_image_ms, 5),
+                               "note": "encode + 50 x ms_per_step + decode; text encoder not included (SURVEY 8f2)"}}
 
 
 def cpu_baseline(args, blocks=1):
@@ -401,6 +453,7 @@ def main():
                     help="latency mode: one image per pair of GPUs (positive branch on the even rank, negative on the odd one); needs an even --gpus")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", dest="no_vae", action="store_true", help="skip the VAE encode/decode leg (reported beside, not inside, the metric)")
     ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=8, help="cap on timed CPU samples of --impl reference")
     ap.add_argument("--warmup-ref", dest="warmup_ref", type=int, default=2, help="cap on warm-up CPU samples of --impl reference")
     args = ap.parse_args()

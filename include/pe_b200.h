@@ -211,8 +211,11 @@ typedef struct pe_conv2d_desc {
     const void* gate;   /* PE_EPI_GATE_RESIDUAL: bf16 [N]                                    */
     int32_t H, W, C, N;
     int32_t kh, kw, pad;
-    int32_t _pad0;
+    int32_t flags;      /* PE_CONV_FLAG_*                                                   */
 } pe_conv2d_desc;
+#define PE_CONV_FLAG_TILE_W_LOG2(n) (((n) & 7) << 4)   /* explicit pixel-patch width 2^n (3..7; patch height 128 >> n); 0 = automatic */
+#define PE_CONV_FLAG_CTA_PAIR 1   /* cta_group::2: a tile is two stacked 128-pixel patches on an SM pair, each CTA loads half of the
+                                     weight rows (halves the L2 -> SM weight traffic that bounds the narrow layers) */
 int pe_conv2d(pe_handle_t h, const pe_conv2d_desc* desc, int epilogue, void* stream);
 
 /* QwenImageRMS_norm (:76-78) over the channels of every pixel, optionally followed by nn.SiLU:

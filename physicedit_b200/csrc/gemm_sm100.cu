@@ -18,6 +18,7 @@
 // ApproximateGELU (DiffSynth-Studio/diffsynth/models/qwen_image_dit.py:42-49,228-316), the
 // gate/residual adds of QwenImageTransformerBlock.forward (:386-399), RMSNorm (models/utils.py:241-257),
 // apply_rotary_emb_qwen (qwen_image_dit.py:51-57) and the three torch.cat's (:304-306).
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "common.cuh"
 
@@ -30,6 +31,8 @@ constexpr int kUmmaK = 16;
 constexpr int kTileN = 256;
 constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
+constexpr int kMaxStages = 12;
+constexpr int kTileRegionBytes = 224 << 10;   // operand ring; full-width tiles use 192 KB of it: 4 x 48 KB (one CTA, 256 W rows) or 6 x 32 KB (CTA pair)
 constexpr int kPanelBytes = 32 << 20;   // rasterisation: the m-tiles of a group share a sweep over n; their A panel (<= 32 MB) stays in the 126 MB L2
 
 struct SegDev {
@@ -70,16 +73,28 @@ struct GemmParams {
     int tiles_x;
     int tile_w_log2;
     int trim_n;            // issue the MMAs of a ragged last n-tile with N = round_up(N - n0, 16) instead of 256
+    int num_stages;        // depth of the TMA -> MMA ring: the 192 KB tile region divided by the stage size (4 / 6 for 256-column tiles, up to
+                           // kMaxStages for narrow layers, whose loads are latency- rather than bandwidth-bound)
+    int stage_smem_bytes;  // shared-memory pitch of one stage: 16 KB A box + W box rounded up to 1 KB
     int stage_tx_bytes;    // bytes one pipeline stage receives (A box + W box): the W box has only round_up(N, 16) rows for narrow layers
     unsigned int* abort_flag;
 };
 
-// (y0, x0) of the output-pixel patch that m-tile `m0 / 128` covers
-__device__ __forceinline__ void conv_tile_origin(const GemmParams& p, int m0, int& y0, int& x0) {
-    const int mt = m0 >> 7;
+// (y0, x0) of the 128-pixel patch this CTA owns inside m-tile `m0 / kTileM`: a tile is one patch (kTileM = 128) or, on a CTA pair
+// (kTileM = 256), two vertically stacked patches, the lower one belonging to CTA rank 1
+template <int kTileM>
+__device__ __forceinline__ void conv_tile_origin(const GemmParams& p, int m0, int cta_rank, int& y0, int& x0) {
+    const int mt = m0 / kTileM;
     const int ty = mt / p.tiles_x;
-    y0 = ty << (7 - p.tile_w_log2);
+    const int tile_h = 128 >> p.tile_w_log2;
+    y0 = ty * tile_h * (kTileM / 128) + cta_rank * tile_h;
     x0 = (mt - ty * p.tiles_x) << p.tile_w_log2;
+}
+
+// columns of the n-tile at n0 that the MMAs cover: 256, or for a ragged last tile of a narrow layer round_up(N - n0, 16)
+__device__ __forceinline__ int tile_n_cols(const GemmParams& p, int n0) {
+    const int n_left = p.N - n0;
+    return (p.trim_n && n_left < kTileN) ? ((n_left + 15) & ~15) : kTileN;
 }
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
@@ -253,18 +268,17 @@ __device__ __forceinline__ void epilogue_qkv_head(uint32_t taddr_head, const Seg
 
 template <int kCG, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-    constexpr int kStages = kCG == 1 ? 4 : 6;
+    constexpr int kStages = kMaxStages;         // barrier slots; p.num_stages of them are in use
     constexpr int kABytes = 128 * kBlockK * 2;
-    constexpr int kBRows = kCG == 1 ? 256 : 128;
-    constexpr int kBBytes = kBRows * kBlockK * 2;
-    constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kTileM = 128 * kCG;
+    const int num_stages = p.num_stages;
+    const uint32_t stage_pitch = (uint32_t)p.stage_smem_bytes;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;
-    auto a_smem = [&](int s) { return smem_base + s * kStageBytes; };
-    auto b_smem = [&](int s) { return smem_base + s * kStageBytes + kABytes; };
+    const uint32_t bar_base = smem_base + kTileRegionBytes;
+    auto a_smem = [&](int s) { return smem_base + s * stage_pitch; };
+    auto b_smem = [&](int s) { return smem_base + s * stage_pitch + kABytes; };
     auto full_bar = [&](int s) { return bar_base + s * 8; };
     auto empty_bar = [&](int s) { return bar_base + (kStages + s) * 8; };
     auto tfull_bar = [&](int s) { return bar_base + (2 * kStages + s) * 8; };
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
     }
     if (warp == 1 && elect_one()) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < num_stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -312,34 +326,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const Tile tile = decode_tile<kTileM>(p, t);
             const SegDev& sg = p.seg[tile.seg];
             int cy0 = 0, cx0 = 0;
-            if (kCG == 1 && p.conv) conv_tile_origin(p, tile.m0, cy0, cx0);
+            if (p.conv) conv_tile_origin<kTileM>(p, tile.m0, (int)cta_rank, cy0, cx0);
+            // tap (dy, dx), channel block of k-block kb: the CTA's pixel patch shifted by the tap; pixels outside the map (negative or
+            // >= H / W coordinates) and channels >= C are zero-filled by the TMA unit.  The coordinates advance incrementally: this warp's
+            // serial instruction chain per k-block is what bounds the narrow layers (r1: two integer divisions here cost ~350 cycles per
+            // k-block, more than the MMAs of a 96-column tile -- profiles/r01_vae_conv.md)
+            int cc = 0, cx = cx0 - p.conv_pad, cy = cy0 - p.conv_pad, ctap_x = 0;
+            const int b_row = kCG == 1 ? tile.n0 : tile.n0 + (int)cta_rank * (tile_n_cols(p, tile.n0) >> 1);   // a pair's CTAs supply half of the rows each
+            const int a_row = tile.m0 + (int)cta_rank * 128;
+            const uint32_t fb = kCG == 1 ? 0u : mapa(full_bar(0), 0);      // a pair's bytes are all accounted on the leader's barriers
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 if (!mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_flag, 1)) { ok = false; break; }
                 if (elect_one()) {
                     if (kCG == 1) {
                         mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx_bytes);
-                        if (p.conv) {
-                            // tap (dy, dx), channel block cb: the [tile_h x tile_w] pixel patch shifted by the tap; pixels outside the
-                            // map (negative or >= H / W coordinates) and channels >= C are zero-filled by the TMA unit
-                            const int tap = kb / p.kb_per_tap;
-                            const int cb = kb - tap * p.kb_per_tap;
-                            const int dy = tap / p.conv_kw;
-                            const int dx = tap - dy * p.conv_kw;
-                            tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cb * kBlockK, cx0 + dx - p.conv_pad, cy0 + dy - p.conv_pad);
-                        } else {
-                            tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, tile.m0);
-                        }
-                        tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, tile.n0);
+                        if (p.conv) tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cc, cx, cy);
+                        else tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, a_row);
+                        tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, b_row);
                     } else {
-                        // both CTAs' bytes are accounted on the leader's barrier
-                        const uint32_t fb = mapa(full_bar(stage), 0);
-                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
-                        tma_load_2d_cg2(a_smem(stage), &sg.tmA, fb, kb * kBlockK, tile.m0 + (int)cta_rank * 128);
-                        tma_load_2d_cg2(b_smem(stage), &sg.tmB, fb, kb * kBlockK, tile.n0 + (int)cta_rank * 128);
+                        const uint32_t fbs = fb + stage * 8;
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx_bytes);
+                        if (p.conv) tma_load_3d_cg2(a_smem(stage), &sg.tmA, fbs, cc, cx, cy);
+                        else tma_load_2d_cg2(a_smem(stage), &sg.tmA, fbs, kb * kBlockK, a_row);
+                        tma_load_2d_cg2(b_smem(stage), &sg.tmB, fbs, kb * kBlockK, b_row);
+                    }
+                }
+                if (p.conv) {
+                    cc += kBlockK;
+                    if (cc >= p.kb_per_tap * kBlockK) {          // next tap
+                        cc = 0;
+                        ++cx;
+                        if (++ctap_x == p.conv_kw) { ctap_x = 0; cx -= p.conv_kw; ++cy; }
                     }
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                if (++stage == num_stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -356,10 +377,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTileN;
                 uint32_t idesc = idesc_full;
-                if (kCG == 1 && p.trim_n) {
+                if (p.trim_n) {
                     // narrow layers (96 / 192 / 384 conv channels): do not multiply the zero-filled weight rows of a ragged n-tile
-                    const int n_left = p.N - decode_tile<kTileM>(p, t).n0;
-                    if (n_left < kTileN) idesc = make_idesc_bf16(kTileM, (uint32_t)((n_left + 15) & ~15), 0, 0);
+                    const int n_cols = tile_n_cols(p, decode_tile<kTileM>(p, t).n0);
+                    if (n_cols < kTileN) idesc = make_idesc_bf16(kTileM, (uint32_t)n_cols, 0, 0);
                 }
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     if (!mbar_wait(full_bar(stage), phase, p.abort_flag, 3)) { ok = false; break; }
@@ -378,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         }
                     }
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
@@ -399,9 +420,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kTileN;
             long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
             bool row_valid = row < sg.M;
-            if (kCG == 1 && p.conv) {
+            if (p.conv) {
                 int cy0, cx0;
-                conv_tile_origin(p, tile.m0, cy0, cx0);
+                conv_tile_origin<kTileM>(p, tile.m0, (int)cta_rank, cy0, cx0);
                 const int r = ew * 32 + lane;
                 const int yy = cy0 + (r >> p.tile_w_log2);
                 const int xx = cx0 + (r & ((1 << p.tile_w_log2) - 1));
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
 template <int kCG>
 constexpr int gemm_smem_bytes() {
-    return 1024 /*alignment slack*/ + (kCG == 1 ? 4 * (16384 + 32768) : 6 * (16384 + 16384)) + 256;
+    return 1024 /*alignment slack*/ + kTileRegionBytes + 256 /*barriers: (2 * kMaxStages + 4) * 8 + TMEM slot*/;
 }
 
 template <int kCG, int EPI>
@@ -492,6 +513,20 @@ int dispatch_epilogue(Handle* h, const GemmParams& p, int epilogue, cudaStream_t
 
 }  // namespace
 
+// Ring geometry for a launch whose CTAs each receive a 16 KB A box and a `b_rows_per_cta`-row W box per stage.
+static void set_ring(GemmParams& p, int cg, int b_rows_per_cta) {
+    const int b_bytes = b_rows_per_cta * kBlockK * 2;
+    p.stage_smem_bytes = 128 * kBlockK * 2 + ((b_bytes + 1023) & ~1023);
+    p.num_stages = kTileRegionBytes / p.stage_smem_bytes;
+    if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+    if (b_rows_per_cta * cg == kTileN) p.num_stages = cg == 1 ? 4 : 6;   // the DiT's full-width GEMMs: the ring they were tuned and profiled with
+    if (const char* e = getenv("PE_GEMM_MAX_STAGES")) {          // tuning aid: cap the ring depth
+        const int cap = atoi(e);
+        if (cap >= 2 && cap < p.num_stages) p.num_stages = cap;
+    }
+    p.stage_tx_bytes = cg * (128 * kBlockK * 2 + b_bytes);       // a pair's boxes all land on the leader's barrier
+}
+
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream) {
     PE_REQUIRE(h, nseg >= 1 && nseg <= 2, "pe_gemm: nseg must be 1 or 2 (got %d)", nseg);
     PE_REQUIRE(h, N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "pe_gemm: N and K must be positive multiples of 8 (N=%d K=%d)", N, K);
@@ -511,7 +546,7 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
     }
     // narrow layers (PE_GEMM_FLAG_TRIM_N, N < 256): the W box has only round_up(N, 16) rows, so no zero-filled rows are written to shared memory
     const int b_box_rows = ((flags & PE_GEMM_FLAG_TRIM_N) && N < kTileN) ? ((N + 15) & ~15) : kTileN;
-    p.stage_tx_bytes = 128 * kBlockK * 2 + b_box_rows * kBlockK * 2;
+    set_ring(p, cg, b_box_rows / cg);
     int total_m_tiles = 0;
     for (int s = 0; s < nseg; ++s) {
         const pe_gemm_seg& in = segs[s];
@@ -525,7 +560,7 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         SegDev& d = p.seg[s];
         int rc = make_tmap_2d(h, &d.tmA, in.a, (uint64_t)in.M, (uint64_t)K, (uint64_t)in.lda, 128);
         if (rc) return rc;
-        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? (uint32_t)b_box_rows : 128u);
+        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? (uint32_t)b_box_rows : (uint32_t)(b_box_rows >> 1));
         if (rc) return rc;
         d.bias = static_cast<const bf16*>(in.bias);
         d.out = static_cast<bf16*>(in.out);
@@ -594,6 +629,8 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     p.conv_H = d->H;
     p.conv_W = d->W;
     p.tile_w_log2 = d->W > 8 ? 4 : 3;             // 8 x 16 pixel patches (16 x 8 for maps narrower than 9 pixels)
+    if ((d->flags >> 4) & 7) p.tile_w_log2 = (d->flags >> 4) & 7;      // PE_CONV_FLAG_TILE_W_LOG2(n): explicit patch width 2^n (tuning / tests)
+    const int cg = (d->flags & PE_CONV_FLAG_CTA_PAIR) ? 2 : 1;   // CTA pair: two stacked patches per tile, each CTA loads half of the weights
     const int tile_w = 1 << p.tile_w_log2, tile_h = 128 >> p.tile_w_log2;
     p.tiles_x = ceil_div(d->W, tile_w);
     p.trim_n = 1;
@@ -601,8 +638,11 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     int rc = make_tmap_3d(h, &sd.tmA, d->x, (uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->ldx, (uint64_t)d->ldx * d->W,
                           64, (uint32_t)tile_w, (uint32_t)tile_h);
     if (rc) return rc;
-    const int b_box_rows = d->N < kTileN ? ((d->N + 15) & ~15) : kTileN;
-    p.stage_tx_bytes = 128 * kBlockK * 2 + b_box_rows * kBlockK * 2;
+    // W box: the rows one CTA supplies -- the whole (narrow) n-tile, or half of it on a CTA pair; never zero-filled rows, which would
+    // still cost L2 -> SM bandwidth (ncu: l1tex__m_xbar2l1tex_read_bytes counts the full box)
+    const int n_tile_rows = d->N < kTileN ? ((d->N + 15) & ~15) : kTileN;
+    const int b_box_rows = n_tile_rows / cg;
+    set_ring(p, cg, b_box_rows);
     rc = make_tmap_2d(h, &sd.tmB, d->w, (uint64_t)d->N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)b_box_rows);
     if (rc) return rc;
     sd.bias = static_cast<const bf16*>(d->bias);
@@ -610,17 +650,18 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     sd.gate = static_cast<const bf16*>(d->gate);
     sd.ldo = d->ldo;
     sd.M = d->H * d->W;
-    sd.m_tiles = p.tiles_x * ceil_div(d->H, tile_h);
+    sd.m_tiles = p.tiles_x * ceil_div(d->H, tile_h * cg);
     p.total_m_tiles = sd.m_tiles;
     {
-        const long long tile_row_bytes = (long long)128 * p.K * 2;
+        const long long tile_row_bytes = (long long)128 * cg * p.K * 2;
         int gm_max = (int)(kPanelBytes / tile_row_bytes);
         if (gm_max < 1) gm_max = 1;
         const int groups = ceil_div(p.total_m_tiles, gm_max);
         p.group_m = ceil_div(p.total_m_tiles, groups);
     }
     p.num_tiles = p.total_m_tiles * p.num_n;
-    return dispatch_epilogue<1>(h, p, epilogue, stream);
+    if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
+    return dispatch_epilogue<2>(h, p, epilogue, stream);
 }
 
 }  // namespace pe

@@ -170,6 +170,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst_smem, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // 1-D bulk copy global -> this CTA's smem (no tensor map): `bytes` and both addresses multiples of 16; completes tx-bytes on `bar`
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

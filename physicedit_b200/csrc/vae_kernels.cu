@@ -46,13 +46,14 @@ __device__ __forceinline__ void round_pair(float& a, float& b) {
     a = __uint_as_float(p << 16);
     b = __uint_as_float(p & 0xffff0000u);
 }
-template <int kGroup, int kVec>
-__global__ void __launch_bounds__(kWarps * 32) channel_rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
+template <int kGroup, int kVec, int kUnroll>
+__global__ void __launch_bounds__(kWarps * 32, 4) channel_rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
                                                                        long long rows, int C, const bf16* __restrict__ gamma, float scale, int act) {
     constexpr int kRowsPerWarp = 32 / kGroup;
+    constexpr int kRowsPerIter = kRowsPerWarp * kUnroll;   // kUnroll independent rows per lane group: their loads are all in flight together
     const int lane = threadIdx.x & 31;
     const int gl = lane & (kGroup - 1);                 // lane inside its row group
-    const int sub = lane / kGroup;                      // which of the warp's rows
+    const int sub = lane / kGroup;                      // which of the warp's concurrent rows
     const int nvec = C >> 3;
     float g[kVec][8];
 #pragma unroll
@@ -62,49 +63,57 @@ __global__ void __launch_bounds__(kWarps * 32) channel_rmsnorm_kernel(const bf16
     }
     const long long warp_id = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const long long warp_stride = (long long)gridDim.x * kWarps;
-    for (long long r0 = warp_id * kRowsPerWarp; r0 < rows; r0 += warp_stride * kRowsPerWarp) {
-        const long long row = r0 + sub;
-        const bool live = row < rows;
-        const bf16* xr = x + row * ldx;
-        float v[kVec][8];
-        float ss = 0.f;
+    for (long long r0 = warp_id * kRowsPerIter; r0 < rows; r0 += warp_stride * kRowsPerIter) {
+        uint4 raw[kUnroll][kVec];
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) {
-            const int vi = gl + kGroup * i;
-            if (live && vi < nvec) {
-                unpack8v(*reinterpret_cast<const uint4*>(xr + vi * 8), v[i]);
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long row = r0 + u * kRowsPerWarp + sub;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+            for (int i = 0; i < kVec; ++i) {
+                const int vi = gl + kGroup * i;
+                raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
+                if (row < rows && vi < nvec) raw[u][i] = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
             }
         }
 #pragma unroll
-        for (int o = kGroup / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        // x / n as x * (1 / n): one reciprocal per pixel instead of an IEEE division per element (the two differ by <= 1 fp32 ulp, i.e. the
-        // bf16 result differs for ~2^-15 of the elements, by one bf16 ulp)
-        const float rn = __frcp_rn(fmaxf(bf16_round(sqrtf(ss)), 1e-12f));
-        bf16* orow = out + row * ldo;
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long row = r0 + u * kRowsPerWarp + sub;
+            float v[kVec][8];
+            float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) {
-            const int vi = gl + kGroup * i;
-            if (live && vi < nvec) {
-                float o[8];
+            for (int i = 0; i < kVec; ++i) {
+                unpack8v(raw[u][i], v[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rn;
+                for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+            }
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+            for (int o = kGroup / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            // x / n as x * (1 / n): one reciprocal per pixel instead of an IEEE division per element (the two differ by <= 1 fp32 ulp, i.e.
+            // the bf16 result differs for ~2^-15 of the elements, by one bf16 ulp)
+            const float rn = __frcp_rn(fmaxf(bf16_round(sqrtf(ss)), 1e-12f));
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] *= scale;
+            for (int i = 0; i < kVec; ++i) {
+                const int vi = gl + kGroup * i;
+                if (row < rows && vi < nvec) {
+                    float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] *= g[i][j];
-                if (act) {
+                    for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rn;
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-o[j]));
+                    for (int j = 0; j < 8; ++j) o[j] *= scale;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] *= g[i][j];
+                    if (act) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) round_pair(o[j], o[j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-o[j]));
+                    }
+                    *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) = pack8v(o);
                 }
-                *reinterpret_cast<uint4*>(orow + vi * 8) = pack8v(o);
             }
         }
     }
@@ -229,15 +238,16 @@ int channel_rmsnorm_run(Handle* h, const void* x, int64_t ldx, void* out, int64_
     PE_REQUIRE(h, ldx % 8 == 0 && ldo % 8 == 0 && ldx >= C && ldo >= C, "pe_channel_rmsnorm: row strides must be multiples of 8 and >= C");
     const float scale = (float)sqrt((double)C);                 // self.scale = dim ** 0.5, applied as an fp32 scalar
     const int group = C <= 128 ? 16 : 32;
-    long long blocks = (rows + kWarps * (32 / group) - 1) / (kWarps * (32 / group));
+    const int rows_per_iter = (32 / group) * (C <= 256 ? 4 : 2);
+    long long blocks = (rows + kWarps * rows_per_iter - 1) / (kWarps * rows_per_iter);
     const long long cap = (long long)h->sm_count * 8;
     if (blocks > cap) blocks = cap;
     const bf16* xp = static_cast<const bf16*>(x);
     bf16* op = static_cast<bf16*>(out);
     const bf16* gp = static_cast<const bf16*>(gamma);
-    if (C <= 128) channel_rmsnorm_kernel<16, 1><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
-    else if (C <= 256) channel_rmsnorm_kernel<32, 1><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
-    else channel_rmsnorm_kernel<32, 2><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
+    if (C <= 128) channel_rmsnorm_kernel<16, 1, 4><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
+    else if (C <= 256) channel_rmsnorm_kernel<32, 1, 4><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
+    else channel_rmsnorm_kernel<32, 2, 2><<<(int)blocks, kWarps * 32, 0, s>>>(xp, ldx, op, ldo, rows, C, gp, scale, act);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

@@ -26,6 +26,7 @@ EPI_BIAS_SILU = 6
 EPI_F32 = 7
 GEMM_FLAG_CTA_PAIR = 1
 GEMM_FLAG_TRIM_N = 2
+CONV_FLAG_CTA_PAIR = 1
 ATTN_FLAG_SINGLE_Q_TILE = 1
 ATTN_FLAG_P_VIA_SMEM = 2
 ATTN_FLAG_SPLIT_ROW_SOFTMAX = 8
@@ -62,7 +63,7 @@ class Conv2dDesc(Structure):
     """Mirror of `pe_conv2d_desc` (include/pe_b200.h)."""
     _fields_ = [
         ("x", c_void_p), ("ldx", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("gate", c_void_p),
-        ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("kh", c_int32), ("kw", c_int32), ("pad", c_int32), ("_pad0", c_int32),
+        ("H", c_int32), ("W", c_int32), ("C", c_int32), ("N", c_int32), ("kh", c_int32), ("kw", c_int32), ("pad", c_int32), ("flags", c_int32),
     ]
 
 
@@ -327,7 +328,8 @@ class Native:
         self.launches += 1
 
     # ---- QwenImageVAE path (include/pe_b200.h, last section) -----------------------------------------------------------------
-    def conv2d(self, x, H: int, W: int, C: int, w, bias, out, N: int, kh: int, kw: int, pad: int, epilogue: int = EPI_BIAS, gate=None) -> None:
+    def conv2d(self, x, H: int, W: int, C: int, w, bias, out, N: int, kh: int, kw: int, pad: int, epilogue: int = EPI_BIAS, gate=None,
+               flags: int = 0) -> None:
         """x: [H*W, >=C] channels-last map, w: [N, kh*kw*round_up(C,64)], out: [H*W, >=N]; stride 1, same output size."""
         _bf16(x, "x"); _bf16(w, "w"); _bf16(out, "out")
         if x.shape[0] != H * W or out.shape[0] != H * W or not w.is_contiguous():
@@ -336,7 +338,7 @@ class Native:
         if w.shape[0] != N or w.shape[1] != kh * kw * cpad:
             raise NativeError(f"conv2d: w must be [{N}, {kh * kw * cpad}], got {tuple(w.shape)}")
         d = Conv2dDesc(x=x.data_ptr(), ldx=x.stride(0), w=w.data_ptr(), bias=_ptr(bias), out=out.data_ptr(), ldo=out.stride(0), gate=_ptr(gate),
-                       H=H, W=W, C=C, N=N, kh=kh, kw=kw, pad=pad)
+                       H=H, W=W, C=C, N=N, kh=kh, kw=kw, pad=pad, flags=flags)
         self._check(self.lib.pe_conv2d(self.h, byref(d), epilogue, self._stream_prof()), "pe_conv2d")
         self.launches += 1
 

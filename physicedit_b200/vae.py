@@ -30,6 +30,7 @@ LATENT_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.55
 LATENT_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251,
               1.9160]
 
+_PAIR_MIN_PIXELS = 16384      # >= 64 CTA-pair tiles of 256 pixels
 _ATTN_QUERY_CHUNK = 8192      # query rows per score block: 8192 x S fp32 scores (512 MB at S = 16384)
 
 
@@ -276,12 +277,15 @@ class QwenImageVAE(nn.Module):
         elif out is None:                       # narrow output inside a zero-padded `ldo`-wide map (feeds a K = ldo layer)
             out = torch.zeros((H * W, ldo), dtype=torch.bfloat16, device=x.device)
         nat.tag = f"vae_conv{kh}x{kw}_{H}x{W}_{cin}to{n8}"
+        # maps with enough tiles to fill the GPU run on CTA pairs (cta_group::2): each CTA loads half of the weight rows, which halves
+        # the L2 -> SM weight traffic that bounds these narrow (96 / 192 / 384 channel) layers
+        pair = H * W >= _PAIR_MIN_PIXELS
         if kh == 1 and kw == 1:
             nat.gemm([dict(a=x, w=w2d, bias=b, out=out, gate=P["ones"] if residual else None)], n8, w2d.shape[1],
-                     nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N)
+                     nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N | (nv.GEMM_FLAG_CTA_PAIR if pair else 0))
         else:
             nat.conv2d(x, H, W, cin, w2d, b, out, n8, kh, kw, 1 if kh == 3 else 0, nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS,
-                       gate=P["ones"] if residual else None)
+                       gate=P["ones"] if residual else None, flags=nv.CONV_FLAG_CTA_PAIR if pair else 0)
         return out
 
     @staticmethod

@@ -44,7 +44,7 @@ class EmulatedNative:
             out[:, :N] = y.to(torch.bfloat16)
         self._note("pe_gemm")
 
-    def conv2d(self, x, H, W, C, w, bias, out, N, kh, kw, pad, epilogue=EPI_BIAS, gate=None):
+    def conv2d(self, x, H, W, C, w, bias, out, N, kh, kw, pad, epilogue=EPI_BIAS, gate=None, flags=0):
         cpad = (C + 63) // 64 * 64
         assert x.shape[0] == H * W and x.stride(0) >= C and w.shape == (N, kh * kw * cpad) and N % 8 == 0 and C % 8 == 0
         xm = x[:, :C].float().reshape(H, W, C).permute(2, 0, 1).unsqueeze(0)

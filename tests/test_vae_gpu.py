@@ -52,6 +52,7 @@ def _rand(shape, seed, scale=1.0):
 
 
 @gpu
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("H,W,C,N,kh,kw,pad,ld_extra,residual", [
     (13, 21, 96, 96, 3, 3, 1, 0, False),      # ragged patch grid, C not a multiple of 64, trimmed n-tile
     (16, 16, 64, 384, 3, 3, 1, 0, False),     # two n-tiles (256 + 128)
@@ -61,7 +62,7 @@ def _rand(shape, seed, scale=1.0):
     (7, 5, 64, 16, 3, 3, 1, 64 - 16, False),  # narrow output inside a wider map (ldo > N), tiny map
     (40, 56, 96, 192, 3, 3, 1, 0, True),      # several m-tiles per row and column
 ])
-def test_conv2d_matches_contract(nat, emu, H, W, C, N, kh, kw, pad, ld_extra, residual):
+def test_conv2d_matches_contract(nat, emu, H, W, C, N, kh, kw, pad, ld_extra, residual, pair):
     cpad = (C + 63) // 64 * 64
     x = _rand((H * W, C), 1 + H)
     w = _rand((N, kh * kw * cpad), 2 + W, scale=(kh * kw * C) ** -0.5)
@@ -72,7 +73,7 @@ def test_conv2d_matches_contract(nat, emu, H, W, C, N, kh, kw, pad, ld_extra, re
     want = out0.clone()
     emu.conv2d(x, H, W, C, w, b, want, N, kh, kw, pad, epi, gate=gate if residual else None)
     got = out0.clone().cuda()
-    nat.conv2d(x.cuda(), H, W, C, w.cuda(), b.cuda(), got, N, kh, kw, pad, epi, gate=gate.cuda() if residual else None)
+    nat.conv2d(x.cuda(), H, W, C, w.cuda(), b.cuda(), got, N, kh, kw, pad, epi, gate=gate.cuda() if residual else None, flags=pair)
     nat.check_async()
     assert_within_one_ulp(got[:, :N], want[:, :N], "conv2d", floor=4.0 if residual else 1e-30)
     assert rel_l2(got[:, :N], want[:, :N]) < 2e-3
@@ -81,20 +82,21 @@ def test_conv2d_matches_contract(nat, emu, H, W, C, N, kh, kw, pad, ld_extra, re
 
 
 @gpu
-@pytest.mark.parametrize("M,N,K", [(300, 384, 384), (77, 64, 96), (1000, 1048, 384), (130, 16, 64)])
-def test_gemm_trim_n_and_f32_epilogue(nat, emu, M, N, K):
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(300, 384, 384), (77, 64, 96), (1000, 1048, 384), (130, 16, 64), (600, 96, 192)])
+def test_gemm_trim_n_and_f32_epilogue(nat, emu, M, N, K, pair):
     from physicedit_b200 import native as nv
     a, w, b = _rand((M, K), 5), _rand((N, K), 6, K ** -0.5), _rand((N,), 7, 0.1)
     want = torch.empty((M, N), dtype=torch.bfloat16)
     emu.gemm([dict(a=a, w=w, bias=b, out=want)], N, K, 0)
     got = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
-    nat.gemm([dict(a=a.cuda(), w=w.cuda(), bias=b.cuda(), out=got)], N, K, nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N)
+    nat.gemm([dict(a=a.cuda(), w=w.cuda(), bias=b.cuda(), out=got)], N, K, nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N | pair)
     nat.check_async()
     assert_within_one_ulp(got, want, "gemm trim_n")
     wantf = torch.empty((M, N), dtype=torch.float32)
     emu.gemm([dict(a=a, w=w, bias=None, out=wantf)], N, K, 7)
     gotf = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
-    nat.gemm([dict(a=a.cuda(), w=w.cuda(), bias=None, out=gotf)], N, K, nv.EPI_F32, nv.GEMM_FLAG_TRIM_N)
+    nat.gemm([dict(a=a.cuda(), w=w.cuda(), bias=None, out=gotf)], N, K, nv.EPI_F32, nv.GEMM_FLAG_TRIM_N | pair)
     nat.check_async()
     assert torch.allclose(gotf.cpu(), wantf, rtol=1e-4, atol=1e-4), (gotf.cpu() - wantf).abs().max()
 
