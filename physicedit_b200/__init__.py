@@ -24,6 +24,7 @@ _LAZY = {
     "VisualThinkingDualAdapter": ("adapters", "VisualThinkingDualAdapter"),
     "adopt_dit": ("compat", "adopt_dit"),
     "adopt_adapter": ("compat", "adopt_adapter"),
+    "adopt_vae": ("compat", "adopt_vae"),
 }
 
 

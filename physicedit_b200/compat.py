@@ -1,6 +1,6 @@
 """Glue for running the reference's own scripts / pipeline objects on the native path.
 
-* `adopt_dit(ref_dit)` / `adopt_adapter(ref_adapter)`: wrap modules that the REFERENCE loaded (its ModelManager, LoRA loader,
+* `adopt_dit(ref_dit)` / `adopt_adapter(ref_adapter)` / `adopt_vae(ref_vae)`: wrap modules that the REFERENCE loaded (its ModelManager, LoRA loader,
   `load_state_dict(strict=False)`) into the native classes without copying weights (`load_state_dict(assign=True)`).
 * `install()`: registers a `diffsynth` alias package so that the imports used by scripts/inference/*.py and
   scripts/train/train_physicedit.py (`from diffsynth import load_state_dict`, `from diffsynth.pipelines.qwen_image_physical import
@@ -36,6 +36,15 @@ def adopt_adapter(ref_adapter: torch.nn.Module):
     return ad.eval()
 
 
+def adopt_vae(ref_vae: torch.nn.Module):
+    """The reference's loaded QwenImageVAE (models/qwen_image_vae.py:640) -> the native module on the same parameter storage."""
+    from .vae import QwenImageVAE
+    with torch.device("meta"):
+        vae = QwenImageVAE()
+    vae.load_state_dict(ref_vae.state_dict(), assign=True)
+    return vae.eval()
+
+
 @dataclass
 class ControlNetInput:
     """pipelines/flux_image_new.py:5-13 (only imported by the scripts; blockwise controlnet is out of scope)."""
@@ -49,7 +58,7 @@ class ControlNetInput:
 
 
 def install() -> None:
-    from . import pipeline, scheduler, lora, dit, adapters, model_fn
+    from . import pipeline, scheduler, lora, dit, adapters, model_fn, vae
 
     def mod(name, **attrs):
         m = types.ModuleType(name)
@@ -69,6 +78,7 @@ def install() -> None:
     mod("diffsynth.models").__path__ = []
     mod("diffsynth.models.qwen_image_dit", QwenImageDiT=dit.QwenImageDiT, QwenImageTransformerBlock=dit.QwenImageTransformerBlock,
         QwenEmbedRope=dit.QwenEmbedRope, RMSNorm=dit.RMSNorm)
+    mod("diffsynth.models.qwen_image_vae", QwenImageVAE=vae.QwenImageVAE, QwenImageVAEStateDictConverter=vae.QwenImageVAEStateDictConverter)
     mod("diffsynth.models.utils", load_state_dict=pipeline.load_state_dict, hash_state_dict_keys=pipeline.hash_state_dict_keys,
         RMSNorm=dit.RMSNorm, AdaLayerNorm=dit.AdaLayerNorm, TimestepEmbeddings=dit.TimestepEmbeddings)
     mod("diffsynth.schedulers").__path__ = []
