@@ -31,6 +31,31 @@ t = torch.randn(3, 3072, **bf); ta = torch.empty_like(t)
 nat.act(t, ta, 1)
 w = torch.randn(1030, 3072, **bf); y = torch.empty(3, 1030, **bf)
 nat.gemv(ta, w, torch.zeros(1030, **bf), y, 0, 0, None)
+# VAE path: implicit-GEMM conv (one CTA / CTA pair, ragged patches, trimmed n-tile, residual epilogue), narrow GEMM with the fp32 epilogue,
+# channel RMS-norm, layout kernels, softmax, transpose
+for pair in (0, 1):
+    H, W, C, N = 13, 21, 96, 96
+    x = torch.randn(H * W, C, **bf); w = torch.randn(N, 9 * 128, **bf) * 0.03; b = torch.randn(N, **bf)
+    out = torch.randn(H * W, N, **bf)
+    nat.conv2d(x, H, W, C, w, b, out, N, 3, 3, 1, nv.EPI_GATE_RESIDUAL, gate=torch.ones(N, **bf), flags=pair)
+    w2 = torch.randn(384, 4 * 384, **bf) * 0.03
+    x2 = torch.randn(12 * 20, 384, **bf); o2 = torch.empty(12 * 20, 384, **bf)
+    nat.conv2d(x2, 12, 20, 384, w2, torch.zeros(384, **bf), o2, 384, 2, 2, 0, nv.EPI_BIAS, flags=pair)
+    a = torch.randn(130, 96, **bf); wq = torch.randn(72, 96, **bf); sc = torch.empty(130, 72, device=dev, dtype=torch.float32)
+    nat.gemm([dict(a=a, w=wq, bias=None, out=sc)], 72, 96, nv.EPI_F32, nv.GEMM_FLAG_TRIM_N | pair)
+for C in (96, 192, 384):
+    x = torch.randn(333, C, **bf); o = torch.empty_like(x)
+    nat.channel_rmsnorm(x, o, C, torch.ones(C, **bf), True)
+x = torch.randn(10 * 14, 96, **bf)
+nat.upsample2x(x, torch.empty(4 * 140, 96, **bf), 10, 14, 96)
+nat.space_to_depth(x, torch.empty(35, 384, **bf), 10, 14, 96)
+lat = torch.randn(16, 6, 10, **bf); z = torch.zeros(60, 64, **bf); p0 = torch.randn(16, **bf); p1 = torch.rand(16, **bf) + 0.5
+nat.nchw_to_nhwc(lat, z, 16, 1, p0, p1)
+nat.nhwc_to_nchw(z, torch.empty(16, 6, 10, **bf), 16, 2, p0, p1)
+s32 = torch.randn(61, 64, device=dev); pr = torch.empty(61, 64, **bf)
+nat.softmax_rows(s32, pr, 61, 0.05)
+vt = torch.zeros(384, 64, **bf)
+nat.transpose(torch.randn(61, 384, **bf), vt[:, :61])
 nat.check_async()
 torch.cuda.synchronize()
 print("sanitize targets done")
