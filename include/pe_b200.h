@@ -214,6 +214,8 @@ typedef struct pe_conv2d_desc {
     int32_t flags;      /* PE_CONV_FLAG_*                                                   */
 } pe_conv2d_desc;
 #define PE_CONV_FLAG_TILE_W_LOG2(n) (((n) & 7) << 4)   /* explicit pixel-patch width 2^n (3..7; patch height 128 >> n); 0 = automatic */
+#define PE_CONV_FLAG_SINGLE_PATCH 2  /* N <= 128 on one CTA: do NOT pair two 128-pixel patches per tile (the default pairs them so that both
+                                        share every weight box and each k-block iteration carries twice the MMA work) */
 #define PE_CONV_FLAG_CTA_PAIR 1   /* cta_group::2: a tile is two stacked 128-pixel patches on an SM pair, each CTA loads half of the
                                      weight rows (halves the L2 -> SM weight traffic that bounds the narrow layers) */
 int pe_conv2d(pe_handle_t h, const pe_conv2d_desc* desc, int epilogue, void* stream);

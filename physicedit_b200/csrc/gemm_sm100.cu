@@ -49,7 +49,14 @@ struct SegDev {
     long long ldo;
     int M;
     int m_tiles;
+    int wide_store;   // out (and out_k / out_v) 32-byte aligned, ldo and N multiples of 16: a lane stores 32 bytes (a whole L2 sector) at a time
 };
+
+// one lane's 32-byte store (two packed 8 x bf16 groups, adjacent columns of its row)
+__device__ __forceinline__ void st_global_32B(void* dst, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 
 struct GemmParams {
     SegDev seg[2];
@@ -72,6 +79,10 @@ struct GemmParams {
     int conv_W;
     int tiles_x;
     int tile_w_log2;
+    int dual_m;            // narrow conv layers (N <= 128) on one CTA: a tile is TWO stacked 128-pixel patches that share every weight box --
+                           // the accumulator stage holds patch 0 in TMEM columns [0, 128) and patch 1 in [128, 256), epilogue warps 4-7 drain
+                           // patch 0 and warps 8-11 patch 1.  Doubles the MMA work per k-block iteration of the producer / issuer chains.
+    int patches_per_tile;  // 1, or 2 (CTA pair: one patch per CTA; dual_m: both patches in this CTA)
     int trim_n;            // issue the MMAs of a ragged last n-tile with N = round_up(N - n0, 16) instead of 256
     int num_stages;        // depth of the TMA -> MMA ring: the 192 KB tile region divided by the stage size (4 / 6 for 256-column tiles, up to
                            // kMaxStages for narrow layers, whose loads are latency- rather than bandwidth-bound)
@@ -80,14 +91,14 @@ struct GemmParams {
     unsigned int* abort_flag;
 };
 
-// (y0, x0) of the 128-pixel patch this CTA owns inside m-tile `m0 / kTileM`: a tile is one patch (kTileM = 128) or, on a CTA pair
-// (kTileM = 256), two vertically stacked patches, the lower one belonging to CTA rank 1
+// (y0, x0) of 128-pixel patch `sub` of m-tile `m0 / kTileM`: a tile is one patch or two vertically stacked patches (CTA pair: patch =
+// CTA rank; dual_m: both patches belong to this CTA)
 template <int kTileM>
-__device__ __forceinline__ void conv_tile_origin(const GemmParams& p, int m0, int cta_rank, int& y0, int& x0) {
+__device__ __forceinline__ void conv_tile_origin(const GemmParams& p, int m0, int sub, int& y0, int& x0) {
     const int mt = m0 / kTileM;
     const int ty = mt / p.tiles_x;
     const int tile_h = 128 >> p.tile_w_log2;
-    y0 = ty * tile_h * (kTileM / 128) + cta_rank * tile_h;
+    y0 = (ty * p.patches_per_tile + sub) * tile_h;
     x0 = (mt - ty * p.tiles_x) << p.tile_w_log2;
 }
 
@@ -133,18 +144,20 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const SegDev& sg, long long row, int n, int N) {
     if (EPI == PE_EPI_F32) {
         // raw fp32 accumulators (attention scores of the VAE mid block, qwen_image_vae.py:189): out is float [M, ldo]
+        // a lane owns one row: 32-byte stores (whole L2 sectors) instead of 16-byte ones; N and ldo are multiples of 8 floats
         float* o = reinterpret_cast<float*>(sg.out) + row * sg.ldo + n;
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            if (n + v * 4 >= N) break;
-            float4 f;
-            f.x = __uint_as_float(acc[v * 4]); f.y = __uint_as_float(acc[v * 4 + 1]);
-            f.z = __uint_as_float(acc[v * 4 + 2]); f.w = __uint_as_float(acc[v * 4 + 3]);
-            *reinterpret_cast<float4*>(o + v * 4) = f;
+        for (int v = 0; v < 4; ++v) {
+            if (n + v * 8 >= N) break;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"l"(o + v * 8), "r"(acc[v * 8]), "r"(acc[v * 8 + 1]), "r"(acc[v * 8 + 2]), "r"(acc[v * 8 + 3]), "r"(acc[v * 8 + 4]),
+                           "r"(acc[v * 8 + 5]), "r"(acc[v * 8 + 6]), "r"(acc[v * 8 + 7])
+                         : "memory");
         }
         return;
     }
     bf16* out_row = sg.out + row * sg.ldo;
+    uint4 held = make_uint4(0u, 0u, 0u, 0u);      // the even 8-column group of a pair, waiting for its odd neighbour (wide_store)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         const int nn = n + v * 8;
@@ -198,7 +211,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         o.y = pack_bf16(x[2], x[3]);
         o.z = pack_bf16(x[4], x[5]);
         o.w = pack_bf16(x[6], x[7]);
-        *reinterpret_cast<uint4*>(out_row + nn) = o;
+        if (!sg.wide_store) *reinterpret_cast<uint4*>(out_row + nn) = o;
+        else if ((v & 1) == 0) held = o;
+        else st_global_32B(out_row + nn - 8, held, o);
     }
 }
 
@@ -234,16 +249,23 @@ __device__ __forceinline__ void epilogue_qkv_head(uint32_t taddr_head, const Seg
     bf16* dst = (which == 0 ? sg.out : (which == 1 ? sg.out_k : sg.out_v)) + row * sg.ldo + col0;
     if (which == 2) {
 #pragma unroll
-        for (int v = 0; v < 16; ++v) {
-            uint4 o;
+        for (int v = 0; v < 16; v += 2) {
+            uint4 o, o2;
             o.x = y0[v * 4]; o.y = y0[v * 4 + 1]; o.z = y0[v * 4 + 2]; o.w = y0[v * 4 + 3];
-            *reinterpret_cast<uint4*>(dst + v * 8) = o;
+            o2.x = y0[v * 4 + 4]; o2.y = y0[v * 4 + 5]; o2.z = y0[v * 4 + 6]; o2.w = y0[v * 4 + 7];
+            if (sg.wide_store) {
+                st_global_32B(dst + v * 8, o, o2);
+            } else {
+                *reinterpret_cast<uint4*>(dst + v * 8) = o;
+                *reinterpret_cast<uint4*>(dst + v * 8 + 8) = o2;
+            }
         }
         return;
     }
     const float rs = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
     const bf16* w = which == 0 ? sg.norm_q_w : sg.norm_k_w;
     const float4* rope = reinterpret_cast<const float4*>(sg.rope + row * 64);   // 2 (cos,sin) pairs per float4
+    uint4 held = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int v = 0; v < 16; ++v) {   // 8 columns = 4 rotary pairs per iteration
         const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + v * 8));
@@ -262,7 +284,9 @@ __device__ __forceinline__ void epilogue_qkv_head(uint32_t taddr_head, const Seg
         }
         uint4 o;
         o.x = ov[0]; o.y = ov[1]; o.z = ov[2]; o.w = ov[3];
-        *reinterpret_cast<uint4*>(dst + v * 8) = o;
+        if (!sg.wide_store) *reinterpret_cast<uint4*>(dst + v * 8) = o;
+        else if ((v & 1) == 0) held = o;
+        else st_global_32B(dst + v * 8 - 8, held, o);
     }
 }
 
@@ -278,7 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + kTileRegionBytes;
     auto a_smem = [&](int s) { return smem_base + s * stage_pitch; };
-    auto b_smem = [&](int s) { return smem_base + s * stage_pitch + kABytes; };
+    const uint32_t b_off = p.dual_m ? 2u * kABytes : (uint32_t)kABytes;      // dual_m stages hold two A boxes in front of the W box
+    auto b_smem = [&](int s) { return smem_base + s * stage_pitch + b_off; };
     auto full_bar = [&](int s) { return bar_base + s * 8; };
     auto empty_bar = [&](int s) { return bar_base + (kStages + s) * 8; };
     auto tfull_bar = [&](int s) { return bar_base + (2 * kStages + s) * 8; };
@@ -326,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const Tile tile = decode_tile<kTileM>(p, t);
             const SegDev& sg = p.seg[tile.seg];
             int cy0 = 0, cx0 = 0;
-            if (p.conv) conv_tile_origin<kTileM>(p, tile.m0, (int)cta_rank, cy0, cx0);
+            if (p.conv) conv_tile_origin<kTileM>(p, tile.m0, kCG == 2 ? (int)cta_rank : 0, cy0, cx0);
             // tap (dy, dx), channel block of k-block kb: the CTA's pixel patch shifted by the tap; pixels outside the map (negative or
             // >= H / W coordinates) and channels >= C are zero-filled by the TMA unit.  The coordinates advance incrementally: this warp's
             // serial instruction chain per k-block is what bounds the narrow layers (r1: two integer divisions here cost ~350 cycles per
@@ -340,8 +365,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (elect_one()) {
                     if (kCG == 1) {
                         mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx_bytes);
-                        if (p.conv) tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cc, cx, cy);
-                        else tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, a_row);
+                        if (p.conv) {
+                            tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cc, cx, cy);
+                            if (p.dual_m) tma_load_3d(a_smem(stage) + kABytes, &sg.tmA, full_bar(stage), cc, cx, cy + (128 >> p.tile_w_log2));
+                        } else {
+                            tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, a_row);
+                        }
                         tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, b_row);
                     } else {
                         const uint32_t fbs = fb + stage * 8;
@@ -388,10 +417,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     if (elect_one()) {
                         const uint64_t adesc = make_smem_desc_sw128(a_smem(stage), 16, 1024);
                         const uint64_t bdesc = make_smem_desc_sw128(b_smem(stage), 16, 1024);
+                        // +32 bytes per UMMA_K step inside the 128-byte swizzle row (addr field is >>4).  The dual_m variant is a separate
+                        // straight-line batch: testing the flag between the MMAs of the common path cost that path ~70 ns per k-block
+                        // (r1: 0.33 -> 0.41 ms on the 1024^2 96->96 layer, back to 0.33 with the test hoisted)
+                        if (kCG == 1 && p.dual_m) {
+                            // second patch of the tile: next A box (+16 KB = +1024 in the descriptor's >>4 address field), same weights,
+                            // accumulator columns [128, 256)
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            // +32 bytes per UMMA_K step inside the 128-byte swizzle row (addr field is >>4)
-                            umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                umma_bf16<kCG>(d_tmem + 128, adesc + (kABytes >> 4) + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_bf16<kCG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                         if (kCG == 1) umma_commit(empty_bar(stage)); else umma_commit_cg2(empty_bar(stage), 3);
                         if (kb == p.num_kb - 1) {
@@ -420,9 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kTileN;
             long long row = tile.m0 + (int)cta_rank * 128 + ew * 32 + lane;
             bool row_valid = row < sg.M;
+            const bool dual = kCG == 1 && p.dual_m;
             if (p.conv) {
                 int cy0, cx0;
-                conv_tile_origin<kTileM>(p, tile.m0, (int)cta_rank, cy0, cx0);
+                conv_tile_origin<kTileM>(p, tile.m0, dual ? half : (int)cta_rank, cy0, cx0);
                 const int r = ew * 32 + lane;
                 const int yy = cy0 + (r >> p.tile_w_log2);
                 const int xx = cx0 + (r & ((1 << p.tile_w_log2) - 1));
@@ -433,12 +473,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 const int n_head0 = tile.n0 + half * 128;
                 if (n_head0 < p.N) epilogue_qkv_head(taddr + half * 128, sg, row, row_valid, n_head0, p.heads);
             } else {
+                // each warp drains one 128-column half of the accumulator stage: columns [128 half, +128) of a 256-column tile, or, for a
+                // dual_m tile, the whole (<= 128-column) result of patch `half`
+                const int c0 = dual ? 0 : half * 4;
+                const uint32_t tcol = dual ? (uint32_t)half * 128u : 0u;
 #pragma unroll 1
-                for (int c = half * 4; c < half * 4 + 4; ++c) {
+                for (int c = c0; c < c0 + 4; ++c) {
                     const int n = tile.n0 + c * 32;
                     if (n >= p.N) break;
                     uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld32(taddr + tcol + c * 32, r);
                     tmem_ld_wait();
                     if (row_valid) epilogue_chunk<EPI>(r, sg, row, n, p.N);
                 }
@@ -513,18 +557,23 @@ int dispatch_epilogue(Handle* h, const GemmParams& p, int epilogue, cudaStream_t
 
 }  // namespace
 
+// A/B switch for experiments: PE_GEMM_NARROW_STORES=1 keeps the 16-byte epilogue stores (read once per process)
+static bool narrow_stores() {
+    static const bool v = [] { const char* e = getenv("PE_GEMM_NARROW_STORES"); return e != nullptr && e[0] == '1'; }();
+    return v;
+}
+
 // Ring geometry for a launch whose CTAs each receive a 16 KB A box and a `b_rows_per_cta`-row W box per stage.
-static void set_ring(GemmParams& p, int cg, int b_rows_per_cta) {
+static void set_ring(GemmParams& p, int cg, int b_rows_per_cta, int a_boxes = 1) {
     const int b_bytes = b_rows_per_cta * kBlockK * 2;
-    p.stage_smem_bytes = 128 * kBlockK * 2 + ((b_bytes + 1023) & ~1023);
+    const int a_bytes = a_boxes * 128 * kBlockK * 2;
+    p.stage_smem_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
     p.num_stages = kTileRegionBytes / p.stage_smem_bytes;
     if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     if (b_rows_per_cta * cg == kTileN) p.num_stages = cg == 1 ? 4 : 6;   // the DiT's full-width GEMMs: the ring they were tuned and profiled with
-    if (const char* e = getenv("PE_GEMM_MAX_STAGES")) {          // tuning aid: cap the ring depth
-        const int cap = atoi(e);
-        if (cap >= 2 && cap < p.num_stages) p.num_stages = cap;
-    }
-    p.stage_tx_bytes = cg * (128 * kBlockK * 2 + b_bytes);       // a pair's boxes all land on the leader's barrier
+    static const int stage_cap = [] { const char* e = getenv("PE_GEMM_MAX_STAGES"); return e ? atoi(e) : 0; }();   // tuning aid: cap the ring depth
+    if (stage_cap >= 2 && stage_cap < p.num_stages) p.num_stages = stage_cap;
+    p.stage_tx_bytes = cg * (a_bytes + b_bytes);                 // a pair's boxes all land on the leader's barrier
 }
 
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream) {
@@ -572,9 +621,14 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         d.rope = static_cast<const float2*>(in.rope);
         d.ldo = in.ldo;
         d.M = in.M;
+        {
+            uintptr_t al = reinterpret_cast<uintptr_t>(in.out) | reinterpret_cast<uintptr_t>(in.out_k) | reinterpret_cast<uintptr_t>(in.out_v);
+            d.wide_store = ((al & 31) == 0 && in.ldo % 16 == 0 && N % 16 == 0 && !narrow_stores()) ? 1 : 0;
+        }
         d.m_tiles = ceil_div(in.M, tile_m);
         total_m_tiles += d.m_tiles;
         if (epilogue == PE_EPI_GATE_RESIDUAL) PE_REQUIRE(h, in.gate != nullptr, "pe_gemm: gate-residual epilogue needs gate");
+        if (epilogue == PE_EPI_F32) PE_REQUIRE(h, (reinterpret_cast<uintptr_t>(in.out) & 31) == 0, "pe_gemm: the fp32 output must be 32-byte aligned");
         if (epilogue == PE_EPI_QKV_NORM_ROPE)
             PE_REQUIRE(h, in.bias && in.out_k && in.out_v && in.norm_q_w && in.norm_k_w && in.rope,
                        "pe_gemm: QKV epilogue needs bias, out_k, out_v, norm weights and rope table");
@@ -634,6 +688,9 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     const int tile_w = 1 << p.tile_w_log2, tile_h = 128 >> p.tile_w_log2;
     p.tiles_x = ceil_div(d->W, tile_w);
     p.trim_n = 1;
+    // narrow layers on one CTA: two patches per tile share the weight boxes (see GemmParams::dual_m)
+    p.dual_m = (cg == 1 && d->N <= 128 && !(d->flags & PE_CONV_FLAG_SINGLE_PATCH)) ? 1 : 0;
+    p.patches_per_tile = (cg == 2 || p.dual_m) ? 2 : 1;
     SegDev& sd = p.seg[0];
     int rc = make_tmap_3d(h, &sd.tmA, d->x, (uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->ldx, (uint64_t)d->ldx * d->W,
                           64, (uint32_t)tile_w, (uint32_t)tile_h);
@@ -642,18 +699,19 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
     // still cost L2 -> SM bandwidth (ncu: l1tex__m_xbar2l1tex_read_bytes counts the full box)
     const int n_tile_rows = d->N < kTileN ? ((d->N + 15) & ~15) : kTileN;
     const int b_box_rows = n_tile_rows / cg;
-    set_ring(p, cg, b_box_rows);
+    set_ring(p, cg, b_box_rows, p.dual_m ? 2 : 1);
     rc = make_tmap_2d(h, &sd.tmB, d->w, (uint64_t)d->N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)b_box_rows);
     if (rc) return rc;
     sd.bias = static_cast<const bf16*>(d->bias);
     sd.out = static_cast<bf16*>(d->out);
     sd.gate = static_cast<const bf16*>(d->gate);
     sd.ldo = d->ldo;
+    sd.wide_store = ((reinterpret_cast<uintptr_t>(d->out) & 31) == 0 && d->ldo % 16 == 0 && d->N % 16 == 0 && !narrow_stores()) ? 1 : 0;
     sd.M = d->H * d->W;
-    sd.m_tiles = p.tiles_x * ceil_div(d->H, tile_h * cg);
+    sd.m_tiles = p.tiles_x * ceil_div(d->H, tile_h * p.patches_per_tile);
     p.total_m_tiles = sd.m_tiles;
     {
-        const long long tile_row_bytes = (long long)128 * cg * p.K * 2;
+        const long long tile_row_bytes = (long long)128 * p.patches_per_tile * p.K * 2;
         int gm_max = (int)(kPanelBytes / tile_row_bytes);
         if (gm_max < 1) gm_max = 1;
         const int groups = ceil_div(p.total_m_tiles, gm_max);

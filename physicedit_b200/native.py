@@ -27,6 +27,7 @@ EPI_F32 = 7
 GEMM_FLAG_CTA_PAIR = 1
 GEMM_FLAG_TRIM_N = 2
 CONV_FLAG_CTA_PAIR = 1
+CONV_FLAG_SINGLE_PATCH = 2
 ATTN_FLAG_SINGLE_Q_TILE = 1
 ATTN_FLAG_P_VIA_SMEM = 2
 ATTN_FLAG_SPLIT_ROW_SOFTMAX = 8

@@ -277,15 +277,16 @@ class QwenImageVAE(nn.Module):
         elif out is None:                       # narrow output inside a zero-padded `ldo`-wide map (feeds a K = ldo layer)
             out = torch.zeros((H * W, ldo), dtype=torch.bfloat16, device=x.device)
         nat.tag = f"vae_conv{kh}x{kw}_{H}x{W}_{cin}to{n8}"
-        # maps with enough tiles to fill the GPU run on CTA pairs (cta_group::2): each CTA loads half of the weight rows, which halves
-        # the L2 -> SM weight traffic that bounds these narrow (96 / 192 / 384 channel) layers
+        # 192 / 384-channel layers on maps with enough tiles to fill the GPU run on CTA pairs (cta_group::2): each CTA loads half of the
+        # weight rows, which halves their L2 -> SM weight traffic; layers of <= 128 channels pair two pixel patches inside one CTA instead
+        # (pe_conv2d's default), which doubles the MMA work per k-block iteration of the producer / issuer instruction chains
         pair = H * W >= _PAIR_MIN_PIXELS
         if kh == 1 and kw == 1:
             nat.gemm([dict(a=x, w=w2d, bias=b, out=out, gate=P["ones"] if residual else None)], n8, w2d.shape[1],
                      nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS, nv.GEMM_FLAG_TRIM_N | (nv.GEMM_FLAG_CTA_PAIR if pair else 0))
         else:
             nat.conv2d(x, H, W, cin, w2d, b, out, n8, kh, kw, 1 if kh == 3 else 0, nv.EPI_GATE_RESIDUAL if residual else nv.EPI_BIAS,
-                       gate=P["ones"] if residual else None, flags=nv.CONV_FLAG_CTA_PAIR if pair else 0)
+                       gate=P["ones"] if residual else None, flags=nv.CONV_FLAG_CTA_PAIR if (pair and n8 > 128) else 0)
         return out
 
     @staticmethod

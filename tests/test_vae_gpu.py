@@ -52,7 +52,7 @@ def _rand(shape, seed, scale=1.0):
 
 
 @gpu
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])       # pe_conv2d flags: 0 default (two patches per tile when N <= 128), 1 CTA pair, 2 single patch
 @pytest.mark.parametrize("H,W,C,N,kh,kw,pad,ld_extra,residual", [
     (13, 21, 96, 96, 3, 3, 1, 0, False),      # ragged patch grid, C not a multiple of 64, trimmed n-tile
     (16, 16, 64, 384, 3, 3, 1, 0, False),     # two n-tiles (256 + 128)
@@ -61,6 +61,8 @@ def _rand(shape, seed, scale=1.0):
     (12, 20, 384, 96, 2, 2, 0, 0, False),     # the downsample form: 2x2 taps, zeros only on the bottom / right
     (7, 5, 64, 16, 3, 3, 1, 64 - 16, False),  # narrow output inside a wider map (ldo > N), tiny map
     (40, 56, 96, 192, 3, 3, 1, 0, True),      # several m-tiles per row and column
+    (24, 33, 96, 96, 3, 3, 1, 0, True),       # dual-patch tiles with a ragged last tile row (24 = 16 + 8) and residual
+    (50, 16, 128, 128, 3, 3, 1, 0, False),    # N = 128 exactly; lower patch of the last tile entirely outside the map
 ])
 def test_conv2d_matches_contract(nat, emu, H, W, C, N, kh, kw, pad, ld_extra, residual, pair):
     cpad = (C + 63) // 64 * 64

@@ -20,8 +20,8 @@ def main():
         b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
         out = torch.empty(H * W, N, device="cuda", dtype=torch.bfloat16)
         ref = None
-        for pair in (0, 1):
-            for lg in (3, 4, 5, 6, 7):
+        for pair in (0, 1, 2):
+            for lg in (4,):
                 flags = pair | (lg << 4)
                 for _ in range(2):
                     nat.conv2d(x, H, W, C, w, b, out, N, 3, 3, 1, 0, flags=flags)
