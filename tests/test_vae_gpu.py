@@ -276,3 +276,26 @@ def test_pipeline_call_pil_in_pil_out(nat, vae):
     enc = m.encode(pipe.preprocess_image(edit))
     want = VO.encode({k: v.float() for k, v in vae[1].items()}, pipe.preprocess_image(edit).float().cpu())
     assert rel_l2(enc, want) <= 2.0e-2
+
+
+@gpu
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_epilogue_store_width_paths_agree(nat, pair):
+    """The bf16 epilogues store 32 bytes per lane when the output is 32-byte aligned (ldo, N multiples of 16) and fall back to 16-byte
+    stores otherwise: the same GEMM into an aligned buffer and into a view that starts 16 bytes into a wider buffer must be identical,
+    for the plain and the in-place residual epilogue, and must not touch the columns around the view."""
+    from physicedit_b200 import native as nv
+    M, N, K = 300, 256, 192
+    a, w, b = _rand((M, K), 21).cuda(), _rand((N, K), 22, K ** -0.5).cuda(), _rand((N,), 23, 0.1).cuda()
+    gate = _rand((N,), 24).cuda()
+    res = _rand((M, N), 25).cuda()
+    for epi in (nv.EPI_BIAS, nv.EPI_GATE_RESIDUAL):
+        aligned = res.clone()
+        nat.gemm([dict(a=a, w=w, bias=b, out=aligned, gate=gate)], N, K, epi, pair)
+        wide = torch.full((M, N + 16), 3.0, dtype=torch.bfloat16, device="cuda")
+        view = wide[:, 8:8 + N]                      # 16-byte aligned rows, not 32-byte aligned
+        view.copy_(res)
+        nat.gemm([dict(a=a, w=w, bias=b, out=view, gate=gate)], N, K, epi, pair)
+        nat.check_async()
+        assert torch.equal(view, aligned), f"epilogue {epi}: 16-byte and 32-byte store paths differ"
+        assert float((wide[:, :8] - 3.0).abs().max()) == 0.0 and float((wide[:, 8 + N:] - 3.0).abs().max()) == 0.0
