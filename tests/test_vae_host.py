@@ -80,3 +80,39 @@ def test_load_vae_by_registry_hash(tmp_path, capsys):
     torch.save({"x.weight": torch.zeros(2, 2)}, bad)
     assert load_vae(str(bad), device="cpu") is None
     assert "cannot detect the model type" in capsys.readouterr().out
+
+
+def test_argument_errors_match_the_scope(model):
+    """Single frames only (the pipeline never passes video to the VAE, qwen_image_physical.py:665,1273): T > 1 is refused loudly, and
+    encode insists on the 8-pixel grid the three stride-2 stages need."""
+    with pytest.raises(NotImplementedError):
+        model.decode(torch.zeros(1, 16, 2, 4, 4, dtype=torch.bfloat16))
+    with pytest.raises(NotImplementedError):
+        model.encode(torch.zeros(1, 3, 5, 32, 32, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):
+        model.encode(torch.zeros(1, 3, 36, 32, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):
+        V.QwenImageVAE(z_dim=4)
+
+
+def test_packed_weights_follow_weight_updates(model):
+    """prepare() caches repacked weights; load_state_dict / .to() must drop the cache (otherwise a LoRA-style in-place update or a
+    checkpoint reload would silently keep running on the old weights)."""
+    assert model._packed is not None
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.load_state_dict(sd, assign=True)
+    assert model._packed is None
+    model.prepare()
+    w2d, b, n8, kh, kw, cin = model._packed["decoder.conv_out"]
+    assert (n8, kh, kw, cin) == (8, 3, 3, 96) and w2d.shape == (8, 9 * 128) and float(w2d[3:].abs().max()) == 0.0
+    # tap-major, channel-minor packing of the LAST temporal slice
+    w = model.decoder.conv_out.weight
+    assert torch.equal(w2d[:3].reshape(3, 3, 3, 128)[..., :96], w[:, :, -1].permute(0, 2, 3, 1))
+    # stride-2 conv as a 2x2 conv over the space-to-depth map: tap (a, b), phase (py, px) <- kernel element (2a+py, 2b+px)
+    w2d, b, n8, kh, kw, cin = model._packed["encoder.down_blocks.2"]
+    wd = model.encoder.down_blocks[2].resample[1].weight
+    v = w2d.reshape(96, 2, 2, 4, 96)
+    assert (kh, kw, cin) == (2, 2, 384)
+    assert torch.equal(v[:, 1, 0, 0], wd[:, :, 2, 0]) and torch.equal(v[:, 0, 1, 2], wd[:, :, 1, 2])
+    assert torch.equal(v[:, 0, 0, 3], wd[:, :, 1, 1]) and torch.equal(v[:, 1, 1, 0], wd[:, :, 2, 2])
+    assert float(v[:, 1, :, 2:].abs().max()) == 0.0 and float(v[:, :, 1, 1::2].abs().max()) == 0.0     # kernel rows / columns 3 do not exist
