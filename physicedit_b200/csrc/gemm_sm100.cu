@@ -14,6 +14,12 @@
 // double-stream DiT block): both streams run in ONE launch, each with its own tensor maps, which
 // also gives free M-tail handling (TMA zero-fills out-of-bounds rows, stores are row-guarded).
 //
+// Convolution mode (pe_conv2d, the VAE): the same kernel with a different producer -- the A tile is one 128-pixel patch of a
+// channels-last activation map read tap by tap through a 3-D tensor map (zero padding = TMA out-of-bounds fill, no im2col), K runs
+// over (tap, 64-channel block); narrow layers trim the MMA / W box to round_up(N, 16) columns, deepen the ring, and (N <= 128) keep
+// two patches' accumulators in one TMEM stage so that both share every weight box.  Replaces QwenImageCausalConv3d / nn.Conv2d in
+// DiffSynth-Studio/diffsynth/models/qwen_image_vae.py:43-51,243,247-249 and the residual add :152.
+//
 // Reference call sites replaced: F.linear in QwenDoubleStreamAttention.forward / QwenFeedForward /
 // ApproximateGELU (DiffSynth-Studio/diffsynth/models/qwen_image_dit.py:42-49,228-316), the
 // gate/residual adds of QwenImageTransformerBlock.forward (:386-399), RMSNorm (models/utils.py:241-257),
