@@ -233,6 +233,19 @@ class QwenImagePhysicPipeline(nn.Module):
         image = ((vae_output - min_value) * (255 / (max_value - min_value))).clip(0, 255)
         return Image.fromarray(image.to(device="cpu", dtype=torch.uint8).numpy())
 
+    @staticmethod
+    def calculate_dimensions(target_area, ratio):
+        """QwenImageUnit_EditImageEmbedder.calculate_dimensions (qwen_image_physical.py:1249-1255): (width, height) on a 32-pixel grid."""
+        import math
+        width = math.sqrt(target_area * ratio)
+        height = width / ratio
+        return round(width / 32) * 32, round(height / 32) * 32
+
+    def auto_resize_edit_image(self, edit_image):
+        """:1258-1260: resize a PIL image to ~1024 x 1024 pixels keeping its aspect ratio."""
+        w, h = QwenImagePhysicPipeline.calculate_dimensions(1024 * 1024, edit_image.size[0] / edit_image.size[1])
+        return edit_image.resize((w, h))
+
     def generate_noise(self, shape, seed=None, rand_device="cpu", rand_torch_dtype=torch.float32, device=None, torch_dtype=None):
         generator = None if seed is None else torch.Generator(rand_device).manual_seed(seed)
         noise = torch.randn(shape, generator=generator, device=rand_device, dtype=rand_torch_dtype)
@@ -327,8 +340,10 @@ class QwenImagePhysicPipeline(nn.Module):
 
     @torch.no_grad()
     def __call__(self, prompt=None, negative_prompt="", cfg_scale=4.0, height=1328, width=1328, seed=None, rand_device="cpu",
-                 num_inference_steps=30, edit_image=None, is_train=True, progress_bar_cmd=None, tiled=False, tile_size=128, tile_stride=64,
-                 prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, output_type="pil", **kwargs):
+                 num_inference_steps=30, edit_image=None, edit_image_auto_resize=True, context_image=None, is_train=True,
+                 progress_bar_cmd=None, tiled=False, tile_size=128, tile_stride=64,
+                 prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, context_latents=None,
+                 output_type="pil", **kwargs):
         """Reference signature subset.  The pre-loop units that need the Qwen2.5-VL encoder / VAE run only if those
         modules were attached (`pipe.text_encoder`, `pipe.vae`); otherwise pass `prompt_inputs_posi/nega` and
         `edit_latents` and get latents back (`output_type="latent"`)."""
@@ -343,12 +358,22 @@ class QwenImagePhysicPipeline(nn.Module):
         if edit_latents is None and edit_image is not None:
             if self.vae is None:
                 raise RuntimeError("no VAE loaded: pass edit_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
-            # QwenImageUnit_EditImageEmbedder.process (qwen_image_physical.py:1265-1285): one image or a list of images
+            # QwenImageUnit_EditImageEmbedder.process (qwen_image_physical.py:1265-1285): one image or a list of images, each resized to
+            # ~1024^2 pixels on a 32-pixel grid first unless edit_image_auto_resize=False (tensors are taken as already pre-processed)
+            def prep(im):
+                if isinstance(im, torch.Tensor):
+                    return im
+                return self.preprocess_image(self.auto_resize_edit_image(im) if edit_image_auto_resize else im)
             imgs = edit_image if isinstance(edit_image, (list, tuple)) else [edit_image]
-            enc = [self.vae.encode(im if isinstance(im, torch.Tensor) else self.preprocess_image(im), tiled=tiled, tile_size=tile_size,
-                                   tile_stride=tile_stride) for im in imgs]
+            enc = [self.vae.encode(prep(im), tiled=tiled, tile_size=tile_size, tile_stride=tile_stride) for im in imgs]
             edit_latents = enc if isinstance(edit_image, (list, tuple)) else enc[0]
-        latents = self.denoise(latents, prompt_inputs_posi, prompt_inputs_nega, edit_latents, height=height, width=width,
+        if context_latents is None and context_image is not None:
+            if self.vae is None:
+                raise RuntimeError("no VAE loaded: pass context_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
+            # QwenImageUnit_ContextImageEmbedder.process (:1293-1299): resized to the output size
+            ctx = context_image if isinstance(context_image, torch.Tensor) else self.preprocess_image(context_image.resize((width, height)))
+            context_latents = self.vae.encode(ctx, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
+        latents = self.denoise(latents, prompt_inputs_posi, prompt_inputs_nega, edit_latents, context_latents, height=height, width=width,
                                num_inference_steps=num_inference_steps, cfg_scale=cfg_scale, progress_bar_cmd=progress_bar_cmd)
         if output_type == "latent" or self.vae is None:
             return latents

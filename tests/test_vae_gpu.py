@@ -266,7 +266,7 @@ def test_pipeline_call_pil_in_pil_out(nat, vae):
     rng = np.random.default_rng(0)
     edit = Image.fromarray(rng.integers(0, 256, size=(64, 96, 3), dtype=np.uint8))
     kw = dict(prompt_inputs_posi={k: posi[k].cuda() for k in keys}, prompt_inputs_nega={k: nega[k].cuda() for k in keys}, edit_image=edit,
-              height=64, width=96, seed=3, num_inference_steps=2, is_train=False)
+              edit_image_auto_resize=False, context_image=edit.resize((48, 32)), height=64, width=96, seed=3, num_inference_steps=2, is_train=False)
     img = pipe(**kw)
     nat.check_async()
     assert isinstance(img, Image.Image) and img.size == (96, 64)

@@ -116,3 +116,16 @@ def test_packed_weights_follow_weight_updates(model):
     assert torch.equal(v[:, 1, 0, 0], wd[:, :, 2, 0]) and torch.equal(v[:, 0, 1, 2], wd[:, :, 1, 2])
     assert torch.equal(v[:, 0, 0, 3], wd[:, :, 1, 1]) and torch.equal(v[:, 1, 1, 0], wd[:, :, 2, 2])
     assert float(v[:, 1, :, 2:].abs().max()) == 0.0 and float(v[:, :, 1, 1::2].abs().max()) == 0.0     # kernel rows / columns 3 do not exist
+
+
+def test_edit_image_auto_resize_dimensions():
+    """QwenImageUnit_EditImageEmbedder.calculate_dimensions / edit_image_auto_resize (qwen_image_physical.py:1249-1260): ~1024^2 pixels on
+    a 32-pixel grid, aspect ratio kept.  Known answers computed from the reference formula."""
+    from PIL import Image
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline as P
+    assert P.calculate_dimensions(1024 * 1024, 1.0) == (1024, 1024)
+    assert P.calculate_dimensions(1024 * 1024, 16 / 9) == (1376, 768)
+    assert P.calculate_dimensions(1024 * 1024, 3 / 4) == (896, 1184)
+    assert P.calculate_dimensions(1024 * 1024, 832 / 480) == (1344, 768)
+    img = Image.new("RGB", (640, 360))
+    assert P.auto_resize_edit_image(None, img).size == (1376, 768)
