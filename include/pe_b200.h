@@ -69,7 +69,6 @@ int pe_sm_count(pe_handle_t h);
 /* ------------------------------------------------------------------------------------------- */
 typedef enum pe_epilogue {
     PE_EPI_BIAS = 0,           /* out = bf16(acc + bias)                                         */
-    PE_EPI_BIAS_GELU_TANH = 1, /* reserved                                                       */
     PE_EPI_BIAS_GELU_SIGMOID = 2, /* h=bf16(acc+bias); out = h * sigmoid(1.702 h)  (ApproximateGELU) */
     PE_EPI_BIAS_GELU_ERF = 3,  /* h=bf16(acc+bias); out = gelu_erf(h)   (nn.GELU, helpers.py:127) */
     PE_EPI_GATE_RESIDUAL = 4,  /* o=bf16(acc+bias); out = residual + gate[n]*o  (in place on out) */

@@ -128,7 +128,7 @@ def rope_tables(img_shapes: Sequence[Tuple[int, int, int]], txt_len: int) -> Tup
 def apply_rope(x: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
     """apply_rotary_emb_qwen (:51-57): adjacent pairs as complex, fp32 multiply, cast back.  x [B,h,S,128]."""
     xc = torch.view_as_complex(x.float().reshape(*x.shape[:-1], -1, 2))
-    return torch.view_as_real(xc * freqs).flatten(3).type_as(x)
+    return torch.view_as_real(xc * freqs.to(x.device)).flatten(3).type_as(x)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -154,7 +154,16 @@ def _heads(x: torch.Tensor) -> torch.Tensor:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """qwen_image_flash_attention default branch (:37-38): SDPA, no mask, scale 1/sqrt(128); 'b n s d -> b s (n d)'."""
-    x = F.scaled_dot_product_attention(q, k, v)
+    if q.is_cuda and q.dtype == torch.float32:
+        # The oracle proper on a GPU (tests at the benchmark's sequence lengths): SDPA's fused fp32 kernels may use TF32 tensor
+        # cores, and its math backend materialises all heads' S x S scores at once (42 GB at S = 20992).  Same formula, exact
+        # fp32, one head at a time.
+        x = torch.empty_like(q)
+        for h in range(q.shape[1]):
+            p = torch.softmax((q[:, h] @ k[:, h].transpose(-1, -2)) * (q.shape[-1] ** -0.5), dim=-1)
+            x[:, h] = p @ v[:, h]
+    else:
+        x = F.scaled_dot_product_attention(q, k, v)
     B, n, S, d = x.shape
     return x.permute(0, 2, 1, 3).reshape(B, S, n * d)
 
@@ -330,14 +339,14 @@ class FlowMatchOracle:
 
 
 def denoise_loop(W, A, latents, posi, nega, edit_latents, height, width, num_inference_steps, cfg_scale=4.0,
-                 num_layers=None, cuda_scalar_div=False):
+                 num_layers=None, cuda_scalar_div=False, timestep_dtype=None):
     """QwenImagePhysicPipeline.__call__ lines 600, 646-661: CFG (2 forwards / step) + Euler update.
     posi / nega: dicts with prompt_emb, prompt_emb_mask, special_token_mask (prompt_emb is mutated in place)."""
     sch = FlowMatchOracle()
     sch.set_timesteps(num_inference_steps, dynamic_shift_len=(height // 16) * (width // 16))
-    dtype = latents.dtype
+    dtype = timestep_dtype or latents.dtype          # timestep_dtype=bf16 with fp32 latents: fp32 arithmetic on the bf16 path's timestep bookkeeping
     for pid, t in enumerate(sch.timesteps):
-        t = t.unsqueeze(0).to(dtype)
+        t = t.unsqueeze(0).to(dtype).to(latents.device)
         kw = dict(height=height, width=width, edit_latents=edit_latents, num_layers=num_layers, cuda_scalar_div=cuda_scalar_div)
         vp = model_fn(W, A, latents, t, posi["prompt_emb"], posi["prompt_emb_mask"], posi["special_token_mask"], **kw)
         if cfg_scale != 1.0:

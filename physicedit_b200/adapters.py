@@ -231,6 +231,16 @@ class Dinov2Encoder(nn.Module):
         self._packed = None
         self._pos_cache = {}
 
+    # packed copies (patch-embed weight, fused QKV) and the interpolated position table are derived from the parameters:
+    # any weight load or device / dtype move drops them (an in-place load keeps data_ptr, so pointer checks are not enough)
+    def load_state_dict(self, *args, **kwargs):
+        self._packed, self._pos_cache = None, {}
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed, self._pos_cache = None, {}
+        return super()._apply(fn, *args, **kwargs)
+
     def _pos(self, gh: int, gw: int) -> torch.Tensor:
         """interpolate_pos_encoding (:90-140): bicubic antialias in fp32, depends on the weights and grid only -> cached."""
         key = (gh, gw, self.embeddings.position_embeddings.data_ptr())

@@ -160,13 +160,16 @@ int pe_check_async_error(pe_handle_t hh, void* stream, unsigned int* diag) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (h == nullptr) return PE_ERR_INVALID_ARGUMENT;
     PE_CHECK_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    unsigned int v = 0;
-    PE_CHECK_CUDA(h, cudaMemcpy(&v, h->abort_flag, sizeof(v), cudaMemcpyDeviceToHost));
-    if (diag) *diag = v;
-    if (v != 0) {
-        cudaMemset(h->abort_flag, 0, sizeof(v));
+    unsigned int w[2] = {0, 0};       // [0] pipeline time-out (site, block), [1] data-dependent argument error (special-token count)
+    PE_CHECK_CUDA(h, cudaMemcpy(w, h->abort_flag, sizeof(w), cudaMemcpyDeviceToHost));
+    const unsigned int v = w[0];
+    if (diag) *diag = v != 0 ? v : w[1];
+    if (v != 0 || w[1] != 0) cudaMemset(h->abort_flag, 0, sizeof(w));
+    if (v != 0)
         return pe::set_error(h, PE_ERR_KERNEL_TIMEOUT, "kernel pipeline wait timed out: site=%u block=%u", (v >> 16) & 0x7fffu, v & 0xffffu);
-    }
+    if (w[1] != 0)
+        return pe::set_error(h, PE_ERR_INVALID_ARGUMENT, "pe_special_gather: the mask selects %u rows but the destination holds fewer "
+                             "(rows beyond it were NOT processed)", w[1]);
     return PE_OK;
 }
 

@@ -439,7 +439,8 @@ __global__ void cfg_euler_kernel(bf16* __restrict__ lat, const bf16* __restrict_
 // -------------------------------------------------------------------------------------------------
 // special tokens: ordered gather of the masked rows, and blend + scatter back
 // -------------------------------------------------------------------------------------------------
-__global__ void special_index_kernel(const uint8_t* __restrict__ mask, int T, int32_t* __restrict__ idx, int max_rows) {
+__global__ void special_index_kernel(const uint8_t* __restrict__ mask, int T, int32_t* __restrict__ idx, int max_rows,
+                                     unsigned int* __restrict__ async_err) {
     // single CTA of 1024 threads; ordered compaction via per-chunk ballot + running offset
     __shared__ int warp_cnt[32];
     __shared__ int base;
@@ -465,7 +466,12 @@ __global__ void special_index_kernel(const uint8_t* __restrict__ mask, int T, in
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) idx[max_rows] = base;
+    if (threadIdx.x == 0) {
+        idx[max_rows] = base;
+        // more masked rows than the caller made room for: the reference handles any count (qwen_image_physical.py:1334), so dropping
+        // rows would be a silent wrong answer -> raise the handle's asynchronous argument error (pe_check_async_error reports it)
+        if (base > max_rows) atomicMax(async_err + 1, (unsigned int)base);
+    }
 }
 __global__ void special_gather_rows_kernel(const bf16* __restrict__ pe, const int32_t* __restrict__ idx, int C, bf16* __restrict__ dst) {
     const int r = blockIdx.x;
@@ -619,7 +625,7 @@ int special_gather_run(Handle* h, const void* prompt_emb, const uint8_t* mask, i
                        cudaStream_t s) {
     PE_REQUIRE(h, prompt_emb && mask && dst && idx, "pe_special_gather: null pointer");
     PE_REQUIRE(h, T > 0 && C > 0 && C % 8 == 0 && max_rows > 0, "pe_special_gather: bad sizes");
-    special_index_kernel<<<1, 1024, 0, s>>>(mask, T, idx, max_rows);
+    special_index_kernel<<<1, 1024, 0, s>>>(mask, T, idx, max_rows, h->abort_flag);
     special_gather_rows_kernel<<<max_rows, 128, 0, s>>>(static_cast<const bf16*>(prompt_emb), idx, C, static_cast<bf16*>(dst));
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;

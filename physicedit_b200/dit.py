@@ -232,6 +232,21 @@ class QwenImageDiT(nn.Module):
         for i, b in enumerate(self.transformer_blocks):
             object.__setattr__(b, "_owner", (self, i))
 
+    # Timestep-keyed caches of the engine (temb, modulation vectors, norm_out scale/shift) are derived from the weights.  An
+    # in-place load (`load_state_dict(ckpt, strict=False)` without assign, as INTEGRATION.md shows) keeps every data_ptr, so the
+    # engine's pointer check cannot see it: drop the caches on every load and on every device / dtype move.
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        if self._engine is not None:
+            self._engine.invalidate()
+        return res
+
+    def _apply(self, fn, *args, **kwargs):
+        res = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_engine", None) is not None:
+            object.__setattr__(self, "_engine", None)          # storage may have moved: re-pack lazily
+        return res
+
     def engine(self) -> "DiTEngine":
         if self._engine is None:
             object.__setattr__(self, "_engine", DiTEngine(self))

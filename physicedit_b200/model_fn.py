@@ -14,20 +14,20 @@ import torch
 
 from . import native as nv
 
-_MASK_SUM_CACHE: dict = {}
-
-
 def _txt_len(mask: Optional[torch.Tensor], T: int) -> int:
-    """`prompt_emb_mask.sum(dim=1).tolist()` (:1341) is a device->host sync in the reference; the result only
-    depends on the mask tensor, so it is read once per mask tensor version."""
+    """`prompt_emb_mask.sum(dim=1).tolist()` (:1341): a device->host sync per forward in the reference.  The pipeline's loops
+    read it once per request and pass `txt_len=`; a direct call without it pays the same sync the reference pays (no cache:
+    a cache keyed on the tensor's address can be hit by a later request's mask at a recycled address)."""
     if mask is None:
         return T
-    key = (mask.data_ptr(), mask._version, tuple(mask.shape))
-    if key not in _MASK_SUM_CACHE:
-        if len(_MASK_SUM_CACHE) > 64:
-            _MASK_SUM_CACHE.clear()
-        _MASK_SUM_CACHE[key] = int(mask.sum(dim=1).max().item())
-    return _MASK_SUM_CACHE[key]
+    return int(mask.sum(dim=1).max().item())
+
+
+def prompt_lengths(prompt_emb_mask: Optional[torch.Tensor], special_token_mask: Optional[torch.Tensor], T: int) -> dict:
+    """The two data-dependent sizes of a request -- text length (:1341) and number of special tokens (:1334) -- read from the
+    device ONCE; pass the result as `**prompt_lengths(...)` (keys `txt_len`, `n_special`) to keep the denoise loop sync-free."""
+    n_sp = 0 if special_token_mask is None else int(special_token_mask.sum().item())
+    return dict(txt_len=_txt_len(prompt_emb_mask, T), n_special=n_sp)
 
 
 def model_fn_qwen_image(
@@ -60,6 +60,8 @@ def model_fn_qwen_image(
     timestep_host: Optional[float] = None,
     out: Optional[torch.Tensor] = None,
     cfg_branch: int = 0,
+    txt_len: Optional[int] = None,
+    n_special: Optional[int] = None,
     **kwargs,
 ):
     if entity_prompt_emb is not None or blockwise_controlnet_conditioning is not None or edit_rope_interpolation or enable_fp8_attention:
@@ -72,10 +74,16 @@ def model_fn_qwen_image(
     eng = dit.engine()
     nat = eng.nat
     t_bf16 = timestep.to(device=latents.device, dtype=torch.bfloat16).reshape(-1)[:1].contiguous()
-    if timestep_host is None and not timestep.is_cuda:
-        timestep_host = float(timestep.reshape(-1)[0])
+    if timestep_host is None:
+        # The reference loop hands over a CUDA bf16 timestep (:649).  Its value keys the conditioning cache (temb, the 120 modulation
+        # vectors, norm_out's scale/shift depend on nothing else), so the two CFG branches of a step share one pass over the 13.6 GB of
+        # modulation weights.  Reading it back is one 2-byte D2H per forward -- the reference itself syncs every forward at :1341.
+        timestep_host = float(t_bf16[0].item()) if timestep.is_cuda else float(timestep.reshape(-1)[0].to(torch.bfloat16))
     T = prompt_emb.shape[1]
-    assert _txt_len(prompt_emb_mask, T) == T, "padded prompts are not produced by the B=1 pipeline (RoPE table would not match either)"
+    if txt_len is None:
+        txt_len = _txt_len(prompt_emb_mask, T)
+    if txt_len != T:
+        raise ValueError(f"padded prompts ({txt_len} valid of {T} tokens) are not produced by the B=1 pipeline; trim prompt_emb to its mask")
     pe2d = prompt_emb[0]
     if not pe2d.is_contiguous():
         raise ValueError("prompt_emb must be contiguous: it is updated in place")
@@ -83,14 +91,17 @@ def model_fn_qwen_image(
     special_token_loss = 0
     if special_token_mask is not None:
         ad = visual_thinking_adapter
-        n_sp = getattr(model_fn_qwen_image, "special_token_num", 64)
-        gathered = torch.empty(n_sp, pe2d.shape[1], dtype=torch.bfloat16, device=pe2d.device)
-        idx = torch.empty(n_sp + 1, dtype=torch.int32, device=pe2d.device)
-        nat.special_gather(pe2d, special_token_mask[0].view(torch.uint8), gathered, idx)
-        pred_dino, pred_vae = ad.heads(gathered)
-        nat.special_blend_scatter(pe2d, idx, pred_dino, pred_vae, t_bf16, ad.t_min, ad.t_max)       # in place (:1336)
-        if is_train:
-            special_token_loss = ad.get_loss(pred_dino.unsqueeze(0), pred_vae.unsqueeze(0), pseudo_special_emb_dino, pseudo_special_emb_vae, timestep)
+        # any number of special tokens, like the reference's boolean gather (:1334); a count the caller did not pass is read from the
+        # device (the gather kernel raises the handle's async error if the mask holds MORE rows than `n_special`: never a silent drop)
+        n_sp = int(special_token_mask.sum().item()) if n_special is None else int(n_special)
+        if n_sp > 0:
+            gathered = torch.empty(n_sp, pe2d.shape[1], dtype=torch.bfloat16, device=pe2d.device)
+            idx = torch.empty(n_sp + 1, dtype=torch.int32, device=pe2d.device)
+            nat.special_gather(pe2d, special_token_mask[0].view(torch.uint8), gathered, idx)
+            pred_dino, pred_vae = ad.heads(gathered)
+            nat.special_blend_scatter(pe2d, idx, pred_dino, pred_vae, t_bf16, ad.t_min, ad.t_max)       # in place (:1336)
+            if is_train:
+                special_token_loss = ad.get_loss(pred_dino.unsqueeze(0), pred_vae.unsqueeze(0), pseudo_special_emb_dino, pseudo_special_emb_vae, timestep)
 
     lat_list = [latents]
     if context_latents is not None:

@@ -25,7 +25,7 @@ from . import native as nv
 from .adapters import Dinov2withNorm, PerceiverResampler, VisualThinkingAdapter, VisualThinkingDualAdapter
 from .dit import QwenImageDiT
 from .lora import GeneralLoRALoader
-from .model_fn import model_fn_qwen_image
+from .model_fn import model_fn_qwen_image, prompt_lengths
 from .scheduler import FlowMatchScheduler
 from .vae import QwenImageVAE
 
@@ -265,6 +265,10 @@ class QwenImagePhysicPipeline(nn.Module):
         self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength,
                                      dynamic_shift_len=(height // 16) * (width // 16), exponential_shift_mu=exponential_shift_mu)
         nat = nv.Native.get(latents.device.index or 0)
+        # CFG needs both branches (:653-658 always runs the negative forward when cfg_scale != 1): refuse a half-specified request
+        # instead of combining with an uninitialised negative prediction
+        use_cfg = self._use_cfg(cfg_scale, inputs_nega)
+        inputs_posi, inputs_nega = self._with_lengths(inputs_posi), self._with_lengths(inputs_nega) if use_cfg else None
         ts = self.scheduler.timesteps
         ts_dev = ts.to(dtype=self.torch_dtype).to(latents.device) if timesteps_device is None else timesteps_device   # one H2D for the whole table
         latents = latents.clone()
@@ -280,10 +284,29 @@ class QwenImagePhysicPipeline(nn.Module):
             kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=ts_dev[progress_id:progress_id + 1],
                       height=height, width=width, edit_latents=edit_latents, context_latents=context_latents, is_train=False,
                       progress_id=progress_id, timestep_host=t_host)
-            self.run_cfg_branches(kw, inputs_posi, inputs_nega if cfg_scale != 1.0 else None, vp, vn, ts_dev[progress_id:progress_id + 1], t_host)
+            self.run_cfg_branches(kw, inputs_posi, inputs_nega, vp, vn, ts_dev[progress_id:progress_id + 1], t_host)
             ds = float(self.scheduler.dsigma(t))
-            nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), ds)
+            nat.cfg_euler_step(latents, vp, vn if use_cfg else None, float(cfg_scale), ds)
+        # a kernel whose bounded pipeline wait timed out leaves its output partly written and the handle's flag set: surface it here,
+        # at the loop's natural sync point, instead of handing garbage latents to the VAE / the caller
+        nat.check_async()
         return latents
+
+    @staticmethod
+    def _use_cfg(cfg_scale, inputs_nega) -> bool:
+        if cfg_scale != 1.0 and inputs_nega is None:
+            raise ValueError(f"cfg_scale={cfg_scale} needs the negative-prompt inputs (the reference always runs the negative branch when "
+                             "cfg_scale != 1, qwen_image_physical.py:653-658); pass inputs_nega or cfg_scale=1.0")
+        return cfg_scale != 1.0
+
+    @staticmethod
+    def _with_lengths(inputs: Optional[dict]) -> Optional[dict]:
+        """Adds txt_len / n_special (read from the masks once per request) so the per-step forwards need no device->host sync."""
+        if inputs is None or "txt_len" in inputs:
+            return inputs
+        out = dict(inputs)
+        out.update(prompt_lengths(inputs.get("prompt_emb_mask"), inputs.get("special_token_mask"), inputs["prompt_emb"].shape[1]))
+        return out
 
     @torch.no_grad()
     def run_cfg_branches(self, kw: dict, inputs_posi: dict, inputs_nega: Optional[dict], vp, vn, t_dev, t_host) -> None:
@@ -326,6 +349,8 @@ class QwenImagePhysicPipeline(nn.Module):
         """One iteration of the loop above against the CURRENT scheduler table (call scheduler.set_timesteps first):
         updates `latents` in place and returns it.  This is the unit bench.py times end to end."""
         nat = nv.Native.get(latents.device.index or 0)
+        use_cfg = self._use_cfg(cfg_scale, inputs_nega)
+        inputs_posi, inputs_nega = self._with_lengths(inputs_posi), self._with_lengths(inputs_nega) if use_cfg else None
         t = self.scheduler.timesteps[progress_id]
         t_host = float(t.to(self.torch_dtype))
         t_dev = t.to(self.torch_dtype).reshape(1).to(latents.device, non_blocking=True)
@@ -334,8 +359,8 @@ class QwenImagePhysicPipeline(nn.Module):
         vp, vn = self._vbuf[0], self._vbuf[1]
         kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=t_dev, height=height, width=width,
                   edit_latents=edit_latents, context_latents=context_latents, is_train=False, progress_id=progress_id, timestep_host=t_host)
-        self.run_cfg_branches(kw, inputs_posi, inputs_nega if cfg_scale != 1.0 else None, vp, vn, t_dev, t_host)
-        nat.cfg_euler_step(latents, vp, vn if cfg_scale != 1.0 else None, float(cfg_scale), float(self.scheduler.dsigma(t)))
+        self.run_cfg_branches(kw, inputs_posi, inputs_nega, vp, vn, t_dev, t_host)
+        nat.cfg_euler_step(latents, vp, vn if use_cfg else None, float(cfg_scale), float(self.scheduler.dsigma(t)))
         return latents
 
     @torch.no_grad()
@@ -417,14 +442,18 @@ class QwenImagePhysicPipeline(nn.Module):
         return {"pseudo_special_emb_dino": delta(dino_branch(dino_middle, True), dino_branch(dino_source, False)),
                 "pseudo_special_emb_vae": delta(vae_branch(vae_middle_latents, True), vae_branch(vae_source_latents, False))}
 
-    def training_loss(self, global_step=None, **inputs):
-        """:313-329, forward value only (no autograd through the native kernels yet -- SURVEY 8f3)."""
-        timestep_id = torch.randint(0, self.scheduler.num_train_timesteps, (1,))
+    def training_loss(self, global_step=None, timestep_id=None, noise=None, **inputs):
+        """:313-329, forward value.  Called as the train script does (`pipe.training_loss(global_step=, **models, **inputs)`,
+        scripts/train/train_physicedit.py:309-310: the in-iteration models arrive inside **inputs) or with the inputs only.
+        `timestep_id` / `noise` pin the two random draws (:314, :317) for parity tests; by default they are drawn as in the reference."""
+        if timestep_id is None:
+            timestep_id = torch.randint(0, self.scheduler.num_train_timesteps, (1,))
         timestep = self.scheduler.timesteps[timestep_id].to(dtype=self.torch_dtype, device=self.device)
-        noise = torch.randn_like(inputs["input_latents"])
+        if noise is None:
+            noise = torch.randn_like(inputs["input_latents"])
         inputs["latents"] = self.scheduler.add_noise(inputs["input_latents"], noise, timestep)
         target = self.scheduler.training_target(inputs["input_latents"], noise, timestep)
-        models = {name: getattr(self, name) for name in self.in_iteration_models}
+        models = {name: getattr(self, name) for name in self.in_iteration_models if name not in inputs}
         noise_pred, special_token_loss = self.model_fn(**models, **inputs, timestep=timestep)
         loss = torch.nn.functional.mse_loss(noise_pred.float(), target.float())
         self.special_token_loss = float(special_token_loss.detach().mean().item()) if torch.is_tensor(special_token_loss) else 0.0

@@ -11,53 +11,43 @@ import torch
 
 
 class FlowMatchScheduler:
-    def __init__(self, num_inference_steps=100, num_train_timesteps=1000, shift=3.0, sigma_max=1.0, sigma_min=0.003 / 1.002,
-                 inverse_timesteps=False, extra_one_step=False, reverse_sigmas=False, exponential_shift=False,
-                 exponential_shift_mu=None, shift_terminal=None):
+    """Only the configuration PhysicEdit constructs (qwen_image_physical.py:192: extra_one_step, exponential shift with a
+    terminal stretch) is implemented; the other modes of the reference class (plain `shift`, inverse / reversed sigmas) are
+    rejected instead of carried along untested."""
+
+    def __init__(self, num_inference_steps=100, num_train_timesteps=1000, sigma_max=1.0, sigma_min=0.0, extra_one_step=True,
+                 exponential_shift=True, exponential_shift_mu=0.8, shift_terminal=0.02, **unsupported):
+        bad = {k: v for k, v in unsupported.items() if v not in (None, False) and k != "shift"}
+        if bad or not (extra_one_step and exponential_shift) or shift_terminal is None:
+            raise NotImplementedError(f"FlowMatchScheduler: only the Qwen-Image configuration is implemented (got {bad or 'a non-exponential schedule'})")
         self.num_train_timesteps = num_train_timesteps
-        self.shift = shift
         self.sigma_max, self.sigma_min = sigma_max, sigma_min
-        self.inverse_timesteps, self.extra_one_step, self.reverse_sigmas = inverse_timesteps, extra_one_step, reverse_sigmas
-        self.exponential_shift, self.exponential_shift_mu = exponential_shift, exponential_shift_mu
+        self.exponential_shift_mu = exponential_shift_mu
         self.shift_terminal = shift_terminal
+        self.inverse_timesteps = self.reverse_sigmas = False
         self.set_timesteps(num_inference_steps)
 
-    def set_timesteps(self, num_inference_steps=100, denoising_strength=1.0, training=False, shift=None, dynamic_shift_len=None,
-                      exponential_shift_mu=None):
-        if shift is not None:
-            self.shift = shift
-        sigma_start = self.sigma_min + (self.sigma_max - self.sigma_min) * denoising_strength
-        if self.extra_one_step:
-            self.sigmas = torch.linspace(sigma_start, self.sigma_min, num_inference_steps + 1)[:-1]
+    def set_timesteps(self, num_inference_steps=100, denoising_strength=1.0, training=False, dynamic_shift_len=None,
+                      exponential_shift_mu=None, **_):
+        """flow_match.py:34-69 for this configuration.  The torch ops and their order are the bit-exactness contract (fp32 CPU
+        tensors; `math.exp(mu)` in double, folded into the tensor expression exactly as there)."""
+        top = self.sigma_min + (self.sigma_max - self.sigma_min) * denoising_strength
+        grid = torch.linspace(top, self.sigma_min, num_inference_steps + 1)[:-1]           # extra_one_step: N+1 points, last dropped
+        if exponential_shift_mu is not None:
+            mu = exponential_shift_mu
+        elif dynamic_shift_len is not None:
+            mu = self.calculate_shift(dynamic_shift_len)
         else:
-            self.sigmas = torch.linspace(sigma_start, self.sigma_min, num_inference_steps)
-        if self.inverse_timesteps:
-            self.sigmas = torch.flip(self.sigmas, dims=[0])
-        if self.exponential_shift:
-            if exponential_shift_mu is not None:
-                mu = exponential_shift_mu
-            elif dynamic_shift_len is not None:
-                mu = self.calculate_shift(dynamic_shift_len)
-            else:
-                mu = self.exponential_shift_mu
-            self.sigmas = math.exp(mu) / (math.exp(mu) + (1 / self.sigmas - 1))
-        else:
-            self.sigmas = self.shift * self.sigmas / (1 + (self.shift - 1) * self.sigmas)
-        if self.shift_terminal is not None:
-            one_minus_z = 1 - self.sigmas
-            scale_factor = one_minus_z[-1] / (1 - self.shift_terminal)
-            self.sigmas = 1 - (one_minus_z / scale_factor)
-        if self.reverse_sigmas:
-            self.sigmas = 1 - self.sigmas
+            mu = self.exponential_shift_mu
+        shifted = math.exp(mu) / (math.exp(mu) + (1 / grid - 1))
+        gap = 1 - shifted                                                                    # stretch so that the last sigma is shift_terminal
+        self.sigmas = 1 - (gap / (gap[-1] / (1 - self.shift_terminal)))
         self.timesteps = self.sigmas * self.num_train_timesteps
-        if training:
-            x = self.timesteps
-            y = torch.exp(-2 * ((x - num_inference_steps / 2) / num_inference_steps) ** 2)
-            y_shifted = y - y.min()
-            self.linear_timesteps_weights = y_shifted * (num_inference_steps / y_shifted.sum())
-            self.training = True
-        else:
-            self.training = False
+        self.training = bool(training)
+        if training:                                                                         # :62-66 bell-shaped loss weights, sum = N
+            bell = torch.exp(-2 * ((self.timesteps - num_inference_steps / 2) / num_inference_steps) ** 2)
+            bell = bell - bell.min()
+            self.linear_timesteps_weights = bell * (num_inference_steps / bell.sum())
 
     def _timestep_id(self, timestep):
         if isinstance(timestep, torch.Tensor):
@@ -69,7 +59,7 @@ class FlowMatchScheduler:
         tid = self._timestep_id(timestep)
         sigma = self.sigmas[tid]
         if to_final or tid + 1 >= len(self.timesteps):
-            sigma_ = 1 if (self.inverse_timesteps or self.reverse_sigmas) else 0
+            sigma_ = 0
         else:
             sigma_ = self.sigmas[tid + 1]
         return sigma_ - sigma
@@ -101,6 +91,8 @@ class FlowMatchScheduler:
 
     def calculate_shift(self, image_seq_len, base_seq_len: int = 256, max_seq_len: int = 8192, base_shift: float = 0.5,
                         max_shift: float = 0.9):
-        m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
-        b = base_shift - m * base_seq_len
-        return image_seq_len * m + b
+        """:114-125: mu is linear in the number of latent tokens (0.5 at 256, 0.9 at 8192, extrapolating beyond).  Same double
+        arithmetic, same order: slope, intercept, then len * slope + intercept."""
+        slope = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+        intercept = base_shift - slope * base_seq_len
+        return image_seq_len * slope + intercept

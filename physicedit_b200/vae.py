@@ -355,6 +355,8 @@ class QwenImageVAE(nn.Module):
         out = torch.empty((x.shape[0], 3, x.shape[2] * 8, x.shape[3] * 8), dtype=torch.bfloat16, device=x.device)
         for b in range(x.shape[0]):
             self._decode_one(nat, P, x[b].contiguous(), out[b])
+        if kwargs.get("check_async", True):
+            nat.check_async()          # the image goes to the host next: a timed-out kernel must raise here, not return garbage
         return out.unsqueeze(2) if five_d else out
 
     def _decode_one(self, nat, P, lat, out):
@@ -394,6 +396,8 @@ class QwenImageVAE(nn.Module):
         out = torch.empty((x.shape[0], 16, x.shape[2] // 8, x.shape[3] // 8), dtype=torch.bfloat16, device=x.device)
         for b in range(x.shape[0]):
             self._encode_one(nat, P, x[b].contiguous(), out[b])
+        if kwargs.get("check_async", True):
+            nat.check_async()          # once per image, before the latents enter a 50-step loop
         return out.unsqueeze(2) if five_d else out
 
     def _encode_one(self, nat, P, img, out):

@@ -4,7 +4,7 @@ emulation (tests/abi_emulator.py) on seeded ragged inputs, then whole encode / d
 
 Tolerances: layout kernels bit-exact; the convolution / GEMM differ from an fp32 CPU conv only by summation order, i.e. by at most one
 bf16 rounding of a value (checked as: <= 1 bf16 ulp everywhere, and rel-L2 <= 2e-3); whole-model error vs the fp32 oracle must stay
-within the reference's own bf16-vs-fp32 noise floor (measured in the goldens, ~1.1e-2) x 1.5 + 1e-3."""
+within the reference's own bf16-vs-fp32 noise floor (measured in the goldens, ~1.1e-2) + 1e-3 -- the DiT's rule."""
 import os
 import sys
 
@@ -197,8 +197,8 @@ def test_vae_encode_decode_match_reference_goldens(nat, vae, golden):
         err_d, err_e = rel_l2(dec, c["fp32"]["decode"]), rel_l2(enc, c["fp32"]["encode"])
         print(f"vae {key}: decode err {err_d:.3e} (reference bf16 floor {floor_d:.3e}), encode err {err_e:.3e} (floor {floor_e:.3e}), "
               f"vs reference bf16: decode {rel_l2(dec, c['bf16']['decode']):.3e} encode {rel_l2(enc, c['bf16']['encode']):.3e}")
-        assert err_d <= floor_d * 1.5 + 1e-3, (key, err_d, floor_d)
-        assert err_e <= floor_e * 1.5 + 1e-3, (key, err_e, floor_e)
+        assert err_d <= floor_d + 1e-3, (key, err_d, floor_d)
+        assert err_e <= floor_e + 1e-3, (key, err_e, floor_e)
 
 
 @gpu
@@ -217,8 +217,10 @@ def test_vae_mid_size_vs_fp32_oracle_and_batch(nat, vae):
     want_d = VO.decode(Wf, inp["latents"].float())
     want_e = VO.encode(Wf, inp["image"].float())
     err_d, err_e = rel_l2(dec[:1], want_d), rel_l2(enc, want_e)
-    print(f"vae 24x40: decode err {err_d:.3e}, encode err {err_e:.3e} vs fp32 oracle")
-    assert err_d <= 2.0e-2 and err_e <= 2.0e-2          # 1.5 x the reference's bf16 floor (1.1e-2 .. 1.25e-2) + 1e-3
+    # floor at THIS size: the oracle's bf16 mode (the reference's arithmetic op by op, pinned by tests/test_vae_oracle.py) vs its fp32 mode
+    floor_d, floor_e = rel_l2(VO.decode(W, inp["latents"]), want_d), rel_l2(VO.encode(W, inp["image"]), want_e)
+    print(f"vae 24x40: decode err {err_d:.3e} (floor {floor_d:.3e}), encode err {err_e:.3e} (floor {floor_e:.3e}) vs fp32 oracle")
+    assert err_d <= floor_d + 1e-3 and err_e <= floor_e + 1e-3, (err_d, floor_d, err_e, floor_e)
     assert torch.equal(m.decode(lat[1:])[0], dec[1]), "batch element 1 differs from a single-image call"
     # 5-D (B, C, 1, H, W) inputs keep their frame axis, as in the reference (:706-735)
     assert m.decode(lat[:1].unsqueeze(2)).shape == (1, 3, 1, 192, 320)
