@@ -112,6 +112,9 @@ int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int 
                                             max every step; r1: same speed isolated, 2 % slower inside the denoise loop -> not the default */
 #define PE_ATTN_FLAG_KV64 16           /* attention_kernel3: 64-row KV steps with two S buffers per query tile in TMEM, so S(j+2) is issued
                                             one step ahead and the softmax never waits on the PV -> S latency chain */
+#define PE_ATTN_FLAG_HALF_ROW 32        /* attention_kernel4: two threads per query row like kernel2, but the exponent reference trails the row
+                                            max by one KV step (no per-step exchange between the two owners) and part of the exponentials
+                                            run on the FMA pipe; a step whose logits jump > 2^100 over the reference is redone exactly */
 int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v, void* o,
                      int S, int H, int64_t ld, float scale, int flags, void* stream);
 

@@ -22,6 +22,7 @@ struct Handle {
     // scratch owned by the handle (tile counters, split reductions ...)
     void* workspace = nullptr;
     size_t workspace_bytes = 0;
+    int attn_seq = 0;                        // launch counter of the half-row attention kernel (names its overflow flags)
 };
 
 int set_error(Handle* h, int code, const char* fmt, ...);

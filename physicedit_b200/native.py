@@ -32,6 +32,7 @@ ATTN_FLAG_SINGLE_Q_TILE = 1
 ATTN_FLAG_P_VIA_SMEM = 2
 ATTN_FLAG_SPLIT_ROW_SOFTMAX = 8
 ATTN_FLAG_KV64 = 16
+ATTN_FLAG_HALF_ROW = 32
 
 EXPORTED_SYMBOLS = [
     "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count", "pe_workspace",

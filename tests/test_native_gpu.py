@@ -84,7 +84,7 @@ def test_gemm_rejects_bad_arguments(nat):
 
 
 @gpu
-@pytest.mark.parametrize("flags", [0, 16, 8, 1, 2, 3])
+@pytest.mark.parametrize("flags", [0, 32, 16, 8, 1, 2, 3])
 @pytest.mark.parametrize("S,H", [(256, 2), (1000, 3), (130, 1), (60, 1), (64, 1), (8480, 2)])
 def test_attention_vs_fp32_softmax(nat, flags, S, H):
     torch.manual_seed(S)
@@ -110,14 +110,14 @@ def test_attention_peaked_rows_trigger_lazy_rescale(nat):
     v = torch.randn(S, 128, device="cuda").bfloat16()
     o = torch.zeros_like(q)
     ref = torch.softmax(q.float() @ k.float().t() / math.sqrt(128), dim=-1) @ v.float()
-    for flags in (0, 8, 16):
+    for flags in (0, 8, 16, 32):
         nat.attention(q, k, v, o, H, 1 / math.sqrt(128), flags)
         nat.check_async()
         assert rel_l2(o, ref) < 5e-3
     # a jump of more than 2^100 between consecutive KV tiles takes the overflow-guard (redo) path
     k2 = torch.randn(S, 128, device="cuda").bfloat16()
     k2[384:] *= 60.0
-    for flags in (0, 8, 3, 16):
+    for flags in (0, 8, 3, 16, 32):        # (32: the trailing-reference kernel flags the item and the exact kernel redoes it)
         nat.attention(q, k2, v, o, H, 1 / math.sqrt(128), flags)
         nat.check_async()
         ref = torch.softmax(q.float() @ k2.float().t() / math.sqrt(128), dim=-1) @ v.float()
@@ -404,7 +404,7 @@ def test_training_loss_forward_value(golden):
 # sizes in seconds, the properties can.
 # ---------------------------------------------------------------------------------------------------------------------
 @gpu
-@pytest.mark.parametrize("flags", [0, 8, 16])
+@pytest.mark.parametrize("flags", [0, 8, 16, 32])
 def test_full_size_attention_properties(nat, flags):
     S, H = 8192 + 512, 24
     d = H * 128

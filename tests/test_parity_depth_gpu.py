@@ -103,7 +103,7 @@ def oracle_forward(sd, ad, inp, t, H, W, dtype, layers, bf16_timestep=False):
     reference's fp32 and bf16 modes (a phase shift of up to ~2 rad in the top sinusoid components), so the floor it gives is
     rounding noise only: the stricter of the two protocols."""
     Wd = Upcast(sd) if dtype == torch.float32 else sd
-    Ad = Upcast(ad) if dtype == torch.float32 else ad
+    Ad = Upcast(ad) if (dtype == torch.float32 and ad is not None) else ad
     c = lambda x: x.cuda().to(dtype) if x.is_floating_point() else x.cuda()
     tt = t.cuda().to(torch.bfloat16 if bf16_timestep else dtype)
     sp = inp.get("special_token_mask")
@@ -213,7 +213,7 @@ def test_one_block_at_config_4_and_5_shapes(name, S_hw, T):
 
 
 @gpu
-@pytest.mark.parametrize("flags", [0, 16])
+@pytest.mark.parametrize("flags", [0, 16, 32])
 def test_attention_config4_sequence_vs_fp32(flags):
     """S = 16384 + 4096 + 512 = 20992, 24 heads: every output element against exact fp32 softmax attention (one head at a time)."""
     from physicedit_b200 import native as nv
