@@ -4,7 +4,9 @@
   `load_state_dict(strict=False)`) into the native classes without copying weights (`load_state_dict(assign=True)`).
 * `install()`: registers a `diffsynth` alias package so that the imports used by scripts/inference/*.py and
   scripts/train/train_physicedit.py (`from diffsynth import load_state_dict`, `from diffsynth.pipelines.qwen_image_physical import
-  QwenImagePhysicPipeline, ModelConfig`, `from diffsynth.pipelines.flux_image_new import ControlNetInput`) resolve here.
+  QwenImagePhysicPipeline, ModelConfig`, `from diffsynth.pipelines.flux_image_new import ControlNetInput`,
+  `from diffsynth.trainers.utils import DiffusionTrainingModule, ModelLogger, qwen_image_parser, ...`,
+  `from diffsynth.trainers.unified_dataset import UnifiedDataset`) resolve here.
 """
 from __future__ import annotations
 
@@ -58,7 +60,7 @@ class ControlNetInput:
 
 
 def install() -> None:
-    from . import pipeline, scheduler, lora, dit, adapters, model_fn, vae
+    from . import pipeline, scheduler, lora, dit, adapters, model_fn, vae, units, trainers
 
     def mod(name, **attrs):
         m = types.ModuleType(name)
@@ -70,7 +72,14 @@ def install() -> None:
     root.__path__ = []
     mod("diffsynth.pipelines").__path__ = []
     mod("diffsynth.pipelines.qwen_image_physical", QwenImagePhysicPipeline=pipeline.QwenImagePhysicPipeline, ModelConfig=pipeline.ModelConfig,
-        model_fn_qwen_image=model_fn.model_fn_qwen_image, SPECIAL_TOKEN_NUM=pipeline.SPECIAL_TOKEN_NUM)
+        model_fn_qwen_image=model_fn.model_fn_qwen_image, SPECIAL_TOKEN_NUM=pipeline.SPECIAL_TOKEN_NUM,
+        **{k: getattr(units, k) for k in dir(units) if k.startswith("QwenImageUnit_") or k in ("PipelineUnit", "PipelineUnitRunner", "SYSTEM_PROMPT_SAMPLE")})
+    mod("diffsynth.utils", BasePipeline=pipeline.QwenImagePhysicPipeline, ModelConfig=pipeline.ModelConfig, PipelineUnit=units.PipelineUnit,
+        PipelineUnitRunner=units.PipelineUnitRunner)
+    mod("diffsynth.trainers").__path__ = []
+    mod("diffsynth.trainers.utils", **{k: getattr(trainers, k) for k in ("DiffusionTrainingModule", "ModelLogger", "qwen_image_parser",
+                                                                          "launch_training_task", "launch_data_process_task", "PhysicalEditingDataset")})
+    mod("diffsynth.trainers.unified_dataset", UnifiedDataset=trainers.UnifiedDataset)
     mod("diffsynth.pipelines.flux_image_new", ControlNetInput=ControlNetInput)
     mod("diffsynth.pipelines.helpers", **{k: getattr(adapters, k) for k in ("FeedForward", "PerceiverAttention", "PerceiverResampler",
                                                                               "VisualThinkingAdapter", "VisualThinkingDualAdapter")})

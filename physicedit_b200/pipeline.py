@@ -27,6 +27,7 @@ from .dit import QwenImageDiT
 from .lora import GeneralLoRALoader
 from .model_fn import model_fn_qwen_image, prompt_lengths
 from .scheduler import FlowMatchScheduler
+from .units import PipelineUnit, PipelineUnitRunner, QwenImageUnit_PhysicalVerbalEmbedder, QwenImageUnit_PhysicalVisualEmbedder, default_units
 from .vae import QwenImageVAE
 
 SPECIAL_TOKEN_NUM = 64        # qwen_image_physical.py:28
@@ -157,7 +158,10 @@ class QwenImagePhysicPipeline(nn.Module):
         self.blockwise_controlnet = None
         self.tokenizer = None
         self.processor = None
+        self.boi_token_id = self.eoi_token_id = None
+        self.unit_runner = PipelineUnitRunner()
         self.in_iteration_models = ("dit", "blockwise_controlnet", "visual_thinking_adapter")
+        self.units = default_units()
         self.model_fn = model_fn_qwen_image
         self.special_token_loss = 0.0
         self.vram_management_enabled = False
@@ -166,23 +170,62 @@ class QwenImagePhysicPipeline(nn.Module):
     @staticmethod
     def from_pretrained(torch_dtype=torch.bfloat16, device="cuda", model_configs=(), tokenizer_config=None, processor_config=None,
                         dinov2_path=None):
+        """:497-541.  Model files are recognised by the md5 of their state-dict keys + shapes like the reference's ModelManager
+        (models/model_manager.py:350-376; registry rows configs/model_config.py:21-24): DiT, VAE and the Qwen2.5-VL text encoder.
+        `tokenizer_config` / `processor_config` point at local folders (no network): Qwen2Tokenizer / Qwen2VLProcessor, plus the 66
+        added special tokens `<begin_of_img> <end_of_img> <img0..63>` (:528-539)."""
         pipe = QwenImagePhysicPipeline(device=device, torch_dtype=torch_dtype, dinov2_path=dinov2_path)
         for cfg in model_configs:
             cfg.download_if_necessary()
             paths = cfg.path if isinstance(cfg.path, list) else [cfg.path]
+            dtype = cfg.offload_dtype or torch_dtype
             try:
-                dtype = cfg.offload_dtype or torch_dtype
                 sd = load_state_dict(paths if len(paths) > 1 else paths[0], torch_dtype=dtype, device="cpu")
-                if hash_state_dict_keys(sd) == VAE_KEY_HASH:          # model detection by key hash (model_manager.py:350-376)
+                key_hash = hash_state_dict_keys(sd)
+                if key_hash == VAE_KEY_HASH:
                     pipe.vae = load_vae(paths, torch_dtype=dtype, device=device, state_dict=sd)
-                    continue
-                model = load_dit(paths, torch_dtype=dtype, device=device, state_dict=sd)
+                elif key_hash == DIT_KEY_HASH:
+                    pipe.dit = load_dit(paths, torch_dtype=dtype, device=device, state_dict=sd)
+                else:
+                    from .text_encoder import load_text_encoder
+                    te = load_text_encoder(sd, torch_dtype=dtype, device=device)
+                    if te is not None:
+                        pipe.text_encoder = te
+                    else:
+                        print(f"    We cannot detect the model type. No models are loaded ({paths}).")
             except Exception as e:  # noqa: BLE001  (the reference's loader prints and moves on, model_manager.py:375-376)
                 print(f"    Loading {paths} failed: {e}")
-                model = None
-            if model is not None:
-                pipe.dit = model
+        pipe.attach_tokenizer(tokenizer_config, processor_config)
         return pipe
+
+    def attach_tokenizer(self, tokenizer_config=None, processor_config=None, tokenizer=None, processor=None):
+        """:522-539: tokenizer (only needed with a text encoder), processor, and the special tokens whose ids delimit the 64 rows the
+        adapter rewrites.  Objects can be handed in directly (tests); otherwise they are loaded from the configs' local paths."""
+        if tokenizer is None and tokenizer_config is not None and self.text_encoder is not None:
+            tokenizer_config.download_if_necessary()
+            from transformers import Qwen2Tokenizer
+            tokenizer = Qwen2Tokenizer.from_pretrained(tokenizer_config.path)
+        if processor is None and processor_config is not None:
+            processor_config.download_if_necessary()
+            from transformers import Qwen2VLProcessor
+            processor = Qwen2VLProcessor.from_pretrained(processor_config.path)
+        self.tokenizer = tokenizer if tokenizer is not None else self.tokenizer
+        if processor is not None:
+            self.processor = processor
+            processor.tokenizer.add_special_tokens({"additional_special_tokens": ["<begin_of_img>", "<end_of_img>"] + [f"<img{i}>" for i in range(SPECIAL_TOKEN_NUM)]})
+            self.boi_token_id = processor.tokenizer.convert_tokens_to_ids("<begin_of_img>")
+            self.eoi_token_id = processor.tokenizer.convert_tokens_to_ids("<end_of_img>")
+        return self
+
+    def to(self, *args, **kwargs):
+        """BasePipeline.to (utils/__init__.py:33-40): device / dtype of the intermediates follow the move."""
+        device, dtype, _, _ = torch._C._nn._parse_to(*args, **kwargs)
+        if device is not None:
+            self.device = device
+        if dtype is not None:
+            self.torch_dtype = dtype
+        super().to(*args, **kwargs)
+        return self
 
     def load_lora(self, module: nn.Module, lora_config=None, alpha=1, hotload=False, state_dict=None):
         if hotload:
@@ -364,42 +407,66 @@ class QwenImagePhysicPipeline(nn.Module):
         return latents
 
     @torch.no_grad()
-    def __call__(self, prompt=None, negative_prompt="", cfg_scale=4.0, height=1328, width=1328, seed=None, rand_device="cpu",
-                 num_inference_steps=30, edit_image=None, edit_image_auto_resize=True, context_image=None, is_train=True,
-                 progress_bar_cmd=None, tiled=False, tile_size=128, tile_stride=64,
-                 prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, context_latents=None,
-                 output_type="pil", **kwargs):
-        """Reference signature subset.  The pre-loop units that need the Qwen2.5-VL encoder / VAE run only if those
-        modules were attached (`pipe.text_encoder`, `pipe.vae`); otherwise pass `prompt_inputs_posi/nega` and
-        `edit_latents` and get latents back (`output_type="latent"`)."""
-        height, width = self.check_resize_height_width(height, width)
-        latents = self.generate_noise((1, 16, height // 8, width // 8), seed=seed, rand_device=rand_device)
-        if prompt_inputs_posi is None:
-            if self.text_encoder is None:
-                raise RuntimeError("no text encoder attached: pass prompt_inputs_posi / prompt_inputs_nega (prompt_emb, prompt_emb_mask, "
-                                   "special_token_mask) -- the Qwen2.5-VL encoder is outside this framework's scope (SURVEY 8f2)")
-            prompt_inputs_posi = self.text_encoder.encode_for_pipeline(self, prompt, edit_image, positive=True)
-            prompt_inputs_nega = self.text_encoder.encode_for_pipeline(self, negative_prompt, edit_image, positive=False)
-        if edit_latents is None and edit_image is not None:
-            if self.vae is None:
-                raise RuntimeError("no VAE loaded: pass edit_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
-            # QwenImageUnit_EditImageEmbedder.process (qwen_image_physical.py:1265-1285): one image or a list of images, each resized to
-            # ~1024^2 pixels on a 32-pixel grid first unless edit_image_auto_resize=False (tensors are taken as already pre-processed)
-            def prep(im):
-                if isinstance(im, torch.Tensor):
-                    return im
-                return self.preprocess_image(self.auto_resize_edit_image(im) if edit_image_auto_resize else im)
-            imgs = edit_image if isinstance(edit_image, (list, tuple)) else [edit_image]
-            enc = [self.vae.encode(prep(im), tiled=tiled, tile_size=tile_size, tile_stride=tile_stride) for im in imgs]
-            edit_latents = enc if isinstance(edit_image, (list, tuple)) else enc[0]
-        if context_latents is None and context_image is not None:
-            if self.vae is None:
-                raise RuntimeError("no VAE loaded: pass context_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
-            # QwenImageUnit_ContextImageEmbedder.process (:1293-1299): resized to the output size
-            ctx = context_image if isinstance(context_image, torch.Tensor) else self.preprocess_image(context_image.resize((width, height)))
-            context_latents = self.vae.encode(ctx, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
-        latents = self.denoise(latents, prompt_inputs_posi, prompt_inputs_nega, edit_latents, context_latents, height=height, width=width,
-                               num_inference_steps=num_inference_steps, cfg_scale=cfg_scale, progress_bar_cmd=progress_bar_cmd)
+    def __call__(self, prompt=None, negative_prompt="", cfg_scale=4.0, input_image=None, denoising_strength=1.0, inpaint_mask=None,
+                 inpaint_blur_size=None, inpaint_blur_sigma=None, height=1328, width=1328, seed=None, rand_device="cpu", num_inference_steps=30,
+                 exponential_shift_mu=None, blockwise_controlnet_inputs=None, eligen_entity_prompts=None, eligen_entity_masks=None,
+                 eligen_enable_on_negative=False, edit_image=None, edit_image_auto_resize=True, edit_rope_interpolation=False, context_image=None,
+                 enable_fp8_attention=False, tiled=False, tile_size=128, tile_stride=64, progress_bar_cmd=None, supported_rules=None,
+                 contradicted_rules=None, middle_key_frames=None, stitched_image=None, state=None, transition=None, triplet=None, is_train=True,
+                 have_text_reasoning=True,
+                 prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, context_latents=None, output_type="pil"):
+        """:544-669, same keyword surface.  The request is carried in three dictionaries (shared / positive / negative) through
+        `self.units` by `self.unit_runner`; then the CFG denoise loop (native: `denoise`) and the VAE decode.  Extras beyond the
+        reference: `prompt_inputs_posi/nega`, `edit_latents`, `context_latents` hand over pre-computed unit outputs (a unit whose
+        model is absent returns nothing, so they survive), `output_type="latent"` skips the decode."""
+        if inpaint_mask is not None:
+            raise NotImplementedError("inpainting (inpaint_mask) is outside the PhysicEdit hot path: no PhysicEdit script passes it")
+        inputs_posi = dict(prompt_inputs_posi or {}, prompt=prompt)
+        inputs_nega = dict(prompt_inputs_nega or {}, negative_prompt=negative_prompt)
+        inputs_shared = {
+            "cfg_scale": cfg_scale, "input_image": input_image, "denoising_strength": denoising_strength, "inpaint_mask": inpaint_mask,
+            "inpaint_blur_size": inpaint_blur_size, "inpaint_blur_sigma": inpaint_blur_sigma, "height": height, "width": width, "seed": seed,
+            "rand_device": rand_device, "enable_fp8_attention": enable_fp8_attention, "num_inference_steps": num_inference_steps,
+            "blockwise_controlnet_inputs": blockwise_controlnet_inputs, "tiled": tiled, "tile_size": tile_size, "tile_stride": tile_stride,
+            "eligen_entity_prompts": eligen_entity_prompts, "eligen_entity_masks": eligen_entity_masks,
+            "eligen_enable_on_negative": eligen_enable_on_negative, "edit_image": edit_image, "edit_image_auto_resize": edit_image_auto_resize,
+            "edit_rope_interpolation": edit_rope_interpolation, "context_image": context_image, "supported_rules": supported_rules,
+            "contradicted_rules": contradicted_rules, "middle_key_frames": middle_key_frames, "stitched_image": stitched_image, "state": state,
+            "transition": transition, "triplet": triplet, "is_train": is_train,
+        }
+        # the scheduler table must exist before the units run (InputImageEmbedder adds noise at timesteps[0], :600)
+        self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength, dynamic_shift_len=(height // 16) * (width // 16),
+                                     exponential_shift_mu=exponential_shift_mu)
+        units = [u for u in self.units if u is not None]
+        if not is_train:
+            units = [u for u in units if not isinstance(u, QwenImageUnit_PhysicalVisualEmbedder)]
+        if not have_text_reasoning:
+            units = [u for u in units if not isinstance(u, QwenImageUnit_PhysicalVerbalEmbedder)]
+        if self.vae is None and ((edit_image is not None and edit_latents is None) or (context_image is not None and context_latents is None)
+                                 or input_image is not None):
+            raise RuntimeError("no VAE loaded: pass edit_latents / context_latents, or load the qwen_image_vae checkpoint (load_vae / from_pretrained)")
+        if edit_latents is not None and self.text_encoder is None:   # pre-computed latents AND prompt embeddings: the image itself is not needed
+            inputs_shared["edit_image"] = None
+        for unit in units:
+            if self.vae is None and unit.onload_model_names == ("vae",) and not (unit.input_params and "noise" in unit.input_params):
+                continue                                  # no VAE loaded: image-embedding units have nothing to run on (latents must be handed in)
+            inputs_shared, inputs_posi, inputs_nega = self.unit_runner(unit, self, inputs_shared, inputs_posi, inputs_nega)
+        if edit_latents is not None:
+            inputs_shared["edit_latents"] = edit_latents
+        if context_latents is not None:
+            inputs_shared["context_latents"] = context_latents
+        if "prompt_emb" not in inputs_posi:
+            raise RuntimeError("no prompt embedding: load the Qwen2.5-VL text encoder (from_pretrained / load_text_encoder) together with the "
+                               "tokenizer and processor, or pass prompt_inputs_posi / prompt_inputs_nega (prompt_emb, prompt_emb_mask, special_token_mask)")
+        if any(inputs_posi.get(k) is not None for k in ("entity_prompt_emb",)) or inputs_shared.get("blockwise_controlnet_conditioning"):
+            raise NotImplementedError("EliGen entity control / blockwise controlnet reach model_fn, which does not implement them (SURVEY 8f5)")
+        height, width = inputs_shared["height"], inputs_shared["width"]
+        keys = ("prompt_emb", "prompt_emb_mask", "special_token_mask")
+        posi = {k: inputs_posi.get(k) for k in keys}
+        nega = {k: inputs_nega.get(k) for k in keys} if (cfg_scale != 1.0 and "prompt_emb" in inputs_nega) else None
+        latents = self.denoise(inputs_shared["latents"], posi, nega, inputs_shared.get("edit_latents"), inputs_shared.get("context_latents"),
+                               height=height, width=width, num_inference_steps=num_inference_steps, cfg_scale=cfg_scale,
+                               denoising_strength=denoising_strength, exponential_shift_mu=exponential_shift_mu, progress_bar_cmd=progress_bar_cmd)
         if output_type == "latent" or self.vae is None:
             return latents
         image = self.vae.decode(latents, device=self.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)

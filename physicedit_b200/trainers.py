@@ -1,0 +1,166 @@
+"""The `diffsynth.trainers.*` names scripts/train/train_physicedit.py imports (:1-6), so that the script resolves against this
+framework under `compat.install()`.
+
+In scope here is only what touches the hot path's checkpoint / module contract: `DiffusionTrainingModule` (which parameters are
+trainable, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into LoRA and
+`pipe.*` keys), `ModelLogger` (who writes that file) and the argument parser's flag set.  Dataset readers and the accelerate
+training loop are the reference's training control plane (OUT OF SCOPE; backward through the native kernels is
+row 8f3): their names exist and fail loudly when used.
+Reference: DiffSynth-Studio/diffsynth/trainers/utils.py:777-1115.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+
+import torch
+
+from .pipeline import ModelConfig
+
+
+class DiffusionTrainingModule(torch.nn.Module):
+    """trainers/utils.py:777-888."""
+
+    def to(self, *args, **kwargs):
+        for _, model in self.named_children():
+            model.to(*args, **kwargs)
+        return self
+
+    def trainable_modules(self):
+        return (p for p in self.parameters() if p.requires_grad)
+
+    def trainable_param_names(self):
+        return {n for n, p in self.named_parameters() if p.requires_grad}
+
+    def add_lora_to_model(self, model, target_modules, lora_rank, lora_alpha=None, upcast_dtype=None):
+        """PEFT injection of un-merged LoRA (:799-808).  The DiT keeps real nn.Linear modules under the reference's names, so PEFT can
+        wrap them -- but the native forward reads the folded weights only (no per-step LoRA compute), hence training
+        through it needs row 8f3."""
+        try:
+            from peft import LoraConfig, inject_adapter_in_model
+        except ImportError as e:
+            raise ImportError("add_lora_to_model needs `peft` (not installed here); inference folds LoRA with pipe.load_lora instead") from e
+        model = inject_adapter_in_model(LoraConfig(r=lora_rank, lora_alpha=lora_alpha or lora_rank, target_modules=target_modules), model)
+        if upcast_dtype is not None:
+            for p in model.parameters():
+                if p.requires_grad:
+                    p.data = p.to(upcast_dtype)
+        return model
+
+    def mapping_lora_state_dict(self, state_dict):
+        """PEFT keys without an adapter name get `.default` (:811-819): the layout GeneralLoRALoader.get_name_dict expects."""
+        out = {}
+        for k, v in state_dict.items():
+            if "lora_A.default.weight" in k or "lora_B.default.weight" in k:
+                out[k] = v
+            elif "lora_A.weight" in k or "lora_B.weight" in k:
+                out[k.replace("lora_A.weight", "lora_A.default.weight").replace("lora_B.weight", "lora_B.default.weight")] = v
+        return out
+
+    def export_trainable_state_dict(self, state_dict, remove_prefix=None):
+        """Trainable parameters only, `remove_prefix` (normally "pipe.dit.") stripped (:822-832): LoRA keys come out as
+        `transformer_blocks.N...lora_A.default.weight`, adapter keys keep `pipe.visual_thinking_adapter...`."""
+        names = self.trainable_param_names()
+        out = {}
+        for k, v in state_dict.items():
+            if k in names:
+                out[k[len(remove_prefix):] if (remove_prefix and k.startswith(remove_prefix)) else k] = v
+        return out
+
+    def transfer_data_to_device(self, data, device, torch_float_dtype=None):
+        for k, v in data.items():
+            if isinstance(v, torch.Tensor):
+                v = v.to(device)
+                if torch_float_dtype is not None and v.is_floating_point():
+                    v = v.to(torch_float_dtype)
+                data[k] = v
+        return data
+
+    def parse_model_configs(self, model_paths, model_id_with_origin_paths, enable_fp8_training=False, local_model_path=None, skip_download=False):
+        if enable_fp8_training:
+            raise NotImplementedError("fp8 weight storage (enable_fp8_training) is outside the hot path (SURVEY 8f5)")
+        cfgs = [ModelConfig(path=p) for p in json.loads(model_paths)] if model_paths is not None else []
+        for spec in (model_id_with_origin_paths.split(",") if model_id_with_origin_paths else []):
+            mid, pattern = spec.split(":")
+            cfgs.append(ModelConfig(model_id=mid, origin_file_pattern=pattern, local_model_path=local_model_path, skip_download=skip_download))
+        return cfgs
+
+
+class ModelLogger:
+    """trainers/utils.py:891-929: rank 0 writes the trainable-only state dict as safetensors at epoch end / every save_steps."""
+
+    def __init__(self, output_path, remove_prefix_in_ckpt=None, state_dict_converter=lambda x: x):
+        self.output_path = output_path
+        self.remove_prefix_in_ckpt = remove_prefix_in_ckpt
+        self.state_dict_converter = state_dict_converter
+        self.num_steps = 0
+
+    def on_step_end(self, accelerator, model, save_steps=None):
+        self.num_steps += 1
+        if save_steps is not None and self.num_steps % save_steps == 0:
+            self.save_model(accelerator, model, f"step-{self.num_steps}.safetensors")
+
+    def on_epoch_end(self, accelerator, model, epoch_id):
+        self.save_model(accelerator, model, f"epoch-{epoch_id}.safetensors")
+
+    def on_training_end(self, accelerator, model, save_steps=None):
+        if save_steps is not None and self.num_steps % save_steps != 0:
+            self.save_model(accelerator, model, f"step-{self.num_steps}.safetensors")
+
+    def save_model(self, accelerator, model, file_name):
+        accelerator.wait_for_everyone()
+        if accelerator.is_main_process:
+            sd = accelerator.unwrap_model(model).export_trainable_state_dict(accelerator.get_state_dict(model), remove_prefix=self.remove_prefix_in_ckpt)
+            os.makedirs(self.output_path, exist_ok=True)
+            accelerator.save(self.state_dict_converter(sd), os.path.join(self.output_path, file_name), safe_serialization=True)
+
+
+# flag, type (None = store_true), default, required  -- the flag set of qwen_image_parser (:1072-1115)
+_FLAGS = [
+    ("dataset_base_path", str, "", True), ("dataset_metadata_path", str, None, False), ("max_pixels", int, 1024 * 1024, False), ("height", int, None, False),
+    ("width", int, None, False), ("data_file_keys", str, "image", False), ("dataset_repeat", int, 1, False), ("model_paths", str, None, False),
+    ("model_id_with_origin_paths", str, None, False), ("tokenizer_path", str, None, False), ("learning_rate", float, 1e-4, False), ("num_epochs", int, 1, False),
+    ("output_path", str, "./models", False), ("remove_prefix_in_ckpt", str, "pipe.dit.", False), ("trainable_models", str, None, False),
+    ("lora_base_model", str, None, False), ("lora_target_modules", str, "q,k,v,o,ffn.0,ffn.2", False), ("lora_rank", int, 32, False),
+    ("lora_checkpoint", str, None, False), ("extra_inputs", str, None, False), ("use_gradient_checkpointing", None, False, False),
+    ("use_gradient_checkpointing_offload", None, False, False), ("gradient_accumulation_steps", int, 1, False), ("find_unused_parameters", None, False, False),
+    ("save_steps", int, None, False), ("dataset_num_workers", int, 0, False), ("weight_decay", float, 0.01, False), ("processor_path", str, None, False),
+    ("enable_fp8_training", None, False, False), ("task", str, "sft", False), ("num_frames", int, 81, False), ("wandb_project", str, None, False),
+    ("wandb_run_name", str, None, False), ("save_every_n_steps", int, None, False), ("eval_every_n_steps", int, None, False), ("resume_from", str, None, False),
+    ("resume_original_num_processes", int, 4, False), ("local_model_path", str, None, False), ("dinov2_path", str, None, True),
+]
+
+
+def qwen_image_parser():
+    ap = argparse.ArgumentParser(description="Qwen-Image / PhysicEdit training arguments (flag-compatible with the reference's qwen_image_parser).")
+    for name, typ, default, required in _FLAGS:
+        if typ is None:
+            ap.add_argument(f"--{name}", default=False, action="store_true")
+        else:
+            ap.add_argument(f"--{name}", type=typ, default=default, required=required)
+    ap.add_argument("--resume_type", type=str, choices=["auto", "full", "model"], default="auto")
+    return ap
+
+
+def _control_plane(name):
+    def stub(*args, **kwargs):
+        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (dataset readers, accelerate loop): outside the "
+                                  "hot path this framework replaces (SURVEY.md section 2 / 8f3).  Use the reference's trainers with "
+                                  "pipe.model_fn = physicedit_b200.model_fn_qwen_image for forward-only evaluation.")
+    stub.__name__ = name
+    return stub
+
+
+launch_training_task = _control_plane("utils.launch_training_task")
+launch_data_process_task = _control_plane("utils.launch_data_process_task")
+
+
+class PhysicalEditingDataset(torch.utils.data.Dataset):
+    def __init__(self, *args, **kwargs):
+        _control_plane("utils.PhysicalEditingDataset")()
+
+
+class UnifiedDataset(torch.utils.data.Dataset):
+    def __init__(self, *args, **kwargs):
+        _control_plane("unified_dataset.UnifiedDataset")()

@@ -1,0 +1,209 @@
+"""The reference's scripts resolve against this framework (CPU; no kernels run here).
+
+* `compat.install()` serves every `diffsynth.*` import of scripts/inference/validate.py and scripts/train/train_physicedit.py,
+* validate.py's own `load_finetuned_into_pipe` (:33-65) -- LoRA keys -> `pipe.load_lora`, `pipe.*` keys -> `pipe.load_state_dict(strict=False)`
+  -- works on this pipeline object with a synthetic checkpoint in the training script's key layout,
+* `pipe(prompt, edit_image=PIL, is_train=False)` walks the unit list through `pipe.unit_runner` with the reference's contracts
+  (processor / tokenizer from the reference tree, a stub VL model and a stub VAE) and reaches the denoise loop with the tensors the
+  reference would hand to `model_fn` (shapes, masks, the 64 special positions, bf16 CPU-generator noise).
+The reference tree (for the scripts and the vendored tokenizer files) is optional: tests that need it skip without it.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "scripts", "inference", "validate.py")), reason="reference tree not present")
+
+
+@pytest.fixture()
+def compat_installed():
+    from physicedit_b200 import compat
+    saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
+    for k in saved:
+        del sys.modules[k]
+    compat.install()
+    yield
+    for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+
+
+def _cpu_pipe(layers=1):
+    from physicedit_b200.dit import QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = QwenImageDiT(num_layers=layers).to(torch.bfloat16)
+    return pipe
+
+
+def test_every_diffsynth_import_of_the_scripts_resolves(compat_installed):
+    src = """
+from diffsynth import load_state_dict
+from diffsynth.pipelines.qwen_image_physical import QwenImagePhysicPipeline, ModelConfig
+from diffsynth.pipelines.flux_image_new import ControlNetInput
+from diffsynth.trainers.utils import DiffusionTrainingModule, ModelLogger, qwen_image_parser, launch_training_task, launch_data_process_task, PhysicalEditingDataset
+from diffsynth.trainers.unified_dataset import UnifiedDataset
+from diffsynth.utils import PipelineUnit, PipelineUnitRunner
+"""
+    ns = {}
+    exec(src, ns)                                                   # lines 2-6 of train_physicedit.py, :17-18 of validate.py
+    args = ns["qwen_image_parser"]().parse_args(["--dataset_base_path", "x", "--dinov2_path", "y", "--lora_rank", "128", "--use_gradient_checkpointing"])
+    assert args.remove_prefix_in_ckpt == "pipe.dit." and args.lora_rank == 128 and args.use_gradient_checkpointing and args.resume_type == "auto"
+    with pytest.raises(NotImplementedError, match="control plane"):
+        ns["PhysicalEditingDataset"](args=args)
+    pipe = _cpu_pipe()
+    names = [type(u).__name__ for u in pipe.units]
+    assert names == ["QwenImageUnit_ShapeChecker", "QwenImageUnit_NoiseInitializer", "QwenImageUnit_InputImageEmbedder", "QwenImageUnit_Inpaint",
+                     "QwenImageUnit_EditImageEmbedder", "QwenImageUnit_ContextImageEmbedder", "QwenImageUnit_PhysicalVisualEmbedder",
+                     "QwenImageUnit_PhysicalVerbalEmbedder", "QwenImageUnit_PromptEmbedder", "QwenImageUnit_EntityControl",
+                     "QwenImageUnit_BlockwiseControlNet"]                # qwen_image_physical.py:233-245, same order
+    assert pipe.in_iteration_models == ("dit", "blockwise_controlnet", "visual_thinking_adapter") and callable(pipe.unit_runner)
+
+
+def test_training_module_exports_the_checkpoint_layout_validate_py_splits():
+    from physicedit_b200.trainers import DiffusionTrainingModule
+
+    class M(DiffusionTrainingModule):
+        def __init__(self):
+            super().__init__()
+            self.pipe = _cpu_pipe()
+    m = M()
+    m.pipe.freeze_except([])
+    blk = m.pipe.dit.transformer_blocks[0]
+    blk.attn.to_q.register_parameter("lora_A_default", torch.nn.Parameter(torch.zeros(4, 3072)))     # stands in for a PEFT-injected tensor
+    for p in m.pipe.visual_thinking_adapter.parameters():
+        p.requires_grad_(True)
+    sd = m.export_trainable_state_dict(m.state_dict(), remove_prefix="pipe.dit.")
+    assert "transformer_blocks.0.attn.to_q.lora_A_default" in sd                                       # `pipe.dit.` stripped
+    assert "pipe.visual_thinking_adapter.head_dino.0.weight" in sd and len(sd) == 1 + 8                 # adapter keys keep `pipe.`
+    assert m.mapping_lora_state_dict({"a.lora_A.weight": 1, "a.lora_B.default.weight": 2, "b.bias": 3}) == {"a.lora_A.default.weight": 1, "a.lora_B.default.weight": 2}
+
+
+@needs_ref
+def test_validate_py_loads_a_finetuned_checkpoint_into_this_pipeline(compat_installed, tmp_path):
+    spec = importlib.util.spec_from_file_location("ref_validate", os.path.join(REF, "scripts", "inference", "validate.py"))
+    sys.dont_write_bytecode = True
+    validate = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(validate)                               # the reference script itself, imports served by compat.install()
+    assert validate.QwenImagePhysicPipeline.__module__.startswith("physicedit_b200")
+    pipe = _cpu_pipe()
+    g = torch.Generator().manual_seed(0)
+    w_q = pipe.dit.transformer_blocks[0].attn.to_q.weight.detach().clone()
+    w_mod = pipe.dit.transformer_blocks[0].img_mod[1].weight.detach().clone()
+    ck = {}
+    for name, (o, i) in (("transformer_blocks.0.attn.to_q", (3072, 3072)), ("transformer_blocks.0.img_mod.1", (18432, 3072))):
+        ck[f"{name}.lora_A.default.weight"] = (torch.randn(8, i, generator=g) * 0.05).bfloat16()         # key layout of train_multigpu.sh:27-31
+        ck[f"{name}.lora_B.default.weight"] = (torch.randn(o, 8, generator=g) * 0.05).bfloat16()
+    ad_new = {k: torch.randn(v.shape, generator=g).bfloat16() for k, v in pipe.visual_thinking_adapter.state_dict().items()}
+    ck.update({f"pipe.visual_thinking_adapter.{k}": v for k, v in ad_new.items()})
+    ck["stray.key"] = torch.zeros(1)                                                                     # not `pipe.`-prefixed: ignored (:57-59)
+    from safetensors.torch import save_file
+    path = str(tmp_path / "step-8000.safetensors")
+    save_file(ck, path)
+    with pytest.raises(FileNotFoundError):
+        validate.load_finetuned_into_pipe(pipe, str(tmp_path / "missing.safetensors"))
+    validate.load_finetuned_into_pipe(pipe, path)
+    for name, w0 in (("transformer_blocks.0.attn.to_q", w_q), ("transformer_blocks.0.img_mod.1", w_mod)):
+        want = w0 + torch.mm(ck[f"{name}.lora_B.default.weight"], ck[f"{name}.lora_A.default.weight"])    # bf16 mm + bf16 add, alpha = 1
+        got = dict(pipe.dit.named_modules())[name].weight
+        assert torch.equal(got, want)
+    for k, v in ad_new.items():
+        assert torch.equal(pipe.visual_thinking_adapter.state_dict()[k], v)
+    assert validate.resize_image(__import__("PIL.Image", fromlist=["Image"]).new("RGB", (640, 480))).size == (1184, 896)
+
+
+class _StubVL:
+    """Stands in for the Qwen2.5-VL encoder with its two entry points (models/qwen_image_text_encoder_withdecode.py:188, HF generate)."""
+
+    def __init__(self, reply_ids):
+        self.reply_ids, self.calls = reply_ids, []
+
+    def edit_forward(self, input_ids=None, attention_mask=None, pixel_values=None, image_grid_thw=None, output_hidden_states=True, **kw):
+        self.calls.append(("edit_forward", input_ids.shape, None if pixel_values is None else tuple(pixel_values.shape)))
+        g = torch.Generator().manual_seed(int(input_ids.sum()) % 1000)
+        return (torch.randn(input_ids.shape[0], input_ids.shape[1], 3584, generator=g),)
+
+    def generate(self, input_ids=None, max_new_tokens=None, **kw):
+        self.calls.append(("generate", input_ids.shape, max_new_tokens))
+        return torch.cat([input_ids, self.reply_ids.unsqueeze(0)], dim=1)
+
+
+class _StubVAE:
+    def encode(self, x, **kw):
+        return torch.zeros(x.shape[0], 16, x.shape[2] // 8, x.shape[3] // 8, dtype=x.dtype)
+
+
+@needs_ref
+def test_call_walks_the_units_and_reaches_the_denoise_loop(monkeypatch):
+    from PIL import Image
+    from transformers import Qwen2Tokenizer, Qwen2VLProcessor
+    from physicedit_b200.pipeline import ModelConfig
+    tok_dir = os.path.join(REF, "DiffSynth-Studio", "models", "Qwen", "Qwen-Image", "tokenizer")
+    proc_dir = os.path.join(REF, "DiffSynth-Studio", "models", "Qwen", "Qwen-Image-Edit", "processor")
+    tok = Qwen2Tokenizer.from_pretrained(tok_dir)
+    base = Qwen2VLProcessor.from_pretrained(proc_dir)
+    # the vendored processor folder carries no vocabulary (its tokenizer knows only the added tokens): give it the real one
+    proc = Qwen2VLProcessor(image_processor=base.image_processor, tokenizer=Qwen2Tokenizer.from_pretrained(tok_dir),
+                            video_processor=base.video_processor, chat_template=base.chat_template)
+    pipe = _cpu_pipe()
+    reply = tok('{"middle_transition_prompt": "The cup tips over and the water spreads."}', return_tensors="pt").input_ids[0]
+    pipe.text_encoder = _StubVL(reply)
+    pipe.vae = _StubVAE()
+    pipe.attach_tokenizer(tokenizer=tok, processor=proc)
+    assert pipe.eoi_token_id - pipe.boi_token_id == 1 and pipe.boi_token_id >= len(tok)                 # the 66 added tokens (:528-539)
+    seen = {}
+
+    def fake_denoise(latents, inputs_posi, inputs_nega, edit_latents=None, context_latents=None, **kw):
+        seen.update(latents=latents, posi=inputs_posi, nega=inputs_nega, edit_latents=edit_latents, kw=kw)
+        return latents
+    monkeypatch.setattr(pipe, "denoise", fake_denoise)
+    img = Image.new("RGB", (800, 600), (90, 120, 30))
+    out = pipe("knock the cup over", edit_image=img, seed=7, num_inference_steps=4, height=500, width=760, is_train=False, output_type="latent")
+    # ShapeChecker rounds up to multiples of 16; NoiseInitializer draws bf16 on the CPU generator (NOT fp32 -> bf16)
+    assert out.shape == (1, 16, 64, 96) and seen["kw"]["height"] == 512 and seen["kw"]["width"] == 768
+    want = torch.randn((1, 16, 64, 96), generator=torch.Generator("cpu").manual_seed(7), dtype=torch.bfloat16)
+    assert torch.equal(out, want)
+    # EditImageEmbedder: auto-resized to ~1024^2 on a 32-pixel grid before the VAE
+    assert seen["edit_latents"].shape == (1, 16, 896 // 8, 1184 // 8)
+    # VerbalEmbedder generated once per CFG branch (<= 1000 new tokens), PromptEmbedder encoded once per branch with the image
+    kinds = [c[0] for c in pipe.text_encoder.calls]
+    assert kinds == ["generate", "generate", "edit_forward", "edit_forward"] and pipe.text_encoder.calls[0][2] == 1000
+    posi, nega = seen["posi"], seen["nega"]
+    T = posi["prompt_emb"].shape[1]
+    assert posi["prompt_emb"].dtype == torch.bfloat16 and posi["prompt_emb_mask"].shape == (1, T) and posi["prompt_emb_mask"].all()
+    sp = posi["special_token_mask"]
+    assert sp.shape == (1, T) and int(sp.sum()) == 64 and sp[0].nonzero().flatten().diff().eq(1).all()   # 64 consecutive <imgN> positions
+    assert nega["prompt_emb"].shape[1] < T and int(nega["special_token_mask"].sum()) == 64               # empty negative prompt, same tail
+    # the generated JSON was parsed and appended to the positive prompt as "\nkey: value" (:859-872, :813-814)
+    edit_calls = [c for c in pipe.text_encoder.calls if c[0] == "edit_forward"]
+    assert edit_calls[0][1][1] > edit_calls[1][1][1] and edit_calls[0][2][1] == 1176
+
+
+def test_unit_runner_contracts():
+    from physicedit_b200.units import PipelineUnit, PipelineUnitRunner
+
+    class Both(PipelineUnit):
+        def __init__(self):
+            super().__init__(seperate_cfg=True, input_params_posi={"p": "prompt"}, input_params_nega={"p": "negative_prompt"}, input_params=("k",))
+
+        def process(self, pipe, p, k):
+            return {"emb": f"{p}|{k}"}
+    run = PipelineUnitRunner()
+    sh, po, ne = run(Both(), None, {"cfg_scale": 4.0, "k": 1}, {"prompt": "a"}, {"negative_prompt": "b"})
+    assert po["emb"] == "a|1" and ne["emb"] == "b|1"
+    sh, po, ne = run(Both(), None, {"cfg_scale": 1, "k": 1}, {"prompt": "a"}, {"negative_prompt": "b"})
+    assert ne["emb"] == "a|1"                                        # cfg_scale == 1: the negative side inherits the positive outputs (:268-269)
+
+    class Take(PipelineUnit):
+        def __init__(self):
+            super().__init__(take_over=True)
+
+        def process(self, pipe, inputs_shared, inputs_posi, inputs_nega):
+            inputs_shared["seen"] = True
+            return inputs_shared, inputs_posi, inputs_nega
+    assert run(Take(), None, {}, {}, {})[0]["seen"]
