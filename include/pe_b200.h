@@ -246,6 +246,40 @@ int pe_transpose(pe_handle_t h, const void* src, int64_t lds, void* dst, int64_t
 int pe_softmax_rows(pe_handle_t h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad,
                     float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Qwen2.5-VL text-encoder path: edit_forward prefill and greedy generate            */
+/*   call sites: pipelines/qwen_image_physical.py:774-800 (prompt_emb), :859-873 (generate);      */
+/*   model wrapper models/qwen_image_text_encoder_withdecode.py:147-275; arithmetic = transformers */
+/*   modeling_qwen2_5_vl.py (un-pinned third-party dependency; installed 5.5.0).  The linears run  */
+/*   on pe_gemm / pe_gemv, the norms on pe_rmsnorm; the entry points below are the rest.           */
+/* ------------------------------------------------------------------------------------------- */
+/* out[r, i] = bf16(bf16(silu(x[r, i])) * x[r, I + i]): act_fn(gate_proj(x)) * up_proj(x) on a fused [rows, 2I] gate|up buffer
+ * (Qwen2MLP.forward modeling_qwen2_5_vl.py:622-624, Qwen2_5_VLMLP.forward :87-88). */
+int pe_swiglu(pe_handle_t h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, void* stream);
+/* rotate-half RoPE in place on x [T, H*D] (row stride ldx): token t takes row (row_ptr ? *row_ptr : row0) + t of the fp32 tables
+ * cos / sin [*, D].  mode 0: fp32 arithmetic (apply_rotary_pos_emb_vision :159-171); mode 1: the language model's bf16 op order with
+ * bf16-rounded cos / sin (apply_multimodal_rotary_pos_emb :627-668 on bf16 tensors).  row_ptr is a DEVICE pointer so that a decode step
+ * captured in a CUDA graph reads its position at replay time. */
+int pe_rope_half(pe_handle_t h, void* x, int64_t ldx, int T, int H, int D, const float* cos_table, const float* sin_table,
+                 const int32_t* row_ptr, int row0, int mode, void* stream);
+/* o[i, hd] = softmax(scale * q[i, hd] . k[lo_i:hi_i, hd / (H/Hkv)]^T) v[lo_i:hi_i, ...]: grouped KV heads (repeat_kv :174-183) and a
+ * per-query KV range instead of an additive mask.  kv_lo / kv_hi: device int32 [Sq] or NULL (0 / the KV length); kv_len_ptr: device
+ * int32 holding the KV length when kv_hi is NULL (KV-cache decode), else Skv.  D in {64, 80, 128}.  Replaces the SDPA calls of
+ * Qwen2_5_VLAttention.forward :739-751 (causal) and Qwen2_5_VLVisionAttention.forward :262-283 (per-window / full chunks). */
+int pe_range_attention(pe_handle_t h, const void* q, const void* k, const void* v, void* o, int H, int Hkv, int Sq, int Skv, int D,
+                       int64_t ldq, int64_t ldkv, int64_t ldo, float scale, const int32_t* kv_lo, const int32_t* kv_hi,
+                       const int32_t* kv_len_ptr, void* stream);
+/* out[i, :] = table[ids[i], :] for ids[i] >= 0 (negative: row left as is): embed_tokens (:874) and the masked_scatter of the image
+ * embeddings into the token stream (:1311-1316).  ids: device int64 [n]. */
+int pe_gather_rows(pe_handle_t h, const void* table, int64_t ldt, const int64_t* ids, void* out, int64_t ldo, int n, int C, void* stream);
+/* out[0] = first index of max(x[0:n]) (torch.argmax; greedy decoding); optionally log[*log_pos] = out[0] (device-side token log). */
+int pe_argmax(pe_handle_t h, const void* x, int n, int64_t* out, int64_t* log, const int32_t* log_pos, void* stream);
+/* cache_k[pos[0], :] = k_new, cache_v[pos[0], :] = v_new (DynamicCache.update of one decode step, position read on the device). */
+int pe_kv_append(pe_handle_t h, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C,
+                 const int32_t* pos, void* stream);
+/* counters[0:n] += 1 (KV length, rope row and step counters of the captured decode step). */
+int pe_advance(pe_handle_t h, int32_t* counters, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,15 @@ int nchw_to_nhwc_run(Handle* h, const void* src, void* dst, int64_t ldd, int C, 
 int nhwc_to_nchw_run(Handle* h, const void* src, int64_t lds, void* dst, int C, int64_t HW, int op, const void* p0, const void* p1, cudaStream_t s);
 int transpose_run(Handle* h, const void* src, int64_t lds, void* dst, int64_t ldd, int R, int C, cudaStream_t s);
 int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s);
+int swiglu_run(Handle* h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, cudaStream_t s);
+int rope_half_run(Handle* h, void* x, int64_t ldx, int T, int H, int D, const float* cs, const float* sn, const int* row_ptr, int row0, int mode,
+                  cudaStream_t s);
+int range_attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int H, int Hkv, int Sq, int Skv, int D, int64_t ldq,
+                        int64_t ldkv, int64_t ldo, float scale, const int* kv_lo, const int* kv_hi, const int* kv_len_ptr, cudaStream_t s);
+int gather_rows_run(Handle* h, const void* table, int64_t ldt, const int64_t* ids, void* out, int64_t ldo, int n, int C, cudaStream_t s);
+int argmax_run(Handle* h, const void* x, int n, int64_t* out, int64_t* log, const int* log_pos, cudaStream_t s);
+int kv_append_run(Handle* h, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C, const int* pos, cudaStream_t s);
+int advance_run(Handle* h, int* pos, int n, cudaStream_t s);
 
 }  // namespace pe
 
@@ -311,6 +320,44 @@ int pe_softmax_rows(pe_handle_t hh, const void* scores, int64_t lds, void* probs
                     void* stream) {
     PE_H(hh);
     return pe::softmax_rows_run(h, scores, lds, probs, ldp, rows, n, n_pad, scale, static_cast<cudaStream_t>(stream));
+}
+
+int pe_swiglu(pe_handle_t hh, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, void* stream) {
+    PE_H(hh);
+    return pe::swiglu_run(h, x, ldx, out, ldo, rows, I, static_cast<cudaStream_t>(stream));
+}
+
+int pe_rope_half(pe_handle_t hh, void* x, int64_t ldx, int T, int H, int D, const float* cos_table, const float* sin_table, const int32_t* row_ptr,
+                 int row0, int mode, void* stream) {
+    PE_H(hh);
+    return pe::rope_half_run(h, x, ldx, T, H, D, cos_table, sin_table, row_ptr, row0, mode, static_cast<cudaStream_t>(stream));
+}
+
+int pe_range_attention(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int H, int Hkv, int Sq, int Skv, int D, int64_t ldq,
+                       int64_t ldkv, int64_t ldo, float scale, const int32_t* kv_lo, const int32_t* kv_hi, const int32_t* kv_len_ptr, void* stream) {
+    PE_H(hh);
+    return pe::range_attention_run(h, q, k, v, o, H, Hkv, Sq, Skv, D, ldq, ldkv, ldo, scale, kv_lo, kv_hi, kv_len_ptr, static_cast<cudaStream_t>(stream));
+}
+
+int pe_gather_rows(pe_handle_t hh, const void* table, int64_t ldt, const int64_t* ids, void* out, int64_t ldo, int n, int C, void* stream) {
+    PE_H(hh);
+    return pe::gather_rows_run(h, table, ldt, ids, out, ldo, n, C, static_cast<cudaStream_t>(stream));
+}
+
+int pe_argmax(pe_handle_t hh, const void* x, int n, int64_t* out, int64_t* log, const int32_t* log_pos, void* stream) {
+    PE_H(hh);
+    return pe::argmax_run(h, x, n, out, log, log_pos, static_cast<cudaStream_t>(stream));
+}
+
+int pe_kv_append(pe_handle_t hh, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C, const int32_t* pos,
+                 void* stream) {
+    PE_H(hh);
+    return pe::kv_append_run(h, k_new, v_new, cache_k, cache_v, ldc, C, pos, static_cast<cudaStream_t>(stream));
+}
+
+int pe_advance(pe_handle_t hh, int32_t* counters, int n, void* stream) {
+    PE_H(hh);
+    return pe::advance_run(h, counters, n, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,263 @@
+// Kernels of the Qwen2.5-VL text-encoder path: the conditioning model that turns (prompt, edit image) into prompt_emb and
+// GENERATES the "physical thinking" text (DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py:774-800, 859-873; model wrapper
+// models/qwen_image_text_encoder_withdecode.py; arithmetic = transformers' modeling_qwen2_5_vl.py, the unpinned dependency).
+// The GEMMs are pe_gemm / pe_gemv; this file holds what surrounds them -- all HBM- or latency-bound, bf16 rounding points replayed:
+//   pe_swiglu            down_proj(act_fn(gate_proj(x)) * up_proj(x))                 Qwen2MLP.forward / Qwen2_5_VLMLP.forward
+//   pe_rope_half         q*cos + rotate_half(q)*sin                                    apply_multimodal_rotary_pos_emb / apply_rotary_pos_emb_vision
+//   pe_range_attention   softmax(q k^T * scale) v with grouped KV heads and a per-query KV range (causal prefill, KV-cache decode with
+//                        the length read from device memory, the vision tower's window blocks); head dim 64 / 80 / 128
+//   pe_gather_rows       embed_tokens(input_ids), masked_scatter of the image embeddings
+//   pe_argmax            greedy next token (first maximal index, like torch.argmax)
+//   pe_kv_append         KV-cache write at a device-side position + position increment: one decode step has no host-side state, so it
+//                        can be captured once in a CUDA graph and replayed per token
+#include "ptx.cuh"
+#include "common.cuh"
+
+namespace pe {
+namespace {
+
+__device__ __forceinline__ float silu_bf16(float g) { return bf16_round(g / (1.0f + __expf(-g))); }
+
+// ---- out[r, i] = bf16( bf16(silu(x[r, i])) * x[r, I + i] ) ------------------------------------------------------------------------
+__global__ void swiglu_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo, int rows, int I) {
+    const int nvec = I >> 3;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)rows * nvec) return;
+    const int r = (int)(gid / nvec), v = (int)(gid - (long long)r * nvec);
+    const uint4 g4 = *reinterpret_cast<const uint4*>(x + r * ldx + v * 8);
+    const uint4 u4 = *reinterpret_cast<const uint4*>(x + r * ldx + I + v * 8);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 g = unpack_bf16(gw[j]), u = unpack_bf16(uw[j]);
+        ow[j] = pack_bf16(silu_bf16(g.x) * u.x, silu_bf16(g.y) * u.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + v * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// ---- rotate-half RoPE in place on x [T, H*D] -------------------------------------------------------------------------------------
+// token t uses table row (row_ptr ? *row_ptr : row0) + t of cos / sin [*, D] (fp32, both halves of D filled as HF's cat(freqs, freqs)).
+// mode 0: fp32 fused (vision tower: q.float()*cos + rotate_half(q.float())*sin -> bf16)
+// mode 1: the language model's bf16 op order: cos / sin rounded to bf16, a = bf16(q*cos), b = bf16(rot*sin), out = bf16(a + b)
+__global__ void rope_half_kernel(bf16* __restrict__ x, long long ldx, int T, int H, int D, const float* __restrict__ cs, const float* __restrict__ sn,
+                                 const int* __restrict__ row_ptr, int row0, int mode) {
+    const int half = D >> 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)T * H * half) return;
+    const int i = (int)(gid % half);
+    const int hd = (int)((gid / half) % H);
+    const int t = (int)(gid / ((long long)half * H));
+    const long long row = (long long)(row_ptr ? *row_ptr : row0) + t;
+    bf16* p = x + t * ldx + hd * D;
+    const float x1 = __bfloat162float(p[i]), x2 = __bfloat162float(p[i + half]);
+    float c1 = cs[row * D + i], c2 = cs[row * D + i + half], s1 = sn[row * D + i], s2 = sn[row * D + i + half];
+    float o1, o2;
+    if (mode == 1) {
+        c1 = bf16_round(c1); c2 = bf16_round(c2); s1 = bf16_round(s1); s2 = bf16_round(s2);
+        o1 = bf16_round(x1 * c1) + bf16_round(-x2 * s1);
+        o2 = bf16_round(x2 * c2) + bf16_round(x1 * s2);
+    } else {
+        o1 = x1 * c1 - x2 * s1;
+        o2 = x2 * c2 + x1 * s2;
+    }
+    p[i] = __float2bfloat16_rn(o1);
+    p[i + half] = __float2bfloat16_rn(o2);
+}
+
+// ---- attention with grouped KV heads and a per-query KV range ---------------------------------------------------------------------
+// One warp per (query, head): lanes stride over the KV rows of [lo, hi), each lane keeps a private online softmax (fp32) over its rows
+// and the 32 partial results are merged at the end.  CUDA cores on purpose: the shapes here are a 1-row decode step over a KV cache,
+// ~200-1500-token prefills and 64-token vision windows, once per image -- latency-bound, not the DiT's tensor-bound attention.
+template <int D>
+__global__ void __launch_bounds__(128) range_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                                                              bf16* __restrict__ o, int H, int group, int Sq, int Skv, long long ldq, long long ldkv,
+                                                              long long ldo, float scale, const int* __restrict__ kv_lo, const int* __restrict__ kv_hi,
+                                                              const int* __restrict__ kv_len_ptr) {
+    __shared__ float qs[4][D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 4 + warp;
+    const int hd = blockIdx.y;
+    if (qi >= Sq) return;
+    const int hkv = hd / group;
+    const bf16* qrow = q + (long long)qi * ldq + hd * D;
+    for (int d = lane; d < D; d += 32) qs[warp][d] = __bfloat162float(qrow[d]) * scale;
+    __syncwarp();
+    const int lo = kv_lo ? kv_lo[qi] : 0;
+    int hi = kv_hi ? kv_hi[qi] : (kv_len_ptr ? *kv_len_ptr : Skv);
+    if (hi > Skv) hi = Skv;
+    float m = -INFINITY, l = 0.f;
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    for (int kj = lo + lane; kj < hi; kj += 32) {
+        const bf16* krow = k + (long long)kj * ldkv + hkv * D;
+        float s = 0.f;
+#pragma unroll
+        for (int d8 = 0; d8 < D / 8; ++d8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(krow + d8 * 8);
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+            const float* qq = &qs[warp][d8 * 8];
+            s += a.x * qq[0] + a.y * qq[1] + b.x * qq[2] + b.y * qq[3] + c.x * qq[4] + c.y * qq[5] + e.x * qq[6] + e.y * qq[7];
+        }
+        const float m_new = fmaxf(m, s);
+        const float f = __expf(m - m_new);
+        const float pw = __expf(s - m_new);
+        l = l * f + pw;
+        const bf16* vrow = v + (long long)kj * ldkv + hkv * D;
+#pragma unroll
+        for (int d8 = 0; d8 < D / 8; ++d8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(vrow + d8 * 8);
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+            float* ac = &acc[d8 * 8];
+            ac[0] = ac[0] * f + pw * a.x; ac[1] = ac[1] * f + pw * a.y; ac[2] = ac[2] * f + pw * b.x; ac[3] = ac[3] * f + pw * b.y;
+            ac[4] = ac[4] * f + pw * c.x; ac[5] = ac[5] * f + pw * c.y; ac[6] = ac[6] * f + pw * e.x; ac[7] = ac[7] * f + pw * e.y;
+        }
+        m = m_new;
+    }
+    float mg = m;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+    const float f = (m == -INFINITY) ? 0.f : __expf(m - mg);
+    l *= f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = l > 0.f ? 1.0f / l : 0.f;          // an empty range gives a zero row (never produced by the callers)
+    bf16* orow = o + (long long)qi * ldo + hd * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float a = acc[d] * f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == (d & 31)) orow[d] = __float2bfloat16_rn(a * inv);
+    }
+}
+
+// ---- out[i, :] = table[ids[i], :] ; ids < 0 leave the row untouched (used to scatter image embeddings into the token stream) ----------
+__global__ void gather_rows_kernel(const bf16* __restrict__ table, long long ldt, const long long* __restrict__ ids, bf16* __restrict__ out,
+                                   long long ldo, int n, int C) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const long long id = ids[r];
+    if (id < 0) return;
+    const int nvec = C >> 3;
+    for (int vv = threadIdx.x; vv < nvec; vv += blockDim.x)
+        *reinterpret_cast<uint4*>(out + r * ldo + vv * 8) = __ldg(reinterpret_cast<const uint4*>(table + id * ldt + vv * 8));
+}
+
+// ---- first index of the maximum of a bf16 vector (torch.argmax semantics) -> int64; one CTA -----------------------------------------
+__global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ x, int n, long long* __restrict__ out, long long* __restrict__ log,
+                                                      const int* __restrict__ log_pos) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float val = __bfloat162float(x[i]);
+        if (val > best || (val == best && i < bi)) { best = val; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) {
+            out[0] = bi;
+            if (log != nullptr) log[log_pos ? *log_pos : 0] = bi;       // generated-token log, indexed by the device-side step counter
+        }
+    }
+}
+
+// ---- KV cache append at a device-side position, then advance the counters -----------------------------------------------------------
+// cache_k / cache_v [max_len, C]; k_new / v_new [C]; pos[0] = number of cached rows (row to write), pos[1] = rope table row, pos[2] = step.
+__global__ void kv_append_kernel(const bf16* __restrict__ k_new, const bf16* __restrict__ v_new, bf16* __restrict__ cache_k, bf16* __restrict__ cache_v,
+                                 long long ldc, int C, const int* __restrict__ pos) {
+    const long long row = pos[0];
+    for (int i = threadIdx.x; i < (C >> 3); i += blockDim.x) {
+        *reinterpret_cast<uint4*>(cache_k + row * ldc + i * 8) = *reinterpret_cast<const uint4*>(k_new + i * 8);
+        *reinterpret_cast<uint4*>(cache_v + row * ldc + i * 8) = *reinterpret_cast<const uint4*>(v_new + i * 8);
+    }
+}
+__global__ void advance_kernel(int* __restrict__ pos, int n) {
+    if (threadIdx.x < n) pos[threadIdx.x] += 1;
+}
+
+}  // namespace
+
+int swiglu_run(Handle* h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, cudaStream_t s) {
+    PE_REQUIRE(h, x && out && rows > 0 && I > 0 && I % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "pe_swiglu: bad arguments (rows=%d I=%d)", rows, I);
+    const long long n = (long long)rows * (I / 8);
+    swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(out), ldo, rows, I);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int rope_half_run(Handle* h, void* x, int64_t ldx, int T, int H, int D, const float* cs, const float* sn, const int* row_ptr, int row0, int mode,
+                  cudaStream_t s) {
+    PE_REQUIRE(h, x && cs && sn && T > 0 && H > 0 && D > 0 && D % 2 == 0, "pe_rope_half: bad arguments (T=%d H=%d D=%d)", T, H, D);
+    PE_REQUIRE(h, mode == 0 || mode == 1, "pe_rope_half: mode must be 0 (fp32 fused) or 1 (bf16 op order)");
+    const long long n = (long long)T * H * (D / 2);
+    rope_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<bf16*>(x), ldx, T, H, D, cs, sn, row_ptr, row0, mode);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int range_attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int H, int Hkv, int Sq, int Skv, int D, int64_t ldq,
+                        int64_t ldkv, int64_t ldo, float scale, const int* kv_lo, const int* kv_hi, const int* kv_len_ptr, cudaStream_t s) {
+    PE_REQUIRE(h, q && k && v && o, "pe_range_attention: null pointer");
+    PE_REQUIRE(h, H > 0 && Hkv > 0 && H % Hkv == 0 && Sq > 0 && Skv > 0, "pe_range_attention: bad head / sequence sizes (H=%d Hkv=%d Sq=%d Skv=%d)", H, Hkv, Sq, Skv);
+    PE_REQUIRE(h, D == 64 || D == 80 || D == 128, "pe_range_attention: head dim must be 64, 80 or 128 (got %d)", D);
+    PE_REQUIRE(h, ldq % 8 == 0 && ldkv % 8 == 0, "pe_range_attention: ldq / ldkv must be multiples of 8");
+    const dim3 grid(ceil_div(Sq, 4), H);
+    const bf16 *qb = static_cast<const bf16*>(q), *kb = static_cast<const bf16*>(k), *vb = static_cast<const bf16*>(v);
+    bf16* ob = static_cast<bf16*>(o);
+    const int group = H / Hkv;
+    if (D == 64) range_attention_kernel<64><<<grid, 128, 0, s>>>(qb, kb, vb, ob, H, group, Sq, Skv, ldq, ldkv, ldo, scale, kv_lo, kv_hi, kv_len_ptr);
+    else if (D == 80) range_attention_kernel<80><<<grid, 128, 0, s>>>(qb, kb, vb, ob, H, group, Sq, Skv, ldq, ldkv, ldo, scale, kv_lo, kv_hi, kv_len_ptr);
+    else range_attention_kernel<128><<<grid, 128, 0, s>>>(qb, kb, vb, ob, H, group, Sq, Skv, ldq, ldkv, ldo, scale, kv_lo, kv_hi, kv_len_ptr);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int gather_rows_run(Handle* h, const void* table, int64_t ldt, const int64_t* ids, void* out, int64_t ldo, int n, int C, cudaStream_t s) {
+    PE_REQUIRE(h, table && ids && out && n > 0 && C > 0 && C % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0, "pe_gather_rows: bad arguments (n=%d C=%d)", n, C);
+    gather_rows_kernel<<<n, 128, 0, s>>>(static_cast<const bf16*>(table), ldt, reinterpret_cast<const long long*>(ids), static_cast<bf16*>(out), ldo, n, C);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int argmax_run(Handle* h, const void* x, int n, int64_t* out, int64_t* log, const int* log_pos, cudaStream_t s) {
+    PE_REQUIRE(h, x && out && n > 0, "pe_argmax: bad arguments (n=%d)", n);
+    argmax_kernel<<<1, 1024, 0, s>>>(static_cast<const bf16*>(x), n, reinterpret_cast<long long*>(out), reinterpret_cast<long long*>(log), log_pos);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int kv_append_run(Handle* h, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C, const int* pos, cudaStream_t s) {
+    PE_REQUIRE(h, k_new && v_new && cache_k && cache_v && pos && C > 0 && C % 8 == 0 && ldc % 8 == 0, "pe_kv_append: bad arguments (C=%d)", C);
+    kv_append_kernel<<<1, 128, 0, s>>>(static_cast<const bf16*>(k_new), static_cast<const bf16*>(v_new), static_cast<bf16*>(cache_k),
+                                       static_cast<bf16*>(cache_v), ldc, C, pos);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int advance_run(Handle* h, int* pos, int n, cudaStream_t s) {
+    PE_REQUIRE(h, pos && n > 0 && n <= 32, "pe_advance: bad arguments");
+    advance_kernel<<<1, 32, 0, s>>>(pos, n);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+}  // namespace pe

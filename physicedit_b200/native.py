@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
     "pe_softmax_rows",
+    "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_advance",
 ]
 
 
@@ -108,6 +109,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_swiglu.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
+    lib.pe_rope_half.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.pe_range_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pe_gather_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]
+    lib.pe_argmax.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pe_kv_append.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
+    lib.pe_advance.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     return lib
 
 
@@ -397,4 +406,60 @@ class Native:
             raise NativeError("softmax_rows: scores must be CUDA float32 [rows, >=n] with as many rows as probs")
         self._check(self.lib.pe_softmax_rows(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
                                              n, probs.shape[1], scale, self._stream_prof()), "pe_softmax_rows")
+        self.launches += 1
+
+    # ---- Qwen2.5-VL text-encoder path (include/pe_b200.h, last section) --------------------------------------------------------
+    def swiglu(self, x, out, I: int) -> None:
+        """x [rows, >= 2I] = gate | up, out [rows, >= I]."""
+        _bf16(x, "x"); _bf16(out, "out")
+        self._check(self.lib.pe_swiglu(self.h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], I, self._stream_prof()), "pe_swiglu")
+        self.launches += 1
+
+    def rope_half(self, x, H: int, D: int, cos, sin, row0: int = 0, row_ptr=None, mode: int = 1) -> None:
+        """In place on x [T, >= H*D]; cos / sin fp32 [rows, D]."""
+        _bf16(x, "x")
+        for t in (cos, sin):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.shape[-1] != D:
+                raise NativeError("rope_half: cos / sin must be contiguous CUDA float32 [rows, D]")
+        if row_ptr is None and row0 + x.shape[0] > cos.shape[0]:
+            raise NativeError("rope_half: table too short")
+        self._check(self.lib.pe_rope_half(self.h, x.data_ptr(), x.stride(0), x.shape[0], H, D, cos.data_ptr(), sin.data_ptr(), _ptr(row_ptr), row0, mode,
+                                          self._stream_prof()), "pe_rope_half")
+        self.launches += 1
+
+    def range_attention(self, q, k, v, o, H: int, Hkv: int, D: int, scale: float, kv_lo=None, kv_hi=None, kv_len_ptr=None, Skv: Optional[int] = None) -> None:
+        """q [Sq, >= H*D], k / v [Skv, >= Hkv*D] (same stride), o [Sq, >= H*D]; kv_lo / kv_hi int32 [Sq] device tensors or None."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+            _bf16(t, n)
+        if k.stride(0) != v.stride(0):
+            raise NativeError("k and v must share one row stride")
+        for t in (kv_lo, kv_hi, kv_len_ptr):
+            if t is not None and (t.dtype != torch.int32 or not t.is_cuda):
+                raise NativeError("range_attention: kv_lo / kv_hi / kv_len_ptr must be CUDA int32 tensors")
+        self._check(self.lib.pe_range_attention(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), H, Hkv, q.shape[0],
+                                                k.shape[0] if Skv is None else Skv, D, q.stride(0), k.stride(0), o.stride(0), scale, _ptr(kv_lo),
+                                                _ptr(kv_hi), _ptr(kv_len_ptr), self._stream_prof()), "pe_range_attention")
+        self.launches += 1
+
+    def gather_rows(self, table, ids, out) -> None:
+        _bf16(table, "table"); _bf16(out, "out")
+        if ids.dtype != torch.int64 or not ids.is_cuda or not ids.is_contiguous():
+            raise NativeError("gather_rows: ids must be a contiguous CUDA int64 tensor")
+        self._check(self.lib.pe_gather_rows(self.h, table.data_ptr(), table.stride(0), ids.data_ptr(), out.data_ptr(), out.stride(0), ids.numel(),
+                                            table.shape[1], self._stream_prof()), "pe_gather_rows")
+        self.launches += 1
+
+    def argmax(self, x, out, log=None, log_pos=None) -> None:
+        _bf16(x, "x")
+        self._check(self.lib.pe_argmax(self.h, x.data_ptr(), x.numel(), out.data_ptr(), _ptr(log), _ptr(log_pos), self._stream_prof()), "pe_argmax")
+        self.launches += 1
+
+    def kv_append(self, k_new, v_new, cache_k, cache_v, pos) -> None:
+        _bf16(k_new, "k_new"); _bf16(v_new, "v_new"); _bf16(cache_k, "cache_k"); _bf16(cache_v, "cache_v")
+        self._check(self.lib.pe_kv_append(self.h, k_new.data_ptr(), v_new.data_ptr(), cache_k.data_ptr(), cache_v.data_ptr(), cache_k.stride(0),
+                                          k_new.numel(), pos.data_ptr(), self._stream_prof()), "pe_kv_append")
+        self.launches += 1
+
+    def advance(self, counters, n: int) -> None:
+        self._check(self.lib.pe_advance(self.h, counters.data_ptr(), n, self._stream_prof()), "pe_advance")
         self.launches += 1
