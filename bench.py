@@ -406,6 +406,13 @@ def run_native(args):
         res["collectives"] = coll
     if not args.no_vae:
         res["vae"] = vae_leg(device, H, W, ms / args.steps)
+    if world == 1 and not args.no_text_encoder:
+        vae_ms = (res["vae"]["encode"]["ms"] + res["vae"]["decode"]["ms"]) if "vae" in res else 0.0
+        try:
+            res["text_encoder"] = text_encoder_leg(device, ms / args.steps, vae_ms)
+        except Exception as e:  # noqa: BLE001  (a reported leg beside the metric: never takes the headline line down)
+            res["text_encoder"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_stock_gpu:
         del pipe, eng, lat, dev, d_in
         torch.cuda.empty_cache()
@@ -552,6 +559,87 @@ def stock_gpu_leg(device, H, W, layers=4, iters=10, warmup=3):
                        "the full-depth figure against the fp32 oracle is in profiles/r02_parity_depth.json (tests/test_parity_depth_gpu.py)"}}
 
 
+def text_encoder_leg(device, ms_per_step, vae_ms, new_tokens=96):
+    """The step in front of the loop, outside the headline metric: the Qwen2.5-VL text encoder at its real size (7B config of
+    the reference's wrapper, random-init bf16 weights) on the native path -- `generate` (prefill + greedy KV-cache decode replayed from a
+    CUDA graph) and `edit_forward` on a processor-shaped request (a 392x392 image = 196 image tokens + text).  B=1 decode is HBM-bound:
+    the roofline is the bytes of weights one token must stream divided by the measured HBM bandwidth."""
+    from physicedit_b200.text_encoder import QwenImageTextEncoder, VLConfig
+    cfg = VLConfig()
+    with torch.device("meta"):
+        te = QwenImageTextEncoder(cfg, rope_mode="mrope")
+    g = torch.Generator(device=device).manual_seed(1)
+    sd = {}
+    for k, v in te.state_dict().items():
+        if "embed_tokens" in k:
+            t = torch.randn(v.shape, generator=g, device=device, dtype=torch.float32)
+        elif v.dim() >= 2:
+            fan_in = math.prod(v.shape[1:])
+            t = (torch.rand(v.shape, generator=g, device=device, dtype=torch.float32) * 2 - 1) * (1.0 / math.sqrt(fan_in))
+        elif k.endswith(".bias"):
+            t = (torch.rand(v.shape, generator=g, device=device, dtype=torch.float32) * 2 - 1) * 0.02
+        else:
+            t = torch.ones(v.shape, device=device)
+        sd[k] = t.to(torch.bfloat16)
+    te.load_state_dict(sd, assign=True)
+    te.eval()
+    te.cfg.eos_token_id = -1                      # random weights: never stop early, time exactly `new_tokens`
+    n_img, n_txt = 196, 120
+    ids = torch.cat([torch.randint(1000, 100000, (40,), generator=torch.Generator().manual_seed(0)), torch.full((n_img,), cfg.image_token_id),
+                     torch.randint(1000, 100000, (n_txt,), generator=torch.Generator().manual_seed(1))]).view(1, -1)
+    req = dict(input_ids=ids.to(device), attention_mask=torch.ones_like(ids).to(device),
+               pixel_values=torch.randn(784, 1176, device=device).to(torch.bfloat16), image_grid_thw=torch.tensor([[1, 28, 28]], device=device))
+    te.generate(**req, max_new_tokens=8)          # warm-up (packs the weights, compiles nothing: kernels are prebuilt)
+    torch.cuda.synchronize(device)
+    te.generate(**req, max_new_tokens=new_tokens)
+    torch.cuda.synchronize(device)
+    st = dict(te.last_generate_stats)
+    # what the pipeline does: the positive and the negative branch decoded together (batch 2: one pass over the weights, two tokens)
+    req2 = dict(req, input_ids=req["input_ids"][:, :-37].contiguous(), attention_mask=req["attention_mask"][:, :-37].contiguous())
+    te.generate_batch([req, req2], max_new_tokens=new_tokens)
+    torch.cuda.synchronize(device)
+    st2 = dict(te.last_generate_stats)
+    # per-kernel breakdown of one decode step: a few eager (graph-less) tokens with per-launch CUDA events
+    from physicedit_b200 import native as nv
+    nat = nv.Native.get(device.index or 0)
+    te.use_cuda_graph = False
+    nat.prof = {}
+    te.generate(**req, max_new_tokens=6)
+    torch.cuda.synchronize(device)
+    breakdown = {k: round(v[1] * 1e3 / 5, 1) for k, v in sorted(nat.profile_summary().items(), key=lambda kv: -kv[1][1]) if k.startswith("te_")}
+    nat.prof = None
+    te.use_cuda_graph = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        h = te.edit_forward(**req)[-1]
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms_edit = e0.elapsed_time(e1) / 3
+    c = cfg
+    per_layer = (c.heads + 2 * c.kv_heads) * c.head_dim * c.hidden + c.hidden * c.heads * c.head_dim + 3 * c.hidden * c.intermediate
+    bytes_per_token = 2 * (c.layers * per_layer + c.vocab * c.hidden)           # decoder weights + lm_head, bf16 (KV cache and norms are noise)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    gbs = bytes_per_token / (st["ms_per_token"] * 1e-3) / 1e9
+    pre_loop_ms = st2["prefill_s"] * 1e3 + 1000 * st2["ms_per_token"] + 2 * ms_edit       # both CFG branches in one batch, 1000 new tokens each (the cap)
+    image_ms = pre_loop_ms + vae_ms + 50 * ms_per_step
+    return {"what": "Qwen2.5-VL 7B-config text encoder on the native path (random-init weights), outside the headline metric",
+            "prompt_tokens": st["prompt_tokens"], "new_tokens_timed": st["tokens_computed"], "decode_ms_per_token": round(st["ms_per_token"], 3),
+            "decode_ms_per_step_both_cfg_branches": round(st2["ms_per_token"], 3), "prefill_ms_both_cfg_branches": round(st2["prefill_s"] * 1e3, 2),
+            "cuda_graph": st["cuda_graph"], "graph_capture_ms": round(st.get("graph_capture_s", 0) * 1e3, 1), "prefill_ms": round(st["prefill_s"] * 1e3, 2),
+            "edit_forward_ms": round(ms_edit, 2), "decode_step_kernel_us": breakdown,
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks.get("hbm_gbs", 6500.0), "unit": "GB/s",
+                         "frac": round(gbs / peaks.get("hbm_gbs", 6500.0), 4), "algorithmic_bytes": bytes_per_token},
+            "finite": bool(torch.isfinite(h.float()).all()),
+            "image_50_steps_with_text_encoder": {"pre_loop_ms": round(pre_loop_ms, 1), "ms": round(image_ms, 1), "images_per_sec_per_gpu": round(1e3 / image_ms, 5),
+                                                 "note": "generate for both CFG branches in one batch (2 prefills + 1000 batch-2 decode steps, the reference's max_new_tokens) + 2 x "
+                                                         "edit_forward + VAE encode/decode + 50 denoise steps; real prompts stop at EOS earlier"}}
+
+
 def _cpu_threads():
     try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is allowed every host thread it can use
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
@@ -658,6 +746,7 @@ def main():
                     help="latency mode: one image per pair of GPUs (positive branch on the even rank, negative on the odd one); needs an even --gpus")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text-encoder", dest="no_text_encoder", action="store_true", help="skip the Qwen2.5-VL text-encoder leg (7B config, random weights)")
     ap.add_argument("--no-stock-gpu", dest="no_stock_gpu", action="store_true", help="skip the stock-PyTorch GPU baseline leg (4 blocks, same inputs)")
     ap.add_argument("--no-cfg-parallel-leg", dest="no_cfg_parallel_leg", action="store_true", help="N>=2: skip the CFG-parallel latency sub-leg")
     ap.add_argument("--no-full-forward", dest="no_full_forward", action="store_true", help="--impl reference: skip the one real 60-block CPU forward")

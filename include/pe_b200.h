@@ -253,6 +253,13 @@ int pe_softmax_rows(pe_handle_t h, const void* scores, int64_t lds, void* probs,
 /*   modeling_qwen2_5_vl.py (un-pinned third-party dependency; installed 5.5.0).  The linears run  */
 /*   on pe_gemm / pe_gemv, the norms on pe_rmsnorm; the entry points below are the rest.           */
 /* ------------------------------------------------------------------------------------------- */
+/* M <= 8 linear of the one-token decode step with its neighbours fused in (every CTA redoes the prologue on the <= 18944 inputs):
+ *   act_in 0 / 1: x [batch, K] (1: SiLU first);  act_in 2: x [batch, 2K] = gate | up, input = bf16(bf16(silu(gate)) * up) (Qwen2MLP);
+ *   norm_w != NULL: input = bf16(norm_w * bf16(x * rsqrt(mean(x^2) + eps))) (Qwen2_5_VLRMSNorm :66-71 in front of q/k/v and gate/up);
+ *   residual != NULL: y = bf16(residual + bf16(acc + bias)) (Qwen2_5_VLDecoderLayer.forward :818, :824; may alias y).
+ * Same arithmetic and rounding points as pe_rmsnorm / pe_swiglu / pe_gemv / pe_add_rows run one after the other. */
+int pe_gemv_fused(pe_handle_t h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
+                  const void* norm_w, float norm_eps, const void* residual, void* stream);
 /* out[r, i] = bf16(bf16(silu(x[r, i])) * x[r, I + i]): act_fn(gate_proj(x)) * up_proj(x) on a fused [rows, 2I] gate|up buffer
  * (Qwen2MLP.forward modeling_qwen2_5_vl.py:622-624, Qwen2_5_VLMLP.forward :87-88). */
 int pe_swiglu(pe_handle_t h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, void* stream);
@@ -277,6 +284,10 @@ int pe_argmax(pe_handle_t h, const void* x, int n, int64_t* out, int64_t* log, c
 /* cache_k[pos[0], :] = k_new, cache_v[pos[0], :] = v_new (DynamicCache.update of one decode step, position read on the device). */
 int pe_kv_append(pe_handle_t h, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C,
                  const int32_t* pos, void* stream);
+/* One decode row qkv = [q (Hq heads) | k (Hkv heads) | v]: pe_rope_half (mode 1) on the q and k heads at table row counters[1], then
+ * cache_k[counters[0], :] = rotated k, cache_v[counters[0], :] = v.  Fuses two pe_rope_half and one pe_kv_append launch. */
+int pe_rope_kv_append(pe_handle_t h, void* qkv, int Hq, int Hkv, int D, const float* cos_table, const float* sin_table, void* cache_k,
+                      void* cache_v, int64_t ldc, const int32_t* counters, void* stream);
 /* counters[0:n] += 1 (KV length, rope row and step counters of the captured decode step). */
 int pe_advance(pe_handle_t h, int32_t* counters, int n, void* stream);
 

@@ -64,7 +64,8 @@ int layernorm_modulate2_run(Handle* h, const void* x, void* out, int rows, int C
                             const void* shift1, const void* ops1, cudaStream_t s);
 int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void* w, float eps, cudaStream_t s);
 int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
-             int act_out, const uint8_t* one_plus_mask, cudaStream_t s);
+             int act_out, const uint8_t* one_plus_mask, cudaStream_t s, const void* norm_w = nullptr, float norm_eps = 0.f,
+             const void* residual = nullptr);
 int act_run(Handle* h, const void* x, void* y, long long n, int act, cudaStream_t s);
 int timestep_embedding_run(Handle* h, const void* t_in, void* out, int raw, cudaStream_t s);
 int patchify_run(Handle* h, const void* latents, void* tokens, int H8, int W8, cudaStream_t s);
@@ -96,6 +97,8 @@ int gather_rows_run(Handle* h, const void* table, int64_t ldt, const int64_t* id
 int argmax_run(Handle* h, const void* x, int n, int64_t* out, int64_t* log, const int* log_pos, cudaStream_t s);
 int kv_append_run(Handle* h, const void* k_new, const void* v_new, void* cache_k, void* cache_v, int64_t ldc, int C, const int* pos, cudaStream_t s);
 int advance_run(Handle* h, int* pos, int n, cudaStream_t s);
+int rope_kv_append_run(Handle* h, void* qkv, int Hq, int Hkv, int D, const float* cs, const float* sn, void* cache_k, void* cache_v, int64_t ldc,
+                       const int* ctr, cudaStream_t s);
 
 }  // namespace pe
 
@@ -238,6 +241,12 @@ int pe_gemv(pe_handle_t hh, const void* x, const void* w, const void* bias, void
     return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, act_out, one_plus_mask, static_cast<cudaStream_t>(stream));
 }
 
+int pe_gemv_fused(pe_handle_t hh, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
+                  const void* norm_w, float norm_eps, const void* residual, void* stream) {
+    PE_H(hh);
+    return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, 0, nullptr, static_cast<cudaStream_t>(stream), norm_w, norm_eps, residual);
+}
+
 int pe_act(pe_handle_t hh, const void* x, void* y, int64_t n, int act, void* stream) {
     PE_H(hh);
     return pe::act_run(h, x, y, (long long)n, act, static_cast<cudaStream_t>(stream));
@@ -353,6 +362,12 @@ int pe_kv_append(pe_handle_t hh, const void* k_new, const void* v_new, void* cac
                  void* stream) {
     PE_H(hh);
     return pe::kv_append_run(h, k_new, v_new, cache_k, cache_v, ldc, C, pos, static_cast<cudaStream_t>(stream));
+}
+
+int pe_rope_kv_append(pe_handle_t hh, void* qkv, int Hq, int Hkv, int D, const float* cos_table, const float* sin_table, void* cache_k, void* cache_v,
+                      int64_t ldc, const int32_t* counters, void* stream) {
+    PE_H(hh);
+    return pe::rope_kv_append_run(h, qkv, Hq, Hkv, D, cos_table, sin_table, cache_k, cache_v, ldc, counters, static_cast<cudaStream_t>(stream));
 }
 
 int pe_advance(pe_handle_t hh, int32_t* counters, int n, void* stream) {

@@ -293,65 +293,143 @@ __device__ __forceinline__ float silu_bf16(float x) { return bf16_round(x / (1.0
 // The per-lane partial sums and the butterfly reduction are those of the one-row formulation, so results are bit-identical to it.
 constexpr int kGemvRows = 4;
 
-template <int kBatch>
+template <int kBatch, int kRows = kGemvRows, int kDepth = 1>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                   const bf16* __restrict__ bias, bf16* __restrict__ y, int N, int K,
-                                                                  int act_in, int act_out, const uint8_t* __restrict__ one_plus_mask) {
-    extern __shared__ float xs[];   // [kBatch][K]
-    for (int i = threadIdx.x; i < kBatch * K; i += blockDim.x) {
-        float f = __bfloat162float(x[i]);
-        if (act_in == 1) f = silu_bf16(f);
-        xs[i] = f;
+                                                                  int act_in, int act_out, const uint8_t* __restrict__ one_plus_mask,
+                                                                  const bf16* __restrict__ norm_w = nullptr, float norm_eps = 0.f,
+                                                                  const bf16* __restrict__ residual = nullptr) {
+    // kRows output features per warp, kDepth 16-byte vectors per feature in flight per lane (plus the same again being consumed).
+    // (4, 1) streams wide matrices (N >= ~10 k: one shared-memory read of x feeds four dot products); (1, 4) is for narrow outputs
+    // (the 3584-wide projections of the Qwen2.5-VL decode step, K up to 18944): four times as many warps share the rows, so all SMs
+    // stream, and each lane keeps four loads of its single row in flight.
+    // Optional prologues on the staged input (one-token decode of the Qwen2.5-VL text encoder: every CTA redoes them, K <= 18944 values):
+    //   act_in 2   x is [kBatch][2K] = gate | up of a SwiGLU MLP: staged value = bf16(bf16(silu(gate)) * up)          (Qwen2MLP.forward)
+    //   norm_w     RMSNorm in front of the linear: staged value = bf16(norm_w * bf16(x * rsqrt(mean(x^2) + eps)))     (Qwen2_5_VLRMSNorm)
+    // and epilogue: residual != nullptr  ->  y = bf16(residual + bf16(acc + bias))                                     (decoder-layer skip adds)
+    // The staged input is kept as bf16 (every value that lands here IS bf16-representable: raw inputs and the rounded prologue results),
+    // half the shared memory of an fp32 copy: K = 18944 inputs take 37 KB instead of 74 KB per batch row, so five CTAs instead of two fit
+    // an SM and one CTA's prologue overlaps the others' weight streaming (r2: the 3584 x 18944 down-projection went from 2.7 TB/s up).
+    extern __shared__ __align__(16) unsigned char xs_raw[];
+    bf16* xs = reinterpret_cast<bf16*>(xs_raw);   // [kBatch][K]
+    __shared__ float red[kBatch][kWarpsPerCta];
+    {
+        const int kv = K >> 3;
+        for (int i = threadIdx.x; i < kBatch * kv; i += blockDim.x) {
+            const int b = i / kv, j = i - b * kv;
+            uint4 val;
+            if (act_in == 2) {
+                float g[8], u[8], f[8];
+                unpack8(*reinterpret_cast<const uint4*>(x + (size_t)b * 2 * K + j * 8), g);
+                unpack8(*reinterpret_cast<const uint4*>(x + (size_t)b * 2 * K + K + j * 8), u);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = silu_bf16(g[e]) * u[e];
+                val = pack8(f);
+            } else {
+                val = *reinterpret_cast<const uint4*>(x + (size_t)b * K + j * 8);
+                if (act_in == 1) {
+                    float f[8];
+                    unpack8(val, f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = silu_bf16(f[e]);
+                    val = pack8(f);
+                }
+            }
+            *reinterpret_cast<uint4*>(xs + b * K + j * 8) = val;
+        }
     }
     __syncthreads();
+    if (norm_w != nullptr) {
+        const int kv = K >> 3;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            float ss = 0.f;
+            for (int j = threadIdx.x; j < kv; j += blockDim.x) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(xs + b * K + j * 8), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+            }
+            ss = warp_sum(ss);
+            if ((threadIdx.x & 31) == 0) red[b][threadIdx.x >> 5] = ss;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w_ = 0; w_ < kWarpsPerCta; ++w_) tot += red[b][w_];
+            const float rs = rsqrtf(tot / (float)K + norm_eps);
+            for (int j = threadIdx.x; j < kv; j += blockDim.x) {
+                float f[8], g[8];
+                unpack8(*reinterpret_cast<const uint4*>(xs + b * K + j * 8), f);
+                unpack8(*reinterpret_cast<const uint4*>(norm_w + j * 8), g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = g[e] * bf16_round(f[e] * rs);
+                *reinterpret_cast<uint4*>(xs + b * K + j * 8) = pack8(f);
+            }
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int nvec = K >> 3;
-    const int ngroups = (N + kGemvRows - 1) / kGemvRows;
+    const int ngroups = (N + kRows - 1) / kRows;
     for (int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * kWarpsPerCta) {
-        const int n0 = g * kGemvRows;
-        const bf16* wr[kGemvRows];
+        const int n0 = g * kRows;
+        const bf16* wr[kRows];
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) wr[r] = w + (size_t)min(n0 + r, N - 1) * K;     // rows past N repeat the last row (not stored)
-        float acc[kGemvRows][kBatch];
+        for (int r = 0; r < kRows; ++r) wr[r] = w + (size_t)min(n0 + r, N - 1) * K;     // rows past N repeat the last row (not stored)
+        float acc[kRows][kBatch];
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r)
+        for (int r = 0; r < kRows; ++r)
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) acc[r][b] = 0.f;
-        uint4 u[kGemvRows], un[kGemvRows];
+        uint4 u[kRows][kDepth], un[kRows][kDepth];
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) u[r] = lane < nvec ? ld_stream(wr[r] + lane * 8) : make_uint4(0, 0, 0, 0);
-        for (int v0 = 0; v0 < nvec; v0 += 32) {
-            const int vi = v0 + lane;
-            const int vn = vi + 32;
+        for (int r = 0; r < kRows; ++r)
 #pragma unroll
-            for (int r = 0; r < kGemvRows; ++r) un[r] = vn < nvec ? ld_stream(wr[r] + vn * 8) : make_uint4(0, 0, 0, 0);
-            if (vi < nvec) {
-                float f[kGemvRows][8];
+            for (int d = 0; d < kDepth; ++d) u[r][d] = (lane + 32 * d) < nvec ? ld_stream(wr[r] + (lane + 32 * d) * 8) : make_uint4(0, 0, 0, 0);
+        for (int v0 = 0; v0 < nvec; v0 += 32 * kDepth) {
 #pragma unroll
-                for (int r = 0; r < kGemvRows; ++r) unpack8(u[r], f[r]);
+            for (int r = 0; r < kRows; ++r)
 #pragma unroll
-                for (int b = 0; b < kBatch; ++b) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8);
-                    const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + vi * 8 + 4);
+                for (int d = 0; d < kDepth; ++d) {
+                    const int vn = v0 + 32 * kDepth + 32 * d + lane;
+                    un[r][d] = vn < nvec ? ld_stream(wr[r] + vn * 8) : make_uint4(0, 0, 0, 0);
+                }
 #pragma unroll
-                    for (int r = 0; r < kGemvRows; ++r)
-                        acc[r][b] += f[r][0] * x0.x + f[r][1] * x0.y + f[r][2] * x0.z + f[r][3] * x0.w + f[r][4] * x1.x + f[r][5] * x1.y +
-                                     f[r][6] * x1.z + f[r][7] * x1.w;
+            for (int d = 0; d < kDepth; ++d) {
+                const int vi = v0 + 32 * d + lane;
+                if (vi < nvec) {
+                    float f[kRows][8];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) unpack8(u[r][d], f[r]);
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        float xv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(xs + b * K + vi * 8), xv);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r)
+                            acc[r][b] += f[r][0] * xv[0] + f[r][1] * xv[1] + f[r][2] * xv[2] + f[r][3] * xv[3] + f[r][4] * xv[4] + f[r][5] * xv[5] +
+                                         f[r][6] * xv[6] + f[r][7] * xv[7];
+                    }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < kGemvRows; ++r) u[r] = un[r];
+            for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) u[r][d] = un[r][d];
         }
         // reduce; afterwards lane r * kBatch + b holds output (row n0 + r, batch b) and stores it
         float mine = 0.f;
 #pragma unroll
-        for (int r = 0; r < kGemvRows; ++r)
+        for (int r = 0; r < kRows; ++r)
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
                 const float t = warp_sum(acc[r][b]);
                 if (lane == r * kBatch + b) mine = t;
             }
-        if (lane < kGemvRows * kBatch) {
+        if (lane < kRows * kBatch) {
             const int r = lane / kBatch, b = lane - r * kBatch;
             const int n = n0 + r;
             if (n < N) {
@@ -359,6 +437,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
                 float o = bf16_round(mine + bv);
                 if (act_out == 1) o = silu_bf16(o);
                 if (one_plus_mask != nullptr && one_plus_mask[n]) o = bf16_round(1.0f + o);
+                if (residual != nullptr) o += __bfloat162float(residual[(size_t)b * N + n]);
                 y[(size_t)b * N + n] = __float2bfloat16_rn(o);
             }
         }
@@ -554,28 +633,40 @@ int rmsnorm_run(Handle* h, const void* x, void* out, int rows, int C, const void
 }
 
 int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in, int act_out,
-             const uint8_t* one_plus_mask, cudaStream_t s) {
+             const uint8_t* one_plus_mask, cudaStream_t s, const void* norm_w, float norm_eps, const void* residual) {
     PE_REQUIRE(h, batch >= 1 && batch <= 8, "pe_gemv: batch must be 1..8 (got %d)", batch);
+    PE_REQUIRE(h, act_in >= 0 && act_in <= 2 && !(act_in == 2 && norm_w != nullptr), "pe_gemv: act_in must be 0, 1 (SiLU) or 2 (SwiGLU over gate|up), and not combined with a norm");
     PE_REQUIRE(h, N > 0 && K > 0 && K % 8 == 0, "pe_gemv: N>0, K%%8==0 required (N=%d K=%d)", N, K);
     PE_REQUIRE(h, x && w && y, "pe_gemv: null pointer");
-    PE_REQUIRE(h, (size_t)batch * K * 4 <= 200 * 1024, "pe_gemv: batch*K too large for shared memory");
-    const size_t smem = (size_t)batch * K * sizeof(float);
-    int grid = ceil_div(ceil_div(N, kGemvRows), kWarpsPerCta);
+    PE_REQUIRE(h, (size_t)batch * K * 2 <= 200 * 1024, "pe_gemv: batch*K too large for shared memory");
+    const size_t smem = (size_t)batch * K * sizeof(bf16);
+    // narrow outputs (fewer row groups than ~2 per warp slot of the machine): one row per warp, four loads in flight per lane
+    static const int mode = getenv("PE_GEMV_MODE") ? atoi(getenv("PE_GEMV_MODE")) : 0;      // experiments: 1 forces the wide kernel, 2 the narrow one
+    const bool narrow = mode == 2 || (mode == 0 && batch <= 2 && ceil_div(N, kGemvRows) < 2 * h->sm_count * kWarpsPerCta);
+    int grid = ceil_div(ceil_div(N, narrow ? 1 : kGemvRows), kWarpsPerCta);
     const int cap = h->sm_count * 4;
     if (grid > cap) grid = cap;
     const bf16* xb = static_cast<const bf16*>(x);
     const bf16* wb = static_cast<const bf16*>(w);
     const bf16* bb = static_cast<const bf16*>(bias);
     bf16* yb = static_cast<bf16*>(y);
+#define PE_GEMV_LAUNCH(KERN)                                                                                                  \
+    {                                                                                                                        \
+        if (smem > 48 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KERN<<<grid, kWarpsPerCta * 32, smem, s>>>(xb, wb, bb, yb, N, K, act_in, act_out, one_plus_mask,                        \
+                                                   static_cast<const bf16*>(norm_w), norm_eps, static_cast<const bf16*>(residual)); \
+    }
 #define PE_GEMV_CASE(B)                                                                                                      \
     case B: {                                                                                                                \
-        if (smem > 48 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemv_kernel<B><<<grid, kWarpsPerCta * 32, smem, s>>>(xb, wb, bb, yb, N, K, act_in, act_out, one_plus_mask);           \
+        PE_GEMV_LAUNCH((gemv_kernel<B, kGemvRows, 1>))                                                                        \
         break;                                                                                                               \
     }
-    switch (batch) {
+    if (narrow && batch == 1) PE_GEMV_LAUNCH((gemv_kernel<1, 1, 4>))
+    else if (narrow && batch == 2) PE_GEMV_LAUNCH((gemv_kernel<2, 1, 4>))
+    else switch (batch) {
         PE_GEMV_CASE(1) PE_GEMV_CASE(2) PE_GEMV_CASE(3) PE_GEMV_CASE(4) PE_GEMV_CASE(5) PE_GEMV_CASE(6) PE_GEMV_CASE(7) PE_GEMV_CASE(8)
     }
+#undef PE_GEMV_LAUNCH
 #undef PE_GEMV_CASE
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;

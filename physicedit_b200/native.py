@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
     "pe_softmax_rows",
-    "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_advance",
+    "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_gemv_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
     lib.pe_swiglu.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_rope_half.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.pe_range_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64,
@@ -117,6 +118,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_argmax.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pe_kv_append.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]
     lib.pe_advance.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    lib.pe_rope_kv_append.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     return lib
 
 
@@ -409,6 +411,14 @@ class Native:
         self.launches += 1
 
     # ---- Qwen2.5-VL text-encoder path (include/pe_b200.h, last section) --------------------------------------------------------
+    def gemv_fused(self, x, w, bias, y, act_in: int = 0, norm_w=None, eps: float = 1e-6, residual=None) -> None:
+        """x [batch, K] (act_in 2: [batch, 2K] gate|up), w [N, K], y [batch, N]; optional RMSNorm prologue and residual epilogue."""
+        _bf16(x, "x"); _bf16(w, "w"); _bf16(y, "y")
+        batch = 1 if x.dim() == 1 else x.shape[0]
+        self._check(self.lib.pe_gemv_fused(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1], act_in,
+                                           _ptr(norm_w), eps, _ptr(residual), self._stream_prof()), "pe_gemv_fused")
+        self.launches += 1
+
     def swiglu(self, x, out, I: int) -> None:
         """x [rows, >= 2I] = gate | up, out [rows, >= I]."""
         _bf16(x, "x"); _bf16(out, "out")
@@ -458,6 +468,12 @@ class Native:
         _bf16(k_new, "k_new"); _bf16(v_new, "v_new"); _bf16(cache_k, "cache_k"); _bf16(cache_v, "cache_v")
         self._check(self.lib.pe_kv_append(self.h, k_new.data_ptr(), v_new.data_ptr(), cache_k.data_ptr(), cache_v.data_ptr(), cache_k.stride(0),
                                           k_new.numel(), pos.data_ptr(), self._stream_prof()), "pe_kv_append")
+        self.launches += 1
+
+    def rope_kv_append(self, qkv_row, Hq: int, Hkv: int, D: int, cos, sin, cache_k, cache_v, counters) -> None:
+        _bf16(qkv_row, "qkv_row"); _bf16(cache_k, "cache_k"); _bf16(cache_v, "cache_v")
+        self._check(self.lib.pe_rope_kv_append(self.h, qkv_row.data_ptr(), Hq, Hkv, D, cos.data_ptr(), sin.data_ptr(), cache_k.data_ptr(), cache_v.data_ptr(),
+                                               cache_k.stride(0), counters.data_ptr(), self._stream_prof()), "pe_rope_kv_append")
         self.launches += 1
 
     def advance(self, counters, n: int) -> None:

@@ -450,6 +450,14 @@ class QwenImagePhysicPipeline(nn.Module):
         for unit in units:
             if self.vae is None and unit.onload_model_names == ("vae",) and not (unit.input_params and "noise" in unit.input_params):
                 continue                                  # no VAE loaded: image-embedding units have nothing to run on (latents must be handed in)
+            if (isinstance(unit, QwenImageUnit_PhysicalVerbalEmbedder) and cfg_scale != 1 and hasattr(self.text_encoder, "generate_batch")
+                    and getattr(self, "batch_cfg_generation", True) and inputs_shared.get("edit_image") is not None
+                    and None in (supported_rules, contradicted_rules, middle_key_frames, input_image)):
+                # both CFG branches' generations decoded together (same outputs as the runner's two calls, about half the time)
+                out_p, out_n = unit.process_both_branches(self, inputs_posi.get("prompt"), inputs_nega.get("negative_prompt"), inputs_shared["edit_image"])
+                inputs_posi.update(out_p)
+                inputs_nega.update(out_n)
+                continue
             inputs_shared, inputs_posi, inputs_nega = self.unit_runner(unit, self, inputs_shared, inputs_posi, inputs_nega)
         if edit_latents is not None:
             inputs_shared["edit_latents"] = edit_latents

@@ -274,6 +274,7 @@ class QwenImageTextEncoder(nn.Module):
         self.lm_head = nn.Linear(self.cfg.hidden, self.cfg.vocab, bias=False)
         self._packed = None
         self.use_cuda_graph = True
+        self.fused_decode = True          # decode step with the norms / SwiGLU / skip adds fused into the GEMVs (False: one kernel per op)
         self.last_generate_stats: dict = {}
 
     @staticmethod
@@ -419,8 +420,7 @@ class QwenImageTextEncoder(nn.Module):
             pk = P["text"][i]
             nat.rmsnorm(x, xn, l.input_layernorm.weight, c.rms_eps)
             nat.gemm([dict(a=xn, w=pk["wqkv"], bias=pk["bqkv"], out=qkv)], HD + 2 * KD, c.hidden, nv.EPI_BIAS)
-            nat.rope_half(qkv[:, :HD], c.heads, c.head_dim, cos, sin, mode=1)
-            nat.rope_half(qkv[:, HD:HD + KD], c.kv_heads, c.head_dim, cos, sin, mode=1)
+            nat.rope_half(qkv[:, :HD + KD], c.heads + c.kv_heads, c.head_dim, cos, sin, mode=1)        # q and k heads are adjacent columns
             nat.range_attention(qkv[:, :HD], qkv[:, HD:HD + KD], qkv[:, HD + KD:], att, c.heads, c.kv_heads, c.head_dim, c.head_dim ** -0.5, kv_hi=causal_hi)
             if cache is not None:
                 cache[i][0][:T].copy_(qkv[:, HD:HD + KD])
@@ -461,62 +461,119 @@ class QwenImageTextEncoder(nn.Module):
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 1000, **kwargs):
         """Returns [1, T + n] = the prompt followed by the generated ids (ending with the EOS token if one was produced)."""
+        return self.generate_batch([dict(input_ids=input_ids, attention_mask=attention_mask, pixel_values=pixel_values, image_grid_thw=image_grid_thw)],
+                                   max_new_tokens=max_new_tokens)[0]
+
+    @torch.no_grad()
+    def generate_batch(self, requests: Sequence[dict], max_new_tokens: int = 1000) -> List[torch.Tensor]:
+        """Greedy generation for up to 8 independent requests decoded TOGETHER: the pipeline generates once per CFG branch
+        (qwen_image_physical.py:859-873 runs for the positive and for the negative prompt), and a B=1 decode step streams all 15 GB of
+        weights for one token -- decoding both branches in one batch-2 step streams them once for two tokens.  Each request is
+        prefilled on its own (different lengths), keeps its own KV cache and device-side counters, and is cut at its own EOS; rows of a
+        batched GEMV are computed independently, so the token ids are those of the one-by-one runs."""
         import time
-        self._check_b1(input_ids, attention_mask)
         c = self.cfg
         nat, P = self._ctx()
         dev = self.lm_head.weight.device
         bf = dict(dtype=torch.bfloat16, device=dev)
+        nb = len(requests)
+        if not 1 <= nb <= 8:
+            raise ValueError("generate_batch takes 1..8 requests")
         t0 = time.time()
-        T = input_ids.numel()
-        max_len = T + max_new_tokens
         KD, HD = c.kv_heads * c.head_dim, c.heads * c.head_dim
-        cache = [(torch.empty(max_len, KD, **bf), torch.empty(max_len, KD, **bf)) for _ in range(c.layers)]
-        x = self._embed(nat, input_ids, pixel_values, image_grid_thw)
-        pos, delta = self._positions(input_ids, image_grid_thw)
-        cos, sin = (t.to(dev) for t in text_rope_tables(c, pos))
-        h = self._prefill(nat, P, x, cos, sin, cache)
+        Ts, caches, h_last, deltas = [], [], [], []
+        for r in requests:
+            self._check_b1(r["input_ids"], r.get("attention_mask"))
+            T = r["input_ids"].numel()
+            cache = [(torch.empty(T + max_new_tokens, KD, **bf), torch.empty(T + max_new_tokens, KD, **bf)) for _ in range(c.layers)]
+            x = self._embed(nat, r["input_ids"], r.get("pixel_values"), r.get("image_grid_thw"))
+            pos, delta = self._positions(r["input_ids"], r.get("image_grid_thw"))
+            cos, sin = (t.to(dev) for t in text_rope_tables(c, pos))
+            h = self._prefill(nat, P, x, cos, sin, cache)
+            Ts.append(T); caches.append(cache); h_last.append(h[T - 1:T]); deltas.append(delta)
         # decode-time rotary table: all three axes share the position, row r = position r
-        n_rows = T + delta + max_new_tokens + 1
+        n_rows = max(T + d for T, d in zip(Ts, deltas)) + max_new_tokens + 1
         cos_d, sin_d = (t.to(dev) for t in text_rope_tables(c, torch.arange(n_rows).view(1, -1).expand(3, -1)))
-        # device-side state of a decode step: [kv rows cached, rope row, step, kv rows after this step's append]
-        ctr = torch.tensor([T, T + delta, 0, T + 1], dtype=torch.int32, device=dev)
-        log = torch.full((max_new_tokens + 1,), -1, dtype=torch.int64, device=dev)
-        tok = torch.zeros(1, dtype=torch.int64, device=dev)
-        B = dict(x=torch.empty(1, c.hidden, **bf), xn=torch.empty(1, c.hidden, **bf), qkv=torch.empty(1, HD + 2 * KD, **bf), att=torch.empty(1, HD, **bf),
-                 o=torch.empty(1, c.hidden, **bf), gu=torch.empty(1, 2 * c.intermediate, **bf), hm=torch.empty(1, c.intermediate, **bf),
-                 logits=torch.empty(1, c.vocab, **bf))
+        # device-side state of a decode step, per request: [kv rows cached, rope row, step, kv rows after this step's append]
+        ctr = torch.tensor([[T, T + d, 0, T + 1] for T, d in zip(Ts, deltas)], dtype=torch.int32, device=dev)
+        log = torch.full((nb, max_new_tokens + 1), -1, dtype=torch.int64, device=dev)
+        tok = torch.zeros(nb, dtype=torch.int64, device=dev)
+        B = dict(x=torch.empty(nb, c.hidden, **bf), xn=torch.empty(nb, c.hidden, **bf), qkv=torch.empty(nb, HD + 2 * KD, **bf), att=torch.empty(nb, HD, **bf),
+                 o=torch.empty(nb, c.hidden, **bf), gu=torch.empty(nb, 2 * c.intermediate, **bf), hm=torch.empty(nb, c.intermediate, **bf),
+                 logits=torch.empty(nb, c.vocab, **bf))
         emb_w = self.model.language_model.embed_tokens.weight
 
-        def head(hidden_row):
-            nat.gemv(hidden_row, self.lm_head.weight, None, B["logits"])
-            nat.argmax(B["logits"], tok, log, ctr[2:3])
+        def head(hidden_rows, norm_w=None):
+            nat.tag = "te_lm_head"
+            if norm_w is not None:
+                nat.gemv_fused(hidden_rows, self.lm_head.weight, None, B["logits"], norm_w=norm_w, eps=c.rms_eps)      # final norm fused in
+            else:
+                nat.gemv(hidden_rows, self.lm_head.weight, None, B["logits"])
+            for b in range(nb):
+                nat.tag = "te_argmax"
+                nat.argmax(B["logits"][b], tok[b:b + 1], log[b], ctr[b, 2:3])
 
         def step():
-            """one token: embed(tok) -> 28 layers with the KV cache -> norm -> lm_head -> argmax; every position comes from `ctr`."""
+            """one token per request: embed(tok) -> 28 layers with the KV caches -> norm -> lm_head -> argmax; every position comes from `ctr`."""
+            nat.tag = "te_embed"
             nat.gather_rows(emb_w, tok, B["x"])
             for i, l in enumerate(self.model.language_model.layers):
                 pk = P["text"][i]
+                if self.fused_decode:
+                    # 4 + 2 x requests launches per layer: the norms, SwiGLU and skip adds ride in the GEMVs' prologues / epilogues,
+                    # rope + KV append are one kernel (same arithmetic and rounding points as the unfused sequence below)
+                    nat.tag = "te_gemv_qkv"
+                    nat.gemv_fused(B["x"], pk["wqkv"], pk["bqkv"], B["qkv"], norm_w=l.input_layernorm.weight, eps=c.rms_eps)
+                    for b in range(nb):
+                        nat.tag = "te_rope_kv"
+                        nat.rope_kv_append(B["qkv"][b], c.heads, c.kv_heads, c.head_dim, cos_d, sin_d, caches[b][i][0], caches[b][i][1], ctr[b])
+                        nat.tag = "te_attention"
+                        nat.range_attention(B["qkv"][b:b + 1, :HD], caches[b][i][0], caches[b][i][1], B["att"][b:b + 1], c.heads, c.kv_heads, c.head_dim,
+                                            c.head_dim ** -0.5, kv_len_ptr=ctr[b, 3:4])
+                    nat.tag = "te_gemv_o"
+                    nat.gemv_fused(B["att"], l.self_attn.o_proj.weight, None, B["x"], residual=B["x"])
+                    nat.tag = "te_gemv_gate_up"
+                    nat.gemv_fused(B["x"], pk["wgu"], None, B["gu"], norm_w=l.post_attention_layernorm.weight, eps=c.rms_eps)
+                    nat.tag = "te_gemv_down"
+                    nat.gemv_fused(B["gu"], l.mlp.down_proj.weight, None, B["x"], act_in=2, residual=B["x"])
+                    continue
+                nat.tag = "te_rmsnorm"
                 nat.rmsnorm(B["x"], B["xn"], l.input_layernorm.weight, c.rms_eps)
+                nat.tag = "te_gemv_qkv"
                 nat.gemv(B["xn"], pk["wqkv"], pk["bqkv"], B["qkv"])
-                nat.rope_half(B["qkv"][:, :HD], c.heads, c.head_dim, cos_d, sin_d, row_ptr=ctr[1:2], mode=1)
-                nat.rope_half(B["qkv"][:, HD:HD + KD], c.kv_heads, c.head_dim, cos_d, sin_d, row_ptr=ctr[1:2], mode=1)
-                nat.kv_append(B["qkv"][0, HD:HD + KD], B["qkv"][0, HD + KD:], cache[i][0], cache[i][1], ctr[0:1])
-                nat.range_attention(B["qkv"][:, :HD], cache[i][0], cache[i][1], B["att"], c.heads, c.kv_heads, c.head_dim, c.head_dim ** -0.5,
-                                    kv_len_ptr=ctr[3:4])
+                for b in range(nb):
+                    nat.tag = "te_rope"
+                    nat.rope_half(B["qkv"][b:b + 1, :HD + KD], c.heads + c.kv_heads, c.head_dim, cos_d, sin_d, row_ptr=ctr[b, 1:2], mode=1)   # q and k heads are adjacent
+                    nat.tag = "te_kv_append"
+                    nat.kv_append(B["qkv"][b, HD:HD + KD], B["qkv"][b, HD + KD:], caches[b][i][0], caches[b][i][1], ctr[b, 0:1])
+                    nat.tag = "te_attention"
+                    nat.range_attention(B["qkv"][b:b + 1, :HD], caches[b][i][0], caches[b][i][1], B["att"][b:b + 1], c.heads, c.kv_heads, c.head_dim,
+                                        c.head_dim ** -0.5, kv_len_ptr=ctr[b, 3:4])
+                nat.tag = "te_gemv_o"
                 nat.gemv(B["att"], l.self_attn.o_proj.weight, None, B["o"])
-                nat.add_rows(B["x"], B["o"], 1, 1.0)
+                nat.tag = "te_residual"
+                nat.add_rows(B["x"], B["o"], nb, 1.0)
+                nat.tag = "te_rmsnorm"
                 nat.rmsnorm(B["x"], B["xn"], l.post_attention_layernorm.weight, c.rms_eps)
+                nat.tag = "te_gemv_gate_up"
                 nat.gemv(B["xn"], pk["wgu"], None, B["gu"])
+                nat.tag = "te_swiglu"
                 nat.swiglu(B["gu"], B["hm"], c.intermediate)
+                nat.tag = "te_gemv_down"
                 nat.gemv(B["hm"], l.mlp.down_proj.weight, None, B["o"])
-                nat.add_rows(B["x"], B["o"], 1, 1.0)
-            nat.rmsnorm(B["x"], B["xn"], self.model.language_model.norm.weight, c.rms_eps)
-            nat.advance(ctr, 4)
-            head(B["xn"])
+                nat.tag = "te_residual"
+                nat.add_rows(B["x"], B["o"], nb, 1.0)
+            nat.tag = "te_advance"
+            nat.advance(ctr, 4 * nb)
+            if self.fused_decode:
+                head(B["x"], self.model.language_model.norm.weight)
+            else:
+                nat.tag = "te_rmsnorm"
+                nat.rmsnorm(B["x"], B["xn"], self.model.language_model.norm.weight, c.rms_eps)
+                head(B["xn"])
 
-        head(h[T - 1:T].contiguous())                   # token 1 from the prefill's last position (log slot 0)
-        done = 1                                        # tokens generated so far
+        head(torch.cat(h_last, dim=0).contiguous())     # token 1 of every request from its prefill's last position (log slot 0)
+        done = 1                                        # tokens generated so far (per request)
         t_prefill = time.time()
         graph = None
         if self.use_cuda_graph and max_new_tokens > 2:
@@ -526,11 +583,13 @@ class QwenImageTextEncoder(nn.Module):
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):      # records the launches, does not run them: ctr / log / cache stay as they are
+                with torch.cuda.graph(graph, stream=side):      # records the launches, does not run them: ctr / log / caches stay as they are
                     step()
             torch.cuda.current_stream(dev).wait_stream(side)
-        n_out = None
-        while n_out is None:
+        torch.cuda.synchronize(dev)
+        t_loop, done_at_loop = time.time(), done       # capture / warm-up excluded from the per-token figure
+        n_out = [None] * nb
+        while any(n is None for n in n_out):
             upto = min(max_new_tokens, done + 32)
             while done < upto:
                 if graph is not None:
@@ -538,17 +597,18 @@ class QwenImageTextEncoder(nn.Module):
                 else:
                     step()
                 done += 1
-            got = log[:done].tolist()                   # one small D2H per 32 tokens: has EOS appeared?
-            if c.eos_token_id in got:
-                n_out = got.index(c.eos_token_id) + 1
-            elif done >= max_new_tokens:
-                n_out = max_new_tokens
+            got = log[:, :done].tolist()                # one small D2H per 32 tokens: has every request reached its EOS?
+            for b in range(nb):
+                if n_out[b] is None and c.eos_token_id in got[b]:
+                    n_out[b] = got[b].index(c.eos_token_id) + 1
+                elif n_out[b] is None and done >= max_new_tokens:
+                    n_out[b] = max_new_tokens
         nat.check_async()
-        new = log[:n_out].clone()
         t1 = time.time()
-        self.last_generate_stats = {"prompt_tokens": T, "new_tokens": int(n_out), "tokens_computed": int(done), "prefill_s": t_prefill - t0,
-                                    "decode_s": t1 - t_prefill, "ms_per_token": (t1 - t_prefill) * 1e3 / max(done - 1, 1), "cuda_graph": graph is not None}
-        return torch.cat([input_ids.reshape(1, -1).to(dev), new.view(1, -1)], dim=1)
+        self.last_generate_stats = {"requests": nb, "prompt_tokens": Ts[0] if nb == 1 else Ts, "new_tokens": int(n_out[0]) if nb == 1 else [int(n) for n in n_out],
+                                    "tokens_computed": int(done), "prefill_s": t_prefill - t0, "decode_s": t1 - t_prefill, "graph_capture_s": t_loop - t_prefill,
+                                    "ms_per_token": (t1 - t_loop) * 1e3 / max(done - done_at_loop, 1), "cuda_graph": graph is not None}
+        return [torch.cat([r["input_ids"].reshape(1, -1).to(dev), log[b, :n_out[b]].view(1, -1)], dim=1) for b, r in enumerate(requests)]
 
 
 def load_text_encoder(state_dict, torch_dtype=torch.bfloat16, device="cuda", config: Optional[VLConfig] = None):

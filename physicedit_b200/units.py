@@ -248,10 +248,9 @@ class QwenImageUnit_PhysicalVerbalEmbedder(PipelineUnit):
             raise ValueError(f"Unsupported response format. Expected one of {self.ACCEPTED}, got keys {sorted(fields)}: {data}")
         return fields
 
-    def generate_text(self, pipe, model_inputs) -> str:
-        """(:859-872) greedy generation, the prompt tokens trimmed off, decoded; a parsable JSON answer is flattened to "\\nkey: value"
-        lines, anything else is passed through verbatim."""
-        out = pipe.text_encoder.generate(**model_inputs, max_new_tokens=1000)
+    def _answer(self, pipe, model_inputs, out) -> str:
+        """(:861-872) the prompt tokens trimmed off, decoded; a parsable JSON answer is flattened to "\\nkey: value" lines, anything
+        else is passed through verbatim."""
         new_tokens = [o[len(i):] for i, o in zip(model_inputs.input_ids, out)]
         text = pipe.tokenizer.batch_decode(new_tokens, skip_special_tokens=True, clean_up_tokenization_spaces=False)[0]
         try:
@@ -260,14 +259,30 @@ class QwenImageUnit_PhysicalVerbalEmbedder(PipelineUnit):
             return text
         return "".join(f"\n{k}: {v}" for k, v in fields.items())
 
-    def encode_physical_prompt_sample(self, pipe, edit_image, prompt) -> str:
-        """(:943-967)"""
+    def generate_text(self, pipe, model_inputs) -> str:
+        """(:859-860) greedy generation, at most 1000 new tokens."""
+        return self._answer(pipe, model_inputs, pipe.text_encoder.generate(**model_inputs, max_new_tokens=1000))
+
+    def sample_inputs(self, pipe, edit_image, prompt):
+        """(:943-963) the chat request the VL model answers: system prompt, the edit instruction, a ~384^2 copy of the edit image."""
         user = [{"type": "input_text", "text": "Edit Instruction:"}, {"type": "input_text", "text": prompt},
                 {"type": "input_text", "text": "Edit Image:"}, {"type": "image"}]
         chat = pipe.processor.apply_chat_template([{"role": "system", "content": SYSTEM_PROMPT_SAMPLE}, {"role": "user", "content": user}],
                                                   tokenize=False, add_generation_prompt=True, add_vision_id=True)
-        model_inputs = pipe.processor(text=[chat], images=self.resize_image(edit_image), padding=True, return_tensors="pt").to(pipe.device)
-        return self.generate_text(pipe, model_inputs)
+        return pipe.processor(text=[chat], images=self.resize_image(edit_image), padding=True, return_tensors="pt").to(pipe.device)
+
+    def encode_physical_prompt_sample(self, pipe, edit_image, prompt) -> str:
+        """(:943-967)"""
+        return self.generate_text(pipe, self.sample_inputs(pipe, edit_image, prompt))
+
+    def process_both_branches(self, pipe, prompt, negative_prompt, edit_image):
+        """The positive and the negative branch's `process` (the runner calls it once per branch, utils/__init__.py:256-270) in ONE batched
+        generation when the text encoder offers `generate_batch`: B=1 decode streams every weight per token, so two requests decoded
+        together cost about one.  Same requests, same greedy tokens, same parsing -- returns (outputs_posi, outputs_nega)."""
+        reqs = [self.sample_inputs(pipe, edit_image, p) for p in (prompt, negative_prompt)]
+        keys = ("input_ids", "attention_mask", "pixel_values", "image_grid_thw")
+        outs = pipe.text_encoder.generate_batch([{k: r[k] for k in keys if k in r} for r in reqs], max_new_tokens=1000)
+        return tuple({"physical_txt": self._answer(pipe, r, o)} for r, o in zip(reqs, outs))
 
     def process(self, pipe, prompt, edit_image=None, supported_rules=None, contradicted_rules=None, middle_key_frames=None, input_image=None,
                 triplet=None) -> dict:

@@ -155,10 +155,87 @@ def test_greedy_generate_matches_the_oracle(native_te, with_image, graph):
 
 
 @gpu
+def test_batched_generation_of_both_cfg_branches_equals_one_by_one(native_te):
+    """generate_batch (what the pipeline uses for the positive + negative prompt) vs two generate calls: same token ids."""
+    a = {k: v.cuda() for k, v in VO.inputs(True).items()}
+    b = {k: v.cuda() for k, v in VO.inputs(False).items()}
+    c = {k: v.cuda() for k, v in VO.inputs(True, seed=9, n_text=40).items()}
+    native_te.use_cuda_graph = True
+    one = [native_te.generate(**r, max_new_tokens=40) for r in (a, b, c)]
+    both = native_te.generate_batch([a, b, c], max_new_tokens=40)
+    assert native_te.last_generate_stats["requests"] == 3
+    for x, y in zip(one, both):
+        assert torch.equal(x, y)
+
+
+@gpu
 def test_cuda_graph_and_eager_decode_agree(native_te):
     inp = {k: v.cuda() for k, v in VO.inputs(True).items()}
     outs = []
-    for graph in (True, False):
-        native_te.use_cuda_graph = graph
+    for graph, fused in ((True, True), (False, True), (True, False), (False, False)):
+        native_te.use_cuda_graph, native_te.fused_decode = graph, fused       # fused: norms / SwiGLU / skip adds inside the GEMVs, rope + KV append in one kernel
         outs.append(native_te.generate(**inp, max_new_tokens=48))
-    assert torch.equal(outs[0], outs[1])
+    native_te.use_cuda_graph = native_te.fused_decode = True
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+@gpu
+def test_pipeline_call_runs_the_validate_py_flow_on_the_native_text_encoder():
+    """`pipe(prompt, edit_image=PIL, is_train=False)` as scripts/inference/validate.py:127-139 calls it, every model native: the VL model
+    generates the physical-thinking text for both CFG branches, encodes prompt + image into prompt_emb / special_token_mask, the VAE
+    encodes the edit image, the DiT denoises, the VAE decodes.  Synthetic weights (prompt width 3584 as the DiT expects, real
+    tokenizer / processor files when the reference's vendored copies are on the box)."""
+    import os
+    import numpy as np
+    from PIL import Image
+    from physicedit_b200.dit import QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    from physicedit_b200.text_encoder import QwenImageTextEncoder, VLConfig
+    from physicedit_b200.vae import QwenImageVAE
+    from oracle import vae_oracle as VAO
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    qwen = next((p for p in (os.path.join(root, "baseline", "_ref", "models", "Qwen"), "/root/reference/DiffSynth-Studio/models/Qwen") if os.path.isdir(p)), None)
+    if qwen is None:
+        pytest.skip("tokenizer / processor files of the reference are not on this box")
+    from transformers import Qwen2Tokenizer, Qwen2VLProcessor
+    tok = Qwen2Tokenizer.from_pretrained(os.path.join(qwen, "Qwen-Image", "tokenizer"))
+    base = Qwen2VLProcessor.from_pretrained(os.path.join(qwen, "Qwen-Image-Edit", "processor"))
+    proc = Qwen2VLProcessor(image_processor=base.image_processor, tokenizer=Qwen2Tokenizer.from_pretrained(os.path.join(qwen, "Qwen-Image", "tokenizer")),
+                            video_processor=base.video_processor, chat_template=base.chat_template)
+    cfg = VLConfig(layers=2, intermediate=1024, v_hidden=160, v_depth=2, v_heads=2, v_intermediate=220, fullatt=(1,))      # hidden 3584, vocab 152064
+    g = torch.Generator(device="cuda").manual_seed(5)
+    with torch.device("meta"):
+        te = QwenImageTextEncoder(cfg)
+    sd = {}
+    for k, v in te.state_dict().items():
+        if v.dim() >= 2:
+            t = (torch.rand(v.shape, generator=g, device="cuda") * 2 - 1) * (1.0 / math.sqrt(math.prod(v.shape[1:]))) if "embed_tokens" not in k else torch.randn(v.shape, generator=g, device="cuda")
+        else:
+            t = torch.ones(v.shape, device="cuda") if k.endswith("norm.weight") or k.endswith("layernorm.weight") or "norm" in k or "ln_q" in k else torch.zeros(v.shape, device="cuda")
+        sd[k] = t.to(torch.bfloat16)
+    te.load_state_dict(sd, assign=True)
+    pipe = QwenImagePhysicPipeline(device="cuda", torch_dtype=torch.bfloat16, build_training_path=False)
+    W = {k: v.to(torch.bfloat16) for k, v in __import__("oracle.dit_oracle", fromlist=["x"]).synth_weights(__import__("oracle.dit_oracle", fromlist=["x"]).dit_param_shapes(1), seed=4).items()}
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict(W, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe.dit = dit.to("cuda").eval()
+    with torch.device("meta"):
+        vae = QwenImageVAE()
+    vae.load_state_dict({k: v.to(torch.bfloat16) for k, v in VAO.vae_synth_weights(seed=21).items()}, assign=True, strict=True)
+    pipe.vae = vae.to("cuda").eval()
+    pipe.text_encoder = te.eval()
+    pipe.attach_tokenizer(tokenizer=tok, processor=proc)
+    for p_ in pipe.visual_thinking_adapter.parameters():
+        p_.data = ((torch.rand(p_.shape, generator=g, device="cuda") * 2 - 1) * 0.02).to(torch.bfloat16)
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8))
+    te.cfg.eos_token_id = -1                              # random weights: let both branches run into the 1000-token cap like a worst case
+    out = pipe("make the ice melt", edit_image=img, edit_image_auto_resize=False, seed=1, num_inference_steps=2, height=96, width=128, is_train=False)
+    assert isinstance(out, Image.Image) and out.size == (128, 96)
+    st = te.last_generate_stats
+    assert st["requests"] == 2 and st["new_tokens"] == [1000, 1000] and st["cuda_graph"]        # both CFG branches decoded in one batch
+    print(f"\nfull flow: generate {st}")
+    from physicedit_b200 import native as nv
+    nv.Native.get(0).check_async()
