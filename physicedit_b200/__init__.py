@@ -25,6 +25,9 @@ _LAZY = {
     "adopt_dit": ("compat", "adopt_dit"),
     "adopt_adapter": ("compat", "adopt_adapter"),
     "adopt_vae": ("compat", "adopt_vae"),
+    "adopt_text_encoder": ("compat", "adopt_text_encoder"),
+    "QwenImageTextEncoder": ("text_encoder", "QwenImageTextEncoder"),
+    "load_text_encoder": ("text_encoder", "load_text_encoder"),
 }
 
 

@@ -47,6 +47,16 @@ def adopt_vae(ref_vae: torch.nn.Module):
     return vae.eval()
 
 
+def adopt_text_encoder(ref_te: torch.nn.Module):
+    """The reference's loaded QwenImageTextEncoderWithDecode (models/qwen_image_text_encoder_withdecode.py:6, a transformers
+    Qwen2_5_VLForConditionalGeneration) -> the native module on the same parameter storage (7B config of the wrapper)."""
+    from .text_encoder import QwenImageTextEncoder
+    with torch.device("meta"):
+        te = QwenImageTextEncoder()
+    te.load_state_dict(ref_te.state_dict(), assign=True)
+    return te.eval()
+
+
 @dataclass
 class ControlNetInput:
     """pipelines/flux_image_new.py:5-13 (only imported by the scripts; blockwise controlnet is out of scope)."""

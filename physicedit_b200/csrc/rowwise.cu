@@ -652,7 +652,7 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
     bf16* yb = static_cast<bf16*>(y);
 #define PE_GEMV_LAUNCH(KERN)                                                                                                  \
     {                                                                                                                        \
-        if (smem > 48 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (smem > 40 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* static smem counts toward the 48 KB default too */ \
         KERN<<<grid, kWarpsPerCta * 32, smem, s>>>(xb, wb, bb, yb, N, K, act_in, act_out, one_plus_mask,                        \
                                                    static_cast<const bf16*>(norm_w), norm_eps, static_cast<const bf16*>(residual)); \
     }
