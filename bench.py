@@ -81,6 +81,12 @@ def ncu_traffic_bytes(kernel_substr):
             return int((g["dram_read_MB"] + g["dram_write_MB"]) * 1e6)
     except (OSError, KeyError, ValueError):
         pass
+    try:        # r2 full capture of the attention kernel (profiles/r02_ncu_attention_full.json)
+        if "attention_kernel" in kernel_substr:
+            row = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_attention_full.json")))[0]
+            return int((float(row["dram__bytes_read.sum"].split()[0]) + float(row["dram__bytes_write.sum"].split()[0])) * 1e6)
+    except (OSError, KeyError, ValueError, IndexError):
+        pass
     try:
         for row in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_metrics.json"))):
             if kernel_substr in row["kernel"]:
@@ -379,7 +385,7 @@ def run_native(args):
             ach, pk, unit, src = by / avg_s / 1e9, peak_gbs, "GB/s", "MEASURED_PEAKS.json hbm_gbs"
         roofs[tag] = {"bound": bound, "kernel": desc, "achieved": round(ach, 1), "peak": pk, "peak_source": src if peaks else "fallback", "unit": unit,
                       "frac": round(ach / pk, 4), "traffic": ncu_traffic_bytes(ncu_name) if ncu_name else None,
-                      "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_full_metrics.json / r01_gemm_traffic.json)", "algorithmic_bytes": int(by),
+                      "traffic_unit": "bytes per launch (ncu --set full: profiles/r02_ncu_attention_full.json, r01_ncu_full_metrics.json, r01_gemm_traffic.json)", "algorithmic_bytes": int(by),
                       "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms_attr, 4)}
     roof = None
     if roofs:
