@@ -1123,83 +1123,98 @@ __global__ void __launch_bounds__(kA2Threads, 1) attention_kernel4(const __grid_
         }
     } else if (warp == 1) {
         // ======================================= MMA issuer =======================================
-        // (A variant that ran this whole loop on one lane of a diverged warp was measured 35 % slower per batch:
-        //  the uniform datapath that feeds UTCHMMA needs the converged warp.)
+        // In this kernel the softmax link of the per-tile chain is short enough that THIS warp's own serial time line decides the
+        // period (r2 trace: ~740 cycles between the end of tile 1's batch and the start of the wait for P0 -- two commits and two
+        // kv_full polls of 200-280 cycles each, although those barriers completed long before; SYNCS round trips share the SMSP's MIO
+        // queue with the MUFU-heavy softmax warps).  So: the leader is elected once, descriptors are base word + constant (as in
+        // kernel 1), and every barrier the NEXT batch needs is probed with a non-blocking test_wait issued BEFORE the current batch's
+        // 16 blocking UTCHMMA issues -- the probe's round trip overlaps the ~1000 cycles of issue, and the blocking wait is only taken
+        // when the probe said "not yet".
         constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);
+        const bool leader = elect_one();
         uint32_t n = 0, it = 0;
         uint32_t p_phase[2] = {0, 0};
         bool ok = true;
         PE_TRACE_DECL(0)
         auto issue_s = [&](int q, uint32_t k_base) {
-            if (elect_one()) {
+            const uint32_t qlo = desc_lo_k(q_smem(q)), klo = desc_lo_k(k_base);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-                    umma_bf16<1>(s_tmem(q), make_smem_desc_sw128(q_smem(q) + off, 16, 1024),
-                                 make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
-                }
-                umma_commit(s_full(q));
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint32_t off16 = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+                if (kk == 0) umma_ss_lohi<false>(s_tmem(q), qlo + off16, klo + off16, idesc_s);
+                else umma_ss_lohi<true>(s_tmem(q), qlo + off16, klo + off16, idesc_s);
             }
-            __syncwarp();
+            umma_commit(s_full(q));
         };
         auto issue_pv = [&](int q, uint32_t v_base, bool accumulate, bool last) {
-            if (elect_one()) {
+            const uint32_t vlo = desc_lo_v(v_base);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 2048, kHalfBytes, 1024);
-                    // P: kv columns 0-63 are packed in TMEM columns [0,32), kv columns 64-127 in TMEM columns [64,96)
-                    const uint32_t a_tmem = s_tmem(q) + (kk >> 2) * 64 + (kk & 3) * 8;
-                    umma_bf16_ts(o_tmem(q), a_tmem, bdesc, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
-                }
-                if (last) umma_commit(pv_done(q));       // once per item (see attention_kernel)
+            for (int kk = 0; kk < 8; ++kk) {
+                // P: kv columns 0-63 are packed in TMEM columns [0,32), kv columns 64-127 in TMEM columns [64,96)
+                const uint32_t a_tmem = s_tmem(q) + (kk >> 2) * 64 + (kk & 3) * 8;
+                umma_ts_lohi(o_tmem(q), a_tmem, vlo + kk * (2048 >> 4), idesc_o, (accumulate || kk != 0) ? 1u : 0u);
             }
-            __syncwarp();
+            if (last) umma_commit(pv_done(q));       // once per item (see attention_kernel)
         };
+        auto probe = [&](uint32_t bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test_wait(bar, parity)); };
         for (int item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
             if (!mbar_wait(q_full, it & 1u, p.abort_flag, 50)) break;
             uint32_t k_slot = n % kKV;
             if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 51)) break;
             ++n;
             tc_fence_after();
+            if (leader) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) issue_s(q, kv_smem(k_slot));
-            if (elect_one()) {
+                for (int q = 0; q < 2; ++q) issue_s(q, kv_smem(k_slot));
                 umma_commit(kv_empty(k_slot));
                 if (p.n_kv == 1) umma_commit(q_empty);
             }
             __syncwarp();
+            bool v_ready = false, k_ready = false, p_ready[2] = {false, false};
             for (int j = 0; j < p.n_kv && ok; ++j) {
                 const uint32_t v_slot = n % kKV;
-                if (!mbar_wait(kv_full(v_slot), (n / kKV) & 1u, p.abort_flag, 52)) { ok = false; break; }
+                if (!v_ready && !mbar_wait(kv_full(v_slot), (n / kKV) & 1u, p.abort_flag, 52)) { ok = false; break; }
                 ++n;
                 const bool more = j + 1 < p.n_kv;
                 if (more) {
                     k_slot = n % kKV;
-                    if (!mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 53)) { ok = false; break; }
+                    if (!k_ready && !mbar_wait(kv_full(k_slot), (n / kKV) & 1u, p.abort_flag, 53)) { ok = false; break; }
                     ++n;
                 }
+                v_ready = k_ready = false;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (j == 0) {
                         if (!mbar_wait(o_empty(q), (it & 1u) ^ 1u, p.abort_flag, 54)) { ok = false; break; }
                     }
                     PE_TRACE(10 + q, j);
-                    if (!mbar_wait(p_full(q), p_phase[q], p.abort_flag, 55)) { ok = false; break; }
+                    if (!p_ready[q] && !mbar_wait(p_full(q), p_phase[q], p.abort_flag, 55)) { ok = false; break; }
+                    p_ready[q] = false;
                     p_phase[q] ^= 1u;
                     tc_fence_after();
                     PE_TRACE(12 + q, j);
-                    issue_pv(q, kv_smem(v_slot), j > 0, !more);
-                    if (more) issue_s(q, kv_smem(k_slot));
+                    // probes for what follows this batch, issued before its MMAs
+                    if (q == 0) {
+                        p_ready[1] = probe(p_full(1), p_phase[1]);
+                    } else if (more) {
+                        v_ready = probe(kv_full(n % kKV), (n / kKV) & 1u);
+                        if (j + 2 < p.n_kv) k_ready = probe(kv_full((n + 1) % kKV), ((n + 1) / kKV) & 1u);
+                        p_ready[0] = probe(p_full(0), p_phase[0]);
+                    }
+                    if (leader) {
+                        issue_pv(q, kv_smem(v_slot), j > 0, !more);
+                        if (more) issue_s(q, kv_smem(k_slot));
+                        if (q == 1) {
+                            umma_commit(kv_empty(v_slot));
+                            if (more) umma_commit(kv_empty(k_slot));
+                            if (j + 2 == p.n_kv) umma_commit(q_empty);
+                        }
+                    }
+                    __syncwarp();
                     PE_TRACE(14 + q, j);
                 }
                 if (!ok) break;
-                if (elect_one()) {
-                    umma_commit(kv_empty(v_slot));
-                    if (more) umma_commit(kv_empty(k_slot));
-                    if (j + 2 == p.n_kv) umma_commit(q_empty);
-                }
-                __syncwarp();
             }
         }
     } else if (warp >= 4) {
