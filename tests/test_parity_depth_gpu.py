@@ -400,3 +400,47 @@ def test_in_place_weight_load_drops_the_conditioning_cache():
     y32 = oracle_forward(sd2, None, no_sp, t, 64, 64, torch.float32, 1)
     y16 = oracle_forward(sd2, None, no_sp, t, 64, 64, torch.bfloat16, 1)
     assert rel_l2(y1, y32) <= rel_l2(y16, y32) + TOL_EXTRA
+
+
+@gpu
+def test_lora_fold_is_bit_identical_to_the_reference_loader_on_this_gpu():
+    """`pipe.load_lora` (qwen_image_physical.py:250-276 -> lora/__init__.py:28-44): the REFERENCE's GeneralLoRALoader folding r=128 LoRA
+    into its own QwenImageDiT on this GPU vs the native loader folding the same LoRA into the native DiT AFTER its engine fused the QKV
+    weights (the fold must land in the fused buffer through the parameter views): every weight bit-identical, then one forward agrees."""
+    from oracle import ref_import
+    if ref_import.reference_root() is None:
+        pytest.skip("no reference tree on this box")
+    import physicedit_b200 as pe
+    from physicedit_b200.lora import GeneralLoRALoader
+    L = 2
+    Wsd = O.synth_weights(O.dit_param_shapes(L), seed=23, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    targets = ["attn.to_q", "attn.to_k", "attn.to_v", "attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj", "attn.to_out.0", "attn.to_add_out",
+               "img_mlp.net.2", "txt_mlp.net.2", "img_mod.1", "txt_mod.1"]                       # scripts/train/train_multigpu.sh:30
+    lsd = {}
+    for i in range(L):
+        for t in targets:
+            name = f"transformer_blocks.{i}.{t}"
+            out_f, in_f = Wsd[name + ".weight"].shape
+            lsd[f"{name}.lora_A.default.weight"] = (torch.randn(128, in_f, generator=g) * 0.02).bfloat16()
+            lsd[f"{name}.lora_B.default.weight"] = (torch.randn(out_f, 128, generator=g) * 0.02).bfloat16()
+    with ref_import.ReferenceModules() as ref:
+        import importlib
+        ref_lora = importlib.import_module("diffsynth.lora")
+        rdit = ref_import.build_reference_dit(ref, Wsd, L, torch.bfloat16, "cuda")
+        ref_lora.GeneralLoRALoader(device="cuda", torch_dtype=torch.bfloat16).load(rdit, lsd, alpha=1.0)
+        want = {k: v.detach().clone() for k, v in rdit.state_dict().items()}
+    from physicedit_b200.dit import QwenImageDiT
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=L)
+    dit.load_state_dict({k: v.clone() for k, v in Wsd.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    dit = dit.to("cuda").eval()
+    eng = dit.engine()                                                 # pack first: to_q / to_k / to_v become views of one buffer
+    n = GeneralLoRALoader(device="cuda", torch_dtype=torch.bfloat16).load(dit, lsd, alpha=1.0)
+    assert n == len(targets) * L
+    got = dit.state_dict()
+    for k, v in want.items():
+        assert torch.equal(got[k], v), k
+    assert torch.equal(eng.qkv_w[1][0][:3072], want["transformer_blocks.1.attn.to_q.weight"])      # the fused buffer holds the folded weights
+    assert not torch.equal(want["transformer_blocks.0.attn.to_q.weight"].cpu(), Wsd["transformer_blocks.0.attn.to_q.weight"])
