@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PE_B200_ABI_VERSION 1
+#define PE_B200_ABI_VERSION 2
 
 typedef enum pe_status {
     PE_OK = 0,
@@ -94,6 +94,15 @@ typedef struct pe_gemm_seg {
     const void* norm_q_w; /* PE_EPI_QKV_NORM_ROPE: bf16 [128]                                     */
     const void* norm_k_w; /* PE_EPI_QKV_NORM_ROPE: bf16 [128]                                     */
     const void* rope;     /* PE_EPI_QKV_NORM_ROPE: float2 (cos,sin) [M, 64]                       */
+    /* PE_EPI_QKV_NORM_ROPE, head-parallel (Ulysses) mode: route_ranks > 0 splits the heads into route_ranks equal groups; group g's q / k / v
+     * go to q_route[g] / k_route[g] / v_route[g] (buffers [*, heads/route_ranks * 128], row stride ldo, already offset to this segment's first
+     * row) instead of out / out_k / out_v.  The pointers may be PEER-GPU memory mapped into this process (NVLink P2P stores straight from the
+     * epilogue: the all-to-all of a sequence-parallel attention costs no extra pass). */
+    void* q_route[8];
+    void* k_route[8];
+    void* v_route[8];
+    int32_t route_ranks;
+    int32_t _pad1;
 } pe_gemm_seg;
 
 #define PE_GEMM_FLAG_CTA_PAIR 1   /* use cta_group::2 (256-row tiles on an SM pair) */
@@ -117,6 +126,12 @@ int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int 
                                             run on the FMA pipe; a step whose logits jump > 2^100 over the reference is redone exactly */
 int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v, void* o,
                      int S, int H, int64_t ld, float scale, int flags, void* stream);
+/* Same kernel (flags 0 / 1 / 2 only), output ROUTED by query row: rows [route_end[i-1], route_end[i]) are written to
+ * o_route[i] + row * ldo + head * 128 (route_end[-1] = 0, route_end[n_route-1] >= S).  In the sequence-parallel mode rank r computes its
+ * H = heads / ranks heads for ALL rows and writes every row into the attention buffer of the rank that owns it (peer-mapped pointers:
+ * NVLink P2P stores from the epilogue), i.e. the second all-to-all of Ulysses attention is fused into this kernel. */
+int pe_attention_fwd_routed(pe_handle_t h, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags,
+                            int n_route, const int32_t* route_end, void* const* o_route, int64_t ldo, void* stream);
 
 /* small generic attention for the training-path encoders (DINOv2 ViT-B: 261 tokens x 12 heads x 64,
  * transformers modeling_dinov2_with_registers.py:174-254; perceiver resampler: 64 latent queries over

@@ -63,6 +63,10 @@ struct AttnParams {
     int* item_flags;  // kernel 4: per work item, the sequence number of the launch whose trailing reference overflowed on it
     int seq;          // this launch's sequence number
     int only_flagged; // kernel 1 as the fix-up pass of kernel 4: process only items with item_flags[item] == seq
+    // output routed by query row (pe_attention_fwd_routed, kernel 1): rows < route_end[i] (first match) go to route_o[i] + row * ldo + head * 128
+    int n_route;
+    int route_end[8];
+    bf16* route_o[8];
 };
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
@@ -571,7 +575,14 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
             tc_fence_after();
             const float inv = f_pending / l;     // includes the O rescale still pending from the last step
             const long long row = (long long)(qb * kQT + q) * kTile + row_in_tile;
-            bf16* orow = p.o + row * p.ldo + head * kTile;
+            bf16* obase = p.o;
+            if (p.n_route > 0) {                      // sequence-parallel mode: the row's owner rank gets it (possibly over NVLink)
+                obase = p.route_o[p.n_route - 1];
+#pragma unroll 1
+                for (int i = p.n_route - 2; i >= 0; --i)
+                    if (row < p.route_end[i]) obase = p.route_o[i];
+            }
+            bf16* orow = obase + row * p.ldo + head * kTile;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t r[32];
@@ -1894,6 +1905,40 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
         return launch_attention4(h, p, stream);          // half-row threads, trailing reference (no per-step exchange), exp2 split MUFU / FMA
     if (flags & PE_ATTN_FLAG_SPLIT_ROW_SOFTMAX)
         return launch_attention2(h, p, stream);          // split-row softmax: exact max every step, two warps per SMSP per tile
+    const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;
+    const bool p_smem = (flags & PE_ATTN_FLAG_P_VIA_SMEM) != 0;
+    if (one_tile) return p_smem ? launch_attention<1, false>(h, p, stream) : launch_attention<1, true>(h, p, stream);
+    return p_smem ? launch_attention<2, false>(h, p, stream) : launch_attention<2, true>(h, p, stream);
+}
+
+int attention_routed_run(Handle* h, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags, int n_route,
+                         const int32_t* route_end, void* const* o_route, int64_t ldo, cudaStream_t stream) {
+    PE_REQUIRE(h, q && k && v && route_end && o_route, "pe_attention_fwd_routed: null pointer");
+    PE_REQUIRE(h, S > 0 && H > 0 && n_route >= 1 && n_route <= 8, "pe_attention_fwd_routed: bad sizes (S=%d H=%d n_route=%d)", S, H, n_route);
+    PE_REQUIRE(h, ld >= (int64_t)H * 128 && ld % 8 == 0 && ldo % 8 == 0, "pe_attention_fwd_routed: ld must be >= H*128, ld / ldo multiples of 8");
+    PE_REQUIRE(h, (flags & ~3) == 0, "pe_attention_fwd_routed: only the default kernel (flags 0..3) supports routed output");
+    PE_REQUIRE(h, route_end[n_route - 1] >= S, "pe_attention_fwd_routed: the last route must cover row S-1");
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_tmap_2d(h, &p.tmQ, q, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &p.tmK, k, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(h, &p.tmV, v, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, 128);
+    if (rc) return rc;
+    p.n_route = n_route;
+    for (int i = 0; i < n_route; ++i) {
+        PE_REQUIRE(h, o_route[i] != nullptr && (reinterpret_cast<uintptr_t>(o_route[i]) & 15) == 0, "pe_attention_fwd_routed: route %d: null or unaligned pointer", i);
+        p.route_end[i] = route_end[i];
+        p.route_o[i] = static_cast<bf16*>(o_route[i]);
+    }
+    p.o = p.route_o[0];
+    p.ldo = ldo;
+    p.S = S;
+    p.H = H;
+    p.n_kv = ceil_div(S, kTile);
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.abort_flag = h->abort_flag;
     const bool one_tile = (flags & PE_ATTN_FLAG_SINGLE_Q_TILE) != 0;
     const bool p_smem = (flags & PE_ATTN_FLAG_P_VIA_SMEM) != 0;
     if (one_tile) return p_smem ? launch_attention<1, false>(h, p, stream) : launch_attention<1, true>(h, p, stream);

@@ -59,6 +59,8 @@ int make_tmap_3d(Handle* h, CUtensorMap* out, const void* base, uint64_t C, uint
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream);
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
                   int flags, cudaStream_t stream);
+int attention_routed_run(Handle* h, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags, int n_route,
+                         const int32_t* route_end, void* const* o_route, int64_t ldo, cudaStream_t stream);
 int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C, const void* shift, const void* ops, cudaStream_t s);
 int layernorm_modulate2_run(Handle* h, const void* x, void* out, int rows, int C, int split_row, const void* shift0, const void* ops0,
                             const void* shift1, const void* ops1, cudaStream_t s);
@@ -199,6 +201,12 @@ int pe_attention_fwd(pe_handle_t hh, const void* q, const void* k, const void* v
                      float scale, int flags, void* stream) {
     PE_H(hh);
     return pe::attention_run(h, q, k, v, o, S, H, ld, scale, flags, static_cast<cudaStream_t>(stream));
+}
+
+int pe_attention_fwd_routed(pe_handle_t hh, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags,
+                            int n_route, const int32_t* route_end, void* const* o_route, int64_t ldo, void* stream) {
+    PE_H(hh);
+    return pe::attention_routed_run(h, q, k, v, S, H, ld, scale, flags, n_route, route_end, o_route, ldo, static_cast<cudaStream_t>(stream));
 }
 
 int pe_small_attention(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Skv,

@@ -56,6 +56,10 @@ struct SegDev {
     int M;
     int m_tiles;
     int wide_store;   // out (and out_k / out_v) 32-byte aligned, ldo and N multiples of 16: a lane stores 32 bytes (a whole L2 sector) at a time
+    // head-parallel routing of the QKV epilogue (see pe_gemm_seg): heads_per_route > 0 -> head group g = head / heads_per_route is written
+    // to route[which][g] (possibly peer-GPU memory) at column (head % heads_per_route) * 128
+    int heads_per_route;
+    bf16* route[3][8];
 };
 
 // one lane's 32-byte store (two packed 8 x bf16 groups, adjacent columns of its row)
@@ -252,7 +256,13 @@ __device__ __forceinline__ void epilogue_qkv_head(uint32_t taddr_head, const Seg
         }
     }
     if (!row_valid) return;
-    bf16* dst = (which == 0 ? sg.out : (which == 1 ? sg.out_k : sg.out_v)) + row * sg.ldo + col0;
+    bf16* dst;
+    if (sg.heads_per_route > 0) {
+        const int hw = col0 >> 7, g = hw / sg.heads_per_route;
+        dst = sg.route[which][g] + row * sg.ldo + ((hw - g * sg.heads_per_route) << 7);
+    } else {
+        dst = (which == 0 ? sg.out : (which == 1 ? sg.out_k : sg.out_v)) + row * sg.ldo + col0;
+    }
     if (which == 2) {
 #pragma unroll
         for (int v = 0; v < 16; v += 2) {
@@ -638,6 +648,20 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         if (epilogue == PE_EPI_QKV_NORM_ROPE)
             PE_REQUIRE(h, in.bias && in.out_k && in.out_v && in.norm_q_w && in.norm_k_w && in.rope,
                        "pe_gemm: QKV epilogue needs bias, out_k, out_v, norm weights and rope table");
+        if (epilogue == PE_EPI_QKV_NORM_ROPE && in.route_ranks > 0) {
+            PE_REQUIRE(h, in.route_ranks <= 8 && p.heads % in.route_ranks == 0, "pe_gemm: route_ranks must divide the head count (heads=%d ranks=%d)", p.heads, in.route_ranks);
+            d.heads_per_route = p.heads / in.route_ranks;
+            uintptr_t al = 0;
+            for (int g = 0; g < in.route_ranks; ++g) {
+                PE_REQUIRE(h, in.q_route[g] && in.k_route[g] && in.v_route[g], "pe_gemm: null route pointer (group %d)", g);
+                d.route[0][g] = static_cast<bf16*>(in.q_route[g]);
+                d.route[1][g] = static_cast<bf16*>(in.k_route[g]);
+                d.route[2][g] = static_cast<bf16*>(in.v_route[g]);
+                al |= reinterpret_cast<uintptr_t>(in.q_route[g]) | reinterpret_cast<uintptr_t>(in.k_route[g]) | reinterpret_cast<uintptr_t>(in.v_route[g]);
+            }
+            PE_REQUIRE(h, (al & 15) == 0, "pe_gemm: route pointers must be 16-byte aligned");
+            d.wide_store = ((al & 31) == 0 && in.ldo % 16 == 0 && !narrow_stores()) ? 1 : 0;
+        }
     }
     p.total_m_tiles = total_m_tiles;
     {

@@ -302,6 +302,7 @@ class DiTEngine:
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._rope: Dict[tuple, torch.Tensor] = {}
         self._mods_cache: Optional[Tuple[float, torch.Tensor, torch.Tensor, torch.Tensor]] = None
+        self.sp = None          # ulysses.UlyssesContext: ONE image on the ranks of a group (sequence-parallel rows, head-parallel attention)
         self._pack()
 
     # -- weights ---------------------------------------------------------------------------------
@@ -469,6 +470,9 @@ class DiTEngine:
                 out_latents: torch.Tensor, t_key: Optional[float] = None, branch: int = 0) -> torch.Tensor:
         """latents_list: [noise latents, edit/context latents ...] each [1,16,h8,w8] bf16; prompt_emb [T,3584] bf16
         (already updated by the adapter).  Writes the velocity for the first entry into out_latents [1,16,h8,w8]."""
+        if self.sp is not None:
+            from .ulysses import forward_sp
+            return forward_sp(self, self.sp, latents_list, timestep_bf16, prompt_emb, out_latents, t_key)
         nat, dit = self.nat, self.dit
         T = prompt_emb.shape[0]
         shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]

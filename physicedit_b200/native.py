@@ -36,7 +36,7 @@ ATTN_FLAG_HALF_ROW = 32
 
 EXPORTED_SYMBOLS = [
     "pe_abi_version", "pe_create", "pe_destroy", "pe_last_error", "pe_check_async_error", "pe_sm_count", "pe_workspace",
-    "pe_gemm", "pe_attention_fwd", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
+    "pe_gemm", "pe_attention_fwd", "pe_attention_fwd_routed", "pe_small_attention", "pe_layernorm_modulate", "pe_layernorm_modulate2", "pe_layernorm", "pe_add_rows",
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
@@ -59,6 +59,7 @@ class GemmSeg(Structure):
         ("a", c_void_p), ("lda", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
         ("M", c_int32), ("_pad0", c_int32), ("gate", c_void_p), ("out_k", c_void_p), ("out_v", c_void_p),
         ("norm_q_w", c_void_p), ("norm_k_w", c_void_p), ("rope", c_void_p),
+        ("q_route", c_void_p * 8), ("k_route", c_void_p * 8), ("v_route", c_void_p * 8), ("route_ranks", c_int32), ("_pad1", c_int32),
     ]
 
 
@@ -86,6 +87,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_check_async_error.argtypes = [c_void_p, c_void_p, POINTER(c_uint)]
     lib.pe_gemm.argtypes = [c_void_p, POINTER(GemmSeg), c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.pe_attention_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p]
+    lib.pe_attention_fwd_routed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_int, POINTER(c_int32),
+                                            POINTER(c_void_p), c_int64, c_void_p]
     lib.pe_small_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int64, c_int64, c_int64, c_float, c_void_p]
     lib.pe_layernorm_modulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -225,6 +228,11 @@ class Native:
             g.out, g.ldo, g.M = out.data_ptr(), out.stride(0), a.shape[0]
             g.gate, g.out_k, g.out_v = _ptr(s.get("gate")), _ptr(s.get("out_k")), _ptr(s.get("out_v"))
             g.norm_q_w, g.norm_k_w, g.rope = _ptr(s.get("norm_q_w")), _ptr(s.get("norm_k_w")), _ptr(s.get("rope"))
+            routes = s.get("routes")                   # head-parallel QKV: (q_ptrs, k_ptrs, v_ptrs), raw device addresses (may be peer memory)
+            if routes:
+                g.route_ranks = len(routes[0])
+                for r, (qp, kp, vp) in enumerate(zip(*routes)):
+                    g.q_route[r], g.k_route[r], g.v_route[r] = qp, kp, vp
         self._check(self.lib.pe_gemm(self.h, arr, len(segs), N, K, epilogue, flags, self._stream_prof()), "pe_gemm")
         self.launches += 1
 
@@ -241,6 +249,20 @@ class Native:
                 raise NativeError("q, k, v, o must share one row stride")
         self._check(self.lib.pe_attention_fwd(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), q.shape[0], H,
                                               q.stride(0), scale, flags, self._stream_prof()), "pe_attention_fwd")
+        self.launches += 1
+
+    def attention_routed(self, q, k, v, H: int, scale: float, route_end: Sequence[int], o_ptrs: Sequence[int], ldo: int, flags: int = 0) -> None:
+        """Joint attention over q / k / v [S, >= H*128] whose output rows are written to o_ptrs[i] + row * ldo + head * 128 for rows below
+        route_end[i] (first match); the pointers may be peer-GPU memory (sequence-parallel mode)."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v")):
+            _bf16(t, n)
+            if t.stride(0) != q.stride(0):
+                raise NativeError("q, k, v must share one row stride")
+        n = len(route_end)
+        ends = (c_int32 * n)(*[int(e) for e in route_end])
+        ptrs = (c_void_p * n)(*[int(p) for p in o_ptrs])
+        self._check(self.lib.pe_attention_fwd_routed(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.shape[0], H, q.stride(0), scale, flags, n, ends, ptrs,
+                                                     ldo, self._stream_prof()), "pe_attention_fwd_routed")
         self.launches += 1
 
     def small_attention(self, q, k, v, o, B: int, H: int, Sq: int, Skv: int, D: int, scale: float) -> None:

@@ -242,6 +242,15 @@ class QwenImagePhysicPipeline(nn.Module):
     def load_models_to_device(self, model_names=()):
         return None
 
+    def enable_sequence_parallel(self, group=None):
+        """Latency mode for large images: ONE image on all ranks of `group` -- every rank denoises the same request, each DiT forward
+        is split across the ranks (ulysses.py: rows sequence-parallel, attention head-parallel, the two all-to-alls fused into the QKV GEMM's and
+        the attention kernel's epilogues as NVLink P2P stores).  Call on every rank after the weights are in place; `group=None` = WORLD."""
+        from .ulysses import UlyssesContext
+        self.dit.engine().sp = UlyssesContext(group, device=next(self.dit.parameters()).device)
+        self.cfg_streams = 1            # the per-block barriers are stream-ordered: both CFG branches run on one stream
+        return self
+
     def freeze_except(self, model_names):
         for name, model in self.named_children():
             if name in model_names:

@@ -49,7 +49,7 @@ def _build_adapter(seed, t_min, t_max):
 @gpu
 def test_library_is_loaded_and_device_is_sm100(nat):
     assert nat.sm_count >= 100
-    assert nat.lib.pe_abi_version() == 1
+    assert nat.lib.pe_abi_version() == 2
 
 
 @gpu

@@ -81,7 +81,7 @@ def test_c_abi_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in pe_b200.h but not exported"
     assert set(native.EXPORTED_SYMBOLS) <= declared
-    assert lib.pe_abi_version() == 1
+    assert lib.pe_abi_version() == 2
     if not torch.cuda.is_available():
         with pytest.raises(native.NativeUnavailable):      # the product path fails loudly without a GPU: no fallback
             native.Native.get(0)
