@@ -338,6 +338,41 @@ def run_native(args):
                                     "per_step_collective": "one in-place all-gather of the two [1,16,h8,w8] predictions within each pair"}
             pipe.cfg_parallel_group = None
             nat.check_async()
+        # second latency-mode sub-leg: ONE image on all N GPUs, every DiT forward split across the ranks (physicedit_b200/ulysses.py:
+        # rows sequence-parallel, attention head-parallel, the two all-to-alls fused into the QKV GEMM's and the attention kernel's epilogues
+        # as NVLink peer stores).  Every rank must end with bit-identical latents.
+        if 24 % world == 0 and not args.cfg_parallel and not args.no_sequence_parallel_leg:
+            host_s = host_inputs(H, W, seed=100)
+            dev_s = {k: v.to(device, non_blocking=True) for k, v in host_s.items()}
+            ips = dict(prompt_emb=dev_s["pe_posi"], prompt_emb_mask=dev_s["mask_posi"], special_token_mask=dev_s["sp_posi"], txt_len=T_POSI, n_special=64)
+            ins = dict(prompt_emb=dev_s["pe_nega"], prompt_emb_mask=dev_s["mask_nega"], special_token_mask=dev_s["sp_nega"], txt_len=T_NEGA, n_special=64)
+            lats = dev_s["latents"].clone()
+            ksteps = max(2, min(args.steps, 4))
+            streams_before = pipe.cfg_streams
+            pipe.enable_sequence_parallel()
+            for i in range(2):
+                pipe.denoise_step(lats, ips, ins, dev_s["edit_latents"], progress_id=i, height=H, width=W)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(ksteps):
+                pipe.denoise_step(lats, ips, ins, dev_s["edit_latents"], progress_id=2 + i, height=H, width=W)
+            s1.record()
+            barrier()
+            st = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            every = [torch.empty_like(lats) for _ in range(world)]
+            dist.all_gather(every, lats)
+            same = torch.tensor([float(all(torch.equal(every[0], e) for e in every[1:]))], device=device)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            coll["sequence_parallel"] = {"images_in_flight": 1, "ranks": world, "steps": ksteps, "ms_per_step": round(st.item() / ksteps, 3),
+                                         "steps_per_s_per_image": round(ksteps / (st.item() * 1e-3), 4), "speedup_vs_one_gpu_step": round((ms / args.steps) / (st.item() / ksteps), 3),
+                                         "latents_bit_identical_on_all_ranks": bool(same.item() == 1.0),
+                                         "per_block_exchange": "q/k/v head slices and attention rows stored into peer HBM by the QKV GEMM and attention epilogues "
+                                                               "(NVLink P2P, torch symmetric memory); 2 device barriers per block"}
+            pipe.disable_sequence_parallel()
+            pipe.cfg_streams = streams_before
+            nat.check_async()
 
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
@@ -755,6 +790,8 @@ def main():
     ap.add_argument("--no-text-encoder", dest="no_text_encoder", action="store_true", help="skip the Qwen2.5-VL text-encoder leg (7B config, random weights)")
     ap.add_argument("--no-stock-gpu", dest="no_stock_gpu", action="store_true", help="skip the stock-PyTorch GPU baseline leg (4 blocks, same inputs)")
     ap.add_argument("--no-cfg-parallel-leg", dest="no_cfg_parallel_leg", action="store_true", help="N>=2: skip the CFG-parallel latency sub-leg")
+    ap.add_argument("--no-sequence-parallel-leg", dest="no_sequence_parallel_leg", action="store_true",
+                    help="N>=2: skip the sequence-parallel (one image on all N GPUs) latency sub-leg")
     ap.add_argument("--no-full-forward", dest="no_full_forward", action="store_true", help="--impl reference: skip the one real 60-block CPU forward")
     ap.add_argument("--no-vae", dest="no_vae", action="store_true", help="skip the VAE encode/decode leg (reported beside, not inside, the metric)")
     args = ap.parse_args()

@@ -248,7 +248,14 @@ class QwenImagePhysicPipeline(nn.Module):
         the attention kernel's epilogues as NVLink P2P stores).  Call on every rank after the weights are in place; `group=None` = WORLD."""
         from .ulysses import UlyssesContext
         self.dit.engine().sp = UlyssesContext(group, device=next(self.dit.parameters()).device)
+        self._cfg_streams_before_sp = getattr(self, "cfg_streams", 1)
         self.cfg_streams = 1            # the per-block barriers are stream-ordered: both CFG branches run on one stream
+        return self
+
+    def disable_sequence_parallel(self):
+        """Back to one whole forward per rank (the symmetric workspaces stay allocated with the context until it is collected)."""
+        self.dit.engine().sp = None
+        self.cfg_streams = getattr(self, "_cfg_streams_before_sp", self.cfg_streams)
         return self
 
     def freeze_except(self, model_names):

@@ -2,7 +2,9 @@
 
 CFG-parallel latency mode: one image on a pair of GPUs -- the positive branch of every denoise step on rank 0, the negative
 one on rank 1, one in-place NCCL all-gather of the two predictions per step -- must give latents bit-identical to the single-GPU loop on
-both ranks; and the data-parallel plumbing (NCCL weight broadcast, final gather) must hand every rank rank 0's weights."""
+both ranks; the sequence-parallel (Ulysses) forward -- one image on N GPUs, rows split across the ranks, attention head-parallel, the two
+all-to-alls fused into the QKV GEMM's and the attention kernel's epilogues as NVLink peer stores -- must give a velocity bit-identical to the
+single-GPU forward on every rank; and the data-parallel plumbing (NCCL weight broadcast, final gather) must hand every rank rank 0's weights."""
 import os
 import subprocess
 import sys
@@ -21,3 +23,19 @@ def test_cfg_parallel_pair_is_bit_identical_to_the_single_gpu_loop():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bit-identical to the single-GPU loop on both ranks: True" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("resolution,layers", [(512, 2), (1024, 3)])
+def test_sequence_parallel_forward_is_bit_identical_to_the_single_gpu_forward(resolution, layers):
+    """tools/ulysses_check.py exits 0 only when two denoise steps (both CFG branches, adapter included) split across the ranks leave latents that
+    are torch.equal to the single-GPU ones on EVERY rank."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29549",
+           os.path.join(ROOT, "tools", "ulysses_check.py"), "--resolution", str(resolution), "--layers", str(layers), "--steps", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["bit_identical_on_all_ranks"] and res["finite"] and res["ranks"] == 2, res
