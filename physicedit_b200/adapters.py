@@ -45,6 +45,9 @@ class VisualThinkingAdapter(nn.Module):
         self.net = nn.Sequential(nn.Linear(in_dim, out_dim * 3), nn.GELU(), nn.Linear(out_dim * 3, out_dim))
 
     def forward(self, x):
+        from . import autograd as ag
+        if x.requires_grad or ag.needs_grad(self):                       # training: same GEMMs under autograd
+            return ag.mlp_gelu(x, self.net[0], self.net[2])
         nat = _nat(x)
         y = _mlp_gelu(nat, x.reshape(-1, x.shape[-1]).contiguous(), self.net[0], self.net[2])
         return y.view(*x.shape[:-1], -1)
@@ -70,6 +73,9 @@ class VisualThinkingDualAdapter(nn.Module):
         return (_mlp_gelu(nat, x2d, self.head_dino[0], self.head_dino[2]), _mlp_gelu(nat, x2d, self.head_vae[0], self.head_vae[2]))
 
     def forward(self, x, timestep):
+        from . import autograd as ag
+        if x.requires_grad or ag.needs_grad(self):
+            return ag.dual_adapter_forward(self, x, timestep)
         nat = _nat(x)
         x2d = x.reshape(-1, x.shape[-1]).contiguous()
         pd, pv = self.heads(x2d)
@@ -126,8 +132,11 @@ class PerceiverResampler(nn.Module):
         self.norm = nn.LayerNorm(dim)
 
     def forward(self, x):
-        nat = _nat(x)
+        from . import autograd as ag
         assert x.shape[0] == 1, "the reference always calls the resampler with batch 1 (frames are flattened into the sequence)"
+        if x.requires_grad or ag.needs_grad(self):
+            return ag.resampler_forward(self, x)
+        nat = _nat(x)
         n, dim = x.shape[1], x.shape[2]
         m = self.latents.shape[0]
         xm = x[0].contiguous().clone()

@@ -1,0 +1,338 @@
+"""Training path: the differentiable forward of the DiT + adapters and its backward on the native kernels.
+
+What the reference does: `pipe.training_loss` (DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py:313-329) runs `model_fn_qwen_image`
+(:1302-1403) under autograd with PEFT LoRA r = 128 injected un-merged into 12 linears of each of the 60 blocks
+(diffsynth/trainers/utils.py:799-808, scripts/train/train_multigpu.sh:30-31), the adapter stack trainable, gradient checkpointing per block
+(:1379-1389), `accelerator.backward(loss)` (scripts/train/train_physicedit.py:648-652).
+
+What runs here -- first slice of the row, stated honestly:
+  * every matrix product of the forward AND the backward is the tcgen05 GEMM (`pe_gemm`): Y = X W^T (+ b), dX = dY W (W^T materialised by
+    `pe_transpose`, cached for frozen weights), dW | db = dY^T [X | 1] (one GEMM: the bias gradient is the extra column), LoRA down / up
+    projections and their gradients (N or K = 128);
+  * attention forward is the flash kernel (`pe_attention_fwd`); its backward is COMPOSED per head from the same GEMM (scores with the fp32
+    epilogue, dP, dQ, dK, dV), `pe_softmax_rows` (P recomputed), `pe_transpose` and two row-wise kernels (`pe_attention_bwd_delta`,
+    `pe_attention_bwd_ds`) -- the S x S matrices of one head live in HBM (1.2 GB of scratch at S = 8704), so it is HBM-bound (~11 ms per block
+    at 1024^2 against 0.83 ms forward); a fused tcgen05 flash backward is the next step;
+  * the row-wise glue between them (LayerNorm + modulation, per-head RMSNorm + RoPE, x sigmoid(1.702 x), gate * branch + residual, GELU(erf),
+    the blend, the losses) is written with torch ops in the reference's own op order and differentiated by autograd: ATen CUDA kernels, not
+    CPU code and not the oracle, < 3 % of the FLOPs; native fused backward passes for them are also "next".
+Inference never comes here (model_fn routes here only when a gradient is required or un-merged LoRA is present).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+from . import native as nv
+from .lora import LoRALinear
+
+HEAD_DIM = 128
+BF16 = torch.bfloat16
+
+
+def _nat(t: torch.Tensor) -> nv.Native:
+    if not t.is_cuda or t.dtype != BF16:
+        raise nv.NativeUnavailable(f"the native training path runs in bfloat16 on an sm_100 GPU only (got {t.dtype} on {t.device}); no fallback")
+    return nv.Native.get(t.device.index or 0)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """[..., K] -> a [M, K] view / copy the GEMM can read (innermost stride 1, row stride a multiple of 8)."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.stride(0) < x2.shape[1] or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    return x2
+
+
+def _transposed(nat: nv.Native, x2: torch.Tensor, extra_rows: int = 0, ones_row: bool = False) -> torch.Tensor:
+    """x2 [M, C] -> [C + extra_rows, pad8(M)] holding x2^T, zero in the padding; row C = ones over the M valid columns if asked."""
+    M, C = x2.shape
+    out = torch.zeros(C + extra_rows, _pad8(M), dtype=BF16, device=x2.device) if (extra_rows or M % 8) else \
+        torch.empty(C, M, dtype=BF16, device=x2.device)
+    nat.transpose(x2, out[:C, :M])
+    if ones_row:
+        out[C, :M] = 1
+    return out
+
+
+class _WeightTransposes:
+    """W^T of FROZEN weights for the dX GEMMs, keyed by storage address + version (an in-place LoRA fold bumps the version)."""
+
+    def __init__(self, cap_bytes: int = 48 << 30):
+        self.cap, self.used, self.d = cap_bytes, 0, {}
+
+    def get(self, nat: nv.Native, w: torch.Tensor) -> torch.Tensor:
+        if w.requires_grad:
+            return _transposed(nat, w)
+        key = (w.data_ptr(), w._version, tuple(w.shape))
+        t = self.d.get(key)
+        if t is None:
+            t = _transposed(nat, w)
+            nbytes = t.numel() * 2
+            if self.used + nbytes <= self.cap:
+                self.d[key], self.used = t, self.used + nbytes
+        return t
+
+    def clear(self):
+        self.d.clear()
+        self.used = 0
+
+
+weight_transposes = _WeightTransposes()
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x w^T (+ b) on pe_gemm; either operand may require grad (activations x activations products use it too)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        nat = _nat(x)
+        x2 = _rows(x)
+        wc = w if w.is_contiguous() else w.contiguous()
+        y = nat.linear(x2, wc, b)
+        ctx.save_for_backward(x2, wc)
+        ctx.has_bias, ctx.in_shape = b is not None, x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        nat = _nat(x2)
+        dy2 = _rows(dy)
+        N, K = w.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = nat.linear(dy2, weight_transposes.get(nat, w), None).view(ctx.in_shape)
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            dyt = _transposed(nat, dy2)                                    # [N, Mp]
+            xt = _transposed(nat, x2, extra_rows=8 if need_b else 0, ones_row=need_b)     # [K (+8), Mp]: the ones row makes column K the bias gradient
+            g = nat.linear(dyt, xt, None)                                  # [N, K (+8)]
+            if ctx.needs_input_grad[1]:
+                dw = g[:, :K] if need_b else g
+            if need_b:
+                db = g[:, K].contiguous()
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _LinearFn.apply(x, w, b)
+
+
+def lora_linear(x: torch.Tensor, m: LoRALinear) -> torch.Tensor:
+    """peft/tuners/lora/layer.py Linear.forward at dropout 0: base(x) + lora_B(lora_A(x)) * scaling, every product a native GEMM."""
+    y = linear(x, m.base_layer.weight, m.base_layer.bias)
+    z = linear(linear(x, m.lora_A["default"].weight), m.lora_B["default"].weight)
+    return y + z * m.scaling
+
+
+def module_linear(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
+    return lora_linear(x, m) if isinstance(m, LoRALinear) else linear(x, m.weight, m.bias)
+
+
+class _AttentionFn(torch.autograd.Function):
+    """Joint non-causal attention, head dim 128, q / k / v / o token-major [S, H * 128]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H):
+        nat = _nat(q)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o = torch.empty_like(q)
+        nat.attention(q, k, v, o, H, 1.0 / math.sqrt(HEAD_DIM))
+        ctx.save_for_backward(q, k, v, o)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o = ctx.saved_tensors
+        nat, H = _nat(q), ctx.H
+        S, Sp = q.shape[0], _pad8(q.shape[0])
+        dev, scale = q.device, 1.0 / math.sqrt(HEAD_DIM)
+        do = do.contiguous()
+
+        def head_major(t):                                   # [H, Sp, 128], rows >= S zero
+            out = torch.zeros(H, Sp, HEAD_DIM, dtype=BF16, device=dev) if Sp != S else torch.empty(H, S, HEAD_DIM, dtype=BF16, device=dev)
+            out[:, :S].copy_(t.view(S, H, HEAD_DIM).transpose(0, 1))
+            return out
+        qh, kh, vh, doh, oh = (head_major(t) for t in (q, k, v, do, o))
+        f32 = dict(dtype=torch.float32, device=dev)
+        scores, dp, delta = torch.empty(Sp, Sp, **f32), torch.empty(Sp, Sp, **f32), torch.empty(Sp, **f32)
+        P, dS, Pt, dSt = (torch.empty(Sp, Sp, dtype=BF16, device=dev) for _ in range(4))
+        tr = torch.empty(3, HEAD_DIM, Sp, dtype=BF16, device=dev)          # dO^T, K^T, Q^T of the current head
+        dq, dk, dv = (torch.empty(H, Sp, HEAD_DIM, dtype=BF16, device=dev) for _ in range(3))
+        for h in range(H):
+            nat.gemm([dict(a=qh[h], w=kh[h], bias=None, out=scores)], Sp, HEAD_DIM, nv.EPI_F32)           # Q K^T
+            nat.softmax_rows(scores, P, S, scale)                                                       # P = softmax(scale * scores), columns >= S zero
+            nat.gemm([dict(a=doh[h], w=vh[h], bias=None, out=dp)], Sp, HEAD_DIM, nv.EPI_F32)             # dP = dO V^T
+            nat.attention_bwd_delta(doh[h], oh[h], delta)
+            nat.attention_bwd_ds(P, dp, delta, dS, scale)
+            nat.transpose(P, Pt); nat.transpose(dS, dSt)
+            nat.transpose(doh[h], tr[0]); nat.transpose(kh[h], tr[1]); nat.transpose(qh[h], tr[2])
+            nat.gemm([dict(a=Pt, w=tr[0], bias=None, out=dv[h])], HEAD_DIM, Sp)                          # dV = P^T dO
+            nat.gemm([dict(a=dS, w=tr[1], bias=None, out=dq[h])], HEAD_DIM, Sp)                          # dQ = dS K
+            nat.gemm([dict(a=dSt, w=tr[2], bias=None, out=dk[h])], HEAD_DIM, Sp)                         # dK = dS^T Q
+
+        def token_major(t):
+            return t[:, :S].transpose(0, 1).reshape(S, H * HEAD_DIM)
+        return token_major(dq), token_major(dk), token_major(dv), None
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, H: int) -> torch.Tensor:
+    return _AttentionFn.apply(q, k, v, H)
+
+
+# ------------------------------------------------------------------------------------------------
+# row-wise glue in the reference's op order (torch ops; autograd differentiates them)
+# ------------------------------------------------------------------------------------------------
+def _rmsnorm(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """models/utils.py:241-257."""
+    var = x.to(torch.float32).square().mean(-1, keepdim=True)
+    y = (x * torch.rsqrt(var + eps)).to(x.dtype)
+    return y * weight if weight is not None else y
+
+
+def _rope(x: torch.Tensor, cs: torch.Tensor) -> torch.Tensor:
+    """apply_rotary_emb_qwen (qwen_image_dit.py:51-57) with the complex table as (cos, sin): x [S, H, 128], cs fp32 [S, 64, 2]."""
+    xf = x.float().reshape(*x.shape[:-1], -1, 2)
+    c, s = cs[:, None, :, 0], cs[:, None, :, 1]
+    out = torch.stack((xf[..., 0] * c - xf[..., 1] * s, xf[..., 0] * s + xf[..., 1] * c), dim=-1)
+    return out.flatten(-2).type_as(x)
+
+
+def _modulate(x: torch.Tensor, mod: torch.Tensor):
+    """QwenImageTransformerBlock._modulate (:345-347) on 2-D streams: mod [1, 3 * dim] -> (x (1 + scale) + shift, gate)."""
+    shift, scale, gate = mod.chunk(3, dim=-1)
+    return x * (1 + scale) + shift, gate
+
+
+def block_forward(blk, image: torch.Tensor, text: torch.Tensor, temb: torch.Tensor, rope_img: torch.Tensor, rope_txt: torch.Tensor):
+    """QwenImageTransformerBlock.forward + QwenDoubleStreamAttention.forward (qwen_image_dit.py:247-316, 359-401) on [S, 3072] streams."""
+    D, H = image.shape[-1], blk.num_attention_heads
+    st = F.silu(temb)                                                    # the nn.SiLU in front of img_mod / txt_mod
+    img_mod_attn, img_mod_mlp = module_linear(blk.img_mod[1], st).chunk(2, dim=-1)
+    txt_mod_attn, txt_mod_mlp = module_linear(blk.txt_mod[1], st).chunk(2, dim=-1)
+    ln = lambda x: F.layer_norm(x, (D,), eps=1e-6)
+    img_m, img_gate = _modulate(ln(image), img_mod_attn)
+    txt_m, txt_gate = _modulate(ln(text), txt_mod_attn)
+    a = blk.attn
+
+    def heads(x, proj, norm, rope):
+        y = module_linear(proj, x).view(x.shape[0], H, HEAD_DIM)
+        if norm is not None:
+            y = _rope(_rmsnorm(y, norm.weight, norm.eps), rope)
+        return y.reshape(x.shape[0], D)
+    q = torch.cat([heads(txt_m, a.add_q_proj, a.norm_added_q, rope_txt), heads(img_m, a.to_q, a.norm_q, rope_img)], dim=0)
+    k = torch.cat([heads(txt_m, a.add_k_proj, a.norm_added_k, rope_txt), heads(img_m, a.to_k, a.norm_k, rope_img)], dim=0)
+    v = torch.cat([heads(txt_m, a.add_v_proj, None, None), heads(img_m, a.to_v, None, None)], dim=0)
+    o = attention(q, k, v, H)
+    T = text.shape[0]
+    image = image + img_gate * module_linear(a.to_out[0], o[T:])
+    text = text + txt_gate * module_linear(a.to_add_out, o[:T])
+    img_m2, img_gate2 = _modulate(ln(image), img_mod_mlp)
+    txt_m2, txt_gate2 = _modulate(ln(text), txt_mod_mlp)
+
+    def mlp(net, x):
+        h = module_linear(net[0].proj, x)
+        return module_linear(net[2], h * torch.sigmoid(1.702 * h))       # ApproximateGELU (:42-49); Dropout(0) is the identity
+    image = image + img_gate2 * mlp(blk.img_mlp.net, img_m2)
+    text = text + txt_gate2 * mlp(blk.txt_mlp.net, txt_m2)
+    return text, image
+
+
+def dit_forward(dit, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
+                use_gradient_checkpointing: bool = True) -> torch.Tensor:
+    """model_fn_qwen_image :1340-1403 under autograd.  latents_list = [noise latents, (context), edit...] each [1, 16, h8, w8] bf16 (no gradient
+    flows into them: the path trains LoRA and adapters only); timestep_bf16 [1] = the loop's bf16(t); prompt_emb [1, T, 3584] (may carry the
+    adapter's graph).  Returns the velocity [1, 16, h8, w8]."""
+    eng = dit.engine()
+    nat = eng.nat
+    T = prompt_emb.shape[1]
+    shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]
+    S_img = sum(h * w for _, h, w in shapes)
+    with torch.no_grad():                                                 # frozen entry stages whose inputs need no gradient
+        tok = torch.empty(S_img, 64, dtype=BF16, device=prompt_emb.device)
+        off = 0
+        for l, (_, h, w) in zip(latents_list, shapes):
+            nat.patchify(l.reshape(16, l.shape[-2], l.shape[-1]).contiguous(), tok[off:off + h * w])
+            off += h * w
+        temb = dit.time_text_embed(timestep_bf16, raw=True)               # [1, 3072]
+        rope = eng.rope(shapes, T)                                        # fp32 (cos, sin) [T + S_img, 64, 2], text rows first
+    image = module_linear(dit.img_in, tok)
+    text = module_linear(dit.txt_in, _rmsnorm(prompt_emb[0], dit.txt_norm.weight, dit.txt_norm.eps))
+    rope_txt, rope_img = rope[:T], rope[T:]
+    for blk in dit.transformer_blocks:
+        if use_gradient_checkpointing and torch.is_grad_enabled():
+            text, image = checkpoint(block_forward, blk, image, text, temb, rope_img, rope_txt, use_reentrant=False)
+        else:
+            text, image = block_forward(blk, image, text, temb, rope_img, rope_txt)
+    _, h0, w0 = shapes[0]
+    n0 = h0 * w0
+    emb = module_linear(dit.norm_out.linear, F.silu(temb))                # AdaLayerNorm(single) (models/utils.py:296-309): (scale, shift)
+    scale, shift = emb.chunk(2, dim=-1)
+    x = F.layer_norm(image[:n0], (image.shape[-1],), eps=1e-6) * (1 + scale) + shift
+    out = module_linear(dit.proj_out, x)                                  # [n0, 64] = (h w) (c p q)
+    return out.view(h0, w0, 16, 2, 2).permute(2, 0, 3, 1, 4).reshape(1, 16, 2 * h0, 2 * w0)
+
+
+# ------------------------------------------------------------------------------------------------
+# adapter stack under autograd
+# ------------------------------------------------------------------------------------------------
+def mlp_gelu(x: torch.Tensor, l0: torch.nn.Linear, l2: torch.nn.Linear) -> torch.Tensor:
+    """Linear -> nn.GELU (erf) -> Linear (helpers.py:112-121, 127-137, 8-19)."""
+    return module_linear(l2, F.gelu(module_linear(l0, x)))
+
+
+def dual_adapter_forward(ad, x: torch.Tensor, timestep: torch.Tensor):
+    """VisualThinkingDualAdapter.forward (helpers.py:150-164): (mixed, pred_dino, pred_vae)."""
+    pd = mlp_gelu(x, ad.head_dino[0], ad.head_dino[2])
+    pv = mlp_gelu(x, ad.head_vae[0], ad.head_vae[2])
+    alpha = ad._get_alpha(timestep, x.device).type_as(pd)
+    return alpha * pd + (1 - alpha) * pv, pd, pv
+
+
+def perceiver_attention(attn, x: torch.Tensor, latents: torch.Tensor) -> torch.Tensor:
+    """PerceiverAttention.forward (helpers.py:34-65) on 2-D inputs x [n, dim], latents [m, dim]; products on the native GEMM."""
+    x = F.layer_norm(x, (x.shape[-1],), attn.norm_media.weight, attn.norm_media.bias, attn.norm_media.eps)
+    latents = F.layer_norm(latents, (latents.shape[-1],), attn.norm_latents.weight, attn.norm_latents.bias, attn.norm_latents.eps)
+    h, d = attn.heads, attn.dim_head
+    q = module_linear(attn.to_q, latents)
+    k, v = module_linear(attn.to_kv, torch.cat((x, latents), dim=0)).chunk(2, dim=-1)
+    n = k.shape[0]
+    if n % 8:                                                             # GEMM output width / reduction length: multiples of 8 (zero rows, sliced off below)
+        k, v = F.pad(k, (0, 0, 0, 8 - n % 8)), F.pad(v, (0, 0, 0, 8 - n % 8))
+    outs = []
+    for i in range(h):
+        qi, ki, vi = (t[:, i * d:(i + 1) * d] for t in (q, k, v))
+        dots = linear(qi, ki.contiguous())[:, :n] * attn.scale           # einsum('i d, j d -> i j')
+        dots = dots - dots.amax(dim=-1, keepdim=True).detach()
+        p = dots.softmax(dim=-1)
+        if n % 8:
+            p = F.pad(p, (0, 8 - n % 8))
+        outs.append(linear(p, vi.t().contiguous()))                       # einsum('i j, j d -> i d')
+    return module_linear(attn.to_out, torch.cat(outs, dim=-1))
+
+
+def resampler_forward(rs, x: torch.Tensor) -> torch.Tensor:
+    """PerceiverResampler.forward (helpers.py:95-110): x [1, n, dim] -> [1, num_latents, dim]."""
+    n = x.shape[1]
+    xm = x[0] + rs.pos_emb.weight[:n]
+    lat = rs.latents
+    for attn, ff in rs.layers:
+        lat = lat + perceiver_attention(attn, xm, lat)
+        h = F.layer_norm(lat, (lat.shape[-1],), ff.net[0].weight, ff.net[0].bias, ff.net[0].eps)
+        lat = lat + mlp_gelu(h, ff.net[1], ff.net[3])
+    return F.layer_norm(lat, (lat.shape[-1],), rs.norm.weight, rs.norm.bias, rs.norm.eps).unsqueeze(0)
+
+
+def needs_grad(*modules) -> bool:
+    """True when autograd is on and some parameter of the given modules is trainable."""
+    return torch.is_grad_enabled() and any(p.requires_grad for m in modules if m is not None for p in m.parameters())

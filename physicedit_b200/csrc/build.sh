@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        --expt-relaxed-constexpr -Xptxas -v -cudart shared)
 objs=()
 pids=()
-for f in capi rowwise vae_kernels llm_kernels gemm_sm100 attention_sm100; do
+for f in capi rowwise vae_kernels llm_kernels train_kernels gemm_sm100 attention_sm100; do
   "$NVCC" "${FLAGS[@]}" "$@" -c "$here/$f.cu" -o "$out/$f.o" > "$out/$f.ptxas.log" 2>&1 &
   pids+=($!)
   objs+=("$out/$f.o")

@@ -50,3 +50,91 @@ class GeneralLoRALoader:
             model._engine.invalidate()
         print(f"{updated} tensors are updated by LoRA.")
         return updated
+
+
+# ------------------------------------------------------------------------------------------------
+# un-merged LoRA for training
+# ------------------------------------------------------------------------------------------------
+class LoRALinear(torch.nn.Module):
+    """What `peft.inject_adapter_in_model(LoraConfig(r, lora_alpha, target_modules), model)` puts in place of a targeted nn.Linear
+    (DiffSynth-Studio/diffsynth/trainers/utils.py:799-808; peft is an un-pinned dependency that is absent here, so this restates its
+    published layer: peft/tuners/lora/layer.py `Linear`): the frozen `base_layer`, `lora_A.default` (kaiming-uniform, a = sqrt(5)) and
+    `lora_B.default` (zeros), no dropout at the reference's settings, `y = base(x) + lora_B(lora_A(x)) * (lora_alpha / r)`.  Parameter
+    names are PEFT's, so `export_trainable_state_dict` writes the keys `validate.py:44-65` / `GeneralLoRALoader` read back
+    (`...to_q.lora_A.default.weight`).  The forward runs on the native GEMMs through physicedit_b200.autograd."""
+
+    def __init__(self, base_layer: torch.nn.Linear, r: int, lora_alpha: float):
+        super().__init__()
+        import math
+        self.base_layer = base_layer
+        self.r, self.lora_alpha, self.scaling = r, lora_alpha, lora_alpha / r
+        kw = dict(bias=False, device=base_layer.weight.device, dtype=base_layer.weight.dtype)
+        self.lora_A = torch.nn.ModuleDict({"default": torch.nn.Linear(base_layer.in_features, r, **kw)})
+        self.lora_B = torch.nn.ModuleDict({"default": torch.nn.Linear(r, base_layer.out_features, **kw)})
+        torch.nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        torch.nn.init.zeros_(self.lora_B["default"].weight)
+        base_layer.weight.requires_grad_(False)
+        if base_layer.bias is not None:
+            base_layer.bias.requires_grad_(False)
+
+    # the attributes the loaders / the engine read on a plain Linear
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+    @property
+    def in_features(self):
+        return self.base_layer.in_features
+
+    @property
+    def out_features(self):
+        return self.base_layer.out_features
+
+    def forward(self, x):
+        from . import autograd as ag
+        return ag.lora_linear(x, self)
+
+    @torch.no_grad()
+    def merge(self):
+        """Fold `scaling * B @ A` into the base weight (bf16 mm + bf16 add, the arithmetic of GeneralLoRALoader.load) and return the base layer."""
+        w = self.base_layer.weight
+        w.data.add_(self.scaling * torch.mm(self.lora_B["default"].weight.to(w.dtype), self.lora_A["default"].weight.to(w.dtype)))
+        return self.base_layer
+
+
+def inject_lora(model: torch.nn.Module, target_modules, r: int, lora_alpha=None):
+    """PEFT's target matching (a module is wrapped when its qualified name equals a target or ends with "." + target) over the nn.Linear
+    modules of `model`; every other parameter of `model` is frozen, as PEFT's `mark_only_adapters_as_trainable` does."""
+    lora_alpha = r if lora_alpha is None else lora_alpha
+    targets = list(target_modules)
+    hits = [(name, mod) for name, mod in model.named_modules()
+            if isinstance(mod, torch.nn.Linear) and any(name == t or name.endswith("." + t) for t in targets)]
+    if not hits:
+        raise ValueError(f"Target modules {targets} not found in the base model.")
+    for p in model.parameters():
+        p.requires_grad_(False)
+    for name, mod in hits:
+        parent_name, _, leaf = name.rpartition(".")
+        parent = model.get_submodule(parent_name) if parent_name else model
+        setattr(parent, leaf, LoRALinear(mod, r, lora_alpha))
+    model._lora_injected = True
+    if getattr(model, "_engine", None) is not None:
+        model._engine.invalidate()
+    return model
+
+
+def merge_lora(model: torch.nn.Module):
+    """Fold every LoRALinear of `model` and put the plain nn.Linear back (the inference engine then runs on the folded weights)."""
+    for name, mod in list(model.named_modules()):
+        if isinstance(mod, LoRALinear):
+            parent_name, _, leaf = name.rpartition(".")
+            parent = model.get_submodule(parent_name) if parent_name else model
+            setattr(parent, leaf, mod.merge())
+    model._lora_injected = False
+    if getattr(model, "_engine", None) is not None:
+        model._engine.invalidate()
+    return model

@@ -87,6 +87,11 @@ def model_fn_qwen_image(
     pe2d = prompt_emb[0]
     if not pe2d.is_contiguous():
         raise ValueError("prompt_emb must be contiguous: it is updated in place")
+    from . import autograd as ag
+    if getattr(dit, "_lora_injected", False) or prompt_emb.requires_grad or ag.needs_grad(dit, visual_thinking_adapter):
+        # training: un-merged LoRA and / or trainable adapters -> the differentiable path on the same GEMM / attention kernels
+        return _model_fn_autograd(dit, visual_thinking_adapter, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents,
+                                  use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae)
 
     special_token_loss = 0
     if special_token_mask is not None:
@@ -112,4 +117,25 @@ def model_fn_qwen_image(
     if out is None:
         out = torch.empty_like(latents)
     eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host, branch=cfg_branch)
+    return out, special_token_loss
+
+
+def _model_fn_autograd(dit, ad, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents, use_gradient_checkpointing,
+                       is_train, pseudo_special_emb_dino, pseudo_special_emb_vae):
+    """:1331-1403 under autograd (physicedit_b200/autograd.py): same in-place write of the adapter output into `prompt_emb` (:1336), same
+    `(latents, special_token_loss)` return; gradients reach the LoRA factors, the adapter heads and whatever produced the pseudo targets."""
+    from . import autograd as ag
+    special_token_loss = 0
+    if special_token_mask is not None and bool(special_token_mask.any()):
+        special = prompt_emb[special_token_mask].view(prompt_emb.shape[0], -1, prompt_emb.shape[-1])
+        mixed, pred_dino, pred_vae = ag.dual_adapter_forward(ad, special, timestep)
+        prompt_emb[special_token_mask] = mixed.reshape(-1, prompt_emb.shape[-1])
+        if is_train:
+            special_token_loss = ad.get_loss(pred_dino, pred_vae, pseudo_special_emb_dino, pseudo_special_emb_vae, timestep)
+    lat_list = [latents]
+    if context_latents is not None:
+        lat_list.append(context_latents)
+    if edit_latents is not None:
+        lat_list += list(edit_latents) if isinstance(edit_latents, list) else [edit_latents]
+    out = ag.dit_forward(dit, [l.contiguous() for l in lat_list], t_bf16, prompt_emb, use_gradient_checkpointing=use_gradient_checkpointing)
     return out, special_token_loss

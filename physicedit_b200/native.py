@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows",
+    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_attention_bwd_ds",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -112,6 +112,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_attention_bwd_delta.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
+    lib.pe_attention_bwd_ds.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]
     lib.pe_gemv_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
     lib.pe_swiglu.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_rope_half.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
@@ -430,6 +432,25 @@ class Native:
             raise NativeError("softmax_rows: scores must be CUDA float32 [rows, >=n] with as many rows as probs")
         self._check(self.lib.pe_softmax_rows(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
                                              n, probs.shape[1], scale, self._stream_prof()), "pe_softmax_rows")
+        self.launches += 1
+
+    # ---- training path: attention backward helpers ------------------------------------------------------------------------------
+    def attention_bwd_delta(self, d_o, o, delta) -> None:
+        """delta[r] = sum_d dO[r, d] * O[r, d]; dO, O bf16 [rows, D] (row strides free), delta fp32 [rows]."""
+        _bf16(d_o, "dO"); _bf16(o, "O")
+        if delta.dtype != torch.float32 or not delta.is_cuda or not delta.is_contiguous() or delta.numel() != o.shape[0]:
+            raise NativeError("attention_bwd_delta: delta must be a contiguous CUDA float32 [rows]")
+        self._check(self.lib.pe_attention_bwd_delta(self.h, d_o.data_ptr(), d_o.stride(0), o.data_ptr(), o.stride(0), o.shape[0], o.shape[1],
+                                                    delta.data_ptr(), self._stream_prof()), "pe_attention_bwd_delta")
+        self.launches += 1
+
+    def attention_bwd_ds(self, p, dp, delta, ds, scale: float) -> None:
+        """dS = bf16(P * (dP - delta[:, None]) * scale); P, dS bf16 [rows, cols], dP fp32 [rows, cols]."""
+        _bf16(p, "P"); _bf16(ds, "dS")
+        if dp.dtype != torch.float32 or not dp.is_cuda or dp.stride(-1) != 1 or dp.shape != p.shape or ds.shape != p.shape:
+            raise NativeError("attention_bwd_ds: dP must be CUDA float32 of P's shape, dS bf16 of P's shape")
+        self._check(self.lib.pe_attention_bwd_ds(self.h, p.data_ptr(), p.stride(0), dp.data_ptr(), dp.stride(0), delta.data_ptr(), ds.data_ptr(),
+                                                 ds.stride(0), p.shape[0], p.shape[1], scale, self._stream_prof()), "pe_attention_bwd_ds")
         self.launches += 1
 
     # ---- Qwen2.5-VL text-encoder path (include/pe_b200.h, last section) --------------------------------------------------------

@@ -504,6 +504,10 @@ class QwenImagePhysicPipeline(nn.Module):
         dino_* [F,3,224,224] normalised pixels, vae_* [F,16,h8,w8] latents.  Returns the regression targets
         pseudo_special_emb_dino / pseudo_special_emb_vae [1,64,3584]."""
         nat = nv.Native.get(dino_middle.device.index or 0)
+        from . import autograd as ag
+        if ag.needs_grad(self.dino_time_embed, self.dino_resampler, self.dino_resampler_adapter, self.vae_time_embed, self.vae_resampler,
+                         self.vae_resampler_adapter):
+            return self._physical_visual_embeddings_autograd(dino_middle, dino_source, vae_middle_latents, vae_source_latents)
 
         def dino_branch(px, with_time):
             hs = self.dinov2(px)                                         # [F,256,768]
@@ -532,6 +536,32 @@ class QwenImagePhysicPipeline(nn.Module):
 
         return {"pseudo_special_emb_dino": delta(dino_branch(dino_middle, True), dino_branch(dino_source, False)),
                 "pseudo_special_emb_vae": delta(vae_branch(vae_middle_latents, True), vae_branch(vae_source_latents, False))}
+
+    def _physical_visual_embeddings_autograd(self, dino_middle, dino_source, vae_middle_latents, vae_source_latents):
+        """The same unit (:1057-1118) when the resampler stack is trainable (scripts/train/train_multigpu.sh:38): DINOv2 and the VAE stay frozen
+        (no gradient into pixels), everything after them runs under autograd on the native GEMMs (physicedit_b200/autograd.py)."""
+        nat = nv.Native.get(dino_middle.device.index or 0)
+
+        def dino_tokens(px, with_time):
+            with torch.no_grad():
+                hs = self.dinov2(px)                                      # [F, 256, 768]
+            if with_time:
+                hs = hs + self.dino_time_embed.weight[:hs.shape[0]].unsqueeze(1)
+            return hs.reshape(1, -1, hs.shape[-1])
+
+        def vae_tokens(lat, with_time):
+            Fn, L = lat.shape[0], (lat.shape[2] // 2) * (lat.shape[3] // 2)
+            tok = torch.empty(Fn, L, 64, dtype=torch.bfloat16, device=lat.device)
+            with torch.no_grad():
+                for f in range(Fn):
+                    nat.patchify(lat[f].contiguous(), tok[f])
+            if with_time:
+                tok = tok + self.vae_time_embed.weight[:Fn].unsqueeze(1)
+            return tok.reshape(1, Fn * L, 64)
+        dino = lambda px, wt: self.dino_resampler_adapter(self.dino_resampler(dino_tokens(px, wt)))
+        vae = lambda lat, wt: self.vae_resampler_adapter(self.vae_resampler(vae_tokens(lat, wt)))
+        return {"pseudo_special_emb_dino": dino(dino_middle, True) - dino(dino_source, False),
+                "pseudo_special_emb_vae": vae(vae_middle_latents, True) - vae(vae_source_latents, False)}
 
     def training_loss(self, global_step=None, timestep_id=None, noise=None, **inputs):
         """:313-329, forward value.  Called as the train script does (`pipe.training_loss(global_step=, **models, **inputs)`,

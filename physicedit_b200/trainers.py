@@ -34,14 +34,12 @@ class DiffusionTrainingModule(torch.nn.Module):
         return {n for n, p in self.named_parameters() if p.requires_grad}
 
     def add_lora_to_model(self, model, target_modules, lora_rank, lora_alpha=None, upcast_dtype=None):
-        """PEFT injection of un-merged LoRA (:799-808).  The DiT keeps real nn.Linear modules under the reference's names, so PEFT can
-        wrap them -- but the native forward reads the folded weights only (no per-step LoRA compute), hence training
-        through it needs row 8f3."""
-        try:
-            from peft import LoraConfig, inject_adapter_in_model
-        except ImportError as e:
-            raise ImportError("add_lora_to_model needs `peft` (not installed here); inference folds LoRA with pipe.load_lora instead") from e
-        model = inject_adapter_in_model(LoraConfig(r=lora_rank, lora_alpha=lora_alpha or lora_rank, target_modules=target_modules), model)
+        """Injection of un-merged LoRA (:799-808: `inject_adapter_in_model(LoraConfig(r, lora_alpha, target_modules), model)`).  peft is not a
+        dependency here: physicedit_b200.lora.inject_lora restates its Linear layer (same parameter names `lora_A.default.weight` /
+        `lora_B.default.weight`, same init, same target matching, base weights frozen) and the forward / backward of the wrapped linears run
+        on the native GEMMs (physicedit_b200.autograd)."""
+        from .lora import inject_lora
+        model = inject_lora(model, target_modules, lora_rank, lora_alpha)
         if upcast_dtype is not None:
             for p in model.parameters():
                 if p.requires_grad:

@@ -7,7 +7,7 @@ name="$1"; shift
 out="$root/physicedit_b200/lib/variants"; mkdir -p "$out/obj_$name"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -cudart shared)
 pids=()
-for f in capi rowwise vae_kernels llm_kernels gemm_sm100 attention_sm100; do
+for f in capi rowwise vae_kernels llm_kernels train_kernels gemm_sm100 attention_sm100; do
   /usr/local/cuda/bin/nvcc "${FLAGS[@]}" "$@" -c "$root/physicedit_b200/csrc/$f.cu" -o "$out/obj_$name/$f.o" 2>/dev/null &
   pids+=($!)
 done
