@@ -569,6 +569,7 @@ class QwenImagePhysicPipeline(nn.Module):
         `timestep_id` / `noise` pin the two random draws (:314, :317) for parity tests; by default they are drawn as in the reference."""
         if timestep_id is None:
             timestep_id = torch.randint(0, self.scheduler.num_train_timesteps, (1,))
+        timestep_id = torch.as_tensor(timestep_id).reshape(-1).cpu()          # the scheduler's tables live on the host (flow_match.py:34-69)
         timestep = self.scheduler.timesteps[timestep_id].to(dtype=self.torch_dtype, device=self.device)
         if noise is None:
             noise = torch.randn_like(inputs["input_latents"])

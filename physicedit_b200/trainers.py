@@ -2,10 +2,10 @@
 framework under `compat.install()`.
 
 In scope here is only what touches the hot path's checkpoint / module contract: `DiffusionTrainingModule` (which parameters are
-trainable, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into LoRA and
-`pipe.*` keys), `ModelLogger` (who writes that file) and the argument parser's flag set.  Dataset readers and the accelerate
-training loop are the reference's training control plane (OUT OF SCOPE; backward through the native kernels is
-row 8f3): their names exist and fail loudly when used.
+trainable, LoRA injection, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into
+LoRA and `pipe.*` keys), `ModelLogger` (who writes that file), the argument parser's flag set and `launch_training_task` (the optimizer loop,
+on plain torch.distributed DDP instead of accelerate; forward and backward on the native kernels).  Dataset readers are the
+reference's training control plane (OUT OF SCOPE): their names exist and fail loudly when used.
 Reference: DiffSynth-Studio/diffsynth/trainers/utils.py:777-1115.
 """
 from __future__ import annotations
@@ -15,6 +15,7 @@ import json
 import os
 
 import torch
+import torch.distributed as dist
 
 from .pipeline import ModelConfig
 
@@ -143,14 +144,80 @@ def qwen_image_parser():
 
 def _control_plane(name):
     def stub(*args, **kwargs):
-        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (dataset readers, accelerate loop): outside the "
-                                  "hot path this framework replaces (SURVEY.md section 2 / 8f3).  Use the reference's trainers with "
-                                  "pipe.model_fn = physicedit_b200.model_fn_qwen_image for forward-only evaluation.")
+        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (dataset readers): outside the "
+                                  "hot path this framework replaces (SURVEY.md section 2 / 8f3).  Feed launch_training_task any "
+                                  "torch Dataset that yields the sample dictionaries the training module's forward expects.")
     stub.__name__ = name
     return stub
 
 
-launch_training_task = _control_plane("utils.launch_training_task")
+class _Ranks:
+    """The four things the reference asks of `accelerate.Accelerator` in its loop and its ModelLogger (:891-977), on plain torch.distributed."""
+
+    def __init__(self):
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.rank = dist.get_rank() if self.distributed else 0
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.is_main_process = self.rank == 0
+
+    def wait_for_everyone(self):
+        if self.distributed:
+            dist.barrier()
+
+    def unwrap_model(self, model):
+        return model.module if isinstance(model, torch.nn.parallel.DistributedDataParallel) else model
+
+    def get_state_dict(self, model):
+        return self.unwrap_model(model).state_dict()
+
+    def save(self, state_dict, path, safe_serialization=True):
+        from safetensors.torch import save_file
+        save_file({k: v.detach().contiguous().cpu() for k, v in state_dict.items()}, path)
+
+
+def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e-5, weight_decay: float = 1e-2, num_workers: int = 8, save_steps: int = None,
+                         num_epochs: int = 1, gradient_accumulation_steps: int = 1, find_unused_parameters: bool = False, args=None):
+    """trainers/utils.py:932-977 without accelerate: AdamW over `model.trainable_modules()`, constant LR, one sample per step per rank, DDP
+    (NCCL gradient all-reduce, `find_unused_parameters` as the reference passes it: the last block's text tail has no gradient) when a process
+    group with more than one rank is up, gradient accumulation through `no_sync`, ModelLogger hooks at the same points.  The backward runs on
+    the native kernels (physicedit_b200/autograd.py)."""
+    import contextlib
+    if args is not None:
+        learning_rate, weight_decay, num_workers = args.learning_rate, args.weight_decay, args.dataset_num_workers
+        save_steps, num_epochs = args.save_steps, args.num_epochs
+        gradient_accumulation_steps, find_unused_parameters = args.gradient_accumulation_steps, args.find_unused_parameters
+    ranks = _Ranks()
+    optimizer = torch.optim.AdamW(model.trainable_modules(), lr=learning_rate, weight_decay=weight_decay)
+    scheduler = torch.optim.lr_scheduler.ConstantLR(optimizer)
+    sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=ranks.world, rank=ranks.rank, shuffle=True) if ranks.distributed else None
+    loader = torch.utils.data.DataLoader(dataset, shuffle=sampler is None, sampler=sampler, collate_fn=lambda x: x[0], num_workers=num_workers)
+    wrapped = model
+    if ranks.distributed:
+        dev = next(p for p in model.parameters() if p.is_cuda).device
+        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=find_unused_parameters)
+    micro = 0
+    for epoch_id in range(num_epochs):
+        if sampler is not None:
+            sampler.set_epoch(epoch_id)
+        for data in loader:
+            if micro % gradient_accumulation_steps == 0:
+                optimizer.zero_grad()                         # at the start of an accumulation window, like the reference's loop (:966)
+            micro += 1
+            boundary = micro % gradient_accumulation_steps == 0
+            sync = contextlib.nullcontext() if (boundary or not ranks.distributed) else wrapped.no_sync()
+            with sync:
+                loss = wrapped({}, inputs=data) if getattr(dataset, "load_from_cache", False) else wrapped(data)
+                (loss / gradient_accumulation_steps).backward()
+            if boundary:
+                optimizer.step()
+                scheduler.step()
+            model_logger.on_step_end(ranks, wrapped, save_steps)
+        if save_steps is None:
+            model_logger.on_epoch_end(ranks, wrapped, epoch_id)
+    model_logger.on_training_end(ranks, wrapped, save_steps)
+    return wrapped
+
+
 launch_data_process_task = _control_plane("utils.launch_data_process_task")
 
 

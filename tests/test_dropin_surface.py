@@ -207,3 +207,42 @@ def test_unit_runner_contracts():
             inputs_shared["seen"] = True
             return inputs_shared, inputs_posi, inputs_nega
     assert run(Take(), None, {}, {}, {})[0]["seen"]
+
+
+def test_lora_injection_layout_matches_what_the_loaders_read_back():
+    """add_lora_to_model (trainers/utils.py:799-808) without peft: 12 target linears per block wrapped, PEFT's parameter names, base frozen;
+    the exported trainable-only state dict is exactly what GeneralLoRALoader / validate.py:44-65 fold back, bit-identically to merge()."""
+    import copy
+    from physicedit_b200.lora import GeneralLoRALoader, LoRALinear, merge_lora
+    from physicedit_b200.trainers import DiffusionTrainingModule
+    targets = "to_q,to_k,to_v,add_q_proj,add_k_proj,add_v_proj,to_out.0,to_add_out,img_mlp.net.2,img_mod.1,txt_mlp.net.2,txt_mod.1".split(",")
+
+    class M(DiffusionTrainingModule):
+        def __init__(self):
+            super().__init__()
+            self.pipe = _cpu_pipe(layers=1)
+    m = M()
+    plain = copy.deepcopy(m.pipe.dit)
+    m.pipe.freeze_except([])
+    m.pipe.dit = m.add_lora_to_model(m.pipe.dit, target_modules=targets, lora_rank=8, upcast_dtype=torch.bfloat16)
+    wrapped = [n for n, mod in m.pipe.dit.named_modules() if isinstance(mod, LoRALinear)]
+    assert len(wrapped) == 12 and "transformer_blocks.0.attn.to_out.0" in wrapped and "transformer_blocks.0.img_mlp.net.0.proj" not in wrapped
+    names = m.trainable_param_names()
+    assert len(names) == 24 and all(".lora_A.default.weight" in n or ".lora_B.default.weight" in n for n in names)
+    assert all(not p.requires_grad for n, p in m.pipe.dit.named_parameters() if "lora_" not in n)
+    a = m.pipe.dit.transformer_blocks[0].attn.to_q
+    assert a.lora_A["default"].weight.shape == (8, 3072) and a.lora_B["default"].weight.shape == (3072, 8) and a.scaling == 1.0
+    assert torch.count_nonzero(a.lora_B["default"].weight) == 0 and a.weight is a.base_layer.weight          # PEFT init; Linear-like surface
+    torch.manual_seed(0)
+    for n, p in m.pipe.dit.named_parameters():
+        if ".lora_B." in n:
+            p.data.copy_(torch.randn_like(p) * 0.05)
+    sd = m.export_trainable_state_dict(m.state_dict(), remove_prefix="pipe.dit.")
+    assert set(sd) == {n[len("pipe.dit."):] for n in names} and "transformer_blocks.0.attn.to_q.lora_A.default.weight" in sd
+    GeneralLoRALoader(torch_dtype=torch.bfloat16).load(plain, sd, alpha=1.0)                                 # the inference-side fold of that checkpoint
+    merge_lora(m.pipe.dit)
+    assert not any(isinstance(mod, LoRALinear) for mod in m.pipe.dit.modules())
+    merged, folded = m.pipe.dit.state_dict(), plain.state_dict()
+    assert set(merged) == set(folded) and all(torch.equal(merged[k], folded[k]) for k in merged)
+    with pytest.raises(ValueError, match="not found"):
+        m.add_lora_to_model(m.pipe.dit, target_modules=["no_such_linear"], lora_rank=8)

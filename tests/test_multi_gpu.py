@@ -39,3 +39,17 @@ def test_sequence_parallel_forward_is_bit_identical_to_the_single_gpu_forward(re
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["bit_identical_on_all_ranks"] and res["finite"] and res["ranks"] == 2, res
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_training_step_under_ddp_matches_gradient_accumulation():
+    """launch_training_task on 2 ranks (DDP, NCCL gradient all-reduce over the native backward) leaves identical parameters on both
+    ranks, moved like one process accumulating the same two samples (tools/train_ddp_check.py)."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29553",
+           os.path.join(ROOT, "tools", "train_ddp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ranks_identical"] and res["grad_rel_l2_ddp_vs_accumulation"] < 2e-2, res

@@ -258,3 +258,63 @@ def test_resampler_stack_gradients():
     e_n, e_f = rel_l2(cat(got), cat(t32)), rel_l2(cat(t16), cat(t32))
     print(f"\nresampler stack grads: native {e_n:.3e} floor {e_f:.3e}")
     assert e_n <= FLOOR_GAIN * e_f + GRAD_EXTRA
+
+
+class _Samples(torch.utils.data.Dataset):
+    """Pre-computed unit outputs of n requests (what pipe.unit_runner hands training_loss after the frozen encoders ran)."""
+    load_from_cache = False
+
+    def __init__(self, n, H, T):
+        self.items = []
+        for i in range(n):
+            inp = O.synth_inputs(H, H, T, seed=300 + i, dtype=torch.bfloat16)
+            g = torch.Generator().manual_seed(900 + i)
+            self.items.append(dict(input_latents=inp["latents"], prompt_emb=inp["prompt_emb"], prompt_emb_mask=inp["prompt_emb_mask"],
+                                   special_token_mask=inp["special_token_mask"], edit_latents=inp["edit_latents"], height=H, width=H,
+                                   pseudo_special_emb_dino=torch.randn(1, 64, 3584, generator=g).bfloat16(),
+                                   pseudo_special_emb_vae=torch.randn(1, 64, 3584, generator=g).bfloat16(),
+                                   noise=torch.randn(1, 16, H // 8, H // 8, generator=g).bfloat16(), timestep_id=torch.tensor([200 + 150 * i])))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+
+def _training_module(pipe):
+    from physicedit_b200.trainers import DiffusionTrainingModule
+
+    class Module(DiffusionTrainingModule):
+        """The shape of scripts/train/train_physicedit.py's QwenImageTrainingModule.forward (:297-311): units' outputs -> pipe.training_loss."""
+
+        def __init__(self):
+            super().__init__()
+            self.pipe = pipe
+            self.losses = []
+
+        def forward(self, data, inputs=None):
+            d = self.transfer_data_to_device(dict(data), "cuda")
+            d["prompt_emb"] = d["prompt_emb"].clone()
+            loss = self.pipe.training_loss(**d, is_train=True, use_gradient_checkpointing=True)
+            self.losses.append(float(loss.detach()))
+            return loss
+    return Module()
+
+
+@gpu
+def test_launch_training_task_trains_and_writes_the_reference_checkpoint_layout(tmp_path):
+    """The optimizer loop (trainers/utils.py:932-977) on the native backward: AdamW over LoRA + adapter, 3 epochs over 2 fixed samples; the loss on
+    those samples goes down and the checkpoint holds exactly the trainable keys in the layout validate.py:44-65 splits."""
+    from physicedit_b200.trainers import ModelLogger, launch_training_task
+    from safetensors.torch import load_file
+    pipe, sd, ad, lora = _native_training_pipe(2, seed=7, rank=16)
+    model = _training_module(pipe)
+    logger = ModelLogger(str(tmp_path), remove_prefix_in_ckpt="pipe.dit.")
+    launch_training_task(_Samples(2, 64, 80), model, logger, learning_rate=2e-4, weight_decay=0.0, num_workers=0, num_epochs=3)
+    first, last = sum(model.losses[:2]), sum(model.losses[-2:])
+    print(f"\ntraining: loss over the 2 samples {first:.4f} -> {last:.4f} after 3 epochs of AdamW steps")
+    assert last < first
+    ck = load_file(str(tmp_path / "epoch-2.safetensors"))
+    assert any(k.startswith("transformer_blocks.0.attn.to_q.lora_A.default") for k in ck) and any(k.startswith("pipe.visual_thinking_adapter.head_dino.0") for k in ck)
+    assert len(ck) == 2 * 12 * 2 + 8 and not any("base_layer" in k for k in ck)
