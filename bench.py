@@ -460,6 +460,13 @@ def run_native(args):
         res["stock_gpu"] = stock_gpu_leg(device, H, W)
         res["vs_stock_gpu"] = res["stock_gpu"].get("speedup")
         res["parity"] = res["stock_gpu"].get("parity")
+    if world == 1 and not args.no_training_leg:
+        torch.cuda.empty_cache()
+        try:
+            res["training"] = training_leg(device, layers=args.train_layers)
+        except Exception as e:  # noqa: BLE001  (a reported leg beside the metric: never takes the headline line down)
+            res["training"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(res), flush=True)
@@ -598,6 +605,131 @@ def stock_gpu_leg(device, H, W, layers=4, iters=10, warmup=3):
             "note": "burst clocks (a 4-block forward is ~15 ms); the 60-block loop above runs at the power-capped clock",
             "parity": {"native_vs_stock_bf16_rel_l2": rel, "blocks": layers, "what": "rel-L2 of the model_fn output (latents) between the native and the stock bf16 forward, same weights and inputs; "
                        "the full-depth figure against the fp32 oracle is in profiles/r02_parity_depth.json (tests/test_parity_depth_gpu.py)"}}
+
+
+TRAIN_TARGETS = "to_q,to_k,to_v,add_q_proj,add_k_proj,add_v_proj,to_out.0,to_add_out,img_mlp.net.2,img_mod.1,txt_mlp.net.2,txt_mod.1".split(",")
+
+
+def training_leg(device, layers=8, H=480, W=832, T=512, rank=128, iters=3, warmup=2):
+    """One training step (scripts/train/train_multigpu.sh: 480 x 832, LoRA r = 128 un-merged on 12 linears per block, the dual adapter
+    trainable, gradient checkpointing per block): `pipe.training_loss(...).backward()` on the native path against the REFERENCE's own
+    model_fn + QwenImageDiT under torch autograd with the same LoRA layer (stock PyTorch: cuBLASLt + SDPA forward / backward) on the same GPU,
+    same weights, same inputs, `layers` blocks, CUDA events.  Reported beside the headline metric; the native attention backward is a
+    composition of GEMM / softmax / transpose passes (HBM-bound), not yet a fused kernel -- this leg is where that shows."""
+    import torch.nn.functional as F
+    from oracle import ref_import
+    from physicedit_b200 import native as nv
+    from physicedit_b200.lora import inject_lora
+    nat = nv.Native.get(device.index or 0)
+    pipe = build_model(device, layers, seed=0)
+    sd = {k: v.detach().clone() for k, v in pipe.dit.state_dict().items()}
+    ad = {k: v.detach().clone() for k, v in pipe.visual_thinking_adapter.state_dict().items()}
+    pipe.scheduler.set_timesteps(1000, training=True)
+    pipe.freeze_except(["visual_thinking_adapter"])
+    inject_lora(pipe.dit, TRAIN_TARGETS, rank)
+    g = torch.Generator(device=device).manual_seed(1)
+    lora = {}
+    for name, p in pipe.dit.named_parameters():
+        if "lora_" in name:
+            p.data.copy_((torch.randn(p.shape, device=device, generator=g) * (0.5 / math.sqrt(p.shape[1]))).to(torch.bfloat16))
+            lora[name] = p.detach().clone()
+    inp = {k: v.to(device) for k, v in synth_inputs(H, W, T, seed=100, edit_hw=(H, W)).items()}
+    gen = torch.Generator("cpu").manual_seed(5)
+    gt = [torch.randn(1, 64, 3584, generator=gen).to(torch.bfloat16).to(device) for _ in range(2)]
+    noise = torch.randn(1, 16, H // 8, W // 8, generator=gen).to(torch.bfloat16).to(device)
+    tid = torch.tensor([400])
+    params = [p for p in list(pipe.dit.parameters()) + list(pipe.visual_thinking_adapter.parameters()) if p.requires_grad]
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / iters, out
+
+    def native_step():
+        for p in params:
+            p.grad = None
+        loss = pipe.training_loss(input_latents=inp["latents"], prompt_emb=inp["prompt_emb"].clone(), prompt_emb_mask=inp["prompt_emb_mask"],
+                                  special_token_mask=inp["special_token_mask"], height=H, width=W, edit_latents=inp["edit_latents"],
+                                  pseudo_special_emb_dino=gt[0], pseudo_special_emb_vae=gt[1], is_train=True, use_gradient_checkpointing=True,
+                                  timestep_id=tid, noise=noise)
+        loss.backward()
+        return loss.detach()
+    l0 = nat.launches
+    ms_nat, loss_nat = timed(native_step)
+    launches = (nat.launches - l0) // (warmup + iters)
+    nat.check_async()
+    # forward-only and backward-only split of the native step
+    ms_fwd, _ = timed(lambda: pipe.training_loss(input_latents=inp["latents"], prompt_emb=inp["prompt_emb"].clone(), prompt_emb_mask=inp["prompt_emb_mask"],
+                                                  special_token_mask=inp["special_token_mask"], height=H, width=W, edit_latents=inp["edit_latents"],
+                                                  pseudo_special_emb_dino=gt[0], pseudo_special_emb_vae=gt[1], is_train=True, use_gradient_checkpointing=True,
+                                                  timestep_id=tid, noise=noise).detach())
+    g_nat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).float().flatten() for n, p in pipe.dit.named_parameters() if "lora_" in n])
+    out = {"config": {"blocks": layers, "height": H, "width": W, "S": 2 * (H // 16) * (W // 16) + T, "lora_rank": rank, "lora_targets_per_block": len(TRAIN_TARGETS),
+                      "gradient_checkpointing": True, "trainable": "LoRA factors + dual adapter"},
+           "native": {"ms_per_step": round(ms_nat, 2), "ms_forward": round(ms_fwd, 2), "ms_recompute_plus_backward": round(ms_nat - ms_fwd, 2),
+                      "ms_per_block": round(ms_nat / layers, 3), "own_kernel_launches_per_step": launches, "loss": round(float(loss_nat), 5)},
+           "iters": iters, "warmup": warmup}
+    del pipe, params
+    torch.cuda.empty_cache()
+    if ref_import.reference_root() is None:
+        out["stock_gpu"] = {"unavailable": "no reference tree on this box (baseline/_ref)"}
+        return out
+    try:
+        with ref_import.ReferenceModules() as ref:
+            rdit = ref_import.build_reference_dit(ref, sd, layers, torch.bfloat16, device)
+            rad = ref.helpers.VisualThinkingDualAdapter(3584, 3584, 19.999980926513672, 1000.0)
+            rad.load_state_dict(ad)
+            rad = rad.to(device=device, dtype=torch.bfloat16).train()
+
+            class StockLoRA(torch.nn.Module):                     # peft.tuners.lora.Linear at dropout 0 (peft itself is not installed here)
+                def __init__(self, base, a, b):
+                    super().__init__()
+                    self.base_layer, self.a, self.b = base, torch.nn.Parameter(a.clone()), torch.nn.Parameter(b.clone())
+
+                def forward(self, x):
+                    return self.base_layer(x) + F.linear(F.linear(x, self.a), self.b)
+            for p in rdit.parameters():
+                p.requires_grad_(False)
+            for name in sorted({n.split(".lora_A.")[0] for n in lora if ".lora_A." in n}):
+                parent_name, _, leaf = name.rpartition(".")
+                parent = rdit.get_submodule(parent_name)
+                setattr(parent, leaf, StockLoRA(getattr(parent, leaf), lora[name + ".lora_A.default.weight"], lora[name + ".lora_B.default.weight"]))
+            sparams = [p for p in list(rdit.parameters()) + list(rad.parameters()) if p.requires_grad]
+            from physicedit_b200.scheduler import FlowMatchScheduler
+            sch = FlowMatchScheduler()
+            sch.set_timesteps(1000, training=True)
+            t = sch.timesteps[tid].to(torch.bfloat16).to(device)
+            noisy, target, weight = sch.add_noise(inp["latents"], noise, t), sch.training_target(inp["latents"], noise, t), float(sch.training_weight(t))
+            ref_fn = ref.phys.model_fn_qwen_image
+
+            def stock_step():
+                for p in sparams:
+                    p.grad = None
+                pred, sl = ref_fn(dit=rdit, blockwise_controlnet=None, visual_thinking_adapter=rad, latents=noisy, timestep=t, prompt_emb=inp["prompt_emb"].clone(),
+                                  prompt_emb_mask=inp["prompt_emb_mask"], special_token_mask=inp["special_token_mask"], height=H, width=W,
+                                  edit_latents=inp["edit_latents"], is_train=True, use_gradient_checkpointing=True, pseudo_special_emb_dino=gt[0],
+                                  pseudo_special_emb_vae=gt[1])
+                loss = F.mse_loss(pred.float(), target.float()) * weight + sl
+                loss.backward()
+                return loss.detach()
+            ms_stock, loss_stock = timed(stock_step)
+            g_stock = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).float().flatten()
+                                 for n, m in sorted(rdit.named_modules()) if isinstance(m, StockLoRA) for p in (m.a, m.b)])
+            g_nat_sorted = g_nat                                   # named_parameters order: lora_A then lora_B per module, modules in definition order
+            out["stock_gpu"] = {"kind": "reference", "what": f"the reference's model_fn_qwen_image + QwenImageDiT from {ref_import.reference_root()} under torch "
+                                "autograd, LoRA layer restated (peft absent)", "ms_per_step": round(ms_stock, 2), "loss": round(float(loss_stock), 5)}
+            out["speedup_vs_stock_gpu"] = round(ms_stock / ms_nat, 3)
+            out["lora_grad_norm_native_over_stock"] = round((g_nat_sorted.norm() / g_stock.norm()).item(), 4)
+    except Exception as e:  # noqa: BLE001
+        out["stock_gpu"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def text_encoder_leg(device, ms_per_step, vae_ms, new_tokens=96):
@@ -787,6 +919,8 @@ def main():
                     help="latency mode: one image per pair of GPUs (positive branch on the even rank, negative on the odd one); needs an even --gpus")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training-leg", dest="no_training_leg", action="store_true", help="skip the training-step leg (native vs stock autograd)")
+    ap.add_argument("--train-layers", dest="train_layers", type=int, default=8, help="blocks in the training-step leg")
     ap.add_argument("--no-text-encoder", dest="no_text_encoder", action="store_true", help="skip the Qwen2.5-VL text-encoder leg (7B config, random weights)")
     ap.add_argument("--no-stock-gpu", dest="no_stock_gpu", action="store_true", help="skip the stock-PyTorch GPU baseline leg (4 blocks, same inputs)")
     ap.add_argument("--no-cfg-parallel-leg", dest="no_cfg_parallel_leg", action="store_true", help="N>=2: skip the CFG-parallel latency sub-leg")

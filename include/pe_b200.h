@@ -75,7 +75,9 @@ typedef enum pe_epilogue {
     PE_EPI_QKV_NORM_ROPE = 5,  /* N = 3*H*128: per-head RMSNorm(q,k)*w, RoPE(q,k), v passthrough;
                                   writes q/k/v into three [M, H*128] buffers                      */
     PE_EPI_BIAS_SILU = 6,      /* out = silu(bf16(acc + bias))   (timestep MLP)                   */
-    PE_EPI_F32 = 7             /* out = acc as float [M, ldo] (ldo in floats; no bias): attention scores of the VAE mid block */
+    PE_EPI_F32 = 7,            /* out = acc as float [M, ldo] (ldo in floats; no bias): attention scores of the VAE mid block */
+    PE_EPI_ATTN_P = 8,         /* pe_gemm_batched only: out = bf16(exp2(acc * alpha - vec[i]))          (attention backward: P from Q K^T)  */
+    PE_EPI_ATTN_DS = 9         /* pe_gemm_batched only: out = bf16(out * (acc - vec[i]) * alpha), in place (attention backward: dS from dO V^T) */
 } pe_epilogue;
 
 /* One segment (= token stream with its own weights) of a grouped GEMM. */
@@ -110,6 +112,26 @@ typedef struct pe_gemm_seg {
 
 int pe_gemm(pe_handle_t h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, void* stream);
 
+/* `batch` independent products of one shape in ONE launch (training path, SURVEY 8f3: the per-head matrix products of the attention backward that
+ * the reference gets from autograd through F.scaled_dot_product_attention, models/qwen_image_dit.py:14-39).  seg->a / seg->w / seg->out are the
+ * flattened operands of all problems: problem b reads A rows [b * a_batch_rows, + M), W rows [b * w_batch_rows, + N) and writes out rows
+ * [b * out_batch_rows, + M); seg->bias must be null.  Epilogues: PE_EPI_BIAS (plain bf16 store), PE_EPI_F32, and the two attention-backward
+ * ones, which take a per-problem fp32 statistic `vec + b * vec_batch_stride` indexed by the output row (vec_per_column = 0) or column (= 1):
+ *   PE_EPI_ATTN_P : out = bf16(exp2(acc * alpha - vec[i]))   -- P (or P^T) from the scores, vec = log2-domain LSE of pe_attention_fwd_lse
+ *   PE_EPI_ATTN_DS: out = bf16(out * (acc - vec[i]) * alpha) -- dS (or dS^T) in place over P, vec = delta = rowsum(dO * O)                      */
+typedef struct pe_gemm_batch {
+    int32_t batch;
+    int32_t vec_per_column;
+    int64_t a_batch_rows;
+    int64_t w_batch_rows;
+    int64_t out_batch_rows;
+    const float* vec;
+    int64_t vec_batch_stride;
+    float alpha;
+    int32_t _pad;
+} pe_gemm_batch;
+int pe_gemm_batched(pe_handle_t h, const pe_gemm_seg* seg, const pe_gemm_batch* batch, int N, int K, int epilogue, int flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* joint (text+image) non-causal attention, head dim 128                                        */
 /*   replaces qwen_image_flash_attention / F.scaled_dot_product_attention (qwen_image_dit.py:37) */
@@ -130,6 +152,11 @@ int pe_attention_fwd(pe_handle_t h, const void* q, const void* k, const void* v,
  * o_route[i] + row * ldo + head * 128 (route_end[-1] = 0, route_end[n_route-1] >= S).  In the sequence-parallel mode rank r computes its
  * H = heads / ranks heads for ALL rows and writes every row into the attention buffer of the rank that owns it (peer-mapped pointers:
  * NVLink P2P stores from the epilogue), i.e. the second all-to-all of Ulysses attention is fused into this kernel. */
+/* pe_attention_fwd that also returns the row statistics the backward needs: lse[head * S + row] = log2(sum_j exp2(scale * log2(e) * s_j))
+ * (fp32, log2 domain, softmax scale included).  flags: PE_ATTN_FLAG_* of the default kernel only (0 .. 3). */
+int pe_attention_fwd_lse(pe_handle_t h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale, int flags,
+                         float* lse, void* stream);
+
 int pe_attention_fwd_routed(pe_handle_t h, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags,
                             int n_route, const int32_t* route_end, void* const* o_route, int64_t ldo, void* stream);
 

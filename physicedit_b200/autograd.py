@@ -9,10 +9,10 @@ What runs here -- first slice of the row, stated honestly:
   * every matrix product of the forward AND the backward is the tcgen05 GEMM (`pe_gemm`): Y = X W^T (+ b), dX = dY W (W^T materialised by
     `pe_transpose`, cached for frozen weights), dW | db = dY^T [X | 1] (one GEMM: the bias gradient is the extra column), LoRA down / up
     projections and their gradients (N or K = 128);
-  * attention forward is the flash kernel (`pe_attention_fwd`); its backward is COMPOSED per head from the same GEMM (scores with the fp32
-    epilogue, dP, dQ, dK, dV), `pe_softmax_rows` (P recomputed), `pe_transpose` and two row-wise kernels (`pe_attention_bwd_delta`,
-    `pe_attention_bwd_ds`) -- the S x S matrices of one head live in HBM (1.2 GB of scratch at S = 8704), so it is HBM-bound (~11 ms per block
-    at 1024^2 against 0.83 ms forward); a fused tcgen05 flash backward is the next step (DESIGN.md 8);
+  * attention forward is the flash kernel, which also returns the row statistics (`pe_attention_fwd_lse`); its backward is seven BATCHED GEMM
+    launches per block (`pe_gemm_batched`, one problem per head) whose epilogues rebuild P / P^T from the scores and turn dP into dS / dS^T in
+    place (PE_EPI_ATTN_P / PE_EPI_ATTN_DS) -- the bf16 S x S matrices still pass through HBM (18 bytes per score element), so it is HBM-bound;
+    a fully fused tcgen05 flash backward is the next step (DESIGN.md 8);
   * the row-wise glue between them (LayerNorm + modulation, per-head RMSNorm + RoPE, x sigmoid(1.702 x), gate * branch + residual, GELU(erf),
     the blend, the losses) is written with torch ops in the reference's own op order and differentiated by autograd: ATen CUDA kernels, not
     CPU code and not the oracle, < 3 % of the FLOPs; native fused backward passes for them are also "next".
@@ -89,6 +89,12 @@ class _WeightTransposes:
 weight_transposes = _WeightTransposes()
 
 
+def _gemm(nat: nv.Native, a2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a2 w^T (+ b) with the tile shape the inference engine uses for the big layers: cta_group::2 (256-row tiles on an SM pair)."""
+    pair = w.shape[0] % 256 == 0 and a2.shape[0] >= 512
+    return nat.linear(a2, w, b, nv.EPI_BIAS, nv.GEMM_FLAG_CTA_PAIR if pair else 0)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x w^T (+ b) on pe_gemm; either operand may require grad (activations x activations products use it too)."""
 
@@ -97,7 +103,7 @@ class _LinearFn(torch.autograd.Function):
         nat = _nat(x)
         x2 = _rows(x)
         wc = w if w.is_contiguous() else w.contiguous()
-        y = nat.linear(x2, wc, b)
+        y = _gemm(nat, x2, wc, b)
         ctx.save_for_backward(x2, wc)
         ctx.has_bias, ctx.in_shape = b is not None, x.shape
         return y.view(*x.shape[:-1], w.shape[0])
@@ -110,12 +116,12 @@ class _LinearFn(torch.autograd.Function):
         N, K = w.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = nat.linear(dy2, weight_transposes.get(nat, w), None).view(ctx.in_shape)
+            dx = _gemm(nat, dy2, weight_transposes.get(nat, w)).view(ctx.in_shape)
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] or need_b:
             dyt = _transposed(nat, dy2)                                    # [N, Mp]
             xt = _transposed(nat, x2, extra_rows=8 if need_b else 0, ones_row=need_b)     # [K (+8), Mp]: the ones row makes column K the bias gradient
-            g = nat.linear(dyt, xt, None)                                  # [N, K (+8)]
+            g = _gemm(nat, dyt, xt)                                        # [N, K (+8)]
             if ctx.needs_input_grad[1]:
                 dw = g[:, :K] if need_b else g
             if need_b:
@@ -138,51 +144,68 @@ def module_linear(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     return lora_linear(x, m) if isinstance(m, LoRALinear) else linear(x, m.weight, m.bias)
 
 
+ATTN_BWD_SCRATCH_BYTES = 16 << 30        # S x S scratch of the attention backward: heads are processed in chunks that fit
+
+
 class _AttentionFn(torch.autograd.Function):
-    """Joint non-causal attention, head dim 128, q / k / v / o token-major [S, H * 128]."""
+    """Joint non-causal attention, head dim 128, q / k / v / o token-major [S, H * 128].
+
+    Backward, per chunk of heads, SEVEN batched tcgen05 GEMM launches (`pe_gemm_batched`, one problem per head) and no separate softmax /
+    transpose pass over the S x S matrices: with L the forward's log2-domain row statistic and delta = rowsum(dO * O),
+        P    = exp2(c Q K^T - L[row])   P^T  = exp2(c K Q^T - L[col])            (epilogue PE_EPI_ATTN_P)
+        dS   = P (dO V^T - delta[row]) s   dS^T = P^T (V dO^T - delta[col]) s    (epilogue PE_EPI_ATTN_DS, in place over P / P^T)
+        dV = P^T dO      dQ = dS K      dK = dS^T Q
+    Recomputing the transposed matrices on the tensor cores (2 extra products of 2 S^2 128 FLOPs) is cheaper than transposing them through
+    HBM.  18 bytes of HBM traffic per score element in all (bf16 matrices only)."""
 
     @staticmethod
     def forward(ctx, q, k, v, H):
         nat = _nat(q)
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         o = torch.empty_like(q)
-        nat.attention(q, k, v, o, H, 1.0 / math.sqrt(HEAD_DIM))
-        ctx.save_for_backward(q, k, v, o)
+        lse = torch.empty(H, q.shape[0], dtype=torch.float32, device=q.device)
+        nat.attention_lse(q, k, v, o, lse, H, 1.0 / math.sqrt(HEAD_DIM))
+        ctx.save_for_backward(q, k, v, o, lse)
         ctx.H = H
         return o
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, o = ctx.saved_tensors
+        q, k, v, o, lse = ctx.saved_tensors
         nat, H = _nat(q), ctx.H
-        S, Sp = q.shape[0], _pad8(q.shape[0])
+        S, Sp, D = q.shape[0], _pad8(q.shape[0]), HEAD_DIM
         dev, scale = q.device, 1.0 / math.sqrt(HEAD_DIM)
         do = do.contiguous()
 
-        def head_major(t):                                   # [H, Sp, 128], rows >= S zero
-            out = torch.zeros(H, Sp, HEAD_DIM, dtype=BF16, device=dev) if Sp != S else torch.empty(H, S, HEAD_DIM, dtype=BF16, device=dev)
-            out[:, :S].copy_(t.view(S, H, HEAD_DIM).transpose(0, 1))
+        def head_major(t):                                   # [H, Sp, 128], rows >= S zero (they only ever meet zeros of the other operand)
+            out = torch.zeros(H, Sp, D, dtype=BF16, device=dev) if Sp != S else torch.empty(H, S, D, dtype=BF16, device=dev)
+            out[:, :S].copy_(t.view(S, H, D).transpose(0, 1))
             return out
-        qh, kh, vh, doh, oh = (head_major(t) for t in (q, k, v, do, o))
-        f32 = dict(dtype=torch.float32, device=dev)
-        scores, dp, delta = torch.empty(Sp, Sp, **f32), torch.empty(Sp, Sp, **f32), torch.empty(Sp, **f32)
-        P, dS, Pt, dSt = (torch.empty(Sp, Sp, dtype=BF16, device=dev) for _ in range(4))
-        tr = torch.empty(3, HEAD_DIM, Sp, dtype=BF16, device=dev)          # dO^T, K^T, Q^T of the current head
-        dq, dk, dv = (torch.empty(H, Sp, HEAD_DIM, dtype=BF16, device=dev) for _ in range(3))
-        for h in range(H):
-            nat.gemm([dict(a=qh[h], w=kh[h], bias=None, out=scores)], Sp, HEAD_DIM, nv.EPI_F32)           # Q K^T
-            nat.softmax_rows(scores, P, S, scale)                                                       # P = softmax(scale * scores), columns >= S zero
-            nat.gemm([dict(a=doh[h], w=vh[h], bias=None, out=dp)], Sp, HEAD_DIM, nv.EPI_F32)             # dP = dO V^T
-            nat.attention_bwd_delta(doh[h], oh[h], delta)
-            nat.attention_bwd_ds(P, dp, delta, dS, scale)
-            nat.transpose(P, Pt); nat.transpose(dS, dSt)
-            nat.transpose(doh[h], tr[0]); nat.transpose(kh[h], tr[1]); nat.transpose(qh[h], tr[2])
-            nat.gemm([dict(a=Pt, w=tr[0], bias=None, out=dv[h])], HEAD_DIM, Sp)                          # dV = P^T dO
-            nat.gemm([dict(a=dS, w=tr[1], bias=None, out=dq[h])], HEAD_DIM, Sp)                          # dQ = dS K
-            nat.gemm([dict(a=dSt, w=tr[2], bias=None, out=dk[h])], HEAD_DIM, Sp)                         # dK = dS^T Q
+        qh, kh, vh, doh = (head_major(t) for t in (q, k, v, do))
+        qt, kt, dot = (t.transpose(1, 2).contiguous() for t in (qh, kh, doh))          # [H, 128, Sp]: the K-major operands of dK, dQ, dV
+        stat = torch.zeros(2, H, Sp, dtype=torch.float32, device=dev)                  # [0] = L, [1] = delta; padding 0 (finite)
+        stat[0, :, :S] = lse
+        stat[1, :, :S] = (do.float() * o.float()).view(S, H, D).sum(-1).t()
+        dq, dk, dv = (torch.empty(H, Sp, D, dtype=BF16, device=dev) for _ in range(3))
+        hc = max(1, min(H, ATTN_BWD_SCRATCH_BYTES // (4 * Sp * Sp)))                    # two bf16 S x S matrices per head
+        P, Pt = (torch.empty(hc * Sp, Sp, dtype=BF16, device=dev) for _ in range(2))
+        c = scale * 1.4426950408889634
+        flat = lambda t, h0, n: t[h0:h0 + n].reshape(n * t.shape[1], t.shape[2])
+        for h0 in range(0, H, hc):
+            n = min(hc, H - h0)
+            L, dl = stat[0, h0:h0 + n], stat[1, h0:h0 + n]
+            Q, K, V, DO = (flat(t, h0, n) for t in (qh, kh, vh, doh))
+            kw = dict(batch=n, M=S, a_batch_rows=Sp, out_batch_rows=Sp, vec_batch_stride=Sp)
+            nat.gemm_batched(Q, K, P, N=Sp, K=D, w_batch_rows=Sp, epilogue=nv.EPI_ATTN_P, vec=L, alpha=c, **kw)                          # P
+            nat.gemm_batched(K, Q, Pt, N=Sp, K=D, w_batch_rows=Sp, epilogue=nv.EPI_ATTN_P, vec=L, vec_per_column=True, alpha=c, **kw)     # P^T
+            nat.gemm_batched(Pt, flat(dot, h0, n), flat(dv, h0, n), N=D, K=Sp, w_batch_rows=D, **kw)                                     # dV = P^T dO
+            nat.gemm_batched(DO, V, P, N=Sp, K=D, w_batch_rows=Sp, epilogue=nv.EPI_ATTN_DS, vec=dl, alpha=scale, **kw)                    # dS over P
+            nat.gemm_batched(V, DO, Pt, N=Sp, K=D, w_batch_rows=Sp, epilogue=nv.EPI_ATTN_DS, vec=dl, vec_per_column=True, alpha=scale, **kw)   # dS^T over P^T
+            nat.gemm_batched(P, flat(kt, h0, n), flat(dq, h0, n), N=D, K=Sp, w_batch_rows=D, **kw)                                       # dQ = dS K
+            nat.gemm_batched(Pt, flat(qt, h0, n), flat(dk, h0, n), N=D, K=Sp, w_batch_rows=D, **kw)                                      # dK = dS^T Q
 
         def token_major(t):
-            return t[:, :S].transpose(0, 1).reshape(S, H * HEAD_DIM)
+            return t[:, :S].transpose(0, 1).reshape(S, H * D)
         return token_major(dq), token_major(dk), token_major(dv), None
 
 

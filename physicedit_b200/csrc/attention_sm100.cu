@@ -67,6 +67,7 @@ struct AttnParams {
     int n_route;
     int route_end[8];
     bf16* route_o[8];
+    float* lse;      // kernel 1, optional: lse[head * S + row] = log2 of the row's softmax denominator, scale included (for the backward)
 };
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(AttnCfg<kQT, kPTmem>::kThreads, 1) attention_k
             tc_fence_after();
             const float inv = f_pending / l;     // includes the O rescale still pending from the last step
             const long long row = (long long)(qb * kQT + q) * kTile + row_in_tile;
+            if (p.lse != nullptr && row < p.S) p.lse[(long long)head * p.S + row] = m_ref + log2f(l);     // l is relative to the current m_ref
             bf16* obase = p.o;
             if (p.n_route > 0) {                      // sequence-parallel mode: the row's owner rank gets it (possibly over NVLink)
                 obase = p.route_o[p.n_route - 1];
@@ -1873,8 +1875,9 @@ __global__ void __launch_bounds__(128) small_attention_kernel(const bf16* __rest
 }  // namespace
 
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
-                  int flags, cudaStream_t stream) {
+                  int flags, cudaStream_t stream, float* lse) {
     PE_REQUIRE(h, q && k && v && o, "pe_attention_fwd: null pointer");
+    PE_REQUIRE(h, lse == nullptr || (flags & ~3) == 0, "pe_attention_fwd_lse: only the default kernel (flags 0..3) writes the row statistics");
     PE_REQUIRE(h, S > 0 && H > 0, "pe_attention_fwd: S and H must be positive (S=%d H=%d)", S, H);
     PE_REQUIRE(h, ld >= (int64_t)H * 128 && ld % 8 == 0, "pe_attention_fwd: ld must be >= H*128 and a multiple of 8");
     PE_REQUIRE(h, ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -1889,6 +1892,7 @@ int attention_run(Handle* h, const void* q, const void* k, const void* v, void* 
     rc = make_tmap_2d(h, &p.tmV, v, (uint64_t)S, (uint64_t)H * 128, (uint64_t)ld, kv_box_rows);
     if (rc) return rc;
     p.o = static_cast<bf16*>(o);
+    p.lse = lse;
     p.ldo = ld;
     p.S = S;
     p.H = H;

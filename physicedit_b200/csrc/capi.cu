@@ -56,9 +56,9 @@ int make_tmap_3d(Handle* h, CUtensorMap* out, const void* base, uint64_t C, uint
 }
 
 // launchers implemented in the kernel translation units
-int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream);
+int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream, const pe_gemm_batch* bt = nullptr);
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
-                  int flags, cudaStream_t stream);
+                  int flags, cudaStream_t stream, float* lse = nullptr);
 int attention_routed_run(Handle* h, const void* q, const void* k, const void* v, int S, int H, int64_t ld, float scale, int flags, int n_route,
                          const int32_t* route_end, void* const* o_route, int64_t ldo, cudaStream_t stream);
 int layernorm_modulate_run(Handle* h, const void* x, void* out, int rows, int C, const void* shift, const void* ops, cudaStream_t s);
@@ -198,6 +198,19 @@ int pe_gemm(pe_handle_t hh, const pe_gemm_seg* segs, int nseg, int N, int K, int
     PE_H(hh);
     PE_REQUIRE(h, segs != nullptr, "pe_gemm: segs is null");
     return pe::gemm_run(h, segs, nseg, N, K, epilogue, flags, static_cast<cudaStream_t>(stream));
+}
+
+int pe_gemm_batched(pe_handle_t hh, const pe_gemm_seg* seg, const pe_gemm_batch* batch, int N, int K, int epilogue, int flags, void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, seg != nullptr && batch != nullptr, "pe_gemm_batched: null descriptor");
+    return pe::gemm_run(h, seg, 1, N, K, epilogue, flags, static_cast<cudaStream_t>(stream), batch);
+}
+
+int pe_attention_fwd_lse(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale, int flags,
+                         float* lse, void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, lse != nullptr, "pe_attention_fwd_lse: lse is null");
+    return pe::attention_run(h, q, k, v, o, S, H, ld, scale, flags, static_cast<cudaStream_t>(stream), lse);
 }
 
 int pe_attention_fwd(pe_handle_t hh, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld,

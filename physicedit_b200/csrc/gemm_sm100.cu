@@ -94,6 +94,16 @@ struct GemmParams {
                            // patch 0 and warps 8-11 patch 1.  Doubles the MMA work per k-block iteration of the producer / issuer chains.
     int patches_per_tile;  // 1, or 2 (CTA pair: one patch per CTA; dual_m: both patches in this CTA)
     int trim_n;            // issue the MMAs of a ragged last n-tile with N = round_up(N - n0, 16) instead of 256
+    // batched mode (pe_gemm_batched): `batch` independent problems of one shape share a launch.  The operands are the flattened 2-D tensors of
+    // segment 0; problem b reads A rows from b * a_batch_rows, W rows from b * w_batch_rows and writes out rows from b * out_batch_rows.  A tile
+    // that overhangs its problem reads the neighbour's rows -- those accumulator rows / columns are never stored (row < M, col < N).
+    int batch;             // 0 / 1: plain GEMM
+    int m_tiles_per_batch;
+    long long a_batch_rows, w_batch_rows, out_batch_rows;
+    const float* vec;      // PE_EPI_ATTN_P / PE_EPI_ATTN_DS: fp32 vector of problem b at vec + b * vec_batch_stride, indexed by row or by column
+    long long vec_batch_stride;
+    int vec_per_column;
+    float alpha;
     int num_stages;        // depth of the TMA -> MMA ring: the 192 KB tile region divided by the stage size (4 / 6 for 256-column tiles, up to
                            // kMaxStages for narrow layers, whose loads are latency- rather than bandwidth-bound)
     int stage_smem_bytes;  // shared-memory pitch of one stage: 16 KB A box + W box rounded up to 1 KB
@@ -126,8 +136,9 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 
 struct Tile {
     int seg;
-    int m0;   // first row of the tile inside its segment
+    int m0;   // first row of the tile inside its segment (batched mode: inside its problem)
     int n0;
+    int b;    // batched mode: which problem
 };
 
 template <int kTileM>
@@ -141,7 +152,9 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
     const int nt = in_group / gm;
     Tile r;
     r.seg = 0;
+    r.b = 0;
     if (p.nseg > 1 && mt >= p.seg[0].m_tiles) { r.seg = 1; mt -= p.seg[0].m_tiles; }
+    if (p.batch > 1) { r.b = mt / p.m_tiles_per_batch; mt -= r.b * p.m_tiles_per_batch; }
     r.m0 = mt * kTileM;
     r.n0 = nt * kTileN;
     return r;
@@ -151,7 +164,56 @@ __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f
 
 // ---- generic per-chunk epilogues: 32 consecutive columns of one row --------------------------------
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const SegDev& sg, long long row, int n, int N) {
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const SegDev& sg, long long row, int n, int N, float row_val = 0.f,
+                                               const float* col_vec = nullptr, float alpha = 1.f) {
+    if (EPI == PE_EPI_ATTN_P || EPI == PE_EPI_ATTN_DS) {
+        // attention backward (physicedit_b200/autograd.py): the accumulator is a tile of scores S = Q K^T (or its transpose), resp. of
+        // dP = dO V^T; `row_val` / `col_vec` carry the per-query-row statistic (log2-domain LSE, resp. delta = rowsum(dO * O)).
+        //   ATTN_P : out = bf16( exp2(acc * alpha - lse) )                    alpha = softmax scale * log2(e)
+        //   ATTN_DS: out = bf16( P * (acc - delta) * alpha ), P read from out   alpha = softmax scale
+        bf16* out_row = sg.out + row * sg.ldo;
+        // ATTN_DS reads the tile of P it overwrites: all four 16-byte loads of this row's 32 columns are issued before the first store (a store
+        // to out_row would otherwise order the later loads behind it -- with K = 128 these launches are epilogue-bound)
+        uint4 pv[4];
+        if (EPI == PE_EPI_ATTN_DS) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                pv[v] = (n + v * 8 < N) ? *reinterpret_cast<const uint4*>(out_row + n + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int nn = n + v * 8;
+            if (nn >= N) break;
+            float st[8];
+            if (col_vec != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(col_vec + nn)), b = __ldg(reinterpret_cast<const float4*>(col_vec + nn + 4));
+                st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w; st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) st[j] = row_val;
+            }
+            float x[8];
+            if (EPI == PE_EPI_ATTN_P) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = exp2f(fmaf(__uint_as_float(acc[v * 8 + j]), alpha, -st[j]));
+            } else {
+                const uint32_t pw[4] = {pv[v].x, pv[v].y, pv[v].z, pv[v].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 pf = unpack_bf16(pw[j]);
+                    x[2 * j] = pf.x * (__uint_as_float(acc[v * 8 + 2 * j]) - st[2 * j]) * alpha;
+                    x[2 * j + 1] = pf.y * (__uint_as_float(acc[v * 8 + 2 * j + 1]) - st[2 * j + 1]) * alpha;
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16(x[0], x[1]);
+            o.y = pack_bf16(x[2], x[3]);
+            o.z = pack_bf16(x[4], x[5]);
+            o.w = pack_bf16(x[6], x[7]);
+            *reinterpret_cast<uint4*>(out_row + nn) = o;
+        }
+        return;
+    }
     if (EPI == PE_EPI_F32) {
         // raw fp32 accumulators (attention scores of the VAE mid block, qwen_image_vae.py:189): out is float [M, ldo]
         // a lane owns one row: 32-byte stores (whole L2 sectors) instead of 16-byte ones; N and ldo are multiples of 8 floats
@@ -373,8 +435,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             // serial instruction chain per k-block is what bounds the narrow layers (r1: two integer divisions here cost ~350 cycles per
             // k-block, more than the MMAs of a 96-column tile -- profiles/r01_vae_conv.md)
             int cc = 0, cx = cx0 - p.conv_pad, cy = cy0 - p.conv_pad, ctap_x = 0;
-            const int b_row = kCG == 1 ? tile.n0 : tile.n0 + (int)cta_rank * (tile_n_cols(p, tile.n0) >> 1);   // a pair's CTAs supply half of the rows each
-            const int a_row = tile.m0 + (int)cta_rank * 128;
+            const int b_row = (kCG == 1 ? tile.n0 : tile.n0 + (int)cta_rank * (tile_n_cols(p, tile.n0) >> 1))   // a pair's CTAs supply half of the rows each
+                              + (int)(tile.b * p.w_batch_rows);
+            const int a_row = tile.m0 + (int)cta_rank * 128 + (int)(tile.b * p.a_batch_rows);
             const uint32_t fb = kCG == 1 ? 0u : mapa(full_bar(0), 0);      // a pair's bytes are all accounted on the leader's barriers
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 if (!mbar_wait(empty_bar(stage), phase ^ 1u, p.abort_flag, 1)) { ok = false; break; }
@@ -493,6 +556,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 // dual_m tile, the whole (<= 128-column) result of patch `half`
                 const int c0 = dual ? 0 : half * 4;
                 const uint32_t tcol = dual ? (uint32_t)half * 128u : 0u;
+                float row_val = 0.f;
+                const float* col_vec = nullptr;
+                if (EPI == PE_EPI_ATTN_P || EPI == PE_EPI_ATTN_DS) {
+                    const float* vb = p.vec + tile.b * p.vec_batch_stride;
+                    if (p.vec_per_column) col_vec = vb;
+                    else if (row_valid) row_val = __ldg(vb + row);
+                }
+                const long long out_row = row + tile.b * p.out_batch_rows;
 #pragma unroll 1
                 for (int c = c0; c < c0 + 4; ++c) {
                     const int n = tile.n0 + c * 32;
@@ -500,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     uint32_t r[32];
                     tmem_ld32(taddr + tcol + c * 32, r);
                     tmem_ld_wait();
-                    if (row_valid) epilogue_chunk<EPI>(r, sg, row, n, p.N);
+                    if (row_valid) epilogue_chunk<EPI>(r, sg, out_row, n, p.N, row_val, col_vec, p.alpha);
                 }
             }
             tc_fence_before();
@@ -567,6 +638,8 @@ int dispatch_epilogue(Handle* h, const GemmParams& p, int epilogue, cudaStream_t
         case PE_EPI_QKV_NORM_ROPE: return launch_gemm<kCG, PE_EPI_QKV_NORM_ROPE>(h, p, stream);
         case PE_EPI_BIAS_SILU: return launch_gemm<kCG, PE_EPI_BIAS_SILU>(h, p, stream);
         case PE_EPI_F32: return launch_gemm<kCG, PE_EPI_F32>(h, p, stream);
+        case PE_EPI_ATTN_P: return launch_gemm<kCG, PE_EPI_ATTN_P>(h, p, stream);
+        case PE_EPI_ATTN_DS: return launch_gemm<kCG, PE_EPI_ATTN_DS>(h, p, stream);
         default: return set_error(h, PE_ERR_INVALID_ARGUMENT, "pe_gemm: unknown epilogue %d", epilogue);
     }
 }
@@ -592,8 +665,20 @@ static void set_ring(GemmParams& p, int cg, int b_rows_per_cta, int a_boxes = 1)
     p.stage_tx_bytes = cg * (a_bytes + b_bytes);                 // a pair's boxes all land on the leader's barrier
 }
 
-int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream) {
+int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream, const pe_gemm_batch* bt) {
     PE_REQUIRE(h, nseg >= 1 && nseg <= 2, "pe_gemm: nseg must be 1 or 2 (got %d)", nseg);
+    const int batch = bt ? bt->batch : 1;
+    if (bt) {
+        PE_REQUIRE(h, nseg == 1 && batch >= 1 && batch <= 4096, "pe_gemm_batched: one segment, 1 <= batch <= 4096 (batch=%d)", batch);
+        PE_REQUIRE(h, epilogue == PE_EPI_BIAS || epilogue == PE_EPI_F32 || epilogue == PE_EPI_ATTN_P || epilogue == PE_EPI_ATTN_DS,
+                   "pe_gemm_batched: epilogue must be PE_EPI_BIAS, PE_EPI_F32, PE_EPI_ATTN_P or PE_EPI_ATTN_DS");
+        PE_REQUIRE(h, bt->a_batch_rows >= 0 && bt->w_batch_rows >= 0 && bt->out_batch_rows >= 0, "pe_gemm_batched: negative batch stride");
+        PE_REQUIRE(h, segs[0].bias == nullptr, "pe_gemm_batched: no bias in batched mode");
+    }
+    if (epilogue == PE_EPI_ATTN_P || epilogue == PE_EPI_ATTN_DS) {
+        PE_REQUIRE(h, bt && bt->vec, "pe_gemm: the attention-backward epilogues need pe_gemm_batched with a statistic vector");
+        PE_REQUIRE(h, (reinterpret_cast<uintptr_t>(bt->vec) & 15) == 0 && bt->vec_batch_stride % 4 == 0, "pe_gemm_batched: vec must be 16-byte aligned per problem");
+    }
     PE_REQUIRE(h, N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "pe_gemm: N and K must be positive multiples of 8 (N=%d K=%d)", N, K);
     const int cg = (flags & PE_GEMM_FLAG_CTA_PAIR) ? 2 : 1;
     const int tile_m = 128 * cg;
@@ -623,9 +708,11 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
                           (reinterpret_cast<uintptr_t>(in.out) & 15) == 0,
                    "pe_gemm: a / w / out must be 16-byte aligned");
         SegDev& d = p.seg[s];
-        int rc = make_tmap_2d(h, &d.tmA, in.a, (uint64_t)in.M, (uint64_t)K, (uint64_t)in.lda, 128);
+        const uint64_t a_rows = (uint64_t)in.M + (bt ? (uint64_t)(batch - 1) * (uint64_t)bt->a_batch_rows : 0);
+        const uint64_t w_rows = (uint64_t)N + (bt ? (uint64_t)(batch - 1) * (uint64_t)bt->w_batch_rows : 0);
+        int rc = make_tmap_2d(h, &d.tmA, in.a, a_rows, (uint64_t)K, (uint64_t)in.lda, 128);
         if (rc) return rc;
-        rc = make_tmap_2d(h, &d.tmB, in.w, (uint64_t)N, (uint64_t)K, (uint64_t)K, cg == 1 ? (uint32_t)b_box_rows : (uint32_t)(b_box_rows >> 1));
+        rc = make_tmap_2d(h, &d.tmB, in.w, w_rows, (uint64_t)K, (uint64_t)K, cg == 1 ? (uint32_t)b_box_rows : (uint32_t)(b_box_rows >> 1));
         if (rc) return rc;
         d.bias = static_cast<const bf16*>(in.bias);
         d.out = static_cast<bf16*>(in.out);
@@ -641,7 +728,7 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
             uintptr_t al = reinterpret_cast<uintptr_t>(in.out) | reinterpret_cast<uintptr_t>(in.out_k) | reinterpret_cast<uintptr_t>(in.out_v);
             d.wide_store = ((al & 31) == 0 && in.ldo % 16 == 0 && N % 16 == 0 && !narrow_stores()) ? 1 : 0;
         }
-        d.m_tiles = ceil_div(in.M, tile_m);
+        d.m_tiles = ceil_div(in.M, tile_m) * batch;
         total_m_tiles += d.m_tiles;
         if (epilogue == PE_EPI_GATE_RESIDUAL) PE_REQUIRE(h, in.gate != nullptr, "pe_gemm: gate-residual epilogue needs gate");
         if (epilogue == PE_EPI_F32) PE_REQUIRE(h, (reinterpret_cast<uintptr_t>(in.out) & 31) == 0, "pe_gemm: the fp32 output must be 32-byte aligned");
@@ -664,6 +751,17 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         }
     }
     p.total_m_tiles = total_m_tiles;
+    if (bt) {
+        p.batch = batch;
+        p.m_tiles_per_batch = total_m_tiles / batch;
+        p.a_batch_rows = bt->a_batch_rows;
+        p.w_batch_rows = bt->w_batch_rows;
+        p.out_batch_rows = bt->out_batch_rows;
+        p.vec = bt->vec;
+        p.vec_batch_stride = bt->vec_batch_stride;
+        p.vec_per_column = bt->vec_per_column;
+        p.alpha = bt->alpha;
+    }
     {
         // as many m-tiles per group as keep the group's A panel within kPanelBytes, spread evenly (r1: a fixed 16 left a last group of
         // 2 m-tiles that re-streamed the whole weight matrix, and at K = 12288 a 100 MB panel that did not fit the L2 next to W)

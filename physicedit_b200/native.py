@@ -24,6 +24,7 @@ EPI_GATE_RESIDUAL = 4
 EPI_QKV_NORM_ROPE = 5
 EPI_BIAS_SILU = 6
 EPI_F32 = 7
+EPI_ATTN_P, EPI_ATTN_DS = 8, 9
 GEMM_FLAG_CTA_PAIR = 1
 GEMM_FLAG_TRIM_N = 2
 CONV_FLAG_CTA_PAIR = 1
@@ -40,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_attention_bwd_ds",
+    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_attention_bwd_ds", "pe_gemm_batched", "pe_attention_fwd_lse",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -61,6 +62,12 @@ class GemmSeg(Structure):
         ("norm_q_w", c_void_p), ("norm_k_w", c_void_p), ("rope", c_void_p),
         ("q_route", c_void_p * 8), ("k_route", c_void_p * 8), ("v_route", c_void_p * 8), ("route_ranks", c_int32), ("_pad1", c_int32),
     ]
+
+
+class GemmBatch(Structure):
+    """Mirror of `pe_gemm_batch` (include/pe_b200.h)."""
+    _fields_ = [("batch", c_int32), ("vec_per_column", c_int32), ("a_batch_rows", c_int64), ("w_batch_rows", c_int64), ("out_batch_rows", c_int64),
+                ("vec", c_void_p), ("vec_batch_stride", c_int64), ("alpha", c_float), ("_pad", c_int32)]
 
 
 class Conv2dDesc(Structure):
@@ -112,6 +119,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_gemm_batched.argtypes = [c_void_p, POINTER(GemmSeg), POINTER(GemmBatch), c_int, c_int, c_int, c_int, c_void_p]
+    lib.pe_attention_fwd_lse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p, c_void_p]
     lib.pe_attention_bwd_delta.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
     lib.pe_attention_bwd_ds.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]
     lib.pe_gemv_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
@@ -432,6 +441,40 @@ class Native:
             raise NativeError("softmax_rows: scores must be CUDA float32 [rows, >=n] with as many rows as probs")
         self._check(self.lib.pe_softmax_rows(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
                                              n, probs.shape[1], scale, self._stream_prof()), "pe_softmax_rows")
+        self.launches += 1
+
+    # ---- training path: batched GEMM (one launch for the per-head products of the attention backward), forward with row statistics
+    def gemm_batched(self, a, w, out, batch: int, M: int, N: int, K: int, a_batch_rows: int, w_batch_rows: int, out_batch_rows: int,
+                     epilogue: int = EPI_BIAS, vec=None, vec_batch_stride: int = 0, vec_per_column: bool = False, alpha: float = 1.0, flags: int = 0) -> None:
+        """`batch` products out_b [M, N] = epilogue(a_b [M, K] w_b[N, K]^T) in one launch.  a / w / out are 2-D views of the flattened operands
+        (rows of problem b start at b * *_batch_rows); w must be contiguous with row length K; out bf16, or fp32 for EPI_F32."""
+        _bf16(a, "a"); _bf16(w, "w")
+        if epilogue == EPI_F32:
+            if out.dtype != torch.float32 or not out.is_cuda or out.stride(-1) != 1:
+                raise NativeError("out: EPI_F32 needs a CUDA float32 tensor with innermost stride 1")
+        else:
+            _bf16(out, "out")
+        if w.stride(0) != K or a.stride(0) < K:
+            raise NativeError("gemm_batched: w rows must be contiguous of length K, a rows at least K long")
+        if epilogue in (EPI_ATTN_P, EPI_ATTN_DS) and (vec is None or vec.dtype != torch.float32 or not vec.is_cuda):
+            raise NativeError("gemm_batched: the attention-backward epilogues need a CUDA float32 statistic vector")
+        seg = (GemmSeg * 1)()
+        g = seg[0]
+        g.a, g.lda, g.w, g.bias, g.out, g.ldo, g.M = a.data_ptr(), a.stride(0), w.data_ptr(), None, out.data_ptr(), out.stride(0), M
+        bt = GemmBatch(batch, int(bool(vec_per_column)), a_batch_rows, w_batch_rows, out_batch_rows, _ptr(vec), vec_batch_stride, alpha, 0)
+        self._check(self.lib.pe_gemm_batched(self.h, seg, ctypes.byref(bt), N, K, epilogue, flags, self._stream_prof()), "pe_gemm_batched")
+        self.launches += 1
+
+    def attention_lse(self, q, k, v, o, lse, H: int, scale: float, flags: int = 0) -> None:
+        """attention() that also writes lse [H, S] (fp32, log2 domain, scale included) for the backward."""
+        for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+            _bf16(t, n)
+            if t.stride(0) != q.stride(0):
+                raise NativeError("q, k, v, o must share one row stride")
+        if lse.dtype != torch.float32 or not lse.is_cuda or not lse.is_contiguous() or lse.numel() != H * q.shape[0]:
+            raise NativeError("attention_lse: lse must be a contiguous CUDA float32 [H, S]")
+        self._check(self.lib.pe_attention_fwd_lse(self.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), q.shape[0], H, q.stride(0), scale, flags,
+                                                  lse.data_ptr(), self._stream_prof()), "pe_attention_fwd_lse")
         self.launches += 1
 
     # ---- training path: attention backward helpers ------------------------------------------------------------------------------

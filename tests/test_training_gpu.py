@@ -318,3 +318,50 @@ def test_launch_training_task_trains_and_writes_the_reference_checkpoint_layout(
     ck = load_file(str(tmp_path / "epoch-2.safetensors"))
     assert any(k.startswith("transformer_blocks.0.attn.to_q.lora_A.default") for k in ck) and any(k.startswith("pipe.visual_thinking_adapter.head_dino.0") for k in ck)
     assert len(ck) == 2 * 12 * 2 + 8 and not any("base_layer" in k for k in ck)
+
+
+@gpu
+@pytest.mark.parametrize("batch,M,N,K", [(3, 200, 136, 128), (24, 333, 336, 128), (5, 300, 128, 304)])
+def test_batched_gemm_matches_per_problem_products(nat, batch, M, N, K):
+    """pe_gemm_batched: every problem of the launch equals its own product (tiles that overhang a problem read the neighbour's rows: they must
+    never be stored), for the plain and the fp32 epilogue and the two attention-backward epilogues in row and column mode."""
+    from physicedit_b200 import native as nv
+    g = torch.Generator(device="cuda").manual_seed(batch * 1000 + M)
+    Mp = (M + 7) // 8 * 8
+    a = torch.randn(batch, Mp, K, device="cuda", generator=g).bfloat16()
+    w = torch.randn(batch, N, K, device="cuda", generator=g).bfloat16() / math.sqrt(K)
+    ref = torch.einsum("bmk,bnk->bmn", a.float(), w.float())[:, :M]
+    flat = lambda t: t.reshape(-1, t.shape[-1])
+    out = torch.full((batch, Mp, N), 7.0, device="cuda").bfloat16()
+    nat.gemm_batched(flat(a), flat(w), flat(out), batch=batch, M=M, N=N, K=K, a_batch_rows=Mp, w_batch_rows=N, out_batch_rows=Mp)
+    assert rel_l2(out[:, :M], ref) < 4e-3 and (out[:, M:] == 7.0).all()                       # rows >= M of every problem untouched
+    o32 = torch.zeros(batch, Mp, N, device="cuda")
+    nat.gemm_batched(flat(a), flat(w), flat(o32), batch=batch, M=M, N=N, K=K, a_batch_rows=Mp, w_batch_rows=N, out_batch_rows=Mp, epilogue=nv.EPI_F32)
+    assert rel_l2(o32[:, :M], ref) < 1e-5
+    for per_col in (False, True):
+        vec = torch.randn(batch, max(Mp, N), device="cuda", generator=g)
+        st = vec[:, None, :N] if per_col else vec[:, :M, None]
+        p = torch.empty(batch, Mp, N, device="cuda").bfloat16()
+        kw = dict(batch=batch, M=M, N=N, K=K, a_batch_rows=Mp, w_batch_rows=N, out_batch_rows=Mp, vec=vec, vec_batch_stride=vec.shape[1], vec_per_column=per_col)
+        nat.gemm_batched(flat(a), flat(w), flat(p), epilogue=nv.EPI_ATTN_P, alpha=0.7, **kw)
+        p_ref = torch.exp2(ref * 0.7 - st)
+        assert rel_l2(p[:, :M], p_ref) < 4e-3
+        ds = p.clone()
+        nat.gemm_batched(flat(a), flat(w), flat(ds), epilogue=nv.EPI_ATTN_DS, alpha=0.25, **kw)
+        assert rel_l2(ds[:, :M], p[:, :M].float() * (ref - st) * 0.25) < 4e-3
+    nat.check_async()
+
+
+@gpu
+def test_attention_forward_row_statistics(nat):
+    """pe_attention_fwd_lse: same output as pe_attention_fwd, and lse = log2 sum_j exp2(scale log2(e) s_j) per (head, row)."""
+    S, H = 1000, 3
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q, k, v = (torch.randn(S, H * 128, device="cuda", generator=g).bfloat16() for _ in range(3))
+    o1, o2, lse = torch.empty_like(q), torch.empty_like(q), torch.empty(H, S, device="cuda")
+    nat.attention(q, k, v, o1, H, 1 / math.sqrt(128))
+    nat.attention_lse(q, k, v, o2, lse, H, 1 / math.sqrt(128))
+    assert torch.equal(o1, o2)
+    hm = lambda t: t.view(S, H, 128).transpose(0, 1).float()
+    ref = torch.logsumexp(hm(q) @ hm(k).transpose(1, 2) / math.sqrt(128), dim=-1) * 1.4426950408889634
+    assert (lse - ref).abs().max().item() < 2e-3
