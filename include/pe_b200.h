@@ -289,18 +289,15 @@ int pe_softmax_rows(pe_handle_t h, const void* scores, int64_t lds, void* probs,
                     float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
-/* training path: row-wise pieces of the attention backward                         */
+/* training path: the row term of the attention backward                            */
 /*   The reference differentiates F.scaled_dot_product_attention (models/qwen_image_dit.py:14-39) */
 /*   with autograd (pipelines/qwen_image_physical.py:313-329, scripts/train/train_physicedit.py   */
-/*   :648-652).  Here one head's backward is composed from pe_gemm (scores = Q K^T with            */
-/*   PE_EPI_F32, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO), pe_softmax_rows (P recomputed), */
-/*   pe_transpose and the two passes below (physicedit_b200/autograd.py).                         */
+/*   :648-652).  Here the backward is pe_attention_fwd_lse (row statistics) + seven               */
+/*   pe_gemm_batched launches (PE_EPI_ATTN_P / PE_EPI_ATTN_DS) + this pass.                        */
 /* ------------------------------------------------------------------------------------------- */
-/* delta[r] = sum_d dO[r, d] * O[r, d] (fp32), bf16 [rows, D] inputs, D % 8 == 0, D <= 256. */
-int pe_attention_bwd_delta(pe_handle_t h, const void* d_o, int64_t ldd, const void* o, int64_t ldo, int rows, int D, void* delta, void* stream);
-/* dS[r, c] = bf16(P[r, c] * (dP[r, c] - delta[r]) * scale): P bf16 [rows, ldp], dP float [rows, lddp], dS bf16 [rows, ldds], cols % 8 == 0. */
-int pe_attention_bwd_ds(pe_handle_t h, const void* p, int64_t ldp, const void* dp, int64_t lddp, const void* delta, void* ds, int64_t ldds,
-                        int rows, int cols, float scale, void* stream);
+/* delta[h * ld_delta + s] = sum_d dO[s, h*128 + d] * O[s, h*128 + d] (fp32); dO, O bf16 token-major [S, >= H*128]. */
+int pe_attention_bwd_delta(pe_handle_t h, const void* d_o, int64_t ldd, const void* o, int64_t ldo, int S, int H, void* delta, int64_t ld_delta,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Qwen2.5-VL text-encoder path: edit_forward prefill and greedy generate            */

@@ -185,7 +185,7 @@ class _AttentionFn(torch.autograd.Function):
         qt, kt, dot = (t.transpose(1, 2).contiguous() for t in (qh, kh, doh))          # [H, 128, Sp]: the K-major operands of dK, dQ, dV
         stat = torch.zeros(2, H, Sp, dtype=torch.float32, device=dev)                  # [0] = L, [1] = delta; padding 0 (finite)
         stat[0, :, :S] = lse
-        stat[1, :, :S] = (do.float() * o.float()).view(S, H, D).sum(-1).t()
+        nat.attention_bwd_delta(do, o, stat[1], H)
         dq, dk, dv = (torch.empty(H, Sp, D, dtype=BF16, device=dev) for _ in range(3))
         hc = max(1, min(H, ATTN_BWD_SCRATCH_BYTES // (4 * Sp * Sp)))                    # two bf16 S x S matrices per head
         P, Pt = (torch.empty(hc * Sp, Sp, dtype=BF16, device=dev) for _ in range(2))

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_attention_bwd_ds", "pe_gemm_batched", "pe_attention_fwd_lse",
+    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -121,8 +121,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
     lib.pe_gemm_batched.argtypes = [c_void_p, POINTER(GemmSeg), POINTER(GemmBatch), c_int, c_int, c_int, c_int, c_void_p]
     lib.pe_attention_fwd_lse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p, c_void_p]
-    lib.pe_attention_bwd_delta.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
-    lib.pe_attention_bwd_ds.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]
+    lib.pe_attention_bwd_delta.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]
     lib.pe_gemv_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
     lib.pe_swiglu.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_rope_half.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
@@ -478,22 +477,13 @@ class Native:
         self.launches += 1
 
     # ---- training path: attention backward helpers ------------------------------------------------------------------------------
-    def attention_bwd_delta(self, d_o, o, delta) -> None:
-        """delta[r] = sum_d dO[r, d] * O[r, d]; dO, O bf16 [rows, D] (row strides free), delta fp32 [rows]."""
+    def attention_bwd_delta(self, d_o, o, delta, H: int) -> None:
+        """delta[h, s] = sum_d dO[s, h, d] * O[s, h, d]; dO, O bf16 token-major [S, H * 128], delta fp32 [H, >= S] (row stride free)."""
         _bf16(d_o, "dO"); _bf16(o, "O")
-        if delta.dtype != torch.float32 or not delta.is_cuda or not delta.is_contiguous() or delta.numel() != o.shape[0]:
-            raise NativeError("attention_bwd_delta: delta must be a contiguous CUDA float32 [rows]")
-        self._check(self.lib.pe_attention_bwd_delta(self.h, d_o.data_ptr(), d_o.stride(0), o.data_ptr(), o.stride(0), o.shape[0], o.shape[1],
-                                                    delta.data_ptr(), self._stream_prof()), "pe_attention_bwd_delta")
-        self.launches += 1
-
-    def attention_bwd_ds(self, p, dp, delta, ds, scale: float) -> None:
-        """dS = bf16(P * (dP - delta[:, None]) * scale); P, dS bf16 [rows, cols], dP fp32 [rows, cols]."""
-        _bf16(p, "P"); _bf16(ds, "dS")
-        if dp.dtype != torch.float32 or not dp.is_cuda or dp.stride(-1) != 1 or dp.shape != p.shape or ds.shape != p.shape:
-            raise NativeError("attention_bwd_ds: dP must be CUDA float32 of P's shape, dS bf16 of P's shape")
-        self._check(self.lib.pe_attention_bwd_ds(self.h, p.data_ptr(), p.stride(0), dp.data_ptr(), dp.stride(0), delta.data_ptr(), ds.data_ptr(),
-                                                 ds.stride(0), p.shape[0], p.shape[1], scale, self._stream_prof()), "pe_attention_bwd_ds")
+        if delta.dtype != torch.float32 or not delta.is_cuda or delta.stride(-1) != 1 or delta.shape[0] != H or delta.shape[1] < o.shape[0]:
+            raise NativeError("attention_bwd_delta: delta must be CUDA float32 [H, >= S]")
+        self._check(self.lib.pe_attention_bwd_delta(self.h, d_o.data_ptr(), d_o.stride(0), o.data_ptr(), o.stride(0), o.shape[0], H, delta.data_ptr(),
+                                                    delta.stride(0), self._stream_prof()), "pe_attention_bwd_delta")
         self.launches += 1
 
     # ---- Qwen2.5-VL text-encoder path (include/pe_b200.h, last section) --------------------------------------------------------
