@@ -287,6 +287,11 @@ int pe_transpose(pe_handle_t h, const void* src, int64_t lds, void* dst, int64_t
  * P.V product run with its K dimension padded to a multiple of 8). */
 int pe_softmax_rows(pe_handle_t h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad,
                     float scale, void* stream);
+/* The same with a key mask (EliGen entity control, SURVEY 8f5: the additive 0 / -inf mask of QwenImageDiT.process_entity_masks,
+ * models/qwen_image_dit.py:433-498, handed to F.scaled_dot_product_attention :36): mask is a byte matrix [mask_period, ldm], 0 = hidden;
+ * row r of the scores uses mask row r % mask_period (one mask for all heads of a batched score matrix). */
+int pe_softmax_rows_masked(pe_handle_t h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad,
+                           float scale, const void* mask, int64_t ldm, int mask_period, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* training path: the row term of the attention backward                            */

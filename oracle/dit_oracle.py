@@ -97,9 +97,11 @@ def _rope_params(index: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.polar(torch.ones_like(freqs), freqs)
 
 
-def rope_tables(img_shapes: Sequence[Tuple[int, int, int]], txt_len: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def rope_tables(img_shapes: Sequence[Tuple[int, int, int]], txt_len: int, sampling: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """QwenEmbedRope(theta=1e4, axes_dim=[16,56,56], scale_rope=True).forward -> complex64 (vid [S_img,64], txt [T,64]).
-    Tables auto-extend in 512 steps beyond 4096 positions (:94-120)."""
+    Tables auto-extend in 512 steps beyond 4096 positions (:94-120).  sampling=True: forward_sampling (:168-225,
+    `edit_rope_interpolation`) from an EMPTY cache: an image idx > 0 whose (h, w) differs from image 0's takes image 0's table
+    sampled at linspace(0, n0 - 1, n).long() rows / columns, with its own frame-axis entries."""
     max_hw = max(max(h // 2, w // 2) for _, h, w in img_shapes)
     n = 4096
     if max_hw + txt_len > n:
@@ -119,7 +121,15 @@ def rope_tables(img_shapes: Sequence[Tuple[int, int, int]], txt_len: int) -> Tup
         f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
         f_w = torch.cat([fneg[2][-(width - width // 2):], fpos[2][: width // 2]], dim=0)
         f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
-        vid.append(torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1))
+        table = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1)
+        f0, h0, w0 = img_shapes[0]
+        if sampling and idx > 0 and (height, width) != (h0, w0):
+            grid0 = vid[0].reshape(f0, h0, w0, -1)
+            hg, wg = torch.meshgrid(torch.linspace(0, h0 - 1, height).long(), torch.linspace(0, w0 - 1, width).long(), indexing="ij")
+            table = grid0[:, hg, wg, :].clone()
+            table[..., :split[0]] = f_frame
+            table = table.reshape(frame * height * width, -1)
+        vid.append(table)
         max_vid_index = max(height // 2, width // 2, max_vid_index)
     txt = pos[max_vid_index: max_vid_index + txt_len]
     return torch.cat(vid, dim=0), txt
@@ -152,9 +162,15 @@ def _heads(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(B, S, NUM_HEADS, HEAD_DIM).permute(0, 2, 1, 3)          # 'b s (h d) -> b h s d'
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
-    """qwen_image_flash_attention default branch (:37-38): SDPA, no mask, scale 1/sqrt(128); 'b n s d -> b s (n d)'."""
-    if q.is_cuda and q.dtype == torch.float32:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qwen_image_flash_attention default branch (:37-38): SDPA, scale 1/sqrt(128); 'b n s d -> b s (n d)'.  attention_mask: the additive
+    0 / -inf mask [B, 1, S, S] of process_entity_masks (EliGen)."""
+    if attention_mask is not None:
+        x = torch.empty_like(q)
+        for h in range(q.shape[1]):                      # one head at a time (exact in fp32, bounded memory)
+            sc = (q[:, h].float() @ k[:, h].float().transpose(-1, -2)) * (q.shape[-1] ** -0.5) + attention_mask[:, 0].float()
+            x[:, h] = (torch.softmax(sc, dim=-1).to(q.dtype) @ v[:, h]) if q.dtype != torch.float32 else torch.softmax(sc, dim=-1) @ v[:, h]
+    elif q.is_cuda and q.dtype == torch.float32:
         # The oracle proper on a GPU (tests at the benchmark's sequence lengths): SDPA's fused fp32 kernels may use TF32 tensor
         # cores, and its math backend materialises all heads' S x S scores at once (42 GB at S = 20992).  Same formula, exact
         # fp32, one head at a time.
@@ -180,7 +196,7 @@ def _mlp(W: Weights, pre: str, x: torch.Tensor) -> torch.Tensor:
 
 
 def block_forward(W: Weights, i: int, image: torch.Tensor, text: torch.Tensor, temb: torch.Tensor,
-                  rope: Tuple[torch.Tensor, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+                  rope: Tuple[torch.Tensor, torch.Tensor], attention_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """QwenImageTransformerBlock.forward (:359-401) + QwenDoubleStreamAttention.forward (:274-316)."""
     p = f"transformer_blocks.{i}"
     img_mod_attn, img_mod_mlp = linear(F.silu(temb), W, p + ".img_mod.1").chunk(2, dim=-1)
@@ -198,7 +214,7 @@ def block_forward(W: Weights, i: int, image: torch.Tensor, text: torch.Tensor, t
     img_q, img_k = apply_rope(img_q, img_f), apply_rope(img_k, img_f)
     txt_q, txt_k = apply_rope(txt_q, txt_f), apply_rope(txt_k, txt_f)
     joint = attention(torch.cat([txt_q, img_q], dim=2), torch.cat([txt_k, img_k], dim=2),
-                      torch.cat([txt_v, img_v], dim=2)).to(img_q.dtype)
+                      torch.cat([txt_v, img_v], dim=2), attention_mask).to(img_q.dtype)
     txt_o = linear(joint[:, :seq_txt], W, a + ".to_add_out")
     img_o = linear(joint[:, seq_txt:], W, a + ".to_out.0")
 
@@ -246,7 +262,8 @@ def adapter_loss(pred_dino, pred_vae, gt_dino, gt_vae, timestep, t_min, t_max, e
 def model_fn(W: Weights, A: Optional[Weights], latents: torch.Tensor, timestep: torch.Tensor, prompt_emb: torch.Tensor,
              prompt_emb_mask: torch.Tensor, special_token_mask: Optional[torch.Tensor], height: int, width: int,
              edit_latents=None, num_layers: Optional[int] = None, t_min: float = 19.999980926513672, t_max: float = 1000.0,
-             cuda_scalar_div: bool = False, collect: Optional[dict] = None) -> torch.Tensor:
+             cuda_scalar_div: bool = False, collect: Optional[dict] = None, edit_rope_interpolation: bool = False,
+             controlnet: Optional[list] = None, progress_id: int = 0, num_inference_steps: int = 1, entity: Optional[dict] = None) -> torch.Tensor:
     """Returns the predicted velocity [B,16,H/8,W/8].  MUTATES prompt_emb in place like the reference (:1336)."""
     dtype = latents.dtype
     if special_token_mask is not None:
@@ -266,12 +283,22 @@ def model_fn(W: Weights, A: Optional[Weights], latents: torch.Tensor, timestep: 
         image = torch.cat([image] + [patchify(e) for e in edits], dim=1)
     image = linear(image, W, "img_in")
     temb = time_text_embed(W, ts, dtype)
-    text = linear(rmsnorm(prompt_emb, W["txt_norm.weight"]), W, "txt_in")
-    vid_f, txt_f = rope_tables(img_shapes, txt_len)
+    attention_mask = None
+    if entity is not None:                                                                      # :1360-1364, qwen_image_dit.py:433-498
+        text, (vid_f, txt_f), attention_mask = process_entity_masks(W, latents, prompt_emb, txt_len, entity["prompt_emb"], entity["masks"], height, width,
+                                                                    image.shape[1], img_shapes)
+    else:
+        text = linear(rmsnorm(prompt_emb, W["txt_norm.weight"]), W, "txt_in")
+        vid_f, txt_f = rope_tables(img_shapes, txt_len, sampling=edit_rope_interpolation)      # :1367-1370
     if num_layers is None:
         num_layers = 1 + max(int(k.split(".")[1]) for k in W if k.startswith("transformer_blocks."))
+    conds = [controlnet_img_in(c["weights"], patchify(c["latents"])) for c in controlnet] if controlnet else None      # :1372-1374, :164-170
     for i in range(num_layers):
-        text, image = block_forward(W, i, image, text, temb, (vid_f, txt_f))
+        text, image = block_forward(W, i, image, text, temb, (vid_f, txt_f), attention_mask)
+        if conds is not None:                                                                                          # :1389-1396
+            image_slice = image[:, :image_seq_len].clone()
+            image = image.clone()
+            image[:, :image_seq_len] = image_slice + controlnet_sum(controlnet, conds, image_slice, i, progress_id, num_inference_steps)
         if collect is not None:
             collect[f"block{i}"] = (text, image)
     # AdaLayerNorm(single=True): (scale, shift) order (models/utils.py:304-308)
@@ -280,6 +307,73 @@ def model_fn(W: Weights, A: Optional[Weights], latents: torch.Tensor, timestep: 
     image = layernorm(image) * (1 + scale) + shift
     image = linear(image, W, "proj_out")[:, :image_seq_len]
     return unpatchify(image, height // 16, width // 16)
+
+
+# -------------------------------------------------------------------------------------------------
+# EliGen entity control (models/qwen_image_dit.py:433-498)
+# -------------------------------------------------------------------------------------------------
+def process_entity_masks(W: Weights, latents, prompt_emb, txt_len: int, entity_prompt_emb, entity_masks, height: int, width: int, n_image_tokens: int,
+                         img_shapes):
+    """entity_prompt_emb: list of [1, L_i, 3584] (unpadded, batch 1); entity_masks [1, N, 1, H/8, W/8] (non-negative).  Returns the joint text
+    stream [entity prompts ..., global prompt] after txt_norm / txt_in, (image table, concatenated text tables -- every prompt starts at the same
+    position) and the additive attention mask [1, 1, S, S]: prompt i <-> the image tokens whose 2 x 2 latent patch touches mask i (the global
+    prompt sees all), repeated over every image of the sequence; different prompts never see each other."""
+    text = torch.cat([linear(rmsnorm(e, W["txt_norm.weight"]), W, "txt_in") for e in list(entity_prompt_emb) + [prompt_emb]], dim=1)
+    seq_lens = [int(e.shape[1]) for e in entity_prompt_emb] + [txt_len]
+    vid_f, _ = rope_tables(img_shapes, txt_len)
+    txt_f = torch.cat([rope_tables(img_shapes, n)[1] for n in seq_lens], dim=0)
+    N = entity_masks.shape[1] + 1
+    patched = [F.max_pool2d(entity_masks[:, i].float(), 2).flatten(1) > 0 for i in range(N - 1)]            # sum over (C P Q) of the patch > 0
+    patched.append(torch.ones_like(patched[0]))
+    total = sum(seq_lens) + n_image_tokens
+    allow = torch.ones(1, total, total, dtype=torch.bool, device=latents.device)
+    cum = [0]
+    for n in seq_lens:
+        cum.append(cum[-1] + n)
+    i0 = cum[-1]
+    for i in range(N):
+        im = patched[i].unsqueeze(1).repeat(1, seq_lens[i], n_image_tokens // patched[i].shape[-1])
+        allow[:, cum[i]:cum[i + 1], i0:] = im
+        allow[:, i0:, cum[i]:cum[i + 1]] = im.transpose(1, 2)
+        for j in range(N):
+            if j != i:
+                allow[:, cum[i]:cum[i + 1], cum[j]:cum[j + 1]] = False
+    mask = torch.zeros(allow.shape, dtype=torch.float32, device=latents.device).masked_fill(~allow, float("-inf"))
+    return text, (vid_f, txt_f), mask.to(latents.dtype).unsqueeze(1)
+
+
+# -------------------------------------------------------------------------------------------------
+# blockwise controlnet (models/qwen_image_controlnet.py:6-61, pipelines/qwen_image_physical.py:157-180)
+# -------------------------------------------------------------------------------------------------
+def controlnet_img_in(C: Weights, tokens: torch.Tensor) -> torch.Tensor:
+    return linear(tokens, C, "img_in")
+
+
+def controlnet_block(C: Weights, i: int, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """BlockWiseControlBlock.forward (:17-22): output_proj(GELU(input_proj(rms(x) + rms(y))))."""
+    p = f"controlnet_blocks.{i}."
+    h = rmsnorm(x, C[p + "x_rms.weight"]) + rmsnorm(y, C[p + "y_rms.weight"])
+    return linear(F.gelu(linear(h, C, p + "input_proj")), C, p + "output_proj")
+
+
+def controlnet_sum(controlnet, conds, image_slice, block_id, progress_id, num_inference_steps):
+    """QwenImageBlockwiseMultiControlNet.blockwise_forward (:172-180); each entry of `controlnet`: dict(weights, latents, scale, start, end)."""
+    res = 0
+    for c, cond in zip(controlnet, conds):
+        progress = (num_inference_steps - 1 - progress_id) / max(num_inference_steps - 1, 1)
+        if progress > c.get("start", 1.0) + 1e-4 or progress < c.get("end", 0.0) - 1e-4:
+            continue
+        res = res + controlnet_block(c["weights"], block_id, image_slice, cond) * c.get("scale", 1.0)
+    return res
+
+
+def controlnet_param_shapes(num_layers: int, in_dim: int = 64, dim: int = 3072) -> Dict[str, Tuple[int, ...]]:
+    s = {"img_in.weight": (dim, in_dim), "img_in.bias": (dim,)}
+    for i in range(num_layers):
+        p = f"controlnet_blocks.{i}."
+        s.update({p + "x_rms.weight": (dim,), p + "y_rms.weight": (dim,), p + "input_proj.weight": (dim, dim), p + "input_proj.bias": (dim,),
+                  p + "output_proj.weight": (dim, dim), p + "output_proj.bias": (dim,)})
+    return s
 
 
 # -------------------------------------------------------------------------------------------------

@@ -46,7 +46,7 @@ class VisualThinkingAdapter(nn.Module):
 
     def forward(self, x):
         from . import autograd as ag
-        if x.requires_grad or ag.needs_grad(self):                       # training: same GEMMs under autograd
+        if ag.module_trains(self, x):                                    # training: same GEMMs under autograd
             return ag.mlp_gelu(x, self.net[0], self.net[2])
         nat = _nat(x)
         y = _mlp_gelu(nat, x.reshape(-1, x.shape[-1]).contiguous(), self.net[0], self.net[2])
@@ -74,7 +74,7 @@ class VisualThinkingDualAdapter(nn.Module):
 
     def forward(self, x, timestep):
         from . import autograd as ag
-        if x.requires_grad or ag.needs_grad(self):
+        if ag.module_trains(self, x):
             return ag.dual_adapter_forward(self, x, timestep)
         nat = _nat(x)
         x2d = x.reshape(-1, x.shape[-1]).contiguous()
@@ -134,7 +134,7 @@ class PerceiverResampler(nn.Module):
     def forward(self, x):
         from . import autograd as ag
         assert x.shape[0] == 1, "the reference always calls the resampler with batch 1 (frames are flattened into the sequence)"
-        if x.requires_grad or ag.needs_grad(self):
+        if ag.module_trains(self, x):
             return ag.resampler_forward(self, x)
         nat = _nat(x)
         n, dim = x.shape[1], x.shape[2]

@@ -272,7 +272,7 @@ def block_forward(blk, image: torch.Tensor, text: torch.Tensor, temb: torch.Tens
 
 
 def dit_forward(dit, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
-                use_gradient_checkpointing: bool = True) -> torch.Tensor:
+                use_gradient_checkpointing: bool = True, rope_sampling: bool = False) -> torch.Tensor:
     """model_fn_qwen_image :1340-1403 under autograd.  latents_list = [noise latents, (context), edit...] each [1, 16, h8, w8] bf16 (no gradient
     flows into them: the path trains LoRA and adapters only); timestep_bf16 [1] = the loop's bf16(t); prompt_emb [1, T, 3584] (may carry the
     adapter's graph).  Returns the velocity [1, 16, h8, w8]."""
@@ -288,7 +288,7 @@ def dit_forward(dit, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.
             nat.patchify(l.reshape(16, l.shape[-2], l.shape[-1]).contiguous(), tok[off:off + h * w])
             off += h * w
         temb = dit.time_text_embed(timestep_bf16, raw=True)               # [1, 3072]
-        rope = eng.rope(shapes, T)                                        # fp32 (cos, sin) [T + S_img, 64, 2], text rows first
+        rope = eng.rope(shapes, T, rope_sampling)                         # fp32 (cos, sin) [T + S_img, 64, 2], text rows first
     image = module_linear(dit.img_in, tok)
     text = module_linear(dit.txt_in, _rmsnorm(prompt_emb[0], dit.txt_norm.weight, dit.txt_norm.eps))
     rope_txt, rope_img = rope[:T], rope[T:]
@@ -359,3 +359,9 @@ def resampler_forward(rs, x: torch.Tensor) -> torch.Tensor:
 def needs_grad(*modules) -> bool:
     """True when autograd is on and some parameter of the given modules is trainable."""
     return torch.is_grad_enabled() and any(p.requires_grad for m in modules if m is not None for p in m.parameters())
+
+
+def module_trains(m: torch.nn.Module, x: torch.Tensor) -> bool:
+    """Should module `m` run under autograd for input x?  Yes when grad mode is on and either the input already carries a graph or the module
+    is in training mode with trainable parameters (`pipe.freeze_except` puts exactly the trainable models in train mode, :254-259)."""
+    return torch.is_grad_enabled() and (x.requires_grad or (m.training and any(p.requires_grad for p in m.parameters())))

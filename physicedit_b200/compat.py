@@ -59,7 +59,7 @@ def adopt_text_encoder(ref_te: torch.nn.Module):
 
 @dataclass
 class ControlNetInput:
-    """pipelines/flux_image_new.py:5-13 (only imported by the scripts; blockwise controlnet is out of scope)."""
+    """pipelines/flux_image_new.py:5-13: one blockwise-controlnet request (physicedit_b200/controlnet.py)."""
     controlnet_id: int = 0
     scale: float = 1.0
     start: float = 1.0

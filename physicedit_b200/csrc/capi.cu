@@ -89,7 +89,8 @@ int space_to_depth_run(Handle* h, const void* in, void* out, int H, int W, int C
 int nchw_to_nhwc_run(Handle* h, const void* src, void* dst, int64_t ldd, int C, int64_t HW, int op, const void* p0, const void* p1, cudaStream_t s);
 int nhwc_to_nchw_run(Handle* h, const void* src, int64_t lds, void* dst, int C, int64_t HW, int op, const void* p0, const void* p1, cudaStream_t s);
 int transpose_run(Handle* h, const void* src, int64_t lds, void* dst, int64_t ldd, int R, int C, cudaStream_t s);
-int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s);
+int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s,
+                     const void* mask = nullptr, int64_t ldm = 0, int mask_period = 0);
 int attention_bwd_delta_run(Handle* h, const void* d_o, int64_t ldd, const void* o, int64_t ldo, int S, int H, void* delta, int64_t ld_delta, cudaStream_t s);
 int swiglu_run(Handle* h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, cudaStream_t s);
 int rope_half_run(Handle* h, void* x, int64_t ldx, int T, int H, int D, const float* cs, const float* sn, const int* row_ptr, int row0, int mode,
@@ -357,6 +358,13 @@ int pe_attention_bwd_delta(pe_handle_t hh, const void* d_o, int64_t ldd, const v
                            void* stream) {
     PE_H(hh);
     return pe::attention_bwd_delta_run(h, d_o, ldd, o, ldo, S, H, delta, ld_delta, static_cast<cudaStream_t>(stream));
+}
+
+int pe_softmax_rows_masked(pe_handle_t hh, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale,
+                           const void* mask, int64_t ldm, int mask_period, void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, mask != nullptr, "pe_softmax_rows_masked: mask is null");
+    return pe::softmax_rows_run(h, scores, lds, probs, ldp, rows, n, n_pad, scale, static_cast<cudaStream_t>(stream), mask, ldm, mask_period);
 }
 
 int pe_swiglu(pe_handle_t hh, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, void* stream) {

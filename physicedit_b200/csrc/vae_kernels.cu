@@ -195,14 +195,19 @@ __global__ void transpose_kernel(const bf16* __restrict__ src, long long lds, bf
 // one CTA per row; the row (<= 64 KB at 1024^2 images) is re-read from L1/L2 for the three passes.  Columns [n, n_pad) of the
 // output are written as zeros so that a K-padded P.V product ignores them.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long lds, bf16* __restrict__ p, long long ldp, int n,
-                                                           int n_pad, float scale_log2e) {
+                                                           int n_pad, float scale_log2e, const unsigned char* __restrict__ mask, long long ldm,
+                                                           int mask_period) {
+    // mask (optional): byte [mask_period, >= n], 0 = this key is hidden from the row (EliGen entity masks: -inf in the reference's additive
+    // mask, qwen_image_dit.py:493-496); row r uses mask row r % mask_period, so one mask serves every head of a batched score matrix
     __shared__ float red[8];
     __shared__ float bcast;
     const float* row = s + (long long)blockIdx.x * lds;
     bf16* prow = p + (long long)blockIdx.x * ldp;
+    const unsigned char* mrow = mask ? mask + (long long)(blockIdx.x % mask_period) * ldm : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float m = -INFINITY;
-    for (int i = tid; i < n; i += 256) m = fmaxf(m, row[i]);
+    for (int i = tid; i < n; i += 256)
+        if (!mrow || mrow[i]) m = fmaxf(m, row[i]);
     m = warp_max_f(m);
     if (lane == 0) red[warp] = m;
     __syncthreads();
@@ -210,7 +215,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     __syncthreads();
     m = bcast * scale_log2e;
     float sum = 0.f;
-    for (int i = tid; i < n; i += 256) sum += exp2f(row[i] * scale_log2e - m);
+    for (int i = tid; i < n; i += 256)
+        if (!mrow || mrow[i]) sum += exp2f(row[i] * scale_log2e - m);
     sum = warp_sum_f(sum);
     __syncthreads();
     if (lane == 0) red[warp] = sum;
@@ -218,7 +224,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bcast = t; }
     __syncthreads();
     const float inv = 1.0f / bcast;
-    for (int i = tid; i < n_pad; i += 256) prow[i] = __float2bfloat16_rn(i < n ? exp2f(row[i] * scale_log2e - m) * inv : 0.0f);
+    for (int i = tid; i < n_pad; i += 256)
+        prow[i] = __float2bfloat16_rn((i < n && (!mrow || mrow[i])) ? exp2f(row[i] * scale_log2e - m) * inv : 0.0f);
 }
 
 inline int grid_for(long long work_items, int threads, int sm_count) {
@@ -296,11 +303,13 @@ int transpose_run(Handle* h, const void* src, int64_t lds, void* dst, int64_t ld
     return PE_OK;
 }
 
-int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s) {
+int softmax_rows_run(Handle* h, const void* scores, int64_t lds, void* probs, int64_t ldp, int rows, int n, int n_pad, float scale, cudaStream_t s,
+                     const void* mask, int64_t ldm, int mask_period) {
     PE_REQUIRE(h, scores && probs && rows > 0 && n > 0 && n_pad >= n, "pe_softmax_rows: need rows > 0 and 0 < n <= n_pad (n=%d n_pad=%d)", n, n_pad);
     PE_REQUIRE(h, lds >= n && ldp >= n_pad, "pe_softmax_rows: row strides must cover n / n_pad");
+    PE_REQUIRE(h, mask == nullptr || (ldm >= n && mask_period > 0), "pe_softmax_rows_masked: mask rows must cover n, mask_period > 0");
     softmax_rows_kernel<<<rows, 256, 0, s>>>(static_cast<const float*>(scores), lds, static_cast<bf16*>(probs), ldp, n, n_pad,
-                                             scale * 1.4426950408889634f);
+                                             scale * 1.4426950408889634f, static_cast<const unsigned char*>(mask), ldm, mask_period > 0 ? mask_period : 1);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

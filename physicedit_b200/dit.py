@@ -134,8 +134,6 @@ class QwenImageTransformerBlock(nn.Module):
     def forward(self, image, text, temb, image_rotary_emb=None, attention_mask=None, enable_fp8_attention=False):
         """Same signature / return order as the reference (qwen_image_dit.py:359-401): returns (text, image).
         image [1,S_img,3072], text [1,T,3072], temb [1,3072]; image_rotary_emb = (vid complex [S_img,64], txt complex [T,64])."""
-        if attention_mask is not None or enable_fp8_attention:
-            raise NotImplementedError("entity attention masks / fp8 attention are outside the PhysicEdit hot path (SURVEY 8f5)")
         dit, idx = self._owner
         eng = dit.engine()
         T, S_img = text.shape[1], image.shape[1]
@@ -144,7 +142,10 @@ class QwenImageTransformerBlock(nn.Module):
         rope = torch.view_as_real(torch.cat([txt, vid], dim=0).to(torch.complex64)).contiguous().to(x.device)
         ws = eng.workspace(S_img, T)
         mods = eng.block_mods(temb.reshape(1, DIM), [idx])
-        eng.run_block(idx, x, T, mods[0, 0], rope, ws)
+        mask_u8 = None
+        if attention_mask is not None:                   # the reference's additive 0 / -inf mask [1, 1, S, S] (EliGen)
+            mask_u8 = (attention_mask.reshape(attention_mask.shape[-2], attention_mask.shape[-1]) == 0).to(torch.uint8).contiguous()
+        eng.run_block(idx, x, T, mods[0, 0], rope, ws, mask_u8, bool(enable_fp8_attention) and mask_u8 is None)
         return x[:T].unsqueeze(0), x[T:].unsqueeze(0)
 
 
@@ -177,25 +178,42 @@ class QwenEmbedRope(nn.Module):
         if required > self.pos_freqs.shape[0]:
             self._build(math.ceil(required / 512) * 512)
 
-    def forward(self, video_fhw, txt_seq_lens, device=None):
-        self._expand_pos_freqs_if_needed(video_fhw, txt_seq_lens)
+    def _axis_table(self, idx, frame, height, width):
+        """[frame * height * width, 64] complex: frame axis at index idx.., centred height / width axes when scale_rope (:131-150)."""
         split = [x // 2 for x in self.axes_dim]
+        fpos, fneg = self.pos_freqs.split(split, dim=1), self.neg_freqs.split(split, dim=1)
+        f_frame = fpos[0][idx: idx + frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+        if self.scale_rope:
+            f_h = torch.cat([fneg[1][-(height - height // 2):], fpos[1][: height // 2]], dim=0)
+            f_w = torch.cat([fneg[2][-(width - width // 2):], fpos[2][: width // 2]], dim=0)
+        else:
+            f_h, f_w = fpos[1][:height], fpos[2][:width]
+        f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
+        f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
+        return torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1).clone().contiguous()
+
+    def _tables(self, video_fhw, txt_seq_lens, device, sampling):
+        self._expand_pos_freqs_if_needed(video_fhw, txt_seq_lens)
         vid_freqs = []
         max_vid_index = 0
         for idx, (frame, height, width) in enumerate(video_fhw):
             key = f"{idx}_{height}_{width}"
+            if sampling and idx > 0 and f"0_{height}_{width}" not in self.rope_cache:
+                # edit_rope_interpolation (:179-194): an edit image of another size takes the positions of the NOISE image's grid sampled at
+                # linspace(0, n0 - 1, n).long() rows / columns, with its own frame index.  (Like the reference, the entry lands in the cache
+                # shared with forward(): whichever call creates a key first decides it.)
+                f0, h0, w0 = video_fhw[0]
+                grid0 = self.rope_cache[f"0_{h0}_{w0}"].reshape(f0, h0, w0, -1)
+                hi = torch.linspace(0, h0 - 1, height).long()
+                wi = torch.linspace(0, w0 - 1, width).long()
+                hg, wg = torch.meshgrid(hi, wi, indexing="ij")
+                sampled = grid0[:, hg, wg, :]
+                n_frame = self.axes_dim[0] // 2
+                sampled[:, :, :, :n_frame] = self.pos_freqs[idx: idx + frame, :n_frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+                self.rope_cache[key] = sampled.reshape(frame * height * width, -1).clone()
             if key not in self.rope_cache:
-                fpos, fneg = self.pos_freqs.split(split, dim=1), self.neg_freqs.split(split, dim=1)
-                f_frame = fpos[0][idx: idx + frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
-                if self.scale_rope:
-                    f_h = torch.cat([fneg[1][-(height - height // 2):], fpos[1][: height // 2]], dim=0)
-                    f_w = torch.cat([fneg[2][-(width - width // 2):], fpos[2][: width // 2]], dim=0)
-                else:
-                    f_h, f_w = fpos[1][:height], fpos[2][:width]
-                f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
-                f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
-                self.rope_cache[key] = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1).clone().contiguous()
-            vid_freqs.append(self.rope_cache[key])
+                self.rope_cache[key] = self._axis_table(idx, frame, height, width)
+            vid_freqs.append(self.rope_cache[key].contiguous())
             max_vid_index = max(height // 2, width // 2, max_vid_index) if self.scale_rope else max(height, width, max_vid_index)
         max_len = max(txt_seq_lens)
         txt_freqs = self.pos_freqs[max_vid_index: max_vid_index + max_len, ...]
@@ -203,6 +221,14 @@ class QwenEmbedRope(nn.Module):
         if device is not None:
             vid_freqs, txt_freqs = vid_freqs.to(device), txt_freqs.to(device)
         return vid_freqs, txt_freqs
+
+    def forward(self, video_fhw, txt_seq_lens, device=None):
+        """:122-165."""
+        return self._tables(video_fhw, txt_seq_lens, device, sampling=False)
+
+    def forward_sampling(self, video_fhw, txt_seq_lens, device=None):
+        """:168-225 (`edit_rope_interpolation=True`, qwen_image_physical.py:1367-1368)."""
+        return self._tables(video_fhw, txt_seq_lens, device, sampling=True)
 
 
 class QwenImageDiTStateDictConverter:
@@ -357,11 +383,12 @@ class DiTEngine:
             self._ws[key] = Workspace(S_img, T, self.device)
         return self._ws[key]
 
-    def rope(self, img_shapes: Sequence[Tuple[int, int, int]], T: int) -> torch.Tensor:
-        """float2 (cos, sin) table [T + S_img, 64] in joint [text; image] order."""
-        key = (tuple(tuple(s) for s in img_shapes), T)
+    def rope(self, img_shapes: Sequence[Tuple[int, int, int]], T: int, sampling: bool = False) -> torch.Tensor:
+        """float2 (cos, sin) table [T + S_img, 64] in joint [text; image] order; `sampling` = edit_rope_interpolation (forward_sampling)."""
+        key = (tuple(tuple(s) for s in img_shapes), T, bool(sampling))
         if key not in self._rope:
-            vid, txt = self.dit.pos_embed(list(img_shapes), [T], device=None)
+            pe = self.dit.pos_embed
+            vid, txt = (pe.forward_sampling if sampling else pe.forward)(list(img_shapes), [T], device=None)
             joint = torch.cat([txt, vid], dim=0).to(torch.complex64)
             self._rope[key] = torch.view_as_real(joint).contiguous().to(self.device)
         return self._rope[key]
@@ -428,9 +455,11 @@ class DiTEngine:
             self._mods_cache = (t_key,) + res
         return res
 
-    def run_block(self, i: int, x: torch.Tensor, T: int, mods: torch.Tensor, rope: torch.Tensor, ws: Workspace):
+    def run_block(self, i: int, x: torch.Tensor, T: int, mods: torch.Tensor, rope: torch.Tensor, ws: Workspace, attn_mask: Optional[torch.Tensor] = None,
+                  fp8_attention: bool = False):
         """One double-stream block in place on the joint residual stream x [T + S_img, 3072].
-        mods: [2, 18432] = (img, txt) x (shift_a, 1+scale_a, gate_a, shift_m, 1+scale_m, gate_m)."""
+        mods: [2, 18432] = (img, txt) x (shift_a, 1+scale_a, gate_a, shift_m, 1+scale_m, gate_m).
+        attn_mask: uint8 [S, S], 0 = hidden (EliGen) -> the masked attention path; fp8_attention: q / k / v quantised to e4m3."""
         nat, blk = self.nat, self.dit.transformer_blocks[i]
         a = blk.attn
         flags = nv.GEMM_FLAG_CTA_PAIR if self.use_cta_pair else 0
@@ -449,7 +478,12 @@ class DiTEngine:
                   dict(a=ht, w=wq_t, bias=bq_t, out=ws.q[:T], out_k=ws.k[:T], out_v=ws.v[:T], norm_q_w=a.norm_added_q.weight,
                        norm_k_w=a.norm_added_k.weight, rope=rope[:T])], 3 * D, D, nv.EPI_QKV_NORM_ROPE, flags)
         nat.tag = "attention"
-        nat.attention(ws.q, ws.k, ws.v, ws.att, NUM_HEADS, 1.0 / math.sqrt(HEAD_DIM), self.attn_flags)
+        if attn_mask is not None:
+            self.masked_attention(ws.q, ws.k, ws.v, ws.att, attn_mask)
+        elif fp8_attention:
+            self.fp8_attention(ws.q, ws.k, ws.v, ws.att)
+        else:
+            nat.attention(ws.q, ws.k, ws.v, ws.att, NUM_HEADS, 1.0 / math.sqrt(HEAD_DIM), self.attn_flags)
         # output projections + gate * o + residual (in place on x)
         nat.tag = "gemm_out"
         nat.gemm([dict(a=ws.att[T:], w=a.to_out[0].weight, bias=a.to_out[0].bias, out=xi, gate=mi[2 * D:3 * D]),
@@ -466,19 +500,83 @@ class DiTEngine:
         nat.gemm([dict(a=ws.h[T:], w=im[2].weight, bias=im[2].bias, out=xi, gate=mi[5 * D:6 * D]),
                   dict(a=ws.h[:T], w=tm[2].weight, bias=tm[2].bias, out=xt, gate=mt[5 * D:6 * D])], D, 4 * D, nv.EPI_GATE_RESIDUAL, flags)
 
+    MASKED_ATTN_SCRATCH_BYTES = 12 << 30
+
+    def masked_attention(self, q, k, v, o, mask_u8) -> None:
+        """Joint attention under an arbitrary key mask (EliGen: `F.scaled_dot_product_attention(q, k, v, attn_mask=...)`, qwen_image_dit.py:36
+        with the 0 / -inf mask of process_entity_masks :433-498).  The flash kernel has no mask input, so this option takes the materialised
+        route, batched over heads: scores = Q K^T (tcgen05 GEMM, fp32 epilogue) -> masked row softmax -> O = P V (GEMM).  HBM-bound
+        (12 bytes per score element) -- EliGen is not on the PhysicEdit path; correctness first."""
+        nat = self.nat
+        S, H, D = q.shape[0], NUM_HEADS, HEAD_DIM
+        Sp = (S + 7) // 8 * 8
+        dev = q.device
+
+        def head_major(t):
+            out = torch.zeros(H, Sp, D, dtype=torch.bfloat16, device=dev) if Sp != S else torch.empty(H, S, D, dtype=torch.bfloat16, device=dev)
+            out[:, :S].copy_(t.view(S, H, D).transpose(0, 1))
+            return out
+        qh, kh = head_major(q), head_major(k)
+        vt = head_major(v).transpose(1, 2).contiguous()                       # [H, 128, Sp]
+        oh = torch.empty(H, Sp, D, dtype=torch.bfloat16, device=dev)
+        hc = max(1, min(H, self.MASKED_ATTN_SCRATCH_BYTES // (6 * Sp * Sp)))
+        scores = torch.empty(hc * Sp, Sp, dtype=torch.float32, device=dev)
+        probs = torch.empty(hc * Sp, Sp, dtype=torch.bfloat16, device=dev)
+        if mask_u8.shape[0] != Sp:                                            # pad rows (never stored) so that row r -> mask row r % Sp
+            m = torch.ones(Sp, mask_u8.shape[1], dtype=torch.uint8, device=dev)
+            m[:S] = mask_u8
+            mask_u8 = m
+        flat = lambda t, h0, n: t[h0:h0 + n].reshape(n * t.shape[1], t.shape[2])
+        for h0 in range(0, H, hc):
+            n = min(hc, H - h0)
+            kw = dict(batch=n, M=S, a_batch_rows=Sp, out_batch_rows=Sp)
+            nat.gemm_batched(flat(qh, h0, n), flat(kh, h0, n), scores, N=Sp, K=D, w_batch_rows=Sp, epilogue=nv.EPI_F32, **kw)
+            nat.softmax_rows(scores[:n * Sp], probs[:n * Sp], S, 1.0 / math.sqrt(D), mask=mask_u8)
+            nat.gemm_batched(probs, flat(vt, h0, n), flat(oh, h0, n), N=D, K=Sp, w_batch_rows=D, **kw)
+        o.view(S, H, D).copy_(oh[:, :S].transpose(0, 1))
+
+    def fp8_attention(self, q, k, v, o) -> None:
+        """`enable_fp8_attention` (qwen_image_dit.py:24-35; only taken when FlashAttention-3 is installed, otherwise the reference silently runs
+        the bf16 SDPA): q / k / v divided by their standard deviation and rounded to float8_e4m3fn, softmax scale q_std k_std / sqrt(d), output
+        times v_std.  Here the e4m3 VALUES are fed to the bf16 tensor-core kernel (every e4m3 number is a bf16 number), so Q K^T and the softmax
+        see exactly the quantised operands; P stays bf16 where FA3 rounds it to e4m3 as well.  The quantisation glue is torch ops (a non-default
+        option); FA3 is absent here, so this branch is "parity unpinned"."""
+        qs, ks, vs = q.std(), k.std(), v.std()
+        f8 = lambda t, s_: (t / s_).to(torch.float8_e4m3fn).to(torch.bfloat16)
+        scale = float(qs * ks) / math.sqrt(HEAD_DIM)
+        self.nat.attention(f8(q, qs), f8(k, ks), f8(v, vs), o, NUM_HEADS, scale, self.attn_flags)
+        o.mul_(vs)
+
+    def rope_segments(self, img_shapes: Sequence[Tuple[int, int, int]], seg_lens: Sequence[int]) -> torch.Tensor:
+        """(cos, sin) table for a text stream made of several prompts (EliGen, :441-446): every prompt's positions start at the same index."""
+        key = (tuple(tuple(s) for s in img_shapes), tuple(int(x) for x in seg_lens), "segments")
+        if key not in self._rope:
+            pe = self.dit.pos_embed
+            vid, _ = pe.forward(list(img_shapes), [max(seg_lens)], device=None)
+            txt = [pe.forward(list(img_shapes), [int(n)], device=None)[1] for n in seg_lens]
+            joint = torch.cat(txt + [vid], dim=0).to(torch.complex64)
+            self._rope[key] = torch.view_as_real(joint).contiguous().to(self.device)
+        return self._rope[key]
+
     def forward(self, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
-                out_latents: torch.Tensor, t_key: Optional[float] = None, branch: int = 0) -> torch.Tensor:
+                out_latents: torch.Tensor, t_key: Optional[float] = None, branch: int = 0, rope_sampling: bool = False,
+                after_block=None, text_segments: Optional[Sequence[int]] = None, attn_mask: Optional[torch.Tensor] = None,
+                fp8_attention: bool = False) -> torch.Tensor:
         """latents_list: [noise latents, edit/context latents ...] each [1,16,h8,w8] bf16; prompt_emb [T,3584] bf16
-        (already updated by the adapter).  Writes the velocity for the first entry into out_latents [1,16,h8,w8]."""
+        (already updated by the adapter).  Writes the velocity for the first entry into out_latents [1,16,h8,w8].
+        `after_block(i, noise_tokens [n0, 3072])` may update the noise-image tokens in place after block i (blockwise controlnet, :1389-1396)."""
         if self.sp is not None:
+            if after_block is not None or attn_mask is not None or fp8_attention:
+                raise NotImplementedError("blockwise controlnet / EliGen masks / fp8 attention are not wired into the sequence-parallel mode")
             from .ulysses import forward_sp
-            return forward_sp(self, self.sp, latents_list, timestep_bf16, prompt_emb, out_latents, t_key)
+            return forward_sp(self, self.sp, latents_list, timestep_bf16, prompt_emb, out_latents, t_key, rope_sampling=rope_sampling)
         nat, dit = self.nat, self.dit
         T = prompt_emb.shape[0]
         shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]
         S_img = sum(h * w for _, h, w in shapes)
         ws = self.workspace(S_img, T, branch)
-        rope = self.rope(shapes, T)
+        # EliGen: prompt_emb holds [entity prompts ..., global prompt] back to back (text_segments = their lengths), each with its own positions
+        rope = self.rope(shapes, T, rope_sampling) if text_segments is None else self.rope_segments(shapes, text_segments)
         temb, mods, out_mod = self.conditioning(timestep_bf16, t_key)
         # patchify + img_in
         off = 0
@@ -489,10 +587,12 @@ class DiTEngine:
         # txt_norm + txt_in
         nat.rmsnorm(prompt_emb, ws.txt_n, dit.txt_norm.weight, dit.txt_norm.eps)
         nat.gemm([dict(a=ws.txt_n, w=dit.txt_in.weight, bias=dit.txt_in.bias, out=ws.x[:T])], DIM, 3584, nv.EPI_BIAS)
-        for i in range(len(dit.transformer_blocks)):
-            self.run_block(i, ws.x, T, mods[i], rope, ws)
-        # norm_out + proj_out on the noise tokens only (the reference slices after computing all image rows)
         n0 = shapes[0][1] * shapes[0][2]
+        for i in range(len(dit.transformer_blocks)):
+            self.run_block(i, ws.x, T, mods[i], rope, ws, attn_mask, fp8_attention)
+            if after_block is not None:
+                after_block(i, ws.x[T:T + n0])
+        # norm_out + proj_out on the noise tokens only (the reference slices after computing all image rows)
         nat.layernorm_modulate(ws.x[T:T + n0], ws.xhat[:n0], out_mod[0, DIM:], out_mod[0, :DIM])
         nat.gemm([dict(a=ws.xhat[:n0], w=dit.proj_out.weight, bias=dit.proj_out.bias, out=ws.out_tok[:n0])], 64, DIM, nv.EPI_BIAS)
         nat.unpatchify(ws.out_tok[:n0], out_latents.reshape(16, out_latents.shape[-2], out_latents.shape[-1]))

@@ -64,9 +64,6 @@ def model_fn_qwen_image(
     n_special: Optional[int] = None,
     **kwargs,
 ):
-    if entity_prompt_emb is not None or blockwise_controlnet_conditioning is not None or edit_rope_interpolation or enable_fp8_attention:
-        raise NotImplementedError("EliGen entity control, blockwise controlnet, edit_rope_interpolation and fp8 attention are outside "
-                                  "the PhysicEdit hot path (SURVEY.md 8f5): no PhysicEdit script enables them")
     if latents.shape[0] != 1 or prompt_emb.shape[0] != 1:
         raise ValueError("the pipeline is strictly batch 1 (qwen_image_physical.py:688,821); batch edits shard one image per GPU")
     if not (latents.is_cuda and latents.dtype == torch.bfloat16 and prompt_emb.dtype == torch.bfloat16):
@@ -88,10 +85,14 @@ def model_fn_qwen_image(
     if not pe2d.is_contiguous():
         raise ValueError("prompt_emb must be contiguous: it is updated in place")
     from . import autograd as ag
-    if getattr(dit, "_lora_injected", False) or prompt_emb.requires_grad or ag.needs_grad(dit, visual_thinking_adapter):
-        # training: un-merged LoRA and / or trainable adapters -> the differentiable path on the same GEMM / attention kernels
+    if getattr(dit, "_lora_injected", False) or (torch.is_grad_enabled() and is_train and
+                                                  (prompt_emb.requires_grad or ag.needs_grad(dit, visual_thinking_adapter))):
+        # training: un-merged LoRA, or a training call (is_train, grad mode on) with trainable parameters on the path -> the
+        # differentiable path on the same GEMM / attention kernels.  Inference calls (is_train=False, or under no_grad) stay on the engine.
+        if blockwise_controlnet_conditioning is not None or entity_prompt_emb is not None or enable_fp8_attention:
+            raise NotImplementedError("blockwise controlnet / EliGen / fp8 attention under autograd are not part of the PhysicEdit training path")
         return _model_fn_autograd(dit, visual_thinking_adapter, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents,
-                                  use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae)
+                                  use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae, bool(edit_rope_interpolation))
 
     special_token_loss = 0
     if special_token_mask is not None:
@@ -116,12 +117,56 @@ def model_fn_qwen_image(
     lat_list = [l.contiguous() for l in lat_list]
     if out is None:
         out = torch.empty_like(latents)
-    eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host, branch=cfg_branch)
+    text_segments, attn_mask = None, None
+    if entity_prompt_emb is not None:
+        # EliGen (:1360-1364; QwenImageDiT.process_entity_masks, qwen_image_dit.py:433-498): the text stream becomes [entity prompts ..., global
+        # prompt], every prompt with its own positions, under a mask that ties each entity prompt to its image region
+        ents = [e[0] for e in entity_prompt_emb]
+        if entity_prompt_emb_mask is not None and any(int(m.shape[1]) != e.shape[0] for m, e in zip(entity_prompt_emb_mask, ents)):
+            raise ValueError("entity prompt masks must match their embeddings (batch 1: unpadded)")
+        text_segments = [int(e.shape[0]) for e in ents] + [T]
+        attn_mask = entity_attention_mask(entity_masks, text_segments, lat_list)
+        pe2d = torch.cat(ents + [pe2d], dim=0).contiguous()
+    after_block = None
+    if blockwise_controlnet_conditioning is not None:
+        # :1372-1374, :1389-1396: control latents -> tokens -> img_in once per forward; after every block the noise tokens get the scaled sum
+        conds = blockwise_controlnet.preprocess(blockwise_controlnet_inputs, blockwise_controlnet_conditioning)
+
+        def after_block(block_id, noise_tokens):
+            blockwise_controlnet.apply_(noise_tokens, conds, blockwise_controlnet_inputs, progress_id, num_inference_steps, block_id)
+    eng.forward(lat_list, t_bf16, pe2d, out, t_key=timestep_host, branch=cfg_branch, rope_sampling=bool(edit_rope_interpolation), after_block=after_block,
+                text_segments=text_segments, attn_mask=attn_mask, fp8_attention=bool(enable_fp8_attention) and attn_mask is None)
     return out, special_token_loss
 
 
+def entity_attention_mask(entity_masks: torch.Tensor, text_segments, lat_list) -> torch.Tensor:
+    """The boolean form (uint8, 1 = visible) of process_entity_masks' attention mask (qwen_image_dit.py:447-496) in the joint [text; image] order:
+    entity prompt i sees, and is seen by, the image tokens whose 2 x 2 latent patch touches entity mask i -- in EVERY image of the sequence (the
+    mask is repeated over the edit images, which therefore must have the noise image's token count); the global prompt sees everything; different
+    prompts never see each other.  entity_masks [1, N, 1, h8, w8] (what QwenImageUnit_EntityControl produces)."""
+    dev = entity_masks.device
+    n0 = (lat_list[0].shape[-2] // 2) * (lat_list[0].shape[-1] // 2)
+    S_img = sum((l.shape[-2] // 2) * (l.shape[-1] // 2) for l in lat_list)
+    if S_img % n0:
+        raise ValueError("EliGen needs edit / context images with the noise image's latent size (the reference repeats the entity mask over them)")
+    N = entity_masks.shape[1] + 1
+    if len(text_segments) != N:
+        raise ValueError(f"{N - 1} entity masks for {len(text_segments) - 1} entity prompts")
+    patched = torch.nn.functional.max_pool2d(entity_masks[0, :, 0].float().unsqueeze(0), 2)[0].flatten(1) > 0       # [N - 1, n0]
+    patched = torch.cat([patched, torch.ones(1, n0, dtype=torch.bool, device=dev)], dim=0).repeat(1, S_img // n0)     # + the global prompt
+    T_all = sum(text_segments)
+    S = T_all + S_img
+    seg_of_row = torch.repeat_interleave(torch.arange(N, device=dev), torch.tensor(text_segments, device=dev))        # [T_all]
+    mask = torch.ones(S, S, dtype=torch.uint8, device=dev)
+    txt_img = patched[seg_of_row].to(torch.uint8)                                                                     # [T_all, S_img]
+    mask[:T_all, T_all:] = txt_img
+    mask[T_all:, :T_all] = txt_img.t()
+    mask[:T_all, :T_all] = (seg_of_row[:, None] == seg_of_row[None, :]).to(torch.uint8)
+    return mask
+
+
 def _model_fn_autograd(dit, ad, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents, use_gradient_checkpointing,
-                       is_train, pseudo_special_emb_dino, pseudo_special_emb_vae):
+                       is_train, pseudo_special_emb_dino, pseudo_special_emb_vae, rope_sampling=False):
     """:1331-1403 under autograd (physicedit_b200/autograd.py): same in-place write of the adapter output into `prompt_emb` (:1336), same
     `(latents, special_token_loss)` return; gradients reach the LoRA factors, the adapter heads and whatever produced the pseudo targets."""
     from . import autograd as ag
@@ -137,5 +182,6 @@ def _model_fn_autograd(dit, ad, latents, timestep, t_bf16, prompt_emb, special_t
         lat_list.append(context_latents)
     if edit_latents is not None:
         lat_list += list(edit_latents) if isinstance(edit_latents, list) else [edit_latents]
-    out = ag.dit_forward(dit, [l.contiguous() for l in lat_list], t_bf16, prompt_emb, use_gradient_checkpointing=use_gradient_checkpointing)
+    out = ag.dit_forward(dit, [l.contiguous() for l in lat_list], t_bf16, prompt_emb, use_gradient_checkpointing=use_gradient_checkpointing,
+                         rope_sampling=rope_sampling)
     return out, special_token_loss

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
+    "pe_softmax_rows", "pe_softmax_rows_masked", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -119,6 +119,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_softmax_rows_masked.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_int, c_void_p]
     lib.pe_gemm_batched.argtypes = [c_void_p, POINTER(GemmSeg), POINTER(GemmBatch), c_int, c_int, c_int, c_int, c_void_p]
     lib.pe_attention_fwd_lse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p, c_void_p]
     lib.pe_attention_bwd_delta.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]
@@ -433,11 +434,20 @@ class Native:
                                           self._stream_prof()), "pe_transpose")
         self.launches += 1
 
-    def softmax_rows(self, scores, probs, n: int, scale: float) -> None:
-        """probs[:, :n] = softmax(scale * scores[:, :n]); probs[:, n:] = 0.  scores fp32 [rows, >=n], probs bf16 [rows, n_pad]."""
+    def softmax_rows(self, scores, probs, n: int, scale: float, mask=None) -> None:
+        """probs[:, :n] = softmax(scale * scores[:, :n]); probs[:, n:] = 0.  scores fp32 [rows, >=n], probs bf16 [rows, n_pad].
+        mask (optional): uint8 [period, >= n], 0 = key hidden; score row r uses mask row r % period."""
         _bf16(probs, "probs")
         if scores.dtype != torch.float32 or not scores.is_cuda or scores.stride(-1) != 1 or scores.shape[0] != probs.shape[0]:
             raise NativeError("softmax_rows: scores must be CUDA float32 [rows, >=n] with as many rows as probs")
+        if mask is not None:
+            if mask.dtype != torch.uint8 or not mask.is_cuda or mask.stride(-1) != 1 or mask.shape[1] < n:
+                raise NativeError("softmax_rows: mask must be CUDA uint8 [period, >= n]")
+            self._check(self.lib.pe_softmax_rows_masked(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
+                                                        n, probs.shape[1], scale, mask.data_ptr(), mask.stride(0), mask.shape[0], self._stream_prof()),
+                        "pe_softmax_rows_masked")
+            self.launches += 1
+            return
         self._check(self.lib.pe_softmax_rows(self.h, scores.data_ptr(), scores.stride(0), probs.data_ptr(), probs.stride(0), scores.shape[0],
                                              n, probs.shape[1], scale, self._stream_prof()), "pe_softmax_rows")
         self.launches += 1

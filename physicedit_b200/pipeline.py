@@ -317,10 +317,12 @@ class QwenImagePhysicPipeline(nn.Module):
     @torch.no_grad()
     def denoise(self, latents, inputs_posi: dict, inputs_nega: Optional[dict], edit_latents=None, context_latents=None, *, height: int,
                 width: int, num_inference_steps: int = 30, cfg_scale: float = 4.0, denoising_strength: float = 1.0,
-                exponential_shift_mu=None, progress_bar_cmd=None, timesteps_device: Optional[torch.Tensor] = None):
+                exponential_shift_mu=None, progress_bar_cmd=None, timesteps_device: Optional[torch.Tensor] = None,
+                model_kwargs: Optional[dict] = None):
         """Lines 600 and 646-661 of the reference __call__: set_timesteps, then per step two model_fn forwards
         (posi / nega, each with its own persistently-mutated prompt_emb), CFG combine and the Euler update
-        (one fused kernel).  inputs_*: dicts with prompt_emb [1,T,3584], prompt_emb_mask, special_token_mask."""
+        (one fused kernel).  inputs_*: dicts with prompt_emb [1,T,3584], prompt_emb_mask, special_token_mask.
+        `model_kwargs`: further shared model_fn arguments (edit_rope_interpolation, blockwise_controlnet_conditioning / _inputs, ...)."""
         self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength,
                                      dynamic_shift_len=(height // 16) * (width // 16), exponential_shift_mu=exponential_shift_mu)
         nat = nv.Native.get(latents.device.index or 0)
@@ -342,7 +344,10 @@ class QwenImagePhysicPipeline(nn.Module):
             t_host = float(t.to(self.torch_dtype))
             kw = dict(dit=self.dit, visual_thinking_adapter=self.visual_thinking_adapter, latents=latents, timestep=ts_dev[progress_id:progress_id + 1],
                       height=height, width=width, edit_latents=edit_latents, context_latents=context_latents, is_train=False,
-                      progress_id=progress_id, timestep_host=t_host)
+                      progress_id=progress_id, timestep_host=t_host, num_inference_steps=num_inference_steps,
+                      blockwise_controlnet=getattr(self, "blockwise_controlnet", None))
+            if model_kwargs:
+                kw.update(model_kwargs)
             self.run_cfg_branches(kw, inputs_posi, inputs_nega, vp, vn, ts_dev[progress_id:progress_id + 1], t_host)
             ds = float(self.scheduler.dsigma(t))
             nat.cfg_euler_step(latents, vp, vn if use_cfg else None, float(cfg_scale), ds)
@@ -482,15 +487,22 @@ class QwenImagePhysicPipeline(nn.Module):
         if "prompt_emb" not in inputs_posi:
             raise RuntimeError("no prompt embedding: load the Qwen2.5-VL text encoder (from_pretrained / load_text_encoder) together with the "
                                "tokenizer and processor, or pass prompt_inputs_posi / prompt_inputs_nega (prompt_emb, prompt_emb_mask, special_token_mask)")
-        if any(inputs_posi.get(k) is not None for k in ("entity_prompt_emb",)) or inputs_shared.get("blockwise_controlnet_conditioning"):
-            raise NotImplementedError("EliGen entity control / blockwise controlnet reach model_fn, which does not implement them (SURVEY 8f5)")
+        model_kwargs = {"edit_rope_interpolation": bool(edit_rope_interpolation), "enable_fp8_attention": bool(enable_fp8_attention)}
+        if inputs_shared.get("blockwise_controlnet_conditioning"):
+            if self.blockwise_controlnet is None:
+                raise RuntimeError("blockwise_controlnet_inputs were given but pipe.blockwise_controlnet is not loaded")
+            model_kwargs.update(blockwise_controlnet_conditioning=inputs_shared["blockwise_controlnet_conditioning"],
+                                blockwise_controlnet_inputs=inputs_shared["blockwise_controlnet_inputs"])
         height, width = inputs_shared["height"], inputs_shared["width"]
         keys = ("prompt_emb", "prompt_emb_mask", "special_token_mask")
-        posi = {k: inputs_posi.get(k) for k in keys}
-        nega = {k: inputs_nega.get(k) for k in keys} if (cfg_scale != 1.0 and "prompt_emb" in inputs_nega) else None
+        ent = ("entity_prompt_emb", "entity_prompt_emb_mask", "entity_masks")                 # EliGen (QwenImageUnit_EntityControl), per branch
+        pick = lambda d: dict({k: d.get(k) for k in keys}, **{k: d[k] for k in ent if d.get(k) is not None})
+        posi = pick(inputs_posi)
+        nega = pick(inputs_nega) if (cfg_scale != 1.0 and "prompt_emb" in inputs_nega) else None
         latents = self.denoise(inputs_shared["latents"], posi, nega, inputs_shared.get("edit_latents"), inputs_shared.get("context_latents"),
                                height=height, width=width, num_inference_steps=num_inference_steps, cfg_scale=cfg_scale,
-                               denoising_strength=denoising_strength, exponential_shift_mu=exponential_shift_mu, progress_bar_cmd=progress_bar_cmd)
+                               denoising_strength=denoising_strength, exponential_shift_mu=exponential_shift_mu, progress_bar_cmd=progress_bar_cmd,
+                               model_kwargs=model_kwargs)
         if output_type == "latent" or self.vae is None:
             return latents
         image = self.vae.decode(latents, device=self.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)
@@ -505,8 +517,8 @@ class QwenImagePhysicPipeline(nn.Module):
         pseudo_special_emb_dino / pseudo_special_emb_vae [1,64,3584]."""
         nat = nv.Native.get(dino_middle.device.index or 0)
         from . import autograd as ag
-        if ag.needs_grad(self.dino_time_embed, self.dino_resampler, self.dino_resampler_adapter, self.vae_time_embed, self.vae_resampler,
-                         self.vae_resampler_adapter):
+        stack = (self.dino_time_embed, self.dino_resampler, self.dino_resampler_adapter, self.vae_time_embed, self.vae_resampler, self.vae_resampler_adapter)
+        if ag.needs_grad(*stack) and any(m.training for m in stack):
             return self._physical_visual_embeddings_autograd(dino_middle, dino_source, vae_middle_latents, vae_source_latents)
 
         def dino_branch(px, with_time):

@@ -153,14 +153,14 @@ def run_block_sp(eng, ctx: UlyssesContext, ws: UlyssesWorkspace, i: int, mods: t
 
 
 def forward_sp(eng, ctx: UlyssesContext, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
-               out_latents: torch.Tensor, t_key: Optional[float] = None) -> torch.Tensor:
+               out_latents: torch.Tensor, t_key: Optional[float] = None, rope_sampling: bool = False) -> torch.Tensor:
     """DiTEngine.forward across the group: same arguments on every rank, the full velocity on every rank."""
     nat, dit = eng.nat, eng.dit
     T = prompt_emb.shape[0]
     shapes = [(1, l.shape[-2] // 2, l.shape[-1] // 2) for l in latents_list]
     S_img = sum(h * w for _, h, w in shapes)
     ws = ctx.workspace(S_img, T)
-    rope = eng.rope(shapes, T)
+    rope = eng.rope(shapes, T, rope_sampling)
     temb, mods, out_mod = eng.conditioning(timestep_bf16, t_key)
     off = 0
     for l, (_, h, w) in zip(latents_list, shapes):

@@ -213,3 +213,46 @@ def test_aux_training_path_oracle_matches_reference(golden):
         assert ed.shape == ev.shape == (1, 64, 3584)
         assert rel_l2(ed[..., ::8], g["pseudo_special_emb_dino"]) < 5e-5
         assert rel_l2(ev[..., ::8], g["pseudo_special_emb_vae"]) < 5e-5
+
+
+def test_rope_sampling_tables_bit_exact(golden):
+    """edit_rope_interpolation (QwenEmbedRope.forward_sampling, qwen_image_dit.py:168-225): oracle and the product's host code vs the reference."""
+    from physicedit_b200.dit import QwenEmbedRope
+    for key, c in golden("f5")["rope_sampling"].items():
+        shapes = [tuple(s) for s in c["shapes"]]
+        vid, txt = O.rope_tables(shapes, c["T"], sampling=True)
+        assert vid.shape[0] == c["n_vid"] and torch.equal(vid[c["vid_idx"]], c["vid"]) and torch.equal(txt, c["txt"]), key
+        pe = QwenEmbedRope(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+        v2, t2 = pe.forward_sampling(shapes, [c["T"]])
+        assert torch.equal(v2[c["vid_idx"]], c["vid"]) and torch.equal(t2, c["txt"]), key
+        # the plain tables differ whenever an edit image has another size than the noise image
+        v3, _ = QwenEmbedRope(theta=10000, axes_dim=[16, 56, 56], scale_rope=True).forward(shapes, [c["T"]])
+        assert torch.equal(v3, v2) == all(s[1:] == shapes[0][1:] for s in shapes[1:]), key
+
+
+def test_controlnet_oracle_matches_reference(golden):
+    """oracle.controlnet_* vs the reference's QwenImageBlockWiseControlNet / QwenImageBlockwiseMultiControlNet (fp32 near-exact, bf16 bit-exact)."""
+    g = golden("f5")["controlnet"]
+    meta = g["meta"]
+    for dtype in (torch.float32, torch.bfloat16):
+        nets = [dict(weights={k: v.to(dtype) for k, v in O.synth_weights(O.controlnet_param_shapes(meta["L"]), seed=s).items()}, latents=l.to(dtype), **kw)
+                for s, l, kw in zip(meta["seeds"], meta["latents"], (dict(scale=1.0, start=1.0, end=0.0), dict(scale=0.5, start=0.8, end=0.3)))]
+        conds = [O.controlnet_img_in(c["weights"], O.patchify(c["latents"])) for c in nets]
+        ref = g[str(dtype)]
+        tol = dict(rtol=0, atol=0) if dtype == torch.bfloat16 else dict(rtol=1e-5, atol=1e-5)
+        assert torch.allclose(conds[0][:, :, ::meta["stride"]], ref["cond0"], **tol)
+        for (pid, blk), want in ref["res"].items():
+            got = O.controlnet_sum(nets, conds, meta["x"].to(dtype), blk, pid, 5)
+            assert torch.allclose(got[:, :, ::meta["stride"]], want, **tol), (dtype, pid, blk)
+
+
+def test_eligen_oracle_matches_reference(golden):
+    """oracle.process_entity_masks + masked attention inside model_fn vs the reference's model_fn_qwen_image with entity prompts / masks (fp32)."""
+    g = golden("f5")["eligen"]
+    m = g["meta"]
+    W = O.synth_weights(O.dit_param_shapes(1), seed=m["w_seed"])
+    inp = O.synth_inputs(m["H"], m["W"], m["T"], seed=m["in_seed"], dtype=torch.float32, n_special=m["n_special"])
+    y = O.model_fn(W, None, inp["latents"], torch.tensor([m["t"]]), inp["prompt_emb"].clone(), inp["prompt_emb_mask"], None, m["H"], m["W"],
+                   edit_latents=inp["edit_latents"], entity=dict(prompt_emb=g["entity_prompt_emb"], masks=g["entity_masks"]))
+    assert g["differs_from_plain"] > 1e-3
+    assert ((y - g["y"]).norm() / g["y"].norm()).item() < 2e-5
