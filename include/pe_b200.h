@@ -318,6 +318,11 @@ int pe_attention_bwd_delta(pe_handle_t h, const void* d_o, int64_t ldd, const vo
  * Same arithmetic and rounding points as pe_rmsnorm / pe_swiglu / pe_gemv / pe_add_rows run one after the other. */
 int pe_gemv_fused(pe_handle_t h, const void* x, const void* w, const void* bias, void* y, int batch, int N, int K, int act_in,
                   const void* norm_w, float norm_eps, const void* residual, void* stream);
+/* The gate / up projections of the decode step and act_fn(gate) * up in ONE launch (Qwen2MLP.forward modeling_qwen2_5_vl.py:622-624): w = [gate_proj
+ * rows | up_proj rows] [2 I, K], x [batch, K] with the optional RMSNorm prologue of pe_gemv_fused, y[b, i] = bf16(bf16(silu(bf16(g_i))) * bf16(u_i)),
+ * [batch, I].  Bit-identical to pe_gemv_fused into a gate|up buffer followed by pe_swiglu; the down-projection then needs no SwiGLU prologue. */
+int pe_gemv_swiglu(pe_handle_t h, const void* x, const void* w, const void* bias, void* y, int batch, int I, int K, const void* norm_w, float norm_eps,
+                   void* stream);
 /* out[r, i] = bf16(bf16(silu(x[r, i])) * x[r, I + i]): act_fn(gate_proj(x)) * up_proj(x) on a fused [rows, 2I] gate|up buffer
  * (Qwen2MLP.forward modeling_qwen2_5_vl.py:622-624, Qwen2_5_VLMLP.forward :87-88). */
 int pe_swiglu(pe_handle_t h, const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int I, void* stream);

@@ -64,15 +64,36 @@ def _transposed(nat: nv.Native, x2: torch.Tensor, extra_rows: int = 0, ones_row:
 
 
 class _WeightTransposes:
-    """W^T of FROZEN weights for the dX GEMMs, keyed by storage address + version (an in-place LoRA fold bumps the version)."""
+    """W^T of FROZEN weights for the dX GEMMs, keyed by storage address + version (an in-place LoRA fold bumps the version).  An address alone
+    can be recycled by the allocator for a different tensor, so the forward registers the live weight object: when that object dies its entry
+    is dropped by a weakref finalizer before any new tensor can appear at the address."""
 
     def __init__(self, cap_bytes: int = 48 << 30):
-        self.cap, self.used, self.d = cap_bytes, 0, {}
+        self.cap, self.used, self.d, self.owners = cap_bytes, 0, {}, {}
+
+    @staticmethod
+    def _key(w: torch.Tensor):
+        return (w.data_ptr(), w._version, tuple(w.shape))
+
+    def register(self, w: torch.Tensor) -> None:
+        """Called in the forward with the weight object itself (a module parameter)."""
+        if w.requires_grad:
+            return
+        key = self._key(w)
+        if key not in self.owners:
+            import weakref
+            self.owners[key] = weakref.ref(w, lambda _ref, key=key: self._drop(key))
+
+    def _drop(self, key) -> None:
+        self.owners.pop(key, None)
+        t = self.d.pop(key, None)
+        if t is not None:
+            self.used -= t.numel() * 2
 
     def get(self, nat: nv.Native, w: torch.Tensor) -> torch.Tensor:
-        if w.requires_grad:
+        key = self._key(w)
+        if w.requires_grad or key not in self.owners:          # trainable, or an unregistered temporary: never cached
             return _transposed(nat, w)
-        key = (w.data_ptr(), w._version, tuple(w.shape))
         t = self.d.get(key)
         if t is None:
             t = _transposed(nat, w)
@@ -83,6 +104,7 @@ class _WeightTransposes:
 
     def clear(self):
         self.d.clear()
+        self.owners.clear()
         self.used = 0
 
 
@@ -103,6 +125,8 @@ class _LinearFn(torch.autograd.Function):
         nat = _nat(x)
         x2 = _rows(x)
         wc = w if w.is_contiguous() else w.contiguous()
+        if wc is w and isinstance(w, torch.nn.Parameter):
+            weight_transposes.register(w)
         y = _gemm(nat, x2, wc, b)
         ctx.save_for_backward(x2, wc)
         ctx.has_bias, ctx.in_shape = b is not None, x.shape

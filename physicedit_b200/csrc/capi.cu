@@ -270,6 +270,13 @@ int pe_gemv_fused(pe_handle_t hh, const void* x, const void* w, const void* bias
     return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, 0, nullptr, static_cast<cudaStream_t>(stream), norm_w, norm_eps, residual);
 }
 
+int pe_gemv_swiglu(pe_handle_t hh, const void* x, const void* w, const void* bias, void* y, int batch, int I, int K, const void* norm_w, float norm_eps,
+                   void* stream) {
+    PE_H(hh);
+    PE_REQUIRE(h, I > 0, "pe_gemv_swiglu: I must be positive");
+    return pe::gemv_run(h, x, w, bias, y, batch, 2 * I, K, 0, 2, nullptr, static_cast<cudaStream_t>(stream), norm_w, norm_eps, nullptr);
+}
+
 int pe_act(pe_handle_t hh, const void* x, void* y, int64_t n, int act, void* stream) {
     PE_H(hh);
     return pe::act_run(h, x, y, (long long)n, act, static_cast<cudaStream_t>(stream));

@@ -5,6 +5,7 @@
 // input byte is read exactly once.  bf16 rounding points follow the reference op by op
 //  so results are comparable with the reference's bf16 tensors.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "ptx.cuh"
 #include "common.cuh"
 
@@ -373,12 +374,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
     }
     const int lane = threadIdx.x & 31;
     const int nvec = K >> 3;
-    const int ngroups = (N + kRows - 1) / kRows;
+    // act_out 2 (pe_gemv_swiglu): w = [gate rows | up rows] (N = 2 I); a warp takes kRows / 2 gate rows and THEIR up rows, so that
+    // y[b, i] = bf16(bf16(silu(gate_i)) * up_i) leaves this kernel and the down-projection needs no SwiGLU prologue
+    const bool pair = act_out == 2 && kRows >= 2;
+    const int half = N >> 1;
+    const int rows_per_group = pair ? kRows / 2 : kRows;
+    const int ngroups = ((pair ? half : N) + rows_per_group - 1) / rows_per_group;
     for (int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * kWarpsPerCta) {
-        const int n0 = g * kRows;
+        const int n0 = g * rows_per_group;
         const bf16* wr[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) wr[r] = w + (size_t)min(n0 + r, N - 1) * K;     // rows past N repeat the last row (not stored)
+        for (int r = 0; r < kRows; ++r) {
+            const int row = pair ? (r < kRows / 2 ? min(n0 + r, half - 1) : half + min(n0 + r - kRows / 2, half - 1)) : min(n0 + r, N - 1);
+            wr[r] = w + (size_t)row * K;                                               // rows past the end repeat the last row (not stored)
+        }
         float acc[kRows][kBatch];
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
@@ -429,7 +438,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
                 const float t = warp_sum(acc[r][b]);
                 if (lane == r * kBatch + b) mine = t;
             }
-        if (lane < kRows * kBatch) {
+        if (pair) {
+            const float up = __shfl_down_sync(0xffffffffu, mine, (kRows / 2) * kBatch);      // lane (r, b) of a gate row fetches its up row's sum
+            if (lane < (kRows / 2) * kBatch) {
+                const int r = lane / kBatch, b = lane - r * kBatch;
+                const int n = n0 + r;
+                if (n < half) {
+                    const float gv = bf16_round(mine + (bias ? __bfloat162float(bias[n]) : 0.f));
+                    const float uv = bf16_round(up + (bias ? __bfloat162float(bias[half + n]) : 0.f));
+                    y[(size_t)b * half + n] = __float2bfloat16_rn(silu_bf16(gv) * uv);
+                }
+            }
+        } else if (lane < kRows * kBatch) {
             const int r = lane / kBatch, b = lane - r * kBatch;
             const int n = n0 + r;
             if (n < N) {
@@ -441,6 +461,129 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gemv_kernel(const bf16* __r
                 y[(size_t)b * N + n] = __float2bfloat16_rn(o);
             }
         }
+    }
+}
+
+// ---- split-K GEMV for long-K, narrow-N layers (the 3584 x 18944 down-projection of the Qwen2.5-VL decode step) ----------------------------
+// With the whole input staged per CTA (gemv_kernel) this shape paid 38 KB (76 KB at batch 2) of shared memory and a K-long SwiGLU prologue in every
+// one of 448 CTAs for only 8 weight rows each: 3.3 TB/s at batch 1, 2.0 TB/s at batch 2 (profiles/r02_gemv_bench.json).  Here a thread-block
+// CLUSTER of kSplitK CTAs shares a group of rows: CTA r stages (and activates) only K-slice r, every warp accumulates its rows over that slice, the
+// partial sums meet in CTA 0 through distributed shared memory in a fixed order (deterministic) and CTA 0 applies bias / residual.  Four times
+// less shared memory and prologue work per CTA, all 148 SMs streaming from the first microsecond.
+constexpr int kSplitK = 4;
+constexpr int kSplitRows = 2;      // rows per warp
+constexpr int kSplitDepth = 2;     // 16-byte vectors per row in flight per lane (plus the same again being consumed)
+
+template <int kBatch>
+__global__ void __cluster_dims__(kSplitK, 1, 1) __launch_bounds__(kWarpsPerCta * 32)
+gemv_splitk_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias, bf16* __restrict__ y, int N, int K, int act_in,
+                   const bf16* __restrict__ residual) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int kr = (int)cluster.block_rank();
+    const int Ks = K / kSplitK, k0 = kr * Ks;
+    extern __shared__ __align__(16) unsigned char xs_raw[];
+    bf16* xs = reinterpret_cast<bf16*>(xs_raw);                     // [kBatch][Ks]
+    __shared__ float part[kWarpsPerCta][kSplitRows][kBatch];
+    {
+        const int kv = Ks >> 3;
+        for (int i = threadIdx.x; i < kBatch * kv; i += blockDim.x) {
+            const int b = i / kv, j = i - b * kv;
+            uint4 val;
+            if (act_in == 2) {                                      // x = gate | up: staged value = bf16(bf16(silu(gate)) * up)
+                float g[8], u[8], f[8];
+                unpack8(*reinterpret_cast<const uint4*>(x + (size_t)b * 2 * K + k0 + j * 8), g);
+                unpack8(*reinterpret_cast<const uint4*>(x + (size_t)b * 2 * K + K + k0 + j * 8), u);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = silu_bf16(g[e]) * u[e];
+                val = pack8(f);
+            } else {
+                val = *reinterpret_cast<const uint4*>(x + (size_t)b * K + k0 + j * 8);
+                if (act_in == 1) {
+                    float f[8];
+                    unpack8(val, f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = silu_bf16(f[e]);
+                    val = pack8(f);
+                }
+            }
+            *reinterpret_cast<uint4*>(xs + b * Ks + j * 8) = val;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = Ks >> 3;
+    const int rows_per_cluster = kWarpsPerCta * kSplitRows;
+    const int ngroups = (N + rows_per_cluster - 1) / rows_per_cluster;
+    const int cluster_id = blockIdx.x / kSplitK, n_clusters = gridDim.x / kSplitK;
+    for (int g = cluster_id; g < ngroups; g += n_clusters) {          // same trip count in every CTA of a cluster
+        const int n0 = g * rows_per_cluster + warp * kSplitRows;
+        const bf16* wr[kSplitRows];
+#pragma unroll
+        for (int r = 0; r < kSplitRows; ++r) wr[r] = w + (size_t)min(n0 + r, N - 1) * K + k0;
+        float acc[kSplitRows][kBatch];
+#pragma unroll
+        for (int r = 0; r < kSplitRows; ++r)
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) acc[r][b] = 0.f;
+        uint4 u[kSplitRows][kSplitDepth], un[kSplitRows][kSplitDepth];
+#pragma unroll
+        for (int r = 0; r < kSplitRows; ++r)
+#pragma unroll
+            for (int d = 0; d < kSplitDepth; ++d) u[r][d] = (lane + 32 * d) < nvec ? ld_stream(wr[r] + (lane + 32 * d) * 8) : make_uint4(0, 0, 0, 0);
+        for (int v0 = 0; v0 < nvec; v0 += 32 * kSplitDepth) {
+#pragma unroll
+            for (int r = 0; r < kSplitRows; ++r)
+#pragma unroll
+                for (int d = 0; d < kSplitDepth; ++d) {
+                    const int vn = v0 + 32 * kSplitDepth + 32 * d + lane;
+                    un[r][d] = vn < nvec ? ld_stream(wr[r] + vn * 8) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+            for (int d = 0; d < kSplitDepth; ++d) {
+                const int vi = v0 + 32 * d + lane;
+                if (vi < nvec) {
+                    float f[kSplitRows][8];
+#pragma unroll
+                    for (int r = 0; r < kSplitRows; ++r) unpack8(u[r][d], f[r]);
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        float xv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(xs + b * Ks + vi * 8), xv);
+#pragma unroll
+                        for (int r = 0; r < kSplitRows; ++r)
+                            acc[r][b] += f[r][0] * xv[0] + f[r][1] * xv[1] + f[r][2] * xv[2] + f[r][3] * xv[3] + f[r][4] * xv[4] + f[r][5] * xv[5] +
+                                         f[r][6] * xv[6] + f[r][7] * xv[7];
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kSplitRows; ++r)
+#pragma unroll
+                for (int d = 0; d < kSplitDepth; ++d) u[r][d] = un[r][d];
+        }
+#pragma unroll
+        for (int r = 0; r < kSplitRows; ++r)
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const float t = warp_sum(acc[r][b]);
+                if (lane == 0) part[warp][r][b] = t;
+            }
+        cluster.sync();                                               // every CTA's partial sums are in its shared memory
+        if (kr == 0 && lane < kSplitRows * kBatch) {
+            const int r = lane / kBatch, b = lane - r * kBatch;
+            const int n = n0 + r;
+            if (n < N) {
+                float sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < kSplitK; ++q) sum += *cluster.map_shared_rank(&part[warp][r][b], q);      // K-slices in order
+                const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+                float o = bf16_round(sum + bv);
+                if (residual != nullptr) o += __bfloat162float(residual[(size_t)b * N + n]);
+                y[(size_t)b * N + n] = __float2bfloat16_rn(o);
+            }
+        }
+        cluster.sync();                                               // CTA 0 has read them: they may be overwritten (or the CTA may exit)
     }
 }
 
@@ -639,10 +782,27 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
     PE_REQUIRE(h, N > 0 && K > 0 && K % 8 == 0, "pe_gemv: N>0, K%%8==0 required (N=%d K=%d)", N, K);
     PE_REQUIRE(h, x && w && y, "pe_gemv: null pointer");
     PE_REQUIRE(h, (size_t)batch * K * 2 <= 200 * 1024, "pe_gemv: batch*K too large for shared memory");
+    const bf16* xb0 = static_cast<const bf16*>(x);
+    static const int split_mode = getenv("PE_GEMV_SPLITK") ? atoi(getenv("PE_GEMV_SPLITK")) : 1;            // experiments: 0 disables the split-K kernel
+    if (split_mode && batch <= 2 && norm_w == nullptr && act_out == 0 && one_plus_mask == nullptr && K >= 8192 && N <= 8192 && K % (8 * kSplitK) == 0) {
+        // long-K, narrow-N (the decode step's 3584 x 18944 down-projection): K split over a cluster of kSplitK CTAs
+        const int clusters = ceil_div(N, kWarpsPerCta * kSplitRows);
+        const size_t sm = (size_t)batch * (K / kSplitK) * sizeof(bf16);
+        const bf16* wb0 = static_cast<const bf16*>(w);
+        if (batch == 1)
+            gemv_splitk_kernel<1><<<clusters * kSplitK, kWarpsPerCta * 32, sm, s>>>(xb0, wb0, static_cast<const bf16*>(bias), static_cast<bf16*>(y), N, K, act_in,
+                                                                                   static_cast<const bf16*>(residual));
+        else
+            gemv_splitk_kernel<2><<<clusters * kSplitK, kWarpsPerCta * 32, sm, s>>>(xb0, wb0, static_cast<const bf16*>(bias), static_cast<bf16*>(y), N, K, act_in,
+                                                                                   static_cast<const bf16*>(residual));
+        PE_CHECK_CUDA(h, cudaGetLastError());
+        return PE_OK;
+    }
     const size_t smem = (size_t)batch * K * sizeof(bf16);
     // narrow outputs (fewer row groups than ~2 per warp slot of the machine): one row per warp, four loads in flight per lane
     static const int mode = getenv("PE_GEMV_MODE") ? atoi(getenv("PE_GEMV_MODE")) : 0;      // experiments: 1 forces the wide kernel, 2 the narrow one
-    const bool narrow = mode == 2 || (mode == 0 && batch <= 2 && ceil_div(N, kGemvRows) < 2 * h->sm_count * kWarpsPerCta);
+    PE_REQUIRE(h, act_out != 2 || (N % 2 == 0 && residual == nullptr && one_plus_mask == nullptr), "pe_gemv_swiglu: N = 2 I, no residual");
+    const bool narrow = act_out != 2 && (mode == 2 || (mode == 0 && batch <= 2 && ceil_div(N, kGemvRows) < 2 * h->sm_count * kWarpsPerCta));
     int grid = ceil_div(ceil_div(N, narrow ? 1 : kGemvRows), kWarpsPerCta);
     const int cap = h->sm_count * 4;
     if (grid > cap) grid = cap;

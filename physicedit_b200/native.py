@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows", "pe_softmax_rows_masked", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
+    "pe_softmax_rows", "pe_softmax_rows_masked", "pe_gemv_swiglu", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -119,6 +119,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_gemv_swiglu.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]
     lib.pe_softmax_rows_masked.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_int, c_void_p]
     lib.pe_gemm_batched.argtypes = [c_void_p, POINTER(GemmSeg), POINTER(GemmBatch), c_int, c_int, c_int, c_int, c_void_p]
     lib.pe_attention_fwd_lse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p, c_void_p]
@@ -503,6 +504,14 @@ class Native:
         batch = 1 if x.dim() == 1 else x.shape[0]
         self._check(self.lib.pe_gemv_fused(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1], act_in,
                                            _ptr(norm_w), eps, _ptr(residual), self._stream_prof()), "pe_gemv_fused")
+        self.launches += 1
+
+    def gemv_swiglu(self, x, w, bias, y, norm_w=None, eps: float = 1e-6) -> None:
+        """x [batch, K], w [2I, K] = gate rows | up rows, y [batch, I] = silu(gate) * up with the reference's rounding points; optional RMSNorm prologue."""
+        _bf16(x, "x"); _bf16(w, "w"); _bf16(y, "y")
+        batch = 1 if x.dim() == 1 else x.shape[0]
+        self._check(self.lib.pe_gemv_swiglu(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0] // 2, w.shape[1], _ptr(norm_w), eps,
+                                            self._stream_prof()), "pe_gemv_swiglu")
         self.launches += 1
 
     def swiglu(self, x, out, I: int) -> None:

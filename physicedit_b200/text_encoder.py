@@ -533,9 +533,9 @@ class QwenImageTextEncoder(nn.Module):
                     nat.tag = "te_gemv_o"
                     nat.gemv_fused(B["att"], l.self_attn.o_proj.weight, None, B["x"], residual=B["x"])
                     nat.tag = "te_gemv_gate_up"
-                    nat.gemv_fused(B["x"], pk["wgu"], None, B["gu"], norm_w=l.post_attention_layernorm.weight, eps=c.rms_eps)
+                    nat.gemv_swiglu(B["x"], pk["wgu"], None, B["hm"], norm_w=l.post_attention_layernorm.weight, eps=c.rms_eps)   # act_fn(gate) * up in the epilogue
                     nat.tag = "te_gemv_down"
-                    nat.gemv_fused(B["gu"], l.mlp.down_proj.weight, None, B["x"], act_in=2, residual=B["x"])
+                    nat.gemv_fused(B["hm"], l.mlp.down_proj.weight, None, B["x"], residual=B["x"])                                # long K: cluster split-K kernel
                     continue
                 nat.tag = "te_rmsnorm"
                 nat.rmsnorm(B["x"], B["xn"], l.input_layernorm.weight, c.rms_eps)

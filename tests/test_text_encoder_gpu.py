@@ -239,3 +239,50 @@ def test_pipeline_call_runs_the_validate_py_flow_on_the_native_text_encoder():
     print(f"\nfull flow: generate {st}")
     from physicedit_b200 import native as nv
     nv.Native.get(0).check_async()
+
+
+@gpu
+@pytest.mark.parametrize("N,K", [(3584, 18944), (1000, 8192), (24, 9600)])
+def test_split_k_gemv_for_long_rows(N, K):
+    """The decode step's down-projection shape (long K, narrow N) runs on the cluster split-K GEMV: values vs fp32 torch with the reference's
+    rounding points (SwiGLU prologue: bf16(bf16(silu(gate)) * up); epilogue: bf16(residual + bf16(acc + bias))), batch 2 == two batch-1 calls bit for
+    bit (what keeps the batched CFG-branch generation identical to one-by-one), and the same results as the whole-row kernel up to fp32 summation order."""
+    from physicedit_b200 import native as nv
+    nat = nv.Native.get(0)
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.1).bfloat16()
+    res = torch.randn(2, N, device="cuda", generator=g).bfloat16()
+    for act_in in (0, 2):
+        x = torch.randn(2, K * (2 if act_in == 2 else 1), device="cuda", generator=g).bfloat16()
+        staged = (torch.nn.functional.silu(x[:, :K]) * x[:, K:]) if act_in == 2 else x
+        want = (res.float() + (staged.float() @ w.float().t() + bias.float()).bfloat16().float()).bfloat16()
+        y2 = torch.empty(2, N, device="cuda", dtype=torch.bfloat16)
+        nat.gemv_fused(x, w, bias, y2, act_in=act_in, residual=res)
+        assert rel(y2, want) < 4e-3
+        for b in range(2):
+            y1 = torch.empty(1, N, device="cuda", dtype=torch.bfloat16)
+            nat.gemv_fused(x[b:b + 1].contiguous(), w, bias, y1, act_in=act_in, residual=res[b:b + 1].contiguous())
+            assert torch.equal(y1[0], y2[b])
+    nat.check_async()
+
+
+@gpu
+@pytest.mark.parametrize("batch", [1, 2, 5])
+def test_gate_up_gemv_with_swiglu_epilogue_equals_the_two_step_sequence(batch):
+    """pe_gemv_swiglu == pe_gemv_fused into a gate|up buffer followed by pe_swiglu, bit for bit (same dot products, same rounding points)."""
+    from physicedit_b200 import native as nv
+    nat = nv.Native.get(0)
+    g = torch.Generator(device="cuda").manual_seed(batch)
+    I, K = 18944, 3584
+    w = (torch.randn(2 * I, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    x = torch.randn(batch, K, device="cuda", generator=g).bfloat16()
+    nw = (1 + 0.1 * torch.randn(K, device="cuda", generator=g)).bfloat16()
+    gu = torch.empty(batch, 2 * I, device="cuda", dtype=torch.bfloat16)
+    two = torch.empty(batch, I, device="cuda", dtype=torch.bfloat16)
+    one = torch.empty(batch, I, device="cuda", dtype=torch.bfloat16)
+    nat.gemv_fused(x, w, None, gu, norm_w=nw, eps=1e-6)
+    nat.swiglu(gu, two, I)
+    nat.gemv_swiglu(x, w, None, one, norm_w=nw, eps=1e-6)
+    assert torch.equal(one, two)
+    nat.check_async()

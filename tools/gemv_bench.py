@@ -8,16 +8,17 @@ from physicedit_b200 import native as nv
 nat = nv.Native.get(0)
 dev = "cuda"
 res = {}
-for name, N, K, fused in (("qkv", 4608, 3584, "norm"), ("o", 3584, 3584, "res"), ("gate_up", 37888, 3584, "norm"), ("down", 3584, 18944, "swiglu"), ("lm_head", 152064, 3584, "norm")):
+for name, N, K, fused in (("gate_up_swiglu", 37888, 3584, "gu_swiglu"), ("qkv", 4608, 3584, "norm"), ("o", 3584, 3584, "res"), ("gate_up", 37888, 3584, "norm"), ("down", 3584, 18944, "swiglu"), ("down_plain", 3584, 18944, "res"), ("lm_head", 152064, 3584, "norm")):
     for batch in (1, 2):
         L = 28 if name != "lm_head" else 4
         ws = [torch.randn(N, K, device=dev).bfloat16() for _ in range(L)]
         x = torch.randn(batch, K * (2 if fused == "swiglu" else 1), device=dev).bfloat16()
         nw = torch.ones(K, device=dev).bfloat16()
-        y = torch.zeros(batch, N, device=dev).bfloat16()
+        y = torch.zeros(batch, N // (2 if fused == "gu_swiglu" else 1), device=dev).bfloat16()
         def run():
             for w in ws:
-                if fused == "norm": nat.gemv_fused(x, w, None, y, norm_w=nw)
+                if fused == "gu_swiglu": nat.gemv_swiglu(x, w, None, y, norm_w=nw)
+                elif fused == "norm": nat.gemv_fused(x, w, None, y, norm_w=nw)
                 elif fused == "res": nat.gemv_fused(x, w, None, y, residual=y)
                 else: nat.gemv_fused(x, w, None, y, act_in=2, residual=y)
         run(); torch.cuda.synchronize()
