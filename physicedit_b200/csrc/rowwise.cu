@@ -803,9 +803,8 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
     static const int mode = getenv("PE_GEMV_MODE") ? atoi(getenv("PE_GEMV_MODE")) : 0;      // experiments: 1 forces the wide kernel, 2 the narrow one
     PE_REQUIRE(h, act_out != 2 || (N % 2 == 0 && residual == nullptr && one_plus_mask == nullptr), "pe_gemv_swiglu: N = 2 I, no residual");
     const bool narrow = act_out != 2 && (mode == 2 || (mode == 0 && batch <= 2 && ceil_div(N, kGemvRows) < 2 * h->sm_count * kWarpsPerCta));
-    int grid = ceil_div(ceil_div(N, narrow ? 1 : kGemvRows), kWarpsPerCta);
-    const int cap = h->sm_count * 4;
-    if (grid > cap) grid = cap;
+    const int grid_needed = ceil_div(ceil_div(N, narrow ? 1 : kGemvRows), kWarpsPerCta);
+    int grid = grid_needed;
     const bf16* xb = static_cast<const bf16*>(x);
     const bf16* wb = static_cast<const bf16*>(w);
     const bf16* bb = static_cast<const bf16*>(bias);
@@ -813,6 +812,11 @@ int gemv_run(Handle* h, const void* x, const void* w, const void* bias, void* y,
 #define PE_GEMV_LAUNCH(KERN)                                                                                                  \
     {                                                                                                                        \
         if (smem > 40 * 1024) PE_CHECK_CUDA(h, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* static smem counts toward the 48 KB default too */ \
+        /* the row loop is grid-stride: ONE resident wave (SMs x occupancy of this instantiation), never a partial second one (r2: the batch-2 */ \
+        /* wide kernel needs 80 registers -> 3 CTAs per SM; a grid of 4 per SM ran a 1/3-full second wave: 62 us instead of 48 for 272 MB) */ \
+        int occ = 0;                                                                                                         \
+        PE_CHECK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, kWarpsPerCta * 32, smem));                  \
+        grid = grid_needed < h->sm_count * (occ > 0 ? occ : 1) ? grid_needed : h->sm_count * (occ > 0 ? occ : 1);            \
         KERN<<<grid, kWarpsPerCta * 32, smem, s>>>(xb, wb, bb, yb, N, K, act_in, act_out, one_plus_mask,                        \
                                                    static_cast<const bf16*>(norm_w), norm_eps, static_cast<const bf16*>(residual)); \
     }
