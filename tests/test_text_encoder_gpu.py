@@ -179,12 +179,9 @@ def test_cuda_graph_and_eager_decode_agree(native_te):
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
-@gpu
-def test_pipeline_call_runs_the_validate_py_flow_on_the_native_text_encoder():
-    """`pipe(prompt, edit_image=PIL, is_train=False)` as scripts/inference/validate.py:127-139 calls it, every model native: the VL model
-    generates the physical-thinking text for both CFG branches, encodes prompt + image into prompt_emb / special_token_mask, the VAE
-    encodes the edit image, the DiT denoises, the VAE decodes.  Synthetic weights (prompt width 3584 as the DiT expects, real
-    tokenizer / processor files when the reference's vendored copies are on the box)."""
+def _full_native_pipe():
+    """A pipeline with every model native on synthetic weights (prompt width 3584 as the DiT expects; 1-block DiT, 2-layer VL model, the real VAE
+    architecture) and the reference's real tokenizer / processor files; (pipe, text encoder, generator)."""
     import os
     import numpy as np
     from PIL import Image
@@ -229,6 +226,17 @@ def test_pipeline_call_runs_the_validate_py_flow_on_the_native_text_encoder():
     pipe.attach_tokenizer(tokenizer=tok, processor=proc)
     for p_ in pipe.visual_thinking_adapter.parameters():
         p_.data = ((torch.rand(p_.shape, generator=g, device="cuda") * 2 - 1) * 0.02).to(torch.bfloat16)
+    return pipe, te, g
+
+
+@gpu
+def test_pipeline_call_runs_the_validate_py_flow_on_the_native_text_encoder():
+    """`pipe(prompt, edit_image=PIL, is_train=False)` as scripts/inference/validate.py:127-139 calls it, every model native: the VL model
+    generates the physical-thinking text for both CFG branches, encodes prompt + image into prompt_emb / special_token_mask, the VAE
+    encodes the edit image, the DiT denoises, the VAE decodes."""
+    import numpy as np
+    from PIL import Image
+    pipe, te, g = _full_native_pipe()
     rng = np.random.default_rng(0)
     img = Image.fromarray(rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8))
     te.cfg.eos_token_id = -1                              # random weights: let both branches run into the 1000-token cap like a worst case
@@ -285,4 +293,44 @@ def test_gate_up_gemv_with_swiglu_epilogue_equals_the_two_step_sequence(batch):
     nat.swiglu(gu, two, I)
     nat.gemv_swiglu(x, w, None, one, norm_w=nw, eps=1e-6)
     assert torch.equal(one, two)
+    nat.check_async()
+
+
+@gpu
+def test_pipeline_call_with_the_optional_controls():
+    """The same call with the reference's optional controls routed through the units: a blockwise controlnet image
+    (QwenImageUnit_BlockwiseControlNet -> VAE latents -> per-block correction), EliGen entity prompts / masks (QwenImageUnit_EntityControl ->
+    entity prompt embeddings + latent masks -> masked attention), edit_rope_interpolation, and enable_fp8_attention."""
+    import numpy as np
+    from PIL import Image
+    from physicedit_b200.compat import ControlNetInput
+    from physicedit_b200.controlnet import QwenImageBlockWiseControlNet, QwenImageBlockwiseMultiControlNet
+    pipe, te, g = _full_native_pipe()
+    cn = QwenImageBlockWiseControlNet(num_layers=1).to(device="cuda", dtype=torch.bfloat16)
+    for p_ in cn.parameters():
+        p_.data = ((torch.rand(p_.shape, generator=g, device="cuda") * 2 - 1) * (0.02 if p_.dim() == 2 else 0.01)).to(torch.bfloat16)
+    for b in cn.controlnet_blocks:
+        b.x_rms.weight.data.fill_(1.0)
+        b.y_rms.weight.data.fill_(1.0)
+    pipe.blockwise_controlnet = QwenImageBlockwiseMultiControlNet([cn])
+    rng = np.random.default_rng(1)
+    img = Image.fromarray(rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8))
+    ctrl = Image.fromarray(rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8))
+    m1 = np.zeros((96, 128, 3), dtype=np.uint8); m1[:48, :64] = 255
+    m2 = np.zeros((96, 128, 3), dtype=np.uint8); m2[40:, 50:] = 255
+    common = dict(edit_image=img, edit_image_auto_resize=False, seed=1, num_inference_steps=2, height=96, width=128, is_train=False, have_text_reasoning=False,
+                  output_type="latent")
+    from physicedit_b200 import native as nv
+    nat = nv.Native.get(0)
+    plain = pipe("make the ice melt", **common)
+    l0 = nat.launches
+    with_cn = pipe("make the ice melt", blockwise_controlnet_inputs=[ControlNetInput(image=ctrl)], **common)
+    assert nat.launches - l0 > 0 and torch.isfinite(with_cn.float()).all() and not torch.equal(with_cn, plain)
+    with_eligen = pipe("make the ice melt", eligen_entity_prompts=["a red ball", "a porcelain cup on the table"], eligen_entity_masks=[Image.fromarray(m1), Image.fromarray(m2)],
+                       **common)
+    assert torch.isfinite(with_eligen.float()).all() and not torch.equal(with_eligen, plain)
+    with_fp8 = pipe("make the ice melt", enable_fp8_attention=True, **common)
+    assert torch.isfinite(with_fp8.float()).all() and not torch.equal(with_fp8, plain)
+    with_interp = pipe("make the ice melt", edit_rope_interpolation=True, **common)
+    assert torch.equal(with_interp, plain)                       # same-size edit image: forward_sampling builds the plain tables (:179)
     nat.check_async()
