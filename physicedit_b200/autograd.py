@@ -197,7 +197,7 @@ class _AttentionFn(torch.autograd.Function):
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
         nat, H = _nat(q), ctx.H
-        S, Sp, D = q.shape[0], _pad8(q.shape[0]), HEAD_DIM
+        S, Sp, D = q.shape[0], (q.shape[0] + 15) // 16 * 16, HEAD_DIM          # 16: row strides that allow the epilogues' 32-byte stores
         dev, scale = q.device, 1.0 / math.sqrt(HEAD_DIM)
         do = do.contiguous()
 

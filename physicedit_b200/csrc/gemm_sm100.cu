@@ -174,6 +174,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         bf16* out_row = sg.out + row * sg.ldo;
         // ATTN_DS reads the tile of P it overwrites: all four 16-byte loads of this row's 32 columns are issued before the first store (a store
         // to out_row would otherwise order the later loads behind it -- with K = 128 these launches are epilogue-bound)
+        uint4 held_p = make_uint4(0u, 0u, 0u, 0u);
         uint4 pv[4];
         if (EPI == PE_EPI_ATTN_DS) {
 #pragma unroll
@@ -210,7 +211,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
             o.y = pack_bf16(x[2], x[3]);
             o.z = pack_bf16(x[4], x[5]);
             o.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(out_row + nn) = o;
+            // a lane owns one row: 32-byte stores (a whole L2 sector) when the layout allows -- with K = 128 these launches are bound by the
+            // epilogue's store transactions, and half-filled sectors cost as much as full ones
+            if (!sg.wide_store) *reinterpret_cast<uint4*>(out_row + nn) = o;
+            else if ((v & 1) == 0) held_p = o;
+            else st_global_32B(out_row + nn - 8, held_p, o);
         }
         return;
     }
