@@ -5,6 +5,9 @@ Public entry points:
     QwenImagePhysicPipeline  the pipeline with the reference's constructor / loader / LoRA / denoise surface
     QwenImageDiT, adopt_dit  the DiT with the reference's parameter layout; adopt a loaded reference module
     QwenImageVAE, load_vae   the VAE either side of the loop (encode / decode of single images), same parameter layout
+    QwenImageTextEncoder     the Qwen2.5-VL encoder / greedy generator in front of the loop
+    inject_lora, launch_training_task, DiffusionTrainingModule   un-merged LoRA and the training loop (forward + backward on the native kernels)
+    QwenImageBlockWiseControlNet / QwenImageBlockwiseMultiControlNet   the optional blockwise controlnet
     FlowMatchScheduler, GeneralLoRALoader, ModelConfig, load_state_dict
 Everything numeric runs in physicedit_b200/lib/libpe_b200.so (include/pe_b200.h); there is no CPU fallback.
 """
@@ -28,6 +31,12 @@ _LAZY = {
     "adopt_text_encoder": ("compat", "adopt_text_encoder"),
     "QwenImageTextEncoder": ("text_encoder", "QwenImageTextEncoder"),
     "load_text_encoder": ("text_encoder", "load_text_encoder"),
+    "QwenImageBlockWiseControlNet": ("controlnet", "QwenImageBlockWiseControlNet"),
+    "QwenImageBlockwiseMultiControlNet": ("controlnet", "QwenImageBlockwiseMultiControlNet"),
+    "inject_lora": ("lora", "inject_lora"),
+    "merge_lora": ("lora", "merge_lora"),
+    "DiffusionTrainingModule": ("trainers", "DiffusionTrainingModule"),
+    "launch_training_task": ("trainers", "launch_training_task"),
 }
 
 

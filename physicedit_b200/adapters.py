@@ -212,30 +212,30 @@ class _MLP(nn.Module):
 
 
 class _Layer(nn.Module):
-    def __init__(self, hidden, eps):
+    def __init__(self, hidden, eps, mlp_ratio=4):
         super().__init__()
         self.norm1 = nn.LayerNorm(hidden, eps=eps)
         self.attention = _Attention(hidden)
         self.layer_scale1 = _LayerScale(hidden)
         self.norm2 = nn.LayerNorm(hidden, eps=eps)
-        self.mlp = _MLP(hidden)
+        self.mlp = _MLP(hidden, mlp_ratio)
         self.layer_scale2 = _LayerScale(hidden)
 
 
 class _Encoder(nn.Module):
-    def __init__(self, hidden, layers, eps):
+    def __init__(self, hidden, layers, eps, mlp_ratio=4):
         super().__init__()
-        self.layer = nn.ModuleList([_Layer(hidden, eps) for _ in range(layers)])
+        self.layer = nn.ModuleList([_Layer(hidden, eps, mlp_ratio) for _ in range(layers)])
 
 
 class Dinov2Encoder(nn.Module):
     """Same state_dict keys as transformers' Dinov2WithRegistersModel (embeddings.*, encoder.layer.N.*, layernorm.*)."""
 
-    def __init__(self, hidden=768, layers=12, heads=12, patch=14, image_size=518, n_reg=4, eps=1e-6):
+    def __init__(self, hidden=768, layers=12, heads=12, patch=14, image_size=518, n_reg=4, eps=1e-6, mlp_ratio=4):
         super().__init__()
         self.hidden, self.heads, self.patch, self.n_reg, self.eps = hidden, heads, patch, n_reg, eps
         self.embeddings = _Embeddings(hidden, patch, image_size, n_reg)
-        self.encoder = _Encoder(hidden, layers, eps)
+        self.encoder = _Encoder(hidden, layers, eps, mlp_ratio)
         self.layernorm = nn.LayerNorm(hidden, eps=eps)
         self._packed = None
         self._pos_cache = {}
@@ -334,7 +334,8 @@ class Dinov2withNorm(nn.Module):
             with open(os.path.join(dinov2_path, "config.json")) as f:
                 hf = json.load(f)
             cfg = dict(hidden=hf["hidden_size"], layers=hf["num_hidden_layers"], heads=hf["num_attention_heads"], patch=hf["patch_size"],
-                       image_size=hf["image_size"], n_reg=hf.get("num_register_tokens", 4), eps=hf.get("layer_norm_eps", 1e-6))
+                       image_size=hf["image_size"], n_reg=hf.get("num_register_tokens", 4), eps=hf.get("layer_norm_eps", 1e-6),
+                       mlp_ratio=hf.get("mlp_ratio", 4))
             st = os.path.join(dinov2_path, "model.safetensors")
             if os.path.exists(st):
                 from safetensors.torch import load_file

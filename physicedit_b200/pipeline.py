@@ -186,6 +186,16 @@ class QwenImagePhysicPipeline(nn.Module):
                     pipe.vae = load_vae(paths, torch_dtype=dtype, device=device, state_dict=sd)
                 elif key_hash == DIT_KEY_HASH:
                     pipe.dit = load_dit(paths, torch_dtype=dtype, device=device, state_dict=sd)
+                elif "controlnet_blocks.0.x_rms.weight" in sd and "img_in.weight" in sd:
+                    # blockwise controlnets (models/qwen_image_controlnet.py; fetched with index="all" at :516-518): every file is one more entry
+                    from .controlnet import QwenImageBlockWiseControlNet, QwenImageBlockwiseMultiControlNet
+                    layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("controlnet_blocks."))
+                    with torch.device("meta"):
+                        cn = QwenImageBlockWiseControlNet(num_layers=layers, additional_in_dim=sd["img_in.weight"].shape[1] - 64)
+                    cn.load_state_dict({k: v.to(dtype) for k, v in sd.items()}, assign=True)
+                    cn = cn.to(device).eval()
+                    nets = list(pipe.blockwise_controlnet.models) if pipe.blockwise_controlnet is not None else []
+                    pipe.blockwise_controlnet = QwenImageBlockwiseMultiControlNet(nets + [cn])
                 else:
                     from .text_encoder import load_text_encoder
                     te = load_text_encoder(sd, torch_dtype=dtype, device=device)

@@ -246,3 +246,29 @@ def test_lora_injection_layout_matches_what_the_loaders_read_back():
     assert set(merged) == set(folded) and all(torch.equal(merged[k], folded[k]) for k in merged)
     with pytest.raises(ValueError, match="not found"):
         m.add_lora_to_model(m.pipe.dit, target_modules=["no_such_linear"], lora_rank=8)
+
+
+def test_from_pretrained_recognises_files_by_content(tmp_path, capsys):
+    """from_pretrained (:497-541) on local files: a blockwise-controlnet checkpoint is recognised by its keys and appended to pipe.blockwise_controlnet
+    (two files -> two entries, the inpaint variant with its 4 extra input channels), an unknown file prints the reference's message and loads nothing
+    (model_manager.py:375-376), dinov2_path is mandatory (:198) and may be a local HF folder."""
+    from safetensors.torch import save_file
+    from oracle import dit_oracle as O
+    from oracle import ref_import
+    import physicedit_b200 as pe
+    dino = ref_import.tiny_dinov2_folder(str(tmp_path / "dino"))
+    cn = {k: v.to(torch.bfloat16) for k, v in O.synth_weights(O.controlnet_param_shapes(1), seed=1).items()}
+    save_file(cn, str(tmp_path / "cn.safetensors"))
+    inpaint = dict(cn)
+    inpaint["img_in.weight"] = torch.zeros(3072, 68, dtype=torch.bfloat16)
+    save_file(inpaint, str(tmp_path / "cn_inpaint.safetensors"))
+    save_file({"something.weight": torch.zeros(4, 4)}, str(tmp_path / "junk.safetensors"))
+    with pytest.raises(AssertionError, match="dinov2_path"):
+        pe.QwenImagePhysicPipeline.from_pretrained(device="cpu", model_configs=[])
+    pipe = pe.QwenImagePhysicPipeline.from_pretrained(torch_dtype=torch.bfloat16, device="cpu", dinov2_path=dino,
+                                                      model_configs=[pe.ModelConfig(path=str(tmp_path / n)) for n in ("cn.safetensors", "cn_inpaint.safetensors", "junk.safetensors")])
+    assert pipe.dit is None and pipe.vae is None and pipe.text_encoder is None
+    nets = pipe.blockwise_controlnet.models
+    assert len(nets) == 2 and nets[0].img_in.weight.shape == (3072, 64) and nets[1].img_in.weight.shape == (3072, 68)
+    assert torch.equal(nets[0].controlnet_blocks[0].input_proj.weight, cn["controlnet_blocks.0.input_proj.weight"])
+    assert "cannot detect the model type" in capsys.readouterr().out
