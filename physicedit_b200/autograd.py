@@ -28,7 +28,7 @@ import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 
 from . import native as nv
-from .lora import LoRALinear
+from .lora import HotLoRALinear, LoRALinear
 
 HEAD_DIM = 128
 BF16 = torch.bfloat16
@@ -165,7 +165,13 @@ def lora_linear(x: torch.Tensor, m: LoRALinear) -> torch.Tensor:
 
 
 def module_linear(m: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
-    return lora_linear(x, m) if isinstance(m, LoRALinear) else linear(x, m.weight, m.bias)
+    if isinstance(m, LoRALinear):
+        return lora_linear(x, m)
+    y = linear(x, m.weight, m.bias)
+    if isinstance(m, HotLoRALinear):                      # AutoWrappedLinear.forward (vram_management/layers.py:177-179): out + x A^T B^T per attached LoRA
+        for a, b in zip(m.lora_A_weights, m.lora_B_weights):
+            y = y + linear(linear(x, a), b)
+    return y
 
 
 ATTN_BWD_SCRATCH_BYTES = 16 << 30        # S x S scratch of the attention backward: heads are processed in chunks that fit

@@ -121,7 +121,7 @@ def inject_lora(model: torch.nn.Module, target_modules, r: int, lora_alpha=None)
         parent_name, _, leaf = name.rpartition(".")
         parent = model.get_submodule(parent_name) if parent_name else model
         setattr(parent, leaf, LoRALinear(mod, r, lora_alpha))
-    model._lora_injected = True
+    refresh_lora_flag(model)
     if getattr(model, "_engine", None) is not None:
         model._engine.invalidate()
     return model
@@ -134,7 +134,80 @@ def merge_lora(model: torch.nn.Module):
             parent_name, _, leaf = name.rpartition(".")
             parent = model.get_submodule(parent_name) if parent_name else model
             setattr(parent, leaf, mod.merge())
-    model._lora_injected = False
+    refresh_lora_flag(model)
     if getattr(model, "_engine", None) is not None:
         model._engine.invalidate()
     return model
+
+
+class HotLoRALinear(torch.nn.Module):
+    """The LoRA side of `AutoWrappedLinear` (vram_management/layers.py:98-187), which `pipe.enable_lora_magic()` (:288-305) puts around every
+    nn.Linear of the DiT so that `pipe.load_lora(..., hotload=True)` (:265-272) can ATTACH LoRAs without folding them: pairs (A * alpha, B) are
+    appended to two lists and the forward is `linear(x) + sum_i x A_i^T B_i^T` (:177-179); `pipe.clear_lora()` empties the lists.  The VRAM
+    off-loading half of that class is not needed on a 180 GB device.  With empty lists the module is transparent (the inference engine reads
+    `.weight` / `.bias`); with attached LoRAs model_fn takes the un-merged path (physicedit_b200/autograd.py)."""
+
+    def __init__(self, base_layer: torch.nn.Linear, name: str = ""):
+        super().__init__()
+        self.base_layer = base_layer
+        self.name = name
+        self.lora_A_weights, self.lora_B_weights = [], []
+
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+    @property
+    def in_features(self):
+        return self.base_layer.in_features
+
+    @property
+    def out_features(self):
+        return self.base_layer.out_features
+
+    def forward(self, x):
+        from . import autograd as ag
+        return ag.module_linear(self, x)
+
+
+def enable_hot_lora(model: torch.nn.Module) -> int:
+    """Wrap every plain nn.Linear of `model` (idempotent); returns the number of wrappers now present."""
+    for name, mod in list(model.named_modules()):
+        if isinstance(mod, torch.nn.Linear) and not name.endswith("base_layer") and "lora_A" not in name and "lora_B" not in name:
+            parent_name, _, leaf = name.rpartition(".")
+            parent = model.get_submodule(parent_name) if parent_name else model
+            if not isinstance(parent, (HotLoRALinear, LoRALinear)):
+                setattr(parent, leaf, HotLoRALinear(mod, name))
+    return sum(isinstance(m, HotLoRALinear) for m in model.modules())
+
+
+def hotload_lora(model: torch.nn.Module, lora_state_dict, alpha=1.0) -> int:
+    """:265-272: for every wrapped linear `name`, attach (`name.lora_A.default.weight` * alpha, `name.lora_B.default.weight`) when both exist."""
+    n = 0
+    for name, mod in model.named_modules():
+        if isinstance(mod, HotLoRALinear):
+            a, b = f"{name}.lora_A.default.weight", f"{name}.lora_B.default.weight"
+            if a in lora_state_dict and b in lora_state_dict:
+                w = mod.base_layer.weight
+                mod.lora_A_weights.append((lora_state_dict[a] * alpha).to(device=w.device, dtype=w.dtype).contiguous())
+                mod.lora_B_weights.append(lora_state_dict[b].to(device=w.device, dtype=w.dtype).contiguous())
+                n += 1
+    refresh_lora_flag(model)
+    return n
+
+
+def clear_hot_lora(model: torch.nn.Module) -> None:
+    for mod in model.modules():
+        if isinstance(mod, HotLoRALinear):
+            mod.lora_A_weights.clear()
+            mod.lora_B_weights.clear()
+    refresh_lora_flag(model)
+
+
+def refresh_lora_flag(model: torch.nn.Module) -> None:
+    """`_lora_injected` tells model_fn to run the un-merged path: PEFT-style factors present, or a hot LoRA attached."""
+    model._lora_injected = any(isinstance(m, LoRALinear) or (isinstance(m, HotLoRALinear) and m.lora_A_weights) for m in model.modules())

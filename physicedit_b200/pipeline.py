@@ -238,12 +238,42 @@ class QwenImagePhysicPipeline(nn.Module):
         return self
 
     def load_lora(self, module: nn.Module, lora_config=None, alpha=1, hotload=False, state_dict=None):
-        if hotload:
-            raise NotImplementedError("hotload (un-merged LoRA through AutoWrappedLinear) is unused by PhysicEdit (SURVEY 0.5)")
+        """:250-276.  hotload=False folds `alpha * B @ A` into the weights (GeneralLoRALoader); hotload=True attaches the factors un-merged to the
+        wrappers `enable_lora_magic()` installed (none installed -> nothing attaches, like the reference's isinstance filter)."""
         if state_dict is None:
             path = lora_config if isinstance(lora_config, str) else lora_config.path
             state_dict = load_state_dict(path, torch_dtype=self.torch_dtype, device=self.device)
+        if hotload:
+            from .lora import hotload_lora
+            hotload_lora(module, state_dict, alpha=alpha)
+            return
         GeneralLoRALoader(torch_dtype=self.torch_dtype, device=self.device).load(module, state_dict, alpha=alpha)
+
+    def clear_lora(self):
+        """:279-285: detach every hot-loaded LoRA."""
+        from .lora import clear_hot_lora
+        for _, child in self.named_children():
+            clear_hot_lora(child)
+
+    def enable_lora_magic(self):
+        """:288-305: make the DiT's linears able to carry un-merged LoRAs (`load_lora(..., hotload=True)`)."""
+        if self.dit is not None:
+            from .lora import enable_hot_lora
+            enable_hot_lora(self.dit)
+
+    def get_special_divisor(self, global_step=None, warmup_steps=10000):
+        """:308-311."""
+        return 10 - 9.0 * min(1.0, global_step / float(warmup_steps))
+
+    def direct_distill_loss(self, **inputs):
+        """:332-340: run the whole sampler under autograd and regress its end point on `input_latents`."""
+        self.scheduler.set_timesteps(inputs["num_inference_steps"])
+        models = {name: getattr(self, name) for name in self.in_iteration_models if name not in inputs}
+        for progress_id, timestep in enumerate(self.scheduler.timesteps):
+            timestep = timestep.unsqueeze(0).to(dtype=self.torch_dtype, device=self.device)
+            noise_pred, _ = self.model_fn(**models, **inputs, timestep=timestep, progress_id=progress_id)
+            inputs["latents"] = self.step(self.scheduler, progress_id=progress_id, noise_pred=noise_pred, **inputs)
+        return torch.nn.functional.mse_loss(inputs["latents"].float(), inputs["input_latents"].float())
 
     def enable_vram_management(self, *args, **kwargs):
         """Accepted for API compatibility (inference_pica.py:246): weights stay resident -- a B200 has 180 GB."""

@@ -272,3 +272,29 @@ def test_from_pretrained_recognises_files_by_content(tmp_path, capsys):
     assert len(nets) == 2 and nets[0].img_in.weight.shape == (3072, 64) and nets[1].img_in.weight.shape == (3072, 68)
     assert torch.equal(nets[0].controlnet_blocks[0].input_proj.weight, cn["controlnet_blocks.0.input_proj.weight"])
     assert "cannot detect the model type" in capsys.readouterr().out
+
+
+def test_hot_lora_surface():
+    """enable_lora_magic / load_lora(hotload=True) / clear_lora (qwen_image_physical.py:265-305): wrappers around every linear of the DiT, factors
+    attached by PEFT key name and scaled by alpha, the un-merged flag follows the lists; get_special_divisor (:308-311)."""
+    from physicedit_b200.lora import HotLoRALinear
+    pipe = _cpu_pipe(layers=1)
+    n_linear = sum(isinstance(m, torch.nn.Linear) for m in pipe.dit.modules())
+    pipe.load_lora(pipe.dit, state_dict={"transformer_blocks.0.attn.to_q.lora_A.default.weight": torch.ones(4, 3072),
+                                         "transformer_blocks.0.attn.to_q.lora_B.default.weight": torch.ones(3072, 4)}, hotload=True)
+    assert not getattr(pipe.dit, "_lora_injected", False)                # no wrappers yet: nothing attaches (the reference's isinstance filter)
+    pipe.enable_lora_magic()
+    pipe.enable_lora_magic()                                             # idempotent
+    wrappers = {n: m for n, m in pipe.dit.named_modules() if isinstance(m, HotLoRALinear)}
+    assert len(wrappers) == n_linear and "transformer_blocks.0.attn.to_out.0" in wrappers
+    q = wrappers["transformer_blocks.0.attn.to_q"]
+    assert q.weight is q.base_layer.weight and q.in_features == 3072 and not pipe.dit._lora_injected
+    sd = {"transformer_blocks.0.attn.to_q.lora_A.default.weight": torch.ones(4, 3072), "transformer_blocks.0.attn.to_q.lora_B.default.weight": torch.ones(3072, 4),
+          "transformer_blocks.0.attn.to_k.lora_A.default.weight": torch.ones(4, 3072)}          # B missing: skipped
+    pipe.load_lora(pipe.dit, state_dict=sd, alpha=0.5, hotload=True)
+    pipe.load_lora(pipe.dit, state_dict=sd, alpha=2.0, hotload=True)
+    assert len(q.lora_A_weights) == 2 and float(q.lora_A_weights[0][0, 0]) == 0.5 and float(q.lora_A_weights[1][0, 0]) == 2.0 and float(q.lora_B_weights[0][0, 0]) == 1.0
+    assert len(wrappers["transformer_blocks.0.attn.to_k"].lora_A_weights) == 0 and pipe.dit._lora_injected
+    pipe.clear_lora()
+    assert len(q.lora_A_weights) == 0 and not pipe.dit._lora_injected
+    assert pipe.get_special_divisor(global_step=0) == 10 and pipe.get_special_divisor(global_step=5000) == 5.5 and pipe.get_special_divisor(global_step=20000) == 1.0

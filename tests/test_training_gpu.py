@@ -365,3 +365,40 @@ def test_attention_forward_row_statistics(nat):
     hm = lambda t: t.view(S, H, 128).transpose(0, 1).float()
     ref = torch.logsumexp(hm(q) @ hm(k).transpose(1, 2) / math.sqrt(128), dim=-1) * 1.4426950408889634
     assert (lse - ref).abs().max().item() < 2e-3
+
+
+@gpu
+def test_hot_loaded_lora_equals_the_folded_lora_within_rounding():
+    """pipe.enable_lora_magic() + load_lora(hotload=True) (un-merged: out + x A^T B^T, vram_management/layers.py:177-179) vs load_lora() (folded) on
+    the same factors; clear_lora() brings back the plain model bit for bit (and the inference engine)."""
+    from test_parity_depth_gpu import device_model
+    from physicedit_b200.model_fn import model_fn_qwen_image
+    H, T = 128, 72
+    inp = O.synth_inputs(H, H, T, seed=44, dtype=torch.bfloat16)
+    t = torch.tensor([603.0]).bfloat16().cuda()
+
+    def run(pipe):
+        with torch.no_grad():
+            return model_fn_qwen_image(dit=pipe.dit, visual_thinking_adapter=pipe.visual_thinking_adapter, latents=inp["latents"].cuda(), timestep=t,
+                                       prompt_emb=inp["prompt_emb"].cuda().clone(), prompt_emb_mask=inp["prompt_emb_mask"].cuda(),
+                                       special_token_mask=inp["special_token_mask"].cuda(), height=H, width=H, edit_latents=inp["edit_latents"].cuda(), is_train=False)[0]
+    g = torch.Generator().manual_seed(2)
+    lora = {}
+    for blk in range(2):
+        for name, (o, i) in (("attn.to_q", (3072, 3072)), ("attn.add_v_proj", (3072, 3072)), ("img_mlp.net.2", (3072, 12288)), ("txt_mod.1", (18432, 3072))):
+            lora[f"transformer_blocks.{blk}.{name}.lora_A.default.weight"] = (torch.randn(16, i, generator=g) / math.sqrt(i)).bfloat16()
+            lora[f"transformer_blocks.{blk}.{name}.lora_B.default.weight"] = (torch.randn(o, 16, generator=g) * 0.2).bfloat16()
+    pipe, _, _ = device_model(2, seed=12)
+    plain = run(pipe)
+    pipe.enable_lora_magic()
+    assert torch.equal(run(pipe), plain)                                  # wrappers without LoRAs: still the engine, same bits
+    pipe.load_lora(pipe.dit, state_dict=lora, alpha=0.7, hotload=True)
+    hot = run(pipe)
+    pipe.clear_lora()
+    assert torch.equal(run(pipe), plain)
+    pipe2, _, _ = device_model(2, seed=12)
+    pipe2.load_lora(pipe2.dit, state_dict=lora, alpha=0.7)
+    folded = run(pipe2)
+    e, d = rel_l2(hot, folded), rel_l2(hot, plain)
+    print(f"\nhot-loaded vs folded LoRA: {e:.3e}; LoRA effect {d:.3e}")
+    assert e < 1.5e-2 and d > 5 * e
