@@ -607,6 +607,50 @@ def stock_gpu_leg(device, H, W, layers=4, iters=10, warmup=3):
                        "the full-depth figure against the fp32 oracle is in profiles/r02_parity_depth.json (tests/test_parity_depth_gpu.py)"}}
 
 
+def feature_extractor_leg(device, H, W, frames=6, iters=5, warmup=2):
+    """The pseudo-target branch of a training sample (QwenImageUnit_PhysicalVisualEmbedder, qwen_image_physical.py:1057-1118) on the native kernels,
+    forward only (inference mode of the frozen / evaluated stack): DINOv2-with-registers base on `frames` middle key frames + the source image at 224^2,
+    the two perceiver resamplers (64 latents, keys over frames x 256 resp. frames x H/16 x W/16 tokens) and their adapters.  `pe_small_attention` is
+    the CUDA-core attention of both; the GEMMs are `pe_gemm`."""
+    from physicedit_b200 import native as nv
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    nat = nv.Native.get(device.index or 0)
+    pipe = QwenImagePhysicPipeline(device=device, torch_dtype=torch.bfloat16, dinov2_config=dict(hidden=768, layers=12, heads=12))
+    g = torch.Generator(device=device).manual_seed(3)
+    for p in pipe.parameters():
+        if p.dim() >= 2:
+            p.data = ((torch.rand(p.shape, generator=g, device=device) * 2 - 1) / math.sqrt(p.shape[-1])).to(torch.bfloat16)
+    pipe.to(device)
+    pipe.eval()
+    x = dict(dino_middle=torch.randn(frames, 3, 224, 224, device=device, generator=g).to(torch.bfloat16),
+             dino_source=torch.randn(1, 3, 224, 224, device=device, generator=g).to(torch.bfloat16),
+             vae_middle_latents=torch.randn(frames, 16, H // 8, W // 8, device=device, generator=g).to(torch.bfloat16),
+             vae_source_latents=torch.randn(1, 16, H // 8, W // 8, device=device, generator=g).to(torch.bfloat16))
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = nat.launches
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / iters, (nat.launches - l0) // iters
+    ms_all, n_all = timed(lambda: pipe.physical_visual_embeddings(**x))
+    ms_dino, n_dino = timed(lambda: pipe.dinov2(x["dino_middle"]))
+    # ViT-B/14 at 224^2: 261 tokens (256 patches + CLS + 4 registers), 12 layers: per token per layer 24 d^2 (4 projections + 8 d^2 of MLP pairs) + attention 4 n d
+    tok, d = 261, 768
+    fl_dino = frames * 12 * (tok * 24 * d * d + 4 * tok * tok * d)
+    nat.check_async()
+    return {"frames": frames, "ms_pseudo_targets": round(ms_all, 3), "own_kernel_launches": n_all, "ms_dinov2_middle_frames": round(ms_dino, 3),
+            "dinov2_launches": n_dino, "dinov2_tflops": round(fl_dino / (ms_dino * 1e-3) / 1e12, 1),
+            "note": "small-model regime: 1566 tokens x 768 wide, launch-bound (each launch is a few microseconds of work); < 1 % of a training step"}
+
+
 TRAIN_TARGETS = "to_q,to_k,to_v,add_q_proj,add_k_proj,add_v_proj,to_out.0,to_add_out,img_mlp.net.2,img_mod.1,txt_mlp.net.2,txt_mod.1".split(",")
 
 
@@ -678,6 +722,10 @@ def training_leg(device, layers=8, H=480, W=832, T=512, rank=128, iters=3, warmu
            "iters": iters, "warmup": warmup}
     del pipe, params
     torch.cuda.empty_cache()
+    try:
+        out["feature_extractors"] = feature_extractor_leg(device, H, W)
+    except Exception as e:  # noqa: BLE001
+        out["feature_extractors"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if ref_import.reference_root() is None:
         out["stock_gpu"] = {"unavailable": "no reference tree on this box (baseline/_ref)"}
         return out
