@@ -8,6 +8,41 @@ nat = nv.Native.get(0)
 dev = "cuda"
 bf = dict(device=dev, dtype=torch.bfloat16)
 torch.manual_seed(0)
+if os.environ.get("SANITIZE_ONLY_R2"):
+    # ---- round-2 kernels: batched GEMM + attention-backward epilogues, forward with row statistics, delta pass, masked softmax, cluster split-K GEMV,
+    # SwiGLU-epilogue GEMV, staged small attention, LLM row kernels, routed attention / QKV epilogue (local pointers) ----
+    B, M, N, K = 3, 200, 144, 128
+    Mp = 208
+    a = torch.randn(B * Mp, K, **bf); w = torch.randn(B * N, K, **bf) / 11
+    out = torch.zeros(B * Mp, N, **bf); o32 = torch.zeros(B * Mp, N, device=dev)
+    vec = torch.randn(B, 224, device=dev)
+    kw = dict(batch=B, M=M, N=N, K=K, a_batch_rows=Mp, w_batch_rows=N, out_batch_rows=Mp)
+    nat.gemm_batched(a, w, out, **kw)
+    nat.gemm_batched(a, w, o32, epilogue=nv.EPI_F32, **kw)
+    for col in (False, True):
+        nat.gemm_batched(a, w, out, epilogue=nv.EPI_ATTN_P, vec=vec, vec_batch_stride=224, vec_per_column=col, alpha=0.3, **kw)
+        nat.gemm_batched(a, w, out, epilogue=nv.EPI_ATTN_DS, vec=vec, vec_batch_stride=224, vec_per_column=col, alpha=0.3, **kw)
+    S, H = 330, 2
+    q, k, v = (torch.randn(S, H * 128, **bf) for _ in range(3))
+    o = torch.empty_like(q); lse = torch.empty(H, S, device=dev)
+    nat.attention_lse(q, k, v, o, lse, H, 1 / math.sqrt(128))
+    delta = torch.zeros(H, 336, device=dev)
+    nat.attention_bwd_delta(o, q, delta, H)
+    nat.attention_routed(q, k, v, H, 1 / math.sqrt(128), [128, 330], [o.data_ptr(), o.data_ptr()], H * 128, 0)
+    sc = torch.randn(2 * 72, 72, device=dev); pr = torch.empty(2 * 72, 72, **bf); mk = (torch.rand(72, 72, device=dev) > 0.3).to(torch.uint8); mk.fill_diagonal_(1)
+    nat.softmax_rows(sc, pr, 70, 0.1, mask=mk)
+    for batch in (1, 2):
+        wl = torch.randn(50, 8192, **bf) / 90; xl = torch.randn(batch, 2 * 8192, **bf); yl = torch.zeros(batch, 50, **bf)
+        nat.gemv_fused(xl, wl, None, yl, act_in=2, residual=yl)                    # cluster split-K kernel (K >= 8192), ragged N
+        wg = torch.randn(2 * 1000, 512, **bf) / 22; xg = torch.randn(batch, 512, **bf); yg = torch.zeros(batch, 1000, **bf)
+        nat.gemv_swiglu(xg, wg, None, yg, norm_w=torch.ones(512, **bf))
+    qs, ks_, vs_ = torch.randn(2 * 70, 3 * 64, **bf), torch.randn(2 * 261, 3 * 64, **bf), torch.randn(2 * 261, 3 * 64, **bf)
+    os_ = torch.empty(2 * 70, 3 * 64, **bf)
+    nat.small_attention(qs, ks_, vs_, os_, 2, 3, 70, 261, 64, 0.125)               # staged variant (Sq >= 32, K/V fit in shared memory)
+    nat.check_async()
+    torch.cuda.synchronize()
+    print("sanitize targets (r2) done")
+    sys.exit(0)
 if not os.environ.get("SANITIZE_ONLY_VAE"):      # the DiT kernel families (sanitized in r1 sessions 2-3; set the variable to run only the VAE additions)
     # attention: all kernels, ragged S
     for flags in (0, 16, 8):
