@@ -351,6 +351,20 @@ int pe_kv_append(pe_handle_t h, const void* k_new, const void* v_new, void* cach
  * cache_k[counters[0], :] = rotated k, cache_v[counters[0], :] = v.  Fuses two pe_rope_half and one pe_kv_append launch. */
 int pe_rope_kv_append(pe_handle_t h, void* qkv, int Hq, int Hkv, int D, const float* cos_table, const float* sin_table, void* cache_k,
                       void* cache_v, int64_t ldc, const int32_t* counters, void* stream);
+/* The attention part of ONE decode step for up to 8 requests in ONE launch (the per-layer body of Qwen2_5_VLAttention.forward for a single new
+ * token, modeling_qwen2_5_vl.py:690-760, with DynamicCache.update): pe_rope_kv_append + the one-query pe_range_attention of every request.
+ * qkv = [q (Hq heads) | k (Hkv) | v (Hkv)] of the new token (left untouched), counters[0] = cache rows before the append, counters[1] = rope
+ * table row; out [Hq * 128].  Bit-identical to the two-launch sequence. */
+typedef struct pe_decode_req {
+    const void* qkv;
+    void* cache_k;
+    void* cache_v;
+    void* out;
+    const int32_t* counters;
+    int64_t cache_rows;   /* capacity of this request's cache */
+} pe_decode_req;
+int pe_decode_attention_fused(pe_handle_t h, const pe_decode_req* reqs, int n_req, int Hq, int Hkv, int D, int64_t ldc,
+                              const float* cos_table, const float* sin_table, float scale, void* stream);
 /* counters[0:n] += 1 (KV length, rope row and step counters of the captured decode step). */
 int pe_advance(pe_handle_t h, int32_t* counters, int n, void* stream);
 

@@ -56,6 +56,8 @@ int make_tmap_3d(Handle* h, CUtensorMap* out, const void* base, uint64_t C, uint
 }
 
 // launchers implemented in the kernel translation units
+int decode_attention_fused_run(Handle* h, const pe_decode_req* reqs, int n_req, int Hq, int Hkv, int D, int64_t ldc, const float* cs,
+                               const float* sn, float scale, cudaStream_t s);
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream, const pe_gemm_batch* bt = nullptr);
 int attention_run(Handle* h, const void* q, const void* k, const void* v, void* o, int S, int H, int64_t ld, float scale,
                   int flags, cudaStream_t stream, float* lse = nullptr);
@@ -268,6 +270,12 @@ int pe_gemv_fused(pe_handle_t hh, const void* x, const void* w, const void* bias
                   const void* norm_w, float norm_eps, const void* residual, void* stream) {
     PE_H(hh);
     return pe::gemv_run(h, x, w, bias, y, batch, N, K, act_in, 0, nullptr, static_cast<cudaStream_t>(stream), norm_w, norm_eps, residual);
+}
+
+int pe_decode_attention_fused(pe_handle_t hh, const pe_decode_req* reqs, int n_req, int Hq, int Hkv, int D, int64_t ldc,
+                              const float* cos_table, const float* sin_table, float scale, void* stream) {
+    PE_H(hh);
+    return pe::decode_attention_fused_run(h, reqs, n_req, Hq, Hkv, D, ldc, cos_table, sin_table, scale, static_cast<cudaStream_t>(stream));
 }
 
 int pe_gemv_swiglu(pe_handle_t hh, const void* x, const void* w, const void* bias, void* y, int batch, int I, int K, const void* norm_w, float norm_eps,

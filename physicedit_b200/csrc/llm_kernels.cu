@@ -191,6 +191,111 @@ __global__ void __launch_bounds__(kWarps * 32) decode_attention_kernel(const bf1
     }
 }
 
+// ---- the whole attention part of one decode step in ONE launch for up to 8 requests: rope (bf16 op order) of the new q / k heads, KV-cache
+// append, attention of the new query over the cache + itself.  grid = (query heads, requests).  Every CTA rotates its own q head and the k head
+// of its KV group (7 query heads share one: the rotation is 128 elements), reads the cached rows [0, n) like decode_attention_kernel and takes the
+// NEW row from registers (as row n, by the warp n % kWarps that would have read it: same values, same order -> bit-identical to
+// rope_kv_append_kernel + decode_attention_kernel); the first CTA of a KV group writes the rotated k and v into the cache.
+struct DecodeReqDev {
+    const bf16* qkv;      // [ (Hq + 2 Hkv) * 128 ] = q | k | v of the new token (not modified)
+    bf16* cache_k;        // [cap, ldc]
+    bf16* cache_v;
+    bf16* out;            // [Hq * 128]
+    const int* ctr;       // ctr[0] = cache rows before the append, ctr[1] = rope table row
+    int cap;              // cache capacity (rows)
+};
+struct DecodeBatchDev {
+    DecodeReqDev r[8];
+};
+__device__ __forceinline__ void rope4(const float (&x)[4], const float (&xp)[4], const float* __restrict__ cs, const float* __restrict__ sn, long long row,
+                                      int D, int c0, bool hi, float (&o)[4]) {
+    // rotate-half with the language model's rounding points (rope_half_kernel mode 1): channel c < D/2: bf16(bf16(x c) + bf16(-x' s)), c >= D/2:
+    // bf16(bf16(x c) + bf16(x' s)); x' = the partner channel c +- D/2 (held by lane +- 16)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float c = bf16_round(cs[row * D + c0 + i]), sv = bf16_round(sn[row * D + c0 + i]);
+        o[i] = bf16_round(bf16_round(x[i] * c) + bf16_round((hi ? xp[i] : -xp[i]) * sv));
+    }
+}
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) decode_attention_fused_kernel(const DecodeBatchDev batch, int Hq, int Hkv, long long ldc,
+                                                                             const float* __restrict__ cs, const float* __restrict__ sn, float scale) {
+    constexpr int D = 128;
+    __shared__ float sm_m[kWarps], sm_l[kWarps];
+    __shared__ float sm_acc[kWarps][D];
+    const DecodeReqDev& rq = batch.r[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hd = blockIdx.x, group = Hq / Hkv, hkv = hd / group;
+    const int n_prev = min(rq.ctr[0], rq.cap - 1);
+    const long long row = rq.ctr[1];
+    const int c0 = lane * 4;
+    const bool hi = lane >= 16;
+    auto load4 = [&](const bf16* p, float (&f)[4]) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p + c0);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    };
+    float qx[4], qp[4], kx[4], kp[4], vx[4], qr[4], kr[4];
+    load4(rq.qkv + hd * D, qx);
+    load4(rq.qkv + (Hq + hkv) * D, kx);
+    load4(rq.qkv + (Hq + Hkv + hkv) * D, vx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        qp[i] = __shfl_xor_sync(0xffffffffu, qx[i], 16);
+        kp[i] = __shfl_xor_sync(0xffffffffu, kx[i], 16);
+    }
+    rope4(qx, qp, cs, sn, row, D, c0, hi, qr);
+    rope4(kx, kp, cs, sn, row, D, c0, hi, kr);
+    if (hd % group == 0 && warp == 0) {                       // the KV group's first CTA appends the new row
+        uint2 ku, vu;
+        ku.x = pack_bf16(kr[0], kr[1]); ku.y = pack_bf16(kr[2], kr[3]);
+        vu.x = pack_bf16(vx[0], vx[1]); vu.y = pack_bf16(vx[2], vx[3]);
+        *reinterpret_cast<uint2*>(rq.cache_k + (long long)n_prev * ldc + hkv * D + c0) = ku;
+        *reinterpret_cast<uint2*>(rq.cache_v + (long long)n_prev * ldc + hkv * D + c0) = vu;
+    }
+    const float q0 = qr[0] * scale, q1 = qr[1] * scale, q2 = qr[2] * scale, q3 = qr[3] * scale;
+    float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const bf16* kb = rq.cache_k + hkv * D + c0;
+    const bf16* vb = rq.cache_v + hkv * D + c0;
+    auto step = [&](float k0, float k1, float k2, float k3, float v0, float v1, float v2, float v3) {
+        float s = q0 * k0 + q1 * k1 + q2 * k2 + q3 * k3;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const float m_new = fmaxf(m, s);
+        const float f = __expf(m - m_new), pw = __expf(s - m_new);
+        l = l * f + pw;
+        a0 = a0 * f + pw * v0; a1 = a1 * f + pw * v1; a2 = a2 * f + pw * v2; a3 = a3 * f + pw * v3;
+        m = m_new;
+    };
+    for (int kj = warp; kj < n_prev; kj += kWarps) {
+        const uint2 ku = __ldg(reinterpret_cast<const uint2*>(kb + (long long)kj * ldc));
+        const uint2 vu = __ldg(reinterpret_cast<const uint2*>(vb + (long long)kj * ldc));
+        const float2 k01 = unpack_bf16(ku.x), k23 = unpack_bf16(ku.y), v01 = unpack_bf16(vu.x), v23 = unpack_bf16(vu.y);
+        step(k01.x, k01.y, k23.x, k23.y, v01.x, v01.y, v23.x, v23.y);
+    }
+    if (warp == n_prev % kWarps) step(kr[0], kr[1], kr[2], kr[3], vx[0], vx[1], vx[2], vx[3]);      // the new token's own row, from registers
+    if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+    sm_acc[warp][c0 + 0] = a0; sm_acc[warp][c0 + 1] = a1; sm_acc[warp][c0 + 2] = a2; sm_acc[warp][c0 + 3] = a3;
+    __syncthreads();
+    if (warp == 0) {
+        float mg = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) mg = fmaxf(mg, sm_m[w]);
+        float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const float f = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mg);
+            lt += f * sm_l[w];
+            r0 += f * sm_acc[w][c0 + 0]; r1 += f * sm_acc[w][c0 + 1]; r2 += f * sm_acc[w][c0 + 2]; r3 += f * sm_acc[w][c0 + 3];
+        }
+        const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+        uint2 ou;
+        ou.x = pack_bf16(r0 * inv, r1 * inv);
+        ou.y = pack_bf16(r2 * inv, r3 * inv);
+        *reinterpret_cast<uint2*>(rq.out + hd * D + c0) = ou;
+    }
+}
+
 // ---- out[i, :] = table[ids[i], :] ; ids < 0 leave the row untouched (used to scatter image embeddings into the token stream) ----------
 __global__ void gather_rows_kernel(const bf16* __restrict__ table, long long ldt, const long long* __restrict__ ids, bf16* __restrict__ out,
                                    long long ldo, int n, int C) {
@@ -349,6 +454,24 @@ int rope_kv_append_run(Handle* h, void* qkv, int Hq, int Hkv, int D, const float
     PE_REQUIRE(h, qkv && cs && sn && cache_k && cache_v && ctr && Hq > 0 && Hkv > 0 && D > 0 && D % 2 == 0, "pe_rope_kv_append: bad arguments");
     const int n = (Hq + Hkv) * (D / 2) + Hkv * D;
     rope_kv_append_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<bf16*>(qkv), Hq, Hkv, D, cs, sn, static_cast<bf16*>(cache_k), static_cast<bf16*>(cache_v), ldc, ctr);
+    PE_CHECK_CUDA(h, cudaGetLastError());
+    return PE_OK;
+}
+
+int decode_attention_fused_run(Handle* h, const pe_decode_req* reqs, int n_req, int Hq, int Hkv, int D, int64_t ldc, const float* cs,
+                               const float* sn, float scale, cudaStream_t s) {
+    PE_REQUIRE(h, reqs && cs && sn && n_req >= 1 && n_req <= 8, "pe_decode_attention_fused: 1..8 requests (got %d)", n_req);
+    PE_REQUIRE(h, D == 128 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && ldc % 8 == 0 && ldc >= (int64_t)Hkv * D,
+               "pe_decode_attention_fused: head dim 128, Hq a multiple of Hkv, ldc >= Hkv * 128 (Hq=%d Hkv=%d D=%d)", Hq, Hkv, D);
+    DecodeBatchDev b;
+    memset(&b, 0, sizeof(b));
+    for (int i = 0; i < n_req; ++i) {
+        PE_REQUIRE(h, reqs[i].qkv && reqs[i].cache_k && reqs[i].cache_v && reqs[i].out && reqs[i].counters && reqs[i].cache_rows > 0,
+                   "pe_decode_attention_fused: request %d has a null pointer or an empty cache", i);
+        b.r[i] = DecodeReqDev{static_cast<const bf16*>(reqs[i].qkv), static_cast<bf16*>(reqs[i].cache_k), static_cast<bf16*>(reqs[i].cache_v),
+                              static_cast<bf16*>(reqs[i].out), reqs[i].counters, (int)reqs[i].cache_rows};
+    }
+    decode_attention_fused_kernel<16><<<dim3(Hq, n_req), 16 * 32, 0, s>>>(b, Hq, Hkv, ldc, cs, sn, scale);
     PE_CHECK_CUDA(h, cudaGetLastError());
     return PE_OK;
 }

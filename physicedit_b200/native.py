@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pe_rmsnorm", "pe_gemv", "pe_act", "pe_timestep_embedding", "pe_patchify", "pe_unpatchify", "pe_cfg_euler_step",
     "pe_special_gather", "pe_special_blend_scatter",
     "pe_conv2d", "pe_channel_rmsnorm", "pe_upsample2x", "pe_space_to_depth", "pe_nchw_to_nhwc", "pe_nhwc_to_nchw", "pe_transpose",
-    "pe_softmax_rows", "pe_softmax_rows_masked", "pe_gemv_swiglu", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
+    "pe_softmax_rows", "pe_softmax_rows_masked", "pe_gemv_swiglu", "pe_decode_attention_fused", "pe_attention_bwd_delta", "pe_gemm_batched", "pe_attention_fwd_lse",
     "pe_gemv_fused", "pe_swiglu", "pe_rope_half", "pe_range_attention", "pe_gather_rows", "pe_argmax", "pe_kv_append", "pe_rope_kv_append", "pe_advance",
 ]
 
@@ -62,6 +62,11 @@ class GemmSeg(Structure):
         ("norm_q_w", c_void_p), ("norm_k_w", c_void_p), ("rope", c_void_p),
         ("q_route", c_void_p * 8), ("k_route", c_void_p * 8), ("v_route", c_void_p * 8), ("route_ranks", c_int32), ("_pad1", c_int32),
     ]
+
+
+class DecodeReq(Structure):
+    """Mirror of `pe_decode_req` (include/pe_b200.h)."""
+    _fields_ = [("qkv", c_void_p), ("cache_k", c_void_p), ("cache_v", c_void_p), ("out", c_void_p), ("counters", c_void_p), ("cache_rows", c_int64)]
 
 
 class GemmBatch(Structure):
@@ -119,6 +124,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pe_nhwc_to_nchw.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     lib.pe_transpose.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]
     lib.pe_softmax_rows.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]
+    lib.pe_decode_attention_fused.argtypes = [c_void_p, POINTER(DecodeReq), c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_float, c_void_p]
     lib.pe_gemv_swiglu.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p]
     lib.pe_softmax_rows_masked.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_int, c_void_p]
     lib.pe_gemm_batched.argtypes = [c_void_p, POINTER(GemmSeg), POINTER(GemmBatch), c_int, c_int, c_int, c_int, c_void_p]
@@ -504,6 +510,21 @@ class Native:
         batch = 1 if x.dim() == 1 else x.shape[0]
         self._check(self.lib.pe_gemv_fused(self.h, x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), batch, w.shape[0], w.shape[1], act_in,
                                            _ptr(norm_w), eps, _ptr(residual), self._stream_prof()), "pe_gemv_fused")
+        self.launches += 1
+
+    def decode_attention_fused(self, qkv_rows, caches, outs, counters, Hq: int, Hkv: int, D: int, cos, sin, scale: float) -> None:
+        """One decode step's rope + KV append + attention for len(qkv_rows) <= 8 requests in one launch.  qkv_rows[i] [(Hq + 2 Hkv) * D], caches[i] =
+        (cache_k, cache_v) [cap, ldc], outs[i] [Hq * D], counters[i] int32 [>= 2] = (cache rows before the append, rope row)."""
+        n = len(qkv_rows)
+        arr = (DecodeReq * n)()
+        for i in range(n):
+            ck, cv = caches[i]
+            _bf16(qkv_rows[i], "qkv"); _bf16(ck, "cache_k"); _bf16(cv, "cache_v"); _bf16(outs[i], "out")
+            if ck.stride(0) != cv.stride(0) or ck.stride(0) != caches[0][0].stride(0) or ck.shape != cv.shape:
+                raise NativeError("decode_attention_fused: all caches must share one row stride")
+            arr[i] = DecodeReq(qkv_rows[i].data_ptr(), ck.data_ptr(), cv.data_ptr(), outs[i].data_ptr(), counters[i].data_ptr(), ck.shape[0])
+        self._check(self.lib.pe_decode_attention_fused(self.h, arr, n, Hq, Hkv, D, caches[0][0].stride(0), cos.data_ptr(), sin.data_ptr(), scale,
+                                                       self._stream_prof()), "pe_decode_attention_fused")
         self.launches += 1
 
     def gemv_swiglu(self, x, w, bias, y, norm_w=None, eps: float = 1e-6) -> None:

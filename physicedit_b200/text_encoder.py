@@ -524,12 +524,9 @@ class QwenImageTextEncoder(nn.Module):
                     # rope + KV append are one kernel (same arithmetic and rounding points as the unfused sequence below)
                     nat.tag = "te_gemv_qkv"
                     nat.gemv_fused(B["x"], pk["wqkv"], pk["bqkv"], B["qkv"], norm_w=l.input_layernorm.weight, eps=c.rms_eps)
-                    for b in range(nb):
-                        nat.tag = "te_rope_kv"
-                        nat.rope_kv_append(B["qkv"][b], c.heads, c.kv_heads, c.head_dim, cos_d, sin_d, caches[b][i][0], caches[b][i][1], ctr[b])
-                        nat.tag = "te_attention"
-                        nat.range_attention(B["qkv"][b:b + 1, :HD], caches[b][i][0], caches[b][i][1], B["att"][b:b + 1], c.heads, c.kv_heads, c.head_dim,
-                                            c.head_dim ** -0.5, kv_len_ptr=ctr[b, 3:4])
+                    nat.tag = "te_attention"                     # rope + KV append + attention of every request: one launch
+                    nat.decode_attention_fused([B["qkv"][b] for b in range(nb)], [caches[b][i] for b in range(nb)], [B["att"][b] for b in range(nb)],
+                                               [ctr[b] for b in range(nb)], c.heads, c.kv_heads, c.head_dim, cos_d, sin_d, c.head_dim ** -0.5)
                     nat.tag = "te_gemv_o"
                     nat.gemv_fused(B["att"], l.self_attn.o_proj.weight, None, B["x"], residual=B["x"])
                     nat.tag = "te_gemv_gate_up"

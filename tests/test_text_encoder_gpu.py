@@ -334,3 +334,37 @@ def test_pipeline_call_with_the_optional_controls():
     with_interp = pipe("make the ice melt", edit_rope_interpolation=True, **common)
     assert torch.equal(with_interp, plain)                       # same-size edit image: forward_sampling builds the plain tables (:179)
     nat.check_async()
+
+
+@gpu
+def test_fused_decode_attention_equals_rope_append_then_attention():
+    """pe_decode_attention_fused (rope + KV append + one-query attention of two requests in one launch) == pe_rope_kv_append + pe_range_attention per
+    request, bit for bit: outputs, and the rows appended to both caches."""
+    from physicedit_b200 import native as nv
+    nat = nv.Native.get(0)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Hq, Hkv, D = 28, 4, 128
+    HD, KD = Hq * D, Hkv * D
+    ang = torch.randn(600, D // 2, device="cuda", generator=g) * 3
+    emb = torch.cat([ang, ang], -1)
+    cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+    reqs = []
+    for cap, n_prev, row in ((500, 333, 340), (420, 17, 17)):
+        ck = torch.randn(cap, KD, device="cuda", generator=g).bfloat16()
+        cv = torch.randn(cap, KD, device="cuda", generator=g).bfloat16()
+        qkv = torch.randn(HD + 2 * KD, device="cuda", generator=g).bfloat16()
+        ctr = torch.tensor([n_prev, row, 0, n_prev + 1], dtype=torch.int32, device="cuda")
+        reqs.append((ck, cv, qkv, ctr))
+    # two-launch reference on copies
+    want = []
+    for ck, cv, qkv, ctr in reqs:
+        ck2, cv2, q2 = ck.clone(), cv.clone(), qkv.clone()
+        nat.rope_kv_append(q2, Hq, Hkv, D, cos, sin, ck2, cv2, ctr)
+        o = torch.empty(1, HD, device="cuda", dtype=torch.bfloat16)
+        nat.range_attention(q2[:HD].view(1, HD), ck2, cv2, o, Hq, Hkv, D, D ** -0.5, kv_len_ptr=ctr[3:4])
+        want.append((o[0], ck2, cv2))
+    outs = [torch.empty(HD, device="cuda", dtype=torch.bfloat16) for _ in reqs]
+    nat.decode_attention_fused([r[2] for r in reqs], [(r[0], r[1]) for r in reqs], outs, [r[3] for r in reqs], Hq, Hkv, D, cos, sin, D ** -0.5)
+    for (o, ck2, cv2), got, (ck, cv, _, _) in zip(want, outs, reqs):
+        assert torch.equal(got, o) and torch.equal(ck, ck2) and torch.equal(cv, cv2)
+    nat.check_async()
