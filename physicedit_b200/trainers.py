@@ -193,8 +193,9 @@ def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e
     loader = torch.utils.data.DataLoader(dataset, shuffle=sampler is None, sampler=sampler, collate_fn=lambda x: x[0], num_workers=num_workers)
     wrapped = model
     if ranks.distributed:
-        dev = next(p for p in model.parameters() if p.is_cuda).device
-        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=find_unused_parameters)
+        cuda = next((p.device for p in model.parameters() if p.is_cuda), None)
+        wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=None if cuda is None else [cuda.index],
+                                                            find_unused_parameters=find_unused_parameters)
     micro = 0
     for epoch_id in range(num_epochs):
         if sampler is not None:

@@ -256,3 +256,26 @@ def test_eligen_oracle_matches_reference(golden):
                    edit_latents=inp["edit_latents"], entity=dict(prompt_emb=g["entity_prompt_emb"], masks=g["entity_masks"]))
     assert g["differs_from_plain"] > 1e-3
     assert ((y - g["y"]).norm() / g["y"].norm()).item() < 2e-5
+
+
+def test_entity_attention_mask_host_logic_matches_the_oracle():
+    """physicedit_b200.model_fn.entity_attention_mask (pure torch: runs on the CPU) == the boolean form of the oracle's process_entity_masks mask
+    (itself pinned to the reference by test_eligen_oracle_matches_reference), with an edit image and three entities of different lengths."""
+    from physicedit_b200.model_fn import entity_attention_mask
+    H = W = 96
+    g = torch.Generator().manual_seed(1)
+    masks = (torch.rand(1, 3, 1, H // 8, W // 8, generator=g) > 0.6).float()
+    lat = [torch.zeros(1, 16, H // 8, W // 8), torch.zeros(1, 16, H // 8, W // 8)]
+    seg = [5, 11, 3, 20]
+    ents = [torch.zeros(1, n, 3584) for n in seg[:-1]]
+    Wt = {"txt_norm.weight": torch.ones(3584), "txt_in.weight": torch.zeros(8, 3584), "txt_in.bias": torch.zeros(8)}
+    n_img = 2 * (H // 16) * (W // 16)
+    _, _, add = O.process_entity_masks(Wt, lat[0], torch.zeros(1, seg[-1], 3584), seg[-1], ents, masks, H, W, n_img, [(1, H // 16, W // 16)] * 2)
+    got = entity_attention_mask(masks, seg, lat)
+    assert got.dtype == torch.uint8 and got.shape == (sum(seg) + n_img,) * 2
+    assert torch.equal(got.bool(), add[0, 0] == 0)
+    assert got.diagonal().all()                                   # every token sees itself: no empty softmax row
+    with pytest.raises(ValueError, match="entity"):
+        entity_attention_mask(masks, seg[1:], lat)
+    with pytest.raises(ValueError, match="latent size"):
+        entity_attention_mask(masks, seg, [lat[0], torch.zeros(1, 16, 10, 14)])

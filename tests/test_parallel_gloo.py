@@ -205,3 +205,74 @@ def test_cfg_parallel_pair_runs_one_branch_per_rank_and_exchanges():
         assert p.exitcode == 0
     assert res[0] == (0, 0, 1, ["posi"], 1.0, -2.0)
     assert res[1] == (1, 0, 1, ["nega"], 1.0, -2.0)
+
+
+class _ToyData(torch.utils.data.Dataset):
+    load_from_cache = False
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.randn(4, 6, generator=g)
+        self.y = torch.randn(4, 2, generator=g)
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        return dict(x=self.x[i], y=self.y[i])
+
+
+def _toy_module():
+    from physicedit_b200.trainers import DiffusionTrainingModule
+
+    class Toy(DiffusionTrainingModule):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(7)
+            self.pipe = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+            self.pipe[0].requires_grad_(False)                       # a frozen part: must not appear in the checkpoint
+
+        def forward(self, data, inputs=None):
+            return torch.nn.functional.mse_loss(self.pipe(data["x"]), data["y"])
+    return Toy()
+
+
+def _train_worker(rank, world, port, q, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from physicedit_b200.trainers import ModelLogger, launch_training_task
+        model = _toy_module()
+        launch_training_task(_ToyData(), model, ModelLogger(out_dir, remove_prefix_in_ckpt="pipe."), learning_rate=1e-2, weight_decay=0.0, num_workers=0,
+                             num_epochs=2, gradient_accumulation_steps=1, find_unused_parameters=False)
+        q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_launch_training_task_world2_matches_single_process_accumulation(tmp_path):
+    """launch_training_task (trainers/utils.py:932-977 on plain torch.distributed): 2 ranks x DDP over a DistributedSampler leave identical
+    parameters on both ranks, only rank 0 writes the trainable-only checkpoints with the prefix stripped, and the run equals one process that
+    accumulates the same two samples per optimizer step (same seeds -> same shuffles)."""
+    from safetensors.torch import load_file
+    from physicedit_b200.trainers import ModelLogger, launch_training_task
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, str(tmp_path / "ddp"))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(res[0], res[1])
+    files = sorted(os.listdir(tmp_path / "ddp"))
+    assert files == ["epoch-0.safetensors", "epoch-1.safetensors"]
+    ck = load_file(str(tmp_path / "ddp" / "epoch-1.safetensors"))
+    assert set(ck) == {"2.weight", "2.bias"}                                           # trainable only, "pipe." stripped
+    assert torch.allclose(ck["2.weight"].flatten(), res[0][-12:-2], atol=0) and torch.allclose(ck["2.bias"], res[0][-2:], atol=0)
+    # the frozen layer did not move
+    torch.manual_seed(7)
+    ref0 = torch.nn.Linear(6, 5)
+    assert torch.equal(res[0][:30], ref0.weight.detach().flatten())
