@@ -147,7 +147,7 @@ class _LinearFn(torch.autograd.Function):
             xt = _transposed(nat, x2, extra_rows=8 if need_b else 0, ones_row=need_b)     # [K (+8), Mp]: the ones row makes column K the bias gradient
             g = _gemm(nat, dyt, xt)                                        # [N, K (+8)]
             if ctx.needs_input_grad[1]:
-                dw = g[:, :K] if need_b else g
+                dw = g[:, :K].contiguous() if need_b else g
             if need_b:
                 db = g[:, K].contiguous()
         return dx, dw, db
