@@ -93,6 +93,24 @@ def make_cfg_pairs():
     return mine, rank // 2, world // 2
 
 
+def make_cfg_sequence_groups():
+    """One image on ALL ranks, both latency modes at once: the world is cut into two halves, each half runs ONE CFG branch of every step
+    sequence-parallel (ulysses.py), and rank i of the first half is paired with rank i of the second for the per-step exchange of the two
+    predictions.  Returns (this rank's sequence-parallel group, its CFG pair group).  Every rank must call it (new_group is collective).
+        sp, pair = parallel.make_cfg_sequence_groups(); pipe.enable_sequence_parallel(sp); pipe.cfg_parallel_group = pair"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world % 2:
+        raise ValueError(f"needs an even number of ranks (world size {world})")
+    half = world // 2
+    halves = [dist.new_group(list(range(0, half))), dist.new_group(list(range(half, world)))]
+    mine_pair = None
+    for i in range(half):
+        g = dist.new_group([i, i + half])
+        if rank % half == i:
+            mine_pair = g
+    return halves[rank // half], mine_pair
+
+
 def exchange_cfg_predictions(vp: torch.Tensor, vn: torch.Tensor, rank_in_pair: int, group) -> None:
     """After rank 0 of the pair filled `vp` (positive branch) and rank 1 filled `vn`, makes both tensors valid on both ranks.
     vp / vn are the two halves of one contiguous [2, ...] buffer (pipeline.denoise allocates them so): with NCCL this is a single

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--resolution", type=int, default=1024)
 ap.add_argument("--layers", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--cfg-split", action="store_true", help="two halves of the world, one CFG branch each (sequence-parallel inside a half)")
 args = ap.parse_args()
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -52,14 +53,19 @@ def run(steps, timed=False):
 
 ref, _ = run(2)
 ref_t = run(args.steps, timed=True)[1]
-pipe.enable_sequence_parallel()
+if args.cfg_split:
+    sp_group, pair_group = parallel.make_cfg_sequence_groups()
+    pipe.enable_sequence_parallel(sp_group)
+    pipe.cfg_parallel_group = pair_group
+else:
+    pipe.enable_sequence_parallel()
 out, _ = run(2)
 same = torch.tensor([int(torch.equal(ref, out))], device=dev)
 dist.all_reduce(same, op=dist.ReduceOp.MIN)
 rel = ((out.float() - ref.float()).norm() / ref.float().norm()).item()
 sp_t = run(args.steps, timed=True)[1]
 if rank == 0:
-    print(json.dumps({"ranks": N, "resolution": args.resolution, "layers": args.layers, "bit_identical_on_all_ranks": bool(same.item()), "rel_l2_vs_single_gpu": rel,
+    print(json.dumps({"ranks": N, "mode": "cfg branch per half x sequence-parallel inside" if args.cfg_split else "sequence-parallel", "resolution": args.resolution, "layers": args.layers, "bit_identical_on_all_ranks": bool(same.item()), "rel_l2_vs_single_gpu": rel,
                       "single_gpu_ms_per_step": round(ref_t, 2), "sequence_parallel_ms_per_step": round(sp_t, 2), "speedup": round(ref_t / sp_t, 3),
                       "finite": bool(torch.isfinite(out.float()).all())}))
 dist.destroy_process_group()
