@@ -53,3 +53,17 @@ def test_training_step_under_ddp_matches_gradient_accumulation():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert res["ranks_identical"] and res["grad_rel_l2_ddp_vs_accumulation"] < 2e-2, res
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs four GPUs")
+def test_cfg_branch_per_half_with_sequence_parallel_halves_is_bit_identical():
+    """parallel.make_cfg_sequence_groups(): two halves of the world, one CFG branch each, sequence-parallel inside a half: same latents as the single-GPU loop on
+    every rank (tools/ulysses_check.py --cfg-split)."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1", "--master-port", "29555",
+           os.path.join(ROOT, "tools", "ulysses_check.py"), "--resolution", "512", "--layers", "2", "--steps", "2", "--cfg-split"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["bit_identical_on_all_ranks"] and res["finite"] and res["ranks"] == 4, res
