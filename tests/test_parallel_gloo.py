@@ -276,3 +276,39 @@ def test_launch_training_task_world2_matches_single_process_accumulation(tmp_pat
     torch.manual_seed(7)
     ref0 = torch.nn.Linear(6, 5)
     assert torch.equal(res[0][:30], ref0.weight.detach().flatten())
+
+
+def _groups_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sp, pair = parallel.make_cfg_sequence_groups()
+        # what a step does with them: the half's ranks agree on a value (stand-in for the sequence-parallel forward), then the pair exchanges predictions
+        t = torch.tensor([float(rank)])
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=sp)
+        vbuf = torch.zeros(2, 3)
+        r = dist.get_rank(pair)
+        vbuf[r] = t.item() + 100 * r
+        parallel.exchange_cfg_predictions(vbuf[0], vbuf[1], r, pair)
+        q.put((rank, dist.get_world_size(sp), dist.get_rank(sp), dist.get_world_size(pair), r, t.item(), vbuf[:, 0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_split_sequence_groups_world4():
+    """parallel.make_cfg_sequence_groups on 4 gloo ranks: halves {0,1} / {2,3} are the sequence-parallel groups, (0,2) and (1,3) the CFG pairs; rank i of
+    the first half holds the positive branch (pair rank 0), its partner the negative one, and after the exchange both hold both predictions."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_groups_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, sp_n, sp_r, pair_n, pair_r, half_sum, both in res:
+        assert sp_n == 2 and pair_n == 2 and sp_r == rank % 2 and pair_r == rank // 2
+        assert half_sum == (1.0 if rank < 2 else 5.0)                                  # 0 + 1 | 2 + 3
+        assert both == [1.0, 105.0]                                                    # [positive half's value, negative half's value + 100]
