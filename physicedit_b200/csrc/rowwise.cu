@@ -123,8 +123,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) layernorm_kernel(const bf16
 // (its speed followed the SM clock).  Arithmetic and rounding points are those of layernorm_kernel<12, 0>.
 // -------------------------------------------------------------------------------------------------
 constexpr int kLnC = 3072;
-constexpr int kLnWarps = 8;
-constexpr int kLnSlots = 3;
+#ifndef PE_LN_WARPS
+#define PE_LN_WARPS 8
+#endif
+#ifndef PE_LN_SLOTS
+#define PE_LN_SLOTS 3
+#endif
+constexpr int kLnWarps = PE_LN_WARPS;
+constexpr int kLnSlots = PE_LN_SLOTS;
 constexpr int kLnRowBytes = kLnC * 2;
 constexpr int kLnSmem = kLnWarps * kLnSlots * kLnRowBytes + 4 * kLnRowBytes + kLnWarps * kLnSlots * 8 + 128;
 
