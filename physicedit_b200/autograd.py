@@ -21,7 +21,7 @@ Inference never comes here (model_fn routes here only when a gradient is require
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 import torch.nn.functional as F

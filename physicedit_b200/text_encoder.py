@@ -24,8 +24,7 @@ bf16 on an sm_100 GPU only; batch 1 (the pipeline is strictly B=1, :688,821).
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import torch

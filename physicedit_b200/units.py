@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import json
 import math
-from typing import Any, Dict, List, Optional
+from typing import List
 
 import torch
 
