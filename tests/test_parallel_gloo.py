@@ -245,7 +245,7 @@ def _train_worker(rank, world, port, q, out_dir):
         model = _toy_module()
         launch_training_task(_ToyData(), model, ModelLogger(out_dir, remove_prefix_in_ckpt="pipe."), learning_rate=1e-2, weight_decay=0.0, num_workers=0,
                              num_epochs=2, gradient_accumulation_steps=1, find_unused_parameters=False)
-        q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()])))
+        q.put((rank, torch.cat([p.detach().flatten() for p in model.parameters()]).tolist()))      # plain lists: a tensor in the queue needs the sender alive
     finally:
         dist.destroy_process_group()
 
@@ -262,7 +262,7 @@ def test_launch_training_task_world2_matches_single_process_accumulation(tmp_pat
     procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, str(tmp_path / "ddp"))) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=180) for _ in procs)
+    res = {r: torch.tensor(v) for r, v in (q.get(timeout=180) for _ in procs)}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
