@@ -480,8 +480,9 @@ constexpr int kSplitK = 4;
 constexpr int kSplitRows = 2;      // rows per warp
 constexpr int kSplitDepth = 2;     // 16-byte vectors per row in flight per lane (plus the same again being consumed)
 
+// capped at 64 registers = 4 CTAs per SM (batch 2 would take 75 -> 3 per SM: A/B on B200 41.1 -> 31.0 us; the same cap on the wide kernel spills and loses)
 template <int kBatch>
-__global__ void __cluster_dims__(kSplitK, 1, 1) __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __cluster_dims__(kSplitK, 1, 1) __launch_bounds__(kWarpsPerCta * 32, 4)
 gemv_splitk_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias, bf16* __restrict__ y, int N, int K, int act_in,
                    const bf16* __restrict__ residual) {
     namespace cg = cooperative_groups;
