@@ -272,6 +272,22 @@ def test_from_pretrained_recognises_files_by_content(tmp_path, capsys):
     assert len(nets) == 2 and nets[0].img_in.weight.shape == (3072, 64) and nets[1].img_in.weight.shape == (3072, 68)
     assert torch.equal(nets[0].controlnet_blocks[0].input_proj.weight, cn["controlnet_blocks.0.input_proj.weight"])
     assert "cannot detect the model type" in capsys.readouterr().out
+    # the scripts' way of naming files (inference_pica.py:229-241): ModelConfig(model_id, origin_file_pattern, local_model_path) -> a glob over local
+    # files; several shards of one model are merged before the model is recognised
+    shard_dir = tmp_path / "models" / "Org" / "Net" / "controlnet"
+    shard_dir.mkdir(parents=True)
+    keys = sorted(cn)
+    save_file({k: cn[k] for k in keys[:3]}, str(shard_dir / "part-00001-of-00002.safetensors"))
+    save_file({k: cn[k] for k in keys[3:]}, str(shard_dir / "part-00002-of-00002.safetensors"))
+    cfg = pe.ModelConfig(model_id="Org/Net", origin_file_pattern="controlnet/part-*.safetensors", local_model_path=str(tmp_path / "models"))
+    pipe2 = pe.QwenImagePhysicPipeline.from_pretrained(torch_dtype=torch.bfloat16, device="cpu", dinov2_path=dino, model_configs=[cfg])
+    assert isinstance(cfg.path, list) and len(cfg.path) == 2 and len(pipe2.blockwise_controlnet.models) == 1
+    assert torch.equal(pipe2.blockwise_controlnet.models[0].controlnet_blocks[0].output_proj.weight, cn["controlnet_blocks.0.output_proj.weight"])
+    folder = pe.ModelConfig(model_id="Org/Net", origin_file_pattern="controlnet/", local_model_path=str(tmp_path / "models"))
+    folder.download_if_necessary()
+    assert folder.path == os.path.join(str(tmp_path / "models" / "Org" / "Net"), "controlnet/")         # folders keep the pattern's trailing slash (:216)
+    with pytest.raises(ValueError, match="No valid model files"):
+        pe.ModelConfig().download_if_necessary()
 
 
 def test_hot_lora_surface():
