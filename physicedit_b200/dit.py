@@ -356,8 +356,7 @@ class DiTEngine:
         m2 = torch.zeros(2 * DIM, dtype=torch.uint8, device=self.device)
         m2[:DIM] = 1                                                   # AdaLayerNorm(single): (scale, shift)
         self.mask2 = m2
-        self._mods_cache = None
-        self._cond_table = None
+        self.invalidate()
 
     def refresh_if_stale(self):
         blocks = self.dit.transformer_blocks
@@ -368,9 +367,14 @@ class DiTEngine:
                 return
 
     def invalidate(self):
-        """Call after modifying weights in place (LoRA fold): drops cached modulation vectors."""
+        """Call after modifying weights in place (LoRA fold): drops cached modulation vectors and the training path's cached weight transposes
+        (a write through `.data`, as the LoRA loader does, does not bump the version the transpose cache is keyed on)."""
         self._mods_cache = None
         self._cond_table = None
+        import sys
+        ag = sys.modules.get("physicedit_b200.autograd")
+        if ag is not None:
+            ag.weight_transposes.clear()
 
     # -- cached per-shape state ---------------------------------------------------------------------
     def workspace(self, S_img: int, T: int, branch: int = 0) -> Workspace:

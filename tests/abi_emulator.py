@@ -105,3 +105,43 @@ class EmulatedNative:
         probs.zero_()
         probs[:, :n] = p.to(torch.bfloat16)
         self._note("pe_softmax_rows")
+
+    # ---- training path (include/pe_b200.h: pe_gemm_batched, pe_attention_fwd_lse, pe_attention_bwd_delta) ------------------------------
+    def linear(self, x, w, bias, epilogue=EPI_BIAS, flags=0):
+        out = torch.empty(x.shape[0], w.shape[0], dtype=torch.bfloat16)
+        self.gemm([dict(a=x, w=w, bias=bias, out=out)], w.shape[0], w.shape[1], epilogue, flags)
+        return out
+
+    def attention_lse(self, q, k, v, o, lse, H, scale, flags=0):
+        """o = softmax(scale q k^T) v per head (token-major [S, H * 128]); lse[h, s] = log2 sum_j exp2(scale log2(e) s_j)."""
+        S = q.shape[0]
+        hm = lambda t: t.float().view(S, H, -1).transpose(0, 1)
+        sc = hm(q) @ hm(k).transpose(1, 2) * scale
+        lse.copy_(torch.logsumexp(sc, dim=-1) * 1.4426950408889634)
+        p = _r(torch.softmax(sc, dim=-1))                               # the kernel feeds bf16 probabilities to the P V product
+        o.copy_((p @ hm(v)).transpose(0, 1).reshape(S, -1).to(torch.bfloat16))
+        self._note("pe_attention_fwd_lse")
+
+    def attention_bwd_delta(self, d_o, o, delta, H):
+        S = o.shape[0]
+        delta[:, :S] = (d_o.float() * o.float()).view(S, H, -1).sum(-1).t()
+        self._note("pe_attention_bwd_delta")
+
+    def gemm_batched(self, a, w, out, batch, M, N, K, a_batch_rows, w_batch_rows, out_batch_rows, epilogue=EPI_BIAS, vec=None, vec_batch_stride=0,
+                     vec_per_column=False, alpha=1.0, flags=0):
+        """Problem b: rows [b * a_batch_rows, + M) of a times rows [b * w_batch_rows, + N) of w -> rows [b * out_batch_rows, + M) of out; only those rows /
+        the first N columns are written.  Epilogues: 0 plain, 7 fp32, 8 exp2(acc * alpha - vec[i]), 9 out * (acc - vec[i]) * alpha in place."""
+        assert N % 8 == 0 and K % 8 == 0 and w.stride(0) == K and a.stride(0) >= K
+        for b in range(batch):
+            acc = a[b * a_batch_rows: b * a_batch_rows + M, :K].float() @ w[b * w_batch_rows: b * w_batch_rows + N, :K].float().t()
+            dst = out[b * out_batch_rows: b * out_batch_rows + M]
+            if epilogue in (8, 9):
+                st = vec.reshape(-1)[b * vec_batch_stride:]
+                st = st[:N][None, :] if vec_per_column else st[:M][:, None]
+                val = torch.exp2(acc * alpha - st) if epilogue == 8 else dst[:, :N].float() * (acc - st) * alpha
+                dst[:, :N] = val.to(torch.bfloat16)
+            elif epilogue == EPI_F32:
+                dst[:, :N] = acc
+            else:
+                dst[:, :N] = acc.to(torch.bfloat16)
+        self._note("pe_gemm_batched")

@@ -1,0 +1,132 @@
+"""Host logic of the training path (physicedit_b200/autograd.py) on the CPU: the autograd Functions are run against tests/abi_emulator.py -- a
+contract-level emulation of the C-ABI entry points they call -- and their gradients compared with torch autograd on the same math in fp32.  What this
+pins without a GPU: which operand is transposed / padded for dX and dW, the bias-gradient-as-extra-column trick, the seven batched products and the
+row / column statistics of the attention backward, zero-padding of ragged sequence lengths, LoRA composition.  The GPU tests run the same host code on
+the real library (tests/test_training_gpu.py)."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from abi_emulator import EmulatedNative  # noqa: E402
+
+
+@pytest.fixture()
+def ag(monkeypatch):
+    from physicedit_b200 import autograd
+    emu = EmulatedNative()
+    monkeypatch.setattr(autograd, "_nat", lambda t: emu)
+    autograd.weight_transposes.clear()
+    autograd.emu = emu
+    return autograd
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(13, 16, 24, True), (40, 8, 64, False), (1, 32, 16, True), (64, 24, 8, True)])
+def test_linear_function_gradients(ag, M, N, K, bias):
+    g = torch.Generator().manual_seed(M * 100 + N)
+    x = torch.randn(3, M, K, generator=g).bfloat16().requires_grad_()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16().requires_grad_()
+    b = (torch.randn(N, generator=g) * 0.1).bfloat16().requires_grad_() if bias else None
+    dy = torch.randn(3, M, N, generator=g).bfloat16()
+    y = ag.linear(x, w, b)
+    assert y.shape == (3, M, N)
+    y.backward(dy)
+    x32, w32 = x.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    b32 = b.detach().float().requires_grad_() if bias else None
+    F.linear(x32, w32, b32).backward(dy.float())
+    assert rel(x.grad, x32.grad) < 6e-3 and rel(w.grad, w32.grad) < 6e-3 and x.grad.shape == x.shape and w.grad.is_contiguous()
+    if bias:
+        assert rel(b.grad, b32.grad) < 6e-3
+    names = [c[0] for c in ag.emu.calls]
+    assert names.count("pe_gemm") == 3 and names.count("pe_transpose") == 3          # Y, dX (+ W^T), dW|db (+ dY^T, X^T)
+
+
+def test_frozen_weight_transposes_are_cached_per_live_parameter(ag):
+    w = torch.nn.Parameter((torch.randn(16, 24) / 5).bfloat16(), requires_grad=False)
+    for _ in range(2):
+        x = torch.randn(9, 24).bfloat16().requires_grad_()
+        ag.linear(x, w, None).sum().backward()
+    assert [c[0] for c in ag.emu.calls].count("pe_transpose") == 1 and ag.weight_transposes.used == 16 * 24 * 2
+    with torch.no_grad():
+        w.add_(1)                                              # an in-place update bumps the version: a new transpose
+    ag.linear(torch.randn(9, 24).bfloat16().requires_grad_(), w, None).sum().backward()
+    assert [c[0] for c in ag.emu.calls].count("pe_transpose") == 2
+    # a write through .data (what GeneralLoRALoader.load does) is invisible to the version counter: the engine's invalidate() clears the cache
+    from physicedit_b200.dit import DiTEngine
+    w.data.add_(1)
+    DiTEngine.invalidate(type("E", (), {})())
+    assert ag.weight_transposes.used == 0
+    ag.linear(torch.randn(9, 24).bfloat16().requires_grad_(), w, None).sum().backward()
+    assert [c[0] for c in ag.emu.calls].count("pe_transpose") == 3
+    n_before = len(ag.weight_transposes.d)
+    del w
+    import gc
+    gc.collect()
+    assert len(ag.weight_transposes.d) < n_before              # the entry dies with the parameter (its address may be recycled)
+
+
+@pytest.mark.parametrize("S,H", [(37, 2), (64, 1), (21, 3)])
+def test_attention_function_gradients(ag, monkeypatch, S, H):
+    monkeypatch.setattr(ag, "HEAD_DIM", 16)
+    g = torch.Generator().manual_seed(S)
+    q, k, v, do = (torch.randn(S, H * 16, generator=g).bfloat16() for _ in range(4))
+
+    def run(native):
+        qq, kk, vv = (t.detach().clone().to(torch.bfloat16 if native else torch.float32).requires_grad_() for t in (q, k, v))
+        if native:
+            o = ag.attention(qq, kk, vv, H)
+        else:
+            hm = lambda t: t.view(S, H, 16).transpose(0, 1)
+            o = (torch.softmax(hm(qq) @ hm(kk).transpose(1, 2) / 4.0, dim=-1) @ hm(vv)).transpose(0, 1).reshape(S, H * 16)
+        o.backward(do.to(o.dtype))
+        return o.detach(), qq.grad, kk.grad, vv.grad
+    got, want = run(True), run(False)
+    for name, a, b in zip(("o", "dq", "dk", "dv"), got, want):
+        assert a.shape == b.shape and rel(a, b) < 1.2e-2, (name, rel(a, b))
+    names = [c[0] for c in ag.emu.calls]
+    assert names.count("pe_gemm_batched") == 7 and names.count("pe_attention_fwd_lse") == 1 and names.count("pe_attention_bwd_delta") == 1
+
+
+def test_lora_and_hot_lora_linear_match_their_formulas(ag):
+    from physicedit_b200.lora import HotLoRALinear, LoRALinear
+    torch.manual_seed(0)
+    base = torch.nn.Linear(24, 16).bfloat16()
+    m = LoRALinear(base, r=8, lora_alpha=16)
+    m.lora_B["default"].weight.data = (torch.randn(16, 8) * 0.3).bfloat16()
+    x = torch.randn(5, 24).bfloat16()
+    y = m(x)
+    A, B = m.lora_A["default"].weight.float(), m.lora_B["default"].weight.float()
+    want = F.linear(x.float(), base.weight.float(), base.bias.float()) + (x.float() @ A.t() @ B.t()) * 2.0
+    assert m.scaling == 2.0 and rel(y, want) < 6e-3
+    y.sum().backward()
+    assert m.lora_A["default"].weight.grad is not None and m.lora_B["default"].weight.grad is not None and base.weight.grad is None
+    h = HotLoRALinear(torch.nn.Linear(24, 16).bfloat16())
+    h.lora_A_weights.append(A.bfloat16()); h.lora_B_weights.append(B.bfloat16())
+    want_h = F.linear(x.float(), h.weight.float(), h.bias.float()) + x.float() @ A.t() @ B.t()
+    assert rel(h(x), want_h) < 6e-3
+
+
+def test_perceiver_attention_with_a_ragged_key_count(ag):
+    """n + m keys not a multiple of 8: the zero padding of k / v rows must not change the softmax."""
+    from physicedit_b200.adapters import PerceiverAttention
+    torch.manual_seed(1)
+    att = PerceiverAttention(dim=32, dim_head=8, heads=2).bfloat16()
+    x, lat = torch.randn(13, 32).bfloat16(), torch.randn(6, 32).bfloat16().requires_grad_()
+    out = ag.perceiver_attention(att, x, lat)
+    xn = F.layer_norm(x.float(), (32,), att.norm_media.weight.float(), att.norm_media.bias.float())
+    ln = F.layer_norm(lat.detach().float(), (32,), att.norm_latents.weight.float(), att.norm_latents.bias.float())
+    q = (ln @ att.to_q.weight.float().t()).view(6, 2, 8).transpose(0, 1)
+    k, v = (torch.cat((xn, ln)) @ att.to_kv.weight.float().t()).chunk(2, dim=-1)
+    k, v = k.view(19, 2, 8).transpose(0, 1), v.view(19, 2, 8).transpose(0, 1)
+    want = (torch.softmax(q @ k.transpose(1, 2) * att.scale, dim=-1) @ v).transpose(0, 1).reshape(6, 16) @ att.to_out.weight.float().t()
+    assert out.shape == (6, 32) and rel(out, want) < 2e-2
+    out.sum().backward()
+    assert lat.grad is not None and torch.isfinite(lat.grad.float()).all()
