@@ -100,8 +100,12 @@ class EmulatedNative:
         dst.copy_(src.t())
         self._note("pe_transpose")
 
-    def softmax_rows(self, scores, probs, n, scale):
-        p = torch.softmax(scores[:, :n].float() * scale, dim=-1)
+    def softmax_rows(self, scores, probs, n, scale, mask=None):
+        sc = scores[:, :n].float() * scale
+        if mask is not None:                                   # byte mask [period, >= n], 0 = hidden; score row r uses mask row r % period
+            rows = torch.arange(scores.shape[0]) % mask.shape[0]
+            sc = sc.masked_fill(mask[rows, :n] == 0, float("-inf"))
+        p = torch.softmax(sc, dim=-1)
         probs.zero_()
         probs[:, :n] = p.to(torch.bfloat16)
         self._note("pe_softmax_rows")

@@ -130,3 +130,24 @@ def test_perceiver_attention_with_a_ragged_key_count(ag):
     assert out.shape == (6, 32) and rel(out, want) < 2e-2
     out.sum().backward()
     assert lat.grad is not None and torch.isfinite(lat.grad.float()).all()
+
+
+def test_masked_attention_host_logic():
+    """DiTEngine.masked_attention (EliGen): head-major zero-padded operands, one byte mask shared by all heads of a batched score matrix, head chunking --
+    on the emulated ABI vs masked softmax attention in fp32; S = 21 is not a multiple of 8 and the scratch budget forces 5 chunks of heads."""
+    from physicedit_b200.dit import DiTEngine, NUM_HEADS
+    emu = EmulatedNative()
+    eng = type("E", (), {"nat": emu, "MASKED_ATTN_SCRATCH_BYTES": 6 * 24 * 24 * 5})()
+    S, H, D = 21, NUM_HEADS, 128
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (torch.randn(S, H * D, generator=g).bfloat16() for _ in range(3))
+    mask = torch.rand(S, S, generator=g) > 0.4
+    mask |= torch.eye(S, dtype=torch.bool)
+    o = torch.empty_like(q)
+    DiTEngine.masked_attention(eng, q, k, v, o, mask.to(torch.uint8))
+    hm = lambda t: t.float().view(S, H, D).transpose(0, 1)
+    sc = (hm(q) @ hm(k).transpose(1, 2) / math.sqrt(D)).masked_fill(~mask, float("-inf"))
+    want = (torch.softmax(sc, dim=-1) @ hm(v)).transpose(0, 1).reshape(S, H * D)
+    assert rel(o, want) < 8e-3
+    names = [c[0] for c in emu.calls]
+    assert names.count("pe_gemm_batched") == 2 * 5 and names.count("pe_softmax_rows") == 5          # ceil(24 heads / 5 per chunk) = 5 chunks
