@@ -39,10 +39,25 @@ class EmulatedNative:
             if s.get("bias") is not None:
                 acc = acc + s["bias"].float()[:N]
             y = _r(acc)
+            if epilogue == 3:                                   # PE_EPI_BIAS_GELU_ERF
+                y = 0.5 * y * (1.0 + torch.erf(y * 0.70710678118654752))
             if epilogue == EPI_GATE_RESIDUAL:
                 y = out[:, :N].float() + _r(s["gate"].float()[:N] * y)
             out[:, :N] = y.to(torch.bfloat16)
         self._note("pe_gemm")
+
+    def rmsnorm(self, x, out, w, eps=1e-6):
+        """models/utils.py:250-257: bf16(bf16(x * rsqrt(mean(x^2) + eps)) * w)."""
+        v = x.float()
+        y = _r(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps))
+        out.copy_((y * w.float() if w is not None else y).to(torch.bfloat16))
+        self._note("pe_rmsnorm")
+
+    def add_rows(self, x, add, period, alpha=1.0):
+        """x[r, :] = bf16(x[r, :] + alpha * add[r % period, :]) in place."""
+        rows = torch.arange(x.shape[0]) % period
+        x.copy_((x.float() + alpha * add.float()[rows]).to(torch.bfloat16))
+        self._note("pe_add_rows")
 
     def conv2d(self, x, H, W, C, w, bias, out, N, kh, kw, pad, epilogue=EPI_BIAS, gate=None, flags=0):
         cpad = (C + 63) // 64 * 64

@@ -2,7 +2,7 @@
 contract-level emulation of the C-ABI entry points they call -- and their gradients compared with torch autograd on the same math in fp32.  What this
 pins without a GPU: which operand is transposed / padded for dX and dW, the bias-gradient-as-extra-column trick, the seven batched products and the
 row / column statistics of the attention backward, zero-padding of ragged sequence lengths, LoRA composition.  The GPU tests run the same host code on
-the real library (tests/test_training_gpu.py)."""
+the real library (tests/test_training_gpu.py, tests/test_f5_gpu.py).  The file also covers the EliGen masked attention and the blockwise controlnet the same way."""
 import math
 import os
 import sys
@@ -151,3 +151,41 @@ def test_masked_attention_host_logic():
     assert rel(o, want) < 8e-3
     names = [c[0] for c in emu.calls]
     assert names.count("pe_gemm_batched") == 2 * 5 and names.count("pe_softmax_rows") == 5          # ceil(24 heads / 5 per chunk) = 5 chunks
+
+
+def test_blockwise_controlnet_host_logic(monkeypatch):
+    """QwenImageBlockwiseMultiControlNet.apply_ / preprocess on the emulated ABI vs the oracle's controlnet_sum (pinned to the reference by
+    tests/golden/f5.pt): activity windows, one vs several controlnets (the summed correction is rounded before it is added), token order of preprocess."""
+    from oracle import dit_oracle as O
+    from physicedit_b200 import native as nv
+    from physicedit_b200.compat import ControlNetInput
+    from physicedit_b200.controlnet import QwenImageBlockWiseControlNet, QwenImageBlockwiseMultiControlNet
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    L, n = 1, 16
+    sds = [{k: v.to(torch.bfloat16) for k, v in O.synth_weights(O.controlnet_param_shapes(L), seed=s).items()} for s in (61, 62)]
+    nets = []
+    for sd in sds:
+        m = QwenImageBlockWiseControlNet(num_layers=L).bfloat16()
+        m.load_state_dict(sd)
+        nets.append(m)
+    multi = QwenImageBlockwiseMultiControlNet(nets)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 3072, generator=g).bfloat16()
+    lat = [torch.randn(1, 16, 8, 8, generator=g).bfloat16() for _ in range(2)]
+    spec = [dict(scale=1.0, start=1.0, end=0.0), dict(scale=0.5, start=0.8, end=0.3)]
+    inputs = [ControlNetInput(controlnet_id=i, **s) for i, s in enumerate(spec)]
+    conds = multi.preprocess(inputs, lat)
+    ora = [dict(weights={k: v.float() for k, v in sd.items()}, latents=l.float(), **s) for sd, l, s in zip(sds, lat, spec)]
+    oconds = [O.controlnet_img_in(c["weights"], O.patchify(c["latents"])) for c in ora]
+    assert rel(conds[0], oconds[0]) < 6e-3 and conds[0].shape == (1, n, 3072)
+    for pid, n_active in ((0, 1), (2, 2), (4, 1)):                          # of 5 steps: progress 1.0, 0.5, 0.0
+        assert sum(multi.active(ci, pid, 5) for ci in inputs) == n_active
+        got = x.clone()
+        multi.apply_(got, conds, inputs, pid, 5, 0)
+        want = x.float() + O.controlnet_sum(ora, oconds, x.float()[None], 0, pid, 5)[0]
+        assert rel(got, want) < 8e-3, pid
+    off = [ControlNetInput(controlnet_id=0, scale=1.0, start=0.4, end=0.0)]
+    same = x.clone()
+    multi.apply_(same, conds[:1], off, 2, 5, 0)
+    assert torch.equal(same, x)
