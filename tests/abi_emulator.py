@@ -164,3 +164,75 @@ class EmulatedNative:
             else:
                 dst[:, :N] = acc.to(torch.bfloat16)
         self._note("pe_gemm_batched")
+
+    # ---- DiT block (include/pe_b200.h: pe_layernorm_modulate2, pe_gemv, pe_act, pe_attention_fwd, QKV / GELU epilogues of pe_gemm) -----
+    def act(self, x, y, act):
+        v = x.float()
+        y.copy_((_r(v / (1 + torch.exp(-v))) if act == 1 else v).to(torch.bfloat16))
+        self._note("pe_act")
+
+    def gemv(self, x, w, bias, y, act_in=0, act_out=0, one_plus_mask=None):
+        """y[b] = bf16(x[b] w^T + bias) (+ SiLU in / out); entries flagged in one_plus_mask come out as bf16(1 + y)."""
+        v = x.float()
+        if act_in == 1:
+            v = _r(v / (1 + torch.exp(-v)))
+        o = _r(v @ w.float().t() + (bias.float() if bias is not None else 0.0))
+        if act_out == 1:
+            o = _r(o / (1 + torch.exp(-o)))
+        if one_plus_mask is not None:
+            o = torch.where(one_plus_mask.bool()[None, :], _r(1.0 + o), o)
+        y.copy_(o.to(torch.bfloat16))
+        self._note("pe_gemv")
+
+    def layernorm_modulate2(self, x, out, split_row, shift0, ops0, shift1, ops1):
+        """rows < split_row: bf16(bf16(bf16(LN(x)) * ops0) + shift0); the others with (shift1, ops1); LN without affine, eps 1e-6, fp32 statistics."""
+        v = x.float()
+        n = _r((v - v.mean(-1, keepdim=True)) * torch.rsqrt(v.var(-1, unbiased=False, keepdim=True) + 1e-6))
+        first = (torch.arange(x.shape[0]) < split_row)[:, None]
+        ops = torch.where(first, ops0.float()[None], ops1.float()[None])
+        sh = torch.where(first, shift0.float()[None], shift1.float()[None])
+        out.copy_(_r(_r(n * ops) + sh).to(torch.bfloat16))
+        self._note("pe_layernorm_modulate2")
+
+    def attention(self, q, k, v, o, H, scale, flags=0):
+        S = q.shape[0]
+        hm = lambda t: t.float().view(S, H, -1).transpose(0, 1)
+        p = _r(torch.softmax(hm(q) @ hm(k).transpose(1, 2) * scale, dim=-1))
+        o.copy_((p @ hm(v)).transpose(0, 1).reshape(S, -1).to(torch.bfloat16))
+        self._note("pe_attention_fwd")
+
+
+def _qkv_epilogue(acc, seg, N):
+    """PE_EPI_QKV_NORM_ROPE: acc [M, 3 * H * 128] = (q heads | k heads | v heads) + bias -> bf16; per-head RMSNorm * w and RoPE (fp32 complex multiply with
+    the (cos, sin) table [M, 64, 2]) on q and k; three outputs."""
+    y = _r(acc + seg["bias"].float()[:N])
+    M, HD = y.shape[0], N // 3
+    H = HD // 128
+    cs = seg["rope"].float()[:M]
+    c, s_ = cs[:, None, :, 0], cs[:, None, :, 1]
+    for part, dst, wn in ((0, seg["out"], seg["norm_q_w"]), (1, seg["out_k"], seg["norm_k_w"]), (2, seg["out_v"], None)):
+        t = y[:, part * HD:(part + 1) * HD].reshape(M, H, 128)
+        if wn is not None:
+            t = _r(_r(t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)) * wn.float())
+            pr = t.reshape(M, H, 64, 2)
+            t = torch.stack((pr[..., 0] * c - pr[..., 1] * s_, pr[..., 0] * s_ + pr[..., 1] * c), dim=-1).reshape(M, H, 128)
+        dst[:, :HD] = t.reshape(M, HD).to(torch.bfloat16)
+
+
+_plain_gemm = EmulatedNative.gemm
+
+
+def _gemm_with_block_epilogues(self, segs, N, K, epilogue=EPI_BIAS, flags=0):
+    if epilogue == 5:                                          # PE_EPI_QKV_NORM_ROPE
+        for s in segs:
+            _qkv_epilogue(s["a"][:, :K].float() @ s["w"].float().t(), s, N)
+        return self._note("pe_gemm")
+    if epilogue == 2:                                          # PE_EPI_BIAS_GELU_SIGMOID: h = bf16(acc + bias); out = h * bf16(sigmoid(bf16(1.702 h)))
+        for s in segs:
+            h = _r(s["a"][:, :K].float() @ s["w"].float().t() + s["bias"].float()[:N])
+            s["out"][:, :N] = (h * _r(torch.sigmoid(_r(1.702 * h)))).to(torch.bfloat16)
+        return self._note("pe_gemm")
+    return _plain_gemm(self, segs, N, K, epilogue, flags)
+
+
+EmulatedNative.gemm = _gemm_with_block_epilogues

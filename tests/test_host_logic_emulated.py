@@ -189,3 +189,34 @@ def test_blockwise_controlnet_host_logic(monkeypatch):
     same = x.clone()
     multi.apply_(same, conds[:1], off, 2, 5, 0)
     assert torch.equal(same, x)
+
+
+def test_dit_block_host_sequencing_matches_the_oracle_block():
+    """DiTEngine.run_block (9 C-ABI calls per double-stream block) on the emulated ABI vs oracle.block_forward in fp32: which modulation slice feeds which
+    LN / gate, the (img, txt) segment order of the grouped GEMMs, the fused [q; k; v] weight packing, the joint [text; image] layout, `1 + scale` mask."""
+    from oracle import dit_oracle as O
+    from physicedit_b200.dit import DIM, DiTEngine, QwenImageDiT, Workspace
+    emu = EmulatedNative()
+    W = O.synth_weights(O.dit_param_shapes(1), seed=33)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in W.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    assert dit.transformer_blocks[0].attn.to_k.weight.data_ptr() == eng.qkv_w[0][0][DIM:].data_ptr()          # parameters are views of the fused buffer
+    T, shapes = 24, [(1, 4, 4), (1, 4, 4)]
+    S_img = 32
+    g = torch.Generator().manual_seed(4)
+    text = torch.randn(1, T, DIM, generator=g).bfloat16()
+    image = torch.randn(1, S_img, DIM, generator=g).bfloat16()
+    temb = torch.randn(1, DIM, generator=g).bfloat16()
+    x = torch.cat([text[0], image[0]], dim=0).contiguous()
+    with torch.no_grad():
+        mods = eng.block_mods(temb, [0])
+        eng.run_block(0, x, T, mods[0, 0], eng.rope(shapes, T), Workspace(S_img, T, "cpu"))
+    W32 = {k: v.to(torch.bfloat16).float() for k, v in W.items()}
+    t_ref, i_ref = O.block_forward(W32, 0, image.float(), text.float(), temb.float(), O.rope_tables(shapes, T))
+    assert rel(x[:T], t_ref[0]) < 1.5e-2 and rel(x[T:], i_ref[0]) < 1.5e-2
+    assert [c[0] for c in emu.calls].count("pe_gemm") == 4 and [c[0] for c in emu.calls].count("pe_layernorm_modulate2") == 2
