@@ -236,3 +236,40 @@ def _gemm_with_block_epilogues(self, segs, N, K, epilogue=EPI_BIAS, flags=0):
 
 
 EmulatedNative.gemm = _gemm_with_block_epilogues
+
+
+# ---- the rest of a whole DiT forward: pe_patchify / pe_unpatchify / pe_layernorm_modulate / pe_timestep_embedding -----------------------
+def _patchify(self, latents, tokens):
+    C, H2, W2 = latents.shape[-3:]
+    x = latents.reshape(C, H2 // 2, 2, W2 // 2, 2)                 # C H P W Q -> (H W) (C P Q)
+    tokens.copy_(x.permute(1, 3, 0, 2, 4).reshape((H2 // 2) * (W2 // 2), C * 4))
+    self._note("pe_patchify")
+
+
+def _unpatchify(self, tokens, latents):
+    C, H2, W2 = latents.shape[-3:]
+    x = tokens[:, :C * 4].reshape(H2 // 2, W2 // 2, C, 2, 2)       # H W C P Q -> C (H P) (W Q)
+    latents.copy_(x.permute(2, 0, 3, 1, 4).reshape(latents.shape))
+    self._note("pe_unpatchify")
+
+
+def _layernorm_modulate(self, x, out, shift, one_plus_scale):
+    v = x.float()
+    n = _r((v - v.mean(-1, keepdim=True)) * torch.rsqrt(v.var(-1, unbiased=False, keepdim=True) + 1e-6))
+    out.copy_(_r(_r(n * one_plus_scale.float()) + shift.float()).to(torch.bfloat16))
+    self._note("pe_layernorm_modulate")
+
+
+def _timestep_embedding(self, t_in, out, raw=True):
+    """256-d sinusoid with the reference's bf16 quirks: ts = bf16(t * float(1/1000)) when raw, frequencies rounded to bf16, fp32 argument, cos half first."""
+    import math
+    t0 = t_in.float().reshape(-1)[:1]
+    ts = _r(t0 * torch.tensor(1.0 / 1000.0, dtype=torch.float64).float()) if raw else t0
+    freq = _r(torch.exp(-math.log(10000.0) * torch.arange(128, dtype=torch.float32) / 128.0))
+    arg = 1000.0 * (ts * freq)
+    out.copy_(torch.cat([torch.cos(arg), torch.sin(arg)]).to(torch.bfloat16))
+    self._note("pe_timestep_embedding")
+
+
+EmulatedNative.patchify, EmulatedNative.unpatchify = _patchify, _unpatchify
+EmulatedNative.layernorm_modulate, EmulatedNative.timestep_embedding = _layernorm_modulate, _timestep_embedding

@@ -220,3 +220,36 @@ def test_dit_block_host_sequencing_matches_the_oracle_block():
     t_ref, i_ref = O.block_forward(W32, 0, image.float(), text.float(), temb.float(), O.rope_tables(shapes, T))
     assert rel(x[:T], t_ref[0]) < 1.5e-2 and rel(x[T:], i_ref[0]) < 1.5e-2
     assert [c[0] for c in emu.calls].count("pe_gemm") == 4 and [c[0] for c in emu.calls].count("pe_layernorm_modulate2") == 2
+
+
+def test_whole_dit_forward_host_sequencing_matches_the_oracle(monkeypatch):
+    """DiTEngine.forward -- patchify of noise + edit latents, img_in, txt_norm + txt_in, timestep embedding + conditioning (modulation GEMVs with the
+    `1 + scale` slots, norm_out's (scale, shift) order), two blocks, norm_out + proj_out on the noise tokens only, unpatchify -- on the emulated ABI vs
+    oracle.model_fn in fp32 with the bf16 timestep bookkeeping; a non-square image and an edit image of another size."""
+    from oracle import dit_oracle as O
+    from physicedit_b200 import native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))          # TimestepEmbeddings.forward asks for the device's handle
+    L, H, Wd, T = 2, 64, 96, 40
+    W = O.synth_weights(O.dit_param_shapes(L), seed=35)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=L)
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in W.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    inp = O.synth_inputs(H, Wd, T, seed=36, dtype=torch.bfloat16, edit_hw=(80, 48))
+    t = torch.tensor([431.0]).to(torch.bfloat16)
+    out = torch.empty_like(inp["latents"])
+    with torch.no_grad():
+        eng.forward([inp["latents"], inp["edit_latents"]], t, inp["prompt_emb"][0].contiguous(), out, t_key=float(t[0]))
+        W32 = {k: v.to(torch.bfloat16).float() for k, v in W.items()}
+        want = O.model_fn(W32, None, inp["latents"].float(), t, inp["prompt_emb"].float().clone(), inp["prompt_emb_mask"], None, H, Wd,
+                          edit_latents=inp["edit_latents"].float(), cuda_scalar_div=True)
+    assert out.shape == want.shape == (1, 16, H // 8, Wd // 8)
+    print(f"whole forward on the emulated ABI vs fp32 oracle: {rel(out, want):.3e}")
+    assert rel(out, want) < 1e-2, rel(out, want)
+    names = [c[0] for c in emu.calls]
+    assert names.count("pe_patchify") == 2 and names.count("pe_unpatchify") == 1 and names.count("pe_attention_fwd") == L
