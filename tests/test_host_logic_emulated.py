@@ -253,3 +253,56 @@ def test_whole_dit_forward_host_sequencing_matches_the_oracle(monkeypatch):
     assert rel(out, want) < 1e-2, rel(out, want)
     names = [c[0] for c in emu.calls]
     assert names.count("pe_patchify") == 2 and names.count("pe_unpatchify") == 1 and names.count("pe_attention_fwd") == L
+
+
+def test_training_forward_and_backward_host_logic_matches_oracle_autograd(ag, monkeypatch):
+    """The CPU twin of tests/test_training_gpu.py: autograd.dit_forward (un-merged LoRA on 6 targets, per-block checkpointing, adapter rows carrying a graph)
+    + backward on the emulated ABI vs autograd through oracle.model_fn in fp32 with W_eff = W + B A."""
+    from oracle import dit_oracle as O
+    from physicedit_b200 import native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.lora import inject_lora
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: ag.emu))
+    H, Wd, T = 64, 64, 24
+    W = O.synth_weights(O.dit_param_shapes(1), seed=37)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in W.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    targets = ["to_q", "add_k_proj", "to_out.0", "img_mlp.net.2", "txt_mod.1", "to_v"]
+    inject_lora(dit, targets, r=8)
+    g = torch.Generator().manual_seed(6)
+    lora = {}
+    for name, p in dit.named_parameters():
+        if "lora_" in name:
+            p.data = (torch.randn(p.shape, generator=g) * (0.5 / math.sqrt(p.shape[1]))).bfloat16()
+            lora[name] = p
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), ag.emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    inp = O.synth_inputs(H, Wd, T, seed=38, dtype=torch.bfloat16)
+    t = torch.tensor([520.0]).to(torch.bfloat16)
+    target = torch.randn(1, 16, H // 8, Wd // 8, generator=g)
+    pe = inp["prompt_emb"].clone().requires_grad_()                       # stands for the rows the adapter wrote
+    pred = ag.dit_forward(dit, [inp["latents"], inp["edit_latents"]], t, pe, use_gradient_checkpointing=True)
+    loss = F.mse_loss(pred.float(), target)
+    loss.backward()
+    # oracle: same function of (A, B, prompt_emb) in fp32
+    W32 = {k: v.to(torch.bfloat16).float() for k, v in W.items()}
+    leaves = {k: v.detach().float().requires_grad_() for k, v in lora.items()}
+    for name in [n for n in leaves if ".lora_A." in n]:
+        mod = name.split(".lora_A.")[0]
+        W32[mod + ".weight"] = W32[mod + ".weight"] + leaves[mod + ".lora_B.default.weight"] @ leaves[name]
+    pe32 = inp["prompt_emb"].float().clone().requires_grad_()
+    want = O.model_fn(W32, None, inp["latents"].float(), t, pe32, inp["prompt_emb_mask"], None, H, Wd, edit_latents=inp["edit_latents"].float(),
+                      cuda_scalar_div=True)
+    loss32 = F.mse_loss(want, target)
+    loss32.backward()
+    assert abs(loss.item() - loss32.item()) < 5e-3 * loss32.item()
+    dead = [k for k, p in lora.items() if p.grad is None]
+    assert all("txt_mlp" in k or "to_add_out" in k for k in dead)          # the text tail of the last block has no gradient
+    cat = lambda d, grad=True: torch.cat([(d[k].grad if d[k].grad is not None else torch.zeros_like(d[k])).float().flatten() for k in sorted(d)])
+    e_lora, e_pe = rel(cat(lora), cat(leaves)), rel(pe.grad, pe32.grad)
+    print(f"emulated training step: loss {loss.item():.5f} vs {loss32.item():.5f}; LoRA grads {e_lora:.3e}; d prompt_emb {e_pe:.3e}")
+    assert e_lora < 3e-2 and e_pe < 3e-2
