@@ -293,9 +293,9 @@ class QwenImageTextEncoder(nn.Module):
     def _pack(self):
         c = self.cfg
         p = self.lm_head.weight
-        if not p.is_cuda or p.dtype != torch.bfloat16:
+        if p.dtype != torch.bfloat16:
             raise nv.NativeUnavailable(f"the native text encoder runs in bfloat16 on an sm_100 GPU only (got {p.dtype} on {p.device}); no fallback")
-        dev = p.device
+        dev = p.device            # the device itself is checked where the handle is taken (_ctx: Native.get raises without libpe_b200.so / an sm_100 GPU)
         P = {"ones_h": torch.ones(c.hidden, dtype=torch.bfloat16, device=dev), "ones_v": torch.ones(c.v_hidden, dtype=torch.bfloat16, device=dev)}
         P["text"] = []
         for l in self.model.language_model.layers:
@@ -321,7 +321,7 @@ class QwenImageTextEncoder(nn.Module):
         return P
 
     def _ctx(self):
-        nat = nv.Native.get(self.lm_head.weight.device.index or 0)
+        nat = nv.Native.get(self.lm_head.weight.device.index or 0)         # NativeUnavailable when the library or the GPU is missing: no fallback
         return nat, (self._packed or self._pack())
 
     # ---- vision tower (Qwen2_5_VisionTransformerPretrainedModel.forward :455-523) ---------------------------------------------
@@ -582,7 +582,8 @@ class QwenImageTextEncoder(nn.Module):
                 with torch.cuda.graph(graph, stream=side):      # records the launches, does not run them: ctr / log / caches stay as they are
                     step()
             torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         t_loop, done_at_loop = time.time(), done       # capture / warm-up excluded from the per-token figure
         n_out = [None] * nb
         while any(n is None for n in n_out):

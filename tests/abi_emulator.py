@@ -273,3 +273,130 @@ def _timestep_embedding(self, t_in, out, raw=True):
 
 EmulatedNative.patchify, EmulatedNative.unpatchify = _patchify, _unpatchify
 EmulatedNative.layernorm_modulate, EmulatedNative.timestep_embedding = _layernorm_modulate, _timestep_embedding
+
+
+# ---- Qwen2.5-VL text-encoder path (include/pe_b200.h, last section) ----------------------------------------------------------------------
+def _swiglu(self, x, out, I):
+    g, u = x[:, :I].float(), x[:, I:2 * I].float()
+    out[:, :I] = (_r(g / (1 + torch.exp(-g))) * u).to(torch.bfloat16)
+    self._note("pe_swiglu")
+
+
+def _rope_half(self, x, H, D, cos, sin, row0=0, row_ptr=None, mode=1):
+    """rotate-half RoPE in place on x [T, >= H * D]; token t uses table row (row_ptr ? *row_ptr : row0) + t.  mode 0: fp32 arithmetic;
+    mode 1: bf16 op order with bf16-rounded cos / sin (bf16(bf16(x c) + bf16(rot s)))."""
+    T = x.shape[0]
+    r0 = int(row_ptr.reshape(-1)[0]) if row_ptr is not None else row0
+    c, s = cos[r0:r0 + T].float()[:, None, :], sin[r0:r0 + T].float()[:, None, :]
+    v = x[:, :H * D].float().reshape(T, H, D)
+    rot = torch.cat([-v[..., D // 2:], v[..., :D // 2]], dim=-1)
+    y = (v * c + rot * s) if mode == 0 else _r(_r(v * _r(c)) + _r(rot * _r(s)))
+    x[:, :H * D] = y.reshape(T, H * D).to(torch.bfloat16)
+    self._note("pe_rope_half")
+
+
+def _range_attention(self, q, k, v, o, H, Hkv, D, scale, kv_lo=None, kv_hi=None, kv_len_ptr=None, Skv=None):
+    """query i of head h attends to keys [lo_i, hi_i) of KV head h // (H / Hkv); defaults lo = 0, hi = kv_len (or all rows)."""
+    Sq = q.shape[0]
+    n = k.shape[0] if Skv is None else Skv
+    if kv_len_ptr is not None:
+        n = min(n, int(kv_len_ptr.reshape(-1)[0]))
+    lo = kv_lo.long() if kv_lo is not None else torch.zeros(Sq, dtype=torch.long)
+    hi = kv_hi.long() if kv_hi is not None else torch.full((Sq,), n, dtype=torch.long)
+    pos = torch.arange(n)
+    allow = (pos[None, :] >= lo[:, None]) & (pos[None, :] < hi[:, None])
+    qh = q[:, :H * D].float().reshape(Sq, H, D).transpose(0, 1)
+    kh = k[:n, :Hkv * D].float().reshape(n, Hkv, D).transpose(0, 1).repeat_interleave(H // Hkv, dim=0)
+    vh = v[:n, :Hkv * D].float().reshape(n, Hkv, D).transpose(0, 1).repeat_interleave(H // Hkv, dim=0)
+    p = torch.softmax((qh @ kh.transpose(1, 2) * scale).masked_fill(~allow[None], float("-inf")), dim=-1)
+    o[:, :H * D] = (p @ vh).transpose(0, 1).reshape(Sq, H * D).to(torch.bfloat16)
+    self._note("pe_range_attention")
+
+
+def _gather_rows(self, table, ids, out):
+    keep = ids >= 0
+    out[keep] = table[ids[keep]]
+    self._note("pe_gather_rows")
+
+
+def _check_async(self):
+    return None
+
+
+EmulatedNative.swiglu, EmulatedNative.rope_half, EmulatedNative.range_attention = _swiglu, _rope_half, _range_attention
+EmulatedNative.gather_rows, EmulatedNative.check_async = _gather_rows, _check_async
+
+
+# ---- decode step -----------------------------------------------------------------------------------------------------------------
+def _gemv_fused(self, x, w, bias, y, act_in=0, norm_w=None, eps=1e-6, residual=None):
+    """pe_gemv_fused: optional SwiGLU (act_in 2, x = gate | up) or RMSNorm prologue on the input, y = bf16(residual + bf16(x w^T + bias))."""
+    v = x.float().reshape(-1, x.shape[-1])
+    K = w.shape[1]
+    if act_in == 2:
+        g, u = v[:, :K], v[:, K:2 * K]
+        v = _r(_r(g / (1 + torch.exp(-g))) * u)
+    elif act_in == 1:
+        v = _r(v / (1 + torch.exp(-v)))
+    if norm_w is not None:
+        v = _r(norm_w.float() * _r(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)))
+    o = _r(v @ w.float().t() + (bias.float() if bias is not None else 0.0))
+    if residual is not None:
+        o = residual.float().reshape(o.shape) + o
+    y.copy_(o.reshape(y.shape).to(torch.bfloat16))
+    self._note("pe_gemv_fused")
+
+
+def _gemv_swiglu(self, x, w, bias, y, norm_w=None, eps=1e-6):
+    v = x.float().reshape(-1, x.shape[-1])
+    if norm_w is not None:
+        v = _r(norm_w.float() * _r(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)))
+    gu = _r(v @ w.float().t() + (bias.float() if bias is not None else 0.0))
+    I = w.shape[0] // 2
+    g, u = gu[:, :I], gu[:, I:]
+    y.copy_((_r(g / (1 + torch.exp(-g))) * u).reshape(y.shape).to(torch.bfloat16))
+    self._note("pe_gemv_swiglu")
+
+
+def _argmax(self, x, out, log=None, log_pos=None):
+    i = int(torch.argmax(x.float().reshape(-1)))               # first maximal index
+    out.reshape(-1)[0] = i
+    if log is not None:
+        log.reshape(-1)[int(log_pos.reshape(-1)[0])] = i
+    self._note("pe_argmax")
+
+
+def _kv_append(self, k_new, v_new, cache_k, cache_v, pos):
+    r = int(pos.reshape(-1)[0])
+    cache_k[r, :k_new.numel()] = k_new.reshape(-1)
+    cache_v[r, :v_new.numel()] = v_new.reshape(-1)
+    self._note("pe_kv_append")
+
+
+def _rope_kv_append(self, qkv_row, Hq, Hkv, D, cos, sin, cache_k, cache_v, counters):
+    row = qkv_row.reshape(1, -1)
+    _rope_half(self, row[:, :(Hq + Hkv) * D], Hq + Hkv, D, cos, sin, row_ptr=counters.reshape(-1)[1:2], mode=1)
+    r = int(counters.reshape(-1)[0])
+    cache_k[r, :Hkv * D] = row[0, Hq * D:(Hq + Hkv) * D]
+    cache_v[r, :Hkv * D] = row[0, (Hq + Hkv) * D:(Hq + 2 * Hkv) * D]
+    self._note("pe_rope_kv_append")
+
+
+def _decode_attention_fused(self, qkv_rows, caches, outs, counters, Hq, Hkv, D, cos, sin, scale):
+    """rope of the new q / k heads, KV append at counters[0], attention of the new query over rows [0, counters[0]]; qkv is left untouched."""
+    for qkv, (ck, cv), out, ctr in zip(qkv_rows, caches, outs, counters):
+        row = qkv.clone().reshape(1, -1)
+        _rope_kv_append(self, row[0], Hq, Hkv, D, cos, sin, ck, cv, ctr)
+        n = int(ctr.reshape(-1)[0]) + 1
+        _range_attention(self, row[:, :Hq * D], ck, cv, out.reshape(1, -1), Hq, Hkv, D, scale, kv_len_ptr=torch.tensor([n], dtype=torch.int32))
+        self.calls = self.calls[:-2]
+        self.launches -= 2
+    self._note("pe_decode_attention_fused")
+
+
+def _advance(self, counters, n):
+    counters.reshape(-1)[:n] += 1
+    self._note("pe_advance")
+
+
+EmulatedNative.gemv_fused, EmulatedNative.gemv_swiglu, EmulatedNative.argmax = _gemv_fused, _gemv_swiglu, _argmax
+EmulatedNative.kv_append, EmulatedNative.rope_kv_append, EmulatedNative.decode_attention_fused, EmulatedNative.advance = _kv_append, _rope_kv_append, _decode_attention_fused, _advance

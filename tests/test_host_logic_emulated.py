@@ -306,3 +306,59 @@ def test_training_forward_and_backward_host_logic_matches_oracle_autograd(ag, mo
     e_lora, e_pe = rel(cat(lora), cat(leaves)), rel(pe.grad, pe32.grad)
     print(f"emulated training step: loss {loss.item():.5f} vs {loss32.item():.5f}; LoRA grads {e_lora:.3e}; d prompt_emb {e_pe:.3e}")
     assert e_lora < 3e-2 and e_pe < 3e-2
+
+
+@pytest.mark.parametrize("with_image", [False, True])
+def test_text_encoder_prefill_host_logic_matches_the_library(monkeypatch, with_image):
+    """QwenImageTextEncoder.edit_forward (vision tower with window reordering and per-patch KV ranges, image-token scatter, mrope tables, the decoder
+    layers with fused [q|k|v] / [gate|up] packing, grouped KV heads, causal ranges) on the emulated ABI vs the installed transformers model in fp32
+    (oracle/vl_oracle.py: small seeded configuration with the real structure)."""
+    from oracle import vl_oracle as VO
+    from physicedit_b200 import native as nv
+    from physicedit_b200.text_encoder import QwenImageTextEncoder
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    hf = VO.hf_model(torch.float32)
+    with torch.device("meta"):
+        te = QwenImageTextEncoder(VO.native_config(), rope_mode="mrope_hf55")
+    te.load_state_dict({k: v.to(torch.bfloat16) for k, v in hf.state_dict().items()}, assign=True, strict=True)
+    te.eval()
+    inp = VO.inputs(with_image=with_image, seed=4)
+    want, _ = VO.edit_forward(hf, inp)
+    got = te.edit_forward(**{k: (v.to(torch.bfloat16) if k == "pixel_values" else v) for k, v in inp.items()})[-1]
+    e = rel(got, want)
+    print(f"text-encoder prefill on the emulated ABI (image: {with_image}) vs transformers fp32: {e:.3e}")
+    assert got.shape == want.shape and e < 2.5e-2
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_text_encoder_greedy_decode_host_logic(monkeypatch, fused):
+    """QwenImageTextEncoder.generate on the emulated ABI (eager steps): KV-cache rows, device-side counters (cache row, rope row with the mrope delta,
+    log slot), EOS handling, the fused and the unfused decode sequence -- token ids vs the installed transformers model's greedy search (a first
+    difference is accepted only where the oracle's own top-2 logits are within 2 bf16 ulps: a tie, not a bug)."""
+    from oracle import vl_oracle as VO
+    from physicedit_b200 import native as nv
+    from physicedit_b200.text_encoder import QwenImageTextEncoder
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    hf = VO.hf_model(torch.float32)
+    with torch.device("meta"):
+        te = QwenImageTextEncoder(VO.native_config(), rope_mode="mrope_hf55")
+    te.load_state_dict({k: v.to(torch.bfloat16) for k, v in hf.state_dict().items()}, assign=True, strict=True)
+    te.eval()
+    te.use_cuda_graph, te.fused_decode = False, fused
+    inp = VO.inputs(with_image=True, seed=4)
+    n = 12
+    seq = te.generate(**{k: (v.to(torch.bfloat16) if k == "pixel_values" else v) for k, v in inp.items()}, max_new_tokens=n)
+    T = inp["input_ids"].shape[1]
+    assert torch.equal(seq[0, :T], inp["input_ids"][0])
+    mine = seq[0, T:].tolist()
+    want, top2 = VO.generate(hf, inp, n)
+    want = want.tolist()
+    k = next((i for i, (a, b) in enumerate(zip(mine, want)) if a != b), None)
+    if k is not None:
+        gap, ulp = (top2[k, 0] - top2[k, 1]).item(), 2.0 ** (math.floor(math.log2(max(abs(top2[k, 0].item()), 1e-6))) - 7)
+        assert gap <= 2 * ulp, f"token {k} differs ({mine[k]} vs {want[k]}) although the oracle's top-2 logits are {gap / ulp:.1f} bf16 ulps apart"
+        mine, want = mine[:k], want[:k]
+    assert mine == want[:len(mine)] and len(mine) >= 4
+    assert te.last_generate_stats["cuda_graph"] is False
