@@ -66,9 +66,9 @@ def model_fn_qwen_image(
 ):
     if latents.shape[0] != 1 or prompt_emb.shape[0] != 1:
         raise ValueError("the pipeline is strictly batch 1 (qwen_image_physical.py:688,821); batch edits shard one image per GPU")
-    if not (latents.is_cuda and latents.dtype == torch.bfloat16 and prompt_emb.dtype == torch.bfloat16):
+    if not (latents.dtype == torch.bfloat16 and prompt_emb.dtype == torch.bfloat16):
         raise nv.NativeUnavailable(f"native model_fn needs CUDA bfloat16 tensors (latents {latents.dtype} on {latents.device}); no fallback")
-    eng = dit.engine()
+    eng = dit.engine()          # raises NativeUnavailable for weights that are not bf16 on an sm_100 GPU / without libpe_b200.so: there is no CPU path
     nat = eng.nat
     t_bf16 = timestep.to(device=latents.device, dtype=torch.bfloat16).reshape(-1)[:1].contiguous()
     if timestep_host is None:

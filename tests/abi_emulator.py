@@ -400,3 +400,40 @@ def _advance(self, counters, n):
 
 EmulatedNative.gemv_fused, EmulatedNative.gemv_swiglu, EmulatedNative.argmax = _gemv_fused, _gemv_swiglu, _argmax
 EmulatedNative.kv_append, EmulatedNative.rope_kv_append, EmulatedNative.decode_attention_fused, EmulatedNative.advance = _kv_append, _rope_kv_append, _decode_attention_fused, _advance
+
+
+# ---- adapter plumbing and the CFG + Euler update -----------------------------------------------------------------------------------------
+def _special_gather(self, prompt_emb, mask_u8, dst, idx):
+    rows = torch.nonzero(mask_u8.reshape(-1) != 0).reshape(-1)
+    n = dst.shape[0]
+    assert rows.numel() <= n, "more special rows than the caller made room for (the kernel raises PE_ERR_INVALID_ARGUMENT)"
+    dst.zero_()
+    idx.fill_(-1)
+    dst[:rows.numel()] = prompt_emb[rows]
+    idx[:rows.numel()] = rows.to(torch.int32)
+    idx[n] = rows.numel()
+    self._note("pe_special_gather")
+
+
+def _special_blend_scatter(self, prompt_emb, idx, pred_dino, pred_vae, t_in, t_min, t_max):
+    """helpers.py:142-164 on a bf16 timestep: alpha = clamp(bf16(bf16(t - t_min) * float(1 / range))), out = bf16(alpha d) + bf16(bf16(1 - alpha) v)."""
+    inv = torch.tensor(1.0 / (t_max - t_min + 1e-6), dtype=torch.float64).float()
+    alpha = _r(_r(t_in.float().reshape(-1)[0] - t_min) * inv).clamp(0.0, 1.0)
+    oma = _r(1.0 - alpha)
+    for i in range(pred_dino.shape[0]):
+        t = int(idx[i])
+        if t >= 0:
+            prompt_emb[t] = (_r(alpha * pred_dino[i].float()) + _r(oma * pred_vae[i].float())).to(torch.bfloat16)
+    self._note("pe_special_blend_scatter")
+
+
+def _cfg_euler_step(self, latents, posi, nega, cfg_scale, dsigma):
+    p = posi.float()
+    if nega is not None:
+        q = nega.float()
+        p = _r(q + _r(cfg_scale * _r(p - q)))
+    latents.copy_((latents.float() + _r(p * dsigma)).to(torch.bfloat16))
+    self._note("pe_cfg_euler_step")
+
+
+EmulatedNative.special_gather, EmulatedNative.special_blend_scatter, EmulatedNative.cfg_euler_step = _special_gather, _special_blend_scatter, _cfg_euler_step

@@ -314,3 +314,29 @@ def test_hot_lora_surface():
     pipe.clear_lora()
     assert len(q.lora_A_weights) == 0 and not pipe.dit._lora_injected
     assert pipe.get_special_divisor(global_step=0) == 10 and pipe.get_special_divisor(global_step=5000) == 5.5 and pipe.get_special_divisor(global_step=20000) == 1.0
+
+
+def test_product_entry_points_fail_loudly_without_a_gpu():
+    """No CPU path anywhere in the product: the step function, the text encoder and the training Functions raise NativeUnavailable when the handle cannot be
+    created (no sm_100 GPU / no libpe_b200.so) -- they never fall back to torch ops or to the oracle."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from physicedit_b200 import native as nv
+    from physicedit_b200 import autograd as ag
+    from physicedit_b200.model_fn import model_fn_qwen_image
+    pipe = _cpu_pipe(layers=1)
+    lat = torch.zeros(1, 16, 8, 8, dtype=torch.bfloat16)
+    kw = dict(dit=pipe.dit, visual_thinking_adapter=pipe.visual_thinking_adapter, latents=lat, timestep=torch.tensor([500.0]).bfloat16(),
+              prompt_emb=torch.zeros(1, 8, 3584, dtype=torch.bfloat16), prompt_emb_mask=torch.ones(1, 8, dtype=torch.long), special_token_mask=None, height=64,
+              width=64, is_train=False)
+    with pytest.raises(nv.NativeUnavailable):
+        model_fn_qwen_image(**kw)
+    with pytest.raises(nv.NativeUnavailable):
+        model_fn_qwen_image(**dict(kw, latents=lat.float()))
+    with pytest.raises(nv.NativeUnavailable):
+        ag.linear(torch.zeros(4, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    from physicedit_b200.text_encoder import QwenImageTextEncoder, VLConfig
+    te = QwenImageTextEncoder(VLConfig(hidden=64, layers=1, heads=2, kv_heads=1, head_dim=32, intermediate=64, vocab=32, v_hidden=32, v_depth=1, v_heads=1,
+                                       v_intermediate=32, v_out=64, fullatt=(0,))).bfloat16()
+    with pytest.raises(nv.NativeUnavailable):
+        te.edit_forward(input_ids=torch.zeros(1, 4, dtype=torch.long), attention_mask=torch.ones(1, 4, dtype=torch.long))

@@ -362,3 +362,53 @@ def test_text_encoder_greedy_decode_host_logic(monkeypatch, fused):
         mine, want = mine[:k], want[:k]
     assert mine == want[:len(mine)] and len(mine) >= 4
     assert te.last_generate_stats["cuda_graph"] is False
+
+
+def test_cfg_denoise_loop_host_logic_matches_the_oracle_loop(monkeypatch):
+    """pipe.denoise (set_timesteps with the dynamic shift, per step two model_fn forwards whose adapter rewrites the 64 special rows of EACH branch's
+    prompt in place, the conditioning table shared by the two branches, CFG combine + Euler update) on the emulated ABI vs oracle.denoise_loop in fp32
+    with the bf16 timestep bookkeeping: 3 steps, 1 block."""
+    from oracle import dit_oracle as O
+    from physicedit_b200 import adapters, native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    H = Wd = 64
+    W = O.synth_weights(O.dit_param_shapes(1), seed=39)
+    A = O.synth_weights(O.adapter_param_shapes(), seed=40)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in W.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict({k: v.to(torch.bfloat16) for k, v in A.items()})
+    pipe.visual_thinking_adapter.to(torch.bfloat16)
+    pipe.cfg_streams = 1
+    posi = O.synth_inputs(H, Wd, 88, seed=41, dtype=torch.bfloat16)
+    nega = O.synth_inputs(H, Wd, 72, seed=42, dtype=torch.bfloat16)
+    keys = ("prompt_emb", "prompt_emb_mask", "special_token_mask")
+    ip, in_ = {k: posi[k].clone() for k in keys}, {k: nega[k].clone() for k in keys}
+    out = pipe.denoise(posi["latents"], ip, in_, posi["edit_latents"], height=H, width=Wd, num_inference_steps=3, cfg_scale=4.0)
+    ad = pipe.visual_thinking_adapter
+    with torch.no_grad():
+        W32 = {k: v.to(torch.bfloat16).float() for k, v in W.items()}
+        A32 = {k: v.to(torch.bfloat16).float() for k, v in A.items()}
+        op = {k: (posi[k].float().clone() if posi[k].is_floating_point() else posi[k]) for k in keys}
+        on = {k: (nega[k].float().clone() if nega[k].is_floating_point() else nega[k]) for k in keys}
+        want = O.denoise_loop(W32, A32, posi["latents"].float(), op, on, posi["edit_latents"].float(), H, Wd, 3, cuda_scalar_div=True, timestep_dtype=torch.bfloat16)
+    e = rel(out, want)
+    sm = posi["special_token_mask"][0]
+    e_special = rel(ip["prompt_emb"][0][sm], op["prompt_emb"][0][sm])
+    print(f"3-step CFG loop on the emulated ABI vs the fp32 oracle loop: latents {e:.3e}; mutated special rows {e_special:.3e}")
+    assert e < 1e-2 and e_special < 1e-2
+    assert torch.equal(ip["prompt_emb"][0][~sm], posi["prompt_emb"][0][~sm])               # only the special rows were written (:1336)
+    names = [c[0] for c in emu.calls]
+    assert names.count("pe_cfg_euler_step") == 3 and names.count("pe_special_blend_scatter") == 6
+    assert names.count("pe_timestep_embedding") == 3                                        # conditioning computed once per timestep, shared by the CFG pair
