@@ -437,3 +437,26 @@ def _cfg_euler_step(self, latents, posi, nega, cfg_scale, dsigma):
 
 
 EmulatedNative.special_gather, EmulatedNative.special_blend_scatter, EmulatedNative.cfg_euler_step = _special_gather, _special_blend_scatter, _cfg_euler_step
+
+
+# ---- training-path feature extractors: pe_layernorm (affine), pe_small_attention ---------------------------------------------------------
+def _layernorm(self, x, out, w=None, b=None, eps=1e-5):
+    v = x.float()
+    y = (v - v.mean(-1, keepdim=True)) * torch.rsqrt(v.var(-1, unbiased=False, keepdim=True) + eps)
+    if w is not None:
+        y = y * w.float() + (b.float() if b is not None else 0.0)
+    out.copy_(y.to(torch.bfloat16))
+    self._note("pe_layernorm")
+
+
+def _small_attention(self, q, k, v, o, B, H, Sq, Skv, D, scale):
+    """q [B * Sq, >= H * D], k / v [B * Skv, >= H * D]: per (batch, head) softmax(scale q k^T) v."""
+    qh = q[:, :H * D].float().reshape(B, Sq, H, D).permute(0, 2, 1, 3)
+    kh = k[:, :H * D].float().reshape(B, Skv, H, D).permute(0, 2, 1, 3)
+    vh = v[:, :H * D].float().reshape(B, Skv, H, D).permute(0, 2, 1, 3)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    o[:, :H * D] = (p @ vh).permute(0, 2, 1, 3).reshape(B * Sq, H * D).to(torch.bfloat16)
+    self._note("pe_small_attention")
+
+
+EmulatedNative.layernorm, EmulatedNative.small_attention = _layernorm, _small_attention

@@ -412,3 +412,33 @@ def test_cfg_denoise_loop_host_logic_matches_the_oracle_loop(monkeypatch):
     names = [c[0] for c in emu.calls]
     assert names.count("pe_cfg_euler_step") == 3 and names.count("pe_special_blend_scatter") == 6
     assert names.count("pe_timestep_embedding") == 3                                        # conditioning computed once per timestep, shared by the CFG pair
+
+
+def test_feature_extractor_host_logic_matches_the_aux_oracle(monkeypatch):
+    """The pseudo-target branch of a training sample (rows a14-a16) on the emulated ABI vs oracle/aux_oracle.py in fp32: DINOv2-with-registers (im2col patch
+    embed with K padded to 592, bicubic position table, CLS / register placement, LayerScale through the gate-residual epilogue, non-affine final norm,
+    5 leading tokens dropped), both perceiver resamplers, their adapters, frame-index embeddings, middle - source deltas."""
+    from oracle import aux_oracle as AO
+    from physicedit_b200 import adapters, native as nv
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    P = AO.aux_synth(seed=5, dtype=torch.bfloat16)
+    ain = AO.aux_inputs(seed=6, n_mid=2, lat_hw=(16, 16), dtype=torch.bfloat16)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, dinov2_config=dict(hidden=768, layers=12, heads=12))
+    pipe.dinov2.encoder.load_state_dict({k: v for k, v in P["dinov2"].items() if not k.startswith("layernorm.")}, strict=True)
+    for name in ("dino_resampler", "vae_resampler", "dino_resampler_adapter", "vae_resampler_adapter", "dino_time_embed", "vae_time_embed"):
+        getattr(pipe, name).load_state_dict(P[name])
+    pipe.to(torch.bfloat16)
+    pipe.eval()
+    Pf = {k: {n: t.float() for n, t in v.items()} for k, v in P.items()}
+    with torch.no_grad():
+        d_nat = pipe.dinov2(ain["dino_middle"])
+        d_ref = AO.dinov2_with_norm(Pf["dinov2"], ain["dino_middle"].float())
+        assert d_nat.shape == d_ref.shape == (2, 256, 768) and rel(d_nat, d_ref) < 2e-2
+        out = pipe.physical_visual_embeddings(**ain)
+        ed, ev = AO.physical_visual_embeddings(Pf, **{k: v.float() for k, v in ain.items()})
+    e_d, e_v = rel(out["pseudo_special_emb_dino"], ed), rel(out["pseudo_special_emb_vae"], ev)
+    print(f"feature extractors on the emulated ABI vs the fp32 aux oracle: dinov2 {rel(d_nat, d_ref):.3e}; targets dino {e_d:.3e} vae {e_v:.3e}")
+    assert out["pseudo_special_emb_dino"].shape == (1, 64, 3584) and e_d < 3e-2 and e_v < 3e-2
