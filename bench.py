@@ -74,13 +74,14 @@ class ClockSampler:
 
 def ncu_traffic_bytes(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures (profiles/r01_ncu_full_metrics.json for
-    the attention and the MLP up-projection with a flushed L2, profiles/r01_gemm_traffic.json for the other GEMM shapes)."""
-    try:
-        g = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get(kernel_substr)
-        if g:
-            return int((g["dram_read_MB"] + g["dram_write_MB"]) * 1e6)
-    except (OSError, KeyError, ValueError):
-        pass
+    the attention and the MLP up-projection with a flushed L2, profiles/r02_gemm_raster_ab.json / r01_gemm_traffic.json for the other GEMM shapes)."""
+    for name in ("r02_gemm_raster_ab.json", "r01_gemm_traffic.json"):      # r2: the down-projection's rasterisation changed, re-captured
+        try:
+            g = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel_substr)
+            if g:
+                return int((g["dram_read_MB"] + g["dram_write_MB"]) * 1e6)
+        except (OSError, KeyError, ValueError, TypeError):
+            pass
     try:        # r2 full capture of the attention kernel (profiles/r02_ncu_attention_full.json)
         if "attention_kernel" in kernel_substr:
             row = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_attention_full.json")))[0]
@@ -458,7 +459,7 @@ def run_native(args):
             ach, pk, unit, src = by / avg_s / 1e9, peak_gbs, "GB/s", "MEASURED_PEAKS.json hbm_gbs"
         roofs[tag] = {"bound": bound, "kernel": desc, "achieved": round(ach, 1), "peak": pk, "peak_source": src if peaks else "fallback", "unit": unit,
                       "frac": round(ach / pk, 4), "traffic": ncu_traffic_bytes(ncu_name) if ncu_name else None,
-                      "traffic_unit": "bytes per launch (ncu --set full: profiles/r02_ncu_attention_full.json, r01_ncu_full_metrics.json, r01_gemm_traffic.json)", "algorithmic_bytes": int(by),
+                      "traffic_unit": "bytes per launch (ncu: profiles/r02_ncu_attention_full.json, r01_ncu_full_metrics.json, r02_gemm_raster_ab.json, r01_gemm_traffic.json)", "algorithmic_bytes": int(by),
                       "launches": n, "avg_ms": round(tot / n, 4), "share_of_step": round(tot / ms_attr, 4)}
     roof = None
     if roofs:

@@ -39,6 +39,7 @@ constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 12;
 constexpr int kTileRegionBytes = 224 << 10;   // operand ring; full-width tiles use 192 KB of it: 4 x 48 KB (one CTA, 256 W rows) or 6 x 32 KB (CTA pair)
+constexpr bool kRoundRasterDefault = true;   // deep-K layers: one rasterisation group = one round of tiles (choose_raster)
 constexpr int kPanelBytes = 32 << 20;   // rasterisation: the m-tiles of a group share a sweep over n; their A panel (<= 32 MB) stays in the 126 MB L2
 
 struct SegDev {
@@ -76,6 +77,10 @@ struct GemmParams {
     int num_n;
     int total_m_tiles;
     int group_m;           // m-tiles per rasterisation group (balanced: ceil(total / number of groups))
+    int group_n;           // n-tiles per rasterisation band (num_n: one band, the r1 order).  Deep-K layers (MLP down) split N into bands whose
+                           // W panel stays in the L2 while the m-groups of the band stream past it; see gemm_run
+    unsigned long long hint_a, hint_w;   // L2 eviction-priority policies of the A / W tile loads (plain 2-D loads only)
+    int max_clusters;      // > 0: launch at most this many CTAs (pairs), so that one round of tiles is exactly one rasterisation group
     int num_tiles;
     int num_kb;
     int heads;             // QKV epilogue: N = 3 * heads * 128
@@ -143,13 +148,23 @@ struct Tile {
 
 template <int kTileM>
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int t) {
-    const int group_size = p.group_m * p.num_n;
+    // band h = n-tiles [h * group_n, ...) (every band but the last is full, so the tiles before band h are h * total_m_tiles * group_n);
+    // inside a band: m-groups of group_m m-tiles; inside a group the m index runs fastest
+    int first_n = 0, band_n = p.num_n;
+    if (p.group_n < p.num_n) {
+        const int band_size = p.total_m_tiles * p.group_n;
+        const int h = t / band_size;
+        t -= h * band_size;
+        first_n = h * p.group_n;
+        band_n = min(p.group_n, p.num_n - first_n);
+    }
+    const int group_size = p.group_m * band_n;
     const int g = t / group_size;
     const int first_m = g * p.group_m;
     const int gm = min(p.group_m, p.total_m_tiles - first_m);
     const int in_group = t - g * group_size;
     int mt = first_m + in_group % gm;
-    const int nt = in_group / gm;
+    const int nt = first_n + in_group / gm;
     Tile r;
     r.seg = 0;
     r.b = 0;
@@ -453,15 +468,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                             tma_load_3d(a_smem(stage), &sg.tmA, full_bar(stage), cc, cx, cy);
                             if (p.dual_m) tma_load_3d(a_smem(stage) + kABytes, &sg.tmA, full_bar(stage), cc, cx, cy + (128 >> p.tile_w_log2));
                         } else {
-                            tma_load_2d(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, a_row);
+                            tma_load_2d_hint(a_smem(stage), &sg.tmA, full_bar(stage), kb * kBlockK, a_row, p.hint_a);
                         }
-                        tma_load_2d(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, b_row);
+                        tma_load_2d_hint(b_smem(stage), &sg.tmB, full_bar(stage), kb * kBlockK, b_row, p.hint_w);
                     } else {
                         const uint32_t fbs = fb + stage * 8;
                         if (leader) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx_bytes);
                         if (p.conv) tma_load_3d_cg2(a_smem(stage), &sg.tmA, fbs, cc, cx, cy);
-                        else tma_load_2d_cg2(a_smem(stage), &sg.tmA, fbs, kb * kBlockK, a_row);
-                        tma_load_2d_cg2(b_smem(stage), &sg.tmB, fbs, kb * kBlockK, b_row);
+                        else tma_load_2d_cg2_hint(a_smem(stage), &sg.tmA, fbs, kb * kBlockK, a_row, p.hint_a);
+                        tma_load_2d_cg2_hint(b_smem(stage), &sg.tmB, fbs, kb * kBlockK, b_row, p.hint_w);
                     }
                 }
                 if (p.conv) {
@@ -615,7 +630,7 @@ int launch_gemm(Handle* h, const GemmParams& p, cudaStream_t stream) {
     }
     int ctas = h->sm_count;
     if (kCG == 2) ctas &= ~1;
-    const int max_useful = p.num_tiles * kCG;
+    const int max_useful = (p.max_clusters > 0 && p.max_clusters < p.num_tiles ? p.max_clusters : p.num_tiles) * kCG;
     if (ctas > max_useful) ctas = max_useful;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -668,6 +683,67 @@ static void set_ring(GemmParams& p, int cg, int b_rows_per_cta, int a_boxes = 1)
     static const int stage_cap = [] { const char* e = getenv("PE_GEMM_MAX_STAGES"); return e ? atoi(e) : 0; }();   // tuning aid: cap the ring depth
     if (stage_cap >= 2 && stage_cap < p.num_stages) p.num_stages = stage_cap;
     p.stage_tx_bytes = cg * (a_bytes + b_bytes);                 // a pair's boxes all land on the leader's barrier
+}
+
+// ---- rasterisation (tile index -> (m-tile, n-tile), see decode_tile) and L2 policies of the operand loads ---------------------------
+// Tiles are dealt round-robin to the persistent CTAs (pairs), so ~`clusters` consecutive tile indices run concurrently and stream K in
+// step: what a round of tiles reads from DRAM is (distinct m-tiles + distinct n-tiles) x tile rows x K x 2 bytes, and anything less needs
+// a panel of one operand to stay in the L2 from one round to the next.
+//  * wide layers (K = 3072): m-groups whose A panel is <= kPanelBytes, each swept over all n-tiles in several rounds; the panel stays
+//    resident, W streams once per group.
+//  * deep-K layers (MLP down-projection: K = 12288, a tile row is 6.3 MB): such a group (5 m-tiles x 12 n-tiles) is smaller than one round,
+//    so nothing is re-used across rounds and the rounds straddle two groups.  There a group is made exactly one round -- group_m =
+//    clusters / num_n m-tiles (6 x 12 = 72 tiles) -- and only that many CTA pairs are launched when it costs no extra round (it does
+//    not at 408 tiles: 6 rounds either way).  Measured at M = 8704 (tools/gemm_raster_ab.py, profiles/r02_gemm_raster_ab.json):
+//    DRAM reads 946 -> 828 MB per launch, 461.5 -> 454.9 us.
+//  * measured and NOT used: evict-first on the streamed operand (the other CTAs of the round read the same rows a little later: DRAM
+//    reads double, 946 -> 1709 MB), n-bands with a resident W panel (group_n < num_n: 1060 MB), one m-group for the wide layers (the
+//    53 MB A panel does not stay: 303 -> 598 MB).  The knobs stay reachable through PE_GEMM_TUNE / PE_GEMM_RASTER for the A/B tool.
+struct RasterTune { int on, automatic, gn, gm, ha, hw, clusters; };
+static RasterTune raster_tune() {
+    // tools/gemm_raster_ab.py: with PE_GEMM_TUNE in the environment, PE_GEMM_RASTER = "auto" | "gn,gm,hint_a,hint_w,clusters" is re-read on every
+    // launch (gn / gm / clusters 0 = the default order's value; hints 0 normal, 1 evict-first, 2 evict-last)
+    static const bool enabled = getenv("PE_GEMM_TUNE") != nullptr;
+    RasterTune t = {0, 0, 0, 0, 0, 0, 0};
+    if (!enabled) return t;
+    const char* e = getenv("PE_GEMM_RASTER");
+    if (!e) return t;
+    if (e[0] == 'a') { t.on = 1; t.automatic = 1; return t; }
+    if (sscanf(e, "%d,%d,%d,%d,%d", &t.gn, &t.gm, &t.ha, &t.hw, &t.clusters) == 5) t.on = 1;
+    return t;
+}
+static unsigned long long l2_policy(int code) { return code == 1 ? kL2EvictFirst : code == 2 ? kL2EvictLast : kL2EvictNormal; }
+
+static void choose_raster(const Handle* h, GemmParams& p, int tile_m, int cg, bool batched) {
+    const long long a_tile_bytes = (long long)tile_m * p.K * 2;      // one m-tile's rows of A
+    // as many m-tiles per group as keep the group's A panel within kPanelBytes, spread evenly (r1: a fixed 16 left a last group of
+    // 2 m-tiles that re-streamed the whole weight matrix, and at K = 12288 a 100 MB panel that did not fit the L2 next to W)
+    int gm_max = (int)(kPanelBytes / a_tile_bytes);
+    if (gm_max < 1) gm_max = 1;
+    const int groups = ceil_div(p.total_m_tiles, gm_max);
+    p.group_m = ceil_div(p.total_m_tiles, groups);
+    p.group_n = p.num_n;
+    p.hint_a = p.hint_w = kL2EvictNormal;
+    const RasterTune t = raster_tune();
+    const bool automatic = t.on ? t.automatic != 0 : kRoundRasterDefault;
+    const int clusters = (h->sm_count > cg ? h->sm_count : cg) / cg;
+    if (automatic && !batched && groups > 1 && gm_max * p.num_n <= clusters) {
+        // an A-panel group is smaller than one round of tiles: make a group exactly one round
+        const int num_tiles = p.total_m_tiles * p.num_n;
+        p.group_m = clusters / p.num_n;
+        const int used = p.group_m * p.num_n;
+        if (ceil_div(num_tiles, used) == ceil_div(num_tiles, clusters)) p.max_clusters = used;
+    }
+    if (t.on && !t.automatic) {
+        if (t.gn > 0) p.group_n = t.gn < p.num_n ? t.gn : p.num_n;
+        if (t.gm > 0) p.group_m = t.gm;
+        p.hint_a = l2_policy(t.ha);
+        p.hint_w = l2_policy(t.hw);
+        p.max_clusters = t.clusters;
+    }
+#ifdef PE_GEMM_GROUP_M
+    p.group_m = PE_GEMM_GROUP_M;      // experiments: fixed group size
+#endif
 }
 
 int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epilogue, int flags, cudaStream_t stream, const pe_gemm_batch* bt) {
@@ -767,18 +843,7 @@ int gemm_run(Handle* h, const pe_gemm_seg* segs, int nseg, int N, int K, int epi
         p.vec_per_column = bt->vec_per_column;
         p.alpha = bt->alpha;
     }
-    {
-        // as many m-tiles per group as keep the group's A panel within kPanelBytes, spread evenly (r1: a fixed 16 left a last group of
-        // 2 m-tiles that re-streamed the whole weight matrix, and at K = 12288 a 100 MB panel that did not fit the L2 next to W)
-        const long long tile_row_bytes = (long long)tile_m * K * 2;
-        int gm_max = (int)(kPanelBytes / tile_row_bytes);
-        if (gm_max < 1) gm_max = 1;
-        const int groups = ceil_div(total_m_tiles, gm_max);
-        p.group_m = ceil_div(total_m_tiles, groups);
-#ifdef PE_GEMM_GROUP_M
-        p.group_m = PE_GEMM_GROUP_M;      // experiments: fixed group size
-#endif
-    }
+    choose_raster(h, p, tile_m, cg, bt != nullptr);
     p.num_tiles = total_m_tiles * p.num_n;
     p.trim_n = (flags & PE_GEMM_FLAG_TRIM_N) ? 1 : 0;
     if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
@@ -850,6 +915,8 @@ int conv2d_run(Handle* h, const pe_conv2d_desc* d, int epilogue, cudaStream_t st
         const int groups = ceil_div(p.total_m_tiles, gm_max);
         p.group_m = ceil_div(p.total_m_tiles, groups);
     }
+    p.group_n = p.num_n;
+    p.hint_a = p.hint_w = kL2EvictNormal;
     p.num_tiles = p.total_m_tiles * p.num_n;
     if (cg == 1) return dispatch_epilogue<1>(h, p, epilogue, stream);
     return dispatch_epilogue<2>(h, p, epilogue, stream);

@@ -164,6 +164,23 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtenso
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// The same two loads with an L2 eviction-priority policy (the encodings `createpolicy.fractional.L2::evict_*.b64 p, 1.0` produces):
+// a streamed operand is loaded evict-first so that it does not push the operand other CTAs are about to re-read out of the L2.
+constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull;
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;
+constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1, unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
