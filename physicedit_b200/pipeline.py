@@ -4,12 +4,11 @@ Mirrors DiffSynth-Studio/diffsynth/pipelines/qwen_image_physical.py (class QwenI
 __init__ :185-247, load_lora :250-276, training_loss :313-329, enable_vram_management :375-494,
 from_pretrained :497-541, __call__ :544-669) and diffsynth/utils/__init__.py (BasePipeline, ModelConfig).
 
-In scope here: the in-iteration models (`dit`, `visual_thinking_adapter`), the scheduler,
-the CFG denoise loop, LoRA fold, checkpoint key layout, and the training-path feature extractors
-(DINOv2, resamplers), and -- SURVEY 8f1 -- the VAE either side of the loop (`physicedit_b200/vae.py`, loaded by registry hash
-like the DiT).  Out of scope (8f2): the Qwen2.5-VL text encoder -- the pipeline accepts it as a user-supplied module
-(`pipe.text_encoder`, any object with the reference's `edit_forward` contract) or takes pre-computed embeddings through
-`denoise(...)`, which is what bench.py and the parity tests drive.
+In scope here: the in-iteration models (`dit`, `visual_thinking_adapter`, `blockwise_controlnet`), the scheduler,
+the CFG denoise loop, LoRA fold / hot-load, checkpoint key layout, the training-path feature extractors (DINOv2, resamplers) and
+`training_loss`, and either side of the loop the VAE (8f1, `vae.py`), the Qwen2.5-VL text encoder (8f2, `text_encoder.py`) and the
+pre-loop units (8b, `units.py`) -- each loaded by registry hash like the DiT.  `denoise(...)` also takes pre-computed prompt
+embeddings / latents directly, which is what bench.py and the parity tests drive.
 """
 from __future__ import annotations
 
@@ -549,17 +548,23 @@ class QwenImagePhysicPipeline(nn.Module):
         return self.vae_output_to_image(image) if output_type == "pil" else image
 
     # ---- training path (forward only) -----------------------------------------
-    @torch.no_grad()
     def physical_visual_embeddings(self, dino_middle: torch.Tensor, dino_source: torch.Tensor, vae_middle_latents: torch.Tensor,
                                    vae_source_latents: torch.Tensor):
         """QwenImageUnit_PhysicalVisualEmbedder.process (:1057-1118) from pre-processed tensors:
         dino_* [F,3,224,224] normalised pixels, vae_* [F,16,h8,w8] latents.  Returns the regression targets
-        pseudo_special_emb_dino / pseudo_special_emb_vae [1,64,3584]."""
-        nat = nv.Native.get(dino_middle.device.index or 0)
+        pseudo_special_emb_dino / pseudo_special_emb_vae [1,64,3584].  With the resampler stack trainable and grad mode on (the train script's
+        `forward_preprocess`, scripts/train/train_physicedit.py:290-295) the targets carry a graph, as in the reference: the adapter loss
+        trains the resamplers through them."""
         from . import autograd as ag
         stack = (self.dino_time_embed, self.dino_resampler, self.dino_resampler_adapter, self.vae_time_embed, self.vae_resampler, self.vae_resampler_adapter)
         if ag.needs_grad(*stack) and any(m.training for m in stack):
             return self._physical_visual_embeddings_autograd(dino_middle, dino_source, vae_middle_latents, vae_source_latents)
+        with torch.no_grad():
+            return self._physical_visual_embeddings_forward(dino_middle, dino_source, vae_middle_latents, vae_source_latents)
+
+    def _physical_visual_embeddings_forward(self, dino_middle, dino_source, vae_middle_latents, vae_source_latents):
+        """Inference-mode body of the unit: everything on the native kernels, no graph."""
+        nat = nv.Native.get(dino_middle.device.index or 0)
 
         def dino_branch(px, with_time):
             hs = self.dinov2(px)                                         # [F,256,768]

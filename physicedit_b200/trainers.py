@@ -4,8 +4,9 @@ framework under `compat.install()`.
 In scope here is only what touches the hot path's checkpoint / module contract: `DiffusionTrainingModule` (which parameters are
 trainable, LoRA injection, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into
 LoRA and `pipe.*` keys), `ModelLogger` (who writes that file), the argument parser's flag set and `launch_training_task` (the optimizer loop,
-on plain torch.distributed DDP instead of accelerate; forward and backward on the native kernels).  Dataset readers are the
-reference's training control plane (OUT OF SCOPE): their names exist and fail loudly when used.
+on plain torch.distributed DDP instead of accelerate; forward and backward on the native kernels) and `PhysicalEditingDataset`,
+the training-data format the script instantiates (`physicedit_b200/datasets.py`).  The other dataset readers (`UnifiedDataset`, the data-process
+task) are imported but never used by the PhysicEdit scripts: their names exist and fail loudly when used.
 Reference: DiffSynth-Studio/diffsynth/trainers/utils.py:777-1115.
 """
 from __future__ import annotations
@@ -86,6 +87,28 @@ class DiffusionTrainingModule(torch.nn.Module):
         return cfgs
 
 
+    def switch_pipe_to_training_mode(self, pipe, trainable_models, lora_base_model, lora_target_modules, lora_rank, lora_checkpoint=None,
+                                     enable_fp8_training=False):
+        """:856-888, called from the train script's module constructor (scripts/train/train_physicedit.py:216-220): the 1000-step training
+        table of the scheduler, everything frozen except `trainable_models`, un-merged LoRA injected into `lora_base_model` (optionally
+        initialised from a checkpoint in either PEFT key layout)."""
+        if enable_fp8_training:
+            raise NotImplementedError("fp8 weight storage (enable_fp8_training) is outside the hot path (SURVEY 8f5)")
+        pipe.scheduler.set_timesteps(1000, training=True)
+        pipe.freeze_except([] if trainable_models is None else trainable_models.split(","))
+        if lora_base_model is not None:
+            model = self.add_lora_to_model(getattr(pipe, lora_base_model), target_modules=lora_target_modules.split(","), lora_rank=lora_rank,
+                                           upcast_dtype=pipe.torch_dtype)
+            if lora_checkpoint is not None:
+                from .pipeline import load_state_dict
+                state_dict = self.mapping_lora_state_dict(load_state_dict(lora_checkpoint))
+                result = model.load_state_dict(state_dict, strict=False)
+                print(f"LoRA checkpoint loaded: {lora_checkpoint}, total {len(state_dict)} keys")
+                if len(result.unexpected_keys) > 0:
+                    print(f"Warning, LoRA key mismatch! Unexpected keys in LoRA checkpoint: {result.unexpected_keys}")
+            setattr(pipe, lora_base_model, model)
+
+
 class ModelLogger:
     """trainers/utils.py:891-929: rank 0 writes the trainable-only state dict as safetensors at epoch end / every save_steps."""
 
@@ -144,9 +167,9 @@ def qwen_image_parser():
 
 def _control_plane(name):
     def stub(*args, **kwargs):
-        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (dataset readers): outside the "
-                                  "hot path this framework replaces (SURVEY.md section 2 / 8f3).  Feed launch_training_task any "
-                                  "torch Dataset that yields the sample dictionaries the training module's forward expects.")
+        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (generic dataset readers no PhysicEdit "
+                                  "script uses): outside the hot path this framework replaces (SURVEY.md section 2 / 8f3).  Use "
+                                  "PhysicalEditingDataset, or feed launch_training_task any torch Dataset that yields its sample dictionaries.")
     stub.__name__ = name
     return stub
 
@@ -222,9 +245,7 @@ def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e
 launch_data_process_task = _control_plane("utils.launch_data_process_task")
 
 
-class PhysicalEditingDataset(torch.utils.data.Dataset):
-    def __init__(self, *args, **kwargs):
-        _control_plane("utils.PhysicalEditingDataset")()
+from .datasets import PhysicalEditingDataset  # noqa: E402,F401  (trainers/utils.py:369-683)
 
 
 class UnifiedDataset(torch.utils.data.Dataset):

@@ -1,0 +1,207 @@
+"""CPU tests of the PhysicEdit training-data format (physicedit_b200/datasets.py) on a synthetic clip tree: selection rules, rule
+splitting, frame-count / resolution / key-frame rules, and -- when a reference tree is around -- record-for-record and pixel-for-pixel
+equality with the reference's own PhysicalEditingDataset (DiffSynth-Studio/diffsynth/trainers/utils.py:369-683) reading the same tree
+through the same decoder."""
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+cv2 = pytest.importorskip("cv2")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from physicedit_b200 import datasets as D  # noqa: E402
+
+
+def write_clip(path, n_frames, w, h, seed):
+    wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), 8, (w, h))
+    assert wr.isOpened()
+    yy, xx = np.mgrid[0:h, 0:w]
+    for f in range(n_frames):
+        img = np.stack([(xx * 2 + f * 5 + seed) % 256, (yy * 3 + f * 3) % 256, (xx + yy + f * 7 + seed * 11) % 256], axis=-1).astype(np.uint8)
+        wr.write(img)
+    wr.release()
+
+
+def meta(idx, **over):
+    rec = {"idx": idx, "prompt": f"original {idx}", "state": f"state {idx}", "transition": f"transition {idx}", "edit_instruction": f"edit {idx}",
+           "triplet": {"subject": "ball", "idx": idx},
+           "stage_a": {"principles": [
+               {"id": "r_grav", "priority": "High", "instruction": " things fall ", "visual_cues": [" moves down ", "", 3], "negations": None},
+               {"id": "r_low", "priority": "low", "instruction": "ignored"},
+               {"priority": "HIGH", "instruction": "no id"},                       # -> rule_2
+               "not a dict",                                                          # malformed: skipped
+               {"id": "r_contra", "priority": "high", "instruction": "stays rigid"},
+               {"id": "r_unknown", "priority": "high", "instruction": "no verdict"}]},
+           "stage_b": {"rule_checks": [{"id": "r_grav", "result": "Supported", "matched_cues": ["moves down"]},
+                                       {"id": "r_contra", "result": "contradicted"}, {"id": "rule_2", "result": "SUPPORTED"},
+                                       {"id": "r_low", "result": "supported"}]}}
+    rec.update(over)
+    return rec
+
+
+@pytest.fixture(scope="module")
+def clip_tree(tmp_path_factory):
+    root = tmp_path_factory.mktemp("clips")
+    a, b = root / "scene_b" / "take1", root / "scene_a"
+    (a / "deeper").mkdir(parents=True)
+    b.mkdir(parents=True)
+    write_clip(a / "0.mp4", 52, 96, 64, 1)            # >= 49 frames: the full window
+    write_clip(a / "1.mp4", 10, 80, 48, 2)            # short clip: 9 frames (9 % 4 == 1)
+    write_clip(a / "7.mp4", 12, 64, 64, 3)            # listed in the exclusion file
+    write_clip(a / "9.mp4", 12, 64, 64, 4)            # no metadata record
+    write_clip(a / "take.mp4", 12, 64, 64, 5)         # stem is not an integer
+    write_clip(a / "deeper" / "3.mp4", 12, 64, 64, 6)  # below a clip directory: never visited
+    write_clip(b / "2.mp4", 30, 200, 120, 7)
+    lines = [json.dumps(meta(0, prompt="superseded")), "", "{broken json", json.dumps({"no": "idx"}), json.dumps(meta(0)), json.dumps(meta(1)),
+             json.dumps(meta(7)), json.dumps(meta(3))]
+    (a / D.METADATA_FILE).write_text("\n".join(lines) + "\n", encoding="utf-8")
+    (a / D.EXCLUDED_FILE).write_text("7.mp4\n\n", encoding="utf-8")
+    (a / "deeper" / D.METADATA_FILE).write_text(json.dumps(meta(3)) + "\n", encoding="utf-8")
+    (b / D.METADATA_FILE).write_text(json.dumps(meta(2, stage_b={})) + "\n", encoding="utf-8")
+    return root
+
+
+def test_index_selection_and_rules(clip_tree, capsys):
+    ds = D.PhysicalEditingDataset(root_dir=str(clip_tree), num_frames=49, height=48, width=80, repeat=3)
+    assert "collected 3 samples from 2 leaf dirs" in capsys.readouterr().out
+    assert [(os.path.basename(os.path.dirname(s["path"])), s["idx"]) for s in ds.samples] == [("scene_a", 2), ("take1", 0), ("take1", 1)]
+    assert len(ds) == 9 and not ds.dynamic_resolution
+    s0 = ds.samples[1]
+    assert s0["original_prompt"] == "original 0" and s0["prompt"] == "edit 0" and s0["triplet"] == {"subject": "ball", "idx": 0}   # the later line won
+    assert s0["supported_rules"] == [{"id": "r_grav", "instruction": "things fall", "matched_cues": ["moves down"]},
+                                     {"id": "rule_2", "instruction": "no id", "matched_cues": []}]
+    assert s0["contradicted_rules"] == [{"id": "r_contra", "instruction": "stays rigid"}]
+    assert ds.samples[0]["supported_rules"] == [] and ds.samples[0]["contradicted_rules"] == []                       # no stage-B verdicts
+    rules = D.high_priority_rules(meta(5))
+    assert [r["id"] for r in rules] == ["r_grav", "rule_2", "r_contra", "r_unknown"]
+    assert rules[0]["visual_cues"] == ["moves down", "3"] and rules[0]["negations"] == []
+    with pytest.raises(TypeError):                                  # a record without stage_a is an error in the reference too (:473)
+        D.high_priority_rules({"prompt": "x"})
+    with pytest.raises(TypeError):
+        D.PhysicalEditingDataset(root_dir=str(clip_tree), require_meta=False)      # 9.mp4 has no record: the default record has no stage_a
+
+
+def test_samples_frames_and_key_frames(clip_tree):
+    ds = D.PhysicalEditingDataset(root_dir=str(clip_tree), num_frames=49, height=48, width=80)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                             # a 49-frame window gives exactly six key frames: no warning
+        s = ds[1]
+    assert set(s) == {"image", "edit_image", "middle_key_frames", "stitched_image", "prompt", "state", "transition", "idx", "path", "original_prompt",
+                      "triplet", "supported_rules", "contradicted_rules"}
+    assert s["idx"] == 0 and s["image"].size == (80, 48) and s["edit_image"].size == (80, 48)
+    assert len(s["middle_key_frames"]) == 6 and s["stitched_image"].size == (160, 144)
+    assert np.array_equal(np.asarray(s["stitched_image"].crop((80, 48, 160, 96))), np.asarray(s["middle_key_frames"][3]))      # row 1, column 1
+    assert not np.array_equal(np.asarray(s["image"]), np.asarray(s["edit_image"]))
+    with pytest.warns(UserWarning, match="Expected 6 frames, but got 1"):
+        short = ds[2]                                              # 10-frame clip -> 9 frames -> 7 inner frames -> one run -> one key frame
+    assert len(short["middle_key_frames"]) == 1 and short["stitched_image"] is None
+    assert ds[2 + 3]["idx"] == ds[2]["idx"]                        # repeat wraps around
+    # dynamic resolution: frames keep their own (floored) size, scaled down to max_pixels
+    dyn = D.PhysicalEditingDataset(root_dir=str(clip_tree), num_frames=5, max_pixels=100 * 62)
+    assert dyn.dynamic_resolution and dyn[0]["image"].size == (96, 48)            # 200 x 120 -> 101 x 61 -> floored to multiples of 16
+    assert dyn[1]["image"].size == (96, 64)                                        # 96 x 64 fits: unchanged
+    assert len(dyn[1]["middle_key_frames"]) == 1
+
+
+def test_frame_count_rule_and_geometry():
+    ds = D.PhysicalEditingDataset.__new__(D.PhysicalEditingDataset)
+    ds.num_frames, ds.time_division_factor, ds.time_division_remainder = 81, 4, 1
+
+    class Src:
+        def __init__(self, n): self.n = n
+        def count(self): return self.n
+    assert [ds._get_num_frames(Src(n)) for n in (200, 81, 80, 78, 6, 5, 4, 2, 1, 0)] == [81, 81, 77, 77, 5, 5, 1, 1, 1, 1]
+    from PIL import Image
+    img = Image.fromarray((np.arange(60 * 100 * 3) % 256).astype(np.uint8).reshape(60, 100, 3))
+    out = D.cover_and_center_crop(img, 32, 32)
+    assert out.size == (32, 32)
+    frames = [Image.new("RGB", (4, 4), (i, 0, 0)) for i in range(20)]
+    picked = D.middle_key_frames(frames, 8)                          # inner = frames 1..18 -> runs [1..8] [9..16] [17, 18] -> centres 5, 13, 18
+    assert [p.getpixel((0, 0))[0] for p in picked] == [5, 13, 18]
+    assert D.middle_key_frames(frames[:2], 8) == []
+
+
+def test_train_script_names_resolve_to_the_dataset(clip_tree):
+    from physicedit_b200 import compat
+    saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
+    try:
+        compat.install()
+        from diffsynth.trainers.utils import PhysicalEditingDataset, qwen_image_parser
+        args = qwen_image_parser().parse_args(["--dataset_base_path", str(clip_tree), "--dinov2_path", "unused", "--height", "48", "--width", "80",
+                                               "--num_frames", "49", "--dataset_repeat", "2"])
+        ds = PhysicalEditingDataset(args=args)                     # scripts/train/train_physicedit.py:420
+        assert isinstance(ds, D.PhysicalEditingDataset) and len(ds) == 6 and ds.num_frames == 49 and (ds.height, ds.width) == (48, 80)
+        loader = torch.utils.data.DataLoader(ds, shuffle=False, collate_fn=lambda x: x[0], num_workers=0)      # as launch_training_task builds it
+        first = next(iter(loader))
+        assert first["idx"] == 2 and first["image"].size == (80, 48)
+    finally:
+        for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+# ---- against the reference class itself -------------------------------------------------------------------------------------------------
+class _Cv2Reader:
+    """What the reference asks of `imageio.get_reader(path)` (count_frames / get_data / close), served by the decoder the product uses here."""
+
+    def __init__(self, path):
+        self.src = D._OpenCVFrames(path)
+
+    def count_frames(self): return self.src.count()
+    def get_data(self, i): return self.src.frame(i)
+    def close(self): self.src.close()
+
+
+def _import_reference_dataset():
+    """The reference's class, unmodified, compiled from its own source file: only the `VIDEO_EXTS` constant and the `PhysicalEditingDataset`
+    class statement of trainers/utils.py are executed (the module's other imports -- peft, accelerate, imageio -- are absent here), with
+    `imageio.get_reader` served by the OpenCV reader."""
+    import ast
+    import typing
+    from pathlib import Path
+    import torchvision
+    from PIL import Image
+    from oracle.ref_import import reference_root
+    root = reference_root()
+    if root is None:
+        pytest.skip("no reference tree (baseline/_ref or /root/reference)")
+    path = os.path.join(root, "trainers", "utils.py")
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    keep = [n for n in tree.body if (isinstance(n, ast.ClassDef) and n.name == "PhysicalEditingDataset")
+            or (isinstance(n, ast.Assign) and any(getattr(t, "id", None) == "VIDEO_EXTS" for t in n.targets))]
+    assert len(keep) == 2
+    imageio = types.ModuleType("imageio")
+    imageio.get_reader = _Cv2Reader
+    ns = dict(imageio=imageio, os=os, torch=torch, warnings=warnings, torchvision=torchvision, json=json, Image=Image, Path=Path,
+              Optional=typing.Optional, List=typing.List, Dict=typing.Dict, Any=typing.Any, Set=typing.Set, Tuple=typing.Tuple)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["PhysicalEditingDataset"]
+
+
+def test_matches_the_reference_dataset_record_for_record_and_pixel_for_pixel(clip_tree, monkeypatch):
+    Ref = _import_reference_dataset()
+    monkeypatch.setattr(D, "open_video", lambda p: D._OpenCVFrames(p))             # same decoder on both sides
+    for kw in (dict(num_frames=49, height=48, width=80), dict(num_frames=13, max_pixels=100 * 60), dict(num_frames=81, height=64, width=64, key_frame_stride=3)):
+        ref = Ref(root_dir=str(clip_tree), **kw)
+        ours = D.PhysicalEditingDataset(root_dir=str(clip_tree), **kw)
+        assert ours.samples == ref.samples and len(ours) == len(ref) and ours.dynamic_resolution == ref.dynamic_resolution
+        for i in range(len(ref)):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r, o = ref[i], ours[i]
+            assert set(r) == set(o)
+            for k in r:
+                if k in ("image", "edit_image"):
+                    assert o[k].size == r[k].size and np.array_equal(np.asarray(o[k]), np.asarray(r[k])), (kw, i, k)
+                elif k == "middle_key_frames":
+                    assert len(o[k]) == len(r[k]) and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(o[k], r[k])), (kw, i)
+                elif k == "stitched_image":
+                    assert (o[k] is None) == (r[k] is None) and (o[k] is None or np.array_equal(np.asarray(o[k]), np.asarray(r[k]))), (kw, i)
+                else:
+                    assert o[k] == r[k], (kw, i, k)

@@ -55,7 +55,9 @@ from diffsynth.utils import PipelineUnit, PipelineUnitRunner
     args = ns["qwen_image_parser"]().parse_args(["--dataset_base_path", "x", "--dinov2_path", "y", "--lora_rank", "128", "--use_gradient_checkpointing"])
     assert args.remove_prefix_in_ckpt == "pipe.dit." and args.lora_rank == 128 and args.use_gradient_checkpointing and args.resume_type == "auto"
     with pytest.raises(NotImplementedError, match="control plane"):
-        ns["PhysicalEditingDataset"](args=args)
+        ns["UnifiedDataset"]()                                      # imported by the train script, never used by it
+    from physicedit_b200.datasets import PhysicalEditingDataset
+    assert ns["PhysicalEditingDataset"] is PhysicalEditingDataset   # the dataset the script builds (:420): tests/test_datasets.py
     pipe = _cpu_pipe()
     names = [type(u).__name__ for u in pipe.units]
     assert names == ["QwenImageUnit_ShapeChecker", "QwenImageUnit_NoiseInitializer", "QwenImageUnit_InputImageEmbedder", "QwenImageUnit_Inpaint",

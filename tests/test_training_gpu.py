@@ -402,3 +402,37 @@ def test_hot_loaded_lora_equals_the_folded_lora_within_rounding():
     e, d = rel_l2(hot, folded), rel_l2(hot, plain)
     print(f"\nhot-loaded vs folded LoRA: {e:.3e}; LoRA effect {d:.3e}")
     assert e < 1.5e-2 and d > 5 * e
+
+
+@gpu
+def test_pseudo_targets_carry_gradients_to_the_resampler_stack(nat):
+    """`pipe.physical_visual_embeddings` as the train script reaches it (units -> QwenImageUnit_PhysicalVisualEmbedder, grad mode on, the resampler
+    stack in `trainable_models`, train_multigpu.sh:38): the regression targets carry a graph -- the adapter loss trains the resamplers through them
+    (qwen_image_physical.py:1057-1118 has no no_grad) -- and equal the inference-mode values."""
+    from oracle import aux_oracle as AO
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    torch.manual_seed(5)
+    pipe = QwenImagePhysicPipeline(device="cuda", torch_dtype=torch.bfloat16, dinov2_config=dict(hidden=768, layers=2, heads=12))
+    pipe.to("cuda")
+    stack = ["dino_time_embed", "dino_resampler", "dino_resampler_adapter", "vae_time_embed", "vae_resampler", "vae_resampler_adapter"]
+    ain = {k: v.cuda() for k, v in AO.aux_inputs(seed=8, n_mid=2, lat_hw=(16, 16), dtype=torch.bfloat16).items()}
+    pipe.freeze_except([])
+    with torch.no_grad():
+        want = pipe.physical_visual_embeddings(**ain)
+    assert not want["pseudo_special_emb_dino"].requires_grad
+    frozen = pipe.physical_visual_embeddings(**ain)                      # grad mode on but nothing trainable: still the inference path
+    assert not frozen["pseudo_special_emb_vae"].requires_grad and torch.equal(frozen["pseudo_special_emb_vae"], want["pseudo_special_emb_vae"])
+    pipe.freeze_except(stack)
+    got = pipe.physical_visual_embeddings(**ain)
+    for k in ("pseudo_special_emb_dino", "pseudo_special_emb_vae"):
+        assert got[k].requires_grad and got[k].shape == (1, 64, 3584)
+        assert rel_l2(got[k], want[k]) < 2e-2, (k, rel_l2(got[k], want[k]))
+    gt = torch.randn(1, 64, 3584, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    loss = F.mse_loss(got["pseudo_special_emb_dino"].float(), gt) + F.mse_loss(got["pseudo_special_emb_vae"].float(), gt)
+    loss.backward()
+    nat.check_async()
+    for name in stack:
+        grads = [p.grad for p in getattr(pipe, name).parameters()]
+        assert all(g is not None and torch.isfinite(g.float()).all() for g in grads), name
+        assert any(g.float().abs().sum() > 0 for g in grads), name
+    assert all(p.grad is None for p in pipe.dinov2.parameters())
