@@ -91,8 +91,15 @@ def model_fn_qwen_image(
         # differentiable path on the same GEMM / attention kernels.  Inference calls (is_train=False, or under no_grad) stay on the engine.
         if blockwise_controlnet_conditioning is not None or entity_prompt_emb is not None or enable_fp8_attention:
             raise NotImplementedError("blockwise controlnet / EliGen / fp8 attention under autograd are not part of the PhysicEdit training path")
-        return _model_fn_autograd(dit, visual_thinking_adapter, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents,
-                                  use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae, bool(edit_rope_interpolation))
+        pred, special_token_loss = _model_fn_autograd(dit, visual_thinking_adapter, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents,
+                                                      context_latents, use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae,
+                                                      bool(edit_rope_interpolation))
+        if out is not None:
+            # the pipeline's denoise loop reads the prediction from the buffer it passed (run_cfg_branches): an evaluation in the middle of a
+            # training run (un-merged LoRA still injected, scripts/train/train_physicedit.py:39-169) comes through here
+            with torch.no_grad():
+                out.copy_(pred)
+        return pred, special_token_loss
 
     special_token_loss = 0
     if special_token_mask is not None:

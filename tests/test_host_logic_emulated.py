@@ -442,3 +442,57 @@ def test_feature_extractor_host_logic_matches_the_aux_oracle(monkeypatch):
     e_d, e_v = rel(out["pseudo_special_emb_dino"], ed), rel(out["pseudo_special_emb_vae"], ev)
     print(f"feature extractors on the emulated ABI vs the fp32 aux oracle: dinov2 {rel(d_nat, d_ref):.3e}; targets dino {e_d:.3e} vae {e_v:.3e}")
     assert out["pseudo_special_emb_dino"].shape == (1, 64, 3584) and e_d < 3e-2 and e_v < 3e-2
+
+
+def test_denoise_with_unmerged_lora_matches_the_merged_weights(monkeypatch):
+    """An evaluation in the middle of a training run (train_physicedit.py:39-169 calls `pipe(..., is_train=False)` with the LoRA wrappers still in
+    the DiT): the loop's forwards go through the un-merged path and must land in the buffers the loop combines -- same latents as after
+    `merge_lora` up to bf16 rounding of `W + B A` vs `W x + B (A x)`."""
+    from oracle import dit_oracle as O
+    from physicedit_b200 import adapters, autograd, native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.lora import inject_lora, merge_lora
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    monkeypatch.setattr(autograd, "_nat", lambda t: emu)
+    autograd.weight_transposes.clear()
+    H = Wd = 64
+    W = O.synth_weights(O.dit_param_shapes(1), seed=61)
+    A = O.synth_weights(O.adapter_param_shapes(), seed=62)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.to(torch.bfloat16) for k, v in W.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+
+    def bind():
+        eng = object.__new__(DiTEngine)
+        eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+        eng._pack()
+        object.__setattr__(dit, "_engine", eng)
+    bind()
+    inject_lora(dit, ["to_q", "to_out.0", "img_mlp.net.2", "img_mod.1", "add_v_proj"], r=8)
+    g = torch.Generator().manual_seed(63)
+    for name, p in dit.named_parameters():
+        if "lora_" in name:
+            p.data = (torch.randn(p.shape, generator=g) * (1.0 / math.sqrt(p.shape[1]))).bfloat16()
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict({k: v.to(torch.bfloat16) for k, v in A.items()})
+    pipe.visual_thinking_adapter.to(torch.bfloat16)
+    pipe.cfg_streams = 1
+    pipe.eval()
+    posi = O.synth_inputs(H, Wd, 88, seed=64, dtype=torch.bfloat16)
+    nega = O.synth_inputs(H, Wd, 72, seed=65, dtype=torch.bfloat16)
+    keys = ("prompt_emb", "prompt_emb_mask", "special_token_mask")
+    run = lambda: pipe.denoise(posi["latents"], {k: posi[k].clone() for k in keys}, {k: nega[k].clone() for k in keys}, posi["edit_latents"], height=H, width=Wd,
+                               num_inference_steps=2, cfg_scale=4.0)
+    unmerged = run()
+    assert torch.isfinite(unmerged.float()).all()
+    merge_lora(dit)
+    bind()
+    merged = run()
+    e = rel(unmerged, merged)
+    print(f"2-step CFG loop, un-merged LoRA vs merged weights: {e:.3e}")
+    assert e < 2e-2 and not torch.equal(merged, posi["latents"])

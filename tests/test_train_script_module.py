@@ -53,6 +53,9 @@ class _StubVAE(torch.nn.Module):
         g = torch.Generator().manual_seed(int(x.shape[-1]) * 7 + int(x.shape[-2]))
         return torch.randn(x.shape[0], 16, x.shape[2] // 8, x.shape[3] // 8, generator=g).to(x.dtype)
 
+    def decode(self, z, **kw):
+        return torch.tanh(z[:, :3].float()).repeat_interleave(8, dim=2).repeat_interleave(8, dim=3).to(z.dtype)
+
 
 @pytest.fixture()
 def script_module(monkeypatch):
@@ -67,7 +70,7 @@ def script_module(monkeypatch):
          "from diffsynth.trainers.utils import DiffusionTrainingModule, ModelLogger, qwen_image_parser, launch_training_task, launch_data_process_task, PhysicalEditingDataset\n"
          "from diffsynth.trainers.unified_dataset import UnifiedDataset\n", ns)                 # lines 1-6 of the script
     tree = ast.parse(open(SCRIPT, encoding="utf-8").read())
-    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "QwenImageTrainingModule"]
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("QwenImageTrainingModule", "WandbModelLogger")]
     exec(compile(ast.Module(body=cls, type_ignores=[]), SCRIPT, "exec"), ns)
     yield ns
     for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
@@ -173,3 +176,32 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
                  "vae_time_embed", "attn.to_q.lora_B", "img_mlp.net.2.lora_B", "img_mod.1.lora_B"):       # lora_B starts at zero (PEFT init): dA = 0 on step one
         hit = [g for n, g in grads.items() if part in n and g is not None]
         assert hit and all(torch.isfinite(g.float()).all() for g in hit) and any(g.float().abs().sum() > 0 for g in hit), part
+
+    # ---- the script's logger on this framework's stand-in for accelerate.Accelerator (trainers._Ranks): checkpoint + mid-training evaluation
+    from safetensors.torch import load_file
+    from physicedit_b200.trainers import _Ranks
+    logger = script_module["WandbModelLogger"](str(tmp_path / "out"), remove_prefix_in_ckpt="pipe.dit.", eval_every_n_steps=1, eval_data=dataset)
+    path = logger.save_checkpoint(_Ranks(), module, 3)                                            # :171-186
+    ck = load_file(path)
+    assert path.endswith("step-3.safetensors") and set(ck) == set(sd) and ck["transformer_blocks.0.attn.to_q.lora_B.default.weight"].shape == (3072, 8)
+    # resume_type "model" (:527-548): keys without `pipe.` get the stripped prefix back, then a non-strict load into the training module
+    before = {k: v.detach().clone() for k, v in module.state_dict().items() if k in module.trainable_param_names()}
+    with torch.no_grad():
+        for p_ in module.trainable_modules():
+            p_.zero_()
+    missing, unexpected = module.load_state_dict({(k if k.startswith("pipe.") else f"pipe.dit.{k}"): v for k, v in ck.items()}, strict=False)
+    assert unexpected == [] and not (set(missing) & set(before))
+    assert all(torch.equal(module.state_dict()[k], v) for k, v in before.items())
+    calls = {}
+
+    def fake_denoise(latents, inputs_posi, inputs_nega, edit_latents=None, context_latents=None, **kw):
+        calls.update(kw, T_posi=inputs_posi["prompt_emb"].shape[1], has_nega=inputs_nega is not None, grad=torch.is_grad_enabled(), training=module.training)
+        return latents
+    monkeypatch.setattr(pipe, "denoise", fake_denoise)
+    module.train()
+    metrics = logger.evaluate_model(module, _Ranks())                                             # :39-169 -> pipe(prompt, edit_image, is_train=False)
+    assert "eval_error" not in metrics, metrics
+    assert os.path.isfile(metrics["eval_edit_image_path"]) and metrics["eval_edit_image_path"].endswith("_idx_4.jpg")
+    assert calls["height"] == 480 and calls["width"] == 832 and calls["num_inference_steps"] == 40 and calls["has_nega"] and not calls["grad"] and not calls["training"]
+    assert module.training and len(pipe.scheduler.timesteps) == 1000                              # training mode and the training table restored
+    assert "generate" in pipe.text_encoder.calls                                                  # inference: the transition text is generated
