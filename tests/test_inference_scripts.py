@@ -86,3 +86,42 @@ def test_inference_pica_main_runs_on_this_framework(monkeypatch, tmp_path, capsy
         for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+@needs_ref
+def test_validate_py_main_256x256_four_steps(monkeypatch, tmp_path, capsys):
+    """BASELINE.json configs[0]: scripts/inference/validate.py, one 256 x 256 edit, 4 denoise steps -- the script's own `main()` (argument parsing,
+    from_pretrained, `load_finetuned_into_pipe` without a checkpoint, image load, `pipe(...)`, save) on this framework with the C ABI emulated.
+    The script's `resize_image` (which would blow the input up to ~1024^2) is pinned to the 256 x 256 the config names."""
+    from PIL import Image
+    from physicedit_b200 import compat
+    from test_train_script_module import _pipe_on_the_emulator
+    script_path = os.path.join(REF, "scripts", "inference", "validate.py")
+    saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
+    compat.install()
+    try:
+        spec = importlib.util.spec_from_file_location("ref_validate_main", script_path)
+        sys.dont_write_bytecode = True
+        script = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(script)
+        emu = EmulatedNative()
+        pipe = _pipe_on_the_emulator(monkeypatch, emu)
+        pipe.cfg_streams = 1
+        monkeypatch.setattr(script.QwenImagePhysicPipeline, "from_pretrained", staticmethod(lambda **kw: pipe))
+        monkeypatch.setattr(script, "resize_image", lambda image, target_area=None: image.resize((256, 256)))
+        src = tmp_path / "in.png"
+        Image.new("RGB", (300, 280), (200, 120, 40)).save(src)
+        dst = tmp_path / "results" / "edited.png"
+        monkeypatch.setattr(sys, "argv", ["validate.py", "--prompt", "let the ice melt", "--image_path", str(src), "--save_path", str(dst), "--seed", "5",
+                                          "--num_inference_steps", "4"])
+        script.main()
+        out = capsys.readouterr().out
+        assert "No checkpoint path provided" in out and "[DONE] Saved result" in out
+        assert Image.open(dst).size == (256, 256)
+        names = [c[0] for c in emu.calls]
+        assert names.count("pe_cfg_euler_step") == 4 and names.count("pe_special_blend_scatter") == 8 and names.count("pe_timestep_embedding") == 4
+        assert names.count("pe_attention_fwd") == 8                      # 4 steps x 2 CFG branches x 1 block
+    finally:
+        for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
