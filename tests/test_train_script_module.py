@@ -205,3 +205,37 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
     assert calls["height"] == 480 and calls["width"] == 832 and calls["num_inference_steps"] == 40 and calls["has_nega"] and not calls["grad"] and not calls["training"]
     assert module.training and len(pipe.scheduler.timesteps) == 1000                              # training mode and the training table restored
     assert "generate" in pipe.text_encoder.calls                                                  # inference: the transition text is generated
+
+
+@needs_ref
+def test_the_whole_train_script_runs_as_main_in_a_fresh_process(tmp_path):
+    """scripts/train/train_physicedit.py executed as `__main__`, unmodified (tests/run_train_script.py: compat aliases, a stand-in for the absent
+    `accelerate`, models on the emulated ABI): flags of train_multigpu.sh at a small size, two clips, one epoch -> trainable-parameter report, two
+    optimizer steps, the epoch checkpoint in the layout validate.py reads and its metadata file."""
+    import json
+    import subprocess
+    from safetensors.torch import load_file
+    from test_datasets import meta, write_clip
+    from physicedit_b200 import datasets as D
+    clip_dir = tmp_path / "clips" / "scene"
+    clip_dir.mkdir(parents=True)
+    for i in (0, 1):
+        write_clip(clip_dir / f"{i}.mp4", 50, 96, 64, 10 + i)
+    (clip_dir / D.METADATA_FILE).write_text("".join(json.dumps(meta(i)) + "\n" for i in (0, 1)), encoding="utf-8")
+    out = tmp_path / "run"
+    flags = ["--dataset_base_path", str(tmp_path / "clips"), "--height", "64", "--width", "96", "--num_frames", "49", "--data_file_keys", "image",
+             "--extra_inputs", EXTRA, "--max_pixels", "1048576", "--dataset_repeat", "1", "--dinov2_path", "unused", "--learning_rate", "5e-5",
+             "--num_epochs", "1", "--remove_prefix_in_ckpt", "pipe.dit.", "--output_path", str(out), "--lora_base_model", "dit",
+             "--lora_target_modules", TARGETS, "--lora_rank", "8", "--use_gradient_checkpointing", "--dataset_num_workers", "0", "--find_unused_parameters",
+             "--trainable_models", TRAINABLE]
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", WANDB_MODE="disabled")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_train_script.py"), SCRIPT] + flags,
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MODEL TRAINABLE PARAMETERS REPORT" in r.stdout and "collected 2 samples" in r.stdout and "[HARNESS] emulated launches" in r.stdout
+    ck = load_file(str(out / "epoch-0.safetensors"))
+    assert "transformer_blocks.0.attn.to_q.lora_A.default.weight" in ck and "pipe.dino_resampler.latents" in ck and "pipe.vae_time_embed.weight" in ck
+    assert not any(k.startswith("pipe.dit.") or k.startswith("pipe.dinov2.") for k in ck)
+    assert ck["transformer_blocks.0.attn.to_q.lora_B.default.weight"].float().abs().sum() > 0           # two AdamW steps moved B off its zero init
+    md = json.loads((out / "epoch-0.json").read_text())
+    assert md["global_step"] == 2 and md["save_type"] == "epoch" and md["num_processes"] == 1 and md["batches_per_epoch_total"] == 2
