@@ -66,7 +66,7 @@ def test_inference_pica_main_runs_on_this_framework(monkeypatch, tmp_path, capsy
         monkeypatch.setattr(script, "load_dataset", lambda name, cache_dir=None: {"picabench": records})
         out_dir = tmp_path / "out"
         monkeypatch.setattr(sys, "argv", ["inference_pica.py", "--base_model_path", str(tmp_path / "base"), "--dinov2_path", "unused", "--data_path", str(tmp_path),
-                                          "--lora_path", ck_path, "--output_path", str(out_dir), "--num_inference_steps", "1", "--start_idx", "1", "--end_idx", "900",
+                                          "--lora_path", ck_path, "--output_path", str(out_dir), "--num_inference_steps", "1", "--start_idx", "2", "--end_idx", "900",
                                           "--seed", "11"])
         script.main()
         assert seen["device"] == "cuda" and len(seen["model_configs"]) == 3 and seen["model_configs"][0].origin_file_pattern.startswith("transformer/")
@@ -74,13 +74,13 @@ def test_inference_pica_main_runs_on_this_framework(monkeypatch, tmp_path, capsy
         want = w_q + torch.mm(ck["transformer_blocks.0.attn.to_q.lora_B.default.weight"], ck["transformer_blocks.0.attn.to_q.lora_A.default.weight"])
         assert torch.equal(pipe.dit.transformer_blocks[0].attn.to_q.weight, want)
         assert all(torch.equal(pipe.visual_thinking_adapter.state_dict()[k], v) for k, v in ad_new.items())
-        # records 1 and 2 were edited at their own size (rounded up to multiples of 16) and saved as <idx>.jpg
+        # record 2 (start_idx .. min(end_idx, len)) was edited at its own size and saved as <idx>.jpg
         files = sorted(os.listdir(out_dir))
-        assert files == ["00001.jpg", "00002.jpg"]
-        assert Image.open(out_dir / "00001.jpg").size == (96, 64)
+        assert files == ["00002.jpg"]
+        assert Image.open(out_dir / "00002.jpg").size == (96, 64)
         names = [c[0] for c in emu.calls]
-        assert names.count("pe_cfg_euler_step") == 2 and names.count("pe_special_blend_scatter") == 4          # 2 images x 1 step x 2 CFG branches
-        assert pipe.text_encoder.calls.count("generate") == 4 and pipe.text_encoder.calls.count("edit_forward") == 4
+        assert names.count("pe_cfg_euler_step") == 1 and names.count("pe_special_blend_scatter") == 2          # 1 image x 1 step x 2 CFG branches
+        assert pipe.text_encoder.calls.count("generate") == 2 and pipe.text_encoder.calls.count("edit_forward") == 2
         assert "[DONE] Generated" in capsys.readouterr().out
     finally:
         for k in [k for k in sys.modules if k == "diffsynth" or k.startswith("diffsynth.")]:
