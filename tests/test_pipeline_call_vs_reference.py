@@ -1,0 +1,116 @@
+"""`pipe(prompt, edit_image=..., is_train=False)` end to end: the REFERENCE pipeline object (its own __init__, units, loop, stock PyTorch DiT on the
+CPU, fp32 and bf16) against this package's pipeline (units, native loop on the emulated C ABI), same weights, same stub text encoder / VAE, same
+tokenizer / processor files.  Compared: the latents each pipeline hands to `vae.decode` -- this package has to be as close to the reference's
+fp32 result as the reference's own bf16 run is (floor + 1e-3), the protocol of the GPU parity tests.  What this adds to the per-part tests: the
+glue of `__call__` itself (how the unit outputs reach `model_fn`, the noise draw, height / width rounding, scheduler shift, CFG, the persistent
+per-branch prompt mutation)."""
+import os
+import sys
+
+import pytest
+import torch
+from PIL import Image
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from abi_emulator import EmulatedNative  # noqa: E402
+from oracle import dit_oracle as O  # noqa: E402
+from oracle import ref_import  # noqa: E402
+from test_units_vs_reference import PROC, TOK, picture  # noqa: E402
+
+pytestmark = pytest.mark.skipif(ref_import.reference_root() is None or not os.path.isdir(TOK), reason="no reference tree / tokenizer files on this machine")
+
+
+class StubVL:
+    def __init__(self, reply_ids):
+        self.reply_ids = reply_ids
+
+    def edit_forward(self, input_ids=None, **kw):
+        g = torch.Generator().manual_seed(int(input_ids.sum()) % 9973)
+        return (torch.randn(input_ids.shape[0], input_ids.shape[1], 3584, generator=g) * 2.0,)
+
+    def generate(self, input_ids=None, **kw):
+        return torch.cat([input_ids, self.reply_ids.unsqueeze(0)], dim=1)
+
+
+class StubVAE:
+    def __init__(self):
+        self.decoded = []
+
+    def encode(self, x, **kw):
+        g = torch.Generator().manual_seed(int(x.shape[-1]) * 31 + int(x.shape[-2]))
+        return torch.randn(x.shape[0], 16, x.shape[2] // 8, x.shape[3] // 8, generator=g).to(x.dtype)
+
+    def decode(self, z, **kw):
+        self.decoded.append(z.detach().float().cpu().clone())
+        return torch.tanh(z[:, :3].float()).repeat_interleave(8, dim=2).repeat_interleave(8, dim=3).to(z.dtype)
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def test_call_matches_the_reference_pipeline(tmp_path, monkeypatch):
+    from transformers import Qwen2Tokenizer, Qwen2VLProcessor
+    from physicedit_b200 import adapters, native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    Wsd = O.synth_weights(O.dit_param_shapes(1), seed=71, dtype=torch.bfloat16)
+    Asd = O.synth_weights(O.adapter_param_shapes(), seed=72, dtype=torch.bfloat16)
+    tok = Qwen2Tokenizer.from_pretrained(TOK)
+    base = Qwen2VLProcessor.from_pretrained(PROC)
+    reply = tok('{"middle_transition_prompt": "The glass tips and the water runs out."}', return_tensors="pt").input_ids[0]
+    image = picture(320, 256, 5)
+    call = dict(prompt="tip the glass over", edit_image=image, seed=3, num_inference_steps=3, height=64, width=96, is_train=False,
+                edit_image_auto_resize=False)            # the edit image keeps its 320 x 256 (320 tokens instead of 4096): a CPU-sized request
+
+    def processor():
+        return Qwen2VLProcessor(image_processor=base.image_processor, tokenizer=Qwen2Tokenizer.from_pretrained(TOK), video_processor=base.video_processor,
+                                chat_template=base.chat_template)
+    ref_import.tiny_dinov2_folder(str(tmp_path / "dino"))
+    out = {}
+    with ref_import.ReferenceModules() as ref:
+        for dtype in (torch.float32, torch.bfloat16):
+            pipe = ref.phys.QwenImagePhysicPipeline(device="cpu", torch_dtype=dtype, dinov2_path=str(tmp_path / "dino"))
+            pipe.dit = ref_import.build_reference_dit(ref, Wsd, 1, dtype, "cpu")
+            pipe.visual_thinking_adapter.load_state_dict({k: v.to(dtype) for k, v in Asd.items()})
+            pipe.visual_thinking_adapter.to(dtype)
+            pipe.text_encoder, pipe.vae, pipe.tokenizer, pipe.processor = StubVL(reply), StubVAE(), tok, processor()
+            pipe.processor.tokenizer.add_special_tokens({"additional_special_tokens": ["<begin_of_img>", "<end_of_img>"] + [f"<img{i}>" for i in range(64)]})
+            pipe.boi_token_id = pipe.processor.tokenizer.convert_tokens_to_ids("<begin_of_img>")            # from_pretrained :528-539
+            pipe.eoi_token_id = pipe.processor.tokenizer.convert_tokens_to_ids("<end_of_img>")
+            if dtype == torch.float32:
+                # NoiseInitializer draws in the pipeline dtype (:689): an fp32 pipeline would start from different noise.  Give the fp32 truth the bf16 draw.
+                draw = pipe.generate_noise
+                pipe.generate_noise = lambda shape, **kw: draw(shape, **dict(kw, rand_torch_dtype=torch.bfloat16)).float()
+            img = pipe(**call)
+            out[dtype] = (pipe.vae.decoded[-1], img)
+    # this package: same weights, native loop on the emulated ABI
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.clone() for k, v in Wsd.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict(Asd)
+    pipe.text_encoder, pipe.vae = StubVL(reply), StubVAE()
+    pipe.batch_cfg_generation = False
+    pipe.attach_tokenizer(tokenizer=tok, processor=processor())
+    pipe.to(torch.bfloat16)
+    pipe.cfg_streams = 1
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    img = pipe(**call)
+    got = pipe.vae.decoded[-1]
+    l32, l16 = out[torch.float32][0], out[torch.bfloat16][0]
+    floor, err = rel(l16, l32), rel(got, l32)
+    print(f"pipe(...) latents: this package vs reference fp32 {err:.3e}; reference bf16 vs fp32 {floor:.3e}; this package vs reference bf16 {rel(got, l16):.3e}")
+    assert got.shape == l32.shape == (1, 16, 8, 12) and floor < 0.1 and err <= floor + 1e-3 and rel(got, l16) < 1e-2, (err, floor, rel(got, l16))
+    assert isinstance(img, Image.Image) and img.size == out[torch.float32][1].size == (96, 64)
+    names = [c[0] for c in emu.calls]
+    assert names.count("pe_cfg_euler_step") == 3 and names.count("pe_special_blend_scatter") == 6
