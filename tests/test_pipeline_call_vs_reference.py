@@ -114,3 +114,65 @@ def test_call_matches_the_reference_pipeline(tmp_path, monkeypatch):
     assert isinstance(img, Image.Image) and img.size == out[torch.float32][1].size == (96, 64)
     names = [c[0] for c in emu.calls]
     assert names.count("pe_cfg_euler_step") == 3 and names.count("pe_special_blend_scatter") == 6
+
+
+def test_training_loss_matches_the_reference_pipeline(tmp_path, monkeypatch):
+    """`pipe.training_loss(global_step=, **models, **inputs)` as scripts/train/train_physicedit.py:309-310 calls it: the reference pipeline object (stock
+    PyTorch autograd on the CPU, bf16) against this package's (autograd Functions on the emulated C ABI), same weights, same `inputs`, same RNG stream for
+    the two draws (timestep id, noise; :314-317).  Trainable here: the dual adapter and the two pseudo targets (the reference's un-merged LoRA needs
+    peft, which is absent -- that part is checked against the oracle).  Compared: the loss, `special_token_loss`, every adapter gradient, d loss / d targets."""
+    from physicedit_b200 import adapters, autograd, native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    Wsd = O.synth_weights(O.dit_param_shapes(1), seed=81, dtype=torch.bfloat16)
+    Asd = O.synth_weights(O.adapter_param_shapes(), seed=82, dtype=torch.bfloat16)
+    H, Wd, T = 64, 96, 120
+    inp = O.synth_inputs(H, Wd, T, seed=83, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(84)
+    base = dict(input_latents=torch.randn(1, 16, H // 8, Wd // 8, generator=g).bfloat16(), height=H, width=Wd, edit_latents=inp["edit_latents"],
+                prompt_emb_mask=inp["prompt_emb_mask"], special_token_mask=inp["special_token_mask"], use_gradient_checkpointing=True,
+                use_gradient_checkpointing_offload=False, cfg_scale=1, is_train=True)
+    gt = [(torch.randn(1, 64, 3584, generator=g) * 0.5).bfloat16() for _ in range(2)]
+
+    def run(pipe):
+        pipe.scheduler.set_timesteps(1000, training=True)
+        pipe.freeze_except(["visual_thinking_adapter"])
+        targets = [t.clone().requires_grad_() for t in gt]
+        inputs = dict(base, prompt_emb=inp["prompt_emb"].clone(), pseudo_special_emb_dino=targets[0], pseudo_special_emb_vae=targets[1])
+        models = {name: getattr(pipe, name) for name in pipe.in_iteration_models}
+        torch.manual_seed(4321)
+        loss = pipe.training_loss(global_step=10, **models, **inputs)
+        loss.backward()
+        grads = {n: p.grad.detach().float().clone() for n, p in pipe.visual_thinking_adapter.named_parameters()}
+        return loss.item(), pipe.special_token_loss, grads, [t.grad.float().clone() for t in targets]
+
+    ref_import.tiny_dinov2_folder(str(tmp_path / "dino"))
+    with ref_import.ReferenceModules() as ref:
+        rp = ref.phys.QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, dinov2_path=str(tmp_path / "dino"))
+        rp.dit = ref_import.build_reference_dit(ref, Wsd, 1, torch.bfloat16, "cpu")
+        rp.visual_thinking_adapter.load_state_dict(Asd)
+        rp.visual_thinking_adapter.to(torch.bfloat16)
+        want = run(rp)
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    monkeypatch.setattr(autograd, "_nat", lambda t: emu)
+    autograd.weight_transposes.clear()
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.clone() for k, v in Wsd.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict(Asd)
+    pipe.to(torch.bfloat16)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    got = run(pipe)
+    cat = lambda d: torch.cat([d[k].flatten() for k in sorted(d)])
+    e_ad, e_t = rel(cat(got[2]), cat(want[2])), max(rel(a, b) for a, b in zip(got[3], want[3]))
+    print(f"training_loss: {got[0]:.5f} vs reference {want[0]:.5f}; special_token_loss {got[1]:.5f} vs {want[1]:.5f}; adapter grads {e_ad:.3e}; d targets {e_t:.3e}")
+    assert set(got[2]) == set(want[2]) and abs(got[0] - want[0]) < 1e-2 * abs(want[0]) and abs(got[1] - want[1]) < 1e-2 * abs(want[1])
+    assert e_ad < 3e-2 and e_t < 3e-2
