@@ -88,7 +88,7 @@ def install() -> None:
         PipelineUnitRunner=units.PipelineUnitRunner)
     mod("diffsynth.trainers").__path__ = []
     mod("diffsynth.trainers.utils", **{k: getattr(trainers, k) for k in ("DiffusionTrainingModule", "ModelLogger", "qwen_image_parser",
-                                                                          "launch_training_task", "launch_data_process_task", "PhysicalEditingDataset")})
+                                                                          "launch_training_task", "launch_data_process_task", "PhysicalEditingDataset", "Pica100kDataset")})
     mod("diffsynth.trainers.unified_dataset", UnifiedDataset=trainers.UnifiedDataset)
     mod("diffsynth.pipelines.flux_image_new", ControlNetInput=ControlNetInput)
     mod("diffsynth.pipelines.helpers", **{k: getattr(adapters, k) for k in ("FeedForward", "PerceiverAttention", "PerceiverResampler",

@@ -1,7 +1,8 @@
-"""The PhysicEdit training-data format: `PhysicalEditingDataset`, the one dataset scripts/train/train_physicedit.py builds (:420) and whose
-sample dictionaries feed `QwenImageTrainingModule.forward_preprocess` (:255-296) and through it the pipeline's units.
+"""The PhysicEdit training-data formats: `PhysicalEditingDataset`, the one dataset scripts/train/train_physicedit.py builds (:420) and whose
+sample dictionaries feed `QwenImageTrainingModule.forward_preprocess` (:255-296) and through it the pipeline's units; and `Pica100kDataset`
+(image pairs of PICA-100K, trainers/utils.py:685-775).
 
-Mirrors DiffSynth-Studio/diffsynth/trainers/utils.py:367-683 (constructor signature, `samples` records, sample keys, frame-count /
+Mirrors DiffSynth-Studio/diffsynth/trainers/utils.py:367-775 (constructor signature, `samples` records, sample keys, frame-count /
 resolution / key-frame rules, warnings and error behaviour); host-side only -- frames are decoded on the CPU and handed to the units as PIL
 images exactly like the reference does, the GPU work starts at the VAE / DINOv2 encoders.
 
@@ -141,6 +142,24 @@ def cover_and_center_crop(image: Image.Image, target_height: int, target_width: 
     return image.crop((left, top, left + target_width, top + target_height))
 
 
+def snapped_size(image: Image.Image, max_pixels: int, height_division_factor: int, width_division_factor: int) -> Tuple[int, int]:
+    """Dynamic resolution (:562-574, :739-751): the image's own (height, width), scaled down to `max_pixels` and floored to the division factors."""
+    width, height = image.size
+    if width * height > max_pixels:
+        scale = (width * height / max_pixels) ** 0.5
+        height, width = int(height / scale), int(width / scale)
+    snap = lambda v, f: max(f, v // f * f)
+    return snap(height, height_division_factor), snap(width, width_division_factor)
+
+
+def resolution_mode(height, width) -> bool:
+    """True = dynamic resolution: unless BOTH sides are given (:406-414, :716-724, messages included)."""
+    print({(False, False): "Height and width are fixed. Setting `dynamic_resolution` to False.",
+           (True, True): "Height and width are none. Setting `dynamic_resolution` to True."}.get(
+               (height is None, width is None), "One of height/width is None. Setting `dynamic_resolution` to True."))
+    return height is None or width is None
+
+
 def middle_key_frames(frames: List[Image.Image], stride: int) -> List[Image.Image]:
     """The centre frame of every `stride`-long run of the frames strictly between the first and the last (:620-633)."""
     inner = frames[1:-1] if len(frames) > 2 else []
@@ -180,10 +199,7 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
         self.height_division_factor, self.width_division_factor = int(height_division_factor), int(width_division_factor)
         self.require_meta = bool(require_meta)
         self.video_file_extension = video_file_extension
-        self.dynamic_resolution = self.height is None or self.width is None
-        print({(False, False): "Height and width are fixed. Setting `dynamic_resolution` to False.",
-               (True, True): "Height and width are none. Setting `dynamic_resolution` to True."}.get(
-                   (self.height is None, self.width is None), "One of height/width is None. Setting `dynamic_resolution` to True."))
+        self.dynamic_resolution = resolution_mode(self.height, self.width)
         self.samples: List[Dict[str, Any]] = self._build_samples(self.root)
         if not self.samples:
             warnings.warn("PhysicalEditingDataset: no valid samples found.")
@@ -254,12 +270,7 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
         """Fixed (height, width), or -- dynamic resolution -- the frame's own size scaled down to `max_pixels` and floored to the division factors (:562-574)."""
         if not self.dynamic_resolution:
             return self.height, self.width
-        width, height = image.size
-        if width * height > self.max_pixels:
-            scale = (width * height / self.max_pixels) ** 0.5
-            height, width = int(height / scale), int(width / scale)
-        snap = lambda v, f: max(f, v // f * f)
-        return snap(height, self.height_division_factor), snap(width, self.width_division_factor)
+        return snapped_size(image, self.max_pixels, self.height_division_factor, self.width_division_factor)
 
     def _get_num_frames(self, source) -> int:
         """`num_frames`, or for a shorter clip the largest n <= its length with n % time_division_factor == time_division_remainder (:576-593)."""
@@ -314,3 +325,45 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
         return {"image": frames[-1], "edit_image": frames[0], "middle_key_frames": keys, "stitched_image": stitched, "prompt": rec["prompt"],
                 "state": rec["state"], "transition": rec["transition"], "idx": rec["idx"], "path": rec["path"], "original_prompt": rec["original_prompt"],
                 "triplet": rec["triplet"], "supported_rules": rec["supported_rules"], "contradicted_rules": rec["contradicted_rules"]}
+
+
+class Pica100kDataset(torch.utils.data.Dataset):
+    """trainers/utils.py:685-775: image pairs of the PICA-100K set (Hugging Face `datasets` record: `src_img`, `tgt_img`, `superficial_prompt`) as
+    training samples -- the target as `image`, the source as a one-element `edit_image` list, both cover-resized / centre-cropped like the clips."""
+
+    def __init__(self, dataset_id: str = "Andrew613/PICA-100K", split: str = "train", cache_dir: Optional[str] = None, max_pixels: int = 1920 * 1080,
+                 height: Optional[int] = None, width: Optional[int] = None, height_division_factor: int = 16, width_division_factor: int = 16,
+                 repeat: int = 1, args=None):
+        if args is not None:
+            dataset_id = getattr(args, "dataset_id", dataset_id)
+            height, width = getattr(args, "height", height), getattr(args, "width", width)
+            max_pixels = getattr(args, "max_pixels", max_pixels)
+            repeat = getattr(args, "dataset_repeat", repeat)
+        self.dataset_id, self.split, self.cache_dir = dataset_id, split, cache_dir
+        self.max_pixels, self.height, self.width, self.repeat = int(max_pixels), height, width, int(repeat)
+        self.height_division_factor, self.width_division_factor = int(height_division_factor), int(width_division_factor)
+        self.dynamic_resolution = resolution_mode(self.height, self.width)
+        from datasets import load_dataset                     # local cache only on a machine without network: the caller's `cache_dir`
+        self.data = load_dataset(self.dataset_id, split=self.split, cache_dir=self.cache_dir)
+
+    _crop_and_resize = staticmethod(cover_and_center_crop)
+
+    def _get_height_width(self, image: Image.Image) -> Tuple[int, int]:
+        if not self.dynamic_resolution:
+            return self.height, self.width
+        return snapped_size(image, self.max_pixels, self.height_division_factor, self.width_division_factor)
+
+    def _process_image(self, image: Image.Image) -> Image.Image:
+        image = image.convert("RGB")
+        return cover_and_center_crop(image, *self._get_height_width(image))
+
+    def __len__(self) -> int:
+        return len(self.data) * self.repeat
+
+    def __getitem__(self, data_id: int) -> Optional[Dict[str, Any]]:
+        rec = self.data[data_id % len(self.data)]
+        src, tgt = rec.get("src_img"), rec.get("tgt_img")
+        if src is None or tgt is None:
+            warnings.warn("Pica100kDataset: missing src_img/tgt_img.")
+            return None
+        return {"image": self._process_image(tgt), "edit_image": [self._process_image(src)], "prompt": rec.get("superficial_prompt", "")}

@@ -245,7 +245,7 @@ def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e
 launch_data_process_task = _control_plane("utils.launch_data_process_task")
 
 
-from .datasets import PhysicalEditingDataset  # noqa: E402,F401  (trainers/utils.py:369-683)
+from .datasets import PhysicalEditingDataset, Pica100kDataset  # noqa: E402,F401  (trainers/utils.py:369-683, :685-775)
 
 
 class UnifiedDataset(torch.utils.data.Dataset):

@@ -205,3 +205,48 @@ def test_matches_the_reference_dataset_record_for_record_and_pixel_for_pixel(cli
                     assert (o[k] is None) == (r[k] is None) and (o[k] is None or np.array_equal(np.asarray(o[k]), np.asarray(r[k]))), (kw, i)
                 else:
                     assert o[k] == r[k], (kw, i, k)
+
+
+def test_pica100k_dataset_matches_the_reference(monkeypatch):
+    """Pica100kDataset (trainers/utils.py:685-775) over in-memory records standing in for the Hugging Face download: same samples as the reference
+    class, pixel for pixel, fixed and dynamic resolution; a record without images warns and yields None."""
+    import ast
+    import typing
+    import datasets as hf
+    import torchvision
+    from PIL import Image
+    from oracle.ref_import import reference_root
+    g = np.random.default_rng(0)
+    pic = lambda w, h: Image.fromarray(g.integers(0, 255, (h, w, 3), dtype=np.uint8))
+    records = [dict(src_img=pic(300, 200), tgt_img=pic(310, 190).convert("L"), superficial_prompt="make it rain"), dict(src_img=pic(64, 64), tgt_img=None),
+               dict(src_img=pic(1000, 700), tgt_img=pic(1000, 700))]
+    seen = {}
+
+    def load_dataset(name, split=None, cache_dir=None):
+        seen.update(name=name, split=split, cache_dir=cache_dir)
+        return records
+    monkeypatch.setattr(hf, "load_dataset", load_dataset)
+    ours = [D.Pica100kDataset(cache_dir="/data", height=128, width=192, repeat=2), D.Pica100kDataset(max_pixels=400 * 300)]
+    assert seen == dict(name="Andrew613/PICA-100K", split="train", cache_dir="/data") or seen["cache_dir"] is None
+    assert len(ours[0]) == 6 and not ours[0].dynamic_resolution and ours[1].dynamic_resolution
+    s = ours[0][3]
+    assert set(s) == {"image", "edit_image", "prompt"} and s["prompt"] == "make it rain" and s["image"].size == (192, 128) and s["image"].mode == "RGB"
+    assert isinstance(s["edit_image"], list) and s["edit_image"][0].size == (192, 128)
+    with pytest.warns(UserWarning, match="missing src_img/tgt_img"):
+        assert ours[0][1] is None
+    assert ours[1][2]["image"].size == (400, 288)                      # 1000 x 700 -> 414 x 289 -> floored to multiples of 16
+    root = reference_root()
+    if root is None:
+        return
+    path = os.path.join(root, "trainers", "utils.py")
+    cls = [n for n in ast.parse(open(path, encoding="utf-8").read()).body if isinstance(n, ast.ClassDef) and n.name == "Pica100kDataset"]
+    ns = dict(torch=torch, warnings=warnings, torchvision=torchvision, Image=Image, load_dataset=load_dataset, Optional=typing.Optional, Dict=typing.Dict,
+              Any=typing.Any, Tuple=typing.Tuple)
+    exec(compile(ast.Module(body=cls, type_ignores=[]), path, "exec"), ns)
+    refs = [ns["Pica100kDataset"](cache_dir="/data", height=128, width=192, repeat=2), ns["Pica100kDataset"](max_pixels=400 * 300)]
+    for o, r in zip(ours, refs):
+        assert len(o) == len(r)
+        for i in (0, 2):
+            a, b = o[i], r[i]
+            assert a["prompt"] == b["prompt"] and np.array_equal(np.asarray(a["image"]), np.asarray(b["image"]))
+            assert len(a["edit_image"]) == len(b["edit_image"]) == 1 and np.array_equal(np.asarray(a["edit_image"][0]), np.asarray(b["edit_image"][0]))
