@@ -165,7 +165,7 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
     assert inputs["prompt_emb"].shape == (1, T, 3584) and int(inputs["special_token_mask"].sum()) == 64 and inputs["prompt_emb_mask"].shape == (1, T)
     assert "generate" not in pipe.text_encoder.calls                   # training: the transition text comes from the rules, not from a generation
     torch.manual_seed(0)
-    loss = module(data, inputs=None)                                                              # :298-325 -> pipe.training_loss(**models, **inputs)
+    loss = module(data, inputs=inputs)                                                            # :298-325 -> pipe.training_loss(**models, **inputs)
     assert loss.ndim == 0 and torch.isfinite(loss) and loss.item() > 0 and pipe.special_token_loss > 0
     loss.backward()
     grads = {n: p.grad for n, p in module.named_parameters() if p.requires_grad}
