@@ -240,8 +240,10 @@ class QwenImagePhysicPipeline(nn.Module):
         """:250-276.  hotload=False folds `alpha * B @ A` into the weights (GeneralLoRALoader); hotload=True attaches the factors un-merged to the
         wrappers `enable_lora_magic()` installed (none installed -> nothing attaches, like the reference's isinstance filter)."""
         if state_dict is None:
-            path = lora_config if isinstance(lora_config, str) else lora_config.path
-            state_dict = load_state_dict(path, torch_dtype=self.torch_dtype, device=self.device)
+            if not isinstance(lora_config, str):
+                lora_config.download_if_necessary()              # a ModelConfig given by model_id / origin_file_pattern resolves to local files here
+                lora_config = lora_config.path
+            state_dict = load_state_dict(lora_config, torch_dtype=self.torch_dtype, device=self.device)
         if hotload:
             from .lora import hotload_lora
             hotload_lora(module, state_dict, alpha=alpha)
@@ -349,8 +351,27 @@ class QwenImagePhysicPipeline(nn.Module):
         noise = torch.randn(shape, generator=generator, device=rand_device, dtype=rand_torch_dtype)
         return noise.to(dtype=torch_dtype or self.torch_dtype, device=device or self.device)
 
-    def step(self, scheduler, latents, progress_id, noise_pred, **kwargs):
-        return scheduler.step(noise_pred, scheduler.timesteps[progress_id], latents)
+    def blend_with_mask(self, base, addition, mask):
+        """utils/__init__.py:146-147."""
+        return base * (1 - mask) + addition * mask
+
+    def step(self, scheduler, latents, progress_id, noise_pred, input_latents=None, inpaint_mask=None, **kwargs):
+        """BasePipeline.step (utils/__init__.py:150-156): one Euler update in torch arithmetic -- the form `direct_distill_loss` differentiates
+        through and the reference's own loop body calls.  With an inpaint mask the prediction outside the mask is replaced by the one that leads
+        back to `input_latents`.  (The native loop, `denoise`, fuses CFG + update into one kernel and does not take masks: `__call__` refuses them.)"""
+        timestep = scheduler.timesteps[progress_id]
+        if inpaint_mask is not None:
+            noise_pred = self.blend_with_mask(scheduler.return_to_timestep(timestep, latents, input_latents), noise_pred, inpaint_mask)
+        return scheduler.step(noise_pred, timestep, latents)
+
+    def enable_cpu_offload(self):
+        """utils/__init__.py:127-129 (deprecated there in favour of enable_vram_management): accepted, weights stay resident (180 GB HBM)."""
+        import warnings
+        warnings.warn("`enable_cpu_offload` will be deprecated. Please use `enable_vram_management`.")
+
+    def get_vram(self):
+        """utils/__init__.py:132-133: total device memory in GiB."""
+        return torch.cuda.mem_get_info(self.device)[1] / (1024 ** 3)
 
     # ---- the hot loop -------------------------------------------------------------------------------
     @torch.no_grad()

@@ -342,3 +342,36 @@ def test_product_entry_points_fail_loudly_without_a_gpu():
                                        v_intermediate=32, v_out=64, fullatt=(0,))).bfloat16()
     with pytest.raises(nv.NativeUnavailable):
         te.edit_forward(input_ids=torch.zeros(1, 4, dtype=torch.long), attention_mask=torch.ones(1, 4, dtype=torch.long))
+
+
+def test_base_pipeline_step_with_and_without_an_inpaint_mask():
+    """BasePipeline.step / blend_with_mask (utils/__init__.py:146-156), the torch-arithmetic update `direct_distill_loss` and the reference's loop body use."""
+    pipe = _cpu_pipe()
+    pipe.scheduler.set_timesteps(4, dynamic_shift_len=16)
+    g = torch.Generator().manual_seed(0)
+    lat, pred, clean = (torch.randn(1, 16, 4, 4, generator=g) for _ in range(3))
+    sig = pipe.scheduler.sigmas
+    want = lat + pred * (sig[2] - sig[1])
+    assert torch.allclose(pipe.step(pipe.scheduler, latents=lat, progress_id=1, noise_pred=pred, input_latents=clean, height=64), want)
+    mask = (torch.rand(1, 1, 4, 4, generator=g) > 0.5).float()
+    expected = (lat - clean) / sig[1]                                # the prediction that returns to `clean` (flow_match.py:85-91)
+    want = lat + (expected * (1 - mask) + pred * mask) * (sig[2] - sig[1])
+    assert torch.allclose(pipe.step(pipe.scheduler, latents=lat, progress_id=1, noise_pred=pred, input_latents=clean, inpaint_mask=mask), want)
+
+
+def test_load_lora_from_a_model_config_given_by_id_and_pattern(tmp_path):
+    """load_lora(module, ModelConfig(model_id=, origin_file_pattern=, local_model_path=)) resolves the file like the reference (:258-263) and folds it."""
+    from safetensors.torch import save_file
+    from physicedit_b200.pipeline import ModelConfig
+    pipe = _cpu_pipe()
+    w0 = pipe.dit.transformer_blocks[0].attn.to_k.weight.detach().clone()
+    g = torch.Generator().manual_seed(1)
+    sd = {"transformer_blocks.0.attn.to_k.lora_A.default.weight": (torch.randn(8, 3072, generator=g) * 0.05).bfloat16(),
+          "transformer_blocks.0.attn.to_k.lora_B.default.weight": (torch.randn(3072, 8, generator=g) * 0.05).bfloat16()}
+    folder = tmp_path / "models" / "me" / "my-lora"
+    folder.mkdir(parents=True)
+    save_file(sd, str(folder / "physicedit.safetensors"))
+    pipe.load_lora(pipe.dit, ModelConfig(model_id="me/my-lora", origin_file_pattern="*.safetensors", local_model_path=str(tmp_path / "models")), alpha=0.5)
+    want = w0 + 0.5 * torch.mm(sd["transformer_blocks.0.attn.to_k.lora_B.default.weight"], sd["transformer_blocks.0.attn.to_k.lora_A.default.weight"])
+    assert torch.equal(pipe.dit.transformer_blocks[0].attn.to_k.weight, want.to(torch.bfloat16)) or \
+        torch.allclose(pipe.dit.transformer_blocks[0].attn.to_k.weight.float(), want.float(), atol=2e-2)
