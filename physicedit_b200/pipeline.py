@@ -167,7 +167,7 @@ class QwenImagePhysicPipeline(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------------
     @staticmethod
-    def from_pretrained(torch_dtype=torch.bfloat16, device="cuda", model_configs=(), tokenizer_config=None, processor_config=None,
+    def from_pretrained(torch_dtype=torch.bfloat16, device="cuda", model_configs=(), tokenizer_config="default", processor_config=None,
                         dinov2_path=None):
         """:497-541.  Model files are recognised by the md5 of their state-dict keys + shapes like the reference's ModelManager
         (models/model_manager.py:350-376; registry rows configs/model_config.py:21-24): DiT, VAE and the Qwen2.5-VL text encoder.
@@ -204,6 +204,8 @@ class QwenImagePhysicPipeline(nn.Module):
                         print(f"    We cannot detect the model type. No models are loaded ({paths}).")
             except Exception as e:  # noqa: BLE001  (the reference's loader prints and moves on, model_manager.py:375-376)
                 print(f"    Loading {paths} failed: {e}")
+        if isinstance(tokenizer_config, str) and tokenizer_config == "default":       # the reference's default argument (:502); only read with a text encoder
+            tokenizer_config = ModelConfig(model_id="Qwen/Qwen-Image", origin_file_pattern="tokenizer/")
         pipe.attach_tokenizer(tokenizer_config, processor_config)
         return pipe
 
