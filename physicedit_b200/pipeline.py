@@ -494,7 +494,7 @@ class QwenImagePhysicPipeline(nn.Module):
                  inpaint_blur_size=None, inpaint_blur_sigma=None, height=1328, width=1328, seed=None, rand_device="cpu", num_inference_steps=30,
                  exponential_shift_mu=None, blockwise_controlnet_inputs=None, eligen_entity_prompts=None, eligen_entity_masks=None,
                  eligen_enable_on_negative=False, edit_image=None, edit_image_auto_resize=True, edit_rope_interpolation=False, context_image=None,
-                 enable_fp8_attention=False, tiled=False, tile_size=128, tile_stride=64, progress_bar_cmd=None, supported_rules=None,
+                 enable_fp8_attention=False, tiled=False, tile_size=128, tile_stride=64, progress_bar_cmd="tqdm", supported_rules=None,
                  contradicted_rules=None, middle_key_frames=None, stitched_image=None, state=None, transition=None, triplet=None, is_train=True,
                  have_text_reasoning=True,
                  prompt_inputs_posi: dict = None, prompt_inputs_nega: dict = None, edit_latents=None, context_latents=None, output_type="pil"):
@@ -504,6 +504,9 @@ class QwenImagePhysicPipeline(nn.Module):
         model is absent returns nothing, so they survive), `output_type="latent"` skips the decode."""
         if inpaint_mask is not None:
             raise NotImplementedError("inpainting (inpaint_mask) is outside the PhysicEdit hot path: no PhysicEdit script passes it")
+        if isinstance(progress_bar_cmd, str):                # the reference's default is tqdm itself (:586); resolved here so that importing the package does not need it
+            from tqdm import tqdm
+            progress_bar_cmd = tqdm
         inputs_posi = dict(prompt_inputs_posi or {}, prompt=prompt)
         inputs_nega = dict(prompt_inputs_nega or {}, negative_prompt=negative_prompt)
         inputs_shared = {
