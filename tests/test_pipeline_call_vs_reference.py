@@ -176,3 +176,63 @@ def test_training_loss_matches_the_reference_pipeline(tmp_path, monkeypatch):
     print(f"training_loss: {got[0]:.5f} vs reference {want[0]:.5f}; special_token_loss {got[1]:.5f} vs {want[1]:.5f}; adapter grads {e_ad:.3e}; d targets {e_t:.3e}")
     assert set(got[2]) == set(want[2]) and abs(got[0] - want[0]) < 1e-2 * abs(want[0]) and abs(got[1] - want[1]) < 1e-2 * abs(want[1])
     assert e_ad < 3e-2 and e_t < 3e-2
+
+
+def test_direct_distill_loss_matches_the_reference_pipeline(tmp_path, monkeypatch):
+    """`pipe.direct_distill_loss(**inputs)` (:332-340, task "direct_distill" of the train script): the whole 2-step sampler under autograd -- per step one
+    model_fn forward (adapter rows rewritten in place) and `pipe.step` -- regressed on `input_latents`; reference pipeline (stock autograd) vs this package
+    (emulated ABI), same weights and inputs.  Trainable: the DiT itself (full-weight gradients stand in for the un-merged LoRA, which needs peft on the
+    reference side); the adapter stays frozen -- with a trainable adapter the reference's own multi-step loop fails in autograd (the in-place write of
+    :1336 bumps the version of a tensor the previous step's graph saved).  Compared: the loss and the gradients of five DiT weights."""
+    from physicedit_b200 import adapters, autograd, native as nv
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    Wsd = O.synth_weights(O.dit_param_shapes(1), seed=91, dtype=torch.bfloat16)
+    Asd = O.synth_weights(O.adapter_param_shapes(), seed=92, dtype=torch.bfloat16)
+    H, Wd, T = 64, 64, 96
+    inp = O.synth_inputs(H, Wd, T, seed=93, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(94)
+    gt = [(torch.randn(1, 64, 3584, generator=g) * 0.5).bfloat16() for _ in range(2)]
+    target = torch.randn(1, 16, H // 8, Wd // 8, generator=g).bfloat16()
+
+    def run(pipe):
+        pipe.freeze_except(["dit"])
+        inputs = dict(latents=inp["latents"].clone(), input_latents=target, height=H, width=Wd, edit_latents=inp["edit_latents"], prompt_emb=inp["prompt_emb"].clone(),
+                      prompt_emb_mask=inp["prompt_emb_mask"], special_token_mask=inp["special_token_mask"], num_inference_steps=2, use_gradient_checkpointing=False,
+                      pseudo_special_emb_dino=gt[0], pseudo_special_emb_vae=gt[1], is_train=True)
+        loss = pipe.direct_distill_loss(**inputs)
+        loss.backward()
+        names = ("img_in.weight", "transformer_blocks.0.attn.to_q.weight", "transformer_blocks.0.attn.add_k_proj.bias", "transformer_blocks.0.img_mlp.net.2.weight",
+                 "transformer_blocks.0.img_mod.1.weight", "proj_out.weight")
+        params = dict(pipe.dit.named_parameters())
+        return loss.item(), {n: params[n].grad.detach().float().clone() for n in names}
+
+    ref_import.tiny_dinov2_folder(str(tmp_path / "dino"))
+    with ref_import.ReferenceModules() as ref:
+        rp = ref.phys.QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, dinov2_path=str(tmp_path / "dino"))
+        rp.dit = ref_import.build_reference_dit(ref, Wsd, 1, torch.bfloat16, "cpu")
+        rp.visual_thinking_adapter.load_state_dict(Asd)
+        rp.visual_thinking_adapter.to(torch.bfloat16)
+        want = run(rp)
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    monkeypatch.setattr(autograd, "_nat", lambda t: emu)
+    autograd.weight_transposes.clear()
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.clone() for k, v in Wsd.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict(Asd)
+    pipe.to(torch.bfloat16)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    got = run(pipe)
+    cat = lambda d: torch.cat([d[k].flatten() for k in sorted(d)])
+    e = rel(cat(got[1]), cat(want[1]))
+    print(f"direct_distill_loss: {got[0]:.5f} vs reference {want[0]:.5f}; DiT weight grads {e:.3e}")
+    assert abs(got[0] - want[0]) < 1e-2 * abs(want[0]) and e < 5e-2
