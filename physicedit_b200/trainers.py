@@ -5,8 +5,8 @@ In scope here is only what touches the hot path's checkpoint / module contract: 
 trainable, LoRA injection, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into
 LoRA and `pipe.*` keys), `ModelLogger` (who writes that file), the argument parser's flag set and `launch_training_task` (the optimizer loop,
 on plain torch.distributed DDP instead of accelerate; forward and backward on the native kernels) and `PhysicalEditingDataset`,
-the training-data format the script instantiates (`physicedit_b200/datasets.py`).  The other dataset readers (`UnifiedDataset`, the data-process
-task) are imported but never used by the PhysicEdit scripts: their names exist and fail loudly when used.
+the training-data format the script instantiates (`physicedit_b200/datasets.py`), and `launch_data_process_task`.  `UnifiedDataset` (a generic reader the
+script imports but never uses) exists as a name that fails loudly when used.
 Reference: DiffSynth-Studio/diffsynth/trainers/utils.py:777-1115.
 """
 from __future__ import annotations
@@ -242,7 +242,21 @@ def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e
     return wrapped
 
 
-launch_data_process_task = _control_plane("utils.launch_data_process_task")
+def launch_data_process_task(dataset, model, model_logger, num_workers: int = 8, args=None):
+    """trainers/utils.py:980-1002 without accelerate: run the module's pre-processing (`model(data, return_inputs=True)`: every pipeline unit -- VAE /
+    text-encoder / DINOv2 forwards on the native kernels) over the dataset once and cache each sample's inputs as
+    `<output_path>/<rank>/<index>.pth`; ranks take the samples `rank, rank + world, ...` and number their own files from 0, like a dataloader
+    sharded by `accelerator.prepare`."""
+    if args is not None:
+        num_workers = args.dataset_num_workers
+    ranks = _Ranks()
+    sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=ranks.world, rank=ranks.rank, shuffle=False) if ranks.distributed else None
+    loader = torch.utils.data.DataLoader(dataset, shuffle=False, sampler=sampler, collate_fn=lambda x: x[0], num_workers=num_workers)
+    folder = os.path.join(model_logger.output_path, str(ranks.rank))
+    os.makedirs(folder, exist_ok=True)
+    for data_id, data in enumerate(loader):
+        with torch.no_grad():
+            torch.save(model(data, return_inputs=True), os.path.join(folder, f"{data_id}.pth"))
 
 
 from .datasets import PhysicalEditingDataset, Pica100kDataset  # noqa: E402,F401  (trainers/utils.py:369-683, :685-775)

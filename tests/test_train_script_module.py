@@ -177,6 +177,14 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
         hit = [g for n, g in grads.items() if part in n and g is not None]
         assert hit and all(torch.isfinite(g.float()).all() for g in hit) and any(g.float().abs().sum() > 0 for g in hit), part
 
+    # ---- task "data_process" (:312-313 + trainers/utils.py:980-1002): the units' outputs of every sample cached to <output_path>/<rank>/<i>.pth
+    module.task = "data_process"
+    cache_logger = script_module["ModelLogger"](str(tmp_path / "cache"))
+    script_module["launch_data_process_task"](dataset, module, cache_logger, num_workers=0)
+    cached = torch.load(str(tmp_path / "cache" / "0" / "0.pth"), weights_only=False)
+    assert set(inputs) == set(cached) and cached["prompt_emb"].shape == inputs["prompt_emb"].shape and cached["input_latents"].shape == (1, 16, 8, 12)
+    assert not cached["pseudo_special_emb_dino"].requires_grad                                    # cached under no_grad
+    module.task = "sft"
     # ---- the script's logger on this framework's stand-in for accelerate.Accelerator (trainers._Ranks): checkpoint + mid-training evaluation
     from safetensors.torch import load_file
     from physicedit_b200.trainers import _Ranks
