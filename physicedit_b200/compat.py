@@ -89,7 +89,9 @@ def install() -> None:
     mod("diffsynth.trainers").__path__ = []
     mod("diffsynth.trainers.utils", **{k: getattr(trainers, k) for k in ("DiffusionTrainingModule", "ModelLogger", "qwen_image_parser",
                                                                           "launch_training_task", "launch_data_process_task", "PhysicalEditingDataset", "Pica100kDataset")})
-    mod("diffsynth.trainers.unified_dataset", UnifiedDataset=trainers.UnifiedDataset)
+    from . import unified_dataset
+    mod("diffsynth.trainers.unified_dataset", **{n: getattr(unified_dataset, n) for n in dir(unified_dataset)
+                                                 if isinstance(getattr(unified_dataset, n), type) and getattr(unified_dataset, n).__module__ == unified_dataset.__name__})
     mod("diffsynth.pipelines.flux_image_new", ControlNetInput=ControlNetInput)
     mod("diffsynth.pipelines.helpers", **{k: getattr(adapters, k) for k in ("FeedForward", "PerceiverAttention", "PerceiverResampler",
                                                                               "VisualThinkingAdapter", "VisualThinkingDualAdapter")})

@@ -5,8 +5,8 @@ In scope here is only what touches the hot path's checkpoint / module contract: 
 trainable, LoRA injection, the `pipe.dit.`-stripped trainable-only state dict that scripts/inference/validate.py:44-65 later splits into
 LoRA and `pipe.*` keys), `ModelLogger` (who writes that file), the argument parser's flag set and `launch_training_task` (the optimizer loop,
 on plain torch.distributed DDP instead of accelerate; forward and backward on the native kernels) and `PhysicalEditingDataset`,
-the training-data format the script instantiates (`physicedit_b200/datasets.py`), and `launch_data_process_task`.  `UnifiedDataset` (a generic reader the
-script imports but never uses) exists as a name that fails loudly when used.
+the training-data format the script instantiates (`physicedit_b200/datasets.py`), `launch_data_process_task` and -- the reader of what that task caches --
+`UnifiedDataset` (`physicedit_b200/unified_dataset.py`).
 Reference: DiffSynth-Studio/diffsynth/trainers/utils.py:777-1115.
 """
 from __future__ import annotations
@@ -165,15 +165,6 @@ def qwen_image_parser():
     return ap
 
 
-def _control_plane(name):
-    def stub(*args, **kwargs):
-        raise NotImplementedError(f"diffsynth.trainers.{name} is the reference's training control plane (generic dataset readers no PhysicEdit "
-                                  "script uses): outside the hot path this framework replaces (SURVEY.md section 2 / 8f3).  Use "
-                                  "PhysicalEditingDataset, or feed launch_training_task any torch Dataset that yields its sample dictionaries.")
-    stub.__name__ = name
-    return stub
-
-
 class _Ranks:
     """The four things the reference asks of `accelerate.Accelerator` in its loop and its ModelLogger (:891-977), on plain torch.distributed."""
 
@@ -262,6 +253,4 @@ def launch_data_process_task(dataset, model, model_logger, num_workers: int = 8,
 from .datasets import PhysicalEditingDataset, Pica100kDataset  # noqa: E402,F401  (trainers/utils.py:369-683, :685-775)
 
 
-class UnifiedDataset(torch.utils.data.Dataset):
-    def __init__(self, *args, **kwargs):
-        _control_plane("unified_dataset.UnifiedDataset")()
+from .unified_dataset import UnifiedDataset  # noqa: E402,F401  (trainers/unified_dataset.py)

@@ -250,3 +250,99 @@ def test_pica100k_dataset_matches_the_reference(monkeypatch):
             a, b = o[i], r[i]
             assert a["prompt"] == b["prompt"] and np.array_equal(np.asarray(a["image"]), np.asarray(b["image"]))
             assert len(a["edit_image"]) == len(b["edit_image"]) == 1 and np.array_equal(np.asarray(a["edit_image"][0]), np.asarray(b["edit_image"][0]))
+
+
+def test_unified_dataset_and_operators_match_the_reference(tmp_path, clip_tree):
+    """`diffsynth.trainers.unified_dataset` (the whole reference module executed from its source, `imageio` served by the OpenCV reader) against
+    physicedit_b200/unified_dataset.py: metadata in all three formats, the default image / video operators (still image, clip, list of images),
+    operator composition with `>>`, routing errors, and the cache mode that reads what `launch_data_process_task` writes."""
+    import types
+    import pandas
+    from PIL import Image
+    from oracle.ref_import import reference_root
+    from physicedit_b200 import unified_dataset as U
+    g = np.random.default_rng(1)
+    base = tmp_path / "data"
+    (base / "imgs").mkdir(parents=True)
+    for name, (w, h) in (("a.png", (300, 200)), ("b.jpg", (640, 640)), ("c.webp", (100, 180))):
+        Image.fromarray(g.integers(0, 255, (h, w, 3), dtype=np.uint8)).save(base / "imgs" / name)
+    write_clip(base / "clip.mp4", 11, 96, 64, 4)
+    rows = [{"image": "imgs/a.png", "prompt": "one", "score": 1.5}, {"image": ["imgs/b.jpg", "imgs/c.webp"], "prompt": "two", "score": 2}]
+    (base / "meta.json").write_text(json.dumps(rows))
+    (base / "meta.jsonl").write_text("".join(json.dumps(r) + "\n" for r in rows))
+    pandas.DataFrame([{"image": "imgs/a.png", "prompt": "one"}, {"image": "imgs/b.jpg", "prompt": "two"}]).to_csv(base / "meta.csv", index=False)
+    cache = tmp_path / "cache"
+    (cache / "0").mkdir(parents=True)
+    (cache / "1").mkdir()
+    torch.save({"prompt_emb": torch.arange(6.0).view(1, 2, 3), "height": 64}, cache / "0" / "0.pth")
+    torch.save({"prompt_emb": torch.ones(1, 2, 3), "height": 96}, cache / "1" / "0.pth")
+    (cache / "1" / "notes.txt").write_text("ignored")
+
+    def scenarios(M):
+        out = {}
+        for meta_name in ("meta.json", "meta.jsonl", "meta.csv"):
+            ds = M.UnifiedDataset(base_path=str(base), metadata_path=str(base / meta_name), repeat=2, data_file_keys=("image",),
+                                  main_data_operator=M.UnifiedDataset.default_image_operator(base_path=str(base), max_pixels=200 * 200, height_division_factor=16,
+                                                                                             width_division_factor=16))
+            out[meta_name] = (len(ds), ds.load_from_cache, [ds[i] for i in range(len(ds))])
+        fixed = M.UnifiedDataset(base_path=str(base), metadata_path=str(base / "meta.json"), data_file_keys=("image", "score"),
+                                 main_data_operator=M.UnifiedDataset.default_image_operator(base_path=str(base), height=96, width=128),
+                                 special_operator_map={"score": M.ToFloat() >> M.ToStr() >> M.ToList()})
+        out["fixed"] = [fixed[0], fixed[1]]
+        video = M.UnifiedDataset.default_video_operator(base_path=str(base), height=48, width=80, num_frames=9)
+        out["video"] = [video("clip.mp4"), video("imgs/a.png")]
+        short = M.UnifiedDataset.default_video_operator(base_path=str(base), num_frames=81, max_pixels=64 * 48)
+        out["short clip"] = short("clip.mp4")                                  # 11 frames -> 9 (9 % 4 == 1), dynamic resolution
+        cached = M.UnifiedDataset(base_path=str(cache), repeat=3)
+        out["cache"] = (len(cached), cached.load_from_cache, sorted((d["height"], d["prompt_emb"].sum().item()) for d in (cached[0], cached[1])))
+        chain = M.ToAbsolutePath("/x") >> (M.ToStr() >> M.ToList())
+        out["chain"] = (chain("y"), len(chain.operators), M.ToStr(none_value="n/a")(None), M.ToInt()("7"), M.DataProcessingOperatorRaw()(3))
+        for bad in (lambda: M.RouteByExtensionName([(("png",), M.LoadImage())])("x.tiff"), lambda: M.RouteByType([(str, M.ToStr())])(3),
+                    lambda: M.DataProcessingOperator()(1)):
+            with pytest.raises((ValueError, NotImplementedError)):
+                bad()
+        return out
+
+    def equal(a, b, path="out"):
+        if isinstance(a, Image.Image):
+            assert isinstance(b, Image.Image) and a.size == b.size and a.mode == b.mode and a.tobytes() == b.tobytes(), path
+        elif isinstance(a, dict):
+            assert set(a) == set(b), path
+            for k in a:
+                equal(a[k], b[k], f"{path}.{k}")
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                equal(x, y, f"{path}[{i}]")
+        elif isinstance(a, float) and a != a:
+            assert b != b, path
+        else:
+            assert a == b, (path, a, b)
+
+    ours = scenarios(U)
+    assert ours["meta.json"][0] == 4 and not ours["meta.json"][1] and ours["meta.json"][2][0]["image"].size == (240, 160)       # 300 x 200 -> 244 x 163 -> / 16
+    assert [im.size for im in ours["meta.json"][2][1]["image"]] == [(192, 192), (96, 176)]
+    assert ours["fixed"][0]["image"].size == (128, 96) and ours["fixed"][0]["score"] == ["1.5"]
+    assert len(ours["video"][0]) == 9 and ours["video"][0][0].size == (80, 48) and len(ours["video"][1]) == 1 and len(ours["short clip"]) == 9
+    assert ours["cache"] == (6, True, [(64, 15.0), (96, 6.0)]) and ours["chain"][:2] == (["/x/y"], 3)
+    root = reference_root()
+    if root is None:
+        return
+    path = os.path.join(root, "trainers", "unified_dataset.py")
+    imageio = types.ModuleType("imageio")
+    imageio.get_reader = _Cv2Reader
+    iio = types.ModuleType("imageio.v3")
+    saved = {k: sys.modules.get(k) for k in ("imageio", "imageio.v3")}
+    sys.modules["imageio"], sys.modules["imageio.v3"] = imageio, iio
+    try:
+        ns = {"__name__": "ref_unified_dataset"}
+        exec(compile(open(path, encoding="utf-8").read(), path, "exec"), ns)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    import unittest.mock
+    with unittest.mock.patch.object(D, "open_video", lambda p: D._OpenCVFrames(p)), unittest.mock.patch.object(U, "open_video", lambda p: D._OpenCVFrames(p)):
+        equal(scenarios(types.SimpleNamespace(**ns)), scenarios(U))

@@ -54,8 +54,8 @@ from diffsynth.utils import PipelineUnit, PipelineUnitRunner
     exec(src, ns)                                                   # lines 2-6 of train_physicedit.py, :17-18 of validate.py
     args = ns["qwen_image_parser"]().parse_args(["--dataset_base_path", "x", "--dinov2_path", "y", "--lora_rank", "128", "--use_gradient_checkpointing"])
     assert args.remove_prefix_in_ckpt == "pipe.dit." and args.lora_rank == 128 and args.use_gradient_checkpointing and args.resume_type == "auto"
-    with pytest.raises(NotImplementedError, match="control plane"):
-        ns["UnifiedDataset"]()                                      # imported by the train script, never used by it
+    from physicedit_b200.unified_dataset import UnifiedDataset
+    assert ns["UnifiedDataset"] is UnifiedDataset                   # imported by the train script (:6): tests/test_datasets.py
     from physicedit_b200.datasets import PhysicalEditingDataset
     assert ns["PhysicalEditingDataset"] is PhysicalEditingDataset   # the dataset the script builds (:420): tests/test_datasets.py
     pipe = _cpu_pipe()

@@ -185,6 +185,11 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
     assert set(inputs) == set(cached) and cached["prompt_emb"].shape == inputs["prompt_emb"].shape and cached["input_latents"].shape == (1, 16, 8, 12)
     assert not cached["pseudo_special_emb_dino"].requires_grad                                    # cached under no_grad
     module.task = "sft"
+    replay = script_module["UnifiedDataset"](base_path=str(tmp_path / "cache"))                   # no metadata file: the cache reader
+    assert replay.load_from_cache and len(replay) == 1
+    torch.manual_seed(0)
+    cached_loss = module({}, inputs=replay[0])                                                    # what launch_training_task does with a cached dataset
+    assert torch.isfinite(cached_loss) and cached_loss.item() > 0
     # ---- the script's logger on this framework's stand-in for accelerate.Accelerator (trainers._Ranks): checkpoint + mid-training evaluation
     from safetensors.torch import load_file
     from physicedit_b200.trainers import _Ranks
