@@ -40,19 +40,15 @@ def _steps(x):
     return list(x.operators) if isinstance(x, DataProcessingPipeline) else [x]
 
 
-class DataProcessingOperatorRaw(DataProcessingOperator):
-    def __call__(self, data):
-        return data
+def _stateless(name: str, fn, doc: str):
+    """An operator class that applies `fn` to its input (the reference spells each of these out as a class, :34-49, :111-114)."""
+    return type(name, (DataProcessingOperator,), {"__call__": lambda self, data: fn(data), "__doc__": doc, "__module__": __name__, "__qualname__": name})
 
 
-class ToInt(DataProcessingOperator):
-    def __call__(self, data):
-        return int(data)
-
-
-class ToFloat(DataProcessingOperator):
-    def __call__(self, data):
-        return float(data)
+DataProcessingOperatorRaw = _stateless("DataProcessingOperatorRaw", lambda data: data, "identity")
+ToInt = _stateless("ToInt", int, "int(data)")
+ToFloat = _stateless("ToFloat", float, "float(data)")
+ToList = _stateless("ToList", lambda data: [data], "[data]")
 
 
 class ToStr(DataProcessingOperator):
@@ -61,11 +57,6 @@ class ToStr(DataProcessingOperator):
 
     def __call__(self, data):
         return str(self.none_value if data is None else data)
-
-
-class ToList(DataProcessingOperator):
-    def __call__(self, data):
-        return [data]
 
 
 class ToAbsolutePath(DataProcessingOperator):
