@@ -380,7 +380,7 @@ class QwenImagePhysicPipeline(nn.Module):
     def denoise(self, latents, inputs_posi: dict, inputs_nega: Optional[dict], edit_latents=None, context_latents=None, *, height: int,
                 width: int, num_inference_steps: int = 30, cfg_scale: float = 4.0, denoising_strength: float = 1.0,
                 exponential_shift_mu=None, progress_bar_cmd=None, timesteps_device: Optional[torch.Tensor] = None,
-                model_kwargs: Optional[dict] = None):
+                model_kwargs: Optional[dict] = None, inpaint_mask: Optional[torch.Tensor] = None, input_latents: Optional[torch.Tensor] = None):
         """Lines 600 and 646-661 of the reference __call__: set_timesteps, then per step two model_fn forwards
         (posi / nega, each with its own persistently-mutated prompt_emb), CFG combine and the Euler update
         (one fused kernel).  inputs_*: dicts with prompt_emb [1,T,3584], prompt_emb_mask, special_token_mask.
@@ -411,6 +411,14 @@ class QwenImagePhysicPipeline(nn.Module):
             if model_kwargs:
                 kw.update(model_kwargs)
             self.run_cfg_branches(kw, inputs_posi, inputs_nega, vp, vn, ts_dev[progress_id:progress_id + 1], t_host)
+            if inpaint_mask is not None:
+                # inpainting (:612, BasePipeline.step utils/__init__.py:150-156): outside the mask the prediction is replaced by the one that leads
+                # back to `input_latents`.  Rare option, 128 KB of latents: the reference's own torch expressions (same rounding points) on top of
+                # the two native forwards instead of the fused CFG + Euler kernel.
+                noise_pred = vn + cfg_scale * (vp - vn) if use_cfg else vp
+                latents = self.step(self.scheduler, latents=latents, progress_id=progress_id, noise_pred=noise_pred, input_latents=input_latents,
+                                    inpaint_mask=inpaint_mask)
+                continue
             ds = float(self.scheduler.dsigma(t))
             nat.cfg_euler_step(latents, vp, vn if use_cfg else None, float(cfg_scale), ds)
         # a kernel whose bounded pipeline wait timed out leaves its output partly written and the handle's flag set: surface it here,
@@ -502,8 +510,6 @@ class QwenImagePhysicPipeline(nn.Module):
         `self.units` by `self.unit_runner`; then the CFG denoise loop (native: `denoise`) and the VAE decode.  Extras beyond the
         reference: `prompt_inputs_posi/nega`, `edit_latents`, `context_latents` hand over pre-computed unit outputs (a unit whose
         model is absent returns nothing, so they survive), `output_type="latent"` skips the decode."""
-        if inpaint_mask is not None:
-            raise NotImplementedError("inpainting (inpaint_mask) is outside the PhysicEdit hot path: no PhysicEdit script passes it")
         if isinstance(progress_bar_cmd, str):                # the reference's default is tqdm itself (:586); resolved here so that importing the package does not need it
             from tqdm import tqdm
             progress_bar_cmd = tqdm
@@ -567,7 +573,7 @@ class QwenImagePhysicPipeline(nn.Module):
         latents = self.denoise(inputs_shared["latents"], posi, nega, inputs_shared.get("edit_latents"), inputs_shared.get("context_latents"),
                                height=height, width=width, num_inference_steps=num_inference_steps, cfg_scale=cfg_scale,
                                denoising_strength=denoising_strength, exponential_shift_mu=exponential_shift_mu, progress_bar_cmd=progress_bar_cmd,
-                               model_kwargs=model_kwargs)
+                               model_kwargs=model_kwargs, inpaint_mask=inputs_shared.get("inpaint_mask"), input_latents=inputs_shared.get("input_latents"))
         if output_type == "latent" or self.vae is None:
             return latents
         image = self.vae.decode(latents, device=self.device, tiled=tiled, tile_size=tile_size, tile_stride=tile_stride)

@@ -64,6 +64,11 @@ def test_call_matches_the_reference_pipeline(tmp_path, monkeypatch):
     call = dict(prompt="tip the glass over", edit_image=image, seed=3, num_inference_steps=3, height=64, width=96, is_train=False,
                 edit_image_auto_resize=False)            # the edit image keeps its 320 x 256 (320 tokens instead of 4096): a CPU-sized request
 
+    # img2img + inpainting (:612-613, BasePipeline.step): start from a noised `input_image`, keep it outside the mask
+    hole = Image.new("L", (96, 64), 0)
+    hole.paste(255, (24, 16, 72, 48))
+    inpaint_call = dict(call, input_image=picture(96, 64, 6), denoising_strength=0.8, inpaint_mask=hole.convert("RGB"), inpaint_blur_size=1, inpaint_blur_sigma=0.8, seed=4)
+
     def processor():
         return Qwen2VLProcessor(image_processor=base.image_processor, tokenizer=Qwen2Tokenizer.from_pretrained(TOK), video_processor=base.video_processor,
                                 chat_template=base.chat_template)
@@ -85,6 +90,9 @@ def test_call_matches_the_reference_pipeline(tmp_path, monkeypatch):
                 pipe.generate_noise = lambda shape, **kw: draw(shape, **dict(kw, rand_torch_dtype=torch.bfloat16)).float()
             img = pipe(**call)
             out[dtype] = (pipe.vae.decoded[-1], img)
+            if dtype == torch.bfloat16:
+                pipe(**inpaint_call)
+                out["inpaint"] = pipe.vae.decoded[-1]
     # this package: same weights, native loop on the emulated ABI
     emu = EmulatedNative()
     monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
@@ -114,6 +122,10 @@ def test_call_matches_the_reference_pipeline(tmp_path, monkeypatch):
     assert isinstance(img, Image.Image) and img.size == out[torch.float32][1].size == (96, 64)
     names = [c[0] for c in emu.calls]
     assert names.count("pe_cfg_euler_step") == 3 and names.count("pe_special_blend_scatter") == 6
+    pipe(**inpaint_call)
+    e_inpaint = rel(pipe.vae.decoded[-1], out["inpaint"])
+    print(f"pipe(..., input_image, inpaint_mask) latents: this package vs reference bf16 {e_inpaint:.3e}")
+    assert e_inpaint < 1e-2
 
 
 def test_training_loss_matches_the_reference_pipeline(tmp_path, monkeypatch):
