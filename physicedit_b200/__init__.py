@@ -7,6 +7,7 @@ Public entry points:
     QwenImageVAE, load_vae   the VAE either side of the loop (encode / decode of single images), same parameter layout
     QwenImageTextEncoder     the Qwen2.5-VL encoder / greedy generator in front of the loop
     inject_lora, launch_training_task, DiffusionTrainingModule   un-merged LoRA and the training loop (forward + backward on the native kernels)
+    PhysicalEditingDataset, Pica100kDataset, UnifiedDataset, launch_data_process_task   the training-data formats either side of that loop
     QwenImageBlockWiseControlNet / QwenImageBlockwiseMultiControlNet   the optional blockwise controlnet
     FlowMatchScheduler, GeneralLoRALoader, ModelConfig, load_state_dict
 Everything numeric runs in physicedit_b200/lib/libpe_b200.so (include/pe_b200.h); there is no CPU fallback.
@@ -37,6 +38,10 @@ _LAZY = {
     "merge_lora": ("lora", "merge_lora"),
     "DiffusionTrainingModule": ("trainers", "DiffusionTrainingModule"),
     "launch_training_task": ("trainers", "launch_training_task"),
+    "launch_data_process_task": ("trainers", "launch_data_process_task"),
+    "PhysicalEditingDataset": ("datasets", "PhysicalEditingDataset"),
+    "Pica100kDataset": ("datasets", "Pica100kDataset"),
+    "UnifiedDataset": ("unified_dataset", "UnifiedDataset"),
 }
 
 
