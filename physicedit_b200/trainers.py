@@ -215,7 +215,9 @@ def launch_training_task(dataset, model, model_logger, learning_rate: float = 1e
         if sampler is not None:
             sampler.set_epoch(epoch_id)
         for data in loader:
-            if data is None:                                  # a clip that could not be decoded (the dataset has warned): skip it instead of crashing in the units
+            if data is None:                                  # a clip that could not be decoded (the dataset has warned)
+                if ranks.distributed:                         # skipping on one rank only would leave the others waiting in the gradient all-reduce
+                    raise RuntimeError("the dataset returned no sample (undecodable clip); remove it from the dataset before a multi-rank run")
                 continue
             if micro % gradient_accumulation_steps == 0:
                 optimizer.zero_grad()                         # at the start of an accumulation window, like the reference's loop (:966)
