@@ -360,7 +360,7 @@ class QwenImagePhysicPipeline(nn.Module):
     def step(self, scheduler, latents, progress_id, noise_pred, input_latents=None, inpaint_mask=None, **kwargs):
         """BasePipeline.step (utils/__init__.py:150-156): one Euler update in torch arithmetic -- the form `direct_distill_loss` differentiates
         through and the reference's own loop body calls.  With an inpaint mask the prediction outside the mask is replaced by the one that leads
-        back to `input_latents`.  (The native loop, `denoise`, fuses CFG + update into one kernel and does not take masks: `__call__` refuses them.)"""
+        back to `input_latents`; `denoise` comes through here for inpainting requests (its mask-free steps use the fused CFG + Euler kernel instead)."""
         timestep = scheduler.timesteps[progress_id]
         if inpaint_mask is not None:
             noise_pred = self.blend_with_mask(scheduler.return_to_timestep(timestep, latents, input_latents), noise_pred, inpaint_mask)
