@@ -398,7 +398,9 @@ class QwenImagePhysicPipeline(nn.Module):
         vbuf = torch.empty((2,) + tuple(latents.shape), dtype=latents.dtype, device=latents.device)     # [posi | nega], one buffer: the
         vp, vn = vbuf[0], vbuf[1]                                                                         # CFG-parallel all-gather runs in place
         # timestep-only quantities for the whole schedule, batch-8 GEMVs (see DiTEngine.precompute_conditioning)
-        self.dit.engine().precompute_conditioning(ts_dev, [float(t.to(self.torch_dtype)) for t in ts])
+        unmerged = getattr(self.dit, "_lora_injected", False)     # evaluation in the middle of training: model_fn takes the un-merged path, which
+        if not unmerged:                                          # computes its own (LoRA-carrying) modulation -- the engine's table would go unused
+            self.dit.engine().precompute_conditioning(ts_dev, [float(t.to(self.torch_dtype)) for t in ts])
         it = enumerate(ts)
         if progress_bar_cmd is not None:
             it = progress_bar_cmd(list(it))
@@ -466,7 +468,8 @@ class QwenImagePhysicPipeline(nn.Module):
             if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
                 self._side_stream = torch.cuda.Stream(dev)
             side = self._side_stream
-            self.dit.engine().conditioning(t_dev, t_host)       # timestep-only tensors: computed (or found cached) before the fork
+            if not getattr(self.dit, "_lora_injected", False):
+                self.dit.engine().conditioning(t_dev, t_host)   # timestep-only tensors: computed (or found cached) before the fork
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self.model_fn(**kw, **inputs_nega, out=vn, cfg_branch=1)
