@@ -375,3 +375,21 @@ def test_load_lora_from_a_model_config_given_by_id_and_pattern(tmp_path):
     want = w0 + 0.5 * torch.mm(sd["transformer_blocks.0.attn.to_k.lora_B.default.weight"], sd["transformer_blocks.0.attn.to_k.lora_A.default.weight"])
     assert torch.equal(pipe.dit.transformer_blocks[0].attn.to_k.weight, want.to(torch.bfloat16)) or \
         torch.allclose(pipe.dit.transformer_blocks[0].attn.to_k.weight.float(), want.float(), atol=2e-2)
+
+
+def test_launcher_runs_a_script_against_the_alias_package(tmp_path):
+    """`python -m physicedit_b200 <script> <args>`: the script's `diffsynth` imports resolve to this package, it runs as __main__ with its own argv."""
+    import subprocess
+    script = tmp_path / "probe.py"
+    script.write_text("import sys\n"
+                      "from diffsynth.pipelines.qwen_image_physical import QwenImagePhysicPipeline, ModelConfig\n"
+                      "from diffsynth.trainers.utils import PhysicalEditingDataset, launch_training_task\n"
+                      "from diffsynth.trainers.unified_dataset import UnifiedDataset, LoadImage\n"
+                      "if __name__ == '__main__':\n"
+                      "    print('ARGV', sys.argv[1:], QwenImagePhysicPipeline.__module__, PhysicalEditingDataset.__module__, UnifiedDataset.__module__)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "physicedit_b200", str(script), "--prompt", "x y"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ARGV ['--prompt', 'x y'] physicedit_b200.pipeline physicedit_b200.datasets physicedit_b200.unified_dataset" in r.stdout
+    r = subprocess.run([sys.executable, "-m", "physicedit_b200"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 2 and "Launcher" in r.stdout
