@@ -301,8 +301,36 @@ def block_forward(blk, image: torch.Tensor, text: torch.Tensor, temb: torch.Tens
     return text, image
 
 
+def controlnet_conditionings(multi, controlnet_inputs, conditionings):
+    """QwenImageBlockwiseMultiControlNet.preprocess (qwen_image_physical.py:164-170) under autograd: control latents -> 2 x 2 patch tokens -> `img_in`
+    of their controlnet (input width padded to a multiple of 8 for the inpaint variant's 64 + 4 channels)."""
+    out = []
+    for ci, cond in zip(controlnet_inputs, conditionings):
+        B, C, Hh, Ww = cond.shape
+        tok = cond.view(B, C, Hh // 2, 2, Ww // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape((Hh // 2) * (Ww // 2), C * 4).to(BF16)
+        lin = multi.models[ci.controlnet_id].img_in
+        w, pad = lin.weight, (-tok.shape[1]) % 8
+        if pad:
+            tok, w = F.pad(tok, (0, pad)), F.pad(w, (0, pad))
+        out.append(linear(tok.contiguous(), w, lin.bias))
+    return out
+
+
+def controlnet_residual(multi, image: torch.Tensor, conds, controlnet_inputs, progress_id, num_inference_steps, block_id):
+    """QwenImageBlockwiseMultiControlNet.blockwise_forward (:172-180) + BlockWiseControlBlock.forward (qwen_image_controlnet.py:15-20) on [n0, 3072]
+    tokens: sum over the controlnets active at this progress of scale * output_proj(GELU(input_proj(rms(x) + rms(y))))."""
+    res = 0
+    for ci, cond in zip(controlnet_inputs, conds):
+        if not multi.active(ci, progress_id, num_inference_steps):
+            continue
+        blk = multi.models[ci.controlnet_id].controlnet_blocks[block_id]
+        h = _rmsnorm(image, blk.x_rms.weight, blk.x_rms.eps) + _rmsnorm(cond, blk.y_rms.weight, blk.y_rms.eps)
+        res = res + module_linear(blk.output_proj, F.gelu(module_linear(blk.input_proj, h))) * ci.scale
+    return res
+
+
 def dit_forward(dit, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.Tensor, prompt_emb: torch.Tensor,
-                use_gradient_checkpointing: bool = True, rope_sampling: bool = False) -> torch.Tensor:
+                use_gradient_checkpointing: bool = True, rope_sampling: bool = False, after_block=None) -> torch.Tensor:
     """model_fn_qwen_image :1340-1403 under autograd.  latents_list = [noise latents, (context), edit...] each [1, 16, h8, w8] bf16 (no gradient
     flows into them: the path trains LoRA and adapters only); timestep_bf16 [1] = the loop's bf16(t); prompt_emb [1, T, 3584] (may carry the
     adapter's graph).  Returns the velocity [1, 16, h8, w8]."""
@@ -322,11 +350,16 @@ def dit_forward(dit, latents_list: Sequence[torch.Tensor], timestep_bf16: torch.
     image = module_linear(dit.img_in, tok)
     text = module_linear(dit.txt_in, _rmsnorm(prompt_emb[0], dit.txt_norm.weight, dit.txt_norm.eps))
     rope_txt, rope_img = rope[:T], rope[T:]
-    for blk in dit.transformer_blocks:
+    for block_id, blk in enumerate(dit.transformer_blocks):
         if use_gradient_checkpointing and torch.is_grad_enabled():
             text, image = checkpoint(block_forward, blk, image, text, temb, rope_img, rope_txt, use_reentrant=False)
         else:
             text, image = block_forward(blk, image, text, temb, rope_img, rope_txt)
+        if after_block is not None:                                       # blockwise controlnet (:1389-1396): the noise tokens get block_id's correction
+            n_noise = shapes[0][1] * shapes[0][2]
+            res = after_block(block_id, image[:n_noise])
+            if torch.is_tensor(res):
+                image = torch.cat([image[:n_noise] + res, image[n_noise:]], dim=0)
     _, h0, w0 = shapes[0]
     n0 = h0 * w0
     emb = module_linear(dit.norm_out.linear, F.silu(temb))                # AdaLayerNorm(single) (models/utils.py:296-309): (scale, shift)

@@ -86,14 +86,20 @@ def model_fn_qwen_image(
         raise ValueError("prompt_emb must be contiguous: it is updated in place")
     from . import autograd as ag
     if getattr(dit, "_lora_injected", False) or (torch.is_grad_enabled() and is_train and
-                                                  (prompt_emb.requires_grad or ag.needs_grad(dit, visual_thinking_adapter))):
+                                                  (prompt_emb.requires_grad or ag.needs_grad(dit, visual_thinking_adapter,
+                                                                                             blockwise_controlnet if blockwise_controlnet_conditioning is not None else None))):
         # training: un-merged LoRA, or a training call (is_train, grad mode on) with trainable parameters on the path -> the
         # differentiable path on the same GEMM / attention kernels.  Inference calls (is_train=False, or under no_grad) stay on the engine.
-        if blockwise_controlnet_conditioning is not None or entity_prompt_emb is not None or enable_fp8_attention:
-            raise NotImplementedError("blockwise controlnet / EliGen / fp8 attention under autograd are not part of the PhysicEdit training path")
+        if entity_prompt_emb is not None or enable_fp8_attention:
+            raise NotImplementedError("EliGen / fp8 attention under autograd are not part of the PhysicEdit training path")
+        after_block = None
+        if blockwise_controlnet_conditioning is not None:               # a trainable (or merely present) blockwise controlnet on the training path
+            conds = ag.controlnet_conditionings(blockwise_controlnet, blockwise_controlnet_inputs, blockwise_controlnet_conditioning)
+            after_block = lambda block_id, noise_tokens: ag.controlnet_residual(blockwise_controlnet, noise_tokens, conds, blockwise_controlnet_inputs,
+                                                                                progress_id, num_inference_steps, block_id)
         pred, special_token_loss = _model_fn_autograd(dit, visual_thinking_adapter, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents,
                                                       context_latents, use_gradient_checkpointing, is_train, pseudo_special_emb_dino, pseudo_special_emb_vae,
-                                                      bool(edit_rope_interpolation))
+                                                      bool(edit_rope_interpolation), after_block)
         if out is not None:
             # the pipeline's denoise loop reads the prediction from the buffer it passed (run_cfg_branches): an evaluation in the middle of a
             # training run (un-merged LoRA still injected, scripts/train/train_physicedit.py:39-169) comes through here
@@ -173,7 +179,7 @@ def entity_attention_mask(entity_masks: torch.Tensor, text_segments, lat_list) -
 
 
 def _model_fn_autograd(dit, ad, latents, timestep, t_bf16, prompt_emb, special_token_mask, edit_latents, context_latents, use_gradient_checkpointing,
-                       is_train, pseudo_special_emb_dino, pseudo_special_emb_vae, rope_sampling=False):
+                       is_train, pseudo_special_emb_dino, pseudo_special_emb_vae, rope_sampling=False, after_block=None):
     """:1331-1403 under autograd (physicedit_b200/autograd.py): same in-place write of the adapter output into `prompt_emb` (:1336), same
     `(latents, special_token_loss)` return; gradients reach the LoRA factors, the adapter heads and whatever produced the pseudo targets."""
     from . import autograd as ag
@@ -190,5 +196,5 @@ def _model_fn_autograd(dit, ad, latents, timestep, t_bf16, prompt_emb, special_t
     if edit_latents is not None:
         lat_list += list(edit_latents) if isinstance(edit_latents, list) else [edit_latents]
     out = ag.dit_forward(dit, [l.contiguous() for l in lat_list], t_bf16, prompt_emb, use_gradient_checkpointing=use_gradient_checkpointing,
-                         rope_sampling=rope_sampling)
+                         rope_sampling=rope_sampling, after_block=after_block)
     return out, special_token_loss

@@ -248,3 +248,74 @@ def test_direct_distill_loss_matches_the_reference_pipeline(tmp_path, monkeypatc
     e = rel(cat(got[1]), cat(want[1]))
     print(f"direct_distill_loss: {got[0]:.5f} vs reference {want[0]:.5f}; DiT weight grads {e:.3e}")
     assert abs(got[0] - want[0]) < 1e-2 * abs(want[0]) and e < 5e-2
+
+
+def test_training_loss_with_a_trainable_blockwise_controlnet_matches_the_reference(tmp_path, monkeypatch):
+    """SURVEY 8f5 under autograd: `training_loss` with `blockwise_controlnet_conditioning` / `_inputs` (what QwenImageUnit_BlockwiseControlNet produces) and the
+    controlnet as the trainable model -- reference pipeline (its QwenImageBlockwiseMultiControlNet, stock autograd) vs this package (autograd Functions on the
+    emulated ABI): loss and every controlnet gradient.  Two requests, one of them outside its [end, start] window at this progress."""
+    from physicedit_b200 import adapters, autograd, native as nv
+    from physicedit_b200.compat import ControlNetInput
+    from physicedit_b200.controlnet import QwenImageBlockWiseControlNet, QwenImageBlockwiseMultiControlNet
+    from physicedit_b200.dit import DiTEngine, QwenImageDiT
+    from physicedit_b200.pipeline import QwenImagePhysicPipeline
+    Wsd = O.synth_weights(O.dit_param_shapes(1), seed=101, dtype=torch.bfloat16)
+    Asd = O.synth_weights(O.adapter_param_shapes(), seed=102, dtype=torch.bfloat16)
+    H, Wd, T = 64, 64, 80
+    inp = O.synth_inputs(H, Wd, T, seed=103, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(104)
+    cn = QwenImageBlockWiseControlNet(num_layers=1)
+    csd = {k: (torch.randn(v.shape, generator=g) * (0.02 if v.dim() > 1 else 0.5) + (1.0 if "rms" in k else 0.0)).bfloat16() for k, v in cn.state_dict().items()}
+    conds = [torch.randn(1, 16, H // 8, Wd // 8, generator=g).bfloat16() for _ in range(2)]
+    cinputs = [ControlNetInput(controlnet_id=0, scale=0.7), ControlNetInput(controlnet_id=0, scale=1.3, start=0.4, end=0.0)]       # progress 1.0 at step 0: inactive
+    gt = [(torch.randn(1, 64, 3584, generator=g) * 0.5).bfloat16() for _ in range(2)]
+    target = torch.randn(1, 16, H // 8, Wd // 8, generator=g).bfloat16()
+
+    def run(pipe, multi):
+        pipe.blockwise_controlnet = multi
+        pipe.scheduler.set_timesteps(1000, training=True)
+        pipe.freeze_except(["blockwise_controlnet"])
+        inputs = dict(input_latents=target, height=H, width=Wd, edit_latents=inp["edit_latents"], prompt_emb=inp["prompt_emb"].clone(), prompt_emb_mask=inp["prompt_emb_mask"],
+                      special_token_mask=inp["special_token_mask"], use_gradient_checkpointing=True, use_gradient_checkpointing_offload=False, cfg_scale=1, is_train=True,
+                      pseudo_special_emb_dino=gt[0], pseudo_special_emb_vae=gt[1], blockwise_controlnet_conditioning=[c.clone() for c in conds],
+                      blockwise_controlnet_inputs=cinputs, progress_id=0, num_inference_steps=5)
+        models = {name: getattr(pipe, name) for name in pipe.in_iteration_models}
+        torch.manual_seed(77)
+        loss = pipe.training_loss(global_step=3, **models, **inputs)
+        loss.backward()
+        return loss.item(), {n: p.grad.detach().float().clone() for n, p in multi.named_parameters() if p.grad is not None}
+
+    ref_import.tiny_dinov2_folder(str(tmp_path / "dino"))
+    with ref_import.ReferenceModules() as ref:
+        import importlib
+        rcn = importlib.import_module("diffsynth.models.qwen_image_controlnet").QwenImageBlockWiseControlNet(num_layers=1)
+        rcn.load_state_dict(csd)
+        rp = ref.phys.QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, dinov2_path=str(tmp_path / "dino"))
+        rp.dit = ref_import.build_reference_dit(ref, Wsd, 1, torch.bfloat16, "cpu")
+        rp.visual_thinking_adapter.load_state_dict(Asd)
+        rp.visual_thinking_adapter.to(torch.bfloat16)
+        want = run(rp, ref.phys.QwenImageBlockwiseMultiControlNet([rcn.to(torch.bfloat16)]))
+    emu = EmulatedNative()
+    monkeypatch.setattr(nv.Native, "get", classmethod(lambda cls, idx=0: emu))
+    monkeypatch.setattr(adapters, "_nat", lambda t: emu)
+    monkeypatch.setattr(autograd, "_nat", lambda t: emu)
+    autograd.weight_transposes.clear()
+    with torch.device("meta"):
+        dit = QwenImageDiT(num_layers=1)
+    dit.load_state_dict({k: v.clone() for k, v in Wsd.items()}, assign=True)
+    dit.pos_embed = type(dit.pos_embed)(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    pipe = QwenImagePhysicPipeline(device="cpu", torch_dtype=torch.bfloat16, build_training_path=False)
+    pipe.dit = dit
+    pipe.visual_thinking_adapter.load_state_dict(Asd)
+    cn.load_state_dict(csd)
+    pipe.to(torch.bfloat16)
+    eng = object.__new__(DiTEngine)
+    eng.dit, eng.device, eng.nat, eng.use_cta_pair, eng.attn_flags, eng._ws, eng._rope, eng.sp = dit, torch.device("cpu"), emu, True, 0, {}, {}, None
+    eng._pack()
+    object.__setattr__(dit, "_engine", eng)
+    got = run(pipe, QwenImageBlockwiseMultiControlNet([cn.to(torch.bfloat16)]))
+    assert set(got[1]) == set(want[1]) and len(got[1]) == 8              # img_in (2) + x_rms, y_rms, input_proj (2), output_proj (2) of block 0
+    cat = lambda d: torch.cat([d[k].flatten() for k in sorted(d)])
+    e = rel(cat(got[1]), cat(want[1]))
+    print(f"training_loss with a blockwise controlnet: {got[0]:.5f} vs reference {want[0]:.5f}; controlnet grads {e:.3e}")
+    assert abs(got[0] - want[0]) < 1e-2 * abs(want[0]) and e < 3e-2
