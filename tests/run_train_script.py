@@ -21,7 +21,7 @@ import torch  # noqa: E402
 from abi_emulator import EmulatedNative  # noqa: E402
 from physicedit_b200 import compat, trainers  # noqa: E402
 from physicedit_b200.pipeline import QwenImagePhysicPipeline  # noqa: E402
-from test_train_script_module import _pipe_on_the_emulator  # noqa: E402
+from test_train_script_module import _pipe_on_the_emulator, small_edit_images  # noqa: E402
 
 
 class Accelerator(trainers._Ranks):
@@ -55,6 +55,7 @@ def main():
             sys.modules["wandb"] = types.SimpleNamespace(log=lambda *a, **k: None, init=lambda *a, **k: None, finish=lambda: None, Image=lambda p: p)
     emu = EmulatedNative()
     pipe = _pipe_on_the_emulator(_Patch(), emu)
+    small_edit_images(_Patch())
     QwenImagePhysicPipeline.from_pretrained = staticmethod(lambda **kw: pipe)
     # after transformers has been imported (it probes `accelerate` once, at import): the stand-in serves the script only
     acc, acc_utils = types.ModuleType("accelerate"), types.ModuleType("accelerate.utils")

@@ -24,7 +24,7 @@ def test_inference_pica_main_runs_on_this_framework(monkeypatch, tmp_path, capsy
     from PIL import Image
     from safetensors.torch import save_file
     from physicedit_b200 import compat
-    from test_train_script_module import _pipe_on_the_emulator
+    from test_train_script_module import _pipe_on_the_emulator, small_edit_images
     saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
     compat.install()
     try:
@@ -45,6 +45,7 @@ def test_inference_pica_main_runs_on_this_framework(monkeypatch, tmp_path, capsy
 
         emu = EmulatedNative()
         pipe = _pipe_on_the_emulator(monkeypatch, emu)
+        small_edit_images(monkeypatch)
         pipe.cfg_streams = 1
         w_q = pipe.dit.transformer_blocks[0].attn.to_q.weight.detach().clone()
         # a checkpoint as train_physicedit.py writes it: LoRA keys with `pipe.dit.` stripped + `pipe.*` keys of the trained modules
@@ -95,7 +96,7 @@ def test_validate_py_main_256x256_four_steps(monkeypatch, tmp_path, capsys):
     The script's `resize_image` (which would blow the input up to ~1024^2) is pinned to the 256 x 256 the config names."""
     from PIL import Image
     from physicedit_b200 import compat
-    from test_train_script_module import _pipe_on_the_emulator
+    from test_train_script_module import _pipe_on_the_emulator, small_edit_images
     script_path = os.path.join(REF, "scripts", "inference", "validate.py")
     saved = {k: v for k, v in sys.modules.items() if k == "diffsynth" or k.startswith("diffsynth.")}
     compat.install()
@@ -106,6 +107,7 @@ def test_validate_py_main_256x256_four_steps(monkeypatch, tmp_path, capsys):
         spec.loader.exec_module(script)
         emu = EmulatedNative()
         pipe = _pipe_on_the_emulator(monkeypatch, emu)
+        small_edit_images(monkeypatch)
         pipe.cfg_streams = 1
         monkeypatch.setattr(script.QwenImagePhysicPipeline, "from_pretrained", staticmethod(lambda **kw: pipe))
         monkeypatch.setattr(script, "resize_image", lambda image, target_area=None: image.resize((256, 256)))

@@ -78,6 +78,13 @@ def script_module(monkeypatch):
     sys.modules.update(saved)
 
 
+def small_edit_images(monkeypatch, area=256 * 256):
+    """CPU sizing of the script-level tests: the edit image is auto-resized to ~256^2 instead of ~1024^2 (256 instead of 4096 tokens per forward on the
+    emulated ABI).  The 1024^2 rule itself is pinned against the reference's unit in tests/test_units_vs_reference.py."""
+    from physicedit_b200 import units as U
+    monkeypatch.setattr(U.QwenImageUnit_EditImageEmbedder, "edit_image_auto_resize", lambda self, image: U.resize_to_area(image, area))
+
+
 def _pipe_on_the_emulator(monkeypatch, emu):
     """A CPU pipeline with a 1-block DiT bound to the emulated ABI, a 1-layer DINOv2, stub VL / VAE and the real tokenizer / processor files."""
     from oracle import dit_oracle as O
@@ -129,6 +136,7 @@ def test_the_train_scripts_module_runs_a_sample_end_to_end(script_module, monkey
     dataset = script_module["PhysicalEditingDataset"](args=args)                                  # train_physicedit.py:420
     emu = EmulatedNative()
     pipe = _pipe_on_the_emulator(monkeypatch, emu)
+    small_edit_images(monkeypatch)
     Pipeline = script_module["QwenImagePhysicPipeline"]
     seen = {}
 
