@@ -87,16 +87,19 @@ class _OpenCVFrames:
 
 
 def open_video(path: str):
-    """A frame source with count() / frame(i) -> uint8 RGB array / close()."""
-    try:
-        import imageio  # noqa: F401
-    except ImportError:
+    """A frame source with count() / frame(i) -> uint8 RGB array / close(): imageio (the reference's decoder) when it is installed and can open the
+    file, else OpenCV; with neither installed an ImportError, with both failing the first decoder's error."""
+    errors = []
+    for backend in (_ImageioFrames, _OpenCVFrames):
         try:
-            import cv2  # noqa: F401
+            return backend(path)
         except ImportError as e:
-            raise ImportError("decoding training clips needs imageio (the reference's decoder) or OpenCV; neither is installed") from e
-        return _OpenCVFrames(path)
-    return _ImageioFrames(path)
+            errors.append(e)
+        except Exception as e:  # noqa: BLE001  (e.g. imageio without its ffmpeg plugin: let the other decoder try)
+            errors.append(e)
+    if all(isinstance(e, ImportError) for e in errors):
+        raise ImportError("decoding training clips needs imageio (the reference's decoder) or OpenCV; neither is installed") from errors[0]
+    raise next(e for e in errors if not isinstance(e, ImportError))
 
 
 # ---- metadata ---------------------------------------------------------------------------------------------------------------------

@@ -346,3 +346,17 @@ def test_unified_dataset_and_operators_match_the_reference(tmp_path, clip_tree):
     import unittest.mock
     with unittest.mock.patch.object(D, "open_video", lambda p: D._OpenCVFrames(p)), unittest.mock.patch.object(U, "open_video", lambda p: D._OpenCVFrames(p)):
         equal(scenarios(types.SimpleNamespace(**ns)), scenarios(U))
+
+
+def test_open_video_falls_back_and_reports(tmp_path, monkeypatch):
+    clip = tmp_path / "c.mp4"
+    write_clip(clip, 5, 64, 48, 1)
+    src = D.open_video(str(clip))                      # imageio is absent here (or cannot open it): OpenCV takes over
+    assert src.count() == 5 and src.frame(0).shape == (48, 64, 3)
+    src.close()
+    with pytest.raises(OSError, match="cannot open"):
+        D.open_video(str(tmp_path / "missing.mp4"))
+    ds = D.PhysicalEditingDataset.__new__(D.PhysicalEditingDataset)
+    ds.num_frames, ds.time_division_factor, ds.time_division_remainder = 81, 4, 1
+    with pytest.warns(UserWarning, match="cannot open video"):
+        assert ds._load_video(str(tmp_path / "missing.mp4")) == []
