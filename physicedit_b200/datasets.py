@@ -285,7 +285,10 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
                 n -= 1
         return max(1, n)
 
-    def _load_video(self, file_path: str) -> List[Image.Image]:
+    def _load_video(self, file_path: str, only_used: bool = False) -> List[Optional[Image.Image]]:
+        """The clip's first `_get_num_frames` frames, RGB, cover-resized and centre-cropped (:595-618).  `only_used=True` (what `__getitem__` asks for)
+        resizes only the frames a sample is made of -- first, last, the middle key frames: 8 of 49 -- and leaves None in the other slots; every frame
+        is processed on its own, so those eight are the same images either way."""
         try:
             source = open_video(file_path)
         except ImportError:
@@ -293,13 +296,20 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
         except Exception as e:  # noqa: BLE001
             warnings.warn(f"cannot open video {file_path}: {e}")
             return []
-        frames: List[Image.Image] = []
+        raw = []
         try:
             for i in range(self._get_num_frames(source)):
                 try:
-                    data = source.frame(i)
+                    raw.append(source.frame(i))
                 except Exception:  # noqa: BLE001  (a clip shorter than its header says: keep what was read)
                     break
+            n = len(raw)
+            used = set(range(n)) if not only_used else {0, n - 1} | set(middle_key_frames(list(range(n)), self.key_frame_stride))
+            frames: List[Optional[Image.Image]] = []
+            for i, data in enumerate(raw):
+                if i not in used:
+                    frames.append(None)
+                    continue
                 img = Image.fromarray(data).convert("RGB")
                 frames.append(cover_and_center_crop(img, *self._get_height_width(img)))
         except Exception as e:  # noqa: BLE001
@@ -319,7 +329,7 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, data_id: int) -> Optional[Dict[str, Any]]:
         rec = self.samples[data_id % len(self.samples)]
-        frames = self._load_video(rec["path"])
+        frames = self._load_video(rec["path"], only_used=True)
         keys = self.extract_middle_key_frames(frames)
         stitched = self.stitch_middle_key_frames(keys)
         if not frames:

@@ -360,3 +360,13 @@ def test_open_video_falls_back_and_reports(tmp_path, monkeypatch):
     ds.num_frames, ds.time_division_factor, ds.time_division_remainder = 81, 4, 1
     with pytest.warns(UserWarning, match="cannot open video"):
         assert ds._load_video(str(tmp_path / "missing.mp4")) == []
+
+
+def test_only_the_frames_a_sample_uses_are_resized(clip_tree):
+    ds = D.PhysicalEditingDataset(root_dir=str(clip_tree), num_frames=49, height=48, width=80)
+    path = ds.samples[1]["path"]
+    full, lazy = ds._load_video(path), ds._load_video(path, only_used=True)
+    assert len(full) == len(lazy) == 49 and all(f is not None for f in full)
+    used = [i for i, f in enumerate(lazy) if f is not None]
+    assert used == [0, 5, 13, 21, 29, 37, 45, 48]                    # first, the six run centres of frames 1..47, last
+    assert all(np.array_equal(np.asarray(lazy[i]), np.asarray(full[i])) for i in used)
