@@ -368,5 +368,5 @@ def test_only_the_frames_a_sample_uses_are_resized(clip_tree):
     full, lazy = ds._load_video(path), ds._load_video(path, only_used=True)
     assert len(full) == len(lazy) == 49 and all(f is not None for f in full)
     used = [i for i, f in enumerate(lazy) if f is not None]
-    assert used == [0, 5, 13, 21, 29, 37, 45, 48]                    # first, the six run centres of frames 1..47, last
+    assert used == [0, 5, 13, 21, 29, 37, 44, 48]                    # first, the six run centres of frames 1..47 (the last run has 7 frames), last
     assert all(np.array_equal(np.asarray(lazy[i]), np.asarray(full[i])) for i in used)
