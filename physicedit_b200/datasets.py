@@ -49,6 +49,9 @@ class _ImageioFrames:
     def frame(self, i):
         return self.reader.get_data(i)
 
+    def skip(self, i) -> bool:
+        return True                                # random access: nothing to do for a frame nobody asks for
+
     def close(self):
         self.reader.close()
 
@@ -80,7 +83,15 @@ class _OpenCVFrames:
         if not ok:
             raise IndexError(f"no frame {i}")
         self.next = i + 1
-        return bgr[:, :, ::-1].copy()              # RGB, like imageio
+        return self.cv2.cvtColor(bgr, self.cv2.COLOR_BGR2RGB)      # RGB, like imageio
+
+    def skip(self, i) -> bool:
+        """Advance past frame i without converting / copying it; False when the stream ends there."""
+        if i != self.next:
+            self.cap.set(self.cv2.CAP_PROP_POS_FRAMES, i)
+        ok = self.cap.grab()
+        self.next = i + 1
+        return bool(ok)
 
     def close(self):
         self.cap.release()
@@ -296,22 +307,27 @@ class PhysicalEditingDataset(torch.utils.data.Dataset):
         except Exception as e:  # noqa: BLE001
             warnings.warn(f"cannot open video {file_path}: {e}")
             return []
-        raw = []
         try:
-            for i in range(self._get_num_frames(source)):
-                try:
-                    raw.append(source.frame(i))
-                except Exception:  # noqa: BLE001  (a clip shorter than its header says: keep what was read)
-                    break
-            n = len(raw)
+            n = self._get_num_frames(source)
             used = set(range(n)) if not only_used else {0, n - 1} | set(middle_key_frames(list(range(n)), self.key_frame_stride))
             frames: List[Optional[Image.Image]] = []
-            for i, data in enumerate(raw):
-                if i not in used:
-                    frames.append(None)
-                    continue
+            for i in range(n):
+                try:
+                    if i not in used:
+                        if not source.skip(i):
+                            raise IndexError(f"no frame {i}")
+                        frames.append(None)
+                        continue
+                    data = source.frame(i)
+                except Exception:  # noqa: BLE001  (a clip shorter than its header says: keep what was read)
+                    break
                 img = Image.fromarray(data).convert("RGB")
                 frames.append(cover_and_center_crop(img, *self._get_height_width(img)))
+            if only_used and len(frames) < n:               # the clip ended early: which frames a sample uses depends on the real length
+                full = self._load_video(file_path)
+                m = len(full)
+                keep = {0, m - 1} | set(middle_key_frames(list(range(m)), self.key_frame_stride))
+                return [f if i in keep else None for i, f in enumerate(full)]
         except Exception as e:  # noqa: BLE001
             warnings.warn(f"error reading video {file_path}: {e}")
             frames = []

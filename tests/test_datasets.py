@@ -370,3 +370,25 @@ def test_only_the_frames_a_sample_uses_are_resized(clip_tree):
     used = [i for i, f in enumerate(lazy) if f is not None]
     assert used == [0, 5, 13, 21, 29, 37, 44, 48]                    # first, the six run centres of frames 1..47 (the last run has 7 frames), last
     assert all(np.array_equal(np.asarray(lazy[i]), np.asarray(full[i])) for i in used)
+
+
+def test_a_clip_shorter_than_its_header_says(monkeypatch):
+    """The header promises 20 frames, the stream ends after 12: the sample is built from the 12 that exist (first, last = frame 11, key frames of 1..10),
+    exactly what resizing everything and picking afterwards gives."""
+    class Truncated:
+        def __init__(self, path): self.closed = False
+        def count(self): return 20
+        def frame(self, i):
+            if i >= 12: raise IndexError(i)
+            return np.full((32, 48, 3), i * 10, np.uint8)
+        def skip(self, i): return i < 12
+        def close(self): self.closed = True
+    monkeypatch.setattr(D, "open_video", Truncated)
+    ds = D.PhysicalEditingDataset.__new__(D.PhysicalEditingDataset)
+    ds.num_frames, ds.time_division_factor, ds.time_division_remainder, ds.key_frame_stride = 81, 4, 1, 4
+    ds.dynamic_resolution, ds.height, ds.width = False, 32, 48
+    full, lazy = ds._load_video("x.mp4"), ds._load_video("x.mp4", only_used=True)
+    assert len(full) == len(lazy) == 12                                  # 20 -> 17 by the frame-count rule, 12 readable
+    used = [i for i, f in enumerate(lazy) if f is not None]
+    assert used == [0, 3, 7, 10, 11] and all(lazy[i].getpixel((0, 0)) == full[i].getpixel((0, 0)) == (i * 10,) * 3 for i in used)
+    assert [f.getpixel((0, 0))[0] for f in ds.extract_middle_key_frames(lazy)] == [30, 70, 100]
